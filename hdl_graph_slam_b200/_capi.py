@@ -1,0 +1,106 @@
+"""ctypes binding of libb200reg.so (include/b200reg.h).  Loading fails loudly: there is no Python/CPU fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libb200reg.so")
+
+B2R_OK = 0
+B2R_EINVAL, B2R_ENODEVICE, B2R_ECUDA, B2R_ESTATE, B2R_EUNSUPPORTED, B2R_ENCCL = -1, -2, -3, -4, -5, -6
+B2R_METHOD_GICP, B2R_METHOD_NDT = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("method", C.c_int32), ("device_id", C.c_int32), ("max_iterations", C.c_int32), ("k_correspondences", C.c_int32),
+        ("transformation_epsilon", C.c_double), ("rotation_epsilon", C.c_double), ("max_correspondence_distance", C.c_double),
+        ("ndt_resolution", C.c_double), ("ndt_step_size", C.c_double), ("ndt_outlier_ratio", C.c_double),
+        ("ndt_search_method", C.c_int32), ("ndt_mt_interval_flag", C.c_int32), ("ndt_fixed_iterations", C.c_int32),
+        ("grid_cell_min", C.c_float),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32), ("iterations", C.c_int32)]
+
+
+class OdometryParams(C.Structure):
+    _fields_ = [
+        ("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double),
+        ("transform_thresholding", C.c_int32), ("max_acceptable_trans", C.c_double), ("max_acceptable_angle", C.c_double),
+        ("publish_status", C.c_int32),
+    ]
+
+
+class OdometryStatus(C.Structure):
+    _fields_ = [
+        ("odom", C.c_float * 16), ("trans", C.c_float * 16), ("converged", C.c_int32), ("iterations", C.c_int32),
+        ("keyframe_updated", C.c_int32), ("frame_rejected", C.c_int32), ("matching_error", C.c_double),
+        ("inlier_fraction", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+# every symbol include/b200reg.h declares: (name, restype, argtypes)
+_VP, _SZ, _I32P, _F32P, _F64P = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
+SYMBOLS = [
+    ("b2r_last_error", C.c_char_p, []),
+    ("b2r_version", C.c_char_p, []),
+    ("b2r_config_default", C.c_int, [C.POINTER(Config), C.c_int]),
+    ("b2r_select_registration_method", C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.POINTER(_VP)]),
+    ("b2r_create", C.c_int, [C.POINTER(Config), C.POINTER(_VP)]),
+    ("b2r_destroy", None, [_VP]),
+    ("b2r_get_config", C.c_int, [_VP, C.POINTER(Config)]),
+    ("b2r_set_target", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_set_source", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_set_target_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_set_source_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_promote_source_to_target", C.c_int, [_VP]),
+    ("b2r_align", C.c_int, [_VP, _F32P, C.POINTER(Result)]),
+    ("b2r_get_aligned", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_fitness", C.c_int, [_VP, _F32P, C.c_double, C.c_float, _F64P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("b2r_target_nearest", C.c_int, [_VP, _VP, _SZ, _SZ, _I32P, _F32P]),
+    ("b2r_get_correspondences", C.c_int, [_VP, _I32P, _SZ]),
+    ("b2r_get_covariances", C.c_int, [_VP, C.c_int, _F64P, _SZ]),
+    ("b2r_gicp_linearize_at", C.c_int, [_VP, _F64P, _F64P, _F64P, _F64P]),
+    ("b2r_gicp_error_at", C.c_int, [_VP, _F64P, _F64P]),
+    ("b2r_ndt_get_voxels", C.c_int, [_VP, _SZ, C.POINTER(_SZ), C.POINTER(C.c_int64), _I32P, _F64P, _F64P, _I32P, _I32P]),
+    ("b2r_ndt_derivatives_at", C.c_int, [_VP, _F64P, _F64P, _F64P, _F64P, C.POINTER(C.c_uint64)]),
+    ("b2r_voxelgrid", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_float, _VP, C.POINTER(_SZ), _I32P, _I32P]),
+    ("b2r_odometry_create", C.c_int, [_VP, C.POINTER(OdometryParams), C.POINTER(_VP)]),
+    ("b2r_odometry_destroy", None, [_VP]),
+    ("b2r_odometry_matching", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),
+    ("b2r_loop_matching", C.c_int, [_VP, _VP, _SZ, _SZ, C.POINTER(_VP), C.POINTER(_SZ), _SZ, _F32P, C.c_double, C.c_double,
+                                    C.POINTER(Result), _I32P]),
+]
+
+_lib = None
+
+
+def load():
+    """Load libb200reg.so.  Raises (never falls back) if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m hdl_graph_slam_b200.build` (or __graft_entry__.build()). "
+            "hdl_graph_slam_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class B2RError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200reg error {code}: {msg}")
+        self.code = code
+
+
+def check(rc):
+    if rc < 0:
+        raise B2RError(rc, load().b2r_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,847 @@
+// api.cu — C ABI of libb200reg.so (see include/b200reg.h) and the host-side drivers above the kernels.
+//
+// Host mirrors of the reference interface for this path (same names / argument meaning / failure behaviour):
+//   b2r_select_registration_method  <- select_registration_method            src/hdl_graph_slam/registrations.cpp:22-124
+//   b2r_set_target / b2r_set_source <- pcl::Registration::setInputTarget/Source   (call sites in b200reg.h)
+//   b2r_align                       <- pcl::Registration::align -> computeTransformation (fast_gicp LsqRegistration LM loop,
+//                                      ndt_omp Newton + More-Thuente loop)
+//   b2r_fitness                     <- getFitnessScore
+//   b2r_odometry_matching           <- ScanMatchingOdometryNodelet::matching  apps/scan_matching_odometry_nodelet.cpp:165-262
+//   b2r_loop_matching               <- LoopDetector::matching                include/hdl_graph_slam/loop_detector.hpp:117-171
+// There is deliberately NO CPU fallback in this file: every compute step is a CUDA kernel launch.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cfloat>
+#include <cstdlib>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "engine.cuh"
+#include "gicp.cuh"
+#include "fitness.cuh"
+#include "ndt.cuh"
+#include "voxelgrid.cuh"
+
+namespace b2r {
+thread_local std::string g_last_error;
+}
+using namespace b2r;
+
+struct b2r_handle {
+  b2r_config cfg;
+  cudaStream_t st = nullptr;
+  Cloud clouds[2];
+  int src = 0, tgt = 1;
+  Scratch scr;
+  // per-align workspaces (sized by the source)
+  DevBuf<int> corr, cpos;
+  DevBuf<float> d2;
+  DevBuf<double> mahal, partials;
+  double* d_out = nullptr;          // 64 doubles
+  unsigned int* d_counter = nullptr;
+  double* h_out = nullptr;          // pinned, 64 doubles
+  // staging for pageable uploads
+  void* staging[2] = {nullptr, nullptr};
+  size_t staging_cap[2] = {0, 0};
+  cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+  // misc device scratch (queries / outputs)
+  DevBuf<float> tmp_f;
+  DevBuf<int> tmp_i;
+  DevBuf<float4> tmp_f4;
+  // last result
+  float final_T[16];                // row-major
+  bool has_final = false;
+  bool corr_valid = false;
+  NdtWork ndt_work;
+  VoxelWork vg_work;
+};
+
+static Cloud& SRC(b2r_handle* h) { return h->clouds[h->src]; }
+static Cloud& TGT(b2r_handle* h) { return h->clouds[h->tgt]; }
+
+extern "C" const char* b2r_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* b2r_version(void) { return "b200reg 0.1 (sm_100a)"; }
+
+extern "C" int b2r_config_default(b2r_config* c, int method) {
+  if (!c) return fail(B2R_EINVAL, "cfg is NULL");
+  std::memset(c, 0, sizeof(*c));
+  c->method = method;
+  c->device_id = 0;
+  c->max_iterations = 64;             // registrations.cpp:32,110
+  c->k_correspondences = 20;          // :34
+  c->transformation_epsilon = 0.01;   // :31,109
+  c->rotation_epsilon = 2e-3;         // fast_gicp default
+  c->max_correspondence_distance = 2.5;  // :33
+  c->ndt_resolution = 0.5;            // :93
+  c->ndt_step_size = 0.1;             // ndt_omp default (never overridden by the factory)
+  c->ndt_outlier_ratio = 0.55;
+  c->ndt_search_method = 7;           // :103 DIRECT7
+  c->ndt_mt_interval_flag = 0;
+  c->ndt_fixed_iterations = 0;
+  c->grid_cell_min = 0.5f;
+  if (method != B2R_METHOD_GICP && method != B2R_METHOD_NDT) return fail(B2R_EINVAL, "unknown method");
+  return B2R_OK;
+}
+
+static const char* find_param(const char* const* keys, const char* const* values, int n, const char* key) {
+  for (int i = 0; i < n; i++)
+    if (keys[i] && std::strcmp(keys[i], key) == 0) return values[i];
+  return nullptr;
+}
+
+extern "C" int b2r_select_registration_method(const char* const* keys, const char* const* values, int n, int device_id,
+                                              b2r_handle** out) {
+  if (!out) return fail(B2R_EINVAL, "out is NULL");
+  *out = nullptr;
+  const char* m = find_param(keys, values, n, "registration_method");
+  std::string method = m ? m : "NDT_OMP";  // registrations.cpp:26
+  auto dparam = [&](const char* k, double def) { const char* v = find_param(keys, values, n, k); return v ? std::atof(v) : def; };
+  auto iparam = [&](const char* k, int def) { const char* v = find_param(keys, values, n, k); return v ? std::atoi(v) : def; };
+  b2r_config c;
+  if (method == "FAST_GICP" || method == "B200_GICP") {
+    b2r_config_default(&c, B2R_METHOD_GICP);
+    c.transformation_epsilon = dparam("reg_transformation_epsilon", 0.01);
+    c.max_iterations = iparam("reg_maximum_iterations", 64);
+    c.max_correspondence_distance = dparam("reg_max_correspondence_distance", 2.5);
+    c.k_correspondences = iparam("reg_correspondence_randomness", 20);
+  } else if (method == "NDT_OMP" || method == "B200_NDT") {
+    b2r_config_default(&c, B2R_METHOD_NDT);
+    c.ndt_resolution = dparam("reg_resolution", 0.5);
+    c.transformation_epsilon = dparam("reg_transformation_epsilon", 0.01);
+    c.max_iterations = iparam("reg_maximum_iterations", 64);
+    const char* s = find_param(keys, values, n, "reg_nn_search_method");
+    std::string sm = s ? s : "DIRECT7";
+    if (sm == "KDTREE") return fail(B2R_EUNSUPPORTED, "reg_nn_search_method=KDTREE is not re-created (DIRECT1/DIRECT7 only)");
+    c.ndt_search_method = (sm == "DIRECT1") ? 1 : 7;  // registrations.cpp:112-118: anything else -> DIRECT7
+  } else {
+    return fail(B2R_EUNSUPPORTED, "registration_method '" + method + "' is not re-created by b200reg; keep the reference branch");
+  }
+  c.device_id = device_id;
+  return b2r_create(&c, out);
+}
+
+static int alloc_cloud(Cloud& c) {
+  B2R_CUDA(cudaMalloc(&c.grid, sizeof(Grid)));
+  B2R_CUDA(c.cell_start.reserve(kCellCap + 1 - 72));  // reserve() pads by n/8+64; exact size is irrelevant, >= kCellCap+1
+  return B2R_OK;
+}
+
+extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
+  if (!cfg || !out) return fail(B2R_EINVAL, "NULL argument");
+  *out = nullptr;
+  if (cfg->method != B2R_METHOD_GICP && cfg->method != B2R_METHOD_NDT) return fail(B2R_EINVAL, "unknown method");
+  if (cfg->k_correspondences < 1 || cfg->k_correspondences > 64) return fail(B2R_EINVAL, "k_correspondences must be in [1,64]");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) return fail(B2R_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (cfg->device_id < 0 || cfg->device_id >= ndev) return fail(B2R_EINVAL, "device_id out of range");
+  B2R_CUDA(cudaSetDevice(cfg->device_id));
+  b2r_handle* h = new b2r_handle();
+  h->cfg = *cfg;
+  if (!(h->cfg.grid_cell_min > 0.f)) h->cfg.grid_cell_min = 0.5f;
+  {  // round the cell size to a power of two
+    int ex;
+    float m = std::frexp(h->cfg.grid_cell_min, &ex);
+    h->cfg.grid_cell_min = std::ldexp(1.0f, m > 0.5f ? ex : ex - 1);
+  }
+  auto bail = [&](int code) { b2r_destroy(h); return code; };
+  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
+  for (int i = 0; i < 2; i++) {
+    int rc = alloc_cloud(h->clouds[i]);
+    if (rc) return bail(rc);
+    if (cudaEventCreateWithFlags(&h->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
+  }
+  if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scr.counts, (size_t)kCellCap * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&h->scr.cursor, (size_t)kCellCap * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scr.bsum, (size_t)kScanBlocks * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess ||
+      cudaMallocHost(&h->h_out, 64 * sizeof(double)) != cudaSuccess)
+    return bail(fail(B2R_ECUDA, "device allocation failed"));
+  cudaMemsetAsync(h->scr.counts, 0, (size_t)kCellCap * sizeof(int), h->st);
+  cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
+  if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
+  for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  *out = h;
+  return B2R_OK;
+}
+
+extern "C" void b2r_destroy(b2r_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device_id);
+  if (h->st) cudaStreamSynchronize(h->st);
+  for (int i = 0; i < 2; i++) {
+    Cloud& c = h->clouds[i];
+    c.raw.release(); c.cell_start.release(); c.sorted.release(); c.pos_of.release(); c.cov.release();
+    if (c.grid) cudaFree(c.grid);
+    ndt_free_map(c.ndt);
+    if (h->staging[i]) cudaFreeHost(h->staging[i]);
+    if (h->staging_ev[i]) cudaEventDestroy(h->staging_ev[i]);
+  }
+  if (h->scr.mm) cudaFree(h->scr.mm);
+  if (h->scr.counts) cudaFree(h->scr.counts);
+  if (h->scr.cursor) cudaFree(h->scr.cursor);
+  if (h->scr.bsum) cudaFree(h->scr.bsum);
+  h->scr.cell_of.release(); h->scr.tmp_idx.release();
+  h->corr.release(); h->cpos.release(); h->d2.release(); h->mahal.release(); h->partials.release();
+  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release();
+  h->ndt_work.release();
+  h->vg_work.release();
+  if (h->d_out) cudaFree(h->d_out);
+  if (h->d_counter) cudaFree(h->d_counter);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+}
+
+extern "C" int b2r_get_config(const b2r_handle* h, b2r_config* out) {
+  if (!h || !out) return fail(B2R_EINVAL, "NULL argument");
+  *out = h->cfg;
+  return B2R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ upload + preprocessing
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t stride_bytes, bool device_ptr) {
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "stride_bytes must be a multiple of 4 and >= 12");
+  if (n > 0 && !pts) return fail(B2R_EINVAL, "points is NULL");
+  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  Cloud& c = h->clouds[which];
+  c.n = n;
+  c.stride_f = (int)(stride_bytes / 4);
+  c.host_ptr = device_ptr ? nullptr : pts;
+  c.invalidate();
+  const size_t bytes = n * stride_bytes;
+  if (device_ptr) {
+    c.raw_view = (const float*)pts;
+  } else {
+    B2R_CUDA(c.raw.reserve(n * c.stride_f + 4));
+    c.raw_view = c.raw.p;
+    if (bytes > 0) {
+      if (is_pinned_host(pts)) {
+        B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyHostToDevice, h->st));
+      } else {
+        int sidx = which & 1;
+        if (h->staging_cap[sidx] < bytes) {
+          if (h->staging[sidx]) { cudaEventSynchronize(h->staging_ev[sidx]); cudaFreeHost(h->staging[sidx]); h->staging[sidx] = nullptr; }
+          size_t want = bytes + bytes / 4 + 4096;
+          B2R_CUDA(cudaMallocHost(&h->staging[sidx], want));
+          h->staging_cap[sidx] = want;
+        } else {
+          B2R_CUDA(cudaEventSynchronize(h->staging_ev[sidx]));
+        }
+        std::memcpy(h->staging[sidx], pts, bytes);
+        B2R_CUDA(cudaMemcpyAsync(c.raw.p, h->staging[sidx], bytes, cudaMemcpyHostToDevice, h->st));
+        B2R_CUDA(cudaEventRecord(h->staging_ev[sidx], h->st));
+      }
+    }
+  }
+  return B2R_OK;
+}
+
+static int ensure_grid(b2r_handle* h, Cloud& c) {
+  if (c.grid_ready) return B2R_OK;
+  const size_t n = c.n;
+  B2R_CUDA(c.sorted.reserve(n + 1));
+  B2R_CUDA(c.pos_of.reserve(n + 1));
+  B2R_CUDA(h->scr.cell_of.reserve(n + 1));
+  B2R_CUDA(h->scr.tmp_idx.reserve(n + 1));
+  GridBuffers B;
+  B.grid = c.grid; B.mm = h->scr.mm; B.counts = h->scr.counts; B.cell_start = c.cell_start.p; B.cursor = h->scr.cursor;
+  B.bsum = h->scr.bsum; B.cell_of = h->scr.cell_of.p; B.tmp_idx = h->scr.tmp_idx.p; B.sorted = c.sorted.p; B.pos_of = c.pos_of.p;
+  build_grid(c.raw_view, c.stride_f, (int)n, h->cfg.grid_cell_min, B, h->st);
+  B2R_CUDA(cudaGetLastError());
+  c.grid_ready = true;
+  return B2R_OK;
+}
+
+static int ensure_cov(b2r_handle* h, Cloud& c) {
+  int rc = ensure_grid(h, c);
+  if (rc) return rc;
+  if (c.cov_ready) return B2R_OK;
+  const size_t n = c.n;
+  B2R_CUDA(c.cov.reserve(n * 6 + 6));
+  if (n > 0) {
+    const int k = h->cfg.k_correspondences;
+    const size_t smem = (size_t)2 * k * kKnnThreads * sizeof(float);
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
+      B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 2 * kKnnThreads * 4));
+      attr_set = true;
+    }
+    k_knn_cov<<<(unsigned)((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, smem, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p);
+    B2R_CUDA(cudaGetLastError());
+  }
+  c.cov_ready = true;
+  return B2R_OK;
+}
+
+static int preprocess(b2r_handle* h, int which, bool is_target) {
+  Cloud& c = h->clouds[which];
+  if (h->cfg.method == B2R_METHOD_GICP) return ensure_cov(h, c);
+  // NDT: the target needs the voxel Gaussians; the source needs nothing beyond the upload
+  if (is_target) return ndt_ensure_map(h->cfg, c, h->ndt_work, h->st);
+  return B2R_OK;
+}
+
+static int set_cloud(b2r_handle* h, bool is_target, const void* pts, size_t n, size_t stride, bool dev) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  int which = is_target ? h->tgt : h->src;
+  int rc = upload(h, which, pts, n, stride, dev);
+  if (rc) return rc;
+  h->corr_valid = false;
+  return preprocess(h, which, is_target);
+}
+
+extern "C" int b2r_set_target(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, true, p, n, s, false); }
+extern "C" int b2r_set_source(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, false, p, n, s, false); }
+extern "C" int b2r_set_target_device(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, true, p, n, s, true); }
+extern "C" int b2r_set_source_device(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, false, p, n, s, true); }
+
+extern "C" int b2r_promote_source_to_target(b2r_handle* h) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  std::swap(h->src, h->tgt);
+  h->corr_valid = false;
+  // the old target becomes a stale source: callers always set a new source before the next align
+  return preprocess(h, h->tgt, true);
+}
+
+// ------------------------------------------------------------------------------------------------ GICP align (LM, A.4)
+static void colmajor_f_to_row_d(const float* g, double* x) {
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) x[r * 4 + c] = (double)g[c * 4 + r];
+}
+static void make_pose(const double* x, PoseArg& P) {
+  for (int i = 0; i < 12; i++) { P.T[i] = x[i]; P.Tf[i] = (float)x[i]; }
+}
+
+static int ensure_align_ws(b2r_handle* h, size_t n) {
+  B2R_CUDA(h->corr.reserve(n + 1));
+  B2R_CUDA(h->cpos.reserve(n + 1));
+  B2R_CUDA(h->d2.reserve(n + 1));
+  B2R_CUDA(h->mahal.reserve(n * 6 + 6));
+  size_t nb = (n + kLinThreads - 1) / kLinThreads + 1;
+  B2R_CUDA(h->partials.reserve(nb * kAcc));
+  return B2R_OK;
+}
+
+static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H, double* b, double* y) {
+  Cloud& s = SRC(h);
+  Cloud& t = TGT(h);
+  LinArgs A;
+  A.sgrid = s.grid; A.ssp = s.sorted.p; A.scov = s.cov.p;
+  A.tgrid = t.grid; A.tcell_start = t.cell_start.p; A.tsp = t.sorted.p; A.tcov = t.cov.p;
+  const double thr = h->cfg.max_correspondence_distance;
+  A.thr2 = thr * thr;
+  float lim = (float)A.thr2;
+  if ((double)lim < A.thr2) lim = std::nextafterf(lim, INFINITY);
+  A.lim = lim;
+  A.corr = h->corr.p; A.cpos = h->cpos.p; A.d2 = h->d2.p; A.mahal = h->mahal.p;
+  A.partials = h->partials.p; A.out = h->d_out; A.counter = h->d_counter;
+  A.use_seed = seed ? 1 : 0;
+  PoseArg P;
+  make_pose(x0, P);
+  const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
+  k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, kAcc * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  // unpack the upper triangle
+  int k = 0;
+  for (int r = 0; r < 6; r++)
+    for (int c = r; c < 6; c++) { H[r * 6 + c] = H[c * 6 + r] = h->h_out[k++]; }
+  for (int i = 0; i < 6; i++) b[i] = h->h_out[21 + i];
+  *y = h->h_out[27];
+  h->corr_valid = true;
+  return B2R_OK;
+}
+
+static int gicp_error(b2r_handle* h, const double* xi, double* y) {
+  Cloud& s = SRC(h);
+  Cloud& t = TGT(h);
+  ErrArgs A;
+  A.sgrid = s.grid; A.ssp = s.sorted.p; A.tsp = t.sorted.p; A.cpos = h->cpos.p; A.mahal = h->mahal.p;
+  A.partials = h->partials.p; A.out = h->d_out + 32; A.counter = h->d_counter + 1;
+  PoseArg P;
+  make_pose(xi, P);
+  const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
+  k_gicp_error<<<nb, kLinThreads, 0, h->st>>>(A, P);
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(h->h_out + 32, h->d_out + 32, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  *y = h->h_out[32];
+  return B2R_OK;
+}
+
+static void store_result(b2r_handle* h, const float* T_row, bool converged, int iterations, b2r_result* out) {
+  for (int i = 0; i < 16; i++) h->final_T[i] = T_row[i];
+  h->has_final = true;
+  if (out) {
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) out->T[c * 4 + r] = T_row[r * 4 + c];
+    out->fitness = NAN;
+    out->converged = converged ? 1 : 0;
+    out->iterations = iterations;
+  }
+}
+
+static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
+  Cloud& s = SRC(h);
+  Cloud& t = TGT(h);
+  double x0[16];
+  colmajor_f_to_row_d(guess, x0);
+  x0[12] = x0[13] = x0[14] = 0; x0[15] = 1;
+  float Tg[16];
+  for (int i = 0; i < 16; i++) Tg[i] = (float)x0[i];
+  if (s.n == 0 || t.n == 0) {  // pcl::Registration::initCompute fails silently: converged_ = false
+    store_result(h, Tg, false, 0, out);
+    return B2R_OK;
+  }
+  int rc = ensure_cov(h, s);
+  if (rc) return rc;
+  rc = ensure_cov(h, t);
+  if (rc) return rc;
+  rc = ensure_align_ws(h, s.n);
+  if (rc) return rc;
+  const b2r_config& cfg = h->cfg;
+  double lambda = -1.0;
+  bool converged = false;
+  int it = 0;
+  bool seed = false;
+  for (it = 0; it < cfg.max_iterations && !converged; it++) {
+    double H[36], b[6], y0, delta[16];
+    rc = gicp_linearize(h, x0, seed, H, b, &y0);
+    if (rc) return rc;
+    seed = true;
+    if (lambda < 0.0) {
+      double mx = 0;
+      for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 6 + i]));
+      lambda = 1e-9 * mx;
+    }
+    double nu = 2.0;
+    bool ok = false;
+    for (int li = 0; li < 10; li++) {
+      double A[36], nb[6], d[6];
+      for (int i = 0; i < 36; i++) A[i] = H[i] + ((i % 7 == 0) ? lambda : 0.0);
+      for (int i = 0; i < 6; i++) nb[i] = -b[i];
+      if (!ldlt6_solve(A, nb, d))
+        for (int i = 0; i < 6; i++) d[i] = NAN;
+      se3_exp(d, delta);
+      double xi[16], yi;
+      mul_iso(delta, x0, xi);
+      rc = gicp_error(h, xi, &yi);
+      if (rc) return rc;
+      double den = 0;
+      for (int i = 0; i < 6; i++) den += d[i] * (lambda * d[i] - b[i]);
+      double rho = (y0 - yi) / den;
+      if (rho < 0) {
+        if (gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon)) { ok = true; break; }
+        lambda = nu * lambda;
+        nu = 2 * nu;
+        continue;
+      }
+      double tt = 2 * rho - 1;
+      lambda = lambda * std::max(1.0 / 3.0, 1 - tt * tt * tt);
+      std::memcpy(x0, xi, sizeof(xi));
+      ok = true;
+      break;
+    }
+    if (!ok) { it++; break; }  // "lm not converged!!"
+    converged = gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon);
+  }
+  float Tf[16];
+  for (int i = 0; i < 16; i++) Tf[i] = (float)x0[i];
+  store_result(h, Tf, converged, it, out);
+  return B2R_OK;
+}
+
+extern "C" int b2r_align(b2r_handle* h, const float guess[16], b2r_result* out) {
+  if (!h || !guess) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  int rc;
+  if (h->cfg.method == B2R_METHOD_GICP) rc = gicp_align(h, guess, out);
+  else {
+    float Tfinal[16];
+    bool conv = false;
+    int iters = 0;
+    rc = ndt_align(h->cfg, SRC(h), TGT(h), h->ndt_work, h->st, guess, Tfinal, &conv, &iters);
+    if (rc == B2R_OK) store_result(h, Tfinal, conv, iters, out);
+  }
+  if (rc != B2R_OK && out) {
+    for (int i = 0; i < 16; i++) out->T[i] = guess[i];
+    out->fitness = NAN; out->converged = 0; out->iterations = 0;
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ outputs
+extern "C" int b2r_get_aligned(b2r_handle* h, void* out_points, size_t n, size_t stride_bytes) {
+  if (!h || (!out_points && n)) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  Cloud& s = SRC(h);
+  if (n != s.n) return fail(B2R_EINVAL, "n does not match the source cloud");
+  if (n == 0) return B2R_OK;
+  B2R_CUDA(h->tmp_f4.reserve(n));
+  XfArg X;
+  for (int i = 0; i < 12; i++) X.Tf[i] = h->final_T[i];
+  k_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(s.raw_view, s.stride_f, (int)n, X, h->tmp_f4.p);
+  B2R_CUDA(cudaGetLastError());
+  std::vector<float4> host(n);
+  B2R_CUDA(cudaMemcpyAsync(host.data(), h->tmp_f4.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  char* o = (char*)out_points;
+  for (size_t i = 0; i < n; i++) {
+    float* p = (float*)(o + i * stride_bytes);
+    p[0] = host[i].x; p[1] = host[i].y; p[2] = host[i].z;
+    if (stride_bytes >= 16) p[3] = 1.0f;
+  }
+  return B2R_OK;
+}
+
+static int fitness_impl(b2r_handle* h, const float* T_row, double max_range, float inl, double* score, uint32_t* n_used, uint32_t* n_inl) {
+  Cloud& s = SRC(h);
+  Cloud& t = TGT(h);
+  if (s.n == 0 || t.n == 0) {
+    if (score) *score = DBL_MAX;
+    if (n_used) *n_used = 0;
+    if (n_inl) *n_inl = 0;
+    return B2R_OK;
+  }
+  int rc = ensure_grid(h, t);
+  if (rc) return rc;
+  size_t nb = (s.n + kLinThreads - 1) / kLinThreads;
+  B2R_CUDA(h->partials.reserve(nb * kAcc + kAcc));
+  FitArgs A;
+  A.src_raw = s.raw_view; A.src_stride_f = s.stride_f; A.n = (int)s.n;
+  A.tgrid = t.grid; A.tcell_start = t.cell_start.p; A.tsp = t.sorted.p;
+  for (int i = 0; i < 12; i++) A.Tf[i] = T_row[i];
+  A.max_range = max_range; A.inlier_thresh_sq = inl;
+  A.partials = h->partials.p; A.out = h->d_out + 40; A.counter = h->d_counter + 2;
+  k_fitness<<<(unsigned)nb, kLinThreads, 0, h->st>>>(A);
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(h->h_out + 40, h->d_out + 40, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  double sum = h->h_out[40], nr = h->h_out[41], ni = h->h_out[42];
+  if (score) *score = nr > 0 ? sum / nr : DBL_MAX;
+  if (n_used) *n_used = (uint32_t)nr;
+  if (n_inl) *n_inl = (uint32_t)ni;
+  return B2R_OK;
+}
+
+extern "C" int b2r_fitness(b2r_handle* h, const float* T, double max_range, float inlier_thresh_sq, double* score, uint32_t* n_used,
+                           uint32_t* n_inliers) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  float Tr[16];
+  if (T) {
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) Tr[r * 4 + c] = T[c * 4 + r];
+  } else {
+    std::memcpy(Tr, h->final_T, sizeof(Tr));
+  }
+  return fitness_impl(h, Tr, max_range, inlier_thresh_sq, score, n_used, n_inliers);
+}
+
+extern "C" int b2r_target_nearest(b2r_handle* h, const void* queries, size_t n, size_t stride_bytes, int32_t* idx_out, float* d2_out) {
+  if (!h || (n && (!queries || !idx_out || !d2_out))) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  Cloud& t = TGT(h);
+  if (n == 0) return B2R_OK;
+  int rc = ensure_grid(h, t);
+  if (rc) return rc;
+  const int sf = (int)(stride_bytes / 4);
+  B2R_CUDA(h->tmp_f.reserve(n * sf + n));
+  B2R_CUDA(h->tmp_i.reserve(n));
+  B2R_CUDA(cudaMemcpyAsync(h->tmp_f.p, queries, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
+  float* d2d = h->tmp_f.p + n * sf;
+  k_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, sf, (int)n, t.grid, t.cell_start.p, t.sorted.p, h->tmp_i.p, d2d);
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(idx_out, h->tmp_i.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaMemcpyAsync(d2_out, d2d, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  return B2R_OK;
+}
+
+extern "C" int b2r_get_correspondences(b2r_handle* h, int32_t* out, size_t n) {
+  if (!h || !out) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  if (!h->corr_valid) return fail(B2R_ESTATE, "no linearisation has run since the clouds were set");
+  if (n != SRC(h).n) return fail(B2R_EINVAL, "n does not match the source cloud");
+  B2R_CUDA(cudaMemcpyAsync(out, h->corr.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  return B2R_OK;
+}
+
+extern "C" int b2r_get_covariances(b2r_handle* h, int which, double* out, size_t n) {
+  if (!h || !out) return fail(B2R_EINVAL, "NULL argument");
+  if (h->cfg.method != B2R_METHOD_GICP) return fail(B2R_ESTATE, "covariances exist only for the GICP engine");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  Cloud& c = which ? TGT(h) : SRC(h);
+  if (n != c.n) return fail(B2R_EINVAL, "n does not match the cloud");
+  int rc = ensure_cov(h, c);
+  if (rc) return rc;
+  std::vector<double> cov(n * 6);
+  std::vector<int> pos(n);
+  B2R_CUDA(cudaMemcpyAsync(cov.data(), c.cov.p, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaMemcpyAsync(pos.data(), c.pos_of.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  for (size_t i = 0; i < n; i++) {
+    double* o = out + i * 9;
+    if (pos[i] < 0) { for (int k = 0; k < 9; k++) o[k] = NAN; continue; }
+    const double* s = &cov[(size_t)pos[i] * 6];
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+  }
+  return B2R_OK;
+}
+
+extern "C" int b2r_gicp_linearize_at(b2r_handle* h, const double T[16], double* H, double* b, double* err) {
+  if (!h || !T || !H || !b || !err) return fail(B2R_EINVAL, "NULL argument");
+  if (h->cfg.method != B2R_METHOD_GICP) return fail(B2R_ESTATE, "GICP engine required");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  Cloud& s = SRC(h);
+  Cloud& t = TGT(h);
+  if (s.n == 0 || t.n == 0) return fail(B2R_ESTATE, "source/target not set");
+  int rc = ensure_cov(h, s);
+  if (!rc) rc = ensure_cov(h, t);
+  if (!rc) rc = ensure_align_ws(h, s.n);
+  if (rc) return rc;
+  double x[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) x[r * 4 + c] = T[c * 4 + r];
+  return gicp_linearize(h, x, false, H, b, err);
+}
+
+extern "C" int b2r_gicp_error_at(b2r_handle* h, const double T[16], double* err) {
+  if (!h || !T || !err) return fail(B2R_EINVAL, "NULL argument");
+  if (!h->corr_valid) return fail(B2R_ESTATE, "no linearisation has run");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  double x[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) x[r * 4 + c] = T[c * 4 + r];
+  return gicp_error(h, x, err);
+}
+
+extern "C" int b2r_ndt_get_voxels(b2r_handle* h, size_t capacity, size_t* n_voxels, int64_t* keys, int32_t* npts, double* mean,
+                                  double* icov, int32_t min_b[3], int32_t div_b[3]) {
+  if (!h || !n_voxels) return fail(B2R_EINVAL, "NULL argument");
+  if (h->cfg.method != B2R_METHOD_NDT) return fail(B2R_ESTATE, "NDT engine required");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  int rc = ndt_ensure_map(h->cfg, TGT(h), h->ndt_work, h->st);
+  if (rc) return rc;
+  return ndt_dump(TGT(h), h->st, capacity, n_voxels, keys, npts, mean, icov, min_b, div_b);
+}
+
+extern "C" int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* score, double* g, double* H, uint64_t* n_pairs) {
+  if (!h || !p || !score || !g || !H) return fail(B2R_EINVAL, "NULL argument");
+  if (h->cfg.method != B2R_METHOD_NDT) return fail(B2R_ESTATE, "NDT engine required");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  if (SRC(h).n == 0 || TGT(h).n == 0) return fail(B2R_ESTATE, "source/target not set");
+  int rc = ndt_ensure_map(h->cfg, TGT(h), h->ndt_work, h->st);
+  if (rc) return rc;
+  return ndt_derivatives_at(h->cfg, SRC(h), TGT(h), h->ndt_work, h->st, p, score, g, H, n_pairs);
+}
+
+extern "C" int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out, size_t* n_out,
+                             int32_t* out_keys, int32_t* out_counts) {
+  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  if (!(leaf > 0.f)) return fail(B2R_EINVAL, "leaf must be positive");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  return voxelgrid_filter(h->vg_work, h->st, in, n, stride_bytes, leaf, out, n_out, out_keys, out_counts);
+}
+
+// ------------------------------------------------------------------------------------------------ odometry mirror
+struct b2r_odometry {
+  b2r_handle* reg;
+  b2r_odometry_params p;
+  bool has_keyframe = false;
+  double prev_time = 0, keyframe_stamp = 0;
+  bool prev_time_zero = true;
+  float prev_trans[16];     // row-major
+  float keyframe_pose[16];  // row-major
+};
+
+static void mat4_identity(float* m) { for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.f : 0.f; }
+static void mat4_mul(const float* a, const float* b, float* o) {
+  float t[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) {
+      float s = a[r * 4 + 0] * b[0 * 4 + c];
+      s += a[r * 4 + 1] * b[1 * 4 + c];
+      s += a[r * 4 + 2] * b[2 * 4 + c];
+      s += a[r * 4 + 3] * b[3 * 4 + c];
+      t[r * 4 + c] = s;
+    }
+  std::memcpy(o, t, sizeof(t));
+}
+static void mat4_inv_rigid_general(const float* m, float* o) {
+  // general affine inverse of [A t; 0 1] with A 3x3 (Eigen Matrix4f::inverse() on a rigid transform)
+  double A[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]}, Ai[9];
+  inv3(A, Ai);
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) o[r * 4 + c] = (float)Ai[r * 3 + c];
+    o[r * 4 + 3] = (float)(-(Ai[r * 3 + 0] * m[3] + Ai[r * 3 + 1] * m[7] + Ai[r * 3 + 2] * m[11]));
+  }
+  o[12] = o[13] = o[14] = 0.f; o[15] = 1.f;
+}
+// w of Eigen::Quaternionf(R) (rotation matrix -> quaternion, Eigen's branchy algorithm)
+static float quat_w_from_R(const float* m) {
+  float t = m[0] + m[5] + m[10];
+  if (t > 0.f) {
+    t = std::sqrt(t + 1.0f);
+    return 0.5f * t;
+  }
+  int i = 0;
+  if (m[5] > m[0]) i = 1;
+  if (m[10] > m[i * 4 + i]) i = 2;
+  int j = (i + 1) % 3, k = (j + 1) % 3;
+  t = std::sqrt(m[i * 4 + i] - m[j * 4 + j] - m[k * 4 + k] + 1.0f);
+  t = 0.5f / t;
+  return (m[k * 4 + j] - m[j * 4 + k]) * t;
+}
+static void row_to_col(const float* r, float* c) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) c[j * 4 + i] = r[i * 4 + j];
+}
+
+extern "C" int b2r_odometry_create(b2r_handle* reg, const b2r_odometry_params* p, b2r_odometry** out) {
+  if (!reg || !out) return fail(B2R_EINVAL, "NULL argument");
+  b2r_odometry* o = new b2r_odometry();
+  o->reg = reg;
+  if (p) o->p = *p;
+  else {
+    o->p.keyframe_delta_trans = 0.25; o->p.keyframe_delta_angle = 0.15; o->p.keyframe_delta_time = 1.0;
+    o->p.transform_thresholding = 0; o->p.max_acceptable_trans = 1.0; o->p.max_acceptable_angle = 1.0; o->p.publish_status = 0;
+  }
+  mat4_identity(o->prev_trans);
+  mat4_identity(o->keyframe_pose);
+  *out = o;
+  return B2R_OK;
+}
+extern "C" void b2r_odometry_destroy(b2r_odometry* o) { delete o; }
+
+extern "C" int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes,
+                                     const float* msf_delta, b2r_odometry_status* out) {
+  if (!o || !out) return fail(B2R_EINVAL, "NULL argument");
+  std::memset(out, 0, sizeof(*out));
+  out->matching_error = NAN;
+  out->inlier_fraction = NAN;
+  b2r_handle* reg = o->reg;
+  float I[16];
+  mat4_identity(I);
+  if (!o->has_keyframe) {  // :166-174
+    o->prev_time_zero = true;
+    mat4_identity(o->prev_trans);
+    mat4_identity(o->keyframe_pose);
+    o->keyframe_stamp = stamp;
+    int rc = b2r_set_target(reg, cloud, n, stride_bytes);
+    if (rc) return rc;
+    o->has_keyframe = true;
+    row_to_col(I, out->odom);
+    row_to_col(I, out->trans);
+    out->keyframe_updated = 1;
+    return B2R_OK;
+  }
+  int rc = b2r_set_source(reg, cloud, n, stride_bytes);  // :177
+  if (rc) return rc;
+  float guess_row[16], delta_row[16];
+  if (msf_delta) { for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) delta_row[r * 4 + c] = msf_delta[c * 4 + r]; }
+  else mat4_identity(delta_row);
+  mat4_mul(o->prev_trans, delta_row, guess_row);  // :210 prev_trans * msf_delta.matrix()
+  float guess_col[16];
+  row_to_col(guess_row, guess_col);
+  b2r_result res;
+  rc = b2r_align(reg, guess_col, &res);
+  if (rc) return rc;
+  out->converged = res.converged;
+  out->iterations = res.iterations;
+  std::memcpy(out->trans, res.T, sizeof(res.T));
+  if (o->p.publish_status) {  // :298-335
+    double score;
+    uint32_t used, inl;
+    rc = b2r_fitness(reg, nullptr, DBL_MAX, 0.5f * 0.5f, &score, &used, &inl);
+    if (rc) return rc;
+    out->matching_error = score;
+    out->inlier_fraction = n ? (float)inl / (float)n : 0.f;
+  }
+  float odom_row[16];
+  if (!res.converged) {  // :214-218
+    mat4_mul(o->keyframe_pose, o->prev_trans, odom_row);
+    row_to_col(odom_row, out->odom);
+    out->frame_rejected = 1;
+    return B2R_OK;
+  }
+  float trans[16];
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) trans[r * 4 + c] = res.T[c * 4 + r];
+  mat4_mul(o->keyframe_pose, trans, odom_row);
+  if (o->p.transform_thresholding) {  // :223-233
+    float inv[16], delta[16];
+    mat4_inv_rigid_general(o->prev_trans, inv);
+    mat4_mul(inv, trans, delta);
+    double dx = std::sqrt((double)delta[3] * delta[3] + (double)delta[7] * delta[7] + (double)delta[11] * delta[11]);
+    double da = std::acos((double)quat_w_from_R(delta));
+    if (dx > o->p.max_acceptable_trans || da > o->p.max_acceptable_angle) {
+      mat4_mul(o->keyframe_pose, o->prev_trans, odom_row);
+      row_to_col(odom_row, out->odom);
+      out->frame_rejected = 1;
+      return B2R_OK;
+    }
+  }
+  o->prev_time = stamp;
+  o->prev_time_zero = false;
+  std::memcpy(o->prev_trans, trans, sizeof(trans));
+  float tn = std::sqrt(trans[3] * trans[3] + trans[7] * trans[7] + trans[11] * trans[11]);
+  double delta_trans = tn;
+  double delta_angle = std::acos((double)quat_w_from_R(trans));
+  double delta_time = stamp - o->keyframe_stamp;
+  if (delta_trans > o->p.keyframe_delta_trans || delta_angle > o->p.keyframe_delta_angle || delta_time > o->p.keyframe_delta_time) {  // :241-252
+    rc = b2r_promote_source_to_target(reg);  // keyframe = filtered; registration->setInputTarget(keyframe)
+    if (rc) return rc;
+    std::memcpy(o->keyframe_pose, odom_row, sizeof(odom_row));
+    o->keyframe_stamp = stamp;
+    o->prev_time = stamp;
+    mat4_identity(o->prev_trans);
+    out->keyframe_updated = 1;
+  }
+  row_to_col(odom_row, out->odom);
+  return B2R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ loop-closure mirror
+extern "C" int b2r_loop_matching(b2r_handle* h, const void* new_keyframe, size_t n_new, size_t stride_bytes, const void* const* candidates,
+                                 const size_t* n_candidates_pts, size_t n_candidates, const float* guesses, double fitness_score_max_range,
+                                 double fitness_score_thresh, b2r_result* results, int32_t* best) {
+  if (!h || !best) return fail(B2R_EINVAL, "NULL argument");
+  *best = -1;
+  if (n_candidates == 0) return B2R_OK;  // loop_detector.hpp:118-120
+  if (!candidates || !n_candidates_pts || !guesses) return fail(B2R_EINVAL, "NULL argument");
+  int rc = b2r_set_target(h, new_keyframe, n_new, stride_bytes);  // :122
+  if (rc) return rc;
+  double best_score = DBL_MAX;
+  int best_i = -1;
+  for (size_t i = 0; i < n_candidates; i++) {  // :135-154
+    rc = b2r_set_source(h, candidates[i], n_candidates_pts[i], stride_bytes);
+    if (rc) return rc;
+    b2r_result r;
+    rc = b2r_align(h, guesses + i * 16, &r);
+    if (rc) return rc;
+    double score;
+    rc = b2r_fitness(h, nullptr, fitness_score_max_range, 0.25f, &score, nullptr, nullptr);
+    if (rc) return rc;
+    r.fitness = score;
+    if (results) results[i] = r;
+    if (!r.converged || score > best_score) continue;  // :147
+    best_score = score;
+    best_i = (int)i;
+  }
+  if (best_score > fitness_score_thresh) best_i = -1;  // :160-163
+  *best = best_i;
+  return B2R_OK;
+}

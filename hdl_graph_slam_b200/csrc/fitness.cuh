@@ -1,0 +1,80 @@
+// fitness.cuh — nearest-neighbour fitness score, inlier count, exact 1-NN queries and the `aligned` output cloud.
+//
+// k_fitness      <- pcl::Registration::getFitnessScore(max_range) (called at apps/scan_matching_odometry_nodelet.cpp:307,
+//                   include/hdl_graph_slam/loop_detector.hpp:146; in-tree twin src/hdl_graph_slam/information_matrix_calculator.cpp:49-80)
+//                   fused with the inlier loop of apps/scan_matching_odometry_nodelet.cpp:309-320
+// k_nearest      <- getSearchMethodTarget()->nearestKSearch(pt, 1, ...) (apps/scan_matching_odometry_nodelet.cpp:316)
+// k_transform    <- the `aligned` cloud written by align() (pcl::transformPointCloud with final_transformation_)
+#pragma once
+#include "common.cuh"
+#include "nn_search.cuh"
+#include "gicp.cuh"
+
+namespace b2r {
+
+struct FitArgs {
+  const float* src_raw;
+  int src_stride_f;
+  int n;
+  const Grid* tgrid;
+  const int* tcell_start;
+  const float4* tsp;
+  float Tf[12];
+  double max_range;       // compared with the SQUARED distance (reference semantics)
+  float inlier_thresh_sq;
+  double* partials;       // [blocks][3]
+  double* out;            // [3] = sum d2, count, inliers
+  unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(kLinThreads) k_fitness(FitArgs A) {
+  __shared__ double red[3 * 32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[3] = {0.0, 0.0, 0.0};
+  if (i < A.n) {
+    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
+    const float x = p[0], y = p[1], z = p[2];
+    const float qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], x, y, z);
+    const float qy = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], x, y, z);
+    const float qz = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], x, y, z);
+    if (finite3(qx, qy, qz)) {
+      const Grid tg = *A.tgrid;
+      Nn1 v;
+      v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
+      grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v);
+      if (v.best_pos >= 0) {
+        if ((double)v.best_d2 <= A.max_range) { acc[0] = (double)v.best_d2; acc[1] = 1.0; }
+        if (v.best_d2 < A.inlier_thresh_sq) acc[2] = 1.0;
+      }
+    }
+  }
+  block_reduce<3>(acc, red);
+  finish_partials<3>(acc, A.partials, A.out, A.counter);
+}
+
+__global__ void k_nearest(const float* __restrict__ q_raw, int stride_f, int n, const Grid* __restrict__ tgrid,
+                          const int* __restrict__ tcell_start, const float4* __restrict__ tsp, int* idx_out, float* d2_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = q_raw + (size_t)i * stride_f;
+  Nn1 v;
+  v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
+  if (finite3(p[0], p[1], p[2])) {
+    const Grid tg = *tgrid;
+    grid_search(tg, tcell_start, tsp, p[0], p[1], p[2], v);
+  }
+  idx_out[i] = v.best_pos >= 0 ? v.best_idx : -1;
+  d2_out[i] = v.best_d2;
+}
+
+struct XfArg { float Tf[12]; };
+__global__ void k_transform(const float* __restrict__ raw, int stride_f, int n, XfArg X, float4* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = raw + (size_t)i * stride_f;
+  const float x = p[0], y = p[1], z = p[2];
+  out[i] = make_float4(xform_row(X.Tf[0], X.Tf[1], X.Tf[2], X.Tf[3], x, y, z), xform_row(X.Tf[4], X.Tf[5], X.Tf[6], X.Tf[7], x, y, z),
+                       xform_row(X.Tf[8], X.Tf[9], X.Tf[10], X.Tf[11], x, y, z), 1.0f);
+}
+
+}  // namespace b2r

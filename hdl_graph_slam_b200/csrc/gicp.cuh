@@ -1,0 +1,305 @@
+// gicp.cuh — GICP kernels: k-NN covariances, fused correspondence + linearisation, LM trial cost.
+//
+// Re-creates, B200-first, the arithmetic of fast_gicp::FastGICP that the reference selects at
+// /root/reference/src/hdl_graph_slam/registrations.cpp:27-36 and runs from apps/scan_matching_odometry_nodelet.cpp:177,210
+// and include/hdl_graph_slam/loop_detector.hpp:136,143:
+//   k_knn_cov          <- FastGICP::calculate_covariances (k exact NN, PLANE regularisation)
+//   k_gicp_linearize   <- FastGICP::update_correspondences + FastGICP::linearize (fused; M_i kept for the trial cost)
+//   k_gicp_error       <- FastGICP::compute_error
+// All per-cloud arrays live in the grid-sorted order (ascending cell, then original index), so neighbouring threads
+// search neighbouring cells; block partials are combined in a fixed order => bitwise reproducible results.
+#pragma once
+#include "common.cuh"
+#include "nn_search.cuh"
+#include "linalg.cuh"
+
+namespace b2r {
+
+constexpr int kKnnThreads = 128;
+constexpr int kLinThreads = 256;
+constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
+
+// ---------------------------------------------------------------- k-NN covariance
+struct KnnList {
+  float* d;   // [k][blockDim] (slot-major => conflict-free)
+  int* pos;   // sorted position of the neighbour
+  const float4* sp;
+  int k, cnt, stride;
+  __device__ __forceinline__ float worst() const { return cnt < k ? INFINITY : d[(k - 1) * stride]; }
+  __device__ __forceinline__ float limit() const { return INFINITY; }
+  __device__ __forceinline__ bool less_than_slot(float d2, int idx, int slot) const {
+    float ds = d[slot * stride];
+    if (d2 < ds) return true;
+    if (d2 > ds) return false;
+    return idx < idx_bits(sp[pos[slot * stride]].w);
+  }
+  __device__ __forceinline__ void visit(float d2, int idx, int p) {
+    if (cnt == k && !less_than_slot(d2, idx, k - 1)) return;
+    int j = (cnt < k) ? cnt++ : k - 1;
+    while (j > 0 && less_than_slot(d2, idx, j - 1)) {
+      d[j * stride] = d[(j - 1) * stride];
+      pos[j * stride] = pos[(j - 1) * stride];
+      j--;
+    }
+    d[j * stride] = d2;
+    pos[j * stride] = p;
+  }
+};
+
+__global__ void __launch_bounds__(kKnnThreads) k_knn_cov(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                         const float4* __restrict__ sp, int k, double* __restrict__ cov) {
+  extern __shared__ float knn_smem[];
+  const Grid g = *gp;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= g.n_valid) return;
+  KnnList L;
+  L.d = knn_smem + threadIdx.x;
+  L.pos = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + threadIdx.x;
+  L.sp = sp;
+  L.k = k;
+  L.cnt = 0;
+  L.stride = blockDim.x;
+  const float4 q = sp[s];
+  grid_search(g, cell_start, sp, q.x, q.y, q.z, L);
+  const int kk = L.cnt;
+  // mean and covariance over the neighbours in ascending (d2, index) order, float64
+  double mx = 0, my = 0, mz = 0;
+  for (int j = 0; j < kk; j++) {
+    float4 p = sp[L.pos[j * L.stride]];
+    mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
+  }
+  const double inv = 1.0 / (double)kk;
+  mx *= inv; my *= inv; mz *= inv;
+  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < kk; j++) {
+    float4 p = sp[L.pos[j * L.stride]];
+    double vx = (double)p.x - mx, vy = (double)p.y - my, vz = (double)p.z - mz;
+    c[0] += vx * vx; c[1] += vx * vy; c[2] += vx * vz;
+    c[4] += vy * vy; c[5] += vy * vz; c[8] += vz * vz;
+  }
+  c[0] *= inv; c[1] *= inv; c[2] *= inv; c[4] *= inv; c[5] *= inv; c[8] *= inv;
+  c[3] = c[1]; c[6] = c[2]; c[7] = c[5];
+  // PLANE regularisation: eigenvalues (descending) replaced by (1, 1, 1e-3)
+  double w[3], V[9];
+  sym_eigen3(c, w, V);
+  const double v0 = 1e-3, v1 = 1.0, v2 = 1.0;  // ascending order: smallest -> 1e-3
+  double* o = cov + (size_t)s * 6;
+  o[0] = v2 * V[2] * V[2] + v1 * V[1] * V[1] + v0 * V[0] * V[0];
+  o[1] = v2 * V[2] * V[5] + v1 * V[1] * V[4] + v0 * V[0] * V[3];
+  o[2] = v2 * V[2] * V[8] + v1 * V[1] * V[7] + v0 * V[0] * V[6];
+  o[3] = v2 * V[5] * V[5] + v1 * V[4] * V[4] + v0 * V[3] * V[3];
+  o[4] = v2 * V[5] * V[8] + v1 * V[4] * V[7] + v0 * V[3] * V[6];
+  o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
+}
+
+// ---------------------------------------------------------------- pose passed by value to the per-iteration kernels
+struct PoseArg {
+  double T[12];  // rows 0..2 of the 4x4 (row-major)
+  float Tf[12];  // float cast of the same (fast_gicp: trans.cast<float>())
+};
+
+// deterministic block reduction of NV doubles per thread; result valid in thread 0
+template <int NV>
+__device__ __forceinline__ void block_reduce(double* v, double* smem /* NV * 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) smem[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double x = (lane < nw) ? smem[i * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      v[i] = x;
+    }
+  }
+}
+
+// last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in block order
+template <int NV>
+__device__ __forceinline__ void finish_partials(const double* v, double* partials, double* out, unsigned int* counter) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) partials[(size_t)blockIdx.x * NV + i] = v[i];
+    __threadfence();
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+      const volatile double* P = partials;
+      for (unsigned int b = 0; b < gridDim.x; b++) s += P[(size_t)b * NV + threadIdx.x];
+      out[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+  }
+}
+
+struct LinArgs {
+  const Grid* sgrid;           // source grid (n_valid)
+  const float4* ssp;           // source points, sorted
+  const double* scov;          // source covariances, sorted (6 per point)
+  const Grid* tgrid;
+  const int* tcell_start;
+  const float4* tsp;
+  const double* tcov;
+  double thr2;                 // max_correspondence_distance^2 (double, compared against (double)d2)
+  float lim;                   // float >= thr2 (search range limit)
+  int* corr;                   // [n_src original] target ORIGINAL index or -1
+  int* cpos;                   // [sorted s] target sorted position or -1
+  float* d2;                   // [sorted s] NN squared distance
+  double* mahal;               // [sorted s][6]
+  double* partials;            // [blocks][kAcc]
+  double* out;                 // [kAcc]
+  unsigned int* counter;
+  int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
+};
+
+__global__ void __launch_bounds__(kLinThreads) k_gicp_linearize(LinArgs A, PoseArg P) {
+  __shared__ double red[kAcc * 32];
+  const int nv = A.sgrid->n_valid;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+  if (s < nv) {
+    const Grid tg = *A.tgrid;
+    const float4 p = A.ssp[s];
+    const float qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
+    const float qy = xform_row(P.Tf[4], P.Tf[5], P.Tf[6], P.Tf[7], p.x, p.y, p.z);
+    const float qz = xform_row(P.Tf[8], P.Tf[9], P.Tf[10], P.Tf[11], p.x, p.y, p.z);
+    Nn1 v;
+    v.best_d2 = INFINITY;
+    v.best_idx = 0x7fffffff;
+    v.best_pos = -1;
+    v.lim = A.lim;
+    if (A.use_seed) {
+      int sp0 = A.cpos[s];
+      if (sp0 >= 0) {
+        float4 t = A.tsp[sp0];
+        v.best_d2 = dist2_f32(qx, qy, qz, t.x, t.y, t.z);
+        v.best_idx = idx_bits(t.w);
+        v.best_pos = sp0;
+      }
+    }
+    if (finite3(qx, qy, qz)) grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v);
+    else v.best_pos = -1;
+    const bool valid = (v.best_pos >= 0) && ((double)v.best_d2 < A.thr2);
+    A.corr[idx_bits(p.w)] = valid ? v.best_idx : -1;
+    A.cpos[s] = valid ? v.best_pos : -1;
+    A.d2[s] = v.best_d2;
+    if (valid) {
+      const double* ca = A.scov + (size_t)s * 6;
+      const double* cb = A.tcov + (size_t)v.best_pos * 6;
+      const double CA[9] = {ca[0], ca[1], ca[2], ca[1], ca[3], ca[4], ca[2], ca[4], ca[5]};
+      const double R[9] = {P.T[0], P.T[1], P.T[2], P.T[4], P.T[5], P.T[6], P.T[8], P.T[9], P.T[10]};
+      double tmp[9], rcr[9], M[9];
+      mul3(R, CA, tmp);
+      // rcr = CB + tmp * R^T  (symmetric; build the upper part and mirror so the inverse is exactly symmetric)
+      double u[6];
+      u[0] = tmp[0] * R[0] + tmp[1] * R[1] + tmp[2] * R[2];
+      u[1] = tmp[0] * R[3] + tmp[1] * R[4] + tmp[2] * R[5];
+      u[2] = tmp[0] * R[6] + tmp[1] * R[7] + tmp[2] * R[8];
+      u[3] = tmp[3] * R[3] + tmp[4] * R[4] + tmp[5] * R[5];
+      u[4] = tmp[3] * R[6] + tmp[4] * R[7] + tmp[5] * R[8];
+      u[5] = tmp[6] * R[6] + tmp[7] * R[7] + tmp[8] * R[8];
+      rcr[0] = cb[0] + u[0]; rcr[1] = cb[1] + u[1]; rcr[2] = cb[2] + u[2];
+      rcr[4] = cb[3] + u[3]; rcr[5] = cb[4] + u[4]; rcr[8] = cb[5] + u[5];
+      rcr[3] = rcr[1]; rcr[6] = rcr[2]; rcr[7] = rcr[5];
+      inv3(rcr, M);
+      double* mo = A.mahal + (size_t)s * 6;
+      mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
+      const float4 tb = A.tsp[v.best_pos];
+      const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;
+      const double tx = P.T[0] * ax + P.T[1] * ay + P.T[2] * az + P.T[3];
+      const double ty = P.T[4] * ax + P.T[5] * ay + P.T[6] * az + P.T[7];
+      const double tz = P.T[8] * ax + P.T[9] * ay + P.T[10] * az + P.T[11];
+      const double ex = (double)tb.x - tx, ey = (double)tb.y - ty, ez = (double)tb.z - tz;
+      const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[4], m12 = M[5], m22 = M[8];
+      const double Mex = m00 * ex + m01 * ey + m02 * ez;
+      const double Mey = m01 * ex + m11 * ey + m12 * ez;
+      const double Mez = m02 * ex + m12 * ey + m22 * ez;
+      acc[27] = ex * Mex + ey * Mey + ez * Mez;
+      // S = skew(tA) = [[0,-tz,ty],[tz,0,-tx],[-ty,tx,0]];  MS = M*S
+      const double ms00 = m01 * tz - m02 * ty, ms01 = -m00 * tz + m02 * tx, ms02 = m00 * ty - m01 * tx;
+      const double ms10 = m11 * tz - m12 * ty, ms11 = -m01 * tz + m12 * tx, ms12 = m01 * ty - m11 * tx;
+      const double ms20 = m12 * tz - m22 * ty, ms21 = -m02 * tz + m22 * tx, ms22 = m02 * ty - m12 * tx;
+      // S^T * MS (upper): S^T = [[0,tz,-ty],[-tz,0,tx],[ty,-tx,0]]
+      acc[0] = tz * ms10 - ty * ms20;   // (0,0)
+      acc[1] = tz * ms11 - ty * ms21;   // (0,1)
+      acc[2] = tz * ms12 - ty * ms22;   // (0,2)
+      acc[3] = -ms00;                   // (0,3) = -(MS)[0][0]
+      acc[4] = -ms10;                   // (0,4) = -(MS)[1][0]
+      acc[5] = -ms20;                   // (0,5)
+      acc[6] = -tz * ms01 + tx * ms21;  // (1,1)
+      acc[7] = -tz * ms02 + tx * ms22;  // (1,2)
+      acc[8] = -ms01;                   // (1,3)
+      acc[9] = -ms11;                   // (1,4)
+      acc[10] = -ms21;                  // (1,5)
+      acc[11] = ty * ms02 - tx * ms12;  // (2,2)
+      acc[12] = -ms02;                  // (2,3)
+      acc[13] = -ms12;                  // (2,4)
+      acc[14] = -ms22;                  // (2,5)
+      acc[15] = m00; acc[16] = m01; acc[17] = m02;  // (3,3..5)
+      acc[18] = m11; acc[19] = m12;                 // (4,4..5)
+      acc[20] = m22;                                // (5,5)
+      // b = J^T M e = [S^T Me ; -Me]
+      acc[21] = tz * Mey - ty * Mez;
+      acc[22] = -tz * Mex + tx * Mez;
+      acc[23] = ty * Mex - tx * Mey;
+      acc[24] = -Mex; acc[25] = -Mey; acc[26] = -Mez;
+    }
+  }
+  block_reduce<kAcc>(acc, red);
+  finish_partials<kAcc>(acc, A.partials, A.out, A.counter);
+}
+
+struct ErrArgs {
+  const Grid* sgrid;
+  const float4* ssp;
+  const float4* tsp;
+  const int* cpos;
+  const double* mahal;
+  double* partials;  // [blocks]
+  double* out;       // [1]
+  unsigned int* counter;
+};
+
+__global__ void __launch_bounds__(kLinThreads) k_gicp_error(ErrArgs A, PoseArg P) {
+  __shared__ double red[32];
+  const int nv = A.sgrid->n_valid;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[1] = {0.0};
+  if (s < nv) {
+    int tp = A.cpos[s];
+    if (tp >= 0) {
+      const float4 p = A.ssp[s];
+      const float4 tb = A.tsp[tp];
+      const double* m = A.mahal + (size_t)s * 6;
+      const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;
+      const double ex = (double)tb.x - (P.T[0] * ax + P.T[1] * ay + P.T[2] * az + P.T[3]);
+      const double ey = (double)tb.y - (P.T[4] * ax + P.T[5] * ay + P.T[6] * az + P.T[7]);
+      const double ez = (double)tb.z - (P.T[8] * ax + P.T[9] * ay + P.T[10] * az + P.T[11]);
+      const double Mex = m[0] * ex + m[1] * ey + m[2] * ez;
+      const double Mey = m[1] * ex + m[3] * ey + m[4] * ez;
+      const double Mez = m[2] * ex + m[4] * ey + m[5] * ez;
+      acc[0] = ex * Mex + ey * Mey + ez * Mez;
+    }
+  }
+  block_reduce<1>(acc, red);
+  finish_partials<1>(acc, A.partials, A.out, A.counter);
+}
+
+}  // namespace b2r

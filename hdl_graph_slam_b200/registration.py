@@ -1,0 +1,293 @@
+"""Host-side mirror of the reference's registration interface, as thin wrappers over the C ABI (libb200reg.so).
+
+Names follow the reference so that tests read like its call sites:
+  select_registration_method   <- src/hdl_graph_slam/registrations.cpp:22-124
+  Registration.setInputTarget / setInputSource / align / hasConverged / getFinalTransformation / getFitnessScore
+                               <- pcl::Registration<PointXYZI,PointXYZI> as used at
+                                  apps/scan_matching_odometry_nodelet.cpp:172,177,210,214,220,246,307 and
+                                  include/hdl_graph_slam/loop_detector.hpp:122,136,143,146,147,153
+  ScanMatchingOdometry.matching <- apps/scan_matching_odometry_nodelet.cpp:165-262
+  LoopDetector.matching         <- include/hdl_graph_slam/loop_detector.hpp:117-171
+  VoxelGrid.filter              <- pcl::VoxelGrid as set up at apps/prefiltering_nodelet.cpp:54-58
+
+Clouds are float32 numpy arrays of shape (n, 4) [x,y,z,1] or (n, 8) [pcl::PointXYZI record]; 4x4 poses are ordinary
+row-major numpy matrices (the wrapper converts to the ABI's column-major layout).  All arithmetic happens in the CUDA
+library; nothing here computes.
+"""
+import ctypes as C
+import numpy as np
+from . import _capi
+from ._capi import Config, Result, OdometryParams, OdometryStatus, check, B2R_METHOD_GICP, B2R_METHOD_NDT
+
+
+def _cloud(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < 3:
+        raise ValueError("cloud must be (n, >=3) float32")
+    return a, a.shape[0], a.shape[1] * 4
+
+
+def _colmajor(T, dtype=np.float32):
+    return np.ascontiguousarray(np.asarray(T, dtype=dtype).T.reshape(-1))
+
+
+def _from_colmajor(buf):
+    return np.array(buf, dtype=np.float32).reshape(4, 4).T.copy()
+
+
+def default_config(method):
+    lib = _capi.load()
+    cfg = Config()
+    check(lib.b2r_config_default(C.byref(cfg), method))
+    return cfg
+
+
+class Registration:
+    """One registration handle (== one pcl::Registration object of the reference)."""
+
+    def __init__(self, cfg=None, _handle=None):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        if _handle is not None:
+            self._h = _handle
+        else:
+            check(self._lib.b2r_create(C.byref(cfg), C.byref(self._h)))
+        self._res = Result()
+        self._res.converged = 0
+        self._keep = {}
+
+    def close(self):
+        if self._h:
+            self._lib.b2r_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def config(self):
+        cfg = Config()
+        check(self._lib.b2r_get_config(self._h, C.byref(cfg)))
+        return cfg
+
+    # --- pcl::Registration surface
+    def setInputTarget(self, cloud):
+        a, n, s = _cloud(cloud)
+        self._keep["t"] = a
+        check(self._lib.b2r_set_target(self._h, a.ctypes.data_as(C.c_void_p), n, s))
+
+    def setInputSource(self, cloud):
+        a, n, s = _cloud(cloud)
+        self._keep["s"] = a
+        check(self._lib.b2r_set_source(self._h, a.ctypes.data_as(C.c_void_p), n, s))
+
+    def setInputTargetDevice(self, ptr, n, stride_bytes):
+        check(self._lib.b2r_set_target_device(self._h, C.c_void_p(ptr), n, stride_bytes))
+
+    def setInputSourceDevice(self, ptr, n, stride_bytes):
+        check(self._lib.b2r_set_source_device(self._h, C.c_void_p(ptr), n, stride_bytes))
+
+    def setInputTargetRaw(self, ptr, n, stride_bytes):
+        """host pointer variant (e.g. pinned memory owned by the caller)"""
+        check(self._lib.b2r_set_target(self._h, C.c_void_p(ptr), n, stride_bytes))
+
+    def setInputSourceRaw(self, ptr, n, stride_bytes):
+        check(self._lib.b2r_set_source(self._h, C.c_void_p(ptr), n, stride_bytes))
+
+    def promoteSourceToTarget(self):
+        check(self._lib.b2r_promote_source_to_target(self._h))
+
+    def align(self, guess=None, want_aligned=False):
+        g = _colmajor(np.eye(4) if guess is None else guess)
+        check(self._lib.b2r_align(self._h, g.ctypes.data_as(C.POINTER(C.c_float)), C.byref(self._res)))
+        if want_aligned:
+            return self.getAligned()
+        return None
+
+    def getAligned(self):
+        src = self._keep.get("s")
+        if src is None:
+            raise RuntimeError("getAligned needs a host source cloud")
+        out = src.copy()
+        check(self._lib.b2r_get_aligned(self._h, out.ctypes.data_as(C.c_void_p), out.shape[0], out.shape[1] * 4))
+        return out
+
+    def hasConverged(self):
+        return bool(self._res.converged)
+
+    def getFinalTransformation(self):
+        return _from_colmajor(self._res.T)
+
+    @property
+    def nr_iterations(self):
+        return int(self._res.iterations)
+
+    def getFitnessScore(self, max_range=np.finfo(np.float64).max, T=None, inlier_thresh_sq=0.25, full=False):
+        score, used, inl = C.c_double(), C.c_uint32(), C.c_uint32()
+        tp = None
+        if T is not None:
+            t = _colmajor(T)
+            tp = t.ctypes.data_as(C.POINTER(C.c_float))
+        check(self._lib.b2r_fitness(self._h, tp, max_range, inlier_thresh_sq, C.byref(score), C.byref(used), C.byref(inl)))
+        if full:
+            return score.value, used.value, inl.value
+        return score.value
+
+    def nearestKSearch(self, queries):
+        """getSearchMethodTarget()->nearestKSearch(pt, 1, ...) for many points: (indices, squared distances)"""
+        a, n, s = _cloud(queries)
+        idx = np.empty(n, np.int32)
+        d2 = np.empty(n, np.float32)
+        check(self._lib.b2r_target_nearest(self._h, a.ctypes.data_as(C.c_void_p), n, s, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                           d2.ctypes.data_as(C.POINTER(C.c_float))))
+        return idx, d2
+
+    # --- parity taps
+    def getCorrespondences(self, n):
+        out = np.empty(n, np.int32)
+        check(self._lib.b2r_get_correspondences(self._h, out.ctypes.data_as(C.POINTER(C.c_int32)), n))
+        return out
+
+    def getCovariances(self, which, n):
+        out = np.empty((n, 3, 3), np.float64)
+        check(self._lib.b2r_get_covariances(self._h, which, out.ctypes.data_as(C.POINTER(C.c_double)), n))
+        return out
+
+    def gicpLinearizeAt(self, T):
+        t = _colmajor(T, np.float64)
+        H = np.empty((6, 6), np.float64)
+        b = np.empty(6, np.float64)
+        e = C.c_double()
+        dp = C.POINTER(C.c_double)
+        check(self._lib.b2r_gicp_linearize_at(self._h, t.ctypes.data_as(dp), H.ctypes.data_as(dp), b.ctypes.data_as(dp), C.byref(e)))
+        return H, b, e.value
+
+    def gicpErrorAt(self, T):
+        t = _colmajor(T, np.float64)
+        e = C.c_double()
+        check(self._lib.b2r_gicp_error_at(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), C.byref(e)))
+        return e.value
+
+    def ndtGetVoxels(self):
+        nv = C.c_size_t()
+        minb = np.zeros(3, np.int32)
+        divb = np.zeros(3, np.int32)
+        ip = C.POINTER(C.c_int32)
+        check(self._lib.b2r_ndt_get_voxels(self._h, 0, C.byref(nv), None, None, None, None, minb.ctypes.data_as(ip), divb.ctypes.data_as(ip)))
+        V = nv.value
+        keys = np.empty(V, np.int64)
+        npts = np.empty(V, np.int32)
+        mean = np.empty((V, 3), np.float64)
+        icov = np.empty((V, 3, 3), np.float64)
+        dp = C.POINTER(C.c_double)
+        check(self._lib.b2r_ndt_get_voxels(self._h, V, C.byref(nv), keys.ctypes.data_as(C.POINTER(C.c_int64)), npts.ctypes.data_as(ip),
+                                           mean.ctypes.data_as(dp), icov.ctypes.data_as(dp), minb.ctypes.data_as(ip), divb.ctypes.data_as(ip)))
+        return dict(keys=keys, npts=npts, mean=mean, icov=icov, min_b=minb, div_b=divb)
+
+    def ndtDerivativesAt(self, p):
+        p = np.ascontiguousarray(p, np.float64)
+        g = np.empty(6, np.float64)
+        H = np.empty((6, 6), np.float64)
+        score = C.c_double()
+        npairs = C.c_uint64()
+        dp = C.POINTER(C.c_double)
+        check(self._lib.b2r_ndt_derivatives_at(self._h, p.ctypes.data_as(dp), C.byref(score), g.ctypes.data_as(dp), H.ctypes.data_as(dp), C.byref(npairs)))
+        return score.value, g, H, npairs.value
+
+    # --- companion
+    def voxelGridFilter(self, cloud, leaf, with_keys=False):
+        a, n, s = _cloud(cloud)
+        out = np.zeros_like(a)
+        n_out = C.c_size_t()
+        keys = np.empty(max(n, 1), np.int32)
+        counts = np.empty(max(n, 1), np.int32)
+        ip = C.POINTER(C.c_int32)
+        rc = check(self._lib.b2r_voxelgrid(self._h, a.ctypes.data_as(C.c_void_p), n, s, leaf, out.ctypes.data_as(C.c_void_p), C.byref(n_out),
+                                           keys.ctypes.data_as(ip), counts.ctypes.data_as(ip)))
+        m = n_out.value
+        if with_keys:
+            return out[:m], keys[:m], counts[:m], rc
+        return out[:m]
+
+
+def select_registration_method(params=None, device_id=0):
+    """Mirror of hdl_graph_slam::select_registration_method(ros::NodeHandle&): `params` plays the private rosparam
+    namespace (same keys, same defaults).  Raises B2RError(B2R_EUNSUPPORTED) for methods this engine does not re-create."""
+    lib = _capi.load()
+    params = params or {}
+    keys = [str(k).encode() for k in params.keys()]
+    vals = [(("true" if v else "false") if isinstance(v, bool) else str(v)).encode() for v in params.values()]
+    n = len(keys)
+    ka = (C.c_char_p * max(n, 1))(*keys)
+    va = (C.c_char_p * max(n, 1))(*vals)
+    h = C.c_void_p()
+    check(lib.b2r_select_registration_method(ka, va, n, device_id, C.byref(h)))
+    return Registration(_handle=h)
+
+
+class ScanMatchingOdometry:
+    """Mirror of ScanMatchingOdometryNodelet's matching() state machine (keyframe, prev_trans, thresholds)."""
+
+    def __init__(self, registration, keyframe_delta_trans=0.25, keyframe_delta_angle=0.15, keyframe_delta_time=1.0,
+                 transform_thresholding=False, max_acceptable_trans=1.0, max_acceptable_angle=1.0, publish_status=False):
+        self._lib = _capi.load()
+        self.registration = registration
+        p = OdometryParams(keyframe_delta_trans, keyframe_delta_angle, keyframe_delta_time, int(transform_thresholding),
+                           max_acceptable_trans, max_acceptable_angle, int(publish_status))
+        self._o = C.c_void_p()
+        check(self._lib.b2r_odometry_create(registration._h, C.byref(p), C.byref(self._o)))
+        self._keep = []
+
+    def close(self):
+        if self._o:
+            self._lib.b2r_odometry_destroy(self._o)
+            self._o = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def matching(self, stamp, cloud, msf_delta=None):
+        a, n, s = _cloud(cloud)
+        return self.matching_raw(stamp, a.ctypes.data, n, s, msf_delta)
+
+    def matching_raw(self, stamp, ptr, n, stride_bytes, msf_delta=None):
+        st = OdometryStatus()
+        dp = None
+        if msf_delta is not None:
+            d = _colmajor(msf_delta)
+            dp = d.ctypes.data_as(C.POINTER(C.c_float))
+        check(self._lib.b2r_odometry_matching(self._o, float(stamp), C.c_void_p(ptr), n, stride_bytes, dp, C.byref(st)))
+        return dict(odom=_from_colmajor(st.odom), trans=_from_colmajor(st.trans), converged=bool(st.converged), iterations=st.iterations,
+                    keyframe_updated=bool(st.keyframe_updated), frame_rejected=bool(st.frame_rejected), matching_error=st.matching_error,
+                    inlier_fraction=st.inlier_fraction)
+
+
+class LoopDetector:
+    """Mirror of LoopDetector::matching: align each candidate to the new keyframe, keep the best converged fitness."""
+
+    def __init__(self, registration, fitness_score_max_range=np.finfo(np.float64).max, fitness_score_thresh=0.5):
+        self._lib = _capi.load()
+        self.registration = registration
+        self.fitness_score_max_range = fitness_score_max_range
+        self.fitness_score_thresh = fitness_score_thresh
+
+    def matching(self, candidate_clouds, new_keyframe_cloud, guesses):
+        nk, n_new, s = _cloud(new_keyframe_cloud)
+        cands = [_cloud(c)[0] for c in candidate_clouds]
+        m = len(cands)
+        ptrs = (C.c_void_p * max(m, 1))(*[c.ctypes.data for c in cands])
+        ns = (C.c_size_t * max(m, 1))(*[c.shape[0] for c in cands])
+        g = np.ascontiguousarray(np.stack([_colmajor(x) for x in guesses]) if m else np.zeros((1, 16), np.float32), np.float32)
+        res = (Result * max(m, 1))()
+        best = C.c_int32(-1)
+        check(self._lib.b2r_loop_matching(self.registration._h, nk.ctypes.data_as(C.c_void_p), n_new, s, ptrs, ns, m,
+                                          g.ctypes.data_as(C.POINTER(C.c_float)), self.fitness_score_max_range, self.fitness_score_thresh,
+                                          res, C.byref(best)))
+        results = [dict(T=_from_colmajor(r.T), fitness=r.fitness, converged=bool(r.converged), iterations=r.iterations) for r in res[:m]]
+        return best.value, results

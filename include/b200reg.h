@@ -1,0 +1,181 @@
+/* b200reg.h — C ABI of libb200reg.so, the B200-native scan-matching engine that drops in behind the
+ * pcl::Registration<pcl::PointXYZI, pcl::PointXYZI> handle of koide3/hdl_graph_slam.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to /root/reference).  The seam is
+ * `select_registration_method()` (include/hdl_graph_slam/registrations.hpp:17, src/hdl_graph_slam/registrations.cpp:22-124);
+ * its two consumers are ScanMatchingOdometryNodelet (apps/scan_matching_odometry_nodelet.cpp:106,165-262,298-335) and
+ * LoopDetector (include/hdl_graph_slam/loop_detector.hpp:47,117-171).  INTEGRATION.md shows the adapter class and the
+ * factory branch a maintainer adds.
+ *
+ * Conventions
+ *   - Point records: float32 x,y,z at byte offsets 0,4,8 of a record `stride_bytes` long (16 = packed float4,
+ *     32 = pcl::PointXYZI with intensity at offset 16).  Host pointers may be pageable or pinned (pinned buffers
+ *     are DMA'd directly); the engine copies, the caller keeps ownership.
+ *   - 4x4 matrices are COLUMN-major (what Eigen::Matrix4f::data() / Eigen::Matrix4d::data() hand out).
+ *   - Every function returns 0 on success or a negative B2R_E* code; nothing throws or aborts; on failure
+ *     b2r_last_error() holds a message and results report converged = 0 (the reference's failure signal,
+ *     scan_matching_odometry_nodelet.cpp:214-218, loop_detector.hpp:147).
+ *   - A handle is used by one thread at a time; distinct handles are independent (own stream and buffers), matching
+ *     the reference's two concurrently-live registration objects (odometry + loop closure).
+ *   - There is no CPU fallback: without a CUDA device b2r_create fails with B2R_ENODEVICE.
+ */
+#ifndef B200REG_H
+#define B200REG_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_OK 0
+#define B2R_EINVAL (-1)     /* bad argument */
+#define B2R_ENODEVICE (-2)  /* no CUDA device / CUDA initialisation failed */
+#define B2R_ECUDA (-3)      /* CUDA runtime error (message in b2r_last_error) */
+#define B2R_ESTATE (-4)     /* source/target not set */
+#define B2R_EUNSUPPORTED (-5) /* registration_method that this engine does not re-create */
+#define B2R_ENCCL (-6)
+
+#define B2R_METHOD_GICP 0 /* fast_gicp::FastGICP semantics   (registrations.cpp:27-36)   */
+#define B2R_METHOD_NDT 1  /* pclomp::NormalDistributionsTransform semantics (registrations.cpp:101-120) */
+
+typedef struct b2r_handle b2r_handle;
+
+/* Mirrors the per-method setters the factory feeds from rosparams (registrations.cpp:30-34,106-118). */
+typedef struct b2r_config {
+  int32_t method;                     /* B2R_METHOD_* */
+  int32_t device_id;                  /* CUDA device ordinal */
+  int32_t max_iterations;             /* reg_maximum_iterations            (64)   */
+  int32_t k_correspondences;          /* reg_correspondence_randomness     (20)   */
+  double transformation_epsilon;      /* reg_transformation_epsilon        (0.01) */
+  double rotation_epsilon;            /* fast_gicp rotation_epsilon_       (2e-3) */
+  double max_correspondence_distance; /* reg_max_correspondence_distance   (2.5)  */
+  double ndt_resolution;              /* reg_resolution                    (0.5 code default, 1.0 in launch files) */
+  double ndt_step_size;               /* ndt_omp step_size_                (0.1)  */
+  double ndt_outlier_ratio;           /* ndt_omp outlier_ratio_            (0.55) */
+  int32_t ndt_search_method;          /* reg_nn_search_method: 1 = DIRECT1, 7 = DIRECT7 (default) */
+  int32_t ndt_mt_interval_flag;       /* 0 = ndt_omp polarity (More-Thuente loop never entered), 1 = active line search */
+  int32_t ndt_fixed_iterations;       /* >0: exactly this many iterations (BASELINE config 3), convergence test off */
+  float grid_cell_min;                /* engine tuning: smallest search-grid cell, power of two (default 0.5 m) */
+} b2r_config;
+
+/* What the callers read back after align(): getFinalTransformation(), hasConverged(), and (loop closure)
+ * getFitnessScore().  80 bytes — also the record all-gathered across GPUs by the batch path. */
+typedef struct b2r_result {
+  float T[16];        /* final_transformation_, column-major */
+  double fitness;     /* getFitnessScore(max_range) when requested, else NaN */
+  int32_t converged;  /* hasConverged() */
+  int32_t iterations; /* outer iterations executed */
+} b2r_result;
+
+const char* b2r_last_error(void);
+const char* b2r_version(void);
+
+/* defaults of the reference factory for `method` */
+int b2r_config_default(b2r_config* cfg, int method);
+
+/* replaces select_registration_method(ros::NodeHandle&) (registrations.cpp:22-124): same parameter NAMES and defaults,
+ * passed as string key/value pairs (the rosparam namespace of the nodelet).  "FAST_GICP"/"B200_GICP" -> GICP engine,
+ * "NDT_OMP"/"B200_NDT" -> NDT engine.  ICP / GICP / GICP_OMP / NDT(pcl) / FAST_VGICP[_CUDA] are not re-created:
+ * returns B2R_EUNSUPPORTED so the caller keeps the reference's own branch. */
+int b2r_select_registration_method(const char* const* keys, const char* const* values, int n_params, int device_id,
+                                   b2r_handle** out);
+
+int b2r_create(const b2r_config* cfg, b2r_handle** out);
+void b2r_destroy(b2r_handle* h);
+int b2r_get_config(const b2r_handle* h, b2r_config* out);
+
+/* replaces registration->setInputTarget(cloud) (scan_matching_odometry_nodelet.cpp:172,246; loop_detector.hpp:122).
+ * Uploads, builds the search grid and (GICP) the k-NN covariances or (NDT) the voxel Gaussians. */
+int b2r_set_target(b2r_handle* h, const void* points, size_t n, size_t stride_bytes);
+/* replaces registration->setInputSource(cloud) (scan_matching_odometry_nodelet.cpp:177; loop_detector.hpp:136). */
+int b2r_set_source(b2r_handle* h, const void* points, size_t n, size_t stride_bytes);
+/* same, for clouds already resident in device memory (device pointers; used by the HBM-resident measurement and by
+ * device-side pipelines such as b2r_voxelgrid_device -> registration). */
+int b2r_set_target_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
+int b2r_set_source_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
+/* keyframe switch `keyframe = filtered; registration->setInputTarget(keyframe)` (scan_matching_odometry_nodelet.cpp:245-246):
+ * the current source (points, grid, covariances) becomes the target without re-upload or recomputation. */
+int b2r_promote_source_to_target(b2r_handle* h);
+
+/* replaces registration->align(*aligned, guess) + hasConverged() + getFinalTransformation()
+ * (scan_matching_odometry_nodelet.cpp:210,214,220; loop_detector.hpp:143,147,153). */
+int b2r_align(b2r_handle* h, const float guess[16], b2r_result* out);
+
+/* the `aligned` output cloud of align(): source transformed by the final pose.  Writes x,y,z (and 1.0f at offset 12 when
+ * stride_bytes >= 16) of n records; other bytes are left untouched. */
+int b2r_get_aligned(b2r_handle* h, void* out_points, size_t n, size_t stride_bytes);
+
+/* replaces registration->getFitnessScore(max_range) (scan_matching_odometry_nodelet.cpp:307; loop_detector.hpp:146;
+ * twin: information_matrix_calculator.cpp:49-80) and the inlier loop of scan_matching_odometry_nodelet.cpp:309-320.
+ * T = NULL uses the last final transformation.  max_range is compared against the SQUARED distance, as in the reference. */
+int b2r_fitness(b2r_handle* h, const float* T, double max_range, float inlier_thresh_sq, double* score, uint32_t* n_used,
+                uint32_t* n_inliers);
+
+/* replaces registration->getSearchMethodTarget()->nearestKSearch(pt, 1, ...) (scan_matching_odometry_nodelet.cpp:316):
+ * exact 1-NN of n query points in the current target. */
+int b2r_target_nearest(b2r_handle* h, const void* queries, size_t n, size_t stride_bytes, int32_t* idx_out, float* d2_out);
+
+/* ---- parity / debug taps (not used by the reference's callers) ------------------------------------------------ */
+/* correspondences_ of the last linearisation (target index per source point, -1 = rejected) */
+int b2r_get_correspondences(b2r_handle* h, int32_t* out, size_t n);
+/* which: 0 = source, 1 = target.  out: n x 9 doubles (3x3 row-major), original point order (GICP). */
+int b2r_get_covariances(b2r_handle* h, int which, double* out, size_t n);
+/* one update_correspondences + linearize at pose T (column-major double): H[36] row-major, b[6], *err = sum e^T M e */
+int b2r_gicp_linearize_at(b2r_handle* h, const double T[16], double* H, double* b, double* err);
+/* one compute_error at pose T with the correspondences of the last linearisation */
+int b2r_gicp_error_at(b2r_handle* h, const double T[16], double* err);
+/* NDT voxel table of the target: returns count through *n_voxels; arrays may be NULL.  keys ascending. */
+int b2r_ndt_get_voxels(b2r_handle* h, size_t capacity, size_t* n_voxels, int64_t* keys, int32_t* npts, double* mean, double* icov,
+                       int32_t min_b[3], int32_t div_b[3]);
+/* one computeDerivatives pass at p = (tx,ty,tz,rx,ry,rz): score, g[6], H[36] row-major, number of (point,cell) pairs */
+int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* score, double* g, double* H, uint64_t* n_pairs);
+
+/* ---- companion: voxel-grid downsample ---------------------------------------------------------------------------
+ * replaces pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(leaf,leaf,leaf) (apps/prefiltering_nodelet.cpp:54-58,138-149;
+ * apps/scan_matching_odometry_nodelet.cpp:86-90,147-157).  in/out records are `stride_bytes` long with intensity at byte
+ * offset 16 when stride_bytes >= 20.  out must hold n records; *n_out receives the voxel count; out_keys/out_counts
+ * (capacity n) may be NULL.  Returns 1 (and passes the input through) when the leaf is too small for int32 indices. */
+int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out, size_t* n_out,
+                  int32_t* out_keys, int32_t* out_counts);
+
+/* ---- host mirrors of the two callers (logic identical to the reference; only the handle is ours) ---------------- */
+typedef struct b2r_odometry b2r_odometry;
+typedef struct b2r_odometry_params {
+  double keyframe_delta_trans;  /* scan_matching_odometry_nodelet.cpp:74 (0.25; 1.0 in hdl_graph_slam.launch:63) */
+  double keyframe_delta_angle;  /* :75 */
+  double keyframe_delta_time;   /* :76 */
+  int32_t transform_thresholding; /* :79 */
+  double max_acceptable_trans;  /* :80 */
+  double max_acceptable_angle;  /* :81 */
+  int32_t publish_status;       /* 1: also compute fitness + inlier fraction each frame (status topic subscribed, :298-335) */
+} b2r_odometry_params;
+typedef struct b2r_odometry_status {
+  float odom[16];           /* keyframe_pose * trans, column-major (return value of matching(), :165-262) */
+  float trans[16];          /* getFinalTransformation() of this frame */
+  int32_t converged;
+  int32_t iterations;
+  int32_t keyframe_updated;
+  int32_t frame_rejected;   /* not converged or thresholded (:214-233) */
+  double matching_error;    /* getFitnessScore()          (status only) */
+  float inlier_fraction;    /* (status only) */
+  int32_t reserved;
+} b2r_odometry_status;
+int b2r_odometry_create(b2r_handle* registration, const b2r_odometry_params* p, b2r_odometry** out);
+void b2r_odometry_destroy(b2r_odometry* o);
+/* ScanMatchingOdometryNodelet::matching(stamp, cloud) (apps/scan_matching_odometry_nodelet.cpp:165-262);
+ * msf_delta may be NULL (identity). */
+int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes, const float* msf_delta,
+                          b2r_odometry_status* out);
+
+/* LoopDetector::matching (include/hdl_graph_slam/loop_detector.hpp:117-171): align every candidate against the new
+ * keyframe, keep the best converged fitness.  guesses: n_candidates x 16 floats, column-major (already z-zeroed by the
+ * caller as in :141-142).  results (n_candidates, may be NULL) receives every candidate's record.
+ * *best = index of the best candidate or -1 ("loop not found"). */
+int b2r_loop_matching(b2r_handle* h, const void* new_keyframe, size_t n_new, size_t stride_bytes, const void* const* candidates,
+                      const size_t* n_candidates_pts, size_t n_candidates, const float* guesses, double fitness_score_max_range,
+                      double fitness_score_thresh, b2r_result* results, int32_t* best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
