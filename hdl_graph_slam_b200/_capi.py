@@ -55,6 +55,7 @@ SYMBOLS = [
     ("b2r_set_target_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_set_source_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_promote_source_to_target", C.c_int, [_VP]),
+    ("b2r_synchronize", C.c_int, [_VP]),
     ("b2r_align", C.c_int, [_VP, _F32P, C.POINTER(Result)]),
     ("b2r_get_aligned", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_fitness", C.c_int, [_VP, _F32P, C.c_double, C.c_float, _F64P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

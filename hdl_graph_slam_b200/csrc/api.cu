@@ -160,6 +160,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  h->ndt_work.scr = &h->scr;
   *out = h;
   return B2R_OK;
 }
@@ -301,6 +302,13 @@ extern "C" int b2r_set_target(b2r_handle* h, const void* p, size_t n, size_t s) 
 extern "C" int b2r_set_source(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, false, p, n, s, false); }
 extern "C" int b2r_set_target_device(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, true, p, n, s, true); }
 extern "C" int b2r_set_source_device(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, false, p, n, s, true); }
+
+extern "C" int b2r_synchronize(b2r_handle* h) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  return B2R_OK;
+}
 
 extern "C" int b2r_promote_source_to_target(b2r_handle* h) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
@@ -635,7 +643,7 @@ extern "C" int b2r_ndt_get_voxels(b2r_handle* h, size_t capacity, size_t* n_voxe
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   int rc = ndt_ensure_map(h->cfg, TGT(h), h->ndt_work, h->st);
   if (rc) return rc;
-  return ndt_dump(TGT(h), h->st, capacity, n_voxels, keys, npts, mean, icov, min_b, div_b);
+  return ndt_dump(TGT(h), h->ndt_work, h->st, capacity, n_voxels, keys, npts, mean, icov, min_b, div_b);
 }
 
 extern "C" int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* score, double* g, double* H, uint64_t* n_pairs) {

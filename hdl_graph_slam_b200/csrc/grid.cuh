@@ -9,11 +9,12 @@
 
 namespace b2r {
 
-constexpr int kCellCap = 1 << 22;          // dense cell table capacity (16 MB of int32)
+constexpr int kCellCap = 1 << 23;          // dense cell table capacity (32 MB of int32)
 constexpr int kScanItems = 8;              // cells per thread in the scan
 constexpr int kScanThreads = 256;
 constexpr int kScanTile = kScanItems * kScanThreads;  // 2048 cells per block
-constexpr int kScanBlocks = kCellCap / kScanTile;     // 2048
+constexpr int kScanBlocks = kCellCap / kScanTile;     // 4096
+constexpr int kScanBPerThread = kScanBlocks / 1024;   // block sums handled per thread in phase B
 
 struct GridBuffers {
   Grid* grid;        // device Grid
@@ -168,12 +169,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_a(const int* __restrict__
 
 __global__ void __launch_bounds__(1024) k_scan_b(int* bsum, Grid* gp, int* cell_start) {
   __shared__ int sm[40];
-  // kScanBlocks == 2048 entries, 2 per thread
-  int a = bsum[threadIdx.x * 2], b = bsum[threadIdx.x * 2 + 1];
+  int v[kScanBPerThread];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanBPerThread; k++) { v[k] = bsum[threadIdx.x * kScanBPerThread + k]; s += v[k]; }
   int total;
-  int ex = block_excl_scan(a + b, sm, total);
-  bsum[threadIdx.x * 2] = ex;
-  bsum[threadIdx.x * 2 + 1] = ex + a;
+  int ex = block_excl_scan(s, sm, total);
+#pragma unroll
+  for (int k = 0; k < kScanBPerThread; k++) { bsum[threadIdx.x * kScanBPerThread + k] = ex; ex += v[k]; }
   if (threadIdx.x == 0) {
     gp->n_valid = total;
     cell_start[gp->ncell] = total;

@@ -1,12 +1,908 @@
-// ndt.cuh — STUB (replaced below in this round)
+// ndt.cuh — NDT kernels and host driver.
+//
+// Re-creates, B200-first, pclomp::NormalDistributionsTransform + pclomp::VoxelGridCovariance (koide3/ndt_omp; SURVEY.md
+// A.2/A.3) — the reference factory's default engine (/root/reference/src/hdl_graph_slam/registrations.cpp:26,101-120):
+//   ndt_build_map (k_vox_*)   <- setInputTarget -> VoxelGridCovariance::filter/applyFilter (voxel Gaussians: mean, cov, icov)
+//   k_ndt_derivatives         <- computeDerivatives + computePointDerivatives + updateDerivatives, DIRECT1 / DIRECT7
+//                                (sum of full Gaussians of the containing cell and its 6 face neighbours, NOT trilinear)
+//   k_ndt_hessian             <- computeHessian / updateHessian (float64 path, reached only when the More-Thuente loop ran)
+//   ndt_align                 <- computeTransformation + computeStepLengthMT (+ trialValueSelectionMT / updateIntervalMT)
+// Per-(point,cell) math is float32 in exactly the operation order of oracle/ndt.cpp::ndt_point_cell (non-contracted
+// intrinsics), exp as (float)exp((double)x); accumulation float64 with a fixed reduction tree.
 #pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
 #include "engine.cuh"
+#include "gicp.cuh"  // block_reduce / finish_partials
+#include "linalg.cuh"
+
 namespace b2r {
-struct NdtVoxelMap {};
-struct NdtWork { void release() {} };
-inline void ndt_free_map(NdtVoxelMap*) {}
-inline int ndt_ensure_map(const b2r_config&, Cloud&, NdtWork&, cudaStream_t) { return fail(B2R_EUNSUPPORTED, "ndt stub"); }
-inline int ndt_dump(Cloud&, cudaStream_t, size_t, size_t*, int64_t*, int32_t*, double*, double*, int32_t*, int32_t*) { return fail(B2R_EUNSUPPORTED, "ndt stub"); }
-inline int ndt_derivatives_at(const b2r_config&, Cloud&, Cloud&, NdtWork&, cudaStream_t, const double*, double*, double*, double*, uint64_t*) { return fail(B2R_EUNSUPPORTED, "ndt stub"); }
-inline int ndt_align(const b2r_config&, Cloud&, Cloud&, NdtWork&, cudaStream_t, const float*, float*, bool*, int*) { return fail(B2R_EUNSUPPORTED, "ndt stub"); }
+
+struct VoxGeom {
+  float leaf, inv_leaf;
+  int min_b[3], max_b[3], div_b[3];
+  int ok;       // 0: dense table would exceed kCellCap
+  int empty;    // no finite points
+};
+
+struct __align__(16) NdtVoxel {
+  double mean[3];
+  double icov[9];
+  int npts;     // number of points, -1 = invalidated (bad eigenvalues / infinite icov)
+  int pad[3];
+};  // 112 bytes
+
+struct NdtVoxelMap {
+  VoxGeom* geom = nullptr;      // device
+  VoxGeom h_geom;               // host copy (valid after ndt_sync_geom)
+  bool h_geom_valid = false;
+  Grid* grid = nullptr;         // device (ncell / n_valid for the shared scan kernels)
+  DevBuf<int> cell_start;       // ncell + 1
+  DevBuf<float4> sorted;        // (x,y,z,bits(idx)) ascending (voxel key, index)
+  DevBuf<int> pos_of;
+  DevBuf<NdtVoxel> vox;         // record of a voxel lives at the sorted position of its first point
+  size_t n = 0;
+};
+
+struct NdtWork {
+  DevBuf<double> partials;
+  double* d_out = nullptr;        // 64 doubles
+  unsigned int* d_counter = nullptr;
+  double* h_out = nullptr;        // pinned
+  VoxGeom* h_geom_pinned = nullptr;
+  unsigned long long* d_pairs = nullptr;
+  Scratch* scr = nullptr;         // shared build scratch of the handle (set by ndt_ensure_map's caller)
+  Scratch own;                    // used when no shared scratch is provided
+  bool own_init = false;
+  void release() {
+    partials.release();
+    if (d_out) cudaFree(d_out);
+    if (d_counter) cudaFree(d_counter);
+    if (h_out) cudaFreeHost(h_out);
+    if (h_geom_pinned) cudaFreeHost(h_geom_pinned);
+    if (d_pairs) cudaFree(d_pairs);
+    if (own_init) {
+      cudaFree(own.mm); cudaFree(own.counts); cudaFree(own.cursor); cudaFree(own.bsum);
+      own.cell_of.release(); own.tmp_idx.release();
+    }
+    d_out = nullptr; d_counter = nullptr; h_out = nullptr; h_geom_pinned = nullptr; d_pairs = nullptr; own_init = false;
+  }
+};
+
+inline void ndt_free_map(NdtVoxelMap* m) {
+  if (!m) return;
+  if (m->geom) cudaFree(m->geom);
+  if (m->grid) cudaFree(m->grid);
+  m->cell_start.release(); m->sorted.release(); m->pos_of.release(); m->vox.release();
+  delete m;
 }
+
+// ------------------------------------------------------------------------------------------------ voxel build kernels
+// VoxelGridCovariance::applyFilter geometry (A.3): min_b = floor(min_p * inv_leaf) ...
+__global__ void k_vox_params(const int* mm, VoxGeom* vg, Grid* g, int n, float leaf) {
+  VoxGeom V;
+  V.leaf = leaf;
+  V.inv_leaf = 1.0f / leaf;
+  V.ok = 1;
+  V.empty = 0;
+  Grid G;
+  G.ox = G.oy = G.oz = 0.f; G.h = leaf; G.inv_h = V.inv_leaf; G.n = n; G.n_valid = 0; G.pad = 0;
+  if (n <= 0 || mm[0] == 0x7fffffff) {
+    V.empty = 1;
+    for (int d = 0; d < 3; d++) { V.min_b[d] = 0; V.max_b[d] = 0; V.div_b[d] = 1; }
+    G.nx = G.ny = G.nz = 1; G.ncell = 1;
+    *vg = V; *g = G;
+    return;
+  }
+  double cells = 1.0;
+  for (int d = 0; d < 3; d++) {
+    float mn = ord2f(mm[d]), mx = ord2f(mm[3 + d]);
+    float a = floorf(fmul(mn, V.inv_leaf)), b = floorf(fmul(mx, V.inv_leaf));
+    if (!(a > -1.0e9f && b < 1.0e9f)) { V.ok = 0; a = 0.f; b = 0.f; }
+    V.min_b[d] = (int)a;
+    V.max_b[d] = (int)b;
+    V.div_b[d] = V.max_b[d] - V.min_b[d] + 1;
+    cells *= (double)V.div_b[d];
+  }
+  if (cells > (double)kCellCap) V.ok = 0;
+  if (V.ok) { G.nx = V.div_b[0]; G.ny = V.div_b[1]; G.nz = V.div_b[2]; G.ncell = G.nx * G.ny * G.nz; }
+  else { G.nx = G.ny = G.nz = 1; G.ncell = 1; }
+  *vg = V; *g = G;
+}
+
+__device__ __forceinline__ int vox_cell_of_point(const VoxGeom& V, float x, float y, float z) {
+  // ijk = (int)(floor(p * inv_leaf) - (float)min_b)   (float32, as in VoxelGridCovariance / VoxelGrid)
+  int i0 = (int)fsub(floorf(fmul(x, V.inv_leaf)), (float)V.min_b[0]);
+  int i1 = (int)fsub(floorf(fmul(y, V.inv_leaf)), (float)V.min_b[1]);
+  int i2 = (int)fsub(floorf(fmul(z, V.inv_leaf)), (float)V.min_b[2]);
+  i0 = clampi(i0, 0, V.div_b[0] - 1); i1 = clampi(i1, 0, V.div_b[1] - 1); i2 = clampi(i2, 0, V.div_b[2] - 1);
+  return i0 + i1 * V.div_b[0] + i2 * V.div_b[0] * V.div_b[1];
+}
+
+__global__ void k_count_vox(const float* __restrict__ raw, int stride_f, int n, const VoxGeom* __restrict__ vg, int* counts, int* cell_of) {
+  const VoxGeom V = *vg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* p = raw + (size_t)i * stride_f;
+    float x = p[0], y = p[1], z = p[2];
+    int c = -1;
+    if (finite3(x, y, z)) {
+      c = V.ok ? vox_cell_of_point(V, x, y, z) : 0;
+      atomicAdd(&counts[c], 1);
+    }
+    cell_of[i] = c;
+  }
+}
+
+// One thread per voxel (the thread whose sorted position is the voxel's first point): sequential float64 moments in
+// ascending point index, then the finalisation of VoxelGridCovariance::applyFilter.
+__global__ void k_vox_finalize(const Grid* __restrict__ gp, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
+                               const float4* __restrict__ sorted, NdtVoxel* vox, int n) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= gp->n_valid) return;
+  const float4 p0 = sorted[s];
+  const int c = cell_of[idx_bits(p0.w)];
+  const int b = cell_start[c];
+  if (b != s) return;
+  const int e = cell_start[c + 1];
+  const int cnt = e - b;
+  double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
+  for (int j = b; j < e; j++) {
+    const float4 p = sorted[j];
+    const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
+    sx += x; sy += y; sz += z;
+    // products of two float32 values are exact in float64, so contraction cannot change these sums
+    cxx += x * x; cxy += x * y; cxz += x * z; cyy += y * y; cyz += y * z; czz += z * z;
+  }
+  NdtVoxel R;
+  const double nn = (double)cnt;
+  R.mean[0] = sx / nn; R.mean[1] = sy / nn; R.mean[2] = sz / nn;
+  R.npts = cnt;
+  R.pad[0] = R.pad[1] = R.pad[2] = 0;
+  for (int k = 0; k < 9; k++) R.icov[k] = 0.0;
+  if (cnt >= 6) {
+    const double S[3] = {sx, sy, sz};
+    const double S2[9] = {cxx, cxy, cxz, cxy, cyy, cyz, cxz, cyz, czz};
+    double cov[9];
+    const double f = __ddiv_rn(__dsub_rn(nn, 1.0), nn);
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int bb = 0; bb < 3; bb++) {
+        // cov = (S2 - 2*(sum*mean^T))/n + mean*mean^T ; cov *= (n-1)/n       (non-contracted, as the oracle)
+        double t = __dmul_rn(2.0, __dmul_rn(S[a], R.mean[bb]));
+        t = __ddiv_rn(__dsub_rn(S2[a * 3 + bb], t), nn);
+        t = __dadd_rn(t, __dmul_rn(R.mean[a], R.mean[bb]));
+        cov[a * 3 + bb] = __dmul_rn(t, f);
+      }
+    double w[3], V[9];
+    sym_eigen3(cov, w, V);
+    if (w[0] < 0 || w[1] < 0 || w[2] <= 0) {
+      R.npts = -1;
+    } else {
+      const double minv = 0.01 * w[2];
+      if (w[0] < minv) {
+        w[0] = minv;
+        if (w[1] < minv) w[1] = minv;
+        double Vi[9], VD[9];
+        inv3(V, Vi);
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int bb = 0; bb < 3; bb++) VD[a * 3 + bb] = V[a * 3 + bb] * w[bb];
+        mul3(VD, Vi, cov);
+      }
+      inv3(cov, R.icov);
+      double mxv = -INFINITY, mnv = INFINITY;
+      bool nan_in = false;
+#pragma unroll
+      for (int a = 0; a < 9; a++) { mxv = fmax(mxv, R.icov[a]); mnv = fmin(mnv, R.icov[a]); nan_in |= (R.icov[a] != R.icov[a]); }
+      if (mxv == INFINITY || mnv == -INFINITY || nan_in) R.npts = -1;
+    }
+  }
+  vox[s] = R;
+}
+
+// ------------------------------------------------------------------------------------------------ derivative kernel
+constexpr int kNdtThreads = 128;
+constexpr int kNdtAcc = 43;  // score, g[6], H[36]
+
+struct NdtArgs {
+  const float* src_raw;
+  int src_stride_f;
+  int n;
+  const VoxGeom* geom;
+  const int* cell_start;
+  const NdtVoxel* vox;
+  float Tf[12];
+  float jang[8][3];
+  float hang[15][3];
+  double jang_d[8][3];
+  double hang_d[15][3];
+  double d1, d2;
+  int ncell_search;  // 1 or 7
+  int compute_hessian;
+  double* partials;
+  double* out;
+  unsigned int* counter;
+  unsigned long long* pairs;
+};
+
+__device__ __forceinline__ float dot3f(const float* a, float x, float y, float z) {
+  return fadd(fadd(fmul(a[0], x), fmul(a[1], y)), fmul(a[2], z));
+}
+
+__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+
+__global__ void __launch_bounds__(kNdtThreads) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
+  __shared__ double red[kNdtAcc * 32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[kNdtAcc];
+#pragma unroll
+  for (int k = 0; k < kNdtAcc; k++) acc[k] = 0.0;
+  unsigned int npairs = 0;
+  if (i < A.n) {
+    const VoxGeom V = *A.geom;
+    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
+    const float x = p[0], y = p[1], z = p[2];
+    const float xt = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], x, y, z);
+    const float yt = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], x, y, z);
+    const float zt = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], x, y, z);
+    if (!V.empty && V.ok && finite3(xt, yt, zt)) {
+      // getNeighborhoodAtPoint{1,7}: ijk = floor(pt / leaf)   (float32 DIVISION here, multiply-by-inverse at build)
+      const float fi = floorf(__fdiv_rn(xt, V.leaf)), fj = floorf(__fdiv_rn(yt, V.leaf)), fk = floorf(__fdiv_rn(zt, V.leaf));
+      if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f && fabsf(fk) < 1.0e9f) {
+        const int ci = (int)fi, cj = (int)fj, ck = (int)fk;
+        bool have_pd = false;
+        float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
+        float ha1 = 0, ha2 = 0, hb1 = 0, hb2 = 0, hc1 = 0, hc2 = 0, hd0 = 0, hd1 = 0, hd2 = 0, he0 = 0, he1 = 0, he2 = 0, hf0 = 0, hf1 = 0, hf2 = 0;
+        const float d2f = (float)A.d2;
+        for (int c = 0; c < A.ncell_search; c++) {
+          const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
+          if (cx < V.min_b[0] || cx > V.max_b[0] || cy < V.min_b[1] || cy > V.max_b[1] || cz < V.min_b[2] || cz > V.max_b[2]) continue;
+          const int cell = (cx - V.min_b[0]) + (cy - V.min_b[1]) * V.div_b[0] + (cz - V.min_b[2]) * V.div_b[0] * V.div_b[1];
+          const int s = A.cell_start[cell], e = A.cell_start[cell + 1];
+          if (e - s < 6) continue;
+          const NdtVoxel* L = A.vox + s;
+          if (L->npts < 6) continue;
+          npairs++;
+          if (!have_pd) {  // computePointDerivatives(x): original point only
+            j13 = dot3f(A.jang[0], x, y, z); j23 = dot3f(A.jang[1], x, y, z);
+            j04 = dot3f(A.jang[2], x, y, z); j14 = dot3f(A.jang[3], x, y, z); j24 = dot3f(A.jang[4], x, y, z);
+            j05 = dot3f(A.jang[5], x, y, z); j15 = dot3f(A.jang[6], x, y, z); j25 = dot3f(A.jang[7], x, y, z);
+            if (A.compute_hessian) {
+              ha1 = dot3f(A.hang[0], x, y, z); ha2 = dot3f(A.hang[1], x, y, z);
+              hb1 = dot3f(A.hang[2], x, y, z); hb2 = dot3f(A.hang[3], x, y, z);
+              hc1 = dot3f(A.hang[4], x, y, z); hc2 = dot3f(A.hang[5], x, y, z);
+              hd0 = dot3f(A.hang[6], x, y, z); hd1 = dot3f(A.hang[7], x, y, z); hd2 = dot3f(A.hang[8], x, y, z);
+              he0 = dot3f(A.hang[9], x, y, z); he1 = dot3f(A.hang[10], x, y, z); he2 = dot3f(A.hang[11], x, y, z);
+              hf0 = dot3f(A.hang[12], x, y, z); hf1 = dot3f(A.hang[13], x, y, z); hf2 = dot3f(A.hang[14], x, y, z);
+            }
+            have_pd = true;
+          }
+          const float q0 = (float)((double)xt - L->mean[0]), q1 = (float)((double)yt - L->mean[1]), q2 = (float)((double)zt - L->mean[2]);
+          float C[9];
+#pragma unroll
+          for (int k = 0; k < 9; k++) C[k] = (float)L->icov[k];
+          // qC = q^T C ; gq[0..2] == qC
+          float gq[6];
+#pragma unroll
+          for (int j = 0; j < 3; j++) gq[j] = fadd(fadd(fmul(q0, C[0 * 3 + j]), fmul(q1, C[1 * 3 + j])), fmul(q2, C[2 * 3 + j]));
+          const float qCq = fadd(fadd(fmul(q0, gq[0]), fmul(q1, gq[1])), fmul(q2, gq[2]));
+          const float arg = fmul(fmul(-d2f, qCq), 0.5f);
+          float ex = (float)exp((double)arg);
+          const float score_inc = (float)(-A.d1 * (double)ex);
+          ex = fmul(d2f, ex);
+          if (ex > 1.f || ex < 0.f || ex != ex) continue;  // contributes nothing (score_inc dropped as well)
+          ex = (float)((double)ex * A.d1);
+          // CJ columns 3..5 (columns 0..2 are C itself)
+          float CJ3[3], CJ4[3], CJ5[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            CJ3[r] = fadd(fmul(C[r * 3 + 1], j13), fmul(C[r * 3 + 2], j23));
+            CJ4[r] = fadd(fadd(fmul(C[r * 3 + 0], j04), fmul(C[r * 3 + 1], j14)), fmul(C[r * 3 + 2], j24));
+            CJ5[r] = fadd(fadd(fmul(C[r * 3 + 0], j05), fmul(C[r * 3 + 1], j15)), fmul(C[r * 3 + 2], j25));
+          }
+          gq[3] = fadd(fadd(fmul(q0, CJ3[0]), fmul(q1, CJ3[1])), fmul(q2, CJ3[2]));
+          gq[4] = fadd(fadd(fmul(q0, CJ4[0]), fmul(q1, CJ4[1])), fmul(q2, CJ4[2]));
+          gq[5] = fadd(fadd(fmul(q0, CJ5[0]), fmul(q1, CJ5[1])), fmul(q2, CJ5[2]));
+          acc[0] += (double)score_inc;
+#pragma unroll
+          for (int k = 0; k < 6; k++) acc[1 + k] += (double)fmul(ex, gq[k]);
+          if (A.compute_hessian) {
+            // P[a][b] = J[:,a] . CJ[:,b]
+            // CJ[r][b]: b<3 -> C[r][b]; b=3 -> CJ3[r]; b=4 -> CJ4[r]; b=5 -> CJ5[r]
+#define B2R_CJ(r, b) ((b) < 3 ? C[(r) * 3 + (b)] : ((b) == 3 ? CJ3[r] : ((b) == 4 ? CJ4[r] : CJ5[r])))
+            float P[6][6];
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+              P[0][b] = B2R_CJ(0, b);
+              P[1][b] = B2R_CJ(1, b);
+              P[2][b] = B2R_CJ(2, b);
+              P[3][b] = fadd(fmul(j13, B2R_CJ(1, b)), fmul(j23, B2R_CJ(2, b)));
+              P[4][b] = fadd(fadd(fmul(j04, B2R_CJ(0, b)), fmul(j14, B2R_CJ(1, b))), fmul(j24, B2R_CJ(2, b)));
+              P[5][b] = fadd(fadd(fmul(j05, B2R_CJ(0, b)), fmul(j15, B2R_CJ(1, b))), fmul(j25, B2R_CJ(2, b)));
+            }
+#undef B2R_CJ
+            // second-derivative terms qC . v_ij  (i,j in 3..5); a=(0,ha1,ha2) b=(0,hb1,hb2) c=(0,hc1,hc2) d,e,f full
+            const float xa = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], ha1)), fmul(gq[2], ha2));
+            const float xb = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hb1)), fmul(gq[2], hb2));
+            const float xc = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hc1)), fmul(gq[2], hc2));
+            const float xd = fadd(fadd(fmul(gq[0], hd0), fmul(gq[1], hd1)), fmul(gq[2], hd2));
+            const float xe = fadd(fadd(fmul(gq[0], he0), fmul(gq[1], he1)), fmul(gq[2], he2));
+            const float xf = fadd(fadd(fmul(gq[0], hf0), fmul(gq[1], hf1)), fmul(gq[2], hf2));
+            const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
+#pragma unroll
+            for (int ii = 0; ii < 6; ii++) {
+#pragma unroll
+              for (int jj = 0; jj < 6; jj++) {
+                float u = fmul(fmul(-d2f, gq[ii]), gq[jj]);
+                const float xh = (ii >= 3 && jj >= 3) ? XH[ii - 3][jj - 3] : 0.f;
+                u = fadd(u, xh);
+                u = fadd(u, P[jj][ii]);
+                acc[7 + ii * 6 + jj] += (double)fmul(ex, u);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  // pair count (integer, exact) through a warp reduction + one atomic per warp
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+  if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
+  block_reduce<kNdtAcc>(acc, red);
+  finish_partials<kNdtAcc>(acc, A.partials, A.out, A.counter);
+}
+
+// float64 Hessian-only pass (ndt_omp computeHessian/updateHessian)
+__global__ void __launch_bounds__(kNdtThreads) k_ndt_hessian(const __grid_constant__ NdtArgs A) {
+  __shared__ double red[36 * 32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.0;
+  if (i < A.n) {
+    const VoxGeom V = *A.geom;
+    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
+    const float xf = p[0], yf = p[1], zf = p[2];
+    const float xt = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], xf, yf, zf);
+    const float yt = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], xf, yf, zf);
+    const float zt = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], xf, yf, zf);
+    if (!V.empty && V.ok && finite3(xt, yt, zt)) {
+      const float fi = floorf(__fdiv_rn(xt, V.leaf)), fj = floorf(__fdiv_rn(yt, V.leaf)), fk = floorf(__fdiv_rn(zt, V.leaf));
+      if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f && fabsf(fk) < 1.0e9f) {
+        const int ci = (int)fi, cj = (int)fj, ck = (int)fk;
+        const double x = (double)xf, y = (double)yf, z = (double)zf;
+        double J[3][6] = {{1, 0, 0, 0, 0, 0}, {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}};
+#define B2R_DJ(r) (x * A.jang_d[r][0] + y * A.jang_d[r][1] + z * A.jang_d[r][2])
+#define B2R_DH(r) (x * A.hang_d[r][0] + y * A.hang_d[r][1] + z * A.hang_d[r][2])
+        J[1][3] = B2R_DJ(0); J[2][3] = B2R_DJ(1); J[0][4] = B2R_DJ(2); J[1][4] = B2R_DJ(3); J[2][4] = B2R_DJ(4);
+        J[0][5] = B2R_DJ(5); J[1][5] = B2R_DJ(6); J[2][5] = B2R_DJ(7);
+        const double va[3] = {0, B2R_DH(0), B2R_DH(1)}, vb[3] = {0, B2R_DH(2), B2R_DH(3)}, vc[3] = {0, B2R_DH(4), B2R_DH(5)};
+        const double vd[3] = {B2R_DH(6), B2R_DH(7), B2R_DH(8)}, ve[3] = {B2R_DH(9), B2R_DH(10), B2R_DH(11)}, vf[3] = {B2R_DH(12), B2R_DH(13), B2R_DH(14)};
+#undef B2R_DJ
+#undef B2R_DH
+        for (int c = 0; c < A.ncell_search; c++) {
+          const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
+          if (cx < V.min_b[0] || cx > V.max_b[0] || cy < V.min_b[1] || cy > V.max_b[1] || cz < V.min_b[2] || cz > V.max_b[2]) continue;
+          const int cell = (cx - V.min_b[0]) + (cy - V.min_b[1]) * V.div_b[0] + (cz - V.min_b[2]) * V.div_b[0] * V.div_b[1];
+          const int s = A.cell_start[cell], e = A.cell_start[cell + 1];
+          if (e - s < 6) continue;
+          const NdtVoxel* L = A.vox + s;
+          if (L->npts < 6) continue;
+          const double q[3] = {(double)xt - L->mean[0], (double)yt - L->mean[1], (double)zt - L->mean[2]};
+          const double* C = L->icov;
+          double Cq[3];
+          for (int r = 0; r < 3; r++) Cq[r] = C[r * 3 + 0] * q[0] + C[r * 3 + 1] * q[1] + C[r * 3 + 2] * q[2];
+          double ex = A.d2 * exp(-A.d2 * (q[0] * Cq[0] + q[1] * Cq[1] + q[2] * Cq[2]) / 2);
+          if (ex > 1 || ex < 0 || ex != ex) continue;
+          ex *= A.d1;
+          double CJ[3][6], qCJ[6];
+          for (int r = 0; r < 3; r++)
+            for (int k = 0; k < 6; k++) CJ[r][k] = C[r * 3 + 0] * J[0][k] + C[r * 3 + 1] * J[1][k] + C[r * 3 + 2] * J[2][k];
+          for (int k = 0; k < 6; k++) qCJ[k] = q[0] * CJ[0][k] + q[1] * CJ[1][k] + q[2] * CJ[2][k];
+#pragma unroll
+          for (int ii = 0; ii < 6; ii++)
+#pragma unroll
+            for (int jj = 0; jj < 6; jj++) {
+              double xh = 0;
+              if (ii >= 3 && jj >= 3) {
+                const int key = (ii - 3) * 3 + (jj - 3);
+                const double* v = (key == 0) ? va : (key == 1 || key == 3) ? vb : (key == 2 || key == 6) ? vc : (key == 4) ? vd : (key == 5 || key == 7) ? ve : vf;
+                double Cv[3];
+                for (int r = 0; r < 3; r++) Cv[r] = C[r * 3 + 0] * v[0] + C[r * 3 + 1] * v[1] + C[r * 3 + 2] * v[2];
+                xh = q[0] * Cv[0] + q[1] * Cv[1] + q[2] * Cv[2];
+              }
+              const double jcj = J[0][jj] * CJ[0][ii] + J[1][jj] * CJ[1][ii] + J[2][jj] * CJ[2][ii];
+              acc[ii * 6 + jj] += ex * (-A.d2 * qCJ[ii] * qCJ[jj] + xh + jcj);
+            }
+        }
+      }
+    }
+  }
+  block_reduce<36>(acc, red);
+  finish_partials<36>(acc, A.partials, A.out, A.counter);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline int ndt_init_work(NdtWork& W) {
+  if (W.d_out) return B2R_OK;
+  B2R_CUDA(cudaMalloc(&W.d_out, 64 * sizeof(double)));
+  B2R_CUDA(cudaMalloc(&W.d_counter, 4 * sizeof(unsigned int)));
+  B2R_CUDA(cudaMemset(W.d_counter, 0, 4 * sizeof(unsigned int)));
+  B2R_CUDA(cudaMalloc(&W.d_pairs, sizeof(unsigned long long)));
+  B2R_CUDA(cudaMallocHost(&W.h_out, 64 * sizeof(double)));
+  B2R_CUDA(cudaMallocHost(&W.h_geom_pinned, sizeof(VoxGeom)));
+  return B2R_OK;
+}
+
+inline int ndt_ensure_map(const b2r_config& cfg, Cloud& c, NdtWork& W, cudaStream_t st) {
+  if (c.ndt_ready) return B2R_OK;
+  int rc = ndt_init_work(W);
+  if (rc) return rc;
+  Scratch* S = W.scr;
+  if (!S) return fail(B2R_ESTATE, "internal: NDT scratch not attached");
+  if (!c.ndt) {
+    c.ndt = new NdtVoxelMap();
+    B2R_CUDA(cudaMalloc(&c.ndt->geom, sizeof(VoxGeom)));
+    B2R_CUDA(cudaMalloc(&c.ndt->grid, sizeof(Grid)));
+    B2R_CUDA(c.ndt->cell_start.reserve(kCellCap + 1 - 72));
+  }
+  NdtVoxelMap& M = *c.ndt;
+  const int n = (int)c.n;
+  M.n = c.n;
+  M.h_geom_valid = false;
+  B2R_CUDA(M.sorted.reserve(c.n + 1));
+  B2R_CUDA(M.pos_of.reserve(c.n + 1));
+  B2R_CUDA(M.vox.reserve(c.n + 1));
+  B2R_CUDA(S->cell_of.reserve(c.n + 1));
+  B2R_CUDA(S->tmp_idx.reserve(c.n + 1));
+  k_grid_reset<<<1, 32, 0, st>>>(S->mm);
+  int nb = n > 0 ? (n + 255) / 256 : 1;
+  if (nb > 1184) nb = 1184;
+  if (n > 0) k_bbox<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, S->mm);
+  k_vox_params<<<1, 1, 0, st>>>(S->mm, M.geom, M.grid, n, (float)cfg.ndt_resolution);
+  if (n > 0) {
+    k_fill_i32<<<nb, 256, 0, st>>>(M.pos_of.p, n, -1);
+    k_count_vox<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.geom, S->counts, S->cell_of.p);
+  }
+  k_scan_a<<<kScanBlocks, kScanThreads, 0, st>>>(S->counts, M.grid, S->bsum);
+  k_scan_b<<<1, 1024, 0, st>>>(S->bsum, M.grid, M.cell_start.p);
+  k_scan_c<<<kScanBlocks, kScanThreads, 0, st>>>(S->counts, M.grid, S->bsum, M.cell_start.p, S->cursor);
+  if (n > 0) {
+    k_scatter<<<nb, 256, 0, st>>>(n, S->cell_of.p, S->cursor, S->tmp_idx.p);
+    k_canon<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.grid, S->cell_of.p, M.cell_start.p, S->tmp_idx.p, M.sorted.p, M.pos_of.p);
+    k_vox_finalize<<<(n + 127) / 128, 128, 0, st>>>(M.grid, S->cell_of.p, M.cell_start.p, M.sorted.p, M.vox.p, n);
+  }
+  B2R_CUDA(cudaGetLastError());
+  c.ndt_ready = true;
+  return B2R_OK;
+}
+
+inline int ndt_sync_geom(NdtVoxelMap& M, NdtWork& W, cudaStream_t st) {
+  if (M.h_geom_valid) return B2R_OK;
+  B2R_CUDA(cudaMemcpyAsync(W.h_geom_pinned, M.geom, sizeof(VoxGeom), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  M.h_geom = *W.h_geom_pinned;
+  M.h_geom_valid = true;
+  if (!M.h_geom.ok) return fail(B2R_EUNSUPPORTED, "NDT voxel grid exceeds the dense table capacity (extent / resolution too large)");
+  return B2R_OK;
+}
+
+inline int ndt_dump(Cloud& c, NdtWork& W, cudaStream_t st, size_t capacity, size_t* n_voxels, int64_t* keys, int32_t* npts, double* mean,
+                    double* icov, int32_t* min_b, int32_t* div_b) {
+  NdtVoxelMap& M = *c.ndt;
+  int rc = ndt_sync_geom(M, W, st);
+  if (rc) return rc;
+  Grid G;
+  B2R_CUDA(cudaMemcpyAsync(&G, M.grid, sizeof(Grid), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> cs((size_t)G.ncell + 1);
+  std::vector<NdtVoxel> vox(M.n + 1);
+  B2R_CUDA(cudaMemcpyAsync(cs.data(), M.cell_start.p, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (M.n) B2R_CUDA(cudaMemcpyAsync(vox.data(), M.vox.p, M.n * sizeof(NdtVoxel), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  size_t V = 0;
+  for (int cell = 0; cell < G.ncell; cell++) {
+    int s = cs[cell], e = cs[cell + 1];
+    if (e <= s) continue;
+    if (V < capacity) {
+      const NdtVoxel& L = vox[s];
+      if (keys) keys[V] = cell;
+      if (npts) npts[V] = L.npts;
+      if (mean) std::memcpy(mean + V * 3, L.mean, 3 * sizeof(double));
+      if (icov) std::memcpy(icov + V * 9, L.icov, 9 * sizeof(double));
+    }
+    V++;
+  }
+  *n_voxels = V;
+  if (min_b) for (int d = 0; d < 3; d++) min_b[d] = M.h_geom.empty ? 0 : M.h_geom.min_b[d];
+  if (div_b) for (int d = 0; d < 3; d++) div_b[d] = M.h_geom.empty ? 0 : M.h_geom.div_b[d];
+  return B2R_OK;
+}
+
+// ---- scalar pose algebra, float32 exactly as oracle/ndt.cpp (host libm on both sides)
+struct NdtScalars {
+  double d1, d2;
+  float jang[8][3], hang[15][3];
+  double jang_d[8][3], hang_d[15][3];
+};
+
+inline void ndt_gauss(const b2r_config& c, NdtScalars& K) {
+  double gauss_c1 = 10 * (1 - c.ndt_outlier_ratio);
+  double gauss_c2 = c.ndt_outlier_ratio / std::pow(c.ndt_resolution, 3);
+  double gauss_d3 = -std::log(gauss_c2);
+  K.d1 = -std::log(gauss_c1 + gauss_c2) - gauss_d3;
+  K.d2 = -2 * std::log((-std::log(gauss_c1 * std::exp(-0.5) + gauss_c2) - gauss_d3) / K.d1);
+}
+
+inline void ndt_angle_derivs(const double* p, NdtScalars& K) {
+  double cx, cy, cz, sx, sy, sz;
+  if (std::fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = std::cos(p[3]); sx = std::sin(p[3]); }
+  if (std::fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = std::cos(p[4]); sy = std::sin(p[4]); }
+  if (std::fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = std::cos(p[5]); sz = std::sin(p[5]); }
+  // Magnusson 2009 eq. 6.19 / 6.21
+  const double J[8][3] = {
+      {(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
+      {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
+      {(-sy * cz), sy * sz, cy},
+      {sx * cy * cz, (-sx * cy * sz), sx * sy},
+      {(-cx * cy * cz), cx * cy * sz, (-cx * sy)},
+      {(-cy * sz), (-cy * cz), 0},
+      {(cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0},
+      {(sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0}};
+  const double Hh[15][3] = {
+      {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy},
+      {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy)},
+      {(cx * cy * cz), (-cx * cy * sz), (cx * sy)},
+      {(sx * cy * cz), (-sx * cy * sz), (sx * sy)},
+      {(-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0},
+      {(cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0},
+      {(-cy * cz), (cy * sz), (sy)},
+      {(-sx * sy * cz), (sx * sy * sz), (sx * cy)},
+      {(cx * sy * cz), (-cx * sy * sz), (-cx * cy)},
+      {(sy * sz), (sy * cz), 0},
+      {(-sx * cy * sz), (-sx * cy * cz), 0},
+      {(cx * cy * sz), (cx * cy * cz), 0},
+      {(-cy * cz), (cy * sz), 0},
+      {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},
+      {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};
+  for (int r = 0; r < 8; r++)
+    for (int c = 0; c < 3; c++) { K.jang_d[r][c] = J[r][c]; K.jang[r][c] = (float)J[r][c]; }
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 3; c++) { K.hang_d[r][c] = Hh[r][c]; K.hang[r][c] = (float)Hh[r][c]; }
+}
+
+// Translation * AngleAxis(rx, X) * AngleAxis(ry, Y) * AngleAxis(rz, Z) in float32 (Eigen composition order, no FMA:
+// this translation unit is compiled for x86-64 without -mfma, host products are separate mul/add)
+inline void ndt_pose_to_matrix(const double* p, float* T) {
+  float ang[3] = {(float)p[3], (float)p[4], (float)p[5]};
+  float R[3][9];
+  for (int a = 0; a < 3; a++) {
+    float s = (float)std::sin((double)ang[a]);
+    float c = (float)std::cos((double)ang[a]);
+    float omc = 1.0f - c;
+    volatile float diag_axis_v = omc + c;
+    float diag_axis = diag_axis_v;
+    float m[9] = {c, 0, 0, 0, c, 0, 0, 0, c};
+    if (a == 0) { m[0] = diag_axis; m[5] = 0.f - s; m[7] = 0.f + s; }
+    if (a == 1) { m[4] = diag_axis; m[2] = 0.f + s; m[6] = 0.f - s; }
+    if (a == 2) { m[8] = diag_axis; m[1] = 0.f - s; m[3] = 0.f + s; }
+    std::memcpy(R[a], m, sizeof(m));
+  }
+  auto mm = [](const float* A, const float* B, float* O) {
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) {
+        volatile float u = A[r * 3 + 0] * B[0 * 3 + c];
+        volatile float v = A[r * 3 + 1] * B[1 * 3 + c];
+        volatile float w = u + v;
+        volatile float v2 = A[r * 3 + 2] * B[2 * 3 + c];
+        O[r * 3 + c] = w + v2;
+      }
+  };
+  float xy[9], xyz[9];
+  mm(R[0], R[1], xy);
+  mm(xy, R[2], xyz);
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) T[r * 4 + c] = xyz[r * 3 + c];
+    T[r * 4 + 3] = (float)p[r];
+  }
+  T[12] = T[13] = T[14] = 0.f;
+  T[15] = 1.f;
+}
+
+// Eigen 3.3 Matrix3f::eulerAngles(0,1,2), float32, first angle in [0, pi] (what the reference's distro Eigen does)
+inline void ndt_euler_xyz(const float* T, float* out) {
+  auto m = [&](int r, int c) { return T[r * 4 + c]; };
+  float res0 = std::atan2(m(1, 2), m(2, 2));
+  volatile float a2 = m(0, 0) * m(0, 0);
+  volatile float b2 = m(0, 1) * m(0, 1);
+  float c2 = std::sqrt(a2 + b2);
+  float res1;
+  if (res0 > 0.f) {
+    res0 -= (float)M_PI;
+    res1 = std::atan2(-m(0, 2), -c2);
+  } else {
+    res1 = std::atan2(-m(0, 2), c2);
+  }
+  float s1 = std::sin(res0), c1 = std::cos(res0);
+  volatile float n1 = s1 * m(2, 0);
+  volatile float n2 = c1 * m(1, 0);
+  volatile float d1 = c1 * m(1, 1);
+  volatile float d2 = s1 * m(2, 1);
+  float res2 = std::atan2(n1 - n2, d1 - d2);
+  out[0] = -res0; out[1] = -res1; out[2] = -res2;
+}
+
+// JacobiSVD(H).solve(rhs) for symmetric H: pseudo-inverse via a 6x6 cyclic Jacobi eigen-decomposition
+inline void ndt_svd6_solve(const double* H, const double* rhs, double* x) {
+  double A[36], V[36], w[6];
+  std::memcpy(A, H, sizeof(A));
+  bool nan_in = false;
+  for (int i = 0; i < 36; i++) nan_in |= (H[i] != H[i]);
+  for (int i = 0; i < 6; i++) nan_in |= (rhs[i] != rhs[i]);
+  if (nan_in) { for (int i = 0; i < 6; i++) x[i] = NAN; return; }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0;
+    for (int p = 0; p < 6; p++)
+      for (int q = p + 1; q < 6; q++) off += A[p * 6 + q] * A[p * 6 + q];
+    if (off == 0.0) break;
+    for (int p = 0; p < 6; p++)
+      for (int q = p + 1; q < 6; q++) {
+        double apq = A[p * 6 + q];
+        if (apq == 0.0) continue;
+        double app = A[p * 6 + p], aqq = A[q * 6 + q];
+        double theta = (aqq - app) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 6; k++) { double akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
+        for (int k = 0; k < 6; k++) { double apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
+        for (int k = 0; k < 6; k++) { double vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
+      }
+  }
+  for (int i = 0; i < 6; i++) w[i] = A[i * 6 + i];
+  for (int i = 0; i < 6; i++) {
+    int m = i;
+    for (int j = i + 1; j < 6; j++) if (w[j] < w[m]) m = j;
+    if (m != i) { std::swap(w[i], w[m]); for (int k = 0; k < 6; k++) std::swap(V[k * 6 + i], V[k * 6 + m]); }
+  }
+  double smax = 0;
+  for (int i = 0; i < 6; i++) smax = std::max(smax, std::fabs(w[i]));
+  double thr = std::max(smax * 6.0 * 2.220446049250313e-16, 2.2250738585072014e-308);
+  for (int i = 0; i < 6; i++) x[i] = 0.0;
+  for (int k = 0; k < 6; k++) {
+    if (!(std::fabs(w[k]) > thr)) continue;
+    double dot = 0;
+    for (int i = 0; i < 6; i++) dot += V[i * 6 + k] * rhs[i];
+    dot /= w[k];
+    for (int i = 0; i < 6; i++) x[i] += V[i * 6 + k] * dot;
+  }
+}
+
+struct NdtPass {
+  double score, g[6], H[36];
+  unsigned long long pairs;
+};
+
+inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& W, cudaStream_t st, const NdtScalars& K, const float* Tf_row,
+                        bool compute_hessian, bool hessian_only, NdtPass* out) {
+  NdtVoxelMap& M = *tgt.ndt;
+  NdtArgs A;
+  A.src_raw = src.raw_view; A.src_stride_f = src.stride_f; A.n = (int)src.n;
+  A.geom = M.geom; A.cell_start = M.cell_start.p; A.vox = M.vox.p;
+  for (int i = 0; i < 12; i++) A.Tf[i] = Tf_row[i];
+  std::memcpy(A.jang, K.jang, sizeof(A.jang)); std::memcpy(A.hang, K.hang, sizeof(A.hang));
+  std::memcpy(A.jang_d, K.jang_d, sizeof(A.jang_d)); std::memcpy(A.hang_d, K.hang_d, sizeof(A.hang_d));
+  A.d1 = K.d1; A.d2 = K.d2;
+  A.ncell_search = (cfg.ndt_search_method == 1) ? 1 : 7;
+  A.compute_hessian = compute_hessian ? 1 : 0;
+  const unsigned nb = (unsigned)((src.n + kNdtThreads - 1) / kNdtThreads);
+  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));
+  A.partials = W.partials.p; A.out = W.d_out; A.counter = W.d_counter; A.pairs = W.d_pairs;
+  if (hessian_only) {
+    k_ndt_hessian<<<nb, kNdtThreads, 0, st>>>(A);
+    B2R_CUDA(cudaGetLastError());
+    B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, 36 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    B2R_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(out->H, W.h_out, 36 * sizeof(double));
+    return B2R_OK;
+  }
+  B2R_CUDA(cudaMemsetAsync(W.d_pairs, 0, sizeof(unsigned long long), st));
+  k_ndt_derivatives<<<nb, kNdtThreads, 0, st>>>(A);
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, kNdtAcc * sizeof(double), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaMemcpyAsync(W.h_out + 48, W.d_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  out->score = W.h_out[0];
+  std::memcpy(out->g, W.h_out + 1, 6 * sizeof(double));
+  if (compute_hessian) std::memcpy(out->H, W.h_out + 7, 36 * sizeof(double));
+  std::memcpy(&out->pairs, W.h_out + 48, sizeof(unsigned long long));
+  return B2R_OK;
+}
+
+inline int ndt_derivatives_at(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& W, cudaStream_t st, const double* p, double* score,
+                              double* g, double* H, uint64_t* n_pairs) {
+  int rc = ndt_sync_geom(*tgt.ndt, W, st);
+  if (rc) return rc;
+  NdtScalars K;
+  ndt_gauss(cfg, K);
+  ndt_angle_derivs(p, K);
+  float Tf[16];
+  ndt_pose_to_matrix(p, Tf);
+  NdtPass P;
+  rc = ndt_run_pass(cfg, src, tgt, W, st, K, Tf, true, false, &P);
+  if (rc) return rc;
+  *score = P.score;
+  std::memcpy(g, P.g, sizeof(P.g));
+  std::memcpy(H, P.H, sizeof(P.H));
+  if (n_pairs) *n_pairs = P.pairs;
+  return B2R_OK;
+}
+
+// More-Thuente helpers (PCL ndt.hpp as copied by ndt_omp)
+inline double mt_psi(double a, double f_a, double f_0, double g_0, double mu) { return f_a - f_0 - mu * g_0 * a; }
+inline double mt_dpsi(double g_a, double g_0, double mu) { return g_a - mu * g_0; }
+inline double mt_trial(double a_l, double f_l, double g_l, double a_u, double f_u, double g_u, double a_t, double f_t, double g_t) {
+  if (f_t > f_l) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = std::sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_q = a_l - 0.5 * (a_l - a_t) * g_l / (g_l - (f_l - f_t) / (a_l - a_t));
+    return (std::fabs(a_c - a_l) < std::fabs(a_q - a_l)) ? a_c : 0.5 * (a_q + a_c);
+  } else if (g_t * g_l < 0) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = std::sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    return (std::fabs(a_c - a_t) >= std::fabs(a_s - a_t)) ? a_c : a_s;
+  } else if (std::fabs(g_t) <= std::fabs(g_l)) {
+    double z = 3 * (f_t - f_l) / (a_t - a_l) - g_t - g_l;
+    double w = std::sqrt(z * z - g_t * g_l);
+    double a_c = a_l + (a_t - a_l) * (w - g_l - z) / (g_t - g_l + 2 * w);
+    double a_s = a_l - (a_l - a_t) / (g_l - g_t) * g_l;
+    double a_t_next = (std::fabs(a_c - a_t) < std::fabs(a_s - a_t)) ? a_c : a_s;
+    return (a_t > a_l) ? std::min(a_t + 0.66 * (a_u - a_t), a_t_next) : std::max(a_t + 0.66 * (a_u - a_t), a_t_next);
+  }
+  double z = 3 * (f_t - f_u) / (a_t - a_u) - g_t - g_u;
+  double w = std::sqrt(z * z - g_t * g_u);
+  return a_u + (a_t - a_u) * (w - g_u - z) / (g_t - g_u + 2 * w);
+}
+inline bool mt_update(double& a_l, double& f_l, double& g_l, double& a_u, double& f_u, double& g_u, double a_t, double f_t, double g_t) {
+  if (f_t > f_l) { a_u = a_t; f_u = f_t; g_u = g_t; return false; }
+  if (g_t * (a_l - a_t) > 0) { a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+  if (g_t * (a_l - a_t) < 0) { a_u = a_l; f_u = f_l; g_u = g_l; a_l = a_t; f_l = f_t; g_l = g_t; return false; }
+  return true;
+}
+
+// pclomp::NormalDistributionsTransform::computeTransformation (A.2).  guess: column-major float (ABI); Tfinal: row-major.
+inline int ndt_align(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& W, cudaStream_t st, const float* guess_col, float* Tfinal,
+                     bool* converged_out, int* iters_out) {
+  for (int i = 0; i < 16; i++) Tfinal[i] = (i % 5 == 0) ? 1.f : 0.f;
+  *converged_out = false;
+  *iters_out = 0;
+  if (src.n == 0 || tgt.n == 0) return B2R_OK;  // initCompute fails silently
+  int rc = ndt_ensure_map(cfg, tgt, W, st);
+  if (rc) return rc;
+  rc = ndt_sync_geom(*tgt.ndt, W, st);
+  if (rc) return rc;
+  if (tgt.ndt->h_geom.empty) return B2R_OK;
+  NdtScalars K;
+  ndt_gauss(cfg, K);
+  float guess[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) guess[r * 4 + c] = guess_col[c * 4 + r];
+  bool is_identity = true;
+  for (int i = 0; i < 16; i++) is_identity &= (guess[i] == ((i % 5 == 0) ? 1.f : 0.f));
+  if (!is_identity) std::memcpy(Tfinal, guess, sizeof(guess));
+  double p[6];
+  {
+    float e[3];
+    ndt_euler_xyz(Tfinal, e);
+    p[0] = Tfinal[3]; p[1] = Tfinal[7]; p[2] = Tfinal[11];
+    p[3] = e[0]; p[4] = e[1]; p[5] = e[2];
+  }
+  ndt_angle_derivs(p, K);
+  NdtPass P;
+  rc = ndt_run_pass(cfg, src, tgt, W, st, K, Tfinal, true, false, &P);  // first pass: cloud transformed by the guess matrix itself
+  if (rc) return rc;
+  double score = P.score, g[6], H[36];
+  std::memcpy(g, P.g, sizeof(g));
+  std::memcpy(H, P.H, sizeof(H));
+  int nr_iterations = 0;
+  bool converged = false;
+  const int max_it = cfg.max_iterations;
+  while (!converged) {
+    double ng[6], dp[6];
+    for (int i = 0; i < 6; i++) ng[i] = -g[i];
+    ndt_svd6_solve(H, ng, dp);
+    double nrm = 0;
+    for (int i = 0; i < 6; i++) nrm += dp[i] * dp[i];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0 || nrm != nrm) { converged = (nrm == nrm); break; }
+    for (int i = 0; i < 6; i++) dp[i] /= nrm;
+    const double step_max = cfg.ndt_step_size, step_min = cfg.transformation_epsilon / 2;
+    const double phi_0 = -score;
+    double d_phi_0 = 0;
+    for (int i = 0; i < 6; i++) d_phi_0 += g[i] * dp[i];
+    d_phi_0 = -d_phi_0;
+    double a_t = 0;
+    bool skip = false;
+    if (d_phi_0 >= 0) {
+      if (d_phi_0 == 0) { skip = true; a_t = 0; }
+      else { d_phi_0 *= -1; for (int i = 0; i < 6; i++) dp[i] *= -1; }
+    }
+    if (!skip) {
+      const double mu = 1.e-4, nu = 0.9;
+      double a_l = 0, a_u = 0;
+      double f_l = mt_psi(a_l, phi_0, phi_0, d_phi_0, mu), g_l = mt_dpsi(d_phi_0, d_phi_0, mu);
+      double f_u = mt_psi(a_u, phi_0, phi_0, d_phi_0, mu), g_u = mt_dpsi(d_phi_0, d_phi_0, mu);
+      bool interval_converged = cfg.ndt_mt_interval_flag ? ((step_max - step_min) < 0) : ((step_max - step_min) > 0);
+      bool open_interval = true;
+      int step_iterations = 0;
+      a_t = nrm;
+      a_t = std::min(a_t, step_max);
+      a_t = std::max(a_t, step_min);
+      double x_t[6];
+      for (int i = 0; i < 6; i++) x_t[i] = p[i] + dp[i] * a_t;
+      ndt_pose_to_matrix(x_t, Tfinal);
+      ndt_angle_derivs(x_t, K);
+      rc = ndt_run_pass(cfg, src, tgt, W, st, K, Tfinal, true, false, &P);
+      if (rc) return rc;
+      score = P.score; std::memcpy(g, P.g, sizeof(g)); std::memcpy(H, P.H, sizeof(H));
+      double phi_t = -score, d_phi_t = 0;
+      for (int i = 0; i < 6; i++) d_phi_t += g[i] * dp[i];
+      d_phi_t = -d_phi_t;
+      double psi_t = mt_psi(a_t, phi_t, phi_0, d_phi_0, mu), d_psi_t = mt_dpsi(d_phi_t, d_phi_0, mu);
+      while (!interval_converged && step_iterations < 10 && !(psi_t <= 0 && d_phi_t <= -nu * d_phi_0)) {
+        if (open_interval) a_t = mt_trial(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+        else a_t = mt_trial(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+        a_t = std::min(a_t, step_max);
+        a_t = std::max(a_t, step_min);
+        for (int i = 0; i < 6; i++) x_t[i] = p[i] + dp[i] * a_t;
+        ndt_pose_to_matrix(x_t, Tfinal);
+        ndt_angle_derivs(x_t, K);
+        rc = ndt_run_pass(cfg, src, tgt, W, st, K, Tfinal, false, false, &P);
+        if (rc) return rc;
+        score = P.score; std::memcpy(g, P.g, sizeof(g));
+        phi_t = -score;
+        d_phi_t = 0;
+        for (int i = 0; i < 6; i++) d_phi_t += g[i] * dp[i];
+        d_phi_t = -d_phi_t;
+        psi_t = mt_psi(a_t, phi_t, phi_0, d_phi_0, mu);
+        d_psi_t = mt_dpsi(d_phi_t, d_phi_0, mu);
+        if (open_interval && (psi_t <= 0 && d_psi_t >= 0)) {
+          open_interval = false;
+          f_l = f_l + phi_0 - mu * d_phi_0 * a_l;
+          g_l = g_l + mu * d_phi_0;
+          f_u = f_u + phi_0 - mu * d_phi_0 * a_u;
+          g_u = g_u + mu * d_phi_0;
+        }
+        if (open_interval) interval_converged = mt_update(a_l, f_l, g_l, a_u, f_u, g_u, a_t, psi_t, d_psi_t);
+        else interval_converged = mt_update(a_l, f_l, g_l, a_u, f_u, g_u, a_t, phi_t, d_phi_t);
+        step_iterations++;
+      }
+      if (step_iterations) {
+        rc = ndt_run_pass(cfg, src, tgt, W, st, K, Tfinal, true, true, &P);
+        if (rc) return rc;
+        std::memcpy(H, P.H, sizeof(H));
+      }
+    }
+    const double delta_p_norm = a_t;
+    for (int i = 0; i < 6; i++) { dp[i] *= delta_p_norm; p[i] += dp[i]; }
+    if (cfg.ndt_fixed_iterations > 0) {
+      if (nr_iterations + 1 >= cfg.ndt_fixed_iterations) converged = true;
+    } else if (nr_iterations > max_it || (nr_iterations && (std::fabs(delta_p_norm) < cfg.transformation_epsilon))) {
+      converged = true;
+    }
+    nr_iterations++;
+  }
+  *converged_out = converged;
+  *iters_out = nr_iterations;
+  return B2R_OK;
+}
+
+}  // namespace b2r

@@ -97,6 +97,9 @@ class Registration:
     def setInputSourceRaw(self, ptr, n, stride_bytes):
         check(self._lib.b2r_set_source(self._h, C.c_void_p(ptr), n, stride_bytes))
 
+    def synchronize(self):
+        check(self._lib.b2r_synchronize(self._h))
+
     def promoteSourceToTarget(self):
         check(self._lib.b2r_promote_source_to_target(self._h))
 

@@ -93,6 +93,8 @@ int b2r_set_source(b2r_handle* h, const void* points, size_t n, size_t stride_by
  * device-side pipelines such as b2r_voxelgrid_device -> registration). */
 int b2r_set_target_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
 int b2r_set_source_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
+/* block until everything enqueued on the handle's stream (uploads, grid / covariance / voxel builds) has finished */
+int b2r_synchronize(b2r_handle* h);
 /* keyframe switch `keyframe = filtered; registration->setInputTarget(keyframe)` (scan_matching_odometry_nodelet.cpp:245-246):
  * the current source (points, grid, covariances) becomes the target without re-upload or recomputation. */
 int b2r_promote_source_to_target(b2r_handle* h);

@@ -4,8 +4,11 @@ import numpy as np
 
 def rot_err(Ta, Tb):
     R = Ta[:3, :3].astype(np.float64).T @ Tb[:3, :3].astype(np.float64)
-    c = np.clip((np.trace(R) - 1) / 2, -1, 1)
-    return float(np.arccos(c))
+    # sin(angle) from the skew part: well conditioned near zero (arccos of the trace is not)
+    v = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = float(np.linalg.norm(v))
+    c = float(np.clip((np.trace(R) - 1) / 2, -1, 1))
+    return float(np.arctan2(s, c)) if s > 1e-3 else s
 
 
 def trans_err(Ta, Tb):

@@ -1,0 +1,24 @@
+"""CPU-only: the engine's exact grid-search logic (nn_search.cuh compiled as HOST code by tests/host_harness.cu) returns
+the oracle's (d2, index) results bit-for-bit, including lattice ties, range-limited search and queries outside the grid."""
+import os
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def harness(oracle):
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    exe = os.path.join(ROOT, "build", "host_harness")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                           "-Xcompiler", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "host_harness.cu"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Xlinker", "-rpath=" + os.path.join(ROOT, "oracle")])
+    return exe
+
+
+@pytest.mark.parametrize("mode,hmin", [(0, 0.5), (1, 0.5), (2, 0.5), (0, 2.0)])
+def test_grid_search_equals_kdtree(harness, mode, hmin):
+    out = subprocess.run([harness, "20000", "4000", str(mode), str(hmin)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout and "limited_mismatch=0" in out.stdout
