@@ -40,6 +40,11 @@ class OdometryStatus(C.Structure):
     ]
 
 
+class Stats(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_classes", C.c_int32), ("reserved", C.c_int32),
+                ("launches", C.c_uint64 * 16), ("calls", C.c_uint64 * 16), ("ms", C.c_double * 16)]
+
+
 # every symbol include/b200reg.h declares: (name, restype, argtypes)
 _VP, _SZ, _I32P, _F32P, _F64P = C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_double)
 SYMBOLS = [
@@ -56,6 +61,10 @@ SYMBOLS = [
     ("b2r_set_source_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_promote_source_to_target", C.c_int, [_VP]),
     ("b2r_synchronize", C.c_int, [_VP]),
+    ("b2r_set_profiling", C.c_int, [_VP, C.c_int]),
+    ("b2r_get_stats", C.c_int, [_VP, C.POINTER(Stats), C.c_int]),
+    ("b2r_kernel_class_name", C.c_char_p, [C.c_int]),
+    ("b2r_get_stream", C.c_int, [_VP, C.POINTER(_VP)]),
     ("b2r_align", C.c_int, [_VP, _F32P, C.POINTER(Result)]),
     ("b2r_get_aligned", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_fitness", C.c_int, [_VP, _F32P, C.c_double, C.c_float, _F64P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -70,6 +79,7 @@ SYMBOLS = [
     ("b2r_odometry_create", C.c_int, [_VP, C.POINTER(OdometryParams), C.POINTER(_VP)]),
     ("b2r_odometry_destroy", None, [_VP]),
     ("b2r_odometry_matching", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),
+    ("b2r_odometry_matching_device", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),
     ("b2r_loop_matching", C.c_int, [_VP, _VP, _SZ, _SZ, C.POINTER(_VP), C.POINTER(_SZ), _SZ, _F32P, C.c_double, C.c_double,
                                     C.POINTER(Result), _I32P]),
 ]

@@ -54,6 +54,7 @@ struct b2r_handle {
   bool corr_valid = false;
   NdtWork ndt_work;
   VoxelWork vg_work;
+  Telemetry tel;
 };
 
 static Cloud& SRC(b2r_handle* h) { return h->clouds[h->src]; }
@@ -161,6 +162,8 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
   h->ndt_work.scr = &h->scr;
+  h->ndt_work.tel = &h->tel;
+  h->vg_work.tel = &h->tel;
   *out = h;
   return B2R_OK;
 }
@@ -186,6 +189,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release();
   h->ndt_work.release();
   h->vg_work.release();
+  h->tel.release();
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->h_out) cudaFreeHost(h->h_out);
@@ -225,6 +229,7 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
     if (bytes > 0) {
       if (is_pinned_host(pts)) {
         B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyHostToDevice, h->st));
+        h->tel.h2d += bytes;
       } else {
         int sidx = which & 1;
         if (h->staging_cap[sidx] < bytes) {
@@ -237,6 +242,7 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
         }
         std::memcpy(h->staging[sidx], pts, bytes);
         B2R_CUDA(cudaMemcpyAsync(c.raw.p, h->staging[sidx], bytes, cudaMemcpyHostToDevice, h->st));
+        h->tel.h2d += bytes;
         B2R_CUDA(cudaEventRecord(h->staging_ev[sidx], h->st));
       }
     }
@@ -254,7 +260,9 @@ static int ensure_grid(b2r_handle* h, Cloud& c) {
   GridBuffers B;
   B.grid = c.grid; B.mm = h->scr.mm; B.counts = h->scr.counts; B.cell_start = c.cell_start.p; B.cursor = h->scr.cursor;
   B.bsum = h->scr.bsum; B.cell_of = h->scr.cell_of.p; B.tmp_idx = h->scr.tmp_idx.p; B.sorted = c.sorted.p; B.pos_of = c.pos_of.p;
-  build_grid(c.raw_view, c.stride_f, (int)n, h->cfg.grid_cell_min, B, h->st);
+  { TEL_BEGIN(&h->tel, h->st);
+    build_grid(c.raw_view, c.stride_f, (int)n, h->cfg.grid_cell_min, B, h->st);
+    TEL_END(&h->tel, KC_GRID, n > 0 ? 10 : 5, h->st); }
   B2R_CUDA(cudaGetLastError());
   c.grid_ready = true;
   return B2R_OK;
@@ -274,7 +282,9 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
       B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 2 * kKnnThreads * 4));
       attr_set = true;
     }
+    TEL_BEGIN(&h->tel, h->st);
     k_knn_cov<<<(unsigned)((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, smem, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p);
+    TEL_END(&h->tel, KC_KNN_COV, 1, h->st);
     B2R_CUDA(cudaGetLastError());
   }
   c.cov_ready = true;
@@ -307,6 +317,34 @@ extern "C" int b2r_synchronize(b2r_handle* h) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   B2R_CUDA(cudaStreamSynchronize(h->st));
+  return B2R_OK;
+}
+
+extern "C" int b2r_get_stream(b2r_handle* h, void** stream) {
+  if (!h || !stream) return fail(B2R_EINVAL, "NULL argument");
+  *stream = (void*)h->st;
+  return B2R_OK;
+}
+
+extern "C" int b2r_set_profiling(b2r_handle* h, int on) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  h->tel.on = on != 0;
+  return B2R_OK;
+}
+
+extern "C" const char* b2r_kernel_class_name(int cls) { return kernel_class_name(cls); }
+
+extern "C" int b2r_get_stats(b2r_handle* h, b2r_stats* out, int reset) {
+  if (!h || !out) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  h->tel.resolve();
+  std::memset(out, 0, sizeof(*out));
+  out->h2d_bytes = h->tel.h2d;
+  out->d2h_bytes = h->tel.d2h;
+  out->n_classes = KC_COUNT;
+  for (int i = 0; i < KC_COUNT; i++) { out->launches[i] = h->tel.launches[i]; out->calls[i] = h->tel.calls[i]; out->ms[i] = h->tel.ms[i]; }
+  if (reset) h->tel.reset();
   return B2R_OK;
 }
 
@@ -355,9 +393,12 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
   PoseArg P;
   make_pose(x0, P);
   const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
-  k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
+    TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, kAcc * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  h->tel.d2h += kAcc * sizeof(double);
   B2R_CUDA(cudaStreamSynchronize(h->st));
   // unpack the upper triangle
   int k = 0;
@@ -378,9 +419,12 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
   PoseArg P;
   make_pose(xi, P);
   const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
-  k_gicp_error<<<nb, kLinThreads, 0, h->st>>>(A, P);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_gicp_error<<<nb, kLinThreads, 0, h->st>>>(A, P);
+    TEL_END(&h->tel, KC_GICP_ERR, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(h->h_out + 32, h->d_out + 32, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  h->tel.d2h += sizeof(double);
   B2R_CUDA(cudaStreamSynchronize(h->st));
   *y = h->h_out[32];
   return B2R_OK;
@@ -498,7 +542,10 @@ extern "C" int b2r_get_aligned(b2r_handle* h, void* out_points, size_t n, size_t
   B2R_CUDA(h->tmp_f4.reserve(n));
   XfArg X;
   for (int i = 0; i < 12; i++) X.Tf[i] = h->final_T[i];
-  k_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(s.raw_view, s.stride_f, (int)n, X, h->tmp_f4.p);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_transform<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(s.raw_view, s.stride_f, (int)n, X, h->tmp_f4.p);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  h->tel.d2h += n * sizeof(float4);
   B2R_CUDA(cudaGetLastError());
   std::vector<float4> host(n);
   B2R_CUDA(cudaMemcpyAsync(host.data(), h->tmp_f4.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->st));
@@ -531,7 +578,10 @@ static int fitness_impl(b2r_handle* h, const float* T_row, double max_range, flo
   for (int i = 0; i < 12; i++) A.Tf[i] = T_row[i];
   A.max_range = max_range; A.inlier_thresh_sq = inl;
   A.partials = h->partials.p; A.out = h->d_out + 40; A.counter = h->d_counter + 2;
-  k_fitness<<<(unsigned)nb, kLinThreads, 0, h->st>>>(A);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_fitness<<<(unsigned)nb, kLinThreads, 0, h->st>>>(A);
+    TEL_END(&h->tel, KC_FITNESS, 1, h->st); }
+  h->tel.d2h += 3 * sizeof(double);
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(h->h_out + 40, h->d_out + 40, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   B2R_CUDA(cudaStreamSynchronize(h->st));
@@ -569,7 +619,11 @@ extern "C" int b2r_target_nearest(b2r_handle* h, const void* queries, size_t n, 
   B2R_CUDA(h->tmp_i.reserve(n));
   B2R_CUDA(cudaMemcpyAsync(h->tmp_f.p, queries, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
   float* d2d = h->tmp_f.p + n * sf;
-  k_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, sf, (int)n, t.grid, t.cell_start.p, t.sorted.p, h->tmp_i.p, d2d);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, sf, (int)n, t.grid, t.cell_start.p, t.sorted.p, h->tmp_i.p, d2d);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  h->tel.h2d += n * stride_bytes;
+  h->tel.d2h += n * 8;
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(idx_out, h->tmp_i.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   B2R_CUDA(cudaMemcpyAsync(d2_out, d2d, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
@@ -735,8 +789,18 @@ extern "C" int b2r_odometry_create(b2r_handle* reg, const b2r_odometry_params* p
 }
 extern "C" void b2r_odometry_destroy(b2r_odometry* o) { delete o; }
 
+static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes, const float* msf_delta,
+                                  b2r_odometry_status* out, bool device);
 extern "C" int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes,
                                      const float* msf_delta, b2r_odometry_status* out) {
+  return odometry_matching_impl(o, stamp, cloud, n, stride_bytes, msf_delta, out, false);
+}
+extern "C" int b2r_odometry_matching_device(b2r_odometry* o, double stamp, const void* d_cloud, size_t n, size_t stride_bytes,
+                                            const float* msf_delta, b2r_odometry_status* out) {
+  return odometry_matching_impl(o, stamp, d_cloud, n, stride_bytes, msf_delta, out, true);
+}
+static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes, const float* msf_delta,
+                                  b2r_odometry_status* out, bool device) {
   if (!o || !out) return fail(B2R_EINVAL, "NULL argument");
   std::memset(out, 0, sizeof(*out));
   out->matching_error = NAN;
@@ -749,7 +813,7 @@ extern "C" int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* 
     mat4_identity(o->prev_trans);
     mat4_identity(o->keyframe_pose);
     o->keyframe_stamp = stamp;
-    int rc = b2r_set_target(reg, cloud, n, stride_bytes);
+    int rc = device ? b2r_set_target_device(reg, cloud, n, stride_bytes) : b2r_set_target(reg, cloud, n, stride_bytes);
     if (rc) return rc;
     o->has_keyframe = true;
     row_to_col(I, out->odom);
@@ -757,7 +821,7 @@ extern "C" int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* 
     out->keyframe_updated = 1;
     return B2R_OK;
   }
-  int rc = b2r_set_source(reg, cloud, n, stride_bytes);  // :177
+  int rc = device ? b2r_set_source_device(reg, cloud, n, stride_bytes) : b2r_set_source(reg, cloud, n, stride_bytes);  // :177
   if (rc) return rc;
   float guess_row[16], delta_row[16];
   if (msf_delta) { for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) delta_row[r * 4 + c] = msf_delta[c * 4 + r]; }

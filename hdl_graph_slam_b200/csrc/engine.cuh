@@ -45,6 +45,63 @@ struct DevBuf {
   }
 };
 
+// ---- telemetry: copy byte counters, launch counters and (optional) CUDA-event timing per kernel class
+enum KernelClass { KC_GRID = 0, KC_KNN_COV, KC_GICP_LIN, KC_GICP_ERR, KC_FITNESS, KC_NDT_BUILD, KC_NDT_DERIV, KC_NDT_HESS, KC_VOXELGRID, KC_MISC, KC_COUNT };
+inline const char* kernel_class_name(int c) {
+  static const char* n[KC_COUNT] = {"grid_build", "knn_covariance", "gicp_correspond_linearize", "gicp_error", "nn_fitness", "ndt_voxel_build",
+                                    "ndt_derivatives", "ndt_hessian", "voxelgrid_downsample", "misc"};
+  return (c >= 0 && c < KC_COUNT) ? n[c] : "?";
+}
+struct Telemetry {
+  unsigned long long h2d = 0, d2h = 0;
+  unsigned long long launches[KC_COUNT] = {0}, calls[KC_COUNT] = {0};
+  double ms[KC_COUNT] = {0};
+  bool on = false;
+  struct Span { cudaEvent_t a, b; int cls; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  cudaEvent_t begin(cudaStream_t st) {
+    if (!on) return nullptr;
+    cudaEvent_t a = get();
+    cudaEventRecord(a, st);
+    return a;
+  }
+  void end(cudaEvent_t a, int cls, int nlaunch, cudaStream_t st) {
+    launches[cls] += nlaunch;
+    calls[cls] += 1;
+    if (!on || !a) return;
+    cudaEvent_t b = get();
+    cudaEventRecord(b, st);
+    spans.push_back({a, b, cls});
+  }
+  void resolve() {  // caller has synchronised the stream
+    for (auto& sp : spans) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ms[sp.cls] += (double)t;
+      pool.push_back(sp.a);
+      pool.push_back(sp.b);
+    }
+    spans.clear();
+  }
+  void reset() {
+    h2d = d2h = 0;
+    for (int i = 0; i < KC_COUNT; i++) { launches[i] = calls[i] = 0; ms[i] = 0; }
+  }
+  void release() {
+    resolve();
+    for (auto e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
+#define TEL_BEGIN(tel, st) cudaEvent_t _tel_ev = (tel) ? (tel)->begin(st) : nullptr
+#define TEL_END(tel, cls, n, st) do { if (tel) (tel)->end(_tel_ev, cls, n, st); } while (0)
+
 struct NdtVoxelMap;  // ndt.cuh
 
 // One point cloud resident on the device with everything derived from it.

@@ -54,6 +54,7 @@ struct NdtWork {
   VoxGeom* h_geom_pinned = nullptr;
   unsigned long long* d_pairs = nullptr;
   Scratch* scr = nullptr;         // shared build scratch of the handle (set by ndt_ensure_map's caller)
+  Telemetry* tel = nullptr;
   Scratch own;                    // used when no shared scratch is provided
   bool own_init = false;
   void release() {
@@ -459,6 +460,7 @@ inline int ndt_ensure_map(const b2r_config& cfg, Cloud& c, NdtWork& W, cudaStrea
   B2R_CUDA(M.vox.reserve(c.n + 1));
   B2R_CUDA(S->cell_of.reserve(c.n + 1));
   B2R_CUDA(S->tmp_idx.reserve(c.n + 1));
+  TEL_BEGIN(W.tel, st);
   k_grid_reset<<<1, 32, 0, st>>>(S->mm);
   int nb = n > 0 ? (n + 255) / 256 : 1;
   if (nb > 1184) nb = 1184;
@@ -476,6 +478,7 @@ inline int ndt_ensure_map(const b2r_config& cfg, Cloud& c, NdtWork& W, cudaStrea
     k_canon<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.grid, S->cell_of.p, M.cell_start.p, S->tmp_idx.p, M.sorted.p, M.pos_of.p);
     k_vox_finalize<<<(n + 127) / 128, 128, 0, st>>>(M.grid, S->cell_of.p, M.cell_start.p, M.sorted.p, M.vox.p, n);
   }
+  TEL_END(W.tel, KC_NDT_BUILD, n > 0 ? 11 : 5, st);
   B2R_CUDA(cudaGetLastError());
   c.ndt_ready = true;
   return B2R_OK;
@@ -704,7 +707,10 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));
   A.partials = W.partials.p; A.out = W.d_out; A.counter = W.d_counter; A.pairs = W.d_pairs;
   if (hessian_only) {
-    k_ndt_hessian<<<nb, kNdtThreads, 0, st>>>(A);
+    { TEL_BEGIN(W.tel, st);
+      k_ndt_hessian<<<nb, kNdtThreads, 0, st>>>(A);
+      TEL_END(W.tel, KC_NDT_HESS, 1, st); }
+    if (W.tel) W.tel->d2h += 36 * sizeof(double);
     B2R_CUDA(cudaGetLastError());
     B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, 36 * sizeof(double), cudaMemcpyDeviceToHost, st));
     B2R_CUDA(cudaStreamSynchronize(st));
@@ -712,7 +718,10 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
     return B2R_OK;
   }
   B2R_CUDA(cudaMemsetAsync(W.d_pairs, 0, sizeof(unsigned long long), st));
-  k_ndt_derivatives<<<nb, kNdtThreads, 0, st>>>(A);
+  { TEL_BEGIN(W.tel, st);
+    k_ndt_derivatives<<<nb, kNdtThreads, 0, st>>>(A);
+    TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
+  if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, kNdtAcc * sizeof(double), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaMemcpyAsync(W.h_out + 48, W.d_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

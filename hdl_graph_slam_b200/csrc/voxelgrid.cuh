@@ -36,6 +36,7 @@ struct VoxelWork {
   VgGeom* geom = nullptr;
   VgGeom* h_geom = nullptr;  // pinned
   int* h_total = nullptr;    // pinned
+  Telemetry* tel = nullptr;
   void release() {
     in.release(); out.release(); keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); flags.release(); slots.release();
     okeys.release(); ocounts.release(); tmp.release();
@@ -152,6 +153,8 @@ inline int voxelgrid_filter(VoxelWork& W, cudaStream_t st, const void* in, size_
   B2R_CUDA(W.tmp.reserve(std::max(tmp_sort, tmp_scan) + 256));
   B2R_CUDA(cudaMemcpyAsync(W.in.p, in, n * stride_bytes, cudaMemcpyHostToDevice, st));
   const unsigned nb = (unsigned)((n + 255) / 256);
+  if (W.tel) W.tel->h2d += n * stride_bytes;
+  TEL_BEGIN(W.tel, st);
   k_grid_reset<<<1, 32, 0, st>>>(W.mm);
   k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, st>>>(W.in.p, sf, N, W.mm);
   k_vg_params<<<1, 1, 0, st>>>(W.mm, W.geom, N, leaf);
@@ -164,6 +167,7 @@ inline int voxelgrid_filter(VoxelWork& W, cudaStream_t st, const void* in, size_
   cub::DeviceScan::ExclusiveSum(W.tmp.p, tb, W.flags.p, W.slots.p, N, st);
   k_vg_centroid<<<nb, 256, 0, st>>>(W.in.p, sf, N, W.keys_b.p, W.vals_b.p, W.flags.p, W.slots.p, W.out.p, sf, W.okeys.p, W.ocounts.p,
                                     (int*)(W.mm + 6));
+  TEL_END(W.tel, KC_VOXELGRID, 14, st);
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(W.h_total, W.mm + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));
@@ -181,6 +185,7 @@ inline int voxelgrid_filter(VoxelWork& W, cudaStream_t st, const void* in, size_
     if (out_counts) B2R_CUDA(cudaMemcpyAsync(out_counts, W.ocounts.p, m * sizeof(int), cudaMemcpyDeviceToHost, st));
     B2R_CUDA(cudaStreamSynchronize(st));
   }
+  if (W.tel) W.tel->d2h += m * stride_bytes;
   *n_out = m;
   return B2R_OK;
 }

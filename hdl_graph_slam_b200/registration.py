@@ -17,7 +17,7 @@ library; nothing here computes.
 import ctypes as C
 import numpy as np
 from . import _capi
-from ._capi import Config, Result, OdometryParams, OdometryStatus, check, B2R_METHOD_GICP, B2R_METHOD_NDT
+from ._capi import Config, Result, OdometryParams, OdometryStatus, Stats, check, B2R_METHOD_GICP, B2R_METHOD_NDT
 
 
 def _cloud(a):
@@ -99,6 +99,23 @@ class Registration:
 
     def synchronize(self):
         check(self._lib.b2r_synchronize(self._h))
+
+    def setProfiling(self, on):
+        check(self._lib.b2r_set_profiling(self._h, int(bool(on))))
+
+    def getStats(self, reset=False):
+        st = Stats()
+        check(self._lib.b2r_get_stats(self._h, C.byref(st), int(reset)))
+        names = [self._lib.b2r_kernel_class_name(i).decode() for i in range(st.n_classes)]
+        return dict(h2d_bytes=int(st.h2d_bytes), d2h_bytes=int(st.d2h_bytes),
+                    launches={n: int(st.launches[i]) for i, n in enumerate(names)},
+                    calls={n: int(st.calls[i]) for i, n in enumerate(names)},
+                    ms={n: float(st.ms[i]) for i, n in enumerate(names)})
+
+    def getStream(self):
+        p = C.c_void_p()
+        check(self._lib.b2r_get_stream(self._h, C.byref(p)))
+        return p.value
 
     def promoteSourceToTarget(self):
         check(self._lib.b2r_promote_source_to_target(self._h))
@@ -259,13 +276,14 @@ class ScanMatchingOdometry:
         a, n, s = _cloud(cloud)
         return self.matching_raw(stamp, a.ctypes.data, n, s, msf_delta)
 
-    def matching_raw(self, stamp, ptr, n, stride_bytes, msf_delta=None):
+    def matching_raw(self, stamp, ptr, n, stride_bytes, msf_delta=None, device=False):
         st = OdometryStatus()
         dp = None
         if msf_delta is not None:
             d = _colmajor(msf_delta)
             dp = d.ctypes.data_as(C.POINTER(C.c_float))
-        check(self._lib.b2r_odometry_matching(self._o, float(stamp), C.c_void_p(ptr), n, stride_bytes, dp, C.byref(st)))
+        fn = self._lib.b2r_odometry_matching_device if device else self._lib.b2r_odometry_matching
+        check(fn(self._o, float(stamp), C.c_void_p(ptr), n, stride_bytes, dp, C.byref(st)))
         return dict(odom=_from_colmajor(st.odom), trans=_from_colmajor(st.trans), converged=bool(st.converged), iterations=st.iterations,
                     keyframe_updated=bool(st.keyframe_updated), frame_rejected=bool(st.frame_rejected), matching_error=st.matching_error,
                     inlier_fraction=st.inlier_fraction)

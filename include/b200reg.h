@@ -93,6 +93,20 @@ int b2r_set_source(b2r_handle* h, const void* points, size_t n, size_t stride_by
  * device-side pipelines such as b2r_voxelgrid_device -> registration). */
 int b2r_set_target_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
 int b2r_set_source_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
+/* telemetry: bytes copied over PCIe, kernel launches and (when profiling is on) CUDA-event time per kernel class.
+ * Used by bench.py for h2d/d2h_bytes_per_step, gpu_launches and the live roofline of the dominant kernel. */
+typedef struct b2r_stats {
+  uint64_t h2d_bytes, d2h_bytes;
+  int32_t n_classes, reserved;
+  uint64_t launches[16]; /* kernel launches per class */
+  uint64_t calls[16];    /* timed spans per class */
+  double ms[16];         /* CUDA-event milliseconds per class (profiling on) */
+} b2r_stats;
+int b2r_set_profiling(b2r_handle* h, int on);
+int b2r_get_stats(b2r_handle* h, b2r_stats* out, int reset);
+const char* b2r_kernel_class_name(int cls);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, so callers can bracket it with events */
+int b2r_get_stream(b2r_handle* h, void** stream);
 /* block until everything enqueued on the handle's stream (uploads, grid / covariance / voxel builds) has finished */
 int b2r_synchronize(b2r_handle* h);
 /* keyframe switch `keyframe = filtered; registration->setInputTarget(keyframe)` (scan_matching_odometry_nodelet.cpp:245-246):
@@ -168,6 +182,10 @@ void b2r_odometry_destroy(b2r_odometry* o);
  * msf_delta may be NULL (identity). */
 int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes, const float* msf_delta,
                           b2r_odometry_status* out);
+
+/* same, for a cloud already resident in device memory (the HBM-resident measurement of bench.py) */
+int b2r_odometry_matching_device(b2r_odometry* o, double stamp, const void* d_cloud, size_t n, size_t stride_bytes, const float* msf_delta,
+                                 b2r_odometry_status* out);
 
 /* LoopDetector::matching (include/hdl_graph_slam/loop_detector.hpp:117-171): align every candidate against the new
  * keyframe, keep the best converged fitness.  guesses: n_candidates x 16 floats, column-major (already z-zeroed by the
