@@ -48,6 +48,8 @@ struct b2r_handle {
   DevBuf<float> tmp_f;
   DevBuf<int> tmp_i;
   DevBuf<float4> tmp_f4;
+  DevBuf<int> hard_list;
+  DevBuf<float> hard_bound;
   // last result
   float final_T[16];                // row-major
   bool has_final = false;
@@ -186,7 +188,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->scr.bsum) cudaFree(h->scr.bsum);
   h->scr.cell_of.release(); h->scr.tmp_idx.release();
   h->corr.release(); h->cpos.release(); h->d2.release(); h->mahal.release(); h->partials.release();
-  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release();
+  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->hard_list.release(); h->hard_bound.release();
   h->ndt_work.release();
   h->vg_work.release();
   h->tel.release();
@@ -282,9 +284,16 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
       B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 2 * kKnnThreads * 4));
       attr_set = true;
     }
+    B2R_CUDA(h->hard_list.reserve(n + 1));
+    B2R_CUDA(h->hard_bound.reserve(n + 1));
+    const size_t smem2 = (size_t)kKnnHardWarps * (2 * k * 32 + k) * sizeof(float);
     TEL_BEGIN(&h->tel, h->st);
-    k_knn_cov<<<(unsigned)((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, smem, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p);
-    TEL_END(&h->tel, KC_KNN_COV, 1, h->st);
+    B2R_CUDA(cudaMemsetAsync(h->d_counter + 3, 0, sizeof(int), h->st));
+    k_knn_cov<<<(unsigned)((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, smem, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p,
+                                                                                            h->hard_list.p, h->hard_bound.p, (int*)(h->d_counter + 3));
+    k_knn_cov_hard<<<148 * 4, kKnnHardWarps * 32, smem2, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p, h->hard_list.p, h->hard_bound.p,
+                                                                   (const int*)(h->d_counter + 3));
+    TEL_END(&h->tel, KC_KNN_COV, 2, h->st);
     B2R_CUDA(cudaGetLastError());
   }
   c.cov_ready = true;
@@ -570,10 +579,12 @@ static int fitness_impl(b2r_handle* h, const float* T_row, double max_range, flo
   }
   int rc = ensure_grid(h, t);
   if (rc) return rc;
+  rc = ensure_grid(h, s);
+  if (rc) return rc;
   size_t nb = (s.n + kLinThreads - 1) / kLinThreads;
   B2R_CUDA(h->partials.reserve(nb * kAcc + kAcc));
   FitArgs A;
-  A.src_raw = s.raw_view; A.src_stride_f = s.stride_f; A.n = (int)s.n;
+  A.sgrid = s.grid; A.ssp = s.sorted.p;
   A.tgrid = t.grid; A.tcell_start = t.cell_start.p; A.tsp = t.sorted.p;
   for (int i = 0; i < 12; i++) A.Tf[i] = T_row[i];
   A.max_range = max_range; A.inlier_thresh_sq = inl;

@@ -13,9 +13,8 @@
 namespace b2r {
 
 struct FitArgs {
-  const float* src_raw;
-  int src_stride_f;
-  int n;
+  const Grid* sgrid;      // source grid: queries are taken in the source's sorted order (spatially coherent warps)
+  const float4* ssp;
   const Grid* tgrid;
   const int* tcell_start;
   const float4* tsp;
@@ -27,44 +26,54 @@ struct FitArgs {
   unsigned int* counter;
 };
 
-__global__ void __launch_bounds__(kLinThreads) k_fitness(FitArgs A) {
+__global__ void __launch_bounds__(kLinThreads, 2) k_fitness(FitArgs A) {
   __shared__ double red[3 * 32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nv = A.sgrid->n_valid;
+  const Grid tg = *A.tgrid;
   double acc[3] = {0.0, 0.0, 0.0};
-  if (i < A.n) {
-    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
-    const float x = p[0], y = p[1], z = p[2];
-    const float qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], x, y, z);
-    const float qy = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], x, y, z);
-    const float qz = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], x, y, z);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  Nn1 v;
+  v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
+  bool need = false, active = false;
+  if (i < nv) {
+    const float4 p = A.ssp[i];
+    qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], p.x, p.y, p.z);
+    qy = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], p.x, p.y, p.z);
+    qz = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], p.x, p.y, p.z);
     if (finite3(qx, qy, qz)) {
-      const Grid tg = *A.tgrid;
-      Nn1 v;
-      v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
-      grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v);
-      if (v.best_pos >= 0) {
-        if ((double)v.best_d2 <= A.max_range) { acc[0] = (double)v.best_d2; acc[1] = 1.0; }
-        if (v.best_d2 < A.inlier_thresh_sq) acc[2] = 1.0;
-      }
+      active = true;
+      need = !grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
     }
+  }
+  warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);
+  if (active && v.best_pos >= 0) {
+    if ((double)v.best_d2 <= A.max_range) { acc[0] = (double)v.best_d2; acc[1] = 1.0; }
+    if (v.best_d2 < A.inlier_thresh_sq) acc[2] = 1.0;
   }
   block_reduce<3>(acc, red);
   finish_partials<3>(acc, A.partials, A.out, A.counter);
 }
 
-__global__ void k_nearest(const float* __restrict__ q_raw, int stride_f, int n, const Grid* __restrict__ tgrid,
-                          const int* __restrict__ tcell_start, const float4* __restrict__ tsp, int* idx_out, float* d2_out) {
+// queries in caller order (no spatial coherence guaranteed); n is rounded up to whole warps by the launcher
+__global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_raw, int stride_f, int n, const Grid* __restrict__ tgrid,
+                                                 const int* __restrict__ tcell_start, const float4* __restrict__ tsp, int* idx_out, float* d2_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* p = q_raw + (size_t)i * stride_f;
+  const Grid tg = *tgrid;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
   v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
-  if (finite3(p[0], p[1], p[2])) {
-    const Grid tg = *tgrid;
-    grid_search(tg, tcell_start, tsp, p[0], p[1], p[2], v);
+  bool need = false;
+  if (i < n) {
+    const float* p = q_raw + (size_t)i * stride_f;
+    qx = p[0]; qy = p[1]; qz = p[2];
+    if (finite3(qx, qy, qz)) need = !grid_search(tg, tcell_start, tsp, qx, qy, qz, v, 1);
   }
-  idx_out[i] = v.best_pos >= 0 ? v.best_idx : -1;
-  d2_out[i] = v.best_d2;
+  warp_finish_nn1(tg, tcell_start, tsp, qx, qy, qz, v, need);
+  if (i < n) {
+    idx_out[i] = v.best_pos >= 0 ? v.best_idx : -1;
+    d2_out[i] = v.best_d2;
+  }
 }
 
 struct XfArg { float Tf[12]; };

@@ -46,8 +46,43 @@ struct KnnList {
   }
 };
 
-__global__ void __launch_bounds__(kKnnThreads) k_knn_cov(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
-                                                         const float4* __restrict__ sp, int k, double* __restrict__ cov) {
+// mean / covariance over the neighbours in ascending (d2, index) order (float64), PLANE regularisation, store 6 doubles
+template <class PosAt>
+__device__ __forceinline__ void knn_cov_store(const float4* __restrict__ sp, int kk, PosAt pos_at, double* __restrict__ o) {
+  double mx = 0, my = 0, mz = 0;
+  for (int j = 0; j < kk; j++) {
+    float4 p = sp[pos_at(j)];
+    mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
+  }
+  const double inv = 1.0 / (double)kk;
+  mx *= inv; my *= inv; mz *= inv;
+  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < kk; j++) {
+    float4 p = sp[pos_at(j)];
+    double vx = (double)p.x - mx, vy = (double)p.y - my, vz = (double)p.z - mz;
+    c[0] += vx * vx; c[1] += vx * vy; c[2] += vx * vz;
+    c[4] += vy * vy; c[5] += vy * vz; c[8] += vz * vz;
+  }
+  c[0] *= inv; c[1] *= inv; c[2] *= inv; c[4] *= inv; c[5] *= inv; c[8] *= inv;
+  c[3] = c[1]; c[6] = c[2]; c[7] = c[5];
+  // PLANE regularisation: eigenvalues (descending) replaced by (1, 1, 1e-3)
+  double w[3], V[9];
+  sym_eigen3(c, w, V);
+  const double v0 = 1e-3, v1 = 1.0, v2 = 1.0;  // ascending order: smallest -> 1e-3
+  o[0] = v2 * V[2] * V[2] + v1 * V[1] * V[1] + v0 * V[0] * V[0];
+  o[1] = v2 * V[2] * V[5] + v1 * V[1] * V[4] + v0 * V[0] * V[3];
+  o[2] = v2 * V[2] * V[8] + v1 * V[1] * V[7] + v0 * V[0] * V[6];
+  o[3] = v2 * V[5] * V[5] + v1 * V[4] * V[4] + v0 * V[3] * V[3];
+  o[4] = v2 * V[5] * V[8] + v1 * V[4] * V[7] + v0 * V[3] * V[6];
+  o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
+}
+
+constexpr int kKnnLocalR = 2;  // thread-local shells r = 0..2 (5x5x5 cells); anything sparser goes to the warp-cooperative kernel
+
+// phase 1: one thread per query (sorted order => a warp walks neighbouring cells), top-k lists in shared memory
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                         const float4* __restrict__ sp, int k, double* __restrict__ cov, int* hard_list,
+                                                         float* hard_bound, int* hard_count) {
   extern __shared__ float knn_smem[];
   const Grid g = *gp;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,36 +95,106 @@ __global__ void __launch_bounds__(kKnnThreads) k_knn_cov(const Grid* __restrict_
   L.cnt = 0;
   L.stride = blockDim.x;
   const float4 q = sp[s];
-  grid_search(g, cell_start, sp, q.x, q.y, q.z, L);
-  const int kk = L.cnt;
-  // mean and covariance over the neighbours in ascending (d2, index) order, float64
-  double mx = 0, my = 0, mz = 0;
-  for (int j = 0; j < kk; j++) {
-    float4 p = sp[L.pos[j * L.stride]];
-    mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
+  const bool done = grid_search(g, cell_start, sp, q.x, q.y, q.z, L, kKnnLocalR);
+  if (!done) {
+    const int slot = atomicAdd(hard_count, 1);
+    hard_list[slot] = s;
+    hard_bound[slot] = L.worst();  // valid upper bound of the true k-th distance (INFINITY if fewer than k found so far)
+    return;
   }
-  const double inv = 1.0 / (double)kk;
-  mx *= inv; my *= inv; mz *= inv;
-  double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < kk; j++) {
-    float4 p = sp[L.pos[j * L.stride]];
-    double vx = (double)p.x - mx, vy = (double)p.y - my, vz = (double)p.z - mz;
-    c[0] += vx * vx; c[1] += vx * vy; c[2] += vx * vz;
-    c[4] += vy * vy; c[5] += vy * vz; c[8] += vz * vz;
+  const int stride = L.stride;
+  const int* posp = L.pos;
+  knn_cov_store(sp, L.cnt, [=](int j) { return posp[j * stride]; }, cov + (size_t)s * 6);
+}
+
+// phase 2: one WARP per hard query.  Every lane keeps a private sorted top-k of the rows it scans inside the box of radius
+// sqrt(bound); the 32 lists are then merged by repeated warp-wide argmin.  Exact: bound >= true k-th distance.
+struct KnnLaneList {
+  float* d;
+  int* pos;
+  const float4* sp;
+  int k, cnt;
+  float bound;
+  __device__ __forceinline__ float worst() const { return cnt < k ? bound : fminf(bound, d[(k - 1) * 32]); }
+  __device__ __forceinline__ float limit() const { return INFINITY; }
+  __device__ __forceinline__ bool less_than_slot(float d2, int idx, int slot) const {
+    float ds = d[slot * 32];
+    if (d2 < ds) return true;
+    if (d2 > ds) return false;
+    return idx < idx_bits(sp[pos[slot * 32]].w);
   }
-  c[0] *= inv; c[1] *= inv; c[2] *= inv; c[4] *= inv; c[5] *= inv; c[8] *= inv;
-  c[3] = c[1]; c[6] = c[2]; c[7] = c[5];
-  // PLANE regularisation: eigenvalues (descending) replaced by (1, 1, 1e-3)
-  double w[3], V[9];
-  sym_eigen3(c, w, V);
-  const double v0 = 1e-3, v1 = 1.0, v2 = 1.0;  // ascending order: smallest -> 1e-3
-  double* o = cov + (size_t)s * 6;
-  o[0] = v2 * V[2] * V[2] + v1 * V[1] * V[1] + v0 * V[0] * V[0];
-  o[1] = v2 * V[2] * V[5] + v1 * V[1] * V[4] + v0 * V[0] * V[3];
-  o[2] = v2 * V[2] * V[8] + v1 * V[1] * V[7] + v0 * V[0] * V[6];
-  o[3] = v2 * V[5] * V[5] + v1 * V[4] * V[4] + v0 * V[3] * V[3];
-  o[4] = v2 * V[5] * V[8] + v1 * V[4] * V[7] + v0 * V[3] * V[6];
-  o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
+  __device__ __forceinline__ void visit(float d2, int idx, int p) {
+    if (d2 > bound) return;
+    if (cnt == k && !less_than_slot(d2, idx, k - 1)) return;
+    int j = (cnt < k) ? cnt++ : k - 1;
+    while (j > 0 && less_than_slot(d2, idx, j - 1)) {
+      d[j * 32] = d[(j - 1) * 32];
+      pos[j * 32] = pos[(j - 1) * 32];
+      j--;
+    }
+    d[j * 32] = d2;
+    pos[j * 32] = p;
+  }
+};
+
+constexpr int kKnnHardWarps = 4;
+
+__global__ void __launch_bounds__(kKnnHardWarps * 32, 4) k_knn_cov_hard(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                                     const float4* __restrict__ sp, int k, double* __restrict__ cov,
+                                                                     const int* __restrict__ hard_list, const float* __restrict__ hard_bound,
+                                                                     const int* __restrict__ hard_count) {
+  extern __shared__ float knn_smem[];  // per warp: d[k][32], pos[k][32], merged[k]
+  const Grid g = *gp;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* wbase = knn_smem + (size_t)wib * (2 * k * 32 + k);
+  int* merged = reinterpret_cast<int*>(wbase + 2 * k * 32);
+  const int nhard = *hard_count;
+  const int nwarps = gridDim.x * kKnnHardWarps;
+  for (int hq = blockIdx.x * kKnnHardWarps + wib; hq < nhard; hq += nwarps) {
+    const int s = hard_list[hq];
+    const float bound = hard_bound[hq];
+    const float4 q = sp[s];
+    KnnLaneList L;
+    L.d = wbase + lane;
+    L.pos = reinterpret_cast<int*>(wbase + k * 32) + lane;
+    L.sp = sp;
+    L.k = k;
+    L.cnt = 0;
+    L.bound = bound;
+    const int cx = cell_coord(q.x, g.ox, g.inv_h, g.nx), cy = cell_coord(q.y, g.oy, g.inv_h, g.ny), cz = cell_coord(q.z, g.oz, g.inv_h, g.nz);
+    int R = 0x3fffffff;
+    if (bound < 1.0e30f) {
+      const float rr = sqrtf(bound) * g.inv_h;
+      if (rr < 1.0e6f) R = (int)rr + 2;
+    }
+    warp_box_scan(g, cell_start, sp, q.x, q.y, q.z, cx, cy, cz, R, lane, L);
+    __syncwarp();
+    // k-way merge of the 32 sorted lane lists
+    int head = 0, kk = 0;
+    for (int j = 0; j < k; j++) {
+      float cd = (head < L.cnt) ? L.d[head * 32] : INFINITY;
+      int cp = (head < L.cnt) ? L.pos[head * 32] : -1;
+      int ci = (cp >= 0) ? idx_bits(sp[cp].w) : 0x7fffffff;
+      float bd = cd;
+      int bi = ci, bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+        if (od < bd || (od == bd && (oi < bi || (oi == bi && ol < bl)))) { bd = od; bi = oi; bl = ol; }
+      }
+      if (bd == INFINITY) break;
+      if (lane == bl) { merged[j] = cp; head++; }
+      kk = j + 1;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int* mp = merged;
+      knn_cov_store(sp, kk, [=](int j) { return mp[j]; }, cov + (size_t)s * 6);
+    }
+    __syncwarp();
+  }
 }
 
 // ---------------------------------------------------------------- pose passed by value to the per-iteration kernels
@@ -167,35 +272,42 @@ struct LinArgs {
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
 };
 
-__global__ void __launch_bounds__(kLinThreads) k_gicp_linearize(LinArgs A, PoseArg P) {
+__global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(LinArgs A, PoseArg P) {
   __shared__ double red[kAcc * 32];
   const int nv = A.sgrid->n_valid;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+  const Grid tg = *A.tgrid;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  Nn1 v;
+  v.best_d2 = INFINITY;
+  v.best_idx = 0x7fffffff;
+  v.best_pos = -1;
+  v.lim = A.lim;
+  bool need = false;
   if (s < nv) {
-    const Grid tg = *A.tgrid;
-    const float4 p = A.ssp[s];
-    const float qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
-    const float qy = xform_row(P.Tf[4], P.Tf[5], P.Tf[6], P.Tf[7], p.x, p.y, p.z);
-    const float qz = xform_row(P.Tf[8], P.Tf[9], P.Tf[10], P.Tf[11], p.x, p.y, p.z);
-    Nn1 v;
-    v.best_d2 = INFINITY;
-    v.best_idx = 0x7fffffff;
-    v.best_pos = -1;
-    v.lim = A.lim;
-    if (A.use_seed) {
-      int sp0 = A.cpos[s];
-      if (sp0 >= 0) {
-        float4 t = A.tsp[sp0];
-        v.best_d2 = dist2_f32(qx, qy, qz, t.x, t.y, t.z);
-        v.best_idx = idx_bits(t.w);
-        v.best_pos = sp0;
+    p = A.ssp[s];
+    qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
+    qy = xform_row(P.Tf[4], P.Tf[5], P.Tf[6], P.Tf[7], p.x, p.y, p.z);
+    qz = xform_row(P.Tf[8], P.Tf[9], P.Tf[10], P.Tf[11], p.x, p.y, p.z);
+    if (finite3(qx, qy, qz)) {
+      if (A.use_seed) {  // last iteration's correspondent is a real candidate: a tight, exact upper bound
+        int sp0 = A.cpos[s];
+        if (sp0 >= 0) {
+          float4 t = A.tsp[sp0];
+          v.best_d2 = dist2_f32(qx, qy, qz, t.x, t.y, t.z);
+          v.best_idx = idx_bits(t.w);
+          v.best_pos = sp0;
+        }
       }
+      need = !grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
     }
-    if (finite3(qx, qy, qz)) grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v);
-    else v.best_pos = -1;
+  }
+  warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);  // all 32 lanes participate
+  if (s < nv) {
     const bool valid = (v.best_pos >= 0) && ((double)v.best_d2 < A.thr2);
     A.corr[idx_bits(p.w)] = valid ? v.best_idx : -1;
     A.cpos[s] = valid ? v.best_pos : -1;

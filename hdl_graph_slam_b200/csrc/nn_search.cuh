@@ -10,6 +10,10 @@
 // float subtraction, multiplication and addition of non-negatives are monotone under round-to-nearest, hence a bound
 // assembled from face distances in the same operation order never exceeds the d2 the point would evaluate to.
 // Rows/shells are skipped only when bound > worst (strict), so equal-distance lower-index candidates stay reachable.
+//
+// Two regimes (profiles/r01_a: a purely thread-local shell walk has a catastrophic latency tail on far-field LiDAR points):
+//   grid_search(..., max_r)   thread-local shells r = 0..max_r  — finishes the dense majority of queries
+//   warp_box_scan / warp_finish_nn1   the 32 lanes of a warp split the rows of a bounded box for ONE unfinished query
 #pragma once
 #include "common.cuh"
 
@@ -34,11 +38,29 @@ B2R_HD void grid_scan_run(const int* __restrict__ cell_start, const float4* __re
   }
 }
 
+// squared distance from q to the nearest face of the block [c-R, c+R]^3 that still has grid behind it;
+// returns INFINITY when the block covers the whole grid.
+B2R_HD float block_face_bound2(const Grid& g, float qx, float qy, float qz, int cx, int cy, int cz, int R) {
+  const float h = g.h;
+  const long long x0 = (long long)cx - R, x1 = (long long)cx + R, y0 = (long long)cy - R, y1 = (long long)cy + R, z0 = (long long)cz - R, z1 = (long long)cz + R;
+  float fb = INFINITY;
+  if (x0 > 0) fb = fminf(fb, fsub(qx, fadd(g.ox, fmul((float)x0, h))));
+  if (x1 < g.nx - 1) fb = fminf(fb, fsub(fadd(g.ox, fmul((float)(x1 + 1), h)), qx));
+  if (y0 > 0) fb = fminf(fb, fsub(qy, fadd(g.oy, fmul((float)y0, h))));
+  if (y1 < g.ny - 1) fb = fminf(fb, fsub(fadd(g.oy, fmul((float)(y1 + 1), h)), qy));
+  if (z0 > 0) fb = fminf(fb, fsub(qz, fadd(g.oz, fmul((float)z0, h))));
+  if (z1 < g.nz - 1) fb = fminf(fb, fsub(fadd(g.oz, fmul((float)(z1 + 1), h)), qz));
+  if (fb == INFINITY) return INFINITY;
+  if (fb < 0.f) fb = 0.f;  // cannot happen for finite q (q is clamped into the block); defensive
+  return fmul(fb, fb);
+}
+
 // Visitor interface:  float worst() const;  float limit() const;  void visit(float d2, int orig_idx, int pos);
+// Returns true when the search is complete (result exact), false when it stopped at max_r with work left.
 template <class Visitor>
-B2R_HD void grid_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sp, float qx, float qy,
-                        float qz, Visitor& v) {
-  if (g.n_valid <= 0) return;
+B2R_HD bool grid_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sp, float qx, float qy,
+                        float qz, Visitor& v, int max_r = 0x3fffffff) {
+  if (g.n_valid <= 0) return true;
   const int cx = cell_coord(qx, g.ox, g.inv_h, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_h, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_h, g.nz);
@@ -76,18 +98,11 @@ B2R_HD void grid_search(const Grid& g, const int* __restrict__ cell_start, const
       }
     }
     // termination: distance to the nearest block face that still has grid behind it
-    float fb = INFINITY;
-    if (x0 > 0) fb = fminf(fb, fsub(qx, fadd(g.ox, fmul((float)x0, h))));
-    if (x1 < g.nx - 1) fb = fminf(fb, fsub(fadd(g.ox, fmul((float)(x1 + 1), h)), qx));
-    if (y0 > 0) fb = fminf(fb, fsub(qy, fadd(g.oy, fmul((float)y0, h))));
-    if (y1 < g.ny - 1) fb = fminf(fb, fsub(fadd(g.oy, fmul((float)(y1 + 1), h)), qy));
-    if (z0 > 0) fb = fminf(fb, fsub(qz, fadd(g.oz, fmul((float)z0, h))));
-    if (z1 < g.nz - 1) fb = fminf(fb, fsub(fadd(g.oz, fmul((float)(z1 + 1), h)), qz));
-    if (fb == INFINITY) break;  // block covers the whole grid
-    if (fb < 0.f) fb = 0.f;     // cannot happen for finite q (q is clamped into the block); defensive
-    const float fb2 = fmul(fb, fb);
-    if (v.worst() < fb2) break;      // every unvisited point evaluates to d2 >= fb2 > worst
-    if (!(fb2 < v.limit())) break;   // every unvisited point is at or beyond the caller's range limit
+    const float fb2 = block_face_bound2(g, qx, qy, qz, cx, cy, cz, r);
+    if (fb2 == INFINITY) return true;      // block covers the whole grid
+    if (v.worst() < fb2) return true;      // every unvisited point evaluates to d2 >= fb2 > worst
+    if (!(fb2 < v.limit())) return true;   // every unvisited point is at or beyond the caller's range limit
+    if (r >= max_r) return false;
   }
 }
 
@@ -107,5 +122,75 @@ struct Nn1 {
     }
   }
 };
+
+#ifdef __CUDACC__
+// The calling warp scans the box [c-R, c+R]^3 (clipped) for ONE query: lane l takes (z,y) rows l, l+32, ...; each row is
+// one contiguous run of the sorted array.  Every lane accumulates into its own visitor.
+template <class Visitor>
+__device__ __forceinline__ void warp_box_scan(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sp, float qx,
+                                              float qy, float qz, int cx, int cy, int cz, int R, int lane, Visitor& v) {
+  const float h = g.h;
+  const int xa = (cx - R < 0 || R > g.nx) ? 0 : cx - R, xb = (R > g.nx || cx + R > g.nx - 1) ? g.nx - 1 : cx + R;
+  const int ya = (cy - R < 0 || R > g.ny) ? 0 : cy - R, yb = (R > g.ny || cy + R > g.ny - 1) ? g.ny - 1 : cy + R;
+  const int za = (cz - R < 0 || R > g.nz) ? 0 : cz - R, zb = (R > g.nz || cz + R > g.nz - 1) ? g.nz - 1 : cz + R;
+  const int ny_r = yb - ya + 1;
+  const int total = ny_r * (zb - za + 1);
+  const float bx = axis_bound(qx, fadd(g.ox, fmul((float)xa, h)), fadd(g.ox, fmul((float)(xb + 1), h)));
+  const float bx2 = fmul(bx, bx);
+  for (int t = lane; t < total; t += 32) {
+    const int z = za + t / ny_r, y = ya + t % ny_r;
+    const float by = axis_bound(qy, fadd(g.oy, fmul((float)y, h)), fadd(g.oy, fmul((float)(y + 1), h)));
+    const float bz = axis_bound(qz, fadd(g.oz, fmul((float)z, h)), fadd(g.oz, fmul((float)(z + 1), h)));
+    const float b = fadd(fadd(bx2, fmul(by, by)), fmul(bz, bz));
+    if (b > v.worst()) continue;
+    const int row = (z * g.ny + y) * g.nx;
+    grid_scan_run(cell_start, sp, row + xa, row + xb, qx, qy, qz, v);
+  }
+}
+
+__device__ __forceinline__ void warp_min_nn1(Nn1& v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, v.best_d2, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, v.best_idx, o);
+    const int op = __shfl_xor_sync(0xffffffffu, v.best_pos, o);
+    if (od < v.best_d2 || (od == v.best_d2 && oi < v.best_idx)) { v.best_d2 = od; v.best_idx = oi; v.best_pos = op; }
+  }
+}
+
+// Must be called by ALL 32 lanes of a warp.  Lanes with need == true hold an unfinished 1-NN query (qx,qy,qz, v after the
+// thread-local phase); the warp finishes them one at a time with growing boxes.  Exact (same argument as grid_search).
+__device__ __forceinline__ void warp_finish_nn1(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sp, float qx,
+                                                float qy, float qz, Nn1& v, bool need) {
+  const int lane = threadIdx.x & 31;
+  unsigned hard = __ballot_sync(0xffffffffu, need);
+  while (hard) {
+    const int L = __ffs(hard) - 1;
+    hard &= hard - 1;
+    const float ax = __shfl_sync(0xffffffffu, qx, L), ay = __shfl_sync(0xffffffffu, qy, L), az = __shfl_sync(0xffffffffu, qz, L);
+    Nn1 w;
+    w.best_d2 = __shfl_sync(0xffffffffu, v.best_d2, L);
+    w.best_idx = __shfl_sync(0xffffffffu, v.best_idx, L);
+    w.best_pos = __shfl_sync(0xffffffffu, v.best_pos, L);
+    w.lim = __shfl_sync(0xffffffffu, v.lim, L);
+    const int cx = cell_coord(ax, g.ox, g.inv_h, g.nx), cy = cell_coord(ay, g.oy, g.inv_h, g.ny), cz = cell_coord(az, g.oz, g.inv_h, g.nz);
+    // first box: large enough for the current bound (best found so far, or the caller's range limit), at least 4 cells
+    float bound = fminf(w.best_d2, w.lim);
+    int R = 4;
+    if (bound < 1.0e30f) {
+      const float rr = sqrtf(bound) * g.inv_h;
+      R = rr < 1.0e6f ? (int)rr + 2 : 0x3fffffff;
+    }
+    for (;;) {
+      warp_box_scan(g, cell_start, sp, ax, ay, az, cx, cy, cz, R, lane, w);
+      warp_min_nn1(w);
+      const float fb2 = block_face_bound2(g, ax, ay, az, cx, cy, cz, R);
+      if (fb2 == INFINITY || w.best_d2 < fb2 || !(fb2 < w.lim)) break;
+      R = (R < (1 << 20)) ? R * 4 : 0x3fffffff;
+    }
+    if (lane == L) { v.best_d2 = w.best_d2; v.best_idx = w.best_idx; v.best_pos = w.best_pos; }
+  }
+}
+#endif
 
 }  // namespace b2r
