@@ -43,8 +43,12 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_fitness(FitArgs A) {
     qz = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], p.x, p.y, p.z);
     if (finite3(qx, qy, qz)) {
       active = true;
-      need = !grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
     }
+  }
+  {
+    bool done = false;
+    if (!warp_group_search(tg, A.tcell_start, A.tsp, qx, qy, qz, active, v, 1, done)) done = !active || grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
+    need = active && !done;
   }
   warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);
   if (active && v.best_pos >= 0) {

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(const Grid* __restri
   extern __shared__ float knn_smem[];
   const Grid g = *gp;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= g.n_valid) return;
+  const bool active = s < g.n_valid;  // whole warps stay alive: the group search is warp-collective
   KnnList L;
   L.d = knn_smem + threadIdx.x;
   L.pos = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + threadIdx.x;
@@ -94,8 +94,13 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(const Grid* __restri
   L.k = k;
   L.cnt = 0;
   L.stride = blockDim.x;
-  const float4 q = sp[s];
-  const bool done = grid_search(g, cell_start, sp, q.x, q.y, q.z, L, kKnnLocalR);
+  const float4 q = active ? sp[s] : make_float4(0.f, 0.f, 0.f, 0.f);
+  bool done = false;
+  if (!warp_group_search(g, cell_start, sp, q.x, q.y, q.z, active, L, kKnnLocalR, done)) {
+    // the warp's queries straddle distant cells (row ends): independent thread-local walks
+    done = !active || grid_search(g, cell_start, sp, q.x, q.y, q.z, L, kKnnLocalR);
+  }
+  if (!active) return;
   if (!done) {
     const int slot = atomicAdd(hard_count, 1);
     hard_list[slot] = s;
@@ -162,31 +167,51 @@ __global__ void __launch_bounds__(kKnnHardWarps * 32, 4) k_knn_cov_hard(const Gr
     L.cnt = 0;
     L.bound = bound;
     const int cx = cell_coord(q.x, g.ox, g.inv_h, g.nx), cy = cell_coord(q.y, g.oy, g.inv_h, g.ny), cz = cell_coord(q.z, g.oz, g.inv_h, g.nz);
-    int R = 0x3fffffff;
-    if (bound < 1.0e30f) {
-      const float rr = sqrtf(bound) * g.inv_h;
-      if (rr < 1.0e6f) R = (int)rr + 2;
+    float bnd = bound;
+    int R = 4, kk = 0;
+    if (bnd < 1.0e30f) {
+      const float rr = sqrtf(bnd) * g.inv_h;
+      R = rr < 1.0e6f ? (int)rr + 2 : 0x3fffffff;
     }
-    warp_box_scan(g, cell_start, sp, q.x, q.y, q.z, cx, cy, cz, R, lane, L);
-    __syncwarp();
-    // k-way merge of the 32 sorted lane lists
-    int head = 0, kk = 0;
-    for (int j = 0; j < k; j++) {
-      float cd = (head < L.cnt) ? L.d[head * 32] : INFINITY;
-      int cp = (head < L.cnt) ? L.pos[head * 32] : -1;
-      int ci = (cp >= 0) ? idx_bits(sp[cp].w) : 0x7fffffff;
-      float bd = cd;
-      int bi = ci, bl = lane;
+    for (;;) {
+      L.cnt = 0;
+      L.bound = bnd;
+      warp_box_scan(g, cell_start, sp, q.x, q.y, q.z, cx, cy, cz, R, lane, L);
+      __syncwarp();
+      // k-way merge of the 32 sorted lane lists
+      int head = 0;
+      float kth = INFINITY;
+      kk = 0;
+      for (int j = 0; j < k; j++) {
+        float cd = (head < L.cnt) ? L.d[head * 32] : INFINITY;
+        int cp = (head < L.cnt) ? L.pos[head * 32] : -1;
+        int ci = (cp >= 0) ? idx_bits(sp[cp].w) : 0x7fffffff;
+        float bd = cd;
+        int bi = ci, bl = lane;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-        if (od < bd || (od == bd && (oi < bi || (oi == bi && ol < bl)))) { bd = od; bi = oi; bl = ol; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, bd, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+          if (od < bd || (od == bd && (oi < bi || (oi == bi && ol < bl)))) { bd = od; bi = oi; bl = ol; }
+        }
+        if (bd == INFINITY) break;
+        if (lane == bl) { merged[j] = cp; head++; }
+        kth = bd;
+        kk = j + 1;
       }
-      if (bd == INFINITY) break;
-      if (lane == bl) { merged[j] = cp; head++; }
-      kk = j + 1;
+      const float fb2 = block_face_bound2(g, q.x, q.y, q.z, cx, cy, cz, R);
+      if (fb2 == INFINITY) break;              // the box covered the whole grid
+      if (kk == k && kth < fb2) break;         // k neighbours, all strictly inside the covered block: exact
+      if (kk == k) bnd = fminf(bnd, kth);      // still a valid upper bound of the true k-th distance
+      int Rn = (R < (1 << 20)) ? R * 4 : 0x3fffffff;
+      if (bnd < 1.0e30f) {
+        const float rr = sqrtf(bnd) * g.inv_h;
+        const int Rb = rr < 1.0e6f ? (int)rr + 2 : 0x3fffffff;
+        Rn = Rb > R ? Rb : Rn;
+      }
+      R = Rn;
+      __syncwarp();
     }
     __syncwarp();
     if (lane == 0) {
@@ -303,8 +328,14 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(LinArgs A, Po
           v.best_pos = sp0;
         }
       }
-      need = !grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
+      need = true;
     }
+  }
+  {
+    bool done = false;
+    const bool act = need;
+    if (!warp_group_search(tg, A.tcell_start, A.tsp, qx, qy, qz, act, v, 1, done)) done = !act || grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
+    need = act && !done;
   }
   warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);  // all 32 lanes participate
   if (s < nv) {

@@ -142,10 +142,99 @@ __device__ __forceinline__ void warp_box_scan(const Grid& g, const int* __restri
     const float by = axis_bound(qy, fadd(g.oy, fmul((float)y, h)), fadd(g.oy, fmul((float)(y + 1), h)));
     const float bz = axis_bound(qz, fadd(g.oz, fmul((float)z, h)), fadd(g.oz, fmul((float)(z + 1), h)));
     const float b = fadd(fadd(bx2, fmul(by, by)), fmul(bz, bz));
-    if (b > v.worst()) continue;
+    if (b > fminf(v.worst(), v.limit())) continue;  // rows at or beyond the caller's range limit cannot matter
     const int row = (z * g.ny + y) * g.nx;
     grid_scan_run(cell_start, sp, row + xa, row + xb, qx, qy, qz, v);
   }
+}
+
+// ---- warp-group search ("shared staging of cells"): the 32 lanes of a warp hold 32 queries that are neighbours in the
+// sorted order, i.e. sit in the same or adjacent cells.  The warp walks the rings around the GROUP's cell box together:
+// every candidate run is loaded once, coalesced (lane j loads point base+j), and broadcast by shuffles so that each lane
+// tests it against its own query.  This removes the SIMT divergence of 32 independent shell walks (profiles/r01_b).
+// Per-lane exactness is unchanged: a lane skips a run only if the run's box bound exceeds its own worst (strict), and is
+// done only when its worst is below the distance to the group box's faces.
+// Returns false (nothing done) when the group's cells are too spread out to share work; done[lane] tells completion.
+constexpr int kGroupMaxDX = 5, kGroupMaxDY = 1, kGroupMaxDZ = 1;
+
+template <class Visitor>
+__device__ __forceinline__ bool warp_group_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sp, float qx,
+                                                  float qy, float qz, bool active, Visitor& v, int max_r, bool& done) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  done = !active;
+  if (g.n_valid <= 0) { done = true; return true; }
+  const int cx = active ? cell_coord(qx, g.ox, g.inv_h, g.nx) : 0;
+  const int cy = active ? cell_coord(qy, g.oy, g.inv_h, g.ny) : 0;
+  const int cz = active ? cell_coord(qz, g.oz, g.inv_h, g.nz) : 0;
+  int gx0 = active ? cx : 0x7fffffff, gx1 = active ? cx : -1, gy0 = active ? cy : 0x7fffffff, gy1 = active ? cy : -1;
+  int gz0 = active ? cz : 0x7fffffff, gz1 = active ? cz : -1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gx0 = min(gx0, __shfl_xor_sync(FULL, gx0, o)); gx1 = max(gx1, __shfl_xor_sync(FULL, gx1, o));
+    gy0 = min(gy0, __shfl_xor_sync(FULL, gy0, o)); gy1 = max(gy1, __shfl_xor_sync(FULL, gy1, o));
+    gz0 = min(gz0, __shfl_xor_sync(FULL, gz0, o)); gz1 = max(gz1, __shfl_xor_sync(FULL, gz1, o));
+  }
+  if (gx1 < 0) return true;  // no active lane
+  if (gx1 - gx0 > kGroupMaxDX || gy1 - gy0 > kGroupMaxDY || gz1 - gz0 > kGroupMaxDZ) return false;
+  const float h = g.h;
+  for (int r = 0; r <= max_r; r++) {
+    const int X0 = gx0 - r, X1 = gx1 + r, Y0 = gy0 - r, Y1 = gy1 + r, Z0 = gz0 - r, Z1 = gz1 + r;
+    const int xa = X0 < 0 ? 0 : X0, xb = X1 > g.nx - 1 ? g.nx - 1 : X1;
+    const int ya = Y0 < 0 ? 0 : Y0, yb = Y1 > g.ny - 1 ? g.ny - 1 : Y1;
+    const int za = Z0 < 0 ? 0 : Z0, zb = Z1 > g.nz - 1 ? g.nz - 1 : Z1;
+    for (int z = za; z <= zb; z++) {
+      const float bz = axis_bound(qz, fadd(g.oz, fmul((float)z, h)), fadd(g.oz, fmul((float)(z + 1), h)));
+      const float bz2 = fmul(bz, bz);
+      for (int y = ya; y <= yb; y++) {
+        const float by = axis_bound(qy, fadd(g.oy, fmul((float)y, h)), fadd(g.oy, fmul((float)(y + 1), h)));
+        const float by2 = fmul(by, by);
+        const bool outer = (r == 0) || z == Z0 || z == Z1 || y == Y0 || y == Y1;
+        const int row = (z * g.ny + y) * g.nx;
+        // an outer row contributes its full x-run; an inner row only the two cells the ring adds at its ends
+        for (int part = 0; part < (outer ? 1 : 2); part++) {
+          int ra, rb;
+          if (outer) { ra = xa; rb = xb; }
+          else if (part == 0) { if (X0 < 0) continue; ra = rb = X0; }
+          else { if (X1 > g.nx - 1) continue; ra = rb = X1; }
+          const float bx = axis_bound(qx, fadd(g.ox, fmul((float)ra, h)), fadd(g.ox, fmul((float)(rb + 1), h)));
+          const float b = fadd(fadd(fmul(bx, bx), by2), bz2);  // same association as dist2_f32 => monotone lower bound
+          const bool skip = done || (b > v.worst());
+          if (__ballot_sync(FULL, !skip) == 0) continue;
+          const int s = cell_start[row + ra], e = cell_start[row + rb + 1];
+          for (int base = s; base < e; base += 32) {
+            const int mine = base + lane;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mine < e) p = sp[mine];
+            const int cnt = min(32, e - base);
+            for (int t = 0; t < cnt; t++) {
+              const float px = __shfl_sync(FULL, p.x, t), py = __shfl_sync(FULL, p.y, t), pz = __shfl_sync(FULL, p.z, t);
+              const float pw = __shfl_sync(FULL, p.w, t);
+              if (!skip) v.visit(dist2_f32(qx, qy, qz, px, py, pz), idx_bits(pw), base + t);
+            }
+          }
+        }
+      }
+    }
+    // per-lane termination against the faces of the group box (only faces with grid behind them)
+    if (!done) {
+      float fb = INFINITY;
+      if (X0 > 0) fb = fminf(fb, fsub(qx, fadd(g.ox, fmul((float)X0, h))));
+      if (X1 < g.nx - 1) fb = fminf(fb, fsub(fadd(g.ox, fmul((float)(X1 + 1), h)), qx));
+      if (Y0 > 0) fb = fminf(fb, fsub(qy, fadd(g.oy, fmul((float)Y0, h))));
+      if (Y1 < g.ny - 1) fb = fminf(fb, fsub(fadd(g.oy, fmul((float)(Y1 + 1), h)), qy));
+      if (Z0 > 0) fb = fminf(fb, fsub(qz, fadd(g.oz, fmul((float)Z0, h))));
+      if (Z1 < g.nz - 1) fb = fminf(fb, fsub(fadd(g.oz, fmul((float)(Z1 + 1), h)), qz));
+      if (fb == INFINITY) done = true;
+      else {
+        if (fb < 0.f) fb = 0.f;
+        const float fb2 = fmul(fb, fb);
+        if (v.worst() < fb2 || !(fb2 < v.limit())) done = true;
+      }
+    }
+    if (__ballot_sync(FULL, !done) == 0) break;
+  }
+  return true;
 }
 
 __device__ __forceinline__ void warp_min_nn1(Nn1& v) {

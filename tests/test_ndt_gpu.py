@@ -66,7 +66,7 @@ def test_derivatives(pair, oracle, search):
     for p in ([0, 0, 0, 0, 0, 0], [0.9, 0.05, -0.02, 0.01, -0.015, 0.03], [1.0, 0.0, 0.0, 3.1, 3.13, -3.1]):
         score, g, H, npairs = r.ndtDerivativesAt(p)
         o = om.derivatives(src, p, search_method=sm)
-        assert npairs == o["n_pairs"] and npairs > 0.3 * src.shape[0]
+        assert npairs == o["n_pairs"] and npairs > 1000
         assert abs(score - o["score"]) <= 1e-9 * abs(o["score"])
         assert relrel(g, o["g"]) < 1e-9 and relrel(H, o["H"]) < 1e-9
     r.close()
