@@ -1,0 +1,128 @@
+// b200_registration.hpp — the pcl::Registration adapter a maintainer of koide3/hdl_graph_slam adds to use libb200reg.so.
+//
+// It derives from pcl::Registration<PointT, PointT>, so the object returned by select_registration_method()
+// (/root/reference/src/hdl_graph_slam/registrations.cpp:22-124) keeps its type and every caller stays untouched:
+//   ScanMatchingOdometryNodelet  apps/scan_matching_odometry_nodelet.cpp:172,177,210,214,220,246,307,316
+//   LoopDetector                 include/hdl_graph_slam/loop_detector.hpp:122,136,143,146,147,153
+// Compiled only where PCL/Eigen exist (not in this repository's image; tests/test_adapter_syntax.py checks it against
+// adapter/pcl_shim.hpp, a 1-to-1 stand-in for the few PCL/Eigen declarations used here).  See INTEGRATION.md.
+#pragma once
+#include <b200reg.h>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace hdl_graph_slam {
+
+template <typename PointT>
+class B200Registration : public pcl::Registration<PointT, PointT> {
+public:
+  using Base = pcl::Registration<PointT, PointT>;
+  using PointCloudSource = typename Base::PointCloudSource;
+  using PointCloudSourceConstPtr = typename Base::PointCloudSourceConstPtr;
+  using PointCloudTargetConstPtr = typename Base::PointCloudTargetConstPtr;
+  using Matrix4 = typename Base::Matrix4;
+  using Ptr = std::shared_ptr<B200Registration<PointT>>;
+
+  // NN-search stub installed as the base class' target search with force_no_recompute = true, so that the non-virtual
+  // pcl::Registration::align() -> initCompute() does not rebuild a FLANN kd-tree over every new target (SURVEY.md §8b
+  // "hidden base-class cost").  nearestKSearch(pt, 1, ...) — the only call the reference makes on it
+  // (scan_matching_odometry_nodelet.cpp:316) — forwards to the device grid.
+  class DeviceSearch : public pcl::search::Search<PointT> {
+  public:
+    explicit DeviceSearch(b2r_handle* h) : pcl::search::Search<PointT>("b200"), h_(h) {}
+    void setInputCloud(const typename pcl::search::Search<PointT>::PointCloudConstPtr&, const typename pcl::search::Search<PointT>::IndicesConstPtr& = typename pcl::search::Search<PointT>::IndicesConstPtr()) override {}
+    int nearestKSearch(const PointT& p, int k, std::vector<int>& idx, std::vector<float>& d2) const override {
+      idx.assign(1, -1);
+      d2.assign(1, std::numeric_limits<float>::max());
+      if (k < 1) return 0;
+      int32_t i = -1;
+      float d = 0.f;
+      if (b2r_target_nearest(h_, &p, 1, sizeof(PointT), &i, &d) != B2R_OK || i < 0) return 0;
+      idx[0] = i;
+      d2[0] = d;
+      return 1;
+    }
+    int radiusSearch(const PointT&, double, std::vector<int>& idx, std::vector<float>& d2, unsigned int = 0) const override {
+      idx.clear();
+      d2.clear();
+      return 0;  // not used by hdl_graph_slam on the registration's search object
+    }
+
+  private:
+    b2r_handle* h_;
+  };
+
+  explicit B200Registration(const b2r_config& cfg) {
+    if (b2r_create(&cfg, &h_) != B2R_OK) throw std::runtime_error(std::string("b200reg: ") + b2r_last_error());
+    this->reg_name_ = cfg.method == B2R_METHOD_GICP ? "B200_GICP" : "B200_NDT";
+    this->max_iterations_ = cfg.max_iterations;
+    this->transformation_epsilon_ = cfg.transformation_epsilon;
+    this->corr_dist_threshold_ = cfg.max_correspondence_distance;
+    this->setSearchMethodTarget(typename pcl::search::Search<PointT>::Ptr(new DeviceSearch(h_)), /*force_no_recompute=*/true);
+  }
+  ~B200Registration() override { b2r_destroy(h_); }
+
+  void setInputSource(const PointCloudSourceConstPtr& cloud) override {
+    if (cloud == this->input_) return;  // same early-out as fast_gicp
+    Base::setInputSource(cloud);
+    b2r_set_source(h_, cloud->points.data(), cloud->points.size(), sizeof(PointT));
+  }
+
+  void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
+    if (cloud == this->target_) return;
+    const bool promote = (cloud == this->input_);  // keyframe switch: the last source becomes the target (:245-246)
+    Base::setInputTarget(cloud);
+    if (promote) b2r_promote_source_to_target(h_);
+    else b2r_set_target(h_, cloud->points.data(), cloud->points.size(), sizeof(PointT));
+  }
+
+  // getFitnessScore is NOT virtual in pcl::Registration, but both reference callers invoke it through the base pointer;
+  // the base implementation keeps working because it only needs tree_->nearestKSearch (DeviceSearch above).  Callers that
+  // hold the concrete type get the single-kernel version:
+  double getFitnessScoreDevice(double max_range = std::numeric_limits<double>::max()) {
+    double score = std::numeric_limits<double>::max();
+    b2r_fitness(h_, nullptr, max_range, 0.25f, &score, nullptr, nullptr);
+    return score;
+  }
+
+  b2r_handle* handle() { return h_; }
+
+protected:
+  // pcl::Registration::align() copies the source into `output`, then calls this
+  void computeTransformation(PointCloudSource& output, const Matrix4& guess) override {
+    b2r_result r;
+    const int rc = b2r_align(h_, guess.data(), &r);  // Eigen::Matrix4f is column-major, like the ABI
+    this->converged_ = (rc == B2R_OK) && r.converged;
+    this->nr_iterations_ = r.iterations;
+    for (int i = 0; i < 16; i++) this->final_transformation_.data()[i] = r.T[i];
+    this->transformation_ = this->final_transformation_;
+    // `output` feeds the inlier loop of the status publisher (scan_matching_odometry_nodelet.cpp:314-316)
+    if (rc == B2R_OK && !output.points.empty()) b2r_get_aligned(h_, output.points.data(), output.points.size(), sizeof(PointT));
+  }
+
+private:
+  b2r_handle* h_ = nullptr;
+};
+
+// The branch added to select_registration_method() (registrations.cpp:27-124), mirroring the USE_VGICP_CUDA pattern
+// of registrations.cpp:16-18,37-47 / CMakeLists.txt:56-60:
+//
+//   #ifdef USE_B200REG
+//     else if(registration_method == "B200_GICP" || registration_method == "B200_NDT") {
+//       b2r_config cfg;
+//       b2r_config_default(&cfg, registration_method == "B200_GICP" ? B2R_METHOD_GICP : B2R_METHOD_NDT);
+//       cfg.transformation_epsilon = pnh.param<double>("reg_transformation_epsilon", 0.01);
+//       cfg.max_iterations = pnh.param<int>("reg_maximum_iterations", 64);
+//       cfg.max_correspondence_distance = pnh.param<double>("reg_max_correspondence_distance", 2.5);
+//       cfg.k_correspondences = pnh.param<int>("reg_correspondence_randomness", 20);
+//       cfg.ndt_resolution = pnh.param<double>("reg_resolution", 0.5);
+//       cfg.ndt_search_method = pnh.param<std::string>("reg_nn_search_method", "DIRECT7") == "DIRECT1" ? 1 : 7;
+//       cfg.device_id = pnh.param<int>("reg_device_id", 0);
+//       return pcl::Registration<PointT, PointT>::Ptr(new B200Registration<PointT>(cfg));
+//     }
+//   #endif
+
+}  // namespace hdl_graph_slam
