@@ -168,7 +168,7 @@ def algorithmic_bytes(cls, n, m, stride_bytes):
         "knn_covariance": n * 16 + n * 48,
         "gicp_correspond_linearize": 64 * (n + m) + 8 * n + 28 * 8,
         "gicp_error": n * (16 + 4 + 48) + m * 16 + 8,
-        "grid_build": n * (stride_bytes + 16 + 4 + 4),
+        "bvh_build": n * (stride_bytes + 16 + 4 + 16),
         "nn_fitness": n * 16 + m * 16 + 24,
         "ndt_derivatives": n * 16 + 43 * 8,  # + V*112 voxel records, added by the caller when V is known
         "ndt_voxel_build": m * 16,

@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 #include "engine.cuh"
 #include "gicp.cuh"
 #include "fitness.cuh"
@@ -48,8 +49,9 @@ struct b2r_handle {
   DevBuf<float> tmp_f;
   DevBuf<int> tmp_i;
   DevBuf<float4> tmp_f4;
-  DevBuf<int> hard_list;
-  DevBuf<float> hard_bound;
+  DevBuf<unsigned int> keys_a, keys_b;
+  DevBuf<int> vals_a, vals_b;
+  DevBuf<char> sort_tmp;
   // last result
   float final_T[16];                // row-major
   bool has_final = false;
@@ -123,11 +125,7 @@ extern "C" int b2r_select_registration_method(const char* const* keys, const cha
   return b2r_create(&c, out);
 }
 
-static int alloc_cloud(Cloud& c) {
-  B2R_CUDA(cudaMalloc(&c.grid, sizeof(Grid)));
-  B2R_CUDA(c.cell_start.reserve(kCellCap + 1 - 72));  // reserve() pads by n/8+64; exact size is irrelevant, >= kCellCap+1
-  return B2R_OK;
-}
+static int alloc_cloud(Cloud&) { return B2R_OK; }
 
 extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   if (!cfg || !out) return fail(B2R_EINVAL, "NULL argument");
@@ -154,12 +152,9 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     if (rc) return bail(rc);
     if (cudaEventCreateWithFlags(&h->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   }
-  if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scr.counts, (size_t)kCellCap * sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&h->scr.cursor, (size_t)kCellCap * sizeof(int)) != cudaSuccess || cudaMalloc(&h->scr.bsum, (size_t)kScanBlocks * sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess || cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess ||
-      cudaMallocHost(&h->h_out, 64 * sizeof(double)) != cudaSuccess)
+  if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMallocHost(&h->h_out, 64 * sizeof(double)) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "device allocation failed"));
-  cudaMemsetAsync(h->scr.counts, 0, (size_t)kCellCap * sizeof(int), h->st);
   cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -176,8 +171,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   for (int i = 0; i < 2; i++) {
     Cloud& c = h->clouds[i];
-    c.raw.release(); c.cell_start.release(); c.sorted.release(); c.pos_of.release(); c.cov.release();
-    if (c.grid) cudaFree(c.grid);
+    c.raw.release(); c.sorted.release(); c.leaf_lo.release(); c.leaf_hi.release(); c.sup_lo.release(); c.sup_hi.release(); c.pos_of.release(); c.cov.release();
     ndt_free_map(c.ndt);
     if (h->staging[i]) cudaFreeHost(h->staging[i]);
     if (h->staging_ev[i]) cudaEventDestroy(h->staging_ev[i]);
@@ -188,7 +182,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->scr.bsum) cudaFree(h->scr.bsum);
   h->scr.cell_of.release(); h->scr.tmp_idx.release();
   h->corr.release(); h->cpos.release(); h->d2.release(); h->mahal.release(); h->partials.release();
-  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->hard_list.release(); h->hard_bound.release();
+  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->keys_a.release(); h->keys_b.release(); h->vals_a.release(); h->vals_b.release(); h->sort_tmp.release();
   h->ndt_work.release();
   h->vg_work.release();
   h->tel.release();
@@ -252,21 +246,36 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
   return B2R_OK;
 }
 
-static int ensure_grid(b2r_handle* h, Cloud& c) {
-  if (c.grid_ready) return B2R_OK;
+static int ensure_grid(b2r_handle* h, Cloud& c) {  // builds the implicit BVH (name kept from the first design)
+  if (c.bvh_ready) return B2R_OK;
   const size_t n = c.n;
-  B2R_CUDA(c.sorted.reserve(n + 1));
+  const int N = (int)n;
+  c.nsup = (int)((n + 1023) / 1024);
+  const size_t padded = (size_t)c.nsup * 1024;
+  B2R_CUDA(c.sorted.reserve(padded + 32));
   B2R_CUDA(c.pos_of.reserve(n + 1));
-  B2R_CUDA(h->scr.cell_of.reserve(n + 1));
-  B2R_CUDA(h->scr.tmp_idx.reserve(n + 1));
-  GridBuffers B;
-  B.grid = c.grid; B.mm = h->scr.mm; B.counts = h->scr.counts; B.cell_start = c.cell_start.p; B.cursor = h->scr.cursor;
-  B.bsum = h->scr.bsum; B.cell_of = h->scr.cell_of.p; B.tmp_idx = h->scr.tmp_idx.p; B.sorted = c.sorted.p; B.pos_of = c.pos_of.p;
-  { TEL_BEGIN(&h->tel, h->st);
-    build_grid(c.raw_view, c.stride_f, (int)n, h->cfg.grid_cell_min, B, h->st);
-    TEL_END(&h->tel, KC_GRID, n > 0 ? 10 : 5, h->st); }
+  B2R_CUDA(c.leaf_lo.reserve((size_t)c.nsup * kSuper + 1));
+  B2R_CUDA(c.leaf_hi.reserve((size_t)c.nsup * kSuper + 1));
+  B2R_CUDA(c.sup_lo.reserve(c.nsup + 1));
+  B2R_CUDA(c.sup_hi.reserve(c.nsup + 1));
+  if (n == 0) { c.bvh_ready = true; return B2R_OK; }
+  B2R_CUDA(h->keys_a.reserve(n)); B2R_CUDA(h->keys_b.reserve(n)); B2R_CUDA(h->vals_a.reserve(n)); B2R_CUDA(h->vals_b.reserve(n));
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys_a.p, h->keys_b.p, h->vals_a.p, h->vals_b.p, N, 0, 32, h->st);
+  B2R_CUDA(h->sort_tmp.reserve(tmp_bytes + 256));
+  TEL_BEGIN(&h->tel, h->st);
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  k_grid_reset<<<1, 32, 0, h->st>>>(h->scr.mm);
+  k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, h->st>>>(c.raw_view, c.stride_f, N, h->scr.mm);
+  k_fill_i32<<<nb, 256, 0, h->st>>>(c.pos_of.p, N, -1);
+  k_morton_keys<<<nb, 256, 0, h->st>>>(c.raw_view, c.stride_f, N, h->scr.mm, h->keys_a.p, h->vals_a.p);
+  size_t tb = h->sort_tmp.cap;
+  cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->keys_a.p, h->keys_b.p, h->vals_a.p, h->vals_b.p, N, 0, 32, h->st);  // stable: ties keep ascending index
+  k_bvh_leaves<<<c.nsup, 1024, 0, h->st>>>(c.raw_view, c.stride_f, N, h->keys_b.p, h->vals_b.p, c.sorted.p, c.pos_of.p, c.leaf_lo.p, c.leaf_hi.p,
+                                           c.sup_lo.p, c.sup_hi.p);
+  TEL_END(&h->tel, KC_GRID, 10, h->st);
   B2R_CUDA(cudaGetLastError());
-  c.grid_ready = true;
+  c.bvh_ready = true;
   return B2R_OK;
 }
 
@@ -274,9 +283,9 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
   int rc = ensure_grid(h, c);
   if (rc) return rc;
   if (c.cov_ready) return B2R_OK;
-  const size_t n = c.n;
-  B2R_CUDA(c.cov.reserve(n * 6 + 6));
-  if (n > 0) {
+  const size_t padded = (size_t)c.nsup * 1024;
+  B2R_CUDA(c.cov.reserve(padded * 6 + 6));
+  if (c.n > 0) {
     const int k = h->cfg.k_correspondences;
     const size_t smem = (size_t)2 * k * kKnnThreads * sizeof(float);
     static bool attr_set = false;
@@ -284,16 +293,9 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
       B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 2 * kKnnThreads * 4));
       attr_set = true;
     }
-    B2R_CUDA(h->hard_list.reserve(n + 1));
-    B2R_CUDA(h->hard_bound.reserve(n + 1));
-    const size_t smem2 = (size_t)kKnnHardWarps * (2 * k * 32 + k) * sizeof(float);
     TEL_BEGIN(&h->tel, h->st);
-    B2R_CUDA(cudaMemsetAsync(h->d_counter + 3, 0, sizeof(int), h->st));
-    k_knn_cov<<<(unsigned)((n + kKnnThreads - 1) / kKnnThreads), kKnnThreads, smem, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p,
-                                                                                            h->hard_list.p, h->hard_bound.p, (int*)(h->d_counter + 3));
-    k_knn_cov_hard<<<148 * 4, kKnnHardWarps * 32, smem2, h->st>>>(c.grid, c.cell_start.p, c.sorted.p, k, c.cov.p, h->hard_list.p, h->hard_bound.p,
-                                                                   (const int*)(h->d_counter + 3));
-    TEL_END(&h->tel, KC_KNN_COV, 2, h->st);
+    k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(c.bvh(), k, c.cov.p);
+    TEL_END(&h->tel, KC_KNN_COV, 1, h->st);
     B2R_CUDA(cudaGetLastError());
   }
   c.cov_ready = true;
@@ -375,7 +377,8 @@ static void make_pose(const double* x, PoseArg& P) {
   for (int i = 0; i < 12; i++) { P.T[i] = x[i]; P.Tf[i] = (float)x[i]; }
 }
 
-static int ensure_align_ws(b2r_handle* h, size_t n) {
+static int ensure_align_ws(b2r_handle* h, size_t n_in) {
+  const size_t n = ((n_in + 1023) / 1024) * 1024;
   B2R_CUDA(h->corr.reserve(n + 1));
   B2R_CUDA(h->cpos.reserve(n + 1));
   B2R_CUDA(h->d2.reserve(n + 1));
@@ -389,8 +392,8 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
   LinArgs A;
-  A.sgrid = s.grid; A.ssp = s.sorted.p; A.scov = s.cov.p;
-  A.tgrid = t.grid; A.tcell_start = t.cell_start.p; A.tsp = t.sorted.p; A.tcov = t.cov.p;
+  A.src = s.bvh(); A.scov = s.cov.p;
+  A.tgt = t.bvh(); A.tcov = t.cov.p;
   const double thr = h->cfg.max_correspondence_distance;
   A.thr2 = thr * thr;
   float lim = (float)A.thr2;
@@ -401,7 +404,7 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
   A.use_seed = seed ? 1 : 0;
   PoseArg P;
   make_pose(x0, P);
-  const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
+  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
   { TEL_BEGIN(&h->tel, h->st);
     k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
@@ -423,11 +426,11 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
   ErrArgs A;
-  A.sgrid = s.grid; A.ssp = s.sorted.p; A.tsp = t.sorted.p; A.cpos = h->cpos.p; A.mahal = h->mahal.p;
+  A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos.p; A.mahal = h->mahal.p;
   A.partials = h->partials.p; A.out = h->d_out + 32; A.counter = h->d_counter + 1;
   PoseArg P;
   make_pose(xi, P);
-  const unsigned nb = (unsigned)((s.n + kLinThreads - 1) / kLinThreads);
+  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
   { TEL_BEGIN(&h->tel, h->st);
     k_gicp_error<<<nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_ERR, 1, h->st); }
@@ -581,11 +584,10 @@ static int fitness_impl(b2r_handle* h, const float* T_row, double max_range, flo
   if (rc) return rc;
   rc = ensure_grid(h, s);
   if (rc) return rc;
-  size_t nb = (s.n + kLinThreads - 1) / kLinThreads;
+  size_t nb = (size_t)s.nsup * 1024 / kLinThreads;
   B2R_CUDA(h->partials.reserve(nb * kAcc + kAcc));
   FitArgs A;
-  A.sgrid = s.grid; A.ssp = s.sorted.p;
-  A.tgrid = t.grid; A.tcell_start = t.cell_start.p; A.tsp = t.sorted.p;
+  A.src = s.bvh(); A.tgt = t.bvh();
   for (int i = 0; i < 12; i++) A.Tf[i] = T_row[i];
   A.max_range = max_range; A.inlier_thresh_sq = inl;
   A.partials = h->partials.p; A.out = h->d_out + 40; A.counter = h->d_counter + 2;
@@ -631,7 +633,7 @@ extern "C" int b2r_target_nearest(b2r_handle* h, const void* queries, size_t n, 
   B2R_CUDA(cudaMemcpyAsync(h->tmp_f.p, queries, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
   float* d2d = h->tmp_f.p + n * sf;
   { TEL_BEGIN(&h->tel, h->st);
-    k_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, sf, (int)n, t.grid, t.cell_start.p, t.sorted.p, h->tmp_i.p, d2d);
+    k_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, sf, (int)n, t.bvh(), h->tmp_i.p, d2d);
     TEL_END(&h->tel, KC_MISC, 1, h->st); }
   h->tel.h2d += n * stride_bytes;
   h->tel.d2h += n * 8;
@@ -660,9 +662,10 @@ extern "C" int b2r_get_covariances(b2r_handle* h, int which, double* out, size_t
   if (n != c.n) return fail(B2R_EINVAL, "n does not match the cloud");
   int rc = ensure_cov(h, c);
   if (rc) return rc;
-  std::vector<double> cov(n * 6);
+  const size_t padded = (size_t)c.nsup * 1024;
+  std::vector<double> cov(padded * 6 + 6);
   std::vector<int> pos(n);
-  B2R_CUDA(cudaMemcpyAsync(cov.data(), c.cov.p, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaMemcpyAsync(cov.data(), c.cov.p, padded * 6 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   B2R_CUDA(cudaMemcpyAsync(pos.data(), c.pos_of.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   B2R_CUDA(cudaStreamSynchronize(h->st));
   for (size_t i = 0; i < n; i++) {

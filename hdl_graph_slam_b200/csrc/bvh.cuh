@@ -1,0 +1,256 @@
+// bvh.cuh — exact nearest-neighbour search over a two-level implicit BVH (Morton-ordered 32-point leaves).
+//
+// Replaces the FLANN kd-tree queries the reference's registration handle performs (fast_gicp update_correspondences /
+// calculate_covariances, pcl::Registration::getFitnessScore; call sites apps/scan_matching_odometry_nodelet.cpp:210,307,316,
+// include/hdl_graph_slam/loop_detector.hpp:143,146) and the kd-tree builds at setInputSource/Target (:172,177,246; :122,136).
+//
+// Structure (per cloud): points sorted by (30-bit Morton key, original index); leaf L = sorted[32L .. 32L+31] with a tight
+// AABB; super-node S = leaves [32S .. 32S+31] with a tight AABB.  LiDAR density varies by 3 orders of magnitude between the
+// near and the far field; fixed-size leaves adapt to it (profiles/r01_b shows why a uniform grid does not).
+//
+// Search = "warp group": the 32 lanes of a warp hold 32 queries that are neighbours in space (a leaf of the query cloud).
+// A leaf of the target is visited if ANY lane still needs it; its 32 points are then tested by all lanes (all-pairs tile).
+//
+// Result contract (oracle/kdtree.hpp): the lexicographically smallest (d2, original index), d2 = ((dx*dx+dy*dy)+dz*dz) in
+// non-contracted float32.  Exactness: the AABB bound is assembled from face distances in the same operation order, so by
+// monotone rounding it never exceeds the d2 of any point inside the box; a leaf is skipped for a lane only if
+// bound > worst (strict) — equal-distance lower-index candidates stay reachable.  No cell quantisation is involved in the
+// decision logic (the Morton key only orders the points), so no representability argument is needed.
+#pragma once
+#include "common.cuh"
+
+namespace b2r {
+
+constexpr int kLeaf = 32;
+constexpr int kSuper = 32;  // leaves per super-node
+constexpr int kPadIdx = 0x7fffffff;
+
+struct Bvh {
+  const float4* sp;       // [nleaf*32] (x,y,z,bits(orig idx)); padding = (+inf,+inf,+inf, kPadIdx)
+  const float4* leaf_lo;  // [nleaf]
+  const float4* leaf_hi;
+  const float4* sup_lo;   // [nsup]
+  const float4* sup_hi;
+  int nleaf, nsup, n;
+};
+
+B2R_HD unsigned int morton_spread10(unsigned int v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+// lower bound of dist2_f32(q, p) for every p inside [lo, hi] (same association as dist2_f32)
+B2R_HD float aabb_bound2(float qx, float qy, float qz, float lx, float ly, float lz, float hx, float hy, float hz) {
+  float bx = 0.f, by = 0.f, bz = 0.f;
+  if (qx < lx) bx = fsub(lx, qx); else if (qx > hx) bx = fsub(qx, hx);
+  if (qy < ly) by = fsub(ly, qy); else if (qy > hy) by = fsub(qy, hy);
+  if (qz < lz) bz = fsub(lz, qz); else if (qz > hz) bz = fsub(qz, hz);
+  return fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
+}
+
+// 1-NN visitor
+struct Nn1 {
+  float best_d2;
+  int best_idx;
+  int best_pos;
+  float lim;
+  B2R_HD float worst() const { return best_d2; }
+  B2R_HD float limit() const { return lim; }
+  B2R_HD void visit(float d2, int idx, int pos) {
+    if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) {
+      best_d2 = d2;
+      best_idx = idx;
+      best_pos = pos;
+    }
+  }
+};
+
+// host/device serial reference of the traversal for ONE query (used by tests/host_harness.cu and as documentation of the
+// pruning rule; the device path below makes the same per-lane decisions, only warp-wide)
+template <class Visitor>
+B2R_HD void bvh_search_one(const Bvh& b, float qx, float qy, float qz, Visitor& v) {
+  for (int s = 0; s < b.nsup; s++) {
+    const float4 slo = b.sup_lo[s], shi = b.sup_hi[s];
+    const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+    if (sb > v.worst() || !(sb < v.limit())) continue;
+    const int l1 = (s + 1) * kSuper < b.nleaf ? (s + 1) * kSuper : b.nleaf;
+    for (int l = s * kSuper; l < l1; l++) {
+      const float4 lo = b.leaf_lo[l], hi = b.leaf_hi[l];
+      const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+      if (lb > v.worst() || !(lb < v.limit())) continue;
+      for (int t = 0; t < kLeaf; t++) {
+        const float4 p = b.sp[l * kLeaf + t];
+        const int idx = idx_bits(p.w);
+        if (idx == kPadIdx) continue;
+        v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx, l * kLeaf + t);
+      }
+    }
+  }
+}
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------ build kernels
+__global__ void k_morton_keys(const float* __restrict__ raw, int stride_f, int n, const int* __restrict__ mm, unsigned int* keys, int* vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = raw + (size_t)i * stride_f;
+  const float x = p[0], y = p[1], z = p[2];
+  unsigned int key = 0xffffffffu;  // non-finite points sort last and are dropped from the structure
+  if (finite3(x, y, z)) {
+    const float mnx = ord2f(mm[0]), mny = ord2f(mm[1]), mnz = ord2f(mm[2]);
+    const float ext = fmaxf(fmaxf(ord2f(mm[3]) - mnx, ord2f(mm[4]) - mny), fmaxf(ord2f(mm[5]) - mnz, 1.0e-6f));
+    const float sc = 1023.0f / ext;
+    const unsigned int ix = (unsigned int)fminf(fmaxf((x - mnx) * sc, 0.f), 1023.f);
+    const unsigned int iy = (unsigned int)fminf(fmaxf((y - mny) * sc, 0.f), 1023.f);
+    const unsigned int iz = (unsigned int)fminf(fmaxf((z - mnz) * sc, 0.f), 1023.f);
+    key = morton_spread10(ix) | (morton_spread10(iy) << 1) | (morton_spread10(iz) << 2);
+  }
+  keys[i] = key;
+  vals[i] = i;
+}
+
+// one block = 1024 threads = 32 leaves = one super-node
+__global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ raw, int stride_f, int n, const unsigned int* __restrict__ keys_sorted,
+                                                     const int* __restrict__ vals_sorted, float4* sorted, int* pos_of, float4* leaf_lo,
+                                                     float4* leaf_hi, float4* sup_lo, float4* sup_hi) {
+  __shared__ float s_lo[32][3], s_hi[32][3];
+  const int s = blockIdx.x * 1024 + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float x = INFINITY, y = INFINITY, z = INFINITY;
+  int idx = kPadIdx;
+  if (s < n && keys_sorted[s] != 0xffffffffu) {
+    idx = vals_sorted[s];
+    const float* p = raw + (size_t)idx * stride_f;
+    x = p[0]; y = p[1]; z = p[2];
+    pos_of[idx] = s;
+  }
+  sorted[s] = make_float4(x, y, z, bits_idx(idx));
+  const bool valid = idx != kPadIdx;
+  float lx = valid ? x : INFINITY, ly = valid ? y : INFINITY, lz = valid ? z : INFINITY;
+  float hx = valid ? x : -INFINITY, hy = valid ? y : -INFINITY, hz = valid ? z : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+    hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+  }
+  const int leaf = blockIdx.x * 32 + warp;
+  if (lane == 0) {
+    leaf_lo[leaf] = make_float4(lx, ly, lz, 0.f);
+    leaf_hi[leaf] = make_float4(hx, hy, hz, 0.f);
+    s_lo[warp][0] = lx; s_lo[warp][1] = ly; s_lo[warp][2] = lz;
+    s_hi[warp][0] = hx; s_hi[warp][1] = hy; s_hi[warp][2] = hz;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float ax = s_lo[lane][0], ay = s_lo[lane][1], az = s_lo[lane][2], bx = s_hi[lane][0], by = s_hi[lane][1], bz = s_hi[lane][2];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ax = fminf(ax, __shfl_xor_sync(0xffffffffu, ax, o)); ay = fminf(ay, __shfl_xor_sync(0xffffffffu, ay, o)); az = fminf(az, __shfl_xor_sync(0xffffffffu, az, o));
+      bx = fmaxf(bx, __shfl_xor_sync(0xffffffffu, bx, o)); by = fmaxf(by, __shfl_xor_sync(0xffffffffu, by, o)); bz = fmaxf(bz, __shfl_xor_sync(0xffffffffu, bz, o));
+    }
+    if (lane == 0) {
+      sup_lo[blockIdx.x] = make_float4(ax, ay, az, 0.f);
+      sup_hi[blockIdx.x] = make_float4(bx, by, bz, 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ warp-group traversal
+// All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
+//   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
+// Order: own leaf, then the super-node nearest to the group's AABB, then all remaining super-nodes by index.
+template <class Visitor>
+__device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
+  const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
+#pragma unroll 8
+  for (int t = 0; t < kLeaf; t++) {
+    const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
+    const int idx = idx_bits(p.w);
+    if (pass && idx != kPadIdx) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx, l * kLeaf + t);
+  }
+}
+
+template <class Visitor>
+__device__ __forceinline__ void bvh_visit_super(const Bvh& b, int s, int skip_leaf, int skip_leaf2, float qx, float qy, float qz, bool active, Visitor& v) {
+  const unsigned FULL = 0xffffffffu;
+  const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
+  const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+  const bool spass = active && !(sb > v.worst()) && (sb < v.limit());
+  if (__ballot_sync(FULL, spass) == 0) return;
+  const int l1 = min((s + 1) * kSuper, b.nleaf);
+  for (int l = s * kSuper; l < l1; l++) {
+    if (l == skip_leaf || l == skip_leaf2) continue;
+    const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
+    const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+    if (__ballot_sync(FULL, pass) == 0) continue;
+    bvh_visit_leaf(b, l, qx, qy, qz, pass, v);
+  }
+}
+
+template <class Visitor>
+__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
+  if (own_leaf >= 0) bvh_visit_leaf(b, own_leaf, qx, qy, qz, active, v);
+  // group AABB of the active queries
+  float glx = active ? qx : INFINITY, gly = active ? qy : INFINITY, glz = active ? qz : INFINITY;
+  float ghx = active ? qx : -INFINITY, ghy = active ? qy : -INFINITY, ghz = active ? qz : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    glx = fminf(glx, __shfl_xor_sync(FULL, glx, o)); gly = fminf(gly, __shfl_xor_sync(FULL, gly, o)); glz = fminf(glz, __shfl_xor_sync(FULL, glz, o));
+    ghx = fmaxf(ghx, __shfl_xor_sync(FULL, ghx, o)); ghy = fmaxf(ghy, __shfl_xor_sync(FULL, ghy, o)); ghz = fmaxf(ghz, __shfl_xor_sync(FULL, ghz, o));
+  }
+  const float gcx = 0.5f * (glx + ghx), gcy = 0.5f * (gly + ghy), gcz = 0.5f * (glz + ghz);
+  // nearest super-node to the group's centre (heuristic only: it decides the ORDER of the visits, never their outcome)
+  float bd = INFINITY;
+  int bs = 0;
+  for (int s = lane; s < b.nsup; s += 32) {
+    const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
+    const float d = aabb_bound2(gcx, gcy, gcz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+    if (d < bd) { bd = d; bs = s; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(FULL, bd, o);
+    const int os = __shfl_xor_sync(FULL, bs, o);
+    if (od < bd || (od == bd && os < bs)) { bd = od; bs = os; }
+  }
+  // inside it, the leaf nearest to the group's centre goes first so that a tight bound exists early
+  int bl = -1;
+  {
+    const int l = bs * kSuper + lane;
+    float ld = INFINITY;
+    if (l < b.nleaf && l != own_leaf) {
+      const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
+      ld = aabb_bound2(gcx, gcy, gcz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    }
+    int ll = l;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(FULL, ld, o);
+      const int ol = __shfl_xor_sync(FULL, ll, o);
+      if (od < ld || (od == ld && ol < ll)) { ld = od; ll = ol; }
+    }
+    if (ld < INFINITY) bl = ll;
+  }
+  if (bl >= 0) {
+    const float4 lo = __ldg(b.leaf_lo + bl), hi = __ldg(b.leaf_hi + bl);
+    const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+    const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+    if (__ballot_sync(FULL, pass)) bvh_visit_leaf(b, bl, qx, qy, qz, pass, v);
+  }
+  bvh_visit_super(b, bs, own_leaf, bl, qx, qy, qz, active, v);
+  for (int s = 0; s < b.nsup; s++) {
+    if (s == bs) continue;
+    bvh_visit_super(b, s, own_leaf, -1, qx, qy, qz, active, v);
+  }
+}
+#endif
+
+}  // namespace b2r

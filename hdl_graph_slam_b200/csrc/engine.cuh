@@ -8,6 +8,7 @@
 #include "../../include/b200reg.h"
 #include "common.cuh"
 #include "grid.cuh"
+#include "bvh.cuh"
 
 namespace b2r {
 
@@ -48,7 +49,7 @@ struct DevBuf {
 // ---- telemetry: copy byte counters, launch counters and (optional) CUDA-event timing per kernel class
 enum KernelClass { KC_GRID = 0, KC_KNN_COV, KC_GICP_LIN, KC_GICP_ERR, KC_FITNESS, KC_NDT_BUILD, KC_NDT_DERIV, KC_NDT_HESS, KC_VOXELGRID, KC_MISC, KC_COUNT };
 inline const char* kernel_class_name(int c) {
-  static const char* n[KC_COUNT] = {"grid_build", "knn_covariance", "gicp_correspond_linearize", "gicp_error", "nn_fitness", "ndt_voxel_build",
+  static const char* n[KC_COUNT] = {"bvh_build", "knn_covariance", "gicp_correspond_linearize", "gicp_error", "nn_fitness", "ndt_voxel_build",
                                     "ndt_derivatives", "ndt_hessian", "voxelgrid_downsample", "misc"};
   return (c >= 0 && c < KC_COUNT) ? n[c] : "?";
 }
@@ -108,25 +109,30 @@ struct NdtVoxelMap;  // ndt.cuh
 struct Cloud {
   size_t n = 0;
   int stride_f = 4;
-  const void* host_ptr = nullptr;  // identity of the host buffer last uploaded (promotion / reuse detection)
+  const void* host_ptr = nullptr;  // identity of the host buffer last uploaded
   DevBuf<float> raw;               // uploaded records
   const float* raw_view = nullptr; // == raw.p, or a caller-owned device pointer (set_*_device)
-  // search grid
-  Grid* grid = nullptr;
-  DevBuf<int> cell_start;          // kCellCap + 1
-  DevBuf<float4> sorted;
+  // implicit BVH (bvh.cuh)
+  DevBuf<float4> sorted, leaf_lo, leaf_hi, sup_lo, sup_hi;
   DevBuf<int> pos_of;
-  bool grid_ready = false;
+  int nsup = 0;
+  bool bvh_ready = false;
   // GICP
   DevBuf<double> cov;              // sorted order, 6 per point
   bool cov_ready = false;
   // NDT (target only)
   NdtVoxelMap* ndt = nullptr;
   bool ndt_ready = false;
-  void invalidate() { grid_ready = cov_ready = ndt_ready = false; }
+  void invalidate() { bvh_ready = cov_ready = ndt_ready = false; }
+  Bvh bvh() const {
+    Bvh b;
+    b.sp = sorted.p; b.leaf_lo = leaf_lo.p; b.leaf_hi = leaf_hi.p; b.sup_lo = sup_lo.p; b.sup_hi = sup_hi.p;
+    b.nsup = nsup; b.nleaf = nsup * kSuper; b.n = (int)n;
+    return b;
+  }
 };
 
-struct Scratch {  // build scratch shared by all builds of a handle (stream-ordered)
+struct Scratch {  // build scratch shared by all builds of a handle (stream-ordered); the dense tables serve the NDT voxel build only
   int* mm = nullptr;
   int* counts = nullptr;
   int* cursor = nullptr;

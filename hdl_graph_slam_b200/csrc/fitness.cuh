@@ -7,17 +7,14 @@
 // k_transform    <- the `aligned` cloud written by align() (pcl::transformPointCloud with final_transformation_)
 #pragma once
 #include "common.cuh"
-#include "nn_search.cuh"
+#include "bvh.cuh"
 #include "gicp.cuh"
 
 namespace b2r {
 
 struct FitArgs {
-  const Grid* sgrid;      // source grid: queries are taken in the source's sorted order (spatially coherent warps)
-  const float4* ssp;
-  const Grid* tgrid;
-  const int* tcell_start;
-  const float4* tsp;
+  Bvh src;                // queries = the source's sorted points (a warp = one leaf = spatial neighbours)
+  Bvh tgt;
   float Tf[12];
   double max_range;       // compared with the SQUARED distance (reference semantics)
   float inlier_thresh_sq;
@@ -26,31 +23,23 @@ struct FitArgs {
   unsigned int* counter;
 };
 
-__global__ void __launch_bounds__(kLinThreads, 2) k_fitness(FitArgs A) {
+__global__ void __launch_bounds__(kLinThreads, 2) k_fitness(const __grid_constant__ FitArgs A) {
   __shared__ double red[3 * 32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nv = A.sgrid->n_valid;
-  const Grid tg = *A.tgrid;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[3] = {0.0, 0.0, 0.0};
+  float4 p = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
   v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
-  bool need = false, active = false;
-  if (i < nv) {
-    const float4 p = A.ssp[i];
+  bool active = false;
+  if (idx_bits(p.w) != kPadIdx) {
     qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], p.x, p.y, p.z);
     qy = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], p.x, p.y, p.z);
     qz = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], p.x, p.y, p.z);
-    if (finite3(qx, qy, qz)) {
-      active = true;
-    }
+    active = finite3(qx, qy, qz);
   }
-  {
-    bool done = false;
-    if (!warp_group_search(tg, A.tcell_start, A.tsp, qx, qy, qz, active, v, 1, done)) done = !active || grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
-    need = active && !done;
-  }
-  warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);
+  bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);
   if (active && v.best_pos >= 0) {
     if ((double)v.best_d2 <= A.max_range) { acc[0] = (double)v.best_d2; acc[1] = 1.0; }
     if (v.best_d2 < A.inlier_thresh_sq) acc[2] = 1.0;
@@ -59,21 +48,20 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_fitness(FitArgs A) {
   finish_partials<3>(acc, A.partials, A.out, A.counter);
 }
 
-// queries in caller order (no spatial coherence guaranteed); n is rounded up to whole warps by the launcher
-__global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_raw, int stride_f, int n, const Grid* __restrict__ tgrid,
-                                                 const int* __restrict__ tcell_start, const float4* __restrict__ tsp, int* idx_out, float* d2_out) {
+// queries in caller order (no spatial coherence guaranteed: still exact, only less efficient)
+__global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_raw, int stride_f, int n, const __grid_constant__ Bvh tgt,
+                                                    int* idx_out, float* d2_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const Grid tg = *tgrid;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
   v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
-  bool need = false;
+  bool active = false;
   if (i < n) {
     const float* p = q_raw + (size_t)i * stride_f;
     qx = p[0]; qy = p[1]; qz = p[2];
-    if (finite3(qx, qy, qz)) need = !grid_search(tg, tcell_start, tsp, qx, qy, qz, v, 1);
+    active = finite3(qx, qy, qz);
   }
-  warp_finish_nn1(tg, tcell_start, tsp, qx, qy, qz, v, need);
+  bvh_group_search(tgt, qx, qy, qz, active, v, -1);
   if (i < n) {
     idx_out[i] = v.best_pos >= 0 ? v.best_idx : -1;
     d2_out[i] = v.best_d2;

@@ -6,11 +6,11 @@
 //   k_knn_cov          <- FastGICP::calculate_covariances (k exact NN, PLANE regularisation)
 //   k_gicp_linearize   <- FastGICP::update_correspondences + FastGICP::linearize (fused; M_i kept for the trial cost)
 //   k_gicp_error       <- FastGICP::compute_error
-// All per-cloud arrays live in the grid-sorted order (ascending cell, then original index), so neighbouring threads
-// search neighbouring cells; block partials are combined in a fixed order => bitwise reproducible results.
+// All per-cloud arrays live in the BVH's sorted order (Morton key, then original index): a warp = one 32-point leaf, so its
+// queries are spatial neighbours; block partials are combined in a fixed order => bitwise reproducible results.
 #pragma once
 #include "common.cuh"
-#include "nn_search.cuh"
+#include "bvh.cuh"
 #include "linalg.cuh"
 
 namespace b2r {
@@ -77,149 +77,26 @@ __device__ __forceinline__ void knn_cov_store(const float4* __restrict__ sp, int
   o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
 }
 
-constexpr int kKnnLocalR = 2;  // thread-local shells r = 0..2 (5x5x5 cells); anything sparser goes to the warp-cooperative kernel
-
-// phase 1: one thread per query (sorted order => a warp walks neighbouring cells), top-k lists in shared memory
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
-                                                         const float4* __restrict__ sp, int k, double* __restrict__ cov, int* hard_list,
-                                                         float* hard_bound, int* hard_count) {
+// one warp per leaf: its 32 points are the queries; per-lane top-k lists in shared memory
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, double* __restrict__ cov) {
   extern __shared__ float knn_smem[];
-  const Grid g = *gp;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = s < g.n_valid;  // whole warps stay alive: the group search is warp-collective
+  const int leaf = s >> 5;
+  if (leaf >= b.nleaf) return;  // whole warps only (blockDim is a multiple of 32)
+  const float4 q = b.sp[s];
+  const bool active = idx_bits(q.w) != kPadIdx;
   KnnList L;
   L.d = knn_smem + threadIdx.x;
   L.pos = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + threadIdx.x;
-  L.sp = sp;
+  L.sp = b.sp;
   L.k = k;
   L.cnt = 0;
   L.stride = blockDim.x;
-  const float4 q = active ? sp[s] : make_float4(0.f, 0.f, 0.f, 0.f);
-  bool done = false;
-  if (!warp_group_search(g, cell_start, sp, q.x, q.y, q.z, active, L, kKnnLocalR, done)) {
-    // the warp's queries straddle distant cells (row ends): independent thread-local walks
-    done = !active || grid_search(g, cell_start, sp, q.x, q.y, q.z, L, kKnnLocalR);
-  }
+  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf);
   if (!active) return;
-  if (!done) {
-    const int slot = atomicAdd(hard_count, 1);
-    hard_list[slot] = s;
-    hard_bound[slot] = L.worst();  // valid upper bound of the true k-th distance (INFINITY if fewer than k found so far)
-    return;
-  }
   const int stride = L.stride;
   const int* posp = L.pos;
-  knn_cov_store(sp, L.cnt, [=](int j) { return posp[j * stride]; }, cov + (size_t)s * 6);
-}
-
-// phase 2: one WARP per hard query.  Every lane keeps a private sorted top-k of the rows it scans inside the box of radius
-// sqrt(bound); the 32 lists are then merged by repeated warp-wide argmin.  Exact: bound >= true k-th distance.
-struct KnnLaneList {
-  float* d;
-  int* pos;
-  const float4* sp;
-  int k, cnt;
-  float bound;
-  __device__ __forceinline__ float worst() const { return cnt < k ? bound : fminf(bound, d[(k - 1) * 32]); }
-  __device__ __forceinline__ float limit() const { return INFINITY; }
-  __device__ __forceinline__ bool less_than_slot(float d2, int idx, int slot) const {
-    float ds = d[slot * 32];
-    if (d2 < ds) return true;
-    if (d2 > ds) return false;
-    return idx < idx_bits(sp[pos[slot * 32]].w);
-  }
-  __device__ __forceinline__ void visit(float d2, int idx, int p) {
-    if (d2 > bound) return;
-    if (cnt == k && !less_than_slot(d2, idx, k - 1)) return;
-    int j = (cnt < k) ? cnt++ : k - 1;
-    while (j > 0 && less_than_slot(d2, idx, j - 1)) {
-      d[j * 32] = d[(j - 1) * 32];
-      pos[j * 32] = pos[(j - 1) * 32];
-      j--;
-    }
-    d[j * 32] = d2;
-    pos[j * 32] = p;
-  }
-};
-
-constexpr int kKnnHardWarps = 4;
-
-__global__ void __launch_bounds__(kKnnHardWarps * 32, 4) k_knn_cov_hard(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
-                                                                     const float4* __restrict__ sp, int k, double* __restrict__ cov,
-                                                                     const int* __restrict__ hard_list, const float* __restrict__ hard_bound,
-                                                                     const int* __restrict__ hard_count) {
-  extern __shared__ float knn_smem[];  // per warp: d[k][32], pos[k][32], merged[k]
-  const Grid g = *gp;
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* wbase = knn_smem + (size_t)wib * (2 * k * 32 + k);
-  int* merged = reinterpret_cast<int*>(wbase + 2 * k * 32);
-  const int nhard = *hard_count;
-  const int nwarps = gridDim.x * kKnnHardWarps;
-  for (int hq = blockIdx.x * kKnnHardWarps + wib; hq < nhard; hq += nwarps) {
-    const int s = hard_list[hq];
-    const float bound = hard_bound[hq];
-    const float4 q = sp[s];
-    KnnLaneList L;
-    L.d = wbase + lane;
-    L.pos = reinterpret_cast<int*>(wbase + k * 32) + lane;
-    L.sp = sp;
-    L.k = k;
-    L.cnt = 0;
-    L.bound = bound;
-    const int cx = cell_coord(q.x, g.ox, g.inv_h, g.nx), cy = cell_coord(q.y, g.oy, g.inv_h, g.ny), cz = cell_coord(q.z, g.oz, g.inv_h, g.nz);
-    float bnd = bound;
-    int R = 4, kk = 0;
-    if (bnd < 1.0e30f) {
-      const float rr = sqrtf(bnd) * g.inv_h;
-      R = rr < 1.0e6f ? (int)rr + 2 : 0x3fffffff;
-    }
-    for (;;) {
-      L.cnt = 0;
-      L.bound = bnd;
-      warp_box_scan(g, cell_start, sp, q.x, q.y, q.z, cx, cy, cz, R, lane, L);
-      __syncwarp();
-      // k-way merge of the 32 sorted lane lists
-      int head = 0;
-      float kth = INFINITY;
-      kk = 0;
-      for (int j = 0; j < k; j++) {
-        float cd = (head < L.cnt) ? L.d[head * 32] : INFINITY;
-        int cp = (head < L.cnt) ? L.pos[head * 32] : -1;
-        int ci = (cp >= 0) ? idx_bits(sp[cp].w) : 0x7fffffff;
-        float bd = cd;
-        int bi = ci, bl = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
-          if (od < bd || (od == bd && (oi < bi || (oi == bi && ol < bl)))) { bd = od; bi = oi; bl = ol; }
-        }
-        if (bd == INFINITY) break;
-        if (lane == bl) { merged[j] = cp; head++; }
-        kth = bd;
-        kk = j + 1;
-      }
-      const float fb2 = block_face_bound2(g, q.x, q.y, q.z, cx, cy, cz, R);
-      if (fb2 == INFINITY) break;              // the box covered the whole grid
-      if (kk == k && kth < fb2) break;         // k neighbours, all strictly inside the covered block: exact
-      if (kk == k) bnd = fminf(bnd, kth);      // still a valid upper bound of the true k-th distance
-      int Rn = (R < (1 << 20)) ? R * 4 : 0x3fffffff;
-      if (bnd < 1.0e30f) {
-        const float rr = sqrtf(bnd) * g.inv_h;
-        const int Rb = rr < 1.0e6f ? (int)rr + 2 : 0x3fffffff;
-        Rn = Rb > R ? Rb : Rn;
-      }
-      R = Rn;
-      __syncwarp();
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const int* mp = merged;
-      knn_cov_store(sp, kk, [=](int j) { return mp[j]; }, cov + (size_t)s * 6);
-    }
-    __syncwarp();
-  }
+  knn_cov_store(b.sp, L.cnt, [=](int j) { return posp[j * stride]; }, cov + (size_t)s * 6);
 }
 
 // ---------------------------------------------------------------- pose passed by value to the per-iteration kernels
@@ -278,12 +155,9 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
 }
 
 struct LinArgs {
-  const Grid* sgrid;           // source grid (n_valid)
-  const float4* ssp;           // source points, sorted
+  Bvh src;                     // source structure (queries = its sorted points)
   const double* scov;          // source covariances, sorted (6 per point)
-  const Grid* tgrid;
-  const int* tcell_start;
-  const float4* tsp;
+  Bvh tgt;
   const double* tcov;
   double thr2;                 // max_correspondence_distance^2 (double, compared against (double)d2)
   float lim;                   // float >= thr2 (search range limit)
@@ -297,49 +171,42 @@ struct LinArgs {
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
 };
 
-__global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(LinArgs A, PoseArg P) {
+__global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
   __shared__ double red[kAcc * 32];
-  const int nv = A.sgrid->n_valid;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-  const Grid tg = *A.tgrid;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
+  const bool is_point = idx_bits(p.w) != kPadIdx;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
   v.best_d2 = INFINITY;
   v.best_idx = 0x7fffffff;
   v.best_pos = -1;
   v.lim = A.lim;
-  bool need = false;
-  if (s < nv) {
-    p = A.ssp[s];
+  bool active = false;
+  if (is_point) {
     qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
     qy = xform_row(P.Tf[4], P.Tf[5], P.Tf[6], P.Tf[7], p.x, p.y, p.z);
     qz = xform_row(P.Tf[8], P.Tf[9], P.Tf[10], P.Tf[11], p.x, p.y, p.z);
     if (finite3(qx, qy, qz)) {
+      active = true;
       if (A.use_seed) {  // last iteration's correspondent is a real candidate: a tight, exact upper bound
         int sp0 = A.cpos[s];
         if (sp0 >= 0) {
-          float4 t = A.tsp[sp0];
+          float4 t = A.tgt.sp[sp0];
           v.best_d2 = dist2_f32(qx, qy, qz, t.x, t.y, t.z);
           v.best_idx = idx_bits(t.w);
           v.best_pos = sp0;
         }
       }
-      need = true;
     }
   }
-  {
-    bool done = false;
-    const bool act = need;
-    if (!warp_group_search(tg, A.tcell_start, A.tsp, qx, qy, qz, act, v, 1, done)) done = !act || grid_search(tg, A.tcell_start, A.tsp, qx, qy, qz, v, 1);
-    need = act && !done;
-  }
-  warp_finish_nn1(tg, A.tcell_start, A.tsp, qx, qy, qz, v, need);  // all 32 lanes participate
-  if (s < nv) {
-    const bool valid = (v.best_pos >= 0) && ((double)v.best_d2 < A.thr2);
+  bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
+  if (is_point) {
+    const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2 < A.thr2);
     A.corr[idx_bits(p.w)] = valid ? v.best_idx : -1;
     A.cpos[s] = valid ? v.best_pos : -1;
     A.d2[s] = v.best_d2;
@@ -364,7 +231,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(LinArgs A, Po
       inv3(rcr, M);
       double* mo = A.mahal + (size_t)s * 6;
       mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
-      const float4 tb = A.tsp[v.best_pos];
+      const float4 tb = A.tgt.sp[v.best_pos];
       const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;
       const double tx = P.T[0] * ax + P.T[1] * ay + P.T[2] * az + P.T[3];
       const double ty = P.T[4] * ax + P.T[5] * ay + P.T[6] * az + P.T[7];
@@ -410,8 +277,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(LinArgs A, Po
 }
 
 struct ErrArgs {
-  const Grid* sgrid;
   const float4* ssp;
+  int n_sorted;      // nleaf * 32 of the source
   const float4* tsp;
   const int* cpos;
   const double* mahal;
@@ -422,13 +289,12 @@ struct ErrArgs {
 
 __global__ void __launch_bounds__(kLinThreads) k_gicp_error(ErrArgs A, PoseArg P) {
   __shared__ double red[32];
-  const int nv = A.sgrid->n_valid;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[1] = {0.0};
-  if (s < nv) {
-    int tp = A.cpos[s];
+  if (s < A.n_sorted) {
+    const float4 p = A.ssp[s];
+    int tp = (idx_bits(p.w) != kPadIdx) ? A.cpos[s] : -1;
     if (tp >= 0) {
-      const float4 p = A.ssp[s];
       const float4 tb = A.tsp[tp];
       const double* m = A.mahal + (size_t)s * 6;
       const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;

@@ -445,6 +445,12 @@ inline int ndt_ensure_map(const b2r_config& cfg, Cloud& c, NdtWork& W, cudaStrea
   if (rc) return rc;
   Scratch* S = W.scr;
   if (!S) return fail(B2R_ESTATE, "internal: NDT scratch not attached");
+  if (!S->counts) {  // dense voxel tables: allocated on first NDT use only (GICP handles stay light)
+    B2R_CUDA(cudaMalloc(&S->counts, (size_t)kCellCap * sizeof(int)));
+    B2R_CUDA(cudaMalloc(&S->cursor, (size_t)kCellCap * sizeof(int)));
+    B2R_CUDA(cudaMalloc(&S->bsum, (size_t)kScanBlocks * sizeof(int)));
+    B2R_CUDA(cudaMemsetAsync(S->counts, 0, (size_t)kCellCap * sizeof(int), st));
+  }
   if (!c.ndt) {
     c.ndt = new NdtVoxelMap();
     B2R_CUDA(cudaMalloc(&c.ndt->geom, sizeof(VoxGeom)));

@@ -1,64 +1,55 @@
-// tests/host_harness.cu — CPU-side check of the engine's exact grid search LOGIC (nn_search.cuh compiled as host code)
-// against the oracle's kd-tree.  Test infrastructure: built by tests/test_host_logic.py with nvcc, never shipped.
-// It mirrors grid.cuh's build serially on the host (same formulas) and then runs grid_search for 1-NN and k-NN.
+// tests/host_harness.cu — CPU-side check of the engine's exact BVH search LOGIC (bvh.cuh compiled as host code: the AABB
+// bound, the strict pruning rule, the (d2, index) ordering) against the oracle's kd-tree.  Test infrastructure: built by
+// tests/test_host_logic.py with nvcc, never shipped.  The structure is built serially on the host with the same rules as
+// k_morton_keys / k_bvh_leaves; the traversal is bvh_search_one, whose per-query decisions are exactly the per-lane
+// decisions of the warp-group traversal used on the device.
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 #include <algorithm>
 #include <cmath>
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
-#include "../hdl_graph_slam_b200/csrc/nn_search.cuh"
+#include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 #include "../oracle/oracle.h"
 
 using namespace b2r;
 
-struct HostGrid {
-  Grid g;
-  std::vector<int> cell_start;
-  std::vector<float4> sorted;
+struct HostBvh {
+  std::vector<float4> sp, llo, lhi, slo, shi;
+  Bvh b;
 };
 
-static HostGrid build(const std::vector<float>& pts, int n, float h_min, int cap) {
-  HostGrid G;
+static HostBvh build(const std::vector<float>& pts, int n) {
+  HostBvh H;
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = 0; i < n; i++)
     for (int d = 0; d < 3; d++) { mn[d] = std::min(mn[d], pts[i * 4 + d]); mx[d] = std::max(mx[d], pts[i * 4 + d]); }
-  float h = h_min;
-  for (;;) {
-    float inv = 1.f / h;
-    double cells = 1;
-    int dims[3];
-    float o[3];
-    for (int d = 0; d < 3; d++) {
-      o[d] = floorf(mn[d] * inv) * h;
-      dims[d] = (int)floorf((mx[d] - o[d]) * inv) + 1;
-      cells *= dims[d];
-    }
-    if (cells <= cap) {
-      G.g.ox = o[0]; G.g.oy = o[1]; G.g.oz = o[2]; G.g.h = h; G.g.inv_h = inv;
-      G.g.nx = dims[0]; G.g.ny = dims[1]; G.g.nz = dims[2]; G.g.ncell = dims[0] * dims[1] * dims[2];
-      break;
-    }
-    h *= 2.f;
-  }
-  G.g.n = n; G.g.n_valid = n;
-  std::vector<std::pair<int, int>> ci(n);
+  float ext = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), std::max(mx[2] - mn[2], 1.0e-6f));
+  float sc = 1023.0f / ext;
+  std::vector<std::pair<unsigned, int>> ki(n);
   for (int i = 0; i < n; i++) {
-    int cx = cell_coord(pts[i * 4 + 0], G.g.ox, G.g.inv_h, G.g.nx);
-    int cy = cell_coord(pts[i * 4 + 1], G.g.oy, G.g.inv_h, G.g.ny);
-    int cz = cell_coord(pts[i * 4 + 2], G.g.oz, G.g.inv_h, G.g.nz);
-    ci[i] = {(cz * G.g.ny + cy) * G.g.nx + cx, i};
+    unsigned ix = (unsigned)std::min(std::max((pts[i * 4] - mn[0]) * sc, 0.f), 1023.f);
+    unsigned iy = (unsigned)std::min(std::max((pts[i * 4 + 1] - mn[1]) * sc, 0.f), 1023.f);
+    unsigned iz = (unsigned)std::min(std::max((pts[i * 4 + 2] - mn[2]) * sc, 0.f), 1023.f);
+    ki[i] = {morton_spread10(ix) | (morton_spread10(iy) << 1) | (morton_spread10(iz) << 2), i};
   }
-  std::sort(ci.begin(), ci.end());
-  G.cell_start.assign(G.g.ncell + 1, 0);
-  for (auto& c : ci) G.cell_start[c.first + 1]++;
-  for (int c = 0; c < G.g.ncell; c++) G.cell_start[c + 1] += G.cell_start[c];
-  G.sorted.resize(n);
+  std::sort(ki.begin(), ki.end());
+  int nsup = (n + 1023) / 1024, nleaf = nsup * 32;
+  H.sp.assign((size_t)nsup * 1024, make_float4(INFINITY, INFINITY, INFINITY, bits_idx(kPadIdx)));
+  for (int s = 0; s < n; s++) { int i = ki[s].second; H.sp[s] = make_float4(pts[i * 4], pts[i * 4 + 1], pts[i * 4 + 2], bits_idx(i)); }
+  H.llo.assign(nleaf, make_float4(INFINITY, INFINITY, INFINITY, 0)); H.lhi.assign(nleaf, make_float4(-INFINITY, -INFINITY, -INFINITY, 0));
+  H.slo.assign(nsup, make_float4(INFINITY, INFINITY, INFINITY, 0)); H.shi.assign(nsup, make_float4(-INFINITY, -INFINITY, -INFINITY, 0));
   for (int s = 0; s < n; s++) {
-    int i = ci[s].second;
-    G.sorted[s] = make_float4(pts[i * 4], pts[i * 4 + 1], pts[i * 4 + 2], bits_idx(i));
+    int l = s / 32, u = s / 1024;
+    float4 p = H.sp[s];
+    H.llo[l].x = std::min(H.llo[l].x, p.x); H.llo[l].y = std::min(H.llo[l].y, p.y); H.llo[l].z = std::min(H.llo[l].z, p.z);
+    H.lhi[l].x = std::max(H.lhi[l].x, p.x); H.lhi[l].y = std::max(H.lhi[l].y, p.y); H.lhi[l].z = std::max(H.lhi[l].z, p.z);
+    H.slo[u].x = std::min(H.slo[u].x, p.x); H.slo[u].y = std::min(H.slo[u].y, p.y); H.slo[u].z = std::min(H.slo[u].z, p.z);
+    H.shi[u].x = std::max(H.shi[u].x, p.x); H.shi[u].y = std::max(H.shi[u].y, p.y); H.shi[u].z = std::max(H.shi[u].z, p.z);
   }
-  return G;
+  H.b.sp = H.sp.data(); H.b.leaf_lo = H.llo.data(); H.b.leaf_hi = H.lhi.data(); H.b.sup_lo = H.slo.data(); H.b.sup_hi = H.shi.data();
+  H.b.nleaf = nleaf; H.b.nsup = nsup; H.b.n = n;
+  return H;
 }
 
 struct HostKnn {
@@ -85,7 +76,6 @@ int main(int argc, char** argv) {
   int n = argc > 1 ? atoi(argv[1]) : 20000;
   int nq = argc > 2 ? atoi(argv[2]) : 5000;
   int mode = argc > 3 ? atoi(argv[3]) : 0;  // 0 lidar-ish, 1 lattice (many exact ties), 2 clustered + far outliers
-  float h_min = argc > 4 ? (float)atof(argv[4]) : 0.5f;
   unsigned long long s = 12345 + mode;
   std::vector<float> pts(n * 4), qs(nq * 4);
   for (int i = 0; i < n; i++) {
@@ -100,10 +90,10 @@ int main(int argc, char** argv) {
     double sc = (mode == 1) ? ((i & 1) ? 0.0 : 0.25) : 0.3;
     qs[i * 4] = pts[j * 4] + (float)((urand(s) - 0.5) * sc); qs[i * 4 + 1] = pts[j * 4 + 1] + (float)((urand(s) - 0.5) * sc);
     qs[i * 4 + 2] = pts[j * 4 + 2] + (float)((urand(s) - 0.5) * sc); qs[i * 4 + 3] = 1.f;
-    if (i % 97 == 0) { qs[i * 4] += 400.f; }  // far outside the grid
+    if (i % 97 == 0) { qs[i * 4] += 400.f; }  // far outside the cloud
   }
-  HostGrid G = build(pts, n, h_min, 1 << 22);
-  printf("grid h=%g dims=%d %d %d ncell=%d\n", G.g.h, G.g.nx, G.g.ny, G.g.nz, G.g.ncell);
+  HostBvh H = build(pts, n);
+  printf("bvh nleaf=%d nsup=%d\n", H.b.nleaf, H.b.nsup);
   const int k = 20;
   std::vector<int32_t> oidx((size_t)nq * k);
   std::vector<float> od2((size_t)nq * k);
@@ -111,19 +101,19 @@ int main(int argc, char** argv) {
   long bad1 = 0, badk = 0, badlim = 0;
   for (int i = 0; i < nq; i++) {
     Nn1 v; v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
-    grid_search(G.g, G.cell_start.data(), G.sorted.data(), qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], v);
+    bvh_search_one(H.b, qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], v);
     if (v.best_idx != oidx[(size_t)i * k] || v.best_d2 != od2[(size_t)i * k]) {
       if (bad1 < 5) printf("1nn mismatch q%d: got (%g,%d) want (%g,%d)\n", i, v.best_d2, v.best_idx, od2[(size_t)i * k], oidx[(size_t)i * k]);
       bad1++;
     }
     // range-limited search (GICP: limit 6.25): result must agree whenever the true NN is inside the limit
     Nn1 w; w.best_d2 = INFINITY; w.best_idx = 0x7fffffff; w.best_pos = -1; w.lim = 6.25f;
-    grid_search(G.g, G.cell_start.data(), G.sorted.data(), qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], w);
+    bvh_search_one(H.b, qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], w);
     bool want_valid = od2[(size_t)i * k] < 6.25f;
     bool got_valid = w.best_pos >= 0 && w.best_d2 < 6.25f;
     if (want_valid != got_valid || (want_valid && (w.best_idx != oidx[(size_t)i * k] || w.best_d2 != od2[(size_t)i * k]))) badlim++;
     HostKnn K; K.k = k; K.d.resize(k); K.id.resize(k);
-    grid_search(G.g, G.cell_start.data(), G.sorted.data(), qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], K);
+    bvh_search_one(H.b, qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], K);
     for (int j = 0; j < k; j++)
       if (K.id[j] != oidx[(size_t)i * k + j] || K.d[j] != od2[(size_t)i * k + j]) { badk++; break; }
   }

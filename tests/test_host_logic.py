@@ -1,5 +1,5 @@
-"""CPU-only: the engine's exact grid-search logic (nn_search.cuh compiled as HOST code by tests/host_harness.cu) returns
-the oracle's (d2, index) results bit-for-bit, including lattice ties, range-limited search and queries outside the grid."""
+"""CPU-only: the engine's exact BVH search logic (bvh.cuh compiled as HOST code by tests/host_harness.cu) returns the
+oracle's (d2, index) results bit-for-bit, including lattice ties, range-limited search and queries far outside the cloud."""
 import os
 import subprocess
 import pytest
@@ -17,8 +17,8 @@ def harness(oracle):
     return exe
 
 
-@pytest.mark.parametrize("mode,hmin", [(0, 0.5), (1, 0.5), (2, 0.5), (0, 2.0)])
-def test_grid_search_equals_kdtree(harness, mode, hmin):
-    out = subprocess.run([harness, "20000", "4000", str(mode), str(hmin)], capture_output=True, text=True)
+@pytest.mark.parametrize("mode,n", [(0, 20000), (1, 20000), (2, 20000), (0, 1500)])
+def test_bvh_search_equals_kdtree(harness, mode, n):
+    out = subprocess.run([harness, str(n), "4000", str(mode)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout and "limited_mismatch=0" in out.stdout
