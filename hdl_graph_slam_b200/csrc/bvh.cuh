@@ -163,14 +163,54 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
 //   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
 // Order: own leaf, then the super-node nearest to the group's AABB, then all remaining super-nodes by index.
+// Visit one leaf for the lanes flagged `pass`.  Two modes (profiles/r01_c: a Morton leaf at a curve discontinuity can
+// span 100 m; its 32 queries then want DIFFERENT leaves and a pure all-pairs tile wastes 31/32 of the work):
+//   tile mode  (>= kTileLanes lanes interested): every lane tests all 32 candidates (broadcast loads);
+//   coop mode  (few lanes interested): for each interested lane L the 32 lanes evaluate the leaf's 32 candidates in ONE
+//              step (lane t owns candidate t), then L's visitor consumes the acceptable ones best-first.
+// Both feed exactly the same (d2, idx) candidates to the same visitors, so the result is identical.
+constexpr int kTileLanes = 12;
+
 template <class Visitor>
 __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned mask = __ballot_sync(FULL, pass);
+  if (mask == 0) return;
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
+  if (__popc(mask) >= kTileLanes) {
 #pragma unroll 8
-  for (int t = 0; t < kLeaf; t++) {
-    const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-    const int idx = idx_bits(p.w);
-    if (pass && idx != kPadIdx) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx, l * kLeaf + t);
+    for (int t = 0; t < kLeaf; t++) {
+      const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
+      const int idx = idx_bits(p.w);
+      if (pass && idx != kPadIdx) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx, l * kLeaf + t);
+    }
+    return;
+  }
+  const float4 mine = __ldg(lp + lane);  // coalesced: candidate `lane`
+  const int my_idx = idx_bits(mine.w);
+  while (mask) {
+    const int L = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const float ax = __shfl_sync(FULL, qx, L), ay = __shfl_sync(FULL, qy, L), az = __shfl_sync(FULL, qz, L);
+    const float d2 = dist2_f32(ax, ay, az, mine.x, mine.y, mine.z);
+    float wL = __shfl_sync(FULL, v.worst(), L);
+    bool ok = (my_idx != kPadIdx) && !(d2 > wL);
+    while (__ballot_sync(FULL, ok)) {
+      float bd = ok ? d2 : INFINITY;
+      int bi = ok ? my_idx : 0x7fffffff, bl = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(FULL, bd, o);
+        const int oi = __shfl_xor_sync(FULL, bi, o);
+        const int ol = __shfl_xor_sync(FULL, bl, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bl = ol; }
+      }
+      if (lane == L) v.visit(bd, bi, l * kLeaf + bl);
+      if (lane == bl) ok = false;
+      wL = __shfl_sync(FULL, v.worst(), L);
+      ok = ok && !(d2 > wL);
+    }
   }
 }
 
