@@ -31,7 +31,7 @@ static HostBvh build(const std::vector<float>& pts, int n) {
     unsigned ix = (unsigned)std::min(std::max((pts[i * 4] - mn[0]) * sc, 0.f), 1023.f);
     unsigned iy = (unsigned)std::min(std::max((pts[i * 4 + 1] - mn[1]) * sc, 0.f), 1023.f);
     unsigned iz = (unsigned)std::min(std::max((pts[i * 4 + 2] - mn[2]) * sc, 0.f), 1023.f);
-    ki[i] = {morton_spread10(ix) | (morton_spread10(iy) << 1) | (morton_spread10(iz) << 2), i};
+    ki[i] = {hilbert30(ix, iy, iz), i};
   }
   std::sort(ki.begin(), ki.end());
   int nsup = (n + 1023) / 1024, nleaf = nsup * 32;
