@@ -234,24 +234,38 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   }
 }
 
-template <class Visitor>
-__device__ __forceinline__ void bvh_visit_super(const Bvh& b, int s, int skip_leaf, int skip_leaf2, float qx, float qy, float qz, bool active, Visitor& v) {
-  const unsigned FULL = 0xffffffffu;
-  const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
-  const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
-  const bool spass = active && !(sb > v.worst()) && (sb < v.limit());
-  if (__ballot_sync(FULL, spass) == 0) return;
-  const int l1 = min((s + 1) * kSuper, b.nleaf);
-  for (int l = s * kSuper; l < l1; l++) {
-    if (l == skip_leaf || l == skip_leaf2) continue;
-    const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
-    const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-    const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-    if (__ballot_sync(FULL, pass) == 0) continue;
-    bvh_visit_leaf(b, l, qx, qy, qz, pass, v);
-  }
+// lower bound of dist2_f32(q, p) for every q inside box G and p inside box N (gap per axis, same association): it never
+// exceeds aabb_bound2(q, N) for a q in G (monotone rounding), so pruning a node for the whole GROUP with it is safe.
+__device__ __forceinline__ float aabb_aabb_bound2(float glx, float gly, float glz, float ghx, float ghy, float ghz, const float4& lo, const float4& hi) {
+  float bx = 0.f, by = 0.f, bz = 0.f;
+  if (ghx < lo.x) bx = fsub(lo.x, ghx); else if (glx > hi.x) bx = fsub(glx, hi.x);
+  if (ghy < lo.y) by = fsub(lo.y, ghy); else if (gly > hi.y) by = fsub(gly, hi.y);
+  if (ghz < lo.z) bz = fsub(lo.z, ghz); else if (glz > hi.z) bz = fsub(glz, hi.z);
+  return fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
 }
 
+template <class Visitor>
+__device__ __forceinline__ float group_max_worst(bool active, const Visitor& v) {
+  float w = active ? fminf(v.worst(), v.limit()) : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
+  return w;
+}
+
+// exact per-lane test + visit of one leaf
+template <class Visitor>
+__device__ __forceinline__ void bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
+  const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
+  const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+  const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+  bvh_visit_leaf(b, l, qx, qy, qz, pass, v);
+}
+
+// All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
+//   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
+// Node tests are lane-parallel against the GROUP's AABB (lane j tests node j: 32 nodes per step, no dependent-load chain);
+// only the surviving leaves get the exact per-lane test.  Order: own leaf, the leaf nearest to the group's centre, then
+// super-nodes by index.
 template <class Visitor>
 __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf) {
   const unsigned FULL = 0xffffffffu;
@@ -266,27 +280,25 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     glx = fminf(glx, __shfl_xor_sync(FULL, glx, o)); gly = fminf(gly, __shfl_xor_sync(FULL, gly, o)); glz = fminf(glz, __shfl_xor_sync(FULL, glz, o));
     ghx = fmaxf(ghx, __shfl_xor_sync(FULL, ghx, o)); ghy = fmaxf(ghy, __shfl_xor_sync(FULL, ghy, o)); ghz = fmaxf(ghz, __shfl_xor_sync(FULL, ghz, o));
   }
-  const float gcx = 0.5f * (glx + ghx), gcy = 0.5f * (gly + ghy), gcz = 0.5f * (glz + ghz);
-  // nearest super-node to the group's centre (heuristic only: it decides the ORDER of the visits, never their outcome)
-  float bd = INFINITY;
-  int bs = 0;
-  for (int s = lane; s < b.nsup; s += 32) {
-    const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
-    const float d = aabb_bound2(gcx, gcy, gcz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
-    if (d < bd) { bd = d; bs = s; }
-  }
+  // seed: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
+  if (own_leaf < 0) {
+    const float gcx = 0.5f * (glx + ghx), gcy = 0.5f * (gly + ghy), gcz = 0.5f * (glz + ghz);
+    float bd = INFINITY;
+    int bs = 0;
+    for (int s = lane; s < b.nsup; s += 32) {
+      const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
+      const float d = aabb_bound2(gcx, gcy, gcz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+      if (d < bd) { bd = d; bs = s; }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float od = __shfl_xor_sync(FULL, bd, o);
-    const int os = __shfl_xor_sync(FULL, bs, o);
-    if (od < bd || (od == bd && os < bs)) { bd = od; bs = os; }
-  }
-  // inside it, the leaf nearest to the group's centre goes first so that a tight bound exists early
-  int bl = -1;
-  {
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(FULL, bd, o);
+      const int os = __shfl_xor_sync(FULL, bs, o);
+      if (od < bd || (od == bd && os < bs)) { bd = od; bs = os; }
+    }
     const int l = bs * kSuper + lane;
     float ld = INFINITY;
-    if (l < b.nleaf && l != own_leaf) {
+    if (l < b.nleaf) {
       const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
       ld = aabb_bound2(gcx, gcy, gcz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
     }
@@ -297,18 +309,38 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       const int ol = __shfl_xor_sync(FULL, ll, o);
       if (od < ld || (od == ld && ol < ll)) { ld = od; ll = ol; }
     }
-    if (ld < INFINITY) bl = ll;
+    if (ld < INFINITY) { bvh_try_leaf(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
-  if (bl >= 0) {
-    const float4 lo = __ldg(b.leaf_lo + bl), hi = __ldg(b.leaf_hi + bl);
-    const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-    const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-    if (__ballot_sync(FULL, pass)) bvh_visit_leaf(b, bl, qx, qy, qz, pass, v);
-  }
-  bvh_visit_super(b, bs, own_leaf, bl, qx, qy, qz, active, v);
-  for (int s = 0; s < b.nsup; s++) {
-    if (s == bs) continue;
-    bvh_visit_super(b, s, own_leaf, -1, qx, qy, qz, active, v);
+  float gw = group_max_worst(active, v);
+  for (int sbase = 0; sbase < b.nsup; sbase += 32) {
+    const int s = sbase + lane;
+    float sgb = INFINITY;
+    if (s < b.nsup) {
+      const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
+      sgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, slo, shi);
+    }
+    unsigned smask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
+    while (smask) {
+      const int sj = __ffs(smask) - 1;
+      smask &= smask - 1;
+      const float sb = __shfl_sync(FULL, sgb, sj);
+      if (sb > gw) continue;  // the bound tightened since the mask was built
+      const int l = (sbase + sj) * kSuper + lane;
+      float lgb = INFINITY;
+      if (l < b.nleaf && l != own_leaf) {
+        const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
+        lgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, lo, hi);
+      }
+      unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY);
+      while (lmask) {
+        const int lj = __ffs(lmask) - 1;
+        lmask &= lmask - 1;
+        const float lb = __shfl_sync(FULL, lgb, lj);
+        if (lb > gw) continue;
+        bvh_try_leaf(b, (sbase + sj) * kSuper + lj, qx, qy, qz, active, v);
+        gw = group_max_worst(active, v);
+      }
+    }
   }
 }
 #endif
