@@ -311,34 +311,43 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (ld < INFINITY) { bvh_try_leaf(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
-  float gw = group_max_worst(active, v);
+  // Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in an unrolled loop (uniform
+  // addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the warp ORs the 32-bit masks.
+  // Masks are conservative snapshots (worst only shrinks); each leaf is re-tested with the current worst when visited.
   for (int sbase = 0; sbase < b.nsup; sbase += 32) {
-    const int s = sbase + lane;
-    float sgb = INFINITY;
-    if (s < b.nsup) {
-      const float4 slo = __ldg(b.sup_lo + s), shi = __ldg(b.sup_hi + s);
-      sgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, slo, shi);
+    unsigned my = 0;
+    const int sn = min(32, b.nsup - sbase);
+    const float w0 = v.worst(), lim0 = v.limit();
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+      if (j < sn) {
+        const float4 slo = __ldg(b.sup_lo + sbase + j), shi = __ldg(b.sup_hi + sbase + j);
+        const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+        if (!(sb > w0) && sb < lim0) my |= 1u << j;
+      }
     }
-    unsigned smask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
+    if (!active) my = 0;
+    unsigned smask = __reduce_or_sync(FULL, my);
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;
-      const float sb = __shfl_sync(FULL, sgb, sj);
-      if (sb > gw) continue;  // the bound tightened since the mask was built
-      const int l = (sbase + sj) * kSuper + lane;
-      float lgb = INFINITY;
-      if (l < b.nleaf && l != own_leaf) {
-        const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
-        lgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, lo, hi);
+      const int l0 = (sbase + sj) * kSuper;
+      unsigned lm = 0;
+      const float w1 = v.worst();
+      if (active && ((my >> sj) & 1u)) {
+#pragma unroll 8
+        for (int j = 0; j < kSuper; j++) {
+          const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
+          const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+          if (!(lb > w1) && lb < lim0) lm |= 1u << j;
+        }
       }
-      unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY);
+      unsigned lmask = __reduce_or_sync(FULL, lm);
+      if (own_leaf >= l0 && own_leaf < l0 + kSuper) lmask &= ~(1u << (own_leaf - l0));
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
-        const float lb = __shfl_sync(FULL, lgb, lj);
-        if (lb > gw) continue;
-        bvh_try_leaf(b, (sbase + sj) * kSuper + lj, qx, qy, qz, active, v);
-        gw = group_max_worst(active, v);
+        bvh_try_leaf(b, l0 + lj, qx, qy, qz, active && ((lm >> lj) & 1u), v);
       }
     }
   }
