@@ -311,9 +311,35 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (ld < INFINITY) { bvh_try_leaf(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
+  const int s0 = own_leaf >= 0 ? own_leaf / kSuper : -1;
   // Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in an unrolled loop (uniform
   // addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the warp ORs the 32-bit masks.
   // Masks are conservative snapshots (worst only shrinks); each leaf is re-tested with the current worst when visited.
+  // pass 1: the super-node that holds the already-visited leaf; its leaves in order of index distance from that leaf
+  // (Hilbert order: index neighbours are space neighbours), so the bound is tight before anything else is looked at
+  if (s0 >= 0) {
+    const int l0 = s0 * kSuper;
+    unsigned lm = 0;
+    const float w1 = v.worst(), lim1 = v.limit();
+    if (active) {
+#pragma unroll 8
+      for (int j = 0; j < kSuper; j++) {
+        const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
+        const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+        if (!(lb > w1) && lb < lim1) lm |= 1u << j;
+      }
+    }
+    unsigned lmask = __reduce_or_sync(FULL, lm) & ~(1u << (own_leaf - l0));
+    const int c = own_leaf - l0;
+    for (int d = 1; d < kSuper && lmask; d++) {
+      const int ja = c - d, jb = c + d;
+      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
+      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
+    }
+  }
+  // pass 2: every other super-node.  Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in
+  // an unrolled loop (uniform addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the
+  // warp ORs the 32-bit masks.  Masks are conservative snapshots (worst only shrinks); each leaf is re-tested when visited.
   for (int sbase = 0; sbase < b.nsup; sbase += 32) {
     unsigned my = 0;
     const int sn = min(32, b.nsup - sbase);
@@ -328,6 +354,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (!active) my = 0;
     unsigned smask = __reduce_or_sync(FULL, my);
+    if (s0 >= sbase && s0 < sbase + 32) smask &= ~(1u << (s0 - sbase));
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;
@@ -343,7 +370,6 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
         }
       }
       unsigned lmask = __reduce_or_sync(FULL, lm);
-      if (own_leaf >= l0 && own_leaf < l0 + kSuper) lmask &= ~(1u << (own_leaf - l0));
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
