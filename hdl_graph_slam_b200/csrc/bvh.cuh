@@ -263,11 +263,13 @@ __device__ __forceinline__ void bvh_try_leaf(const Bvh& b, int l, float qx, floa
 
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
 //   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
+//   part/nparts   : several warps may share one query group; each takes a disjoint share of the nodes (own leaf: all).
 // Node tests are lane-parallel against the GROUP's AABB (lane j tests node j: 32 nodes per step, no dependent-load chain);
 // only the surviving leaves get the exact per-lane test.  Order: own leaf, the leaf nearest to the group's centre, then
 // super-nodes by index.
 template <class Visitor>
-__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf) {
+__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf,
+                                                 int part = 0, int nparts = 1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
@@ -333,6 +335,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     const int c = own_leaf - l0;
     for (int d = 1; d < kSuper && lmask; d++) {
       const int ja = c - d, jb = c + d;
+      if (d % nparts != part) continue;  // work split: ring d of the own super-node belongs to one part
       if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
       if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
     }
@@ -355,6 +358,11 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     if (!active) my = 0;
     unsigned smask = __reduce_or_sync(FULL, my);
     if (s0 >= sbase && s0 < sbase + 32) smask &= ~(1u << (s0 - sbase));
+    if (nparts > 1) {  // work split: super-node s belongs to part s % nparts
+      unsigned keep = 0;
+      for (int j = part - (sbase % nparts); j < 32; j += nparts) if (j >= 0) keep |= 1u << j;
+      smask &= keep;
+    }
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;

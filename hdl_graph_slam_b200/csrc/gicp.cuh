@@ -20,12 +20,18 @@ constexpr int kLinThreads = 256;
 constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
 
 // ---------------------------------------------------------------- k-NN covariance
+constexpr int kKnnParts = 4;   // warps per query leaf (each searches a disjoint share of the target nodes)
+
 struct KnnList {
   float* d;   // [k][blockDim] (slot-major => conflict-free)
   int* pos;   // sorted position of the neighbour
   const float4* sp;
+  volatile int* shared_kth;  // per query: min over the parts' k-th distances (float bits; valid upper bound of the true k-th)
   int k, cnt, stride;
-  __device__ __forceinline__ float worst() const { return cnt < k ? INFINITY : d[(k - 1) * stride]; }
+  __device__ __forceinline__ float worst() const {
+    const float sb = __int_as_float(*shared_kth);
+    return cnt < k ? sb : fminf(d[(k - 1) * stride], sb);
+  }
   __device__ __forceinline__ float limit() const { return INFINITY; }
   __device__ __forceinline__ bool less_than_slot(float d2, int idx, int slot) const {
     float ds = d[slot * stride];
@@ -43,6 +49,7 @@ struct KnnList {
     }
     d[j * stride] = d2;
     pos[j * stride] = p;
+    if (cnt == k) atomicMin((int*)shared_kth, __float_as_int(d[(k - 1) * stride]));  // non-negative floats order like ints
   }
 };
 
@@ -77,26 +84,61 @@ __device__ __forceinline__ void knn_cov_store(const float4* __restrict__ sp, int
   o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
 }
 
-// one warp per leaf: its 32 points are the queries; per-lane top-k lists in shared memory
+// one BLOCK (kKnnParts warps) per leaf: its 32 points are the queries; every warp searches a disjoint share of the target
+// nodes for the same 32 queries with per-lane top-k lists in shared memory and a shared k-th bound; warp 0 merges.
 __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, double* __restrict__ cov) {
-  extern __shared__ float knn_smem[];
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int leaf = s >> 5;
-  if (leaf >= b.nleaf) return;  // whole warps only (blockDim is a multiple of 32)
+  extern __shared__ float knn_smem[];  // d[k][128], pos[k][128], shared_kth[32]
+  const int leaf = blockIdx.x;
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int s = leaf * kLeaf + lane;
+  int* shared_kth = reinterpret_cast<int*>(knn_smem + 2 * k * blockDim.x);
+  if (threadIdx.x < 32) shared_kth[lane] = __float_as_int(INFINITY);
+  __syncthreads();
   const float4 q = b.sp[s];
   const bool active = idx_bits(q.w) != kPadIdx;
   KnnList L;
   L.d = knn_smem + threadIdx.x;
   L.pos = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + threadIdx.x;
   L.sp = b.sp;
+  L.shared_kth = shared_kth + lane;
   L.k = k;
   L.cnt = 0;
   L.stride = blockDim.x;
-  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf);
-  if (!active) return;
+  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf, part, kKnnParts);
+  // publish list lengths, then warp 0 merges the kKnnParts sorted lists of every query (the own leaf was scanned by all
+  // parts: equal positions are taken once)
+  __shared__ int s_cnt[kKnnParts][32];
+  s_cnt[part][lane] = L.cnt;
+  __syncthreads();
+  if (part != 0 || !active) return;
   const int stride = L.stride;
-  const int* posp = L.pos;
-  knn_cov_store(b.sp, L.cnt, [=](int j) { return posp[j * stride]; }, cov + (size_t)s * 6);
+  float* dbase = knn_smem + lane;
+  int* pbase = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + lane;
+  int head[kKnnParts];
+#pragma unroll
+  for (int p = 0; p < kKnnParts; p++) head[p] = 0;
+  int kk = 0, last_pos = -1;
+  int mpos[64];  // merged neighbour positions (k <= 64); only 32 threads per block reach this point
+  while (kk < k) {
+    float bd = INFINITY;
+    int bi = 0x7fffffff, bp = -1, bpart = -1;
+#pragma unroll
+    for (int p = 0; p < kKnnParts; p++) {
+      if (head[p] < s_cnt[p][lane]) {
+        const float cd = dbase[head[p] * stride + p * 32];
+        const int cp = pbase[head[p] * stride + p * 32];
+        const int ci = idx_bits(b.sp[cp].w);
+        if (cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; bp = cp; bpart = p; }
+      }
+    }
+    if (bpart < 0) break;
+#pragma unroll
+    for (int p = 0; p < kKnnParts; p++) if (p == bpart) head[p]++;
+    if (bp == last_pos) continue;  // duplicate (own leaf scanned by every part)
+    last_pos = bp;
+    mpos[kk++] = bp;
+  }
+  knn_cov_store(b.sp, kk, [&](int j) { return mpos[j]; }, cov + (size_t)s * 6);
 }
 
 // ---------------------------------------------------------------- pose passed by value to the per-iteration kernels
