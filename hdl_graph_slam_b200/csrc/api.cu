@@ -287,14 +287,14 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
   B2R_CUDA(c.cov.reserve(padded * 6 + 6));
   if (c.n > 0) {
     const int k = h->cfg.k_correspondences;
-    const size_t smem = ((size_t)2 * k * kKnnThreads + 32) * sizeof(float);
+    const size_t smem = (size_t)k * kKnnThreads * sizeof(unsigned long long);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
-      B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, (64 * 2 * kKnnThreads + 32) * 4));
+      B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
       attr_set = true;
     }
     TEL_BEGIN(&h->tel, h->st);
-    k_knn_cov<<<(unsigned)(padded / kLeaf), kKnnThreads, smem, h->st>>>(c.bvh(), k, c.cov.p);  // one block (4 warps) per leaf
+    k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(c.bvh(), k, c.raw_view, c.stride_f, c.cov.p);
     TEL_END(&h->tel, KC_KNN_COV, 1, h->st);
     B2R_CUDA(cudaGetLastError());
   }

@@ -72,21 +72,38 @@ B2R_HD float aabb_bound2(float qx, float qy, float qz, float lx, float ly, float
   return fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
 }
 
+// Candidates are ranked by the 64-bit key (float bits of d2) << 32 | original index: d2 >= 0, so integer order of the key ==
+// lexicographic order of (d2, idx) — one compare, and a candidate met twice (seed, overlapping parts) is rejected for free.
+B2R_HD unsigned long long nn_key(float d2, int idx) {
+#ifdef __CUDA_ARCH__
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)idx;
+#else
+  union { float f; unsigned int u; } c; c.f = d2;
+  return ((unsigned long long)c.u << 32) | (unsigned int)idx;
+#endif
+}
+B2R_HD float nn_key_d2(unsigned long long k) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float((unsigned int)(k >> 32));
+#else
+  union { float f; unsigned int u; } c; c.u = (unsigned int)(k >> 32); return c.f;
+#endif
+}
+constexpr unsigned long long kKeyInf = 0x7f8000007fffffffull;  // (+inf, kPadIdx)
+
 // 1-NN visitor
 struct Nn1 {
-  float best_d2;
-  int best_idx;
+  unsigned long long best_key;  // kKeyInf = nothing yet
   int best_pos;
   float lim;
-  B2R_HD float worst() const { return best_d2; }
+  B2R_HD float worst() const { return nn_key_d2(best_key); }
   B2R_HD float limit() const { return lim; }
   B2R_HD void visit(float d2, int idx, int pos) {
-    if (d2 < best_d2 || (d2 == best_d2 && idx < best_idx)) {
-      best_d2 = d2;
-      best_idx = idx;
-      best_pos = pos;
-    }
+    const unsigned long long k = nn_key(d2, idx);
+    if (k < best_key) { best_key = k; best_pos = pos; }
   }
+  B2R_HD float best_d2() const { return nn_key_d2(best_key); }
+  B2R_HD int best_idx() const { return (int)(unsigned int)(best_key & 0xffffffffull); }
 };
 
 // host/device serial reference of the traversal for ONE query (used by tests/host_harness.cu and as documentation of the
@@ -199,7 +216,7 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   if (mask == 0) return;
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
   if (__popc(mask) >= kTileLanes) {
-#pragma unroll 8
+#pragma unroll 2
     for (int t = 0; t < kLeaf; t++) {
       const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
       const int idx = idx_bits(p.w);

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_fitness(const __grid_constan
   if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
+  v.best_key = kKeyInf; v.best_pos = -1; v.lim = INFINITY;
   bool active = false;
   if (idx_bits(p.w) != kPadIdx) {
     qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], p.x, p.y, p.z);
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_fitness(const __grid_constan
   }
   bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);
   if (active && v.best_pos >= 0) {
-    if ((double)v.best_d2 <= A.max_range) { acc[0] = (double)v.best_d2; acc[1] = 1.0; }
-    if (v.best_d2 < A.inlier_thresh_sq) acc[2] = 1.0;
+    if ((double)v.best_d2() <= A.max_range) { acc[0] = (double)v.best_d2(); acc[1] = 1.0; }
+    if (v.best_d2() < A.inlier_thresh_sq) acc[2] = 1.0;
   }
   block_reduce<3>(acc, red);
   finish_partials<3>(acc, A.partials, A.out, A.counter);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_d2 = INFINITY; v.best_idx = 0x7fffffff; v.best_pos = -1; v.lim = INFINITY;
+  v.best_key = kKeyInf; v.best_pos = -1; v.lim = INFINITY;
   bool active = false;
   if (i < n) {
     const float* p = q_raw + (size_t)i * stride_f;
@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_
   }
   bvh_group_search(tgt, qx, qy, qz, active, v, -1);
   if (i < n) {
-    idx_out[i] = v.best_pos >= 0 ? v.best_idx : -1;
-    d2_out[i] = v.best_d2;
+    idx_out[i] = v.best_pos >= 0 ? v.best_idx() : -1;
+    d2_out[i] = v.best_d2();
   }
 }
 

@@ -20,52 +20,43 @@ constexpr int kLinThreads = 256;
 constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
 
 // ---------------------------------------------------------------- k-NN covariance
-constexpr int kKnnParts = 4;   // warps per query leaf (each searches a disjoint share of the target nodes)
-
+// per-lane sorted top-k of packed 64-bit keys in shared memory, slot-major ([k][blockDim]); the k-th key is cached in a
+// register so the all-pairs tile loop costs one 64-bit compare per candidate.
 struct KnnList {
-  float* d;   // [k][blockDim] (slot-major => conflict-free)
-  int* pos;   // sorted position of the neighbour
-  const float4* sp;
-  volatile int* shared_kth;  // per query: min over the parts' k-th distances (float bits; valid upper bound of the true k-th)
+  unsigned long long* key;
   int k, cnt, stride;
-  __device__ __forceinline__ float worst() const {
-    const float sb = __int_as_float(*shared_kth);
-    return cnt < k ? sb : fminf(d[(k - 1) * stride], sb);
-  }
+  unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
+  __device__ __forceinline__ float worst() const { return nn_key_d2(wkey); }
   __device__ __forceinline__ float limit() const { return INFINITY; }
-  __device__ __forceinline__ bool less_than_slot(float d2, int idx, int slot) const {
-    float ds = d[slot * stride];
-    if (d2 < ds) return true;
-    if (d2 > ds) return false;
-    return idx < idx_bits(sp[pos[slot * stride]].w);
-  }
-  __device__ __forceinline__ void visit(float d2, int idx, int p) {
-    if (cnt == k && !less_than_slot(d2, idx, k - 1)) return;
+  __device__ __forceinline__ void visit(float d2, int idx, int) {
+    const unsigned long long kq = nn_key(d2, idx);
+    if (kq >= wkey) return;
     int j = (cnt < k) ? cnt++ : k - 1;
-    while (j > 0 && less_than_slot(d2, idx, j - 1)) {
-      d[j * stride] = d[(j - 1) * stride];
-      pos[j * stride] = pos[(j - 1) * stride];
+    while (j > 0) {
+      const unsigned long long prev = key[(j - 1) * stride];
+      if (prev <= kq) break;
+      key[j * stride] = prev;
       j--;
     }
-    d[j * stride] = d2;
-    pos[j * stride] = p;
-    if (cnt == k) atomicMin((int*)shared_kth, __float_as_int(d[(k - 1) * stride]));  // non-negative floats order like ints
+    key[j * stride] = kq;
+    if (cnt == k) wkey = key[(k - 1) * stride];
   }
 };
 
-// mean / covariance over the neighbours in ascending (d2, index) order (float64), PLANE regularisation, store 6 doubles
-template <class PosAt>
-__device__ __forceinline__ void knn_cov_store(const float4* __restrict__ sp, int kk, PosAt pos_at, double* __restrict__ o) {
+// mean / covariance over the neighbours in ascending (d2, index) order (float64), PLANE regularisation, store 6 doubles.
+// pt_at(j) returns the j-th neighbour's coordinates.
+template <class PtAt>
+__device__ __forceinline__ void knn_cov_store(int kk, PtAt pt_at, double* __restrict__ o) {
   double mx = 0, my = 0, mz = 0;
   for (int j = 0; j < kk; j++) {
-    float4 p = sp[pos_at(j)];
+    const float3 p = pt_at(j);
     mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
   }
   const double inv = 1.0 / (double)kk;
   mx *= inv; my *= inv; mz *= inv;
   double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < kk; j++) {
-    float4 p = sp[pos_at(j)];
+    const float3 p = pt_at(j);
     double vx = (double)p.x - mx, vy = (double)p.y - my, vz = (double)p.z - mz;
     c[0] += vx * vx; c[1] += vx * vy; c[2] += vx * vz;
     c[4] += vy * vy; c[5] += vy * vz; c[8] += vz * vz;
@@ -84,61 +75,29 @@ __device__ __forceinline__ void knn_cov_store(const float4* __restrict__ sp, int
   o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
 }
 
-// one BLOCK (kKnnParts warps) per leaf: its 32 points are the queries; every warp searches a disjoint share of the target
-// nodes for the same 32 queries with per-lane top-k lists in shared memory and a shared k-th bound; warp 0 merges.
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, double* __restrict__ cov) {
-  extern __shared__ float knn_smem[];  // d[k][128], pos[k][128], shared_kth[32]
-  const int leaf = blockIdx.x;
-  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
-  const int s = leaf * kLeaf + lane;
-  int* shared_kth = reinterpret_cast<int*>(knn_smem + 2 * k * blockDim.x);
-  if (threadIdx.x < 32) shared_kth[lane] = __float_as_int(INFINITY);
-  __syncthreads();
+// one warp per leaf (4 leaves per block): its 32 points are the queries; per-lane top-k lists in shared memory
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, const float* __restrict__ raw, int stride_f, double* __restrict__ cov) {
+  extern __shared__ unsigned long long knn_keys[];  // [k][blockDim]
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int leaf = s >> 5;
+  if (leaf >= b.nleaf) return;  // whole warps only (blockDim is a multiple of 32)
   const float4 q = b.sp[s];
   const bool active = idx_bits(q.w) != kPadIdx;
   KnnList L;
-  L.d = knn_smem + threadIdx.x;
-  L.pos = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + threadIdx.x;
-  L.sp = b.sp;
-  L.shared_kth = shared_kth + lane;
+  L.key = knn_keys + threadIdx.x;
   L.k = k;
   L.cnt = 0;
   L.stride = blockDim.x;
-  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf, part, kKnnParts);
-  // publish list lengths, then warp 0 merges the kKnnParts sorted lists of every query (the own leaf was scanned by all
-  // parts: equal positions are taken once)
-  __shared__ int s_cnt[kKnnParts][32];
-  s_cnt[part][lane] = L.cnt;
-  __syncthreads();
-  if (part != 0 || !active) return;
+  L.wkey = kKeyInf;
+  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf);
+  if (!active) return;
   const int stride = L.stride;
-  float* dbase = knn_smem + lane;
-  int* pbase = reinterpret_cast<int*>(knn_smem + k * blockDim.x) + lane;
-  int head[kKnnParts];
-#pragma unroll
-  for (int p = 0; p < kKnnParts; p++) head[p] = 0;
-  int kk = 0, last_pos = -1;
-  int mpos[64];  // merged neighbour positions (k <= 64); only 32 threads per block reach this point
-  while (kk < k) {
-    float bd = INFINITY;
-    int bi = 0x7fffffff, bp = -1, bpart = -1;
-#pragma unroll
-    for (int p = 0; p < kKnnParts; p++) {
-      if (head[p] < s_cnt[p][lane]) {
-        const float cd = dbase[head[p] * stride + p * 32];
-        const int cp = pbase[head[p] * stride + p * 32];
-        const int ci = idx_bits(b.sp[cp].w);
-        if (cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; bp = cp; bpart = p; }
-      }
-    }
-    if (bpart < 0) break;
-#pragma unroll
-    for (int p = 0; p < kKnnParts; p++) if (p == bpart) head[p]++;
-    if (bp == last_pos) continue;  // duplicate (own leaf scanned by every part)
-    last_pos = bp;
-    mpos[kk++] = bp;
-  }
-  knn_cov_store(b.sp, kk, [&](int j) { return mpos[j]; }, cov + (size_t)s * 6);
+  const unsigned long long* keyp = L.key;
+  knn_cov_store(L.cnt, [=](int j) {
+    const int idx = (int)(unsigned int)(keyp[j * stride] & 0xffffffffull);
+    const float* p = raw + (size_t)idx * stride_f;
+    return make_float3(p[0], p[1], p[2]);
+  }, cov + (size_t)s * 6);
 }
 
 // ---------------------------------------------------------------- pose passed by value to the per-iteration kernels
@@ -224,8 +183,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(const __grid_
   const bool is_point = idx_bits(p.w) != kPadIdx;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_d2 = INFINITY;
-  v.best_idx = 0x7fffffff;
+  v.best_key = kKeyInf;
   v.best_pos = -1;
   v.lim = A.lim;
   bool active = false;
@@ -239,8 +197,7 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(const __grid_
         int sp0 = A.cpos[s];
         if (sp0 >= 0) {
           float4 t = A.tgt.sp[sp0];
-          v.best_d2 = dist2_f32(qx, qy, qz, t.x, t.y, t.z);
-          v.best_idx = idx_bits(t.w);
+          v.best_key = nn_key(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w));
           v.best_pos = sp0;
         }
       }
@@ -248,10 +205,10 @@ __global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(const __grid_
   }
   bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
   if (is_point) {
-    const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2 < A.thr2);
-    A.corr[idx_bits(p.w)] = valid ? v.best_idx : -1;
+    const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2() < A.thr2);
+    A.corr[idx_bits(p.w)] = valid ? v.best_idx() : -1;
     A.cpos[s] = valid ? v.best_pos : -1;
-    A.d2[s] = v.best_d2;
+    A.d2[s] = v.best_d2();
     if (valid) {
       const double* ca = A.scov + (size_t)s * 6;
       const double* cb = A.tcov + (size_t)v.best_pos * 6;
