@@ -93,6 +93,7 @@ constexpr unsigned long long kKeyInf = 0x7f8000007fffffffull;  // (+inf, kPadIdx
 
 // 1-NN visitor
 struct Nn1 {
+  static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   unsigned long long best_key;  // kKeyInf = nothing yet
   int best_pos;
   float lim;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   if (mask == 0) return;
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
   if (__popc(mask) >= kTileLanes) {
-#pragma unroll 2
+#pragma unroll Visitor::kTileUnroll
     for (int t = 0; t < kLeaf; t++) {
       const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
       const int idx = idx_bits(p.w);

@@ -23,6 +23,7 @@ constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
 // per-lane sorted top-k of packed 64-bit keys in shared memory, slot-major ([k][blockDim]); the k-th key is cached in a
 // register so the all-pairs tile loop costs one 64-bit compare per candidate.
 struct KnnList {
+  static constexpr int kTileUnroll = 2;  // the insertion loop is big: keep the instruction footprint small (i-cache)
   unsigned long long* key;
   int k, cnt, stride;
   unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
