@@ -60,6 +60,9 @@ SYMBOLS = [
     ("b2r_set_target_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_set_source_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
     ("b2r_promote_source_to_target", C.c_int, [_VP]),
+    ("b2r_prefetch_source", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_prefetch_source_device", C.c_int, [_VP, _VP, _SZ, _SZ]),
+    ("b2r_odometry_prefetch", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_int]),
     ("b2r_synchronize", C.c_int, [_VP]),
     ("b2r_set_profiling", C.c_int, [_VP, C.c_int]),
     ("b2r_get_stats", C.c_int, [_VP, C.POINTER(Stats), C.c_int]),

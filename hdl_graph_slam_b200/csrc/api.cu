@@ -31,8 +31,11 @@ using namespace b2r;
 struct b2r_handle {
   b2r_config cfg;
   cudaStream_t st = nullptr;
-  Cloud clouds[2];
-  int src = 0, tgt = 1;
+  Cloud clouds[3];
+  int src = 0, tgt = 1, nxt = 2;   // nxt: cloud being prefetched for the next set_source (software pipelining)
+  cudaStream_t st2 = nullptr;       // prefetch stream (upload + BVH + covariances of the next source overlap the current align)
+  cudaEvent_t ev_prefetch = nullptr;
+  bool prefetched = false;
   Scratch scr;
   // per-align workspaces (sized by the source)
   DevBuf<int> corr, cpos;
@@ -42,16 +45,20 @@ struct b2r_handle {
   unsigned int* d_counter = nullptr;
   double* h_out = nullptr;          // pinned, 64 doubles
   // staging for pageable uploads
-  void* staging[2] = {nullptr, nullptr};
-  size_t staging_cap[2] = {0, 0};
-  cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+  void* staging[3] = {nullptr, nullptr, nullptr};
+  size_t staging_cap[3] = {0, 0, 0};
+  cudaEvent_t staging_ev[3] = {nullptr, nullptr, nullptr};
   // misc device scratch (queries / outputs)
   DevBuf<float> tmp_f;
   DevBuf<int> tmp_i;
   DevBuf<float4> tmp_f4;
-  DevBuf<unsigned int> keys_a, keys_b;
-  DevBuf<int> vals_a, vals_b;
-  DevBuf<char> sort_tmp;
+  struct BuildCtx {  // per-stream build scratch
+    DevBuf<unsigned int> keys_a, keys_b;
+    DevBuf<int> vals_a, vals_b;
+    DevBuf<char> sort_tmp;
+    int* mm = nullptr;
+    void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
+  } bc[2];
   // last result
   float final_T[16];                // row-major
   bool has_final = false;
@@ -147,11 +154,15 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   }
   auto bail = [&](int code) { b2r_destroy(h); return code; };
   if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
-  for (int i = 0; i < 2; i++) {
+  if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
+  if (cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
+  for (int i = 0; i < 3; i++) {
     int rc = alloc_cloud(h->clouds[i]);
     if (rc) return bail(rc);
     if (cudaEventCreateWithFlags(&h->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   }
+  for (int i = 0; i < 2; i++)
+    if (cudaMalloc(&h->bc[i].mm, 8 * sizeof(int)) != cudaSuccess) return bail(fail(B2R_ECUDA, "device allocation failed"));
   if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMallocHost(&h->h_out, 64 * sizeof(double)) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "device allocation failed"));
@@ -169,7 +180,8 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device_id);
   if (h->st) cudaStreamSynchronize(h->st);
-  for (int i = 0; i < 2; i++) {
+  if (h->st2) cudaStreamSynchronize(h->st2);
+  for (int i = 0; i < 3; i++) {
     Cloud& c = h->clouds[i];
     c.raw.release(); c.sorted.release(); c.leaf_lo.release(); c.leaf_hi.release(); c.sup_lo.release(); c.sup_hi.release(); c.pos_of.release(); c.cov.release();
     ndt_free_map(c.ndt);
@@ -182,7 +194,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->scr.bsum) cudaFree(h->scr.bsum);
   h->scr.cell_of.release(); h->scr.tmp_idx.release();
   h->corr.release(); h->cpos.release(); h->d2.release(); h->mahal.release(); h->partials.release();
-  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->keys_a.release(); h->keys_b.release(); h->vals_a.release(); h->vals_b.release(); h->sort_tmp.release();
+  h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->bc[0].release(); h->bc[1].release();
   h->ndt_work.release();
   h->vg_work.release();
   h->tel.release();
@@ -190,6 +202,8 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->st) cudaStreamDestroy(h->st);
+  if (h->st2) cudaStreamDestroy(h->st2);
+  if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
   delete h;
 }
 
@@ -206,7 +220,7 @@ static bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t stride_bytes, bool device_ptr) {
+static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t stride_bytes, bool device_ptr, cudaStream_t st) {
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "stride_bytes must be a multiple of 4 and >= 12");
   if (n > 0 && !pts) return fail(B2R_EINVAL, "points is NULL");
   if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
@@ -214,7 +228,7 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
   Cloud& c = h->clouds[which];
   c.n = n;
   c.stride_f = (int)(stride_bytes / 4);
-  c.host_ptr = device_ptr ? nullptr : pts;
+  c.host_ptr = pts;  // identity of the caller's buffer (host or device): used to recognise a prefetched cloud
   c.invalidate();
   const size_t bytes = n * stride_bytes;
   if (device_ptr) {
@@ -224,10 +238,10 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
     c.raw_view = c.raw.p;
     if (bytes > 0) {
       if (is_pinned_host(pts)) {
-        B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyHostToDevice, h->st));
+        B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyHostToDevice, st));
         h->tel.h2d += bytes;
       } else {
-        int sidx = which & 1;
+        int sidx = which;
         if (h->staging_cap[sidx] < bytes) {
           if (h->staging[sidx]) { cudaEventSynchronize(h->staging_ev[sidx]); cudaFreeHost(h->staging[sidx]); h->staging[sidx] = nullptr; }
           size_t want = bytes + bytes / 4 + 4096;
@@ -237,17 +251,19 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
           B2R_CUDA(cudaEventSynchronize(h->staging_ev[sidx]));
         }
         std::memcpy(h->staging[sidx], pts, bytes);
-        B2R_CUDA(cudaMemcpyAsync(c.raw.p, h->staging[sidx], bytes, cudaMemcpyHostToDevice, h->st));
+        B2R_CUDA(cudaMemcpyAsync(c.raw.p, h->staging[sidx], bytes, cudaMemcpyHostToDevice, st));
         h->tel.h2d += bytes;
-        B2R_CUDA(cudaEventRecord(h->staging_ev[sidx], h->st));
+        B2R_CUDA(cudaEventRecord(h->staging_ev[sidx], st));
       }
     }
   }
   return B2R_OK;
 }
 
-static int ensure_grid(b2r_handle* h, Cloud& c) {  // builds the implicit BVH (name kept from the first design)
+static int ensure_grid(b2r_handle* h, Cloud& c, int ctx = 0) {  // builds the implicit BVH (name kept from the first design)
   if (c.bvh_ready) return B2R_OK;
+  auto& B = h->bc[ctx];
+  cudaStream_t st = ctx ? h->st2 : h->st;
   const size_t n = c.n;
   const int N = (int)n;
   c.nsup = (int)((n + 1023) / 1024);
@@ -259,28 +275,31 @@ static int ensure_grid(b2r_handle* h, Cloud& c) {  // builds the implicit BVH (n
   B2R_CUDA(c.sup_lo.reserve(c.nsup + 1));
   B2R_CUDA(c.sup_hi.reserve(c.nsup + 1));
   if (n == 0) { c.bvh_ready = true; return B2R_OK; }
-  B2R_CUDA(h->keys_a.reserve(n)); B2R_CUDA(h->keys_b.reserve(n)); B2R_CUDA(h->vals_a.reserve(n)); B2R_CUDA(h->vals_b.reserve(n));
+  B2R_CUDA(B.keys_a.reserve(n)); B2R_CUDA(B.keys_b.reserve(n)); B2R_CUDA(B.vals_a.reserve(n)); B2R_CUDA(B.vals_b.reserve(n));
   size_t tmp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, h->keys_a.p, h->keys_b.p, h->vals_a.p, h->vals_b.p, N, 0, 32, h->st);
-  B2R_CUDA(h->sort_tmp.reserve(tmp_bytes + 256));
-  TEL_BEGIN(&h->tel, h->st);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, B.keys_a.p, B.keys_b.p, B.vals_a.p, B.vals_b.p, N, 0, 30, st);
+  B2R_CUDA(B.sort_tmp.reserve(tmp_bytes + 256));
+  TEL_BEGIN(&h->tel, st);
   const unsigned nb = (unsigned)((n + 255) / 256);
-  k_grid_reset<<<1, 32, 0, h->st>>>(h->scr.mm);
-  k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, h->st>>>(c.raw_view, c.stride_f, N, h->scr.mm);
-  k_fill_i32<<<nb, 256, 0, h->st>>>(c.pos_of.p, N, -1);
-  k_morton_keys<<<nb, 256, 0, h->st>>>(c.raw_view, c.stride_f, N, h->scr.mm, h->keys_a.p, h->vals_a.p);
-  size_t tb = h->sort_tmp.cap;
-  cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->keys_a.p, h->keys_b.p, h->vals_a.p, h->vals_b.p, N, 0, 32, h->st);  // stable: ties keep ascending index
-  k_bvh_leaves<<<c.nsup, 1024, 0, h->st>>>(c.raw_view, c.stride_f, N, h->keys_b.p, h->vals_b.p, c.sorted.p, c.pos_of.p, c.leaf_lo.p, c.leaf_hi.p,
-                                           c.sup_lo.p, c.sup_hi.p);
-  TEL_END(&h->tel, KC_GRID, 10, h->st);
+  k_grid_reset<<<1, 32, 0, st>>>(B.mm);
+  k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, st>>>(c.raw_view, c.stride_f, N, B.mm);
+  k_fill_i32<<<nb, 256, 0, st>>>(c.pos_of.p, N, -1);
+  k_morton_keys<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, N, B.mm, B.keys_a.p, B.vals_a.p);
+  size_t tb = B.sort_tmp.cap;
+  // stable LSD sort: ties keep ascending index.  Keys are 30-bit Hilbert indices, or 0xffffffff for dropped points: the two top
+  // bits are constant among valid keys, so sorting bits [0,30) orders them; dropped points are recognised by their key afterwards
+  cub::DeviceRadixSort::SortPairs(B.sort_tmp.p, tb, B.keys_a.p, B.keys_b.p, B.vals_a.p, B.vals_b.p, N, 0, 32, st);
+  k_bvh_leaves<<<c.nsup, 1024, 0, st>>>(c.raw_view, c.stride_f, N, B.keys_b.p, B.vals_b.p, c.sorted.p, c.pos_of.p, c.leaf_lo.p, c.leaf_hi.p,
+                                        c.sup_lo.p, c.sup_hi.p);
+  TEL_END(&h->tel, KC_GRID, 10, st);
   B2R_CUDA(cudaGetLastError());
   c.bvh_ready = true;
   return B2R_OK;
 }
 
-static int ensure_cov(b2r_handle* h, Cloud& c) {
-  int rc = ensure_grid(h, c);
+static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
+  cudaStream_t st = ctx ? h->st2 : h->st;
+  int rc = ensure_grid(h, c, ctx);
   if (rc) return rc;
   if (c.cov_ready) return B2R_OK;
   const size_t padded = (size_t)c.nsup * 1024;
@@ -293,9 +312,9 @@ static int ensure_cov(b2r_handle* h, Cloud& c) {
       B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
       attr_set = true;
     }
-    TEL_BEGIN(&h->tel, h->st);
-    k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(c.bvh(), k, c.raw_view, c.stride_f, c.cov.p);
-    TEL_END(&h->tel, KC_KNN_COV, 1, h->st);
+    TEL_BEGIN(&h->tel, st);
+    k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, st>>>(c.bvh(), k, c.raw_view, c.stride_f, c.cov.p);
+    TEL_END(&h->tel, KC_KNN_COV, 1, st);
     B2R_CUDA(cudaGetLastError());
   }
   c.cov_ready = true;
@@ -312,12 +331,41 @@ static int preprocess(b2r_handle* h, int which, bool is_target) {
 
 static int set_cloud(b2r_handle* h, bool is_target, const void* pts, size_t n, size_t stride, bool dev) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  if (!is_target && h->prefetched) {
+    Cloud& nx = h->clouds[h->nxt];
+    h->prefetched = false;
+    if (nx.host_ptr == pts && nx.n == n && (size_t)nx.stride_f * 4 == stride) {  // this is the cloud we prefetched: adopt it
+      B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+      std::swap(h->src, h->nxt);
+      B2R_CUDA(cudaStreamWaitEvent(h->st, h->ev_prefetch, 0));
+      h->corr_valid = false;
+      return B2R_OK;
+    }
+  }
   int which = is_target ? h->tgt : h->src;
-  int rc = upload(h, which, pts, n, stride, dev);
+  int rc = upload(h, which, pts, n, stride, dev, h->st);
   if (rc) return rc;
   h->corr_valid = false;
   return preprocess(h, which, is_target);
 }
+
+static int prefetch_source(b2r_handle* h, const void* pts, size_t n, size_t stride, bool dev) {
+  if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  // the buffers of the `nxt` slot may still be read by kernels enqueued on the main stream (it was the source of an earlier
+  // align that has completed: b2r_align synchronises), so they are free to be overwritten here
+  int rc = upload(h, h->nxt, pts, n, stride, dev, h->st2);
+  if (rc) return rc;
+  if (h->cfg.method == B2R_METHOD_GICP) {
+    rc = ensure_cov(h, h->clouds[h->nxt], 1);
+    if (rc) return rc;
+  }
+  B2R_CUDA(cudaEventRecord(h->ev_prefetch, h->st2));
+  h->prefetched = true;
+  return B2R_OK;
+}
+
+extern "C" int b2r_prefetch_source(b2r_handle* h, const void* p, size_t n, size_t s) { return prefetch_source(h, p, n, s, false); }
+extern "C" int b2r_prefetch_source_device(b2r_handle* h, const void* p, size_t n, size_t s) { return prefetch_source(h, p, n, s, true); }
 
 extern "C" int b2r_set_target(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, true, p, n, s, false); }
 extern "C" int b2r_set_source(b2r_handle* h, const void* p, size_t n, size_t s) { return set_cloud(h, false, p, n, s, false); }
@@ -328,6 +376,7 @@ extern "C" int b2r_synchronize(b2r_handle* h) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   B2R_CUDA(cudaStreamSynchronize(h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st2));
   return B2R_OK;
 }
 
@@ -349,6 +398,7 @@ extern "C" int b2r_get_stats(b2r_handle* h, b2r_stats* out, int reset) {
   if (!h || !out) return fail(B2R_EINVAL, "NULL argument");
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   B2R_CUDA(cudaStreamSynchronize(h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st2));
   h->tel.resolve();
   std::memset(out, 0, sizeof(*out));
   out->h2d_bytes = h->tel.h2d;
@@ -742,6 +792,10 @@ struct b2r_odometry {
   bool prev_time_zero = true;
   float prev_trans[16];     // row-major
   float keyframe_pose[16];  // row-major
+  // announced next cloud (b2r_odometry_prefetch): prefetched right after the current source has been adopted
+  const void* next_ptr = nullptr;
+  size_t next_n = 0, next_stride = 0;
+  bool next_device = false, next_pending = false;
 };
 
 static void mat4_identity(float* m) { for (int i = 0; i < 16; i++) m[i] = (i % 5 == 0) ? 1.f : 0.f; }
@@ -805,6 +859,18 @@ extern "C" void b2r_odometry_destroy(b2r_odometry* o) { delete o; }
 
 static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes, const float* msf_delta,
                                   b2r_odometry_status* out, bool device);
+extern "C" int b2r_odometry_prefetch(b2r_odometry* o, const void* cloud, size_t n, size_t stride_bytes, int device) {
+  if (!o) return fail(B2R_EINVAL, "NULL argument");
+  o->next_ptr = cloud; o->next_n = n; o->next_stride = stride_bytes; o->next_device = device != 0; o->next_pending = true;
+  return B2R_OK;
+}
+static int odometry_issue_prefetch(b2r_odometry* o) {
+  if (!o->next_pending) return B2R_OK;
+  o->next_pending = false;
+  return o->next_device ? b2r_prefetch_source_device(o->reg, o->next_ptr, o->next_n, o->next_stride)
+                        : b2r_prefetch_source(o->reg, o->next_ptr, o->next_n, o->next_stride);
+}
+
 extern "C" int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size_t n, size_t stride_bytes,
                                      const float* msf_delta, b2r_odometry_status* out) {
   return odometry_matching_impl(o, stamp, cloud, n, stride_bytes, msf_delta, out, false);
@@ -829,6 +895,8 @@ static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* clo
     o->keyframe_stamp = stamp;
     int rc = device ? b2r_set_target_device(reg, cloud, n, stride_bytes) : b2r_set_target(reg, cloud, n, stride_bytes);
     if (rc) return rc;
+    rc = odometry_issue_prefetch(o);
+    if (rc) return rc;
     o->has_keyframe = true;
     row_to_col(I, out->odom);
     row_to_col(I, out->trans);
@@ -836,6 +904,8 @@ static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* clo
     return B2R_OK;
   }
   int rc = device ? b2r_set_source_device(reg, cloud, n, stride_bytes) : b2r_set_source(reg, cloud, n, stride_bytes);  // :177
+  if (rc) return rc;
+  rc = odometry_issue_prefetch(o);  // the NEXT frame's upload / BVH / covariances overlap this frame's align on a second stream
   if (rc) return rc;
   float guess_row[16], delta_row[16];
   if (msf_delta) { for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) delta_row[r * 4 + c] = msf_delta[c * 4 + r]; }

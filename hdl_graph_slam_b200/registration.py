@@ -97,6 +97,15 @@ class Registration:
     def setInputSourceRaw(self, ptr, n, stride_bytes):
         check(self._lib.b2r_set_source(self._h, C.c_void_p(ptr), n, stride_bytes))
 
+    def prefetchSourceRaw(self, ptr, n, stride_bytes, device=False):
+        fn = self._lib.b2r_prefetch_source_device if device else self._lib.b2r_prefetch_source
+        check(fn(self._h, C.c_void_p(ptr), n, stride_bytes))
+
+    def prefetchSource(self, cloud):
+        a, n, s = _cloud(cloud)
+        self._keep["p"] = a
+        check(self._lib.b2r_prefetch_source(self._h, a.ctypes.data_as(C.c_void_p), n, s))
+
     def synchronize(self):
         check(self._lib.b2r_synchronize(self._h))
 
@@ -275,6 +284,9 @@ class ScanMatchingOdometry:
     def matching(self, stamp, cloud, msf_delta=None):
         a, n, s = _cloud(cloud)
         return self.matching_raw(stamp, a.ctypes.data, n, s, msf_delta)
+
+    def prefetch_raw(self, ptr, n, stride_bytes, device=False):
+        check(self._lib.b2r_odometry_prefetch(self._o, C.c_void_p(ptr), n, stride_bytes, int(device)))
 
     def matching_raw(self, stamp, ptr, n, stride_bytes, msf_delta=None, device=False):
         st = OdometryStatus()

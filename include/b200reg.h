@@ -107,6 +107,11 @@ int b2r_get_stats(b2r_handle* h, b2r_stats* out, int reset);
 const char* b2r_kernel_class_name(int cls);
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on, so callers can bracket it with events */
 int b2r_get_stream(b2r_handle* h, void** stream);
+/* Software pipelining for replay / batch callers that already hold the NEXT source cloud: uploads it and builds its search
+ * structure and covariances on a second stream while the current align() runs.  A following b2r_set_source[_device] with the
+ * same pointer, size and stride adopts the prefetched cloud instead of repeating the work.  Results are unchanged. */
+int b2r_prefetch_source(b2r_handle* h, const void* points, size_t n, size_t stride_bytes);
+int b2r_prefetch_source_device(b2r_handle* h, const void* d_points, size_t n, size_t stride_bytes);
 /* block until everything enqueued on the handle's stream (uploads, grid / covariance / voxel builds) has finished */
 int b2r_synchronize(b2r_handle* h);
 /* keyframe switch `keyframe = filtered; registration->setInputTarget(keyframe)` (scan_matching_odometry_nodelet.cpp:245-246):
@@ -186,6 +191,10 @@ int b2r_odometry_matching(b2r_odometry* o, double stamp, const void* cloud, size
 /* same, for a cloud already resident in device memory (the HBM-resident measurement of bench.py) */
 int b2r_odometry_matching_device(b2r_odometry* o, double stamp, const void* d_cloud, size_t n, size_t stride_bytes, const float* msf_delta,
                                  b2r_odometry_status* out);
+
+/* announce the cloud of the NEXT matching() call: the following matching() prefetches it (b2r_prefetch_source) right after it
+ * has set its own source, so the next frame's preprocessing overlaps this frame's align.  device != 0: device pointer */
+int b2r_odometry_prefetch(b2r_odometry* o, const void* cloud, size_t n, size_t stride_bytes, int device);
 
 /* LoopDetector::matching (include/hdl_graph_slam/loop_detector.hpp:117-171): align every candidate against the new
  * keyframe, keep the best converged fitness.  guesses: n_candidates x 16 floats, column-major (already z-zeroed by the

@@ -108,3 +108,24 @@ def test_loop_batch_equals_sequential_matching(synth):
             assert np.array_equal(np.asarray(rec["T"]).reshape(4, 4).T, r["T"]) and rec["fitness"] == r["fitness"]
             assert bool(rec["converged"]) == r["converged"] and int(rec["iterations"]) == r["iterations"]
     reg.close()
+
+
+def test_prefetch_pipeline_gives_identical_odometry(synth):
+    """announcing the next scan (software pipelining on a second stream) must not change a single bit of the results"""
+    frames = [synth.scan("vlp16_16k", frame=k, stride=8) for k in range(7)]
+    outs = []
+    for use_prefetch in (False, True):
+        reg = pkg.select_registration_method({"registration_method": "FAST_GICP"})
+        odo = pkg.ScanMatchingOdometry(reg, keyframe_delta_trans=1.5, keyframe_delta_angle=1.0, keyframe_delta_time=10000.0)
+        res = []
+        for k, cloud in enumerate(frames):
+            if use_prefetch and k + 1 < len(frames):
+                nxt = frames[k + 1]
+                odo.prefetch_raw(nxt.ctypes.data, nxt.shape[0], nxt.shape[1] * 4)
+            st = odo.matching(0.1 * k, cloud)
+            res.append((st["odom"].copy(), st["iterations"], st["converged"], st["keyframe_updated"]))
+        outs.append(res)
+        odo.close()
+        reg.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a[0], b[0]) and a[1:] == b[1:]
