@@ -362,16 +362,26 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
   // an unrolled loop (uniform addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the
   // warp ORs the 32-bit masks.  Masks are conservative snapshots (worst only shrinks); each leaf is re-tested when visited.
   for (int sbase = 0; sbase < b.nsup; sbase += 32) {
-    unsigned my = 0;
-    const int sn = min(32, b.nsup - sbase);
-    const float w0 = v.worst(), lim0 = v.limit();
-#pragma unroll 8
-    for (int j = 0; j < 32; j++) {
-      if (j < sn) {
-        const float4 slo = __ldg(b.sup_lo + sbase + j), shi = __ldg(b.sup_hi + sbase + j);
-        const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
-        if (!(sb > w0) && sb < lim0) my |= 1u << j;
+    // group prefilter (lane j tests super-node sbase+j against the GROUP's AABB and the group's loosest bound): conservative,
+    // one step for 32 nodes; only the survivors get the exact per-lane test below
+    unsigned gmask;
+    {
+      const float gw = group_max_worst(active, v);
+      const int sg = sbase + lane;
+      float sgb = INFINITY;
+      if (sg < b.nsup) {
+        const float4 slo = __ldg(b.sup_lo + sg), shi = __ldg(b.sup_hi + sg);
+        sgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, slo, shi);
       }
+      gmask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
+    }
+    unsigned my = 0;
+    const float w0 = v.worst(), lim0 = v.limit();
+    for (unsigned gm = gmask; gm; gm &= gm - 1) {
+      const int j = __ffs(gm) - 1;
+      const float4 slo = __ldg(b.sup_lo + sbase + j), shi = __ldg(b.sup_hi + sbase + j);
+      const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
+      if (!(sb > w0) && sb < lim0) my |= 1u << j;
     }
     if (!active) my = 0;
     unsigned smask = __reduce_or_sync(FULL, my);

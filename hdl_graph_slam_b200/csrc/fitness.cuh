@@ -23,7 +23,7 @@ struct FitArgs {
   unsigned int* counter;
 };
 
-__global__ void __launch_bounds__(kLinThreads, 2) k_fitness(const __grid_constant__ FitArgs A) {
+__global__ void __launch_bounds__(kLinThreads, 4) k_fitness(const __grid_constant__ FitArgs A) {
   __shared__ double red[3 * 32];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[3] = {0.0, 0.0, 0.0};

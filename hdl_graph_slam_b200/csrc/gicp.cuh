@@ -16,7 +16,7 @@
 namespace b2r {
 
 constexpr int kKnnThreads = 128;
-constexpr int kLinThreads = 256;
+constexpr int kLinThreads = 128;
 constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
 
 // ---------------------------------------------------------------- k-NN covariance
@@ -173,7 +173,7 @@ struct LinArgs {
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
 };
 
-__global__ void __launch_bounds__(kLinThreads, 2) k_gicp_linearize(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
+__global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
   __shared__ double red[kAcc * 32];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kAcc];
