@@ -43,7 +43,9 @@ struct b2r_handle {
   DevBuf<double> mahal, partials;
   double* d_out = nullptr;          // 64 doubles
   unsigned int* d_counter = nullptr;
-  double* h_out = nullptr;          // pinned, 64 doubles
+  double* h_out = nullptr;          // pinned + mapped, 64 doubles + flags: reduction kernels write results here directly
+  double* h_out_dev = nullptr;      // device alias
+  unsigned long long* h_flag = nullptr; unsigned long long* h_flag_dev = nullptr; unsigned long long seq = 0;
   // staging for pageable uploads
   void* staging[3] = {nullptr, nullptr, nullptr};
   size_t staging_cap[3] = {0, 0, 0};
@@ -164,8 +166,12 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   for (int i = 0; i < 2; i++)
     if (cudaMalloc(&h->bc[i].mm, 8 * sizeof(int)) != cudaSuccess) return bail(fail(B2R_ECUDA, "device allocation failed"));
   if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess || cudaMallocHost(&h->h_out, 64 * sizeof(double)) != cudaSuccess)
+      cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess || cudaHostAlloc(&h->h_out, 72 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void**)&h->h_out_dev, h->h_out, 0) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "device allocation failed"));
+  h->h_flag = reinterpret_cast<unsigned long long*>(h->h_out + 64);
+  h->h_flag_dev = reinterpret_cast<unsigned long long*>(h->h_out_dev + 64);
+  h->h_flag[0] = h->h_flag[1] = h->h_flag[2] = 0;
   cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -434,7 +440,7 @@ static int ensure_align_ws(b2r_handle* h, size_t n_in) {
   B2R_CUDA(h->d2.reserve(n + 1));
   B2R_CUDA(h->mahal.reserve(n * 6 + 6));
   size_t nb = (n + kLinThreads - 1) / kLinThreads + 1;
-  B2R_CUDA(h->partials.reserve(nb * kAcc));
+  B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));  // linearize partials, then the trial-cost partials
   return B2R_OK;
 }
 
@@ -450,7 +456,8 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
   if ((double)lim < A.thr2) lim = std::nextafterf(lim, INFINITY);
   A.lim = lim;
   A.corr = h->corr.p; A.cpos = h->cpos.p; A.d2 = h->d2.p; A.mahal = h->mahal.p;
-  A.partials = h->partials.p; A.out = h->d_out; A.counter = h->d_counter;
+  A.partials = h->partials.p; A.out = h->h_out_dev; A.counter = h->d_counter;
+  A.flag = h->h_flag_dev; A.seq = ++h->seq;
   A.use_seed = seed ? 1 : 0;
   PoseArg P;
   make_pose(x0, P);
@@ -459,9 +466,8 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
     k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
-  B2R_CUDA(cudaMemcpyAsync(h->h_out, h->d_out, kAcc * sizeof(double), cudaMemcpyDeviceToHost, h->st));
   h->tel.d2h += kAcc * sizeof(double);
-  B2R_CUDA(cudaStreamSynchronize(h->st));
+  { int wrc = wait_host_flag(h->h_flag, A.seq, h->st); if (wrc) return wrc; }
   // unpack the upper triangle
   int k = 0;
   for (int r = 0; r < 6; r++)
@@ -477,17 +483,17 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
   Cloud& t = TGT(h);
   ErrArgs A;
   A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos.p; A.mahal = h->mahal.p;
-  A.partials = h->partials.p; A.out = h->d_out + 32; A.counter = h->d_counter + 1;
+  A.partials = h->partials.p + ((size_t)s.nsup * 1024 / kLinThreads + 1) * kAcc; A.out = h->h_out_dev + 32; A.counter = h->d_counter + 1;
+  A.flag = h->h_flag_dev + 1; A.seq = ++h->seq;
   PoseArg P;
   make_pose(xi, P);
-  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
+  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kErrThreads);
   { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_error<<<nb, kLinThreads, 0, h->st>>>(A, P);
+    k_gicp_error<<<nb, kErrThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_ERR, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
-  B2R_CUDA(cudaMemcpyAsync(h->h_out + 32, h->d_out + 32, sizeof(double), cudaMemcpyDeviceToHost, h->st));
   h->tel.d2h += sizeof(double);
-  B2R_CUDA(cudaStreamSynchronize(h->st));
+  { int wrc = wait_host_flag(h->h_flag + 1, A.seq, h->st); if (wrc) return wrc; }
   *y = h->h_out[32];
   return B2R_OK;
 }

@@ -103,6 +103,23 @@ struct Telemetry {
 #define TEL_BEGIN(tel, st) cudaEvent_t _tel_ev = (tel) ? (tel)->begin(st) : nullptr
 #define TEL_END(tel, cls, n, st) do { if (tel) (tel)->end(_tel_ev, cls, n, st); } while (0)
 
+// spin on a host-mapped flag written by the last block of a reduction kernel (finish_partials); falls back to querying the
+// stream every few thousand spins so that a failed launch or a device fault still surfaces as an error
+inline int wait_host_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
+  const volatile unsigned long long* f = flag;
+  for (unsigned long spins = 1;; spins++) {
+    if (*f == seq) return B2R_OK;
+    if ((spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(st);
+      if (e == cudaSuccess) {
+        if (*f == seq) return B2R_OK;
+        return fail(B2R_ECUDA, "reduction kernel finished without signalling its result");
+      }
+      if (e != cudaErrorNotReady) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
+    }
+  }
+}
+
 struct NdtVoxelMap;  // ndt.cuh
 
 // One point cloud resident on the device with everything derived from it.

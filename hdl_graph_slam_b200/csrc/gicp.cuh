@@ -132,9 +132,13 @@ __device__ __forceinline__ void block_reduce(double* v, double* smem /* NV * 32 
   }
 }
 
-// last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in block order
+// last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in block order.
+// `out` may live in host-mapped pinned memory: the result then lands in host memory straight from the kernel and `flag`
+// (also host-mapped) is set to `seq` afterwards, so the host can spin on it instead of paying a memcpy + stream sync.
 template <int NV>
-__device__ __forceinline__ void finish_partials(const double* v, double* partials, double* out, unsigned int* counter) {
+__device__ __forceinline__ void finish_partials(const double* v, double* partials, double* out, unsigned int* counter,
+                                                unsigned long long* flag = nullptr, unsigned long long seq = 0,
+                                                const unsigned long long* extra = nullptr) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -152,7 +156,18 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
       for (unsigned int b = 0; b < gridDim.x; b++) s += P[(size_t)b * NV + threadIdx.x];
       out[threadIdx.x] = s;
     }
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x == 0) {
+      *counter = 0;
+      if (extra) reinterpret_cast<unsigned long long*>(out)[NV] = *reinterpret_cast<const volatile unsigned long long*>(extra);
+    }
+    if (flag) {
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
+        __threadfence_system();
+      }
+    }
   }
 }
 
@@ -170,6 +185,8 @@ struct LinArgs {
   double* partials;            // [blocks][kAcc]
   double* out;                 // [kAcc]
   unsigned int* counter;
+  unsigned long long* flag;    // host-mapped completion flag (see finish_partials)
+  unsigned long long seq;
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
 };
 
@@ -273,7 +290,7 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
     }
   }
   block_reduce<kAcc>(acc, red);
-  finish_partials<kAcc>(acc, A.partials, A.out, A.counter);
+  finish_partials<kAcc>(acc, A.partials, A.out, A.counter, A.flag, A.seq);
 }
 
 struct ErrArgs {
@@ -285,9 +302,12 @@ struct ErrArgs {
   double* partials;  // [blocks]
   double* out;       // [1]
   unsigned int* counter;
+  unsigned long long* flag;
+  unsigned long long seq;
 };
 
-__global__ void __launch_bounds__(kLinThreads) k_gicp_error(ErrArgs A, PoseArg P) {
+constexpr int kErrThreads = 256;
+__global__ void __launch_bounds__(kErrThreads) k_gicp_error(ErrArgs A, PoseArg P) {
   __shared__ double red[32];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[1] = {0.0};
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(kLinThreads) k_gicp_error(ErrArgs A, PoseArg P
     }
   }
   block_reduce<1>(acc, red);
-  finish_partials<1>(acc, A.partials, A.out, A.counter);
+  finish_partials<1>(acc, A.partials, A.out, A.counter, A.flag, A.seq);
 }
 
 }  // namespace b2r

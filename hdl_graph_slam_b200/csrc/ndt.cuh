@@ -50,7 +50,9 @@ struct NdtWork {
   DevBuf<double> partials;
   double* d_out = nullptr;        // 64 doubles
   unsigned int* d_counter = nullptr;
-  double* h_out = nullptr;        // pinned
+  double* h_out = nullptr;        // pinned + mapped: kernels write their results here directly
+  double* h_out_dev = nullptr;    // device alias of h_out
+  unsigned long long* h_flag = nullptr; unsigned long long* h_flag_dev = nullptr; unsigned long long seq = 0;
   VoxGeom* h_geom_pinned = nullptr;
   unsigned long long* d_pairs = nullptr;
   Scratch* scr = nullptr;         // shared build scratch of the handle (set by ndt_ensure_map's caller)
@@ -228,6 +230,8 @@ struct NdtArgs {
   double* out;
   unsigned int* counter;
   unsigned long long* pairs;
+  unsigned long long* flag;  // host-mapped completion flag
+  unsigned long long seq;
 };
 
 __device__ __forceinline__ float dot3f(const float* a, float x, float y, float z) {
@@ -354,7 +358,7 @@ __global__ void __launch_bounds__(kNdtThreads) k_ndt_derivatives(const __grid_co
   for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
   if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
   block_reduce<kNdtAcc>(acc, red);
-  finish_partials<kNdtAcc>(acc, A.partials, A.out, A.counter);
+  finish_partials<kNdtAcc>(acc, A.partials, A.out, A.counter, A.flag, A.seq, A.pairs);
 }
 
 // float64 Hessian-only pass (ndt_omp computeHessian/updateHessian)
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(kNdtThreads) k_ndt_hessian(const __grid_consta
     }
   }
   block_reduce<36>(acc, red);
-  finish_partials<36>(acc, A.partials, A.out, A.counter);
+  finish_partials<36>(acc, A.partials, A.out, A.counter, A.flag, A.seq);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -434,7 +438,11 @@ inline int ndt_init_work(NdtWork& W) {
   B2R_CUDA(cudaMalloc(&W.d_counter, 4 * sizeof(unsigned int)));
   B2R_CUDA(cudaMemset(W.d_counter, 0, 4 * sizeof(unsigned int)));
   B2R_CUDA(cudaMalloc(&W.d_pairs, sizeof(unsigned long long)));
-  B2R_CUDA(cudaMallocHost(&W.h_out, 64 * sizeof(double)));
+  B2R_CUDA(cudaHostAlloc(&W.h_out, 72 * sizeof(double), cudaHostAllocMapped));
+  B2R_CUDA(cudaHostGetDevicePointer((void**)&W.h_out_dev, W.h_out, 0));
+  W.h_flag = reinterpret_cast<unsigned long long*>(W.h_out + 64);
+  W.h_flag_dev = reinterpret_cast<unsigned long long*>(W.h_out_dev + 64);
+  *W.h_flag = 0;
   B2R_CUDA(cudaMallocHost(&W.h_geom_pinned, sizeof(VoxGeom)));
   return B2R_OK;
 }
@@ -711,15 +719,16 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   A.compute_hessian = compute_hessian ? 1 : 0;
   const unsigned nb = (unsigned)((src.n + kNdtThreads - 1) / kNdtThreads);
   B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));
-  A.partials = W.partials.p; A.out = W.d_out; A.counter = W.d_counter; A.pairs = W.d_pairs;
+  A.partials = W.partials.p; A.out = W.h_out_dev; A.counter = W.d_counter; A.pairs = W.d_pairs;
+  A.flag = W.h_flag_dev; A.seq = ++W.seq;
   if (hessian_only) {
     { TEL_BEGIN(W.tel, st);
       k_ndt_hessian<<<nb, kNdtThreads, 0, st>>>(A);
       TEL_END(W.tel, KC_NDT_HESS, 1, st); }
     if (W.tel) W.tel->d2h += 36 * sizeof(double);
     B2R_CUDA(cudaGetLastError());
-    B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, 36 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    B2R_CUDA(cudaStreamSynchronize(st));
+    int rc = wait_host_flag(W.h_flag, A.seq, st);
+    if (rc) return rc;
     std::memcpy(out->H, W.h_out, 36 * sizeof(double));
     return B2R_OK;
   }
@@ -729,13 +738,12 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
     TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
   if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());
-  B2R_CUDA(cudaMemcpyAsync(W.h_out, W.d_out, kNdtAcc * sizeof(double), cudaMemcpyDeviceToHost, st));
-  B2R_CUDA(cudaMemcpyAsync(W.h_out + 48, W.d_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  B2R_CUDA(cudaStreamSynchronize(st));
+  int rc = wait_host_flag(W.h_flag, A.seq, st);
+  if (rc) return rc;
   out->score = W.h_out[0];
   std::memcpy(out->g, W.h_out + 1, 6 * sizeof(double));
   if (compute_hessian) std::memcpy(out->H, W.h_out + 7, 36 * sizeof(double));
-  std::memcpy(&out->pairs, W.h_out + 48, sizeof(unsigned long long));
+  std::memcpy(&out->pairs, W.h_out + kNdtAcc, sizeof(unsigned long long));
   return B2R_OK;
 }
 
