@@ -107,17 +107,19 @@ struct Telemetry {
 // stream every few thousand spins so that a failed launch or a device fault still surfaces as an error
 inline int wait_host_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
   const volatile unsigned long long* f = flag;
-  for (unsigned long spins = 1;; spins++) {
+  for (unsigned long spins = 1; spins < 200000; spins++) {  // ~100-200 us of spinning covers a single in-flight kernel
     if (*f == seq) return B2R_OK;
     if ((spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
-      if (e == cudaSuccess) {
-        if (*f == seq) return B2R_OK;
-        return fail(B2R_ECUDA, "reduction kernel finished without signalling its result");
-      }
+      if (e == cudaSuccess) break;
       if (e != cudaErrorNotReady) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
     }
   }
+  // long wait (other streams' work is ahead of ours on the device): stop burning a core and block
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
+  if (*f == seq) return B2R_OK;
+  return fail(B2R_ECUDA, "reduction kernel finished without signalling its result");
 }
 
 struct NdtVoxelMap;  // ndt.cuh
