@@ -38,9 +38,10 @@ struct b2r_handle {
   bool prefetched = false;
   Scratch scr;
   // per-align workspaces (sized by the source)
-  DevBuf<int> corr, cpos;
+  DevBuf<int> corr[2], cpos[2];     // double-buffered: a speculative linearisation writes the other set
   DevBuf<float> d2;
-  DevBuf<double> mahal, partials;
+  DevBuf<double> mahal[2], partials;
+  int cur = 0;                      // buffer set holding the correspondences of the last ACCEPTED linearisation
   double* d_out = nullptr;          // 64 doubles
   unsigned int* d_counter = nullptr;
   double* h_out = nullptr;          // pinned + mapped, 64 doubles + flags: reduction kernels write results here directly
@@ -199,7 +200,8 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->scr.cursor) cudaFree(h->scr.cursor);
   if (h->scr.bsum) cudaFree(h->scr.bsum);
   h->scr.cell_of.release(); h->scr.tmp_idx.release();
-  h->corr.release(); h->cpos.release(); h->d2.release(); h->mahal.release(); h->partials.release();
+  for (int i = 0; i < 2; i++) { h->corr[i].release(); h->cpos[i].release(); h->mahal[i].release(); }
+  h->d2.release(); h->partials.release();
   h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->bc[0].release(); h->bc[1].release();
   h->ndt_work.release();
   h->vg_work.release();
@@ -435,16 +437,21 @@ static void make_pose(const double* x, PoseArg& P) {
 
 static int ensure_align_ws(b2r_handle* h, size_t n_in) {
   const size_t n = ((n_in + 1023) / 1024) * 1024;
-  B2R_CUDA(h->corr.reserve(n + 1));
-  B2R_CUDA(h->cpos.reserve(n + 1));
+  for (int i = 0; i < 2; i++) {
+    B2R_CUDA(h->corr[i].reserve(n + 1));
+    B2R_CUDA(h->cpos[i].reserve(n + 1));
+    B2R_CUDA(h->mahal[i].reserve(n * 6 + 6));
+  }
   B2R_CUDA(h->d2.reserve(n + 1));
-  B2R_CUDA(h->mahal.reserve(n * 6 + 6));
   size_t nb = (n + kLinThreads - 1) / kLinThreads + 1;
   B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));  // linearize partials, then the trial-cost partials
   return B2R_OK;
 }
 
-static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H, double* b, double* y) {
+// One fused pass at pose x: update_correspondences + linearize into buffer set `wset`; seeds (and, if fuse_error, the trial cost
+// of FastGICP::compute_error) come from buffer set `rset`.  *y_prev receives the trial cost when fuse_error.
+static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, int rset, bool fuse_error, double* H, double* b, double* y,
+                          double* y_prev) {
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
   LinArgs A;
@@ -455,7 +462,8 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
   float lim = (float)A.thr2;
   if ((double)lim < A.thr2) lim = std::nextafterf(lim, INFINITY);
   A.lim = lim;
-  A.corr = h->corr.p; A.cpos = h->cpos.p; A.d2 = h->d2.p; A.mahal = h->mahal.p;
+  A.corr = h->corr[wset].p; A.cpos = h->cpos[wset].p; A.d2 = h->d2.p; A.mahal = h->mahal[wset].p;
+  A.cpos_prev = h->cpos[rset].p; A.mahal_prev = h->mahal[rset].p; A.fuse_error = fuse_error ? 1 : 0;
   A.partials = h->partials.p; A.out = h->h_out_dev; A.counter = h->d_counter;
   A.flag = h->h_flag_dev; A.seq = ++h->seq;
   A.use_seed = seed ? 1 : 0;
@@ -474,7 +482,7 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, double* H,
     for (int c = r; c < 6; c++) { H[r * 6 + c] = H[c * 6 + r] = h->h_out[k++]; }
   for (int i = 0; i < 6; i++) b[i] = h->h_out[21 + i];
   *y = h->h_out[27];
-  h->corr_valid = true;
+  if (y_prev) *y_prev = h->h_out[28];
   return B2R_OK;
 }
 
@@ -482,7 +490,7 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
   ErrArgs A;
-  A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos.p; A.mahal = h->mahal.p;
+  A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos[h->cur].p; A.mahal = h->mahal[h->cur].p;
   A.partials = h->partials.p + ((size_t)s.nsup * 1024 / kLinThreads + 1) * kAcc; A.out = h->h_out_dev + 32; A.counter = h->d_counter + 1;
   A.flag = h->h_flag_dev + 1; A.seq = ++h->seq;
   PoseArg P;
@@ -532,12 +540,17 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
   double lambda = -1.0;
   bool converged = false;
   int it = 0;
-  bool seed = false;
+  // fast_gicp's LM loop (LsqRegistration::computeTransformation / step_lm) with ONE kernel per iteration:
+  // the trial cost compute_error(xi) of iteration i and the linearisation linearize(xi) of iteration i+1 walk the same
+  // points at the same pose, so they are fused into one pass that writes the NEW correspondences into the other buffer
+  // set; the set is adopted only if the step is accepted (rho >= 0), so a rejected trial leaves iteration i's data intact.
+  double H[36], b[6], y0;
+  h->cur = 0;
+  rc = gicp_linearize(h, x0, false, h->cur, h->cur, false, H, b, &y0, nullptr);
+  if (rc) return rc;
+  h->corr_valid = true;
   for (it = 0; it < cfg.max_iterations && !converged; it++) {
-    double H[36], b[6], y0, delta[16];
-    rc = gicp_linearize(h, x0, seed, H, b, &y0);
-    if (rc) return rc;
-    seed = true;
+    double delta[16];
     if (lambda < 0.0) {
       double mx = 0;
       for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 6 + i]));
@@ -554,7 +567,11 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
       se3_exp(d, delta);
       double xi[16], yi;
       mul_iso(delta, x0, xi);
-      rc = gicp_error(h, xi, &yi);
+      // the next iteration exists only if this step does not converge and the iteration cap is not reached
+      const bool will_continue = !gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon) && (it + 1 < cfg.max_iterations);
+      double Hn[36], bn[6], yn = 0;
+      if (will_continue) rc = gicp_linearize(h, xi, true, h->cur ^ 1, h->cur, true, Hn, bn, &yn, &yi);
+      else rc = gicp_error(h, xi, &yi);
       if (rc) return rc;
       double den = 0;
       for (int i = 0; i < 6; i++) den += d[i] * (lambda * d[i] - b[i]);
@@ -563,11 +580,17 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
         if (gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon)) { ok = true; break; }
         lambda = nu * lambda;
         nu = 2 * nu;
-        continue;
+        continue;  // the speculative linearisation (other buffer set) is simply dropped
       }
       double tt = 2 * rho - 1;
       lambda = lambda * std::max(1.0 / 3.0, 1 - tt * tt * tt);
       std::memcpy(x0, xi, sizeof(xi));
+      if (will_continue) {  // adopt the linearisation at the accepted pose: it IS the next iteration's linearize(x0)
+        h->cur ^= 1;
+        std::memcpy(H, Hn, sizeof(H));
+        std::memcpy(b, bn, sizeof(b));
+        y0 = yn;
+      }
       ok = true;
       break;
     }
@@ -705,7 +728,7 @@ extern "C" int b2r_get_correspondences(b2r_handle* h, int32_t* out, size_t n) {
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   if (!h->corr_valid) return fail(B2R_ESTATE, "no linearisation has run since the clouds were set");
   if (n != SRC(h).n) return fail(B2R_EINVAL, "n does not match the source cloud");
-  B2R_CUDA(cudaMemcpyAsync(out, h->corr.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaMemcpyAsync(out, h->corr[h->cur].p, n * sizeof(int), cudaMemcpyDeviceToHost, h->st));
   B2R_CUDA(cudaStreamSynchronize(h->st));
   return B2R_OK;
 }
@@ -747,7 +770,10 @@ extern "C" int b2r_gicp_linearize_at(b2r_handle* h, const double T[16], double* 
   double x[16];
   for (int r = 0; r < 4; r++)
     for (int c = 0; c < 4; c++) x[r * 4 + c] = T[c * 4 + r];
-  return gicp_linearize(h, x, false, H, b, err);
+  h->cur = 0;
+  rc = gicp_linearize(h, x, false, 0, 0, false, H, b, err, nullptr);
+  if (rc == B2R_OK) h->corr_valid = true;
+  return rc;
 }
 
 extern "C" int b2r_gicp_error_at(b2r_handle* h, const double T[16], double* err) {

@@ -17,7 +17,7 @@ namespace b2r {
 
 constexpr int kKnnThreads = 128;
 constexpr int kLinThreads = 128;
-constexpr int kAcc = 28;  // 21 (upper H) + 6 (b) + 1 (cost)
+constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at this pose with the PREVIOUS correspondences)
 
 // ---------------------------------------------------------------- k-NN covariance
 // per-lane sorted top-k of packed 64-bit keys in shared memory, slot-major ([k][blockDim]); the k-th key is cached in a
@@ -179,7 +179,10 @@ struct LinArgs {
   double thr2;                 // max_correspondence_distance^2 (double, compared against (double)d2)
   float lim;                   // float >= thr2 (search range limit)
   int* corr;                   // [n_src original] target ORIGINAL index or -1
-  int* cpos;                   // [sorted s] target sorted position or -1
+  int* cpos;                   // [sorted s] target sorted position or -1 (written)
+  const int* cpos_prev;        // previous iteration's correspondences: search seeds, and the trial cost (compute_error) when fuse_error
+  const double* mahal_prev;    // previous iteration's M_i (fuse_error)
+  int fuse_error;              // 1: also accumulate sum e^T M_prev e over the previous correspondences into acc[28]
   float* d2;                   // [sorted s] NN squared distance
   double* mahal;               // [sorted s][6]
   double* partials;            // [blocks][kAcc]
@@ -212,13 +215,28 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
     if (finite3(qx, qy, qz)) {
       active = true;
       if (A.use_seed) {  // last iteration's correspondent is a real candidate: a tight, exact upper bound
-        int sp0 = A.cpos[s];
+        int sp0 = A.cpos_prev[s];
         if (sp0 >= 0) {
           float4 t = A.tgt.sp[sp0];
           v.best_key = nn_key(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w));
           v.best_pos = sp0;
         }
       }
+    }
+  }
+  if (A.fuse_error && is_point) {  // FastGICP::compute_error at this pose with the previous correspondences / mahalanobis
+    const int tp = A.cpos_prev[s];
+    if (tp >= 0) {
+      const float4 tb = A.tgt.sp[tp];
+      const double* m = A.mahal_prev + (size_t)s * 6;
+      const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;
+      const double ex = (double)tb.x - (P.T[0] * ax + P.T[1] * ay + P.T[2] * az + P.T[3]);
+      const double ey = (double)tb.y - (P.T[4] * ax + P.T[5] * ay + P.T[6] * az + P.T[7]);
+      const double ez = (double)tb.z - (P.T[8] * ax + P.T[9] * ay + P.T[10] * az + P.T[11]);
+      const double Mex = m[0] * ex + m[1] * ey + m[2] * ez;
+      const double Mey = m[1] * ex + m[3] * ey + m[4] * ez;
+      const double Mez = m[2] * ex + m[4] * ey + m[5] * ez;
+      acc[28] = ex * Mex + ey * Mey + ez * Mez;
     }
   }
   bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
