@@ -93,6 +93,7 @@ constexpr unsigned long long kKeyInf = 0x7f8000007fffffffull;  // (+inf, kPadIdx
 
 // 1-NN visitor
 struct Nn1 {
+  static constexpr int kTileLanes = 8;   // below 8 interested lanes the cooperative mode (1 step per lane) beats the 32-step tile
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   unsigned long long best_key;  // kKeyInf = nothing yet
   int best_pos;
@@ -207,7 +208,6 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
 //   coop mode  (few lanes interested): for each interested lane L the 32 lanes evaluate the leaf's 32 candidates in ONE
 //              step (lane t owns candidate t), then L's visitor consumes the acceptable ones best-first.
 // Both feed exactly the same (d2, idx) candidates to the same visitors, so the result is identical.
-constexpr int kTileLanes = 3;
 
 template <class Visitor>
 __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   unsigned mask = __ballot_sync(FULL, pass);
   if (mask == 0) return;
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
-  if (__popc(mask) >= kTileLanes) {
+  if (__popc(mask) >= Visitor::kTileLanes) {
 #pragma unroll Visitor::kTileUnroll
     for (int t = 0; t < kLeaf; t++) {
       const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
@@ -235,15 +235,14 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
     float wL = __shfl_sync(FULL, v.worst(), L);
     bool ok = (my_idx != kPadIdx) && !(d2 > wL);
     while (__ballot_sync(FULL, ok)) {
-      float bd = ok ? d2 : INFINITY;
-      int bi = ok ? my_idx : 0x7fffffff, bl = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float od = __shfl_xor_sync(FULL, bd, o);
-        const int oi = __shfl_xor_sync(FULL, bi, o);
-        const int ol = __shfl_xor_sync(FULL, bl, o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bl = ol; }
-      }
+      // best acceptable candidate: min d2 (non-negative floats order like unsigned ints), then min index among equals
+      const unsigned int du = ok ? __float_as_uint(d2) : 0xffffffffu;
+      const unsigned int dmin = __reduce_min_sync(FULL, du);
+      const unsigned int iu = (ok && du == dmin) ? (unsigned int)my_idx : 0xffffffffu;
+      const unsigned int imin = __reduce_min_sync(FULL, iu);
+      const int bl = __ffs(__ballot_sync(FULL, ok && du == dmin && iu == imin)) - 1;
+      const float bd = __uint_as_float(dmin);
+      const int bi = (int)imin;
       if (lane == L) v.visit(bd, bi, l * kLeaf + bl);
       if (lane == bl) ok = false;
       wL = __shfl_sync(FULL, v.worst(), L);

@@ -23,6 +23,7 @@ constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at 
 // per-lane sorted top-k of packed 64-bit keys in shared memory, slot-major ([k][blockDim]); the k-th key is cached in a
 // register so the all-pairs tile loop costs one 64-bit compare per candidate.
 struct KnnList {
+  static constexpr int kTileLanes = 3;   // coop mode only when 1-2 lanes want the leaf (each pick costs an insertion)
   static constexpr int kTileUnroll = 2;  // the insertion loop is big: keep the instruction footprint small (i-cache)
   unsigned long long* key;
   int k, cnt, stride;
@@ -64,16 +65,17 @@ __device__ __forceinline__ void knn_cov_store(int kk, PtAt pt_at, double* __rest
   }
   c[0] *= inv; c[1] *= inv; c[2] *= inv; c[4] *= inv; c[5] *= inv; c[8] *= inv;
   c[3] = c[1]; c[6] = c[2]; c[7] = c[5];
-  // PLANE regularisation: eigenvalues (descending) replaced by (1, 1, 1e-3)
-  double w[3], V[9];
-  sym_eigen3(c, w, V);
-  const double v0 = 1e-3, v1 = 1.0, v2 = 1.0;  // ascending order: smallest -> 1e-3
-  o[0] = v2 * V[2] * V[2] + v1 * V[1] * V[1] + v0 * V[0] * V[0];
-  o[1] = v2 * V[2] * V[5] + v1 * V[1] * V[4] + v0 * V[0] * V[3];
-  o[2] = v2 * V[2] * V[8] + v1 * V[1] * V[7] + v0 * V[0] * V[6];
-  o[3] = v2 * V[5] * V[5] + v1 * V[4] * V[4] + v0 * V[3] * V[3];
-  o[4] = v2 * V[5] * V[8] + v1 * V[4] * V[7] + v0 * V[3] * V[6];
-  o[5] = v2 * V[8] * V[8] + v1 * V[7] * V[7] + v0 * V[6] * V[6];
+  // PLANE regularisation: singular values (descending) replaced by (1, 1, 1e-3).  With orthonormal eigenvectors
+  // v0 (smallest), v1, v2:  1*v2 v2^T + 1*v1 v1^T + 1e-3*v0 v0^T  ==  I - (1 - 1e-3) v0 v0^T : only the normal is needed.
+  double n[3];
+  sym_min_eigvec3(c, n);
+  const double w = 1.0 - 1e-3;
+  o[0] = 1.0 - w * n[0] * n[0];
+  o[1] = -w * n[0] * n[1];
+  o[2] = -w * n[0] * n[2];
+  o[3] = 1.0 - w * n[1] * n[1];
+  o[4] = -w * n[1] * n[2];
+  o[5] = 1.0 - w * n[2] * n[2];
 }
 
 // one warp per leaf (4 leaves per block): its 32 points are the queries; per-lane top-k lists in shared memory

@@ -54,6 +54,7 @@ static HostBvh build(const std::vector<float>& pts, int n) {
 
 struct HostKnn {
   static constexpr int kTileUnroll = 1;
+  static constexpr int kTileLanes = 3;
   std::vector<float> d;
   std::vector<int> id;
   int k, cnt = 0;
