@@ -91,21 +91,24 @@ B2R_HD float nn_key_d2(unsigned long long k) {
 }
 constexpr unsigned long long kKeyInf = 0x7f8000007fffffffull;  // (+inf, kPadIdx)
 
-// 1-NN visitor
+// 1-NN visitor: (d2, idx) kept in two registers — one float compare per candidate, the index only breaks exact ties
 struct Nn1 {
   static constexpr int kTileLanes = 8;   // below 8 interested lanes the cooperative mode (1 step per lane) beats the 32-step tile
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
-  unsigned long long best_key;  // kKeyInf = nothing yet
+  float bd2;       // +inf = nothing yet
+  int bidx;        // kPadIdx = nothing yet
   int best_pos;
   float lim;
-  B2R_HD float worst() const { return nn_key_d2(best_key); }
+  B2R_HD void reset(float limit_) { bd2 = INFINITY; bidx = kPadIdx; best_pos = -1; lim = limit_; }
+  B2R_HD void seed(float d2, int idx, int pos) { bd2 = d2; bidx = idx; best_pos = pos; }
+  B2R_HD float worst() const { return bd2; }
   B2R_HD float limit() const { return lim; }
   B2R_HD void visit(float d2, int idx, int pos) {
-    const unsigned long long k = nn_key(d2, idx);
-    if (k < best_key) { best_key = k; best_pos = pos; }
+    // padding entries carry (+inf, kPadIdx): never better than anything, so no explicit padding test is needed
+    if (d2 < bd2 || (d2 == bd2 && idx < bidx)) { bd2 = d2; bidx = idx; best_pos = pos; }
   }
-  B2R_HD float best_d2() const { return nn_key_d2(best_key); }
-  B2R_HD int best_idx() const { return (int)(unsigned int)(best_key & 0xffffffffull); }
+  B2R_HD float best_d2() const { return bd2; }
+  B2R_HD int best_idx() const { return bidx; }
 };
 
 // host/device serial reference of the traversal for ONE query (used by tests/host_harness.cu and as documentation of the
@@ -220,8 +223,7 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #pragma unroll Visitor::kTileUnroll
     for (int t = 0; t < kLeaf; t++) {
       const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-      const int idx = idx_bits(p.w);
-      if (pass && idx != kPadIdx) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx, l * kLeaf + t);
+      if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
     }
     return;
   }

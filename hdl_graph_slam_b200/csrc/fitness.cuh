@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_fitness(const __grid_constan
   if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_key = kKeyInf; v.best_pos = -1; v.lim = INFINITY;
+  v.reset(INFINITY);
   bool active = false;
   if (idx_bits(p.w) != kPadIdx) {
     qx = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], p.x, p.y, p.z);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256, 2) k_nearest(const float* __restrict__ q_
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_key = kKeyInf; v.best_pos = -1; v.lim = INFINITY;
+  v.reset(INFINITY);
   bool active = false;
   if (i < n) {
     const float* p = q_raw + (size_t)i * stride_f;

@@ -206,9 +206,7 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
   const bool is_point = idx_bits(p.w) != kPadIdx;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   Nn1 v;
-  v.best_key = kKeyInf;
-  v.best_pos = -1;
-  v.lim = A.lim;
+  v.reset(A.lim);
   bool active = false;
   if (is_point) {
     qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
@@ -220,8 +218,7 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
         int sp0 = A.cpos_prev[s];
         if (sp0 >= 0) {
           float4 t = A.tgt.sp[sp0];
-          v.best_key = nn_key(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w));
-          v.best_pos = sp0;
+          v.seed(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w), sp0);
         }
       }
     }

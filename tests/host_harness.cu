@@ -102,14 +102,14 @@ int main(int argc, char** argv) {
   orc_knn(pts.data(), n, 4, qs.data(), nq, 4, k, oidx.data(), od2.data(), 0);
   long bad1 = 0, badk = 0, badlim = 0;
   for (int i = 0; i < nq; i++) {
-    Nn1 v; v.best_key = kKeyInf; v.best_pos = -1; v.lim = INFINITY;
+    Nn1 v; v.reset(INFINITY);
     bvh_search_one(H.b, qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], v);
     if (v.best_idx() != oidx[(size_t)i * k] || v.best_d2() != od2[(size_t)i * k]) {
       if (bad1 < 5) printf("1nn mismatch q%d: got (%g,%d) want (%g,%d)\n", i, v.best_d2(), v.best_idx(), od2[(size_t)i * k], oidx[(size_t)i * k]);
       bad1++;
     }
     // range-limited search (GICP: limit 6.25): result must agree whenever the true NN is inside the limit
-    Nn1 w; w.best_key = kKeyInf; w.best_pos = -1; w.lim = 6.25f;
+    Nn1 w; w.reset(6.25f);
     bvh_search_one(H.b, qs[i * 4], qs[i * 4 + 1], qs[i * 4 + 2], w);
     bool want_valid = od2[(size_t)i * k] < 6.25f;
     bool got_valid = w.best_pos >= 0 && w.best_d2() < 6.25f;
