@@ -1,0 +1,133 @@
+"""GPU edge cases against the oracle: tiny clouds (fewer points than k), duplicated points (exact ties), packed 16-byte
+records, non-finite points, far-apart clouds (no correspondence inside max_correspondence_distance), big k."""
+import numpy as np
+import pytest
+import hdl_graph_slam_b200 as pkg
+from common import rot_err, trans_err, perturb, relrel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def reg():
+    r = pkg.select_registration_method({"registration_method": "FAST_GICP"})
+    yield r
+    r.close()
+
+
+def test_fewer_points_than_k(reg, oracle):
+    rng = np.random.default_rng(0)
+    tgt = np.c_[rng.uniform(-1, 1, (7, 3)), np.ones(7)].astype(np.float32)
+    src = np.c_[rng.uniform(-1, 1, (5, 3)), np.ones(5)].astype(np.float32)
+    reg.setInputTarget(tgt)
+    reg.setInputSource(src)
+    for which, cloud in ((0, src), (1, tgt)):
+        got = reg.getCovariances(which, cloud.shape[0])
+        want = oracle.gicp_covariances(cloud, 20)  # the oracle uses the min(k, n) neighbours it finds
+        assert np.max(np.abs(got - want)) < 1e-8
+    idx, d2 = reg.nearestKSearch(src)
+    oi, od = oracle.knn(tgt, src, 1)
+    assert np.array_equal(idx, oi[:, 0]) and np.array_equal(d2, od[:, 0])
+
+
+def test_duplicate_points_and_ties(reg, oracle, synth):
+    base = synth.scan("vlp16_16k", frame=0, stride=8)[::16].copy()
+    tgt = np.concatenate([base, base, base[::2]])          # every point 2-3 times: exact ties everywhere
+    src = base[::3].copy()                                 # queries coincide with target points: d2 == 0 ties
+    reg.setInputTarget(tgt)
+    idx, d2 = reg.nearestKSearch(src)
+    oi, od = oracle.knn(tgt, src, 1)
+    assert np.array_equal(idx, oi[:, 0]) and np.array_equal(d2, od[:, 0]) and np.all(d2 == 0)
+    assert np.all(idx < base.shape[0])                     # lowest index among the duplicates
+    reg.setInputSource(src)
+    H, b, e = reg.gicpLinearizeAt(np.eye(4))
+    sc, tc = oracle.gicp_covariances(src, 20), oracle.gicp_covariances(tgt, 20)
+    o = oracle.gicp_linearize(src, sc, tgt, tc, np.eye(4), 2.5)
+    assert np.array_equal(reg.getCorrespondences(src.shape[0]), o["corr"])
+
+
+def test_packed_float4_records_equal_pointxyzi_records(synth):
+    c8 = synth.scan("vlp16_16k", frame=2, stride=8)
+    t8 = synth.scan("vlp16_16k", frame=3, stride=8)
+    c4, t4 = np.ascontiguousarray(c8[:, :4]), np.ascontiguousarray(t8[:, :4])
+    out = []
+    for s, t in ((c8, t8), (c4, t4)):
+        r = pkg.select_registration_method({"registration_method": "FAST_GICP"})
+        r.setInputTarget(t)
+        r.setInputSource(s)
+        r.align(np.eye(4, dtype=np.float32))
+        out.append((r.getFinalTransformation(), r.nr_iterations, r.getFitnessScore()))
+        r.close()
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]
+
+
+def test_non_finite_points_are_ignored(reg, oracle, synth):
+    tgt = synth.scan("vlp16_16k", frame=0, stride=8)[::4].copy()
+    src = synth.scan("vlp16_16k", frame=1, stride=8)[::4].copy()
+    tgt_bad = tgt.copy()
+    tgt_bad[5, 0] = np.nan
+    tgt_bad[77, 2] = np.inf
+    keep = np.ones(len(tgt), bool)
+    keep[[5, 77]] = False
+    reg.setInputTarget(tgt_bad)
+    idx, d2 = reg.nearestKSearch(src)
+    oi, od = oracle.knn(tgt[keep], src, 1)
+    remap = np.nonzero(keep)[0]
+    assert np.array_equal(idx, remap[oi[:, 0]]) and np.array_equal(d2, od[:, 0])
+
+
+def test_no_correspondence_within_range(reg, synth):
+    tgt = synth.scan("vlp16_16k", frame=0, stride=8)
+    src = tgt.copy()
+    src[:, 0] += 500.0  # far outside max_correspondence_distance
+    reg.setInputTarget(tgt)
+    reg.setInputSource(src)
+    reg.align(np.eye(4, dtype=np.float32))
+    assert np.all(reg.getCorrespondences(src.shape[0]) == -1)
+    T = reg.getFinalTransformation()
+    assert np.all(np.isfinite(T)) or not reg.hasConverged()
+
+
+def test_large_k(oracle, synth):
+    cloud = synth.scan("vlp16_16k", frame=0, stride=8)[::8].copy()
+    r = pkg.select_registration_method({"registration_method": "FAST_GICP", "reg_correspondence_randomness": 40})
+    r.setInputTarget(cloud)
+    got = r.getCovariances(1, cloud.shape[0])
+    want = oracle.gicp_covariances(cloud, 40)
+    assert np.max(np.abs(got - want)) < 1e-8
+    r.close()
+
+
+def test_full_size_properties(synth):
+    """BASELINE size (65 536 pts): size-independent properties — identity on identical clouds, A->B then B->A ~ inverse,
+    permutation invariance of the integer outputs"""
+    a = synth.scan("vlp16", frame=0, stride=8)
+    b = synth.scan("vlp16", frame=1, stride=8)
+    r = pkg.select_registration_method({"registration_method": "FAST_GICP"})
+    r.setInputTarget(a)
+    r.setInputSource(a)
+    r.align(np.eye(4, dtype=np.float32))
+    assert r.hasConverged() and trans_err(r.getFinalTransformation(), np.eye(4)) < 1e-5
+    corr = r.getCorrespondences(a.shape[0])
+    assert np.array_equal(corr, np.arange(a.shape[0]))      # every point matches itself
+    r.setInputSource(b)
+    r.align(np.eye(4, dtype=np.float32))
+    Tab = r.getFinalTransformation().astype(np.float64)
+    score_ab, used, inl = r.getFitnessScore(full=True)
+    r.setInputTarget(b)
+    r.setInputSource(a)
+    r.align(np.eye(4, dtype=np.float32))
+    Tba = r.getFinalTransformation().astype(np.float64)
+    assert trans_err(Tab @ Tba, np.eye(4)) < 0.05 and rot_err(Tab @ Tba, np.eye(4)) < 5e-3
+    # permuting the source permutes the correspondences and leaves counts / fitness unchanged
+    perm = np.random.default_rng(1).permutation(b.shape[0])
+    r.setInputTarget(a)
+    r.setInputSource(b)
+    H1, b1, e1 = r.gicpLinearizeAt(Tab)
+    c1 = r.getCorrespondences(b.shape[0])
+    r.setInputSource(b[perm].copy())
+    H2, b2, e2 = r.gicpLinearizeAt(Tab)
+    c2 = r.getCorrespondences(b.shape[0])
+    assert np.array_equal(c1[perm], c2)
+    assert relrel(H1, H2) < 1e-9 and abs(e1 - e2) <= 1e-9 * abs(e1)
+    r.close()
