@@ -562,8 +562,9 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
       double A[36], nb[6], d[6];
       for (int i = 0; i < 36; i++) A[i] = H[i] + ((i % 7 == 0) ? lambda : 0.0);
       for (int i = 0; i < 6; i++) nb[i] = -b[i];
-      if (!ldlt6_solve(A, nb, d))
-        for (int i = 0; i < 6; i++) d[i] = NAN;
+      bool solved = ldlt6_solve(A, nb, d);
+      for (int i = 0; i < 6; i++) solved &= std::isfinite(d[i]);
+      if (!solved) break;  // singular / non-finite step: "lm not converged", pose keeps its last valid value (oracle/gicp.cpp)
       se3_exp(d, delta);
       double xi[16], yi;
       mul_iso(delta, x0, xi);

@@ -319,8 +319,12 @@ extern "C" void orc_gicp_align(const float* src, size_t n, size_t sstride, const
       double A[36], nb[6], d[6];
       for (int i = 0; i < 36; i++) A[i] = H[i] + ((i % 7 == 0) ? lambda : 0.0);
       for (int i = 0; i < 6; i++) nb[i] = -b[i];
-      if (!ldlt6_solve(A, nb, d))
-        for (int i = 0; i < 6; i++) d[i] = NAN;
+      bool solved = ldlt6_solve(A, nb, d);
+      for (int i = 0; i < 6; i++) solved &= std::isfinite(d[i]);
+      // Deliberate choice (the reference's behaviour is undefined here: Eigen LDLT on a singular system yields NaN/inf and
+      // maxCoeff() over NaN is unspecified): a singular / non-finite step ends the optimisation as "lm not converged",
+      // the pose keeps its last valid value and converged_ stays false (hdl_graph_slam then skips the frame / candidate).
+      if (!solved) break;
       se3_exp(d, delta);
       double xi[16];
       mul4_iso(delta, x0, xi);
