@@ -32,7 +32,7 @@ public:
   // (scan_matching_odometry_nodelet.cpp:316) — forwards to the device grid.
   class DeviceSearch : public pcl::search::Search<PointT> {
   public:
-    explicit DeviceSearch(b2r_handle* h) : pcl::search::Search<PointT>("b200"), h_(h) {}
+    explicit DeviceSearch(B200Registration* owner) : pcl::search::Search<PointT>("b200"), owner_(owner) {}
     void setInputCloud(const typename pcl::search::Search<PointT>::PointCloudConstPtr&, const typename pcl::search::Search<PointT>::IndicesConstPtr& = typename pcl::search::Search<PointT>::IndicesConstPtr()) override {}
     int nearestKSearch(const PointT& p, int k, std::vector<int>& idx, std::vector<float>& d2) const override {
       idx.assign(1, -1);
@@ -40,7 +40,10 @@ public:
       if (k < 1) return 0;
       int32_t i = -1;
       float d = 0.f;
-      if (b2r_target_nearest(h_, &p, 1, sizeof(PointT), &i, &d) != B2R_OK || i < 0) return 0;
+      if (!owner_->cachedNearest(p, &i, &d)) {  // not the sequential sweep of getFitnessScore / the inlier loop: exact single query
+        if (b2r_target_nearest(owner_->h_, &p, 1, sizeof(PointT), &i, &d) != B2R_OK) return 0;
+      }
+      if (i < 0) return 0;
       idx[0] = i;
       d2[0] = d;
       return 1;
@@ -52,8 +55,41 @@ public:
     }
 
   private:
-    b2r_handle* h_;
+    B200Registration* owner_;
   };
+
+  // pcl::Registration::getFitnessScore (non-virtual, called through the base pointer at loop_detector.hpp:146 and
+  // scan_matching_odometry_nodelet.cpp:307) and the inlier loop (:314-316) sweep the transformed source cloud point by point
+  // through tree_->nearestKSearch.  Answering 65 536 single queries with 65 536 kernel launches would throw the speed-up
+  // away, so the first query after an align() transforms the source with PCL's OWN pcl::transformPointCloud (bit-identical
+  // coordinates to the ones the base class will ask about), resolves all of them in ONE b2r_target_nearest call and serves
+  // the sweep from that cache; a query that is not the next cached point falls back to an exact single query.
+  bool cachedNearest(const PointT& p, int32_t* idx, float* d2) {
+    if (!this->input_ || this->input_->points.empty()) return false;
+    if (!cache_valid_) {
+      pcl::transformPointCloud(*this->input_, cache_cloud_, this->final_transformation_);
+      const size_t n = cache_cloud_.points.size();
+      cache_idx_.resize(n);
+      cache_d2_.resize(n);
+      if (b2r_target_nearest(h_, cache_cloud_.points.data(), n, sizeof(PointT), cache_idx_.data(), cache_d2_.data()) != B2R_OK) return false;
+      cache_valid_ = true;
+      cache_cursor_ = 0;
+    }
+    const size_t n = cache_cloud_.points.size();
+    for (int attempt = 0; attempt < 2; attempt++) {  // the sweep restarts from 0 for the second consumer (inlier loop)
+      const size_t c = attempt == 0 ? cache_cursor_ : 0;
+      if (c < n) {
+        const PointT& q = cache_cloud_.points[c];
+        if (q.x == p.x && q.y == p.y && q.z == p.z) {
+          *idx = cache_idx_[c];
+          *d2 = cache_d2_[c];
+          cache_cursor_ = c + 1;
+          return true;
+        }
+      }
+    }
+    return false;
+  }
 
   explicit B200Registration(const b2r_config& cfg) {
     if (b2r_create(&cfg, &h_) != B2R_OK) throw std::runtime_error(std::string("b200reg: ") + b2r_last_error());
@@ -61,13 +97,14 @@ public:
     this->max_iterations_ = cfg.max_iterations;
     this->transformation_epsilon_ = cfg.transformation_epsilon;
     this->corr_dist_threshold_ = cfg.max_correspondence_distance;
-    this->setSearchMethodTarget(typename pcl::search::Search<PointT>::Ptr(new DeviceSearch(h_)), /*force_no_recompute=*/true);
+    this->setSearchMethodTarget(typename pcl::search::Search<PointT>::Ptr(new DeviceSearch(this)), /*force_no_recompute=*/true);
   }
   ~B200Registration() override { b2r_destroy(h_); }
 
   void setInputSource(const PointCloudSourceConstPtr& cloud) override {
     if (cloud == this->input_) return;  // same early-out as fast_gicp
     Base::setInputSource(cloud);
+    cache_valid_ = false;
     b2r_set_source(h_, cloud->points.data(), cloud->points.size(), sizeof(PointT));
   }
 
@@ -75,6 +112,7 @@ public:
     if (cloud == this->target_) return;
     const bool promote = (cloud == this->input_);  // keyframe switch: the last source becomes the target (:245-246)
     Base::setInputTarget(cloud);
+    cache_valid_ = false;
     if (promote) b2r_promote_source_to_target(h_);
     else b2r_set_target(h_, cloud->points.data(), cloud->points.size(), sizeof(PointT));
   }
@@ -94,6 +132,7 @@ protected:
   // pcl::Registration::align() copies the source into `output`, then calls this
   void computeTransformation(PointCloudSource& output, const Matrix4& guess) override {
     b2r_result r;
+    cache_valid_ = false;
     const int rc = b2r_align(h_, guess.data(), &r);  // Eigen::Matrix4f is column-major, like the ABI
     this->converged_ = (rc == B2R_OK) && r.converged;
     this->nr_iterations_ = r.iterations;
@@ -105,6 +144,12 @@ protected:
 
 private:
   b2r_handle* h_ = nullptr;
+  // nearest-neighbour cache of the transformed source (see cachedNearest)
+  bool cache_valid_ = false;
+  size_t cache_cursor_ = 0;
+  PointCloudSource cache_cloud_;
+  std::vector<int32_t> cache_idx_;
+  std::vector<float> cache_d2_;
 };
 
 // The branch added to select_registration_method() (registrations.cpp:27-124), mirroring the USE_VGICP_CUDA pattern

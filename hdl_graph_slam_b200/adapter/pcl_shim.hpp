@@ -82,4 +82,15 @@ protected:
   double transformation_epsilon_ = 0, corr_dist_threshold_ = 0;
   bool converged_ = false, target_cloud_updated_ = true, force_no_recompute_ = false;
 };
+// stand-in for pcl::transformPointCloud (pcl/common/transforms.h); column-major 4x4 like Eigen
+template <typename PointT>
+inline void transformPointCloud(const PointCloud<PointT>& in, PointCloud<PointT>& out, const Eigen::Matrix4f& T) {
+  out.points = in.points;
+  for (auto& p : out.points) {
+    const float x = p.x, y = p.y, z = p.z;
+    p.x = T.m[0] * x + T.m[4] * y + T.m[8] * z + T.m[12];
+    p.y = T.m[1] * x + T.m[5] * y + T.m[9] * z + T.m[13];
+    p.z = T.m[2] * x + T.m[6] * y + T.m[10] * z + T.m[14];
+  }
+}
 }  // namespace pcl
