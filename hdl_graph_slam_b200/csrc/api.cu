@@ -156,8 +156,12 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     h->cfg.grid_cell_min = std::ldexp(1.0f, m > 0.5f ? ex : ex - 1);
   }
   auto bail = [&](int code) { b2r_destroy(h); return code; };
-  if (cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
-  if (cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
+  {  // the align path (latency-critical chain of small kernels) outranks the prefetch path (throughput work for the NEXT frame)
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
+    if (cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
+  }
   if (cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 3; i++) {
     int rc = alloc_cloud(h->clouds[i]);
