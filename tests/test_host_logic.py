@@ -22,3 +22,11 @@ def test_bvh_search_equals_kdtree(harness, mode, n):
     out = subprocess.run([harness, str(n), "4000", str(mode)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout and "limited_mismatch=0" in out.stdout
+
+
+def test_min_eigenvector_solver_matches_jacobi(tmp_path):
+    exe = tmp_path / "eig_harness"
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                           "-o", str(exe), os.path.join(ROOT, "tests", "eig_harness.cu")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
