@@ -275,12 +275,16 @@ def run_b200(args, wl, rank, world, local_rank):
         clocks = sampler.stop() if (rank == 0 and device_arm) else None
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        per_rank = [ms]
         if world > 1:
             dist.barrier()
+            allms = torch.zeros(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allms, t)
+            per_rank = [float(x) for x in allms.cpu()]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         stats = reg.getStats()
         reg.setProfiling(False)
-        results[arm] = dict(ms=float(t.item()), wall_ms=wall * 1e3, stats=stats, iters=iters, conv=conv, kf=kf, clocks=clocks,
+        results[arm] = dict(ms=float(t.item()), per_rank_ms=per_rank, wall_ms=wall * 1e3, stats=stats, iters=iters, conv=conv, kf=kf, clocks=clocks,
                             last_odom=st["odom"])
         odo.close()
         reg.close()
@@ -337,6 +341,8 @@ def run_b200(args, wl, rank, world, local_rank):
         "cpu_baseline": cpu,
         "kernel_ms_in_timed_region": kernel_ms,
         "wall_ms_per_step": rv["wall_ms"] / K,
+        "per_rank_ms_per_step": [round(x / K, 4) for x in rv["per_rank_ms"]],
+        "host_threads_visible": host_threads(),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
