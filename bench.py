@@ -217,7 +217,7 @@ def run_b200(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, args.warmup
     nframes = K + W + 1
-    frames = make_frames(wl["sensor"], rank * 1000, nframes)  # each rank: its own slice of the circuit (replica)
+    frames = make_frames(wl["sensor"], rank * 37, nframes)  # each rank: its own stretch of the closed circuit (replica), own noise seeds
     n, stride_f = frames[0].shape
     stride_bytes = stride_f * 4
     host = torch.empty((nframes, n, stride_f), dtype=torch.float32, pin_memory=True)

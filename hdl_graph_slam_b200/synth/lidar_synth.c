@@ -5,7 +5,7 @@
  *
  * World (closed, every ray returns): ground z=0, outer box |x|,|y| <= 60 m, ceiling z=25 m, 40 axis-aligned boxes and
  * 24 vertical cylinders from scene seed 0x5CE9E, placed clear of the sensor circuit (radius ~40 m).
- * Sensor height 1.8 m.  Range noise N(0, sigma) per ray from a counter-based hash of (seed, ray index), seed =
+ * Sensor height 1.8 m; the sensor follows the closed circuit of b2s_pose() (radius 40 +- 2 m, ~1 m per frame).  Range noise N(0, sigma) per ray from a counter-based hash of (seed, ray index), seed =
  * 0xB2000000 + frame index by convention.  Points are emitted in the SENSOR frame, azimuth-major (index = az*rings+ring),
  * as `stride` floats per point (x,y,z,1 | intensity,0,0,0 for stride 8  == the 32-byte pcl::PointXYZI record).
  */
@@ -98,15 +98,15 @@ static double cast(const double o[3], const double d[3]) {
   return best;
 }
 
-/* trajectory pose of frame k: unit-speed circuit of mean radius 40 m with a bounded heading wobble. */
+/* trajectory pose of frame k: a CLOSED circuit (period 2*pi/0.025 ~ 251.3 frames per lap, ~1 m per frame) that stays inside the
+ * object-free corridor: radius 40 +- 2 m around the origin, heading = path tangent plus a bounded wobble.  Closed form, so any
+ * frame index (and any rank offset) is valid and loop-closure pairs one lap apart really overlap. */
 void b2s_pose(int k, double step, double* x, double* y, double* yaw) {
-  double px = 0.0, py = -40.0, th = 0.0;
-  for (int i = 0; i < k; i++) {
-    px += step * cos(th);
-    py += step * sin(th);
-    th += step * (0.025 + 0.004 * sin((double)i / 50.0));
-  }
-  *x = px; *y = py; *yaw = th;
+  const double th = 0.025 * step * (double)k;
+  const double r = 40.0 + 2.0 * sin(3.0 * th);
+  *x = r * sin(th);
+  *y = -r * cos(th);
+  *yaw = th + 0.05 * sin(5.0 * th);
 }
 
 /* rings: 16 (VLP-16), 32 (HDL-32e), 64 (KITTI HDL-64E shape). returns number of points = rings*n_az. */
