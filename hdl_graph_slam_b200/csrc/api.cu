@@ -159,6 +159,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   {  // the align path (latency-critical chain of small kernels) outranks the prefetch path (throughput work for the NEXT frame)
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (getenv("B2R_NO_PRIORITY")) lo = hi = 0;
     if (cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
     if (cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
   }

@@ -5,6 +5,7 @@
 #include <vector>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include "../../include/b200reg.h"
 #include "common.cuh"
 #include "grid.cuh"
@@ -107,7 +108,8 @@ struct Telemetry {
 // stream every few thousand spins so that a failed launch or a device fault still surfaces as an error
 inline int wait_host_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
   const volatile unsigned long long* f = flag;
-  for (unsigned long spins = 1; spins < 200000; spins++) {  // ~100-200 us of spinning covers a single in-flight kernel
+  static const unsigned long spin_limit = [] { const char* e = getenv("B2R_SPIN_LIMIT"); return e ? strtoul(e, nullptr, 10) : 200000ul; }();
+  for (unsigned long spins = 1; spins < spin_limit; spins++) {  // ~100-200 us of spinning covers a single in-flight kernel
     if (*f == seq) return B2R_OK;
     if ((spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
