@@ -152,22 +152,10 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
   __syncthreads();
   if (is_last) {
     __threadfence();
-    // fixed-order two-level sum: value i is summed by `parts` threads over the blocks b = part, part+parts, ... and the
-    // partial sums are then added in part order — deterministic, and `parts` times shorter than one serial pass
-    constexpr int W = (NV <= 32) ? 32 : 64;
-    __shared__ double s_part[(NV <= 32 ? 32 : 64) * 8];
-    const int parts = min(8, (int)blockDim.x / W);
-    const int i = threadIdx.x % W, part = threadIdx.x / W;
-    if (part < parts && i < NV) {
-      double s = 0.0;
-      const volatile double* P = partials;
-      for (unsigned int b = part; b < gridDim.x; b += parts) s += P[(size_t)b * NV + i];
-      s_part[part * W + i] = s;
-    }
-    __syncthreads();
     if (threadIdx.x < NV) {
       double s = 0.0;
-      for (int q = 0; q < parts; q++) s += s_part[q * W + threadIdx.x];
+      const volatile double* P = partials;
+      for (unsigned int b = 0; b < gridDim.x; b++) s += P[(size_t)b * NV + threadIdx.x];
       out[threadIdx.x] = s;
     }
     if (threadIdx.x == 0) {
