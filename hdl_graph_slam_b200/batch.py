@@ -190,10 +190,11 @@ def bench_loop_batch(args, rank, world, local_rank):
                 candidates[g].append((None, None))
         if g in mine:
             targets[g] = synth.scan("vlp16", frame=tf)
-    lb = LoopBatch({"registration_method": "FAST_GICP"}, device_id=local_rank, streams_per_gpu=4, fitness_score_max_range=2.5)
-    # warm-up: one group
-    g0 = sorted(mine)[0]
-    lb.run_local(targets, candidates, [g0])
+    n_streams = getattr(args, "streams", 4)
+    lb = LoopBatch({"registration_method": "FAST_GICP"}, device_id=local_rank, streams_per_gpu=n_streams, fitness_score_max_range=2.5)
+    # warm-up: one group per handle (first-use allocations of every handle happen outside the timed region)
+    warm = sorted(mine)[:n_streams]
+    lb.run_local(targets, candidates, warm)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -214,7 +215,7 @@ def bench_loop_batch(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: loop-closure candidate batch (GICP, 64k-pt VLP-16 pairs, targets shared by 8 candidates)",
                        "pairs_total": n_pairs, "pairs_per_gpu": per_gpu, "collective": "one NCCL all-gather of 80-byte records",
-                       "streams_per_gpu": 4, "timing": "host clock around the whole batch incl. H2D, max over ranks (host-driven)"},
+                       "streams_per_gpu": n_streams, "timing": "host clock around the whole batch incl. H2D, max over ranks (host-driven)"},
             "converged": conv, "mean_iterations": iters / n_pairs, "loops_found": int(sum(1 for b in best if b >= 0)), "groups": n_groups,
         }), flush=True)
     lb.close()
