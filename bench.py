@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--workload", default="gicp_odometry_vlp16_64k", choices=list(WORKLOADS) + ["loop_batch"])
     ap.add_argument("--cpu-sample", type=int, default=6, help="frames of the same workload timed on the CPU oracle (cpu_baseline)")
     ap.add_argument("--pairs", type=int, default=256, help="loop_batch: candidate pairs per GPU")
-    ap.add_argument("--streams", type=int, default=4, help="loop_batch: registration handles (host threads + CUDA streams) per GPU")
+    ap.add_argument("--streams", type=int, default=16, help="loop_batch: registration handles (host threads + CUDA streams) per GPU")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="strict call-by-call chain: do not announce the next frame (no software pipelining)")
     return ap.parse_args()

@@ -190,7 +190,7 @@ def bench_loop_batch(args, rank, world, local_rank):
                 candidates[g].append((None, None))
         if g in mine:
             targets[g] = synth.scan("vlp16", frame=tf)
-    n_streams = getattr(args, "streams", 4)
+    n_streams = getattr(args, "streams", 16)
     lb = LoopBatch({"registration_method": "FAST_GICP"}, device_id=local_rank, streams_per_gpu=n_streams, fitness_score_max_range=2.5)
     # warm-up: one group per handle (first-use allocations of every handle happen outside the timed region)
     warm = sorted(mine)[:n_streams]
