@@ -79,6 +79,9 @@ SYMBOLS = [
     ("b2r_ndt_get_voxels", C.c_int, [_VP, _SZ, C.POINTER(_SZ), C.POINTER(C.c_int64), _I32P, _F64P, _F64P, _I32P, _I32P]),
     ("b2r_ndt_derivatives_at", C.c_int, [_VP, _F64P, _F64P, _F64P, _F64P, C.POINTER(C.c_uint64)]),
     ("b2r_voxelgrid", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_float, _VP, C.POINTER(_SZ), _I32P, _I32P]),
+    ("b2r_distance_filter", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, C.c_double, _VP, C.POINTER(_SZ)]),
+    ("b2r_radius_outlier_removal", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, C.c_int, _VP, C.POINTER(_SZ)]),
+    ("b2r_statistical_outlier_removal", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_int, C.c_double, _VP, C.POINTER(_SZ)]),
     ("b2r_odometry_create", C.c_int, [_VP, C.POINTER(OdometryParams), C.POINTER(_VP)]),
     ("b2r_odometry_destroy", None, [_VP]),
     ("b2r_odometry_matching", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),

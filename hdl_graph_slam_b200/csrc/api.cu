@@ -22,6 +22,7 @@
 #include "fitness.cuh"
 #include "ndt.cuh"
 #include "voxelgrid.cuh"
+#include "prefilter.cuh"
 
 namespace b2r {
 thread_local std::string g_last_error;
@@ -31,6 +32,7 @@ using namespace b2r;
 struct b2r_handle {
   b2r_config cfg;
   cudaStream_t st = nullptr;
+  Cloud aux;                        // scratch cloud of the prefilter entry points (never a registration input)
   Cloud clouds[3];
   int src = 0, tgt = 1, nxt = 2;   // nxt: cloud being prefetched for the next set_source (software pipelining)
   cudaStream_t st2 = nullptr;       // prefetch stream (upload + BVH + covariances of the next source overlap the current align)
@@ -193,6 +195,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   cudaSetDevice(h->cfg.device_id);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st2) cudaStreamSynchronize(h->st2);
+  h->aux.raw.release(); h->aux.sorted.release(); h->aux.leaf_lo.release(); h->aux.leaf_hi.release(); h->aux.sup_lo.release(); h->aux.sup_hi.release(); h->aux.pos_of.release(); h->aux.cov.release();
   for (int i = 0; i < 3; i++) {
     Cloud& c = h->clouds[i];
     c.raw.release(); c.sorted.release(); c.leaf_lo.release(); c.leaf_hi.release(); c.sup_lo.release(); c.sup_hi.release(); c.pos_of.release(); c.cov.release();
@@ -819,6 +822,125 @@ extern "C" int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t str
   if (!(leaf > 0.f)) return fail(B2R_EINVAL, "leaf must be positive");
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   return voxelgrid_filter(h->vg_work, h->st, in, n, stride_bytes, leaf, out, n_out, out_keys, out_counts);
+}
+
+// ------------------------------------------------------------------------------------------------ prefilter chain (next rows)
+static int upload_aux(b2r_handle* h, const void* in, size_t n, size_t stride_bytes) {
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  Cloud& c = h->aux;
+  c.n = n;
+  c.stride_f = (int)(stride_bytes / 4);
+  c.invalidate();
+  B2R_CUDA(c.raw.reserve(n * c.stride_f + 4));
+  c.raw_view = c.raw.p;
+  if (n) B2R_CUDA(cudaMemcpyAsync(c.raw.p, in, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
+  h->tel.h2d += n * stride_bytes;
+  return B2R_OK;
+}
+
+static size_t compact_records(const void* in, size_t n, size_t stride_bytes, const unsigned char* keep, void* out) {
+  size_t m = 0;
+  const char* src = (const char*)in;
+  char* dst = (char*)out;
+  for (size_t i = 0; i < n; i++)
+    if (keep[i]) { std::memcpy(dst + m * stride_bytes, src + i * stride_bytes, stride_bytes); m++; }
+  return m;
+}
+
+extern "C" int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, void* out,
+                                   size_t* n_out) {
+  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *n_out = 0;
+  if (n == 0) return B2R_OK;
+  int rc = upload_aux(h, in, n, stride_bytes);
+  if (rc) return rc;
+  B2R_CUDA(h->tmp_i.reserve(n / 4 + 4));
+  unsigned char* d_flags = reinterpret_cast<unsigned char*>(h->tmp_i.p);
+  { TEL_BEGIN(&h->tel, h->st);
+    k_distance_flags<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->aux.raw_view, h->aux.stride_f, (int)n, near_thresh, far_thresh, d_flags);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  B2R_CUDA(cudaGetLastError());
+  std::vector<unsigned char> keep(n);
+  B2R_CUDA(cudaMemcpyAsync(keep.data(), d_flags, n, cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  h->tel.d2h += n;
+  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
+  return B2R_OK;
+}
+
+static int knn_stat(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int k, int mode, std::vector<float>& vals) {
+  if (k < 1 || k > 64) return fail(B2R_EINVAL, "neighbour count must be in [1,64]");
+  int rc = upload_aux(h, in, n, stride_bytes);
+  if (rc) return rc;
+  rc = ensure_grid(h, h->aux);
+  if (rc) return rc;
+  B2R_CUDA(h->tmp_f.reserve(n + 1));
+  k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<int*>(h->tmp_f.p), (int)n, 0x7fc00000);  // NaN = dropped (non-finite) point
+  const size_t smem = (size_t)k * kKnnThreads * sizeof(unsigned long long);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    B2R_CUDA(cudaFuncSetAttribute(k_knn_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
+    attr_set = true;
+  }
+  const size_t padded = (size_t)h->aux.nsup * 1024;
+  { TEL_BEGIN(&h->tel, h->st);
+    k_knn_stat<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(h->aux.bvh(), k, mode, h->tmp_f.p);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  B2R_CUDA(cudaGetLastError());
+  vals.resize(n);
+  B2R_CUDA(cudaMemcpyAsync(vals.data(), h->tmp_f.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  h->tel.d2h += n * sizeof(float);
+  return B2R_OK;
+}
+
+extern "C" int b2r_radius_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double radius, int min_neighbors, void* out,
+                                          size_t* n_out) {
+  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *n_out = 0;
+  if (n == 0) return B2R_OK;
+  std::vector<float> kth;
+  int rc = knn_stat(h, in, n, stride_bytes, min_neighbors + 1, 0, kth);
+  if (rc) return rc;
+  std::vector<unsigned char> keep(n);
+  const double r2 = radius * radius;
+  // PCL RadiusOutlierRemoval (dense path): outlier iff the (min_pts+1)-th neighbour is missing or farther than the radius
+  for (size_t i = 0; i < n; i++) keep[i] = (kth[i] == kth[i] && !std::isinf(kth[i]) && !((double)kth[i] > r2)) ? 1 : 0;
+  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
+  return B2R_OK;
+}
+
+extern "C" int b2r_statistical_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, void* out,
+                                               size_t* n_out) {
+  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *n_out = 0;
+  if (n == 0) return B2R_OK;
+  std::vector<float> dist;
+  int rc = knn_stat(h, in, n, stride_bytes, mean_k + 1, 1, dist);
+  if (rc) return rc;
+  // PCL StatisticalOutlierRemoval::applyFilterIndices: double sums over the valid points in index order
+  double sum = 0, sq_sum = 0;
+  size_t valid = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (dist[i] != dist[i]) continue;
+    sum += (double)dist[i];
+    sq_sum += (double)dist[i] * (double)dist[i];
+    valid++;
+  }
+  std::vector<unsigned char> keep(n, 0);
+  if (valid > 0) {
+    const double mean = sum / (double)valid;
+    const double variance = (sq_sum - sum * sum / (double)valid) / ((double)valid - 1.0);
+    const double stddev = std::sqrt(variance);
+    const double thresh = mean + stddev_mul * stddev;
+    for (size_t i = 0; i < n; i++) keep[i] = (dist[i] == dist[i] && !((double)dist[i] > thresh)) ? 1 : 0;
+  }
+  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
+  return B2R_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ odometry mirror

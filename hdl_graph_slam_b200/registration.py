@@ -226,7 +226,23 @@ class Registration:
         check(self._lib.b2r_ndt_derivatives_at(self._h, p.ctypes.data_as(dp), C.byref(score), g.ctypes.data_as(dp), H.ctypes.data_as(dp), C.byref(npairs)))
         return score.value, g, H, npairs.value
 
-    # --- companion
+    # --- companion / prefilter chain
+    def _filter(self, fn, cloud, *args):
+        a, n, s = _cloud(cloud)
+        out = np.zeros_like(a)
+        n_out = C.c_size_t()
+        check(fn(self._h, a.ctypes.data_as(C.c_void_p), n, s, *args, out.ctypes.data_as(C.c_void_p), C.byref(n_out)))
+        return out[: n_out.value]
+
+    def distanceFilter(self, cloud, near, far):
+        return self._filter(self._lib.b2r_distance_filter, cloud, float(near), float(far))
+
+    def radiusOutlierRemoval(self, cloud, radius, min_neighbors):
+        return self._filter(self._lib.b2r_radius_outlier_removal, cloud, float(radius), int(min_neighbors))
+
+    def statisticalOutlierRemoval(self, cloud, mean_k, stddev_mul):
+        return self._filter(self._lib.b2r_statistical_outlier_removal, cloud, int(mean_k), float(stddev_mul))
+
     def voxelGridFilter(self, cloud, leaf, with_keys=False):
         a, n, s = _cloud(cloud)
         out = np.zeros_like(a)

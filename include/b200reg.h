@@ -159,6 +159,14 @@ int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* score, doub
 int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out, size_t* n_out,
                   int32_t* out_keys, int32_t* out_counts);
 
+/* ---- "next" rows: the rest of the prefilter chain.  Records are copied whole; kept points stay in input order.
+ * PrefilteringNodelet::distance_filter (apps/prefiltering_nodelet.cpp:164-180): keep near < ||p|| < far (float32 norm). */
+int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, void* out, size_t* n_out);
+/* pcl::RadiusOutlierRemoval with setRadiusSearch / setMinNeighborsInRadius (apps/prefiltering_nodelet.cpp:83-90,151-162) */
+int b2r_radius_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double radius, int min_neighbors, void* out, size_t* n_out);
+/* pcl::StatisticalOutlierRemoval with setMeanK / setStddevMulThresh (apps/prefiltering_nodelet.cpp:73-81,151-162) */
+int b2r_statistical_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, void* out, size_t* n_out);
+
 /* ---- host mirrors of the two callers (logic identical to the reference; only the handle is ours) ---------------- */
 typedef struct b2r_odometry b2r_odometry;
 typedef struct b2r_odometry_params {

@@ -388,3 +388,54 @@ extern "C" void orc_fitness(const float* tgt, size_t m, size_t tstride, const fl
   if (nn_idx) std::memcpy(nn_idx, idx.data(), n * sizeof(int32_t));
   if (nn_d2) std::memcpy(nn_d2, d2.data(), n * sizeof(float));
 }
+
+// ---- prefilter chain: PrefilteringNodelet::distance_filter and pcl::Radius/StatisticalOutlierRemoval ----
+// /root/reference/apps/prefiltering_nodelet.cpp:164-180 (distance), :72-93,151-162 (outlier removal).  keep[i] in {0,1}.
+extern "C" void orc_distance_filter(const float* pts, size_t n, size_t stride, double near_t, double far_t, unsigned char* keep) {
+  for (size_t i = 0; i < n; i++) {
+    const float* p = pts + i * stride;
+    float sq = p[0] * p[0] + p[1] * p[1];
+    sq = sq + p[2] * p[2];
+    double d = (double)std::sqrt(sq);  // Eigen Vector3f::norm() in float32, promoted for the comparison
+    keep[i] = (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && d > near_t && d < far_t) ? 1 : 0;
+  }
+}
+
+extern "C" void orc_radius_outlier(const float* pts, size_t n, size_t stride, double radius, int min_neighbors, unsigned char* keep, int threads) {
+  KdTree tree;
+  tree.build(pts, n, stride);
+  const int k = min_neighbors + 1;
+  const double r2 = radius * radius;
+#pragma omp parallel for num_threads(nthreads(threads)) schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    std::vector<int> idx(k);
+    std::vector<float> d2(k);
+    int c = tree.knn(pts + (size_t)i * stride, k, idx.data(), d2.data());
+    // PCL (dense path): nearestKSearch(min_pts + 1); outlier if fewer found or the last one is beyond the radius
+    keep[i] = (c == k && !((double)d2[k - 1] > r2)) ? 1 : 0;
+  }
+}
+
+extern "C" void orc_statistical_outlier(const float* pts, size_t n, size_t stride, int mean_k, double stddev_mul, unsigned char* keep,
+                                        float* dist_out, int threads) {
+  KdTree tree;
+  tree.build(pts, n, stride);
+  const int k = mean_k + 1;
+  std::vector<float> dist(n);
+#pragma omp parallel for num_threads(nthreads(threads)) schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    std::vector<int> idx(k);
+    std::vector<float> d2(k);
+    int c = tree.knn(pts + (size_t)i * stride, k, idx.data(), d2.data());
+    double s = 0.0;
+    for (int j = 1; j < c; j++) s += (double)std::sqrt(d2[j]);  // first neighbour is the point itself
+    dist[i] = (float)(s / (double)mean_k);
+  }
+  double sum = 0, sq = 0;
+  for (size_t i = 0; i < n; i++) { sum += (double)dist[i]; sq += (double)dist[i] * (double)dist[i]; }
+  double mean = sum / (double)n;
+  double variance = (sq - sum * sum / (double)n) / ((double)n - 1.0);
+  double thresh = mean + stddev_mul * std::sqrt(variance);
+  for (size_t i = 0; i < n; i++) keep[i] = !((double)dist[i] > thresh) ? 1 : 0;
+  if (dist_out) std::memcpy(dist_out, dist.data(), n * sizeof(float));
+}

@@ -85,6 +85,13 @@ void orc_fitness(const float* tgt, size_t m, size_t tstride, const float* src, s
 int orc_voxelgrid(const float* in, size_t n, size_t stride, float leaf, float* out_xyzi, int32_t* out_keys,
                   int32_t* out_counts, size_t* n_out);
 
+/* prefilter chain ("next" rows): keep flags of PrefilteringNodelet::distance_filter, pcl::RadiusOutlierRemoval,
+ * pcl::StatisticalOutlierRemoval (apps/prefiltering_nodelet.cpp:72-93,151-180). */
+void orc_distance_filter(const float* pts, size_t n, size_t stride, double near_t, double far_t, unsigned char* keep);
+void orc_radius_outlier(const float* pts, size_t n, size_t stride, double radius, int min_neighbors, unsigned char* keep, int threads);
+void orc_statistical_outlier(const float* pts, size_t n, size_t stride, int mean_k, double stddev_mul, unsigned char* keep, float* dist_out,
+                             int threads);
+
 /* ---- NDT (pclomp::NormalDistributionsTransform + VoxelGridCovariance) ---- */
 typedef struct orc_ndt_map orc_ndt_map;
 orc_ndt_map* orc_ndt_build(const float* tgt, size_t m, size_t stride, float resolution);

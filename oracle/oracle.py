@@ -158,6 +158,29 @@ def voxelgrid(cloud, leaf):
     return out[:m], keys[:m], counts[:m], rc
 
 
+def distance_filter(cloud, near, far):
+    a, ap, n, s = _f32(cloud)
+    keep = np.zeros(max(n, 1), np.uint8)
+    lib().orc_distance_filter(ap, C.c_size_t(n), C.c_size_t(s), C.c_double(near), C.c_double(far), keep.ctypes.data_as(C.c_void_p))
+    return keep[:n].astype(bool)
+
+
+def radius_outlier(cloud, radius, min_neighbors, threads=0):
+    a, ap, n, s = _f32(cloud)
+    keep = np.zeros(max(n, 1), np.uint8)
+    lib().orc_radius_outlier(ap, C.c_size_t(n), C.c_size_t(s), C.c_double(radius), int(min_neighbors), keep.ctypes.data_as(C.c_void_p), threads)
+    return keep[:n].astype(bool)
+
+
+def statistical_outlier(cloud, mean_k, stddev_mul, threads=0):
+    a, ap, n, s = _f32(cloud)
+    keep = np.zeros(max(n, 1), np.uint8)
+    dist = np.zeros(max(n, 1), np.float32)
+    lib().orc_statistical_outlier(ap, C.c_size_t(n), C.c_size_t(s), int(mean_k), C.c_double(stddev_mul), keep.ctypes.data_as(C.c_void_p),
+                                  dist.ctypes.data_as(C.c_void_p), threads)
+    return keep[:n].astype(bool), dist[:n]
+
+
 class NdtMap:
     def __init__(self, tgt, resolution):
         ta, tp, m, ts = _f32(tgt)
