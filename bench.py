@@ -198,7 +198,8 @@ def algorithmic_bytes(cls, n, m, stride_bytes):
     """compulsory bytes per launch of each kernel class (N source points, M target points)."""
     return {
         "knn_covariance": n * 16 + n * 48,
-        "gicp_correspond_linearize": 64 * (n + m) + 8 * n + 28 * 8,
+        "gicp_correspondences": 16 * (n + m) + 16 * n,          # src+tgt float4 once, seed read + corr/cpos/d2 writes
+        "gicp_linearize": n * (16 + 4 + 48 + 48 + 16 + 48) + n * (4 + 48 + 16) + 29 * 8,  # point, cpos, C_A, C_B, target, M out; fused trial cost: cpos', M', target'
         "gicp_error": n * (16 + 4 + 48) + m * 16 + 8,
         "bvh_build": n * (stride_bytes + 16 + 4 + 16),
         "nn_fitness": n * 16 + m * 16 + 24,

@@ -64,6 +64,8 @@ struct b2r_handle {
     int* mm = nullptr;
     void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
   } bc[2];
+  bool knn_smem_attr = false, stat_smem_attr = false;
+  int n_sm = 148;
   // last result
   float final_T[16];                // row-major
   bool has_final = false;
@@ -158,6 +160,8 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     h->cfg.grid_cell_min = std::ldexp(1.0f, m > 0.5f ? ex : ex - 1);
   }
   auto bail = [&](int code) { b2r_destroy(h); return code; };
+  cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, cfg->device_id);
+  if (h->n_sm <= 0) h->n_sm = 148;
   {  // the align path (latency-critical chain of small kernels) outranks the prefetch path (throughput work for the NEXT frame)
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -323,14 +327,44 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
   if (c.n > 0) {
     const int k = h->cfg.k_correspondences;
     const size_t smem = (size_t)k * kKnnThreads * sizeof(unsigned long long);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
-      B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
-      attr_set = true;
-    }
+    long long* prof = nullptr;
+#ifdef B2R_KNN_PROFILE
+    static long long* d_prof = nullptr;
+    if (!d_prof) cudaMalloc(&d_prof, (size_t)(1 << 16) * 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, (size_t)c.nsup * kSuper * 8 * sizeof(long long), st);
+    prof = d_prof;
+#endif
     TEL_BEGIN(&h->tel, st);
-    k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, st>>>(c.bvh(), k, c.raw_view, c.stride_f, c.cov.p);
+    if (k == kKnnRegK) {  // the reference's default reg_correspondence_randomness: lists live in registers
+      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, 0, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
+    } else {
+      if (smem > 48 * 1024 && !h->knn_smem_attr) {
+        B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
+        h->knn_smem_attr = true;
+      }
+      k_knn_cov<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, st>>>(c.bvh(), k, c.raw_view, c.stride_f, c.cov.p, prof);
+    }
     TEL_END(&h->tel, KC_KNN_COV, 1, st);
+#ifdef B2R_KNN_PROFILE
+    {
+      cudaStreamSynchronize(st);
+      const size_t nl = (size_t)c.nsup * kSuper;
+      std::vector<long long> hp(nl * 8);
+      std::vector<float4> lo(nl), hi(nl);
+      cudaMemcpy(hp.data(), d_prof, nl * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+      cudaMemcpy(lo.data(), c.leaf_lo.p, nl * sizeof(float4), cudaMemcpyDeviceToHost);
+      cudaMemcpy(hi.data(), c.leaf_hi.p, nl * sizeof(float4), cudaMemcpyDeviceToHost);
+      if (FILE* f = fopen("gpurun_out/knn_prof.bin", "wb")) {
+        fwrite(hp.data(), sizeof(long long), nl * 8, f);
+        fclose(f);
+      }
+      if (FILE* f = fopen("gpurun_out/knn_prof_box.bin", "wb")) {
+        fwrite(lo.data(), sizeof(float4), nl, f);
+        fwrite(hi.data(), sizeof(float4), nl, f);
+        fclose(f);
+      }
+    }
+#endif
     B2R_CUDA(cudaGetLastError());
   }
   c.cov_ready = true;
@@ -479,7 +513,10 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
   make_pose(x0, P);
   const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
   { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_linearize<<<nb, kLinThreads, 0, h->st>>>(A, P);
+    k_gicp_correspond<kNnDup><<<kNnDup ? 2 * nb : nb, kLinThreads, 0, h->st>>>(A, P);
+    TEL_END(&h->tel, KC_GICP_CORR, 1, h->st); }
+  { TEL_BEGIN(&h->tel, h->st);
+    k_gicp_accumulate<<<nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
   h->tel.d2h += kAcc * sizeof(double);
@@ -879,10 +916,9 @@ static int knn_stat(b2r_handle* h, const void* in, size_t n, size_t stride_bytes
   B2R_CUDA(h->tmp_f.reserve(n + 1));
   k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<int*>(h->tmp_f.p), (int)n, 0x7fc00000);  // NaN = dropped (non-finite) point
   const size_t smem = (size_t)k * kKnnThreads * sizeof(unsigned long long);
-  static bool attr_set = false;
-  if (smem > 48 * 1024 && !attr_set) {
+  if (smem > 48 * 1024 && !h->stat_smem_attr) {
     B2R_CUDA(cudaFuncSetAttribute(k_knn_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
-    attr_set = true;
+    h->stat_smem_attr = true;
   }
   const size_t padded = (size_t)h->aux.nsup * 1024;
   { TEL_BEGIN(&h->tel, h->st);

@@ -109,6 +109,15 @@ struct Nn1 {
   }
   B2R_HD float best_d2() const { return bd2; }
   B2R_HD int best_idx() const { return bidx; }
+#ifdef __CUDACC__
+  // DUP mode (lanes l and l^16 share one query, each saw a different half of the candidates): both adopt the better result
+  __device__ __forceinline__ void merge_pair() {
+    const float od = __shfl_xor_sync(0xffffffffu, bd2, 16);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, 16);
+    const int op = __shfl_xor_sync(0xffffffffu, best_pos, 16);
+    if (od < bd2 || (od == bd2 && oi < bidx)) { bd2 = od; bidx = oi; best_pos = op; }
+  }
+#endif
 };
 
 // host/device serial reference of the traversal for ONE query (used by tests/host_harness.cu and as documentation of the
@@ -212,20 +221,37 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
 //              step (lane t owns candidate t), then L's visitor consumes the acceptable ones best-first.
 // Both feed exactly the same (d2, idx) candidates to the same visitors, so the result is identical.
 
-template <class Visitor>
-__device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
+// DUP = true: the warp carries 16 queries, lanes l and l^16 hold the SAME query and identical visitor state between visits; in
+// tile mode each copy scans one half of the leaf and the pair merges afterwards (twice the warps, half the dependent chain per
+// warp: the searches are latency-bound, profiles/r01_c).  Candidates and tie rule are unchanged, so results are identical.
+template <bool DUP = false, class Visitor>
+__device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   unsigned mask = __ballot_sync(FULL, pass);
-  if (mask == 0) return;
+  if (DUP) mask &= 0xffffu;
+  if (mask == 0) return false;  // warp-uniform: nobody wanted the leaf
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
-  if (__popc(mask) >= Visitor::kTileLanes) {
+#ifdef B2R_KNN_PROFILE
+  if constexpr (sizeof(Visitor) > 32) { if (__popc(mask) >= Visitor::kTileLanes) v.n_tile++; else v.n_coop += __popc(mask); }
+#endif
+  if (__popc(mask) >= (DUP ? (Visitor::kTileLanes + 1) / 2 : Visitor::kTileLanes)) {
+    if constexpr (DUP) {
+      const int t0 = (lane >> 4) * (kLeaf / 2);
 #pragma unroll Visitor::kTileUnroll
-    for (int t = 0; t < kLeaf; t++) {
-      const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-      if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+      for (int t = 0; t < kLeaf / 2; t++) {
+        const float4 p = __ldg(lp + t0 + t);  // two addresses per warp
+        if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+      }
+      v.merge_pair();
+    } else {
+#pragma unroll Visitor::kTileUnroll
+      for (int t = 0; t < kLeaf; t++) {
+        const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
+        if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+      }
     }
-    return;
+    return true;
   }
   const float4 mine = __ldg(lp + lane);  // coalesced: candidate `lane`
   const int my_idx = idx_bits(mine.w);
@@ -245,12 +271,13 @@ __device__ __forceinline__ void bvh_visit_leaf(const Bvh& b, int l, float qx, fl
       const int bl = __ffs(__ballot_sync(FULL, ok && du == dmin && iu == imin)) - 1;
       const float bd = __uint_as_float(dmin);
       const int bi = (int)imin;
-      if (lane == L) v.visit(bd, bi, l * kLeaf + bl);
+      if ((DUP ? (lane & 15) : lane) == L) v.visit(bd, bi, l * kLeaf + bl);
       if (lane == bl) ok = false;
       wL = __shfl_sync(FULL, v.worst(), L);
       ok = ok && !(d2 > wL);
     }
   }
+  return true;
 }
 
 // lower bound of dist2_f32(q, p) for every q inside box G and p inside box N (gap per axis, same association): it never
@@ -272,12 +299,12 @@ __device__ __forceinline__ float group_max_worst(bool active, const Visitor& v) 
 }
 
 // exact per-lane test + visit of one leaf
-template <class Visitor>
-__device__ __forceinline__ void bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
+template <bool DUP = false, class Visitor>
+__device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
   const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-  bvh_visit_leaf(b, l, qx, qy, qz, pass, v);
+  return bvh_visit_leaf<DUP>(b, l, qx, qy, qz, pass, v);
 }
 
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
@@ -286,13 +313,15 @@ __device__ __forceinline__ void bvh_try_leaf(const Bvh& b, int l, float qx, floa
 // Node tests are lane-parallel against the GROUP's AABB (lane j tests node j: 32 nodes per step, no dependent-load chain);
 // only the surviving leaves get the exact per-lane test.  Order: own leaf, the leaf nearest to the group's centre, then
 // super-nodes by index.
-template <class Visitor>
+template <bool DUP = false, class Visitor>
 __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf,
                                                  int part = 0, int nparts = 1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const int jh0 = DUP ? (lane >> 4) * (kSuper / 2) : 0;        // DUP: each copy tests half of a super-node's leaves
+  constexpr int jhn = DUP ? kSuper / 2 : kSuper;
   if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
-  if (own_leaf >= 0) bvh_visit_leaf(b, own_leaf, qx, qy, qz, active, v);
+  if (own_leaf >= 0) bvh_visit_leaf<DUP>(b, own_leaf, qx, qy, qz, active, v);
   // group AABB of the active queries
   float glx = active ? qx : INFINITY, gly = active ? qy : INFINITY, glz = active ? qz : INFINITY;
   float ghx = active ? qx : -INFINITY, ghy = active ? qy : -INFINITY, ghz = active ? qz : -INFINITY;
@@ -330,7 +359,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       const int ol = __shfl_xor_sync(FULL, ll, o);
       if (od < ld || (od == ld && ol < ll)) { ld = od; ll = ol; }
     }
-    if (ld < INFINITY) { bvh_try_leaf(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
+    if (ld < INFINITY) { bvh_try_leaf<DUP>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
   const int s0 = own_leaf >= 0 ? own_leaf / kSuper : -1;
   // Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in an unrolled loop (uniform
@@ -344,19 +373,21 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     const float w1 = v.worst(), lim1 = v.limit();
     if (active) {
 #pragma unroll 8
-      for (int j = 0; j < kSuper; j++) {
+      for (int jj = 0; jj < jhn; jj++) {
+        const int j = jh0 + jj;
         const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
         const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
         if (!(lb > w1) && lb < lim1) lm |= 1u << j;
       }
     }
+    if (DUP) lm |= __shfl_xor_sync(FULL, lm, 16);
     unsigned lmask = __reduce_or_sync(FULL, lm) & ~(1u << (own_leaf - l0));
     const int c = own_leaf - l0;
     for (int d = 1; d < kSuper && lmask; d++) {
       const int ja = c - d, jb = c + d;
       if (d % nparts != part) continue;  // work split: ring d of the own super-node belongs to one part
-      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
-      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
+      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<DUP>(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
+      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<DUP>(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
     }
   }
   // pass 2: every other super-node.  Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in
@@ -400,17 +431,19 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       const float w1 = v.worst();
       if (active && ((my >> sj) & 1u)) {
 #pragma unroll 8
-        for (int j = 0; j < kSuper; j++) {
+        for (int jj = 0; jj < jhn; jj++) {
+          const int j = jh0 + jj;
           const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
           const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
           if (!(lb > w1) && lb < lim0) lm |= 1u << j;
         }
       }
+      if (DUP) lm |= __shfl_xor_sync(FULL, lm, 16);
       unsigned lmask = __reduce_or_sync(FULL, lm);
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
-        bvh_try_leaf(b, l0 + lj, qx, qy, qz, active && ((lm >> lj) & 1u), v);
+        bvh_try_leaf<DUP>(b, l0 + lj, qx, qy, qz, active && ((lm >> lj) & 1u), v);
       }
     }
   }

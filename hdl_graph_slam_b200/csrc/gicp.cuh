@@ -4,7 +4,8 @@
 // /root/reference/src/hdl_graph_slam/registrations.cpp:27-36 and runs from apps/scan_matching_odometry_nodelet.cpp:177,210
 // and include/hdl_graph_slam/loop_detector.hpp:136,143:
 //   k_knn_cov          <- FastGICP::calculate_covariances (k exact NN, PLANE regularisation)
-//   k_gicp_linearize   <- FastGICP::update_correspondences + FastGICP::linearize (fused; M_i kept for the trial cost)
+//   k_gicp_correspond  <- FastGICP::update_correspondences (exact seeded 1-NN, float32)
+//   k_gicp_accumulate  <- FastGICP::linearize (float64; M_i kept) fused with FastGICP::compute_error of the previous set (trial cost)
 //   k_gicp_error       <- FastGICP::compute_error
 // All per-cloud arrays live in the BVH's sorted order (Morton key, then original index): a warp = one 32-point leaf, so its
 // queries are spatial neighbours; block partials are combined in a fixed order => bitwise reproducible results.
@@ -28,17 +29,29 @@ struct KnnList {
   unsigned long long* key;
   int k, cnt, stride;
   unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
+#ifdef B2R_KNN_PROFILE
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0;
+#endif
   __device__ __forceinline__ float worst() const { return nn_key_d2(wkey); }
   __device__ __forceinline__ float limit() const { return INFINITY; }
   __device__ __forceinline__ void visit(float d2, int idx, int) {
     const unsigned long long kq = nn_key(d2, idx);
+#ifdef B2R_KNN_PROFILE
+    n_test++;
+#endif
     if (kq >= wkey) return;
+#ifdef B2R_KNN_PROFILE
+    n_ins++;
+#endif
     int j = (cnt < k) ? cnt++ : k - 1;
     while (j > 0) {
       const unsigned long long prev = key[(j - 1) * stride];
       if (prev <= kq) break;
       key[j * stride] = prev;
       j--;
+#ifdef B2R_KNN_PROFILE
+      n_shift++;
+#endif
     }
     key[j * stride] = kq;
     if (cnt == k) wkey = key[(k - 1) * stride];
@@ -79,7 +92,8 @@ __device__ __forceinline__ void knn_cov_store(int kk, PtAt pt_at, double* __rest
 }
 
 // one warp per leaf (4 leaves per block): its 32 points are the queries; per-lane top-k lists in shared memory
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, const float* __restrict__ raw, int stride_f, double* __restrict__ cov) {
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
+                                                            long long* prof) {
   extern __shared__ unsigned long long knn_keys[];  // [k][blockDim]
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int leaf = s >> 5;
@@ -92,13 +106,117 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, const 
   L.cnt = 0;
   L.stride = blockDim.x;
   L.wkey = kKeyInf;
+#ifdef B2R_KNN_PROFILE
+  const long long t0 = clock64();
+#endif
   bvh_group_search(b, q.x, q.y, q.z, active, L, leaf);
+#ifdef B2R_KNN_PROFILE
+  {
+    const long long t1 = clock64();
+    const unsigned F = 0xffffffffu;
+    int v[6] = {L.n_test, L.n_ins, L.n_shift, L.n_ins, L.n_shift, 0};
+    for (int o = 16; o > 0; o >>= 1) {
+      v[0] += __shfl_xor_sync(F, v[0], o); v[1] += __shfl_xor_sync(F, v[1], o); v[2] += __shfl_xor_sync(F, v[2], o);
+      v[3] = max(v[3], __shfl_xor_sync(F, v[3], o)); v[4] = max(v[4], __shfl_xor_sync(F, v[4], o));
+    }
+    const int ntile = __shfl_sync(F, L.n_tile, 0), ncoop = __shfl_sync(F, L.n_coop, 0);
+    if ((threadIdx.x & 31) == 0) {
+      long long* o = prof + (size_t)leaf * 8;
+      o[0] = t1 - t0; o[1] = ntile; o[2] = ncoop; o[3] = v[0]; o[4] = v[1]; o[5] = v[2]; o[6] = v[3]; o[7] = v[4];
+    }
+  }
+#endif
   if (!active) return;
   const int stride = L.stride;
   const unsigned long long* keyp = L.key;
   knn_cov_store(L.cnt, [=](int j) {
     const int idx = (int)(unsigned int)(keyp[j * stride] & 0xffffffffull);
     const float* p = raw + (size_t)idx * stride_f;
+    return make_float3(p[0], p[1], p[2]);
+  }, cov + (size_t)s * 6);
+}
+
+// ---- register-resident lists (K fixed at compile time).  profiles/r01_g: with the lists in shared memory a warp spends ~400
+// cycles per candidate step, the latency of a data-dependent LDS -> compare -> STS chain (max over lanes of the shift count);
+// in registers every slot is recomputed branch-free from the OLD neighbours (new[j] = old[j-1] > q ? old[j-1] : old[j] > q ? q :
+// old[j]), so the K slot updates are independent instructions.  Same candidates, same (d2, idx) order => identical lists.
+template <int K>
+struct KnnRegs {
+  static constexpr int kTileLanes = 3;
+  static constexpr int kTileUnroll = 1;  // the unrolled insertion is ~6K instructions long already
+  unsigned long long key[K];
+#ifdef B2R_KNN_PROFILE
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0;
+#endif
+  __device__ __forceinline__ void reset() {
+#pragma unroll
+    for (int j = 0; j < K; j++) key[j] = kKeyInf;
+  }
+  __device__ __forceinline__ float worst() const { return nn_key_d2(key[K - 1]); }
+  __device__ __forceinline__ float limit() const { return INFINITY; }
+  __device__ __forceinline__ void visit(float d2, int idx, int) {
+    const unsigned long long kq = nn_key(d2, idx);
+#ifdef B2R_KNN_PROFILE
+    n_test++;
+#endif
+    if (kq >= key[K - 1]) return;  // also rejects padding (kq == kKeyInf)
+#ifdef B2R_KNN_PROFILE
+    n_ins++;
+#endif
+#pragma unroll
+    for (int j = K - 1; j > 0; j--) {  // descending: key[j-1] is still the old value when slot j is rewritten
+      const unsigned long long lo = key[j - 1], cur = key[j];
+      key[j] = lo > kq ? lo : (cur > kq ? kq : cur);
+    }
+    if (key[0] > kq) key[0] = kq;
+  }
+  __device__ __forceinline__ int count() const {
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) c += key[j] != kKeyInf;
+    return c;
+  }
+};
+
+constexpr int kKnnRegK = 20;
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
+                                                                long long* prof) {
+  __shared__ int nbr[K][kKnnThreads];  // neighbour indices, ascending (d2, idx), for the covariance pass
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int leaf = s >> 5;
+  if (leaf >= b.nleaf) return;  // whole warps only
+  const float4 q = b.sp[s];
+  const bool active = idx_bits(q.w) != kPadIdx;
+  KnnRegs<K> L;
+  L.reset();
+#ifdef B2R_KNN_PROFILE
+  const long long t0 = clock64();
+#endif
+  bvh_group_search(b, q.x, q.y, q.z, active, L, leaf);
+#ifdef B2R_KNN_PROFILE
+  {
+    const long long t1 = clock64();
+    const unsigned F = 0xffffffffu;
+    int v[4] = {L.n_test, L.n_ins, L.n_ins, 0};
+    for (int o = 16; o > 0; o >>= 1) {
+      v[0] += __shfl_xor_sync(F, v[0], o); v[1] += __shfl_xor_sync(F, v[1], o);
+      v[2] = max(v[2], __shfl_xor_sync(F, v[2], o));
+    }
+    const int ntile = __shfl_sync(F, L.n_tile, 0), ncoop = __shfl_sync(F, L.n_coop, 0);
+    if ((threadIdx.x & 31) == 0) {
+      long long* o = prof + (size_t)leaf * 8;
+      o[0] = t1 - t0; o[1] = ntile; o[2] = ncoop; o[3] = v[0]; o[4] = v[1]; o[5] = 0; o[6] = v[2]; o[7] = 0;
+    }
+  }
+#endif
+  if (!active) return;
+#pragma unroll
+  for (int j = 0; j < K; j++) nbr[j][threadIdx.x] = (int)(unsigned int)(L.key[j] & 0xffffffffull);
+  const int tx = threadIdx.x;
+  knn_cov_store(L.count(), [&](int j) {
+    const float* p = raw + (size_t)nbr[j][tx] * stride_f;
     return make_float3(p[0], p[1], p[2]);
   }, cov + (size_t)s * 6);
 }
@@ -195,12 +313,18 @@ struct LinArgs {
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
 };
 
-__global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
-  __shared__ double red[kAcc * 32];
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc[kAcc];
-#pragma unroll
-  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+// update_correspondences: exact 1-NN of every transformed source point (float32 search, few registers: it shares the SMs with the
+// k-NN covariance kernel of the prefetched next scan).  Writes corr / cpos / d2; no reduction.
+// DUP: a warp carries 16 queries twice (bvh.cuh: lanes l and l^16 share a query) -> twice the warps, half the chain per warp.
+#ifndef B2R_NN_DUP
+#define B2R_NN_DUP 1
+#endif
+constexpr bool kNnDup = B2R_NN_DUP != 0;
+template <bool DUP>
+__global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = DUP ? (gt >> 5) * 16 + (gt & 15) : gt;
+  const bool writer = !DUP || (gt & 16) == 0;
   float4 p = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
   const bool is_point = idx_bits(p.w) != kPadIdx;
@@ -223,6 +347,25 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
       }
     }
   }
+  bvh_group_search<DUP>(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
+  if (is_point && writer) {
+    const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2() < A.thr2);
+    A.corr[idx_bits(p.w)] = valid ? v.best_idx() : -1;
+    A.cpos[s] = valid ? v.best_pos : -1;
+    A.d2[s] = v.best_d2();
+  }
+}
+
+// linearize over the correspondences just written (float64), fused with the trial cost compute_error over the PREVIOUS set.
+__global__ void __launch_bounds__(kLinThreads, 4) k_gicp_accumulate(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
+  __shared__ double red[kAcc * 32];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+  float4 p = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
+  const bool is_point = idx_bits(p.w) != kPadIdx;
   if (A.fuse_error && is_point) {  // FastGICP::compute_error at this pose with the previous correspondences / mahalanobis
     const int tp = A.cpos_prev[s];
     if (tp >= 0) {
@@ -238,15 +381,12 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
       acc[28] = ex * Mex + ey * Mey + ez * Mez;
     }
   }
-  bvh_group_search(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
   if (is_point) {
-    const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2() < A.thr2);
-    A.corr[idx_bits(p.w)] = valid ? v.best_idx() : -1;
-    A.cpos[s] = valid ? v.best_pos : -1;
-    A.d2[s] = v.best_d2();
+    const int best_pos = A.cpos[s];
+    const bool valid = best_pos >= 0;
     if (valid) {
       const double* ca = A.scov + (size_t)s * 6;
-      const double* cb = A.tcov + (size_t)v.best_pos * 6;
+      const double* cb = A.tcov + (size_t)best_pos * 6;
       const double CA[9] = {ca[0], ca[1], ca[2], ca[1], ca[3], ca[4], ca[2], ca[4], ca[5]};
       const double R[9] = {P.T[0], P.T[1], P.T[2], P.T[4], P.T[5], P.T[6], P.T[8], P.T[9], P.T[10]};
       double tmp[9], rcr[9], M[9];
@@ -265,7 +405,7 @@ __global__ void __launch_bounds__(kLinThreads, 4) k_gicp_linearize(const __grid_
       inv3(rcr, M);
       double* mo = A.mahal + (size_t)s * 6;
       mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
-      const float4 tb = A.tgt.sp[v.best_pos];
+      const float4 tb = A.tgt.sp[best_pos];
       const double ax = (double)p.x, ay = (double)p.y, az = (double)p.z;
       const double tx = P.T[0] * ax + P.T[1] * ay + P.T[2] * az + P.T[3];
       const double ty = P.T[4] * ax + P.T[5] * ay + P.T[6] * az + P.T[7];

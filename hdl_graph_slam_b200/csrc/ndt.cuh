@@ -240,7 +240,10 @@ __device__ __forceinline__ float dot3f(const float* a, float x, float y, float z
 
 __constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 
-__global__ void __launch_bounds__(kNdtThreads) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
+#ifndef B2R_NDT_MINBLOCKS
+#define B2R_NDT_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kNdtThreads, B2R_NDT_MINBLOCKS) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
   __shared__ double red[kNdtAcc * 32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kNdtAcc];
