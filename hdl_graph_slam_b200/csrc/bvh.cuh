@@ -95,6 +95,7 @@ constexpr unsigned long long kKeyInf = 0x7f8000007fffffffull;  // (+inf, kPadIdx
 struct Nn1 {
   static constexpr int kTileLanes = 8;   // below 8 interested lanes the cooperative mode (1 step per lane) beats the 32-step tile
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
+  static constexpr bool kTwoPhase = false;
   float bd2;       // +inf = nothing yet
   int bidx;        // kPadIdx = nothing yet
   int best_pos;
@@ -244,6 +245,27 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
         if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
       }
       v.merge_pair();
+    } else if constexpr (Visitor::kTwoPhase) {
+      // list visitors (an accepted candidate costs ~100 instructions for the whole warp): first mark the candidates that can
+      // still beat the lane's current worst (cheap, branch-free), then let every lane walk ITS OWN marks — the number of
+      // insertion rounds is max-over-lanes of the marks, not the number of steps in which any lane accepts.  Per lane the
+      // candidates arrive in the same ascending order and visit() re-tests exactly, so the lists are identical.
+      unsigned m = 0;
+      const float w = v.worst();
+#pragma unroll 8
+      for (int t = 0; t < kLeaf; t++) {
+        const float4 p = __ldg(lp + t);
+        if (dist2_f32(qx, qy, qz, p.x, p.y, p.z) <= w) m |= 1u << t;
+      }
+      if (!pass) m = 0;
+      while (__any_sync(FULL, m != 0)) {
+        if (m) {
+          const int t = __ffs(m) - 1;
+          m &= m - 1;
+          const float4 p = __ldg(lp + t);
+          v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);
+        }
+      }
     } else {
 #pragma unroll Visitor::kTileUnroll
       for (int t = 0; t < kLeaf; t++) {

@@ -26,6 +26,7 @@ constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at 
 struct KnnList {
   static constexpr int kTileLanes = 3;   // coop mode only when 1-2 lanes want the leaf (each pick costs an insertion)
   static constexpr int kTileUnroll = 2;  // the insertion loop is big: keep the instruction footprint small (i-cache)
+  static constexpr bool kTwoPhase = true;
   unsigned long long* key;
   int k, cnt, stride;
   unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
@@ -143,7 +144,8 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov(Bvh b, int k, const 
 template <int K>
 struct KnnRegs {
   static constexpr int kTileLanes = 3;
-  static constexpr int kTileUnroll = 1;  // the unrolled insertion is ~6K instructions long already
+  static constexpr int kTileUnroll = 1;
+  static constexpr bool kTwoPhase = true;
   unsigned long long key[K];
 #ifdef B2R_KNN_PROFILE
   int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0;
@@ -163,12 +165,15 @@ struct KnnRegs {
 #ifdef B2R_KNN_PROFILE
     n_ins++;
 #endif
+    bool pj = true;  // p_j = old key[j] > kq, monotone in j; p_{K-1} holds (tested above)
 #pragma unroll
     for (int j = K - 1; j > 0; j--) {  // descending: key[j-1] is still the old value when slot j is rewritten
-      const unsigned long long lo = key[j - 1], cur = key[j];
-      key[j] = lo > kq ? lo : (cur > kq ? kq : cur);
+      const unsigned long long lo = key[j - 1];
+      const bool pl = lo > kq;
+      if (pj) key[j] = pl ? lo : kq;   // slot j changes only if p_j: takes its left neighbour, or the new key at the boundary
+      pj = pl;
     }
-    if (key[0] > kq) key[0] = kq;
+    if (pj) key[0] = kq;
   }
   __device__ __forceinline__ int count() const {
     int c = 0;
