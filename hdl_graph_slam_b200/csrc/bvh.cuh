@@ -331,13 +331,11 @@ __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, floa
 
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
 //   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
-//   part/nparts   : several warps may share one query group; each takes a disjoint share of the nodes (own leaf: all).
 // Node tests are lane-parallel against the GROUP's AABB (lane j tests node j: 32 nodes per step, no dependent-load chain);
 // only the surviving leaves get the exact per-lane test.  Order: own leaf, the leaf nearest to the group's centre, then
 // super-nodes by index.
 template <bool DUP = false, class Visitor>
-__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf,
-                                                 int part = 0, int nparts = 1) {
+__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int jh0 = DUP ? (lane >> 4) * (kSuper / 2) : 0;        // DUP: each copy tests half of a super-node's leaves
@@ -383,14 +381,19 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (ld < INFINITY) { bvh_try_leaf<DUP>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
-  const int s0 = own_leaf >= 0 ? own_leaf / kSuper : -1;
   // Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in an unrolled loop (uniform
   // addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the warp ORs the 32-bit masks.
   // Masks are conservative snapshots (worst only shrinks); each leaf is re-tested with the current worst when visited.
-  // pass 1: the super-node that holds the already-visited leaf; its leaves in order of index distance from that leaf
-  // (Hilbert order: index neighbours are space neighbours), so the bound is tight before anything else is looked at
-  if (s0 >= 0) {
-    const int l0 = s0 * kSuper;
+  // pass 1: the window of 32 leaves CENTRED on the already-visited leaf, in order of index distance from it (Hilbert order:
+  // index neighbours are space neighbours), so the bound is tight before anything else is looked at.  The window ignores
+  // super-node borders: a leaf that straddles a jump of the curve at the end of its super-node has half of its true
+  // neighbours in the next one (profiles/r01_g: that leaf alone set the kernel time).
+  int win0 = -1;  // first leaf of the pass-1 window
+  if (own_leaf >= 0) {
+    win0 = own_leaf - kSuper / 2;
+    if (win0 > b.nleaf - kSuper) win0 = b.nleaf - kSuper;
+    if (win0 < 0) win0 = 0;
+    const int l0 = win0;
     unsigned lm = 0;
     const float w1 = v.worst(), lim1 = v.limit();
     if (active) {
@@ -407,7 +410,6 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     const int c = own_leaf - l0;
     for (int d = 1; d < kSuper && lmask; d++) {
       const int ja = c - d, jb = c + d;
-      if (d % nparts != part) continue;  // work split: ring d of the own super-node belongs to one part
       if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<DUP>(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
       if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<DUP>(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
     }
@@ -439,12 +441,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (!active) my = 0;
     unsigned smask = __reduce_or_sync(FULL, my);
-    if (s0 >= sbase && s0 < sbase + 32) smask &= ~(1u << (s0 - sbase));
-    if (nparts > 1) {  // work split: super-node s belongs to part s % nparts
-      unsigned keep = 0;
-      for (int j = part - (sbase % nparts); j < 32; j += nparts) if (j >= 0) keep |= 1u << j;
-      smask &= keep;
-    }
+    if (win0 >= 0 && (win0 % kSuper) == 0 && win0 / kSuper >= sbase && win0 / kSuper < sbase + 32) smask &= ~(1u << (win0 / kSuper - sbase));  // window == one whole super-node
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;
@@ -462,6 +459,10 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       }
       if (DUP) lm |= __shfl_xor_sync(FULL, lm, 16);
       unsigned lmask = __reduce_or_sync(FULL, lm);
+      {  // leaves inside the pass-1 window [win0, win0+32) are done (visited, or pruned for good)
+        const int rel = win0 - l0;
+        if (win0 >= 0 && rel > -kSuper && rel < kSuper) lmask &= ~(rel >= 0 ? (0xffffffffu << rel) : (0xffffffffu >> (-rel)));
+      }
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
