@@ -509,6 +509,12 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
   A.partials = h->partials.p; A.out = h->h_out_dev; A.counter = h->d_counter;
   A.flag = h->h_flag_dev; A.seq = ++h->seq;
   A.use_seed = seed ? 1 : 0;
+  A.prof = nullptr;
+#ifdef B2R_KNN_PROFILE
+  static long long* d_cprof = nullptr;
+  if (!d_cprof) cudaMalloc(&d_cprof, (size_t)(1 << 17) * 4 * sizeof(long long));
+  A.prof = d_cprof;
+#endif
   PoseArg P;
   make_pose(x0, P);
   const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
@@ -519,6 +525,18 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
     k_gicp_accumulate<<<nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
+#ifdef B2R_KNN_PROFILE
+  {
+    cudaStreamSynchronize(h->st);
+    const size_t nwarp = (size_t)(kNnDup ? 2 * nb : nb) * kLinThreads / 32;
+    std::vector<long long> hp(nwarp * 4);
+    cudaMemcpy(hp.data(), d_cprof, nwarp * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(seed ? "gpurun_out/corr_prof_seeded.bin" : "gpurun_out/corr_prof_first.bin", "wb")) {
+      fwrite(hp.data(), sizeof(long long), nwarp * 4, f);
+      fclose(f);
+    }
+  }
+#endif
   h->tel.d2h += kAcc * sizeof(double);
   { int wrc = wait_host_flag(h->h_flag, A.seq, h->st); if (wrc) return wrc; }
   // unpack the upper triangle

@@ -96,6 +96,9 @@ struct Nn1 {
   static constexpr int kTileLanes = 8;   // below 8 interested lanes the cooperative mode (1 step per lane) beats the 32-step tile
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   static constexpr bool kTwoPhase = false;
+#ifdef B2R_KNN_PROFILE
+  int n_tile = 0, n_coop = 0;
+#endif
   float bd2;       // +inf = nothing yet
   int bidx;        // kPadIdx = nothing yet
   int best_pos;
@@ -234,7 +237,7 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   if (mask == 0) return false;  // warp-uniform: nobody wanted the leaf
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
 #ifdef B2R_KNN_PROFILE
-  if constexpr (sizeof(Visitor) > 32) { if (__popc(mask) >= Visitor::kTileLanes) v.n_tile++; else v.n_coop += __popc(mask); }
+  if (__popc(mask) >= (DUP ? (Visitor::kTileLanes + 1) / 2 : Visitor::kTileLanes)) v.n_tile++; else v.n_coop += __popc(mask);
 #endif
   if (__popc(mask) >= (DUP ? (Visitor::kTileLanes + 1) / 2 : Visitor::kTileLanes)) {
     if constexpr (DUP) {
@@ -312,14 +315,6 @@ __device__ __forceinline__ float aabb_aabb_bound2(float glx, float gly, float gl
   return fadd(fadd(fmul(bx, bx), fmul(by, by)), fmul(bz, bz));
 }
 
-template <class Visitor>
-__device__ __forceinline__ float group_max_worst(bool active, const Visitor& v) {
-  float w = active ? fminf(v.worst(), v.limit()) : -INFINITY;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) w = fmaxf(w, __shfl_xor_sync(0xffffffffu, w, o));
-  return w;
-}
-
 // exact per-lane test + visit of one leaf
 template <bool DUP = false, class Visitor>
 __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
@@ -329,17 +324,25 @@ __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, floa
   return bvh_visit_leaf<DUP>(b, l, qx, qy, qz, pass, v);
 }
 
+// loosest bound of the group as ordered bits (non-negative floats order like unsigned ints): one REDUX instruction
+template <class Visitor>
+__device__ __forceinline__ float group_max_worst_fast(bool active, const Visitor& v) {
+  const float w = fminf(v.worst(), v.limit());  // >= 0 or +inf
+  return __uint_as_float(__reduce_max_sync(0xffffffffu, active ? __float_as_uint(w) : 0u));
+}
+
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
 //   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
-// Node tests are lane-parallel against the GROUP's AABB (lane j tests node j: 32 nodes per step, no dependent-load chain);
-// only the surviving leaves get the exact per-lane test.  Order: own leaf, the leaf nearest to the group's centre, then
-// super-nodes by index.
+//   own_leaf <  0 : `hint_leaf` >= 0 names a leaf that probably holds the answers (last iteration's correspondent); else the
+//                   leaf nearest to the group's centre is looked up.
+// Node tests are lane-parallel against the GROUP's AABB and loosest bound (lane j tests node j: 32 nodes per step, no
+// dependent-load chain, conservative); the survivors get the exact per-lane test inside bvh_try_leaf at visit time.
+// Order: own/hinted leaf, the 32-leaf window centred on it by index distance, then the remaining super-nodes by index.
 template <bool DUP = false, class Visitor>
-__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf) {
+__device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf,
+                                                 int hint_leaf = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int jh0 = DUP ? (lane >> 4) * (kSuper / 2) : 0;        // DUP: each copy tests half of a super-node's leaves
-  constexpr int jhn = DUP ? kSuper / 2 : kSuper;
   if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
   if (own_leaf >= 0) bvh_visit_leaf<DUP>(b, own_leaf, qx, qy, qz, active, v);
   // group AABB of the active queries
@@ -350,7 +353,11 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     glx = fminf(glx, __shfl_xor_sync(FULL, glx, o)); gly = fminf(gly, __shfl_xor_sync(FULL, gly, o)); glz = fminf(glz, __shfl_xor_sync(FULL, glz, o));
     ghx = fmaxf(ghx, __shfl_xor_sync(FULL, ghx, o)); ghy = fmaxf(ghy, __shfl_xor_sync(FULL, ghy, o)); ghz = fmaxf(ghz, __shfl_xor_sync(FULL, ghz, o));
   }
-  // seed: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
+  if (own_leaf < 0 && hint_leaf >= 0) {
+    bvh_try_leaf<DUP>(b, hint_leaf, qx, qy, qz, active, v);
+    own_leaf = hint_leaf;
+  }
+  // no hint: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
   if (own_leaf < 0) {
     const float gcx = 0.5f * (glx + ghx), gcy = 0.5f * (gly + ghy), gcz = 0.5f * (glz + ghz);
     float bd = INFINITY;
@@ -381,9 +388,6 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     }
     if (ld < INFINITY) { bvh_try_leaf<DUP>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
-  // Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in an unrolled loop (uniform
-  // addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the warp ORs the 32-bit masks.
-  // Masks are conservative snapshots (worst only shrinks); each leaf is re-tested with the current worst when visited.
   // pass 1: the window of 32 leaves CENTRED on the already-visited leaf, in order of index distance from it (Hilbert order:
   // index neighbours are space neighbours), so the bound is tight before anything else is looked at.  The window ignores
   // super-node borders: a leaf that straddles a jump of the curve at the end of its super-node has half of its true
@@ -393,80 +397,46 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     win0 = own_leaf - kSuper / 2;
     if (win0 > b.nleaf - kSuper) win0 = b.nleaf - kSuper;
     if (win0 < 0) win0 = 0;
-    const int l0 = win0;
-    unsigned lm = 0;
-    const float w1 = v.worst(), lim1 = v.limit();
-    if (active) {
-#pragma unroll 8
-      for (int jj = 0; jj < jhn; jj++) {
-        const int j = jh0 + jj;
-        const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
-        const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-        if (!(lb > w1) && lb < lim1) lm |= 1u << j;
-      }
-    }
-    if (DUP) lm |= __shfl_xor_sync(FULL, lm, 16);
-    unsigned lmask = __reduce_or_sync(FULL, lm) & ~(1u << (own_leaf - l0));
-    const int c = own_leaf - l0;
+    const float gw = group_max_worst_fast(active, v);
+    const float4 lo = __ldg(b.leaf_lo + win0 + lane), hi = __ldg(b.leaf_hi + win0 + lane);
+    const float lgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, lo, hi);
+    unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY) & ~(1u << (own_leaf - win0));
+    const int c = own_leaf - win0;
     for (int d = 1; d < kSuper && lmask; d++) {
       const int ja = c - d, jb = c + d;
-      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<DUP>(b, l0 + ja, qx, qy, qz, active && ((lm >> ja) & 1u), v); }
-      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<DUP>(b, l0 + jb, qx, qy, qz, active && ((lm >> jb) & 1u), v); }
+      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<DUP>(b, win0 + ja, qx, qy, qz, active, v); }
+      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<DUP>(b, win0 + jb, qx, qy, qz, active, v); }
     }
   }
-  // pass 2: every other super-node.  Per-lane EXACT node tests, batched: every lane tests 32 nodes against its own query in
-  // an unrolled loop (uniform addresses => broadcast loads, no dependent-load chain, no ballot inside the loop) and the
-  // warp ORs the 32-bit masks.  Masks are conservative snapshots (worst only shrinks); each leaf is re-tested when visited.
+  // pass 2: every super-node, 32 per step, then the leaves of each survivor, 32 per step — all against the group's box and
+  // its CURRENT loosest bound (one REDUX); leaves inside the pass-1 window are done (visited, or pruned for good).
   for (int sbase = 0; sbase < b.nsup; sbase += 32) {
-    // group prefilter (lane j tests super-node sbase+j against the GROUP's AABB and the group's loosest bound): conservative,
-    // one step for 32 nodes; only the survivors get the exact per-lane test below
-    unsigned gmask;
+    unsigned smask;
     {
-      const float gw = group_max_worst(active, v);
+      const float gw = group_max_worst_fast(active, v);
       const int sg = sbase + lane;
       float sgb = INFINITY;
       if (sg < b.nsup) {
         const float4 slo = __ldg(b.sup_lo + sg), shi = __ldg(b.sup_hi + sg);
         sgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, slo, shi);
       }
-      gmask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
+      smask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
     }
-    unsigned my = 0;
-    const float w0 = v.worst(), lim0 = v.limit();
-    for (unsigned gm = gmask; gm; gm &= gm - 1) {
-      const int j = __ffs(gm) - 1;
-      const float4 slo = __ldg(b.sup_lo + sbase + j), shi = __ldg(b.sup_hi + sbase + j);
-      const float sb = aabb_bound2(qx, qy, qz, slo.x, slo.y, slo.z, shi.x, shi.y, shi.z);
-      if (!(sb > w0) && sb < lim0) my |= 1u << j;
-    }
-    if (!active) my = 0;
-    unsigned smask = __reduce_or_sync(FULL, my);
     if (win0 >= 0 && (win0 % kSuper) == 0 && win0 / kSuper >= sbase && win0 / kSuper < sbase + 32) smask &= ~(1u << (win0 / kSuper - sbase));  // window == one whole super-node
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;
       const int l0 = (sbase + sj) * kSuper;
-      unsigned lm = 0;
-      const float w1 = v.worst();
-      if (active && ((my >> sj) & 1u)) {
-#pragma unroll 8
-        for (int jj = 0; jj < jhn; jj++) {
-          const int j = jh0 + jj;
-          const float4 lo = __ldg(b.leaf_lo + l0 + j), hi = __ldg(b.leaf_hi + l0 + j);
-          const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-          if (!(lb > w1) && lb < lim0) lm |= 1u << j;
-        }
-      }
-      if (DUP) lm |= __shfl_xor_sync(FULL, lm, 16);
-      unsigned lmask = __reduce_or_sync(FULL, lm);
-      {  // leaves inside the pass-1 window [win0, win0+32) are done (visited, or pruned for good)
-        const int rel = win0 - l0;
-        if (win0 >= 0 && rel > -kSuper && rel < kSuper) lmask &= ~(rel >= 0 ? (0xffffffffu << rel) : (0xffffffffu >> (-rel)));
-      }
+      const float gw = group_max_worst_fast(active, v);
+      const float4 lo = __ldg(b.leaf_lo + l0 + lane), hi = __ldg(b.leaf_hi + l0 + lane);
+      const float lgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, lo, hi);
+      unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY);
+      const int rel = win0 - l0;
+      if (win0 >= 0 && rel > -kSuper && rel < kSuper) lmask &= ~(rel >= 0 ? (0xffffffffu << rel) : (0xffffffffu >> (-rel)));
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
-        bvh_try_leaf<DUP>(b, l0 + lj, qx, qy, qz, active && ((lm >> lj) & 1u), v);
+        bvh_try_leaf<DUP>(b, l0 + lj, qx, qy, qz, active, v);
       }
     }
   }

@@ -257,7 +257,7 @@ __device__ __forceinline__ void block_reduce(double* v, double* smem /* NV * 32 
   }
 }
 
-// last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in block order.
+// last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in a fixed order.
 // `out` may live in host-mapped pinned memory: the result then lands in host memory straight from the kernel and `flag`
 // (also host-mapped) is set to `seq` afterwards, so the host can spin on it instead of paying a memcpy + stream sync.
 template <int NV>
@@ -275,11 +275,16 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
   __syncthreads();
   if (is_last) {
     __threadfence();
-    if (threadIdx.x < NV) {
+    // fixed-order parallel sum: warp w owns values w, w+nw, ...; lane l adds rows l, l+32, ... (independent L2 loads, ld.cg:
+    // the rows were written by other SMs during this launch), then a fixed xor tree over the lanes.  The order depends only
+    // on the launch geometry => run-to-run bitwise reproducible.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < NV; i += nw) {
       double s = 0.0;
-      const volatile double* P = partials;
-      for (unsigned int b = 0; b < gridDim.x; b++) s += P[(size_t)b * NV + threadIdx.x];
-      out[threadIdx.x] = s;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * NV + i);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) out[i] = s;
     }
     if (threadIdx.x == 0) {
       *counter = 0;
@@ -316,6 +321,7 @@ struct LinArgs {
   unsigned long long* flag;    // host-mapped completion flag (see finish_partials)
   unsigned long long seq;
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
+  long long* prof;             // B2R_KNN_PROFILE builds only
 };
 
 // update_correspondences: exact 1-NN of every transformed source point (float32 search, few registers: it shares the SMs with the
@@ -337,6 +343,7 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
   Nn1 v;
   v.reset(A.lim);
   bool active = false;
+  int sp0 = -1;
   if (is_point) {
     qx = xform_row(P.Tf[0], P.Tf[1], P.Tf[2], P.Tf[3], p.x, p.y, p.z);
     qy = xform_row(P.Tf[4], P.Tf[5], P.Tf[6], P.Tf[7], p.x, p.y, p.z);
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
     if (finite3(qx, qy, qz)) {
       active = true;
       if (A.use_seed) {  // last iteration's correspondent is a real candidate: a tight, exact upper bound
-        int sp0 = A.cpos_prev[s];
+        sp0 = A.cpos_prev[s];
         if (sp0 >= 0) {
           float4 t = A.tgt.sp[sp0];
           v.seed(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w), sp0);
@@ -352,7 +359,22 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
       }
     }
   }
-  bvh_group_search<DUP>(A.tgt, qx, qy, qz, active, v, -1);  // all 32 lanes participate
+  // traversal hint: the leaf of the middle seeded lane's correspondent (Hilbert order: the group's answers sit around it)
+  int hint = -1;
+  {
+    const unsigned hm = __ballot_sync(0xffffffffu, sp0 >= 0);
+    if (hm) hint = __shfl_sync(0xffffffffu, sp0, __fns(hm, 0, (__popc(hm) + 1) / 2)) >> 5;
+  }
+#ifdef B2R_KNN_PROFILE
+  const long long t0 = clock64();
+#endif
+  bvh_group_search<DUP>(A.tgt, qx, qy, qz, active, v, -1, hint);  // all 32 lanes participate
+#ifdef B2R_KNN_PROFILE
+  if (A.prof && (threadIdx.x & 31) == 0) {
+    long long* o = A.prof + (size_t)(gt >> 5) * 4;
+    o[0] = clock64() - t0; o[1] = v.n_tile; o[2] = v.n_coop; o[3] = blockIdx.x;
+  }
+#endif
   if (is_point && writer) {
     const bool valid = active && (v.best_pos >= 0) && ((double)v.best_d2() < A.thr2);
     A.corr[idx_bits(p.w)] = valid ? v.best_idx() : -1;
