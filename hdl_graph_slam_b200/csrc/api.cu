@@ -64,7 +64,7 @@ struct b2r_handle {
     int* mm = nullptr;
     void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
   } bc[2];
-  bool knn_smem_attr = false, stat_smem_attr = false;
+  bool knn_smem_attr = false, stat_smem_attr = false, knn_pad_attr = false;
   int n_sm = 148;
   // last result
   float final_T[16];                // row-major
@@ -336,7 +336,16 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
 #endif
     TEL_BEGIN(&h->tel, st);
     if (k == kKnnRegK) {  // the reference's default reg_correspondence_randomness: lists live in registers
-      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, 0, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
+      // A prefetch (ctx 1) runs beside the align chain of the current frame and has slack: unused dynamic shared memory caps
+      // it at `pf_blocks` blocks per SM so that the chain's kernels always find free registers (profiles/r01_g).
+      static const int pf_blocks = [] { const char* e = getenv("B2R_KNN_PREFETCH_BLOCKS"); return e ? atoi(e) : 4; }();
+      size_t pad = 0;
+      if (ctx == 1 && pf_blocks >= 1 && pf_blocks < 4) pad = (size_t)(227 * 1024) / pf_blocks - 12 * 1024 - 1024;  // static 11 KB + 1 KB reserved per block
+      if (pad > 0 && !h->knn_pad_attr) {
+        B2R_CUDA(cudaFuncSetAttribute(k_knn_cov_reg<kKnnRegK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024));
+        h->knn_pad_attr = true;
+      }
+      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, pad, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
     } else {
       if (smem > 48 * 1024 && !h->knn_smem_attr) {
         B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
@@ -485,7 +494,7 @@ static int ensure_align_ws(b2r_handle* h, size_t n_in) {
     B2R_CUDA(h->mahal[i].reserve(n * 6 + 6));
   }
   B2R_CUDA(h->d2.reserve(n + 1));
-  size_t nb = (n + kLinThreads - 1) / kLinThreads + 1;
+  size_t nb = (n + kAccThreads - 1) / kAccThreads + 1;
   B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));  // linearize partials, then the trial-cost partials
   return B2R_OK;
 }
@@ -519,16 +528,16 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
   make_pose(x0, P);
   const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
   { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_correspond<kNnDup><<<kNnDup ? 2 * nb : nb, kLinThreads, 0, h->st>>>(A, P);
+    k_gicp_correspond<kNnCopies><<<kNnCopies * nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_CORR, 1, h->st); }
   { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_accumulate<<<nb, kLinThreads, 0, h->st>>>(A, P);
+    k_gicp_accumulate<<<(unsigned)((size_t)s.nsup * 1024 / kAccThreads), kAccThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
 #ifdef B2R_KNN_PROFILE
   {
     cudaStreamSynchronize(h->st);
-    const size_t nwarp = (size_t)(kNnDup ? 2 * nb : nb) * kLinThreads / 32;
+    const size_t nwarp = (size_t)kNnCopies * nb * kLinThreads / 32;
     std::vector<long long> hp(nwarp * 4);
     cudaMemcpy(hp.data(), d_cprof, nwarp * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(seed ? "gpurun_out/corr_prof_seeded.bin" : "gpurun_out/corr_prof_first.bin", "wb")) {
@@ -554,7 +563,7 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
   Cloud& t = TGT(h);
   ErrArgs A;
   A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos[h->cur].p; A.mahal = h->mahal[h->cur].p;
-  A.partials = h->partials.p + ((size_t)s.nsup * 1024 / kLinThreads + 1) * kAcc; A.out = h->h_out_dev + 32; A.counter = h->d_counter + 1;
+  A.partials = h->partials.p + ((size_t)s.nsup * 1024 / kAccThreads + 1) * kAcc; A.out = h->h_out_dev + 32; A.counter = h->d_counter + 1;
   A.flag = h->h_flag_dev + 1; A.seq = ++h->seq;
   PoseArg P;
   make_pose(xi, P);

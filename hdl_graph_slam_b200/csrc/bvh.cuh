@@ -97,7 +97,7 @@ struct Nn1 {
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   static constexpr bool kTwoPhase = false;
 #ifdef B2R_KNN_PROFILE
-  int n_tile = 0, n_coop = 0;
+  int n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   float bd2;       // +inf = nothing yet
   int bidx;        // kPadIdx = nothing yet
@@ -114,12 +114,16 @@ struct Nn1 {
   B2R_HD float best_d2() const { return bd2; }
   B2R_HD int best_idx() const { return bidx; }
 #ifdef __CUDACC__
-  // DUP mode (lanes l and l^16 share one query, each saw a different half of the candidates): both adopt the better result
-  __device__ __forceinline__ void merge_pair() {
-    const float od = __shfl_xor_sync(0xffffffffu, bd2, 16);
-    const int oi = __shfl_xor_sync(0xffffffffu, bidx, 16);
-    const int op = __shfl_xor_sync(0xffffffffu, best_pos, 16);
-    if (od < bd2 || (od == bd2 && oi < bidx)) { bd2 = od; bidx = oi; best_pos = op; }
+  // C copies of one query sit in lanes q, q + 32/C, ...; each saw a different 1/C of the candidates: all adopt the best result
+  template <int C>
+  __device__ __forceinline__ void merge_copies() {
+#pragma unroll
+    for (int off = 32 / C; off < 32; off <<= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, bd2, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, off);
+      const int op = __shfl_xor_sync(0xffffffffu, best_pos, off);
+      if (od < bd2 || (od == bd2 && oi < bidx)) { bd2 = od; bidx = oi; best_pos = op; }
+    }
   }
 #endif
 };
@@ -215,6 +219,28 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
 }
 
 // ------------------------------------------------------------------------------------------------ warp-group traversal
+// Group-level masks are cheap but only as good as the group's box: a group that straddles a jump of the Hilbert curve has a box
+// of tens of metres and would send every leaf in range to bvh_try_leaf (profiles/r01_g: one such warp, 900 leaf tests, set the
+// kernel time).  When a group mask keeps more than kRefineAbove nodes, every lane re-tests the survivors against ITS OWN query
+// (uniform loads, no ballot in the loop) and the warp keeps the union.
+constexpr int kRefineAbove = 4;
+template <class Visitor>
+__device__ __forceinline__ unsigned refine_node_mask(unsigned gmask, const float4* __restrict__ nlo, const float4* __restrict__ nhi, float qx, float qy,
+                                                     float qz, bool active, const Visitor& v) {
+  if (__popc(gmask) <= kRefineAbove) return gmask;
+  unsigned mine = 0;
+  const float w = v.worst(), lim = v.limit();
+  if (active) {
+    for (unsigned m = gmask; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      const float4 lo = __ldg(nlo + j), hi = __ldg(nhi + j);
+      const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+      if (!(lb > w) && lb < lim) mine |= 1u << j;
+    }
+  }
+  return __reduce_or_sync(0xffffffffu, mine);
+}
+
 // All 32 lanes call this together.  Lane l holds query (qx,qy,qz) (active) and its own visitor.
 //   own_leaf >= 0 : the queries ARE that leaf of this same structure (k-NN of a cloud against itself): visited first.
 // Order: own leaf, then the super-node nearest to the group's AABB, then all remaining super-nodes by index.
@@ -225,29 +251,32 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
 //              step (lane t owns candidate t), then L's visitor consumes the acceptable ones best-first.
 // Both feed exactly the same (d2, idx) candidates to the same visitors, so the result is identical.
 
-// DUP = true: the warp carries 16 queries, lanes l and l^16 hold the SAME query and identical visitor state between visits; in
-// tile mode each copy scans one half of the leaf and the pair merges afterwards (twice the warps, half the dependent chain per
-// warp: the searches are latency-bound, profiles/r01_c).  Candidates and tie rule are unchanged, so results are identical.
-template <bool DUP = false, class Visitor>
+// C > 1: the warp carries Q = 32/C queries; lanes q, q+Q, q+2Q, ... hold the SAME query and identical visitor state between
+// visits.  In tile mode each copy scans 1/C of the leaf and the copies merge afterwards: C times the warps, 1/C of the chain per
+// warp — the searches are latency-bound and their kernel time is the slowest warp, i.e. the heaviest query (profiles/r01_g).
+// Candidates and tie rule are unchanged, so results are identical.
+template <int C = 1, class Visitor>
 __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool pass, Visitor& v) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   unsigned mask = __ballot_sync(FULL, pass);
-  if (DUP) mask &= 0xffffu;
+  constexpr int Q = 32 / C;                                                        // distinct queries per warp
+  constexpr int kTile = C == 1 ? Visitor::kTileLanes : (Visitor::kTileLanes / C > 1 ? Visitor::kTileLanes / C : 1);
+  if (C > 1) mask &= (Q == 32 ? 0xffffffffu : ((1u << Q) - 1u));
   if (mask == 0) return false;  // warp-uniform: nobody wanted the leaf
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
 #ifdef B2R_KNN_PROFILE
-  if (__popc(mask) >= (DUP ? (Visitor::kTileLanes + 1) / 2 : Visitor::kTileLanes)) v.n_tile++; else v.n_coop += __popc(mask);
+  if (__popc(mask) >= kTile) v.n_tile++; else v.n_coop += __popc(mask);
 #endif
-  if (__popc(mask) >= (DUP ? (Visitor::kTileLanes + 1) / 2 : Visitor::kTileLanes)) {
-    if constexpr (DUP) {
-      const int t0 = (lane >> 4) * (kLeaf / 2);
-#pragma unroll Visitor::kTileUnroll
-      for (int t = 0; t < kLeaf / 2; t++) {
-        const float4 p = __ldg(lp + t0 + t);  // two addresses per warp
+  if (__popc(mask) >= kTile) {
+    if constexpr (C > 1) {
+      const int t0 = (lane / Q) * (kLeaf / C);
+#pragma unroll
+      for (int t = 0; t < kLeaf / C; t++) {
+        const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
         if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
       }
-      v.merge_pair();
+      v.template merge_copies<C>();
     } else if constexpr (Visitor::kTwoPhase) {
       // list visitors (an accepted candidate costs ~100 instructions for the whole warp): first mark the candidates that can
       // still beat the lane's current worst (cheap, branch-free), then let every lane walk ITS OWN marks — the number of
@@ -296,7 +325,7 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
       const int bl = __ffs(__ballot_sync(FULL, ok && du == dmin && iu == imin)) - 1;
       const float bd = __uint_as_float(dmin);
       const int bi = (int)imin;
-      if ((DUP ? (lane & 15) : lane) == L) v.visit(bd, bi, l * kLeaf + bl);
+      if ((lane & (Q - 1)) == L) v.visit(bd, bi, l * kLeaf + bl);
       if (lane == bl) ok = false;
       wL = __shfl_sync(FULL, v.worst(), L);
       ok = ok && !(d2 > wL);
@@ -316,12 +345,15 @@ __device__ __forceinline__ float aabb_aabb_bound2(float glx, float gly, float gl
 }
 
 // exact per-lane test + visit of one leaf
-template <bool DUP = false, class Visitor>
+template <int C = 1, class Visitor>
 __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
+#ifdef B2R_KNN_PROFILE
+  v.n_try++;
+#endif
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
   const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-  return bvh_visit_leaf<DUP>(b, l, qx, qy, qz, pass, v);
+  return bvh_visit_leaf<C>(b, l, qx, qy, qz, pass, v);
 }
 
 // loosest bound of the group as ordered bits (non-negative floats order like unsigned ints): one REDUX instruction
@@ -338,13 +370,13 @@ __device__ __forceinline__ float group_max_worst_fast(bool active, const Visitor
 // Node tests are lane-parallel against the GROUP's AABB and loosest bound (lane j tests node j: 32 nodes per step, no
 // dependent-load chain, conservative); the survivors get the exact per-lane test inside bvh_try_leaf at visit time.
 // Order: own/hinted leaf, the 32-leaf window centred on it by index distance, then the remaining super-nodes by index.
-template <bool DUP = false, class Visitor>
+template <int C = 1, class Visitor>
 __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float qy, float qz, bool active, Visitor& v, int own_leaf,
                                                  int hint_leaf = -1) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
-  if (own_leaf >= 0) bvh_visit_leaf<DUP>(b, own_leaf, qx, qy, qz, active, v);
+  if (own_leaf >= 0) bvh_visit_leaf<C>(b, own_leaf, qx, qy, qz, active, v);
   // group AABB of the active queries
   float glx = active ? qx : INFINITY, gly = active ? qy : INFINITY, glz = active ? qz : INFINITY;
   float ghx = active ? qx : -INFINITY, ghy = active ? qy : -INFINITY, ghz = active ? qz : -INFINITY;
@@ -354,7 +386,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     ghx = fmaxf(ghx, __shfl_xor_sync(FULL, ghx, o)); ghy = fmaxf(ghy, __shfl_xor_sync(FULL, ghy, o)); ghz = fmaxf(ghz, __shfl_xor_sync(FULL, ghz, o));
   }
   if (own_leaf < 0 && hint_leaf >= 0) {
-    bvh_try_leaf<DUP>(b, hint_leaf, qx, qy, qz, active, v);
+    bvh_try_leaf<C>(b, hint_leaf, qx, qy, qz, active, v);
     own_leaf = hint_leaf;
   }
   // no hint: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
@@ -386,7 +418,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       const int ol = __shfl_xor_sync(FULL, ll, o);
       if (od < ld || (od == ld && ol < ll)) { ld = od; ll = ol; }
     }
-    if (ld < INFINITY) { bvh_try_leaf<DUP>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
+    if (ld < INFINITY) { bvh_try_leaf<C>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
   }
   // pass 1: the window of 32 leaves CENTRED on the already-visited leaf, in order of index distance from it (Hilbert order:
   // index neighbours are space neighbours), so the bound is tight before anything else is looked at.  The window ignores
@@ -401,11 +433,12 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     const float4 lo = __ldg(b.leaf_lo + win0 + lane), hi = __ldg(b.leaf_hi + win0 + lane);
     const float lgb = aabb_aabb_bound2(glx, gly, glz, ghx, ghy, ghz, lo, hi);
     unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY) & ~(1u << (own_leaf - win0));
+    lmask = refine_node_mask(lmask, b.leaf_lo + win0, b.leaf_hi + win0, qx, qy, qz, active, v);
     const int c = own_leaf - win0;
     for (int d = 1; d < kSuper && lmask; d++) {
       const int ja = c - d, jb = c + d;
-      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<DUP>(b, win0 + ja, qx, qy, qz, active, v); }
-      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<DUP>(b, win0 + jb, qx, qy, qz, active, v); }
+      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<C>(b, win0 + ja, qx, qy, qz, active, v); }
+      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<C>(b, win0 + jb, qx, qy, qz, active, v); }
     }
   }
   // pass 2: every super-node, 32 per step, then the leaves of each survivor, 32 per step — all against the group's box and
@@ -423,6 +456,7 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       smask = __ballot_sync(FULL, !(sgb > gw) && sgb < INFINITY);
     }
     if (win0 >= 0 && (win0 % kSuper) == 0 && win0 / kSuper >= sbase && win0 / kSuper < sbase + 32) smask &= ~(1u << (win0 / kSuper - sbase));  // window == one whole super-node
+    smask = refine_node_mask(smask, b.sup_lo + sbase, b.sup_hi + sbase, qx, qy, qz, active, v);
     while (smask) {
       const int sj = __ffs(smask) - 1;
       smask &= smask - 1;
@@ -433,10 +467,11 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY);
       const int rel = win0 - l0;
       if (win0 >= 0 && rel > -kSuper && rel < kSuper) lmask &= ~(rel >= 0 ? (0xffffffffu << rel) : (0xffffffffu >> (-rel)));
+      lmask = refine_node_mask(lmask, b.leaf_lo + l0, b.leaf_hi + l0, qx, qy, qz, active, v);
       while (lmask) {
         const int lj = __ffs(lmask) - 1;
         lmask &= lmask - 1;
-        bvh_try_leaf<DUP>(b, l0 + lj, qx, qy, qz, active, v);
+        bvh_try_leaf<C>(b, l0 + lj, qx, qy, qz, active, v);
       }
     }
   }

@@ -18,6 +18,10 @@ namespace b2r {
 
 constexpr int kKnnThreads = 128;
 constexpr int kLinThreads = 128;
+#ifndef B2R_ACC_THREADS
+#define B2R_ACC_THREADS 128
+#endif
+constexpr int kAccThreads = B2R_ACC_THREADS;  // k_gicp_accumulate: ~120 registers per thread, small blocks slot in beside the k-NN kernel
 constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at this pose with the PREVIOUS correspondences)
 
 // ---------------------------------------------------------------- k-NN covariance
@@ -31,7 +35,7 @@ struct KnnList {
   int k, cnt, stride;
   unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
 #ifdef B2R_KNN_PROFILE
-  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0;
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   __device__ __forceinline__ float worst() const { return nn_key_d2(wkey); }
   __device__ __forceinline__ float limit() const { return INFINITY; }
@@ -148,7 +152,7 @@ struct KnnRegs {
   static constexpr bool kTwoPhase = true;
   unsigned long long key[K];
 #ifdef B2R_KNN_PROFILE
-  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0;
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   __device__ __forceinline__ void reset() {
 #pragma unroll
@@ -326,16 +330,17 @@ struct LinArgs {
 
 // update_correspondences: exact 1-NN of every transformed source point (float32 search, few registers: it shares the SMs with the
 // k-NN covariance kernel of the prefetched next scan).  Writes corr / cpos / d2; no reduction.
-// DUP: a warp carries 16 queries twice (bvh.cuh: lanes l and l^16 share a query) -> twice the warps, half the chain per warp.
-#ifndef B2R_NN_DUP
-#define B2R_NN_DUP 1
+// kNnCopies lanes per query (bvh.cuh): a warp carries 32/kNnCopies queries -> that many times the warps, shorter chains per warp.
+#ifndef B2R_NN_COPIES
+#define B2R_NN_COPIES 4
 #endif
-constexpr bool kNnDup = B2R_NN_DUP != 0;
-template <bool DUP>
+constexpr int kNnCopies = B2R_NN_COPIES;
+template <int C>
 __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
+  constexpr int Q = 32 / C;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const int s = DUP ? (gt >> 5) * 16 + (gt & 15) : gt;
-  const bool writer = !DUP || (gt & 16) == 0;
+  const int s = (gt >> 5) * Q + (gt & (Q - 1));
+  const bool writer = (gt & 31) < Q;
   float4 p = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < A.src.nleaf * kLeaf) p = A.src.sp[s];
   const bool is_point = idx_bits(p.w) != kPadIdx;
@@ -368,11 +373,11 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
 #ifdef B2R_KNN_PROFILE
   const long long t0 = clock64();
 #endif
-  bvh_group_search<DUP>(A.tgt, qx, qy, qz, active, v, -1, hint);  // all 32 lanes participate
+  bvh_group_search<C>(A.tgt, qx, qy, qz, active, v, -1, hint);  // all 32 lanes participate
 #ifdef B2R_KNN_PROFILE
   if (A.prof && (threadIdx.x & 31) == 0) {
     long long* o = A.prof + (size_t)(gt >> 5) * 4;
-    o[0] = clock64() - t0; o[1] = v.n_tile; o[2] = v.n_coop; o[3] = blockIdx.x;
+    o[0] = clock64() - t0; o[1] = v.n_tile; o[2] = v.n_coop; o[3] = v.n_try;
   }
 #endif
   if (is_point && writer) {
@@ -384,7 +389,7 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
 }
 
 // linearize over the correspondences just written (float64), fused with the trial cost compute_error over the PREVIOUS set.
-__global__ void __launch_bounds__(kLinThreads, 4) k_gicp_accumulate(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
+__global__ void __launch_bounds__(kAccThreads, 512 / kAccThreads) k_gicp_accumulate(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
   __shared__ double red[kAcc * 32];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kAcc];
