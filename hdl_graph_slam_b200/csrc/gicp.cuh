@@ -19,7 +19,7 @@ namespace b2r {
 constexpr int kKnnThreads = 128;
 constexpr int kLinThreads = 128;
 #ifndef B2R_ACC_THREADS
-#define B2R_ACC_THREADS 128
+#define B2R_ACC_THREADS 256
 #endif
 constexpr int kAccThreads = B2R_ACC_THREADS;  // k_gicp_accumulate: ~120 registers per thread, small blocks slot in beside the k-NN kernel
 constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at this pose with the PREVIOUS correspondences)
@@ -279,16 +279,33 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
   __syncthreads();
   if (is_last) {
     __threadfence();
-    // fixed-order parallel sum: warp w owns values w, w+nw, ...; lane l adds rows l, l+32, ... (independent L2 loads, ld.cg:
-    // the rows were written by other SMs during this launch), then a fixed xor tree over the lanes.  The order depends only
-    // on the launch geometry => run-to-run bitwise reproducible.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int i = warp; i < NV; i += nw) {
-      double s = 0.0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(partials + (size_t)b * NV + i);
+    // fixed-order parallel sum: warp w adds rows w, w+nw, ... (lane = value: one coalesced row per load, 8 loads in flight,
+    // ld.cg: the rows were written by other SMs during this launch), then thread i adds the per-warp sums in warp order.
+    // The order depends only on the launch geometry => run-to-run bitwise reproducible.
+    __shared__ double fin[8 * NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nw = (blockDim.x >> 5) < 8 ? (int)(blockDim.x >> 5) : 8;
+    const unsigned int nrow = gridDim.x;
+    if (warp < nw) {
+      for (int i = lane; i < NV; i += 32) {
+        double s = 0.0;
+        unsigned int r = warp;
+        for (; r + 7 * nw < nrow; r += 8 * nw) {
+          double t[8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) out[i] = s;
+          for (int u = 0; u < 8; u++) t[u] = __ldcg(partials + (size_t)(r + u * nw) * NV + i);
+#pragma unroll
+          for (int u = 0; u < 8; u++) s += t[u];
+        }
+        for (; r < nrow; r += nw) s += __ldcg(partials + (size_t)r * NV + i);
+        fin[warp * NV + i] = s;
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+      double s = 0.0;
+      for (int w = 0; w < nw; w++) s += fin[w * NV + i];
+      out[i] = s;
     }
     if (threadIdx.x == 0) {
       *counter = 0;

@@ -241,7 +241,7 @@ __device__ __forceinline__ float dot3f(const float* a, float x, float y, float z
 __constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 
 #ifndef B2R_NDT_MINBLOCKS
-#define B2R_NDT_MINBLOCKS 2
+#define B2R_NDT_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(kNdtThreads, B2R_NDT_MINBLOCKS) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
   __shared__ double red[kNdtAcc * 32];
