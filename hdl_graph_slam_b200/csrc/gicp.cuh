@@ -302,21 +302,23 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
       }
     }
     __syncthreads();
+    bool wrote = false;
     for (int i = threadIdx.x; i < NV; i += blockDim.x) {
       double s = 0.0;
       for (int w = 0; w < nw; w++) s += fin[w * NV + i];
       out[i] = s;
+      wrote = true;
     }
     if (threadIdx.x == 0) {
       *counter = 0;
-      if (extra) reinterpret_cast<unsigned long long*>(out)[NV] = *reinterpret_cast<const volatile unsigned long long*>(extra);
+      if (extra) { reinterpret_cast<unsigned long long*>(out)[NV] = *reinterpret_cast<const volatile unsigned long long*>(extra); wrote = true; }
     }
-    if (flag) {
-      __threadfence_system();
+    if (flag) {  // release: the threads that wrote result words fence at system scope, the block meets, thread 0 publishes the flag
+      if (wrote) __threadfence_system();
       __syncthreads();
       if (threadIdx.x == 0) {
-        *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
         __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
       }
     }
   }
