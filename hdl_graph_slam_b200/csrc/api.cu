@@ -518,6 +518,8 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
   A.partials = h->partials.p; A.out = h->h_out_dev; A.counter = h->d_counter;
   A.flag = h->h_flag_dev; A.seq = ++h->seq;
   A.use_seed = seed ? 1 : 0;
+  static const bool index_seed = !getenv("B2R_NO_INDEX_SEED");
+  A.tgt_pos_of = index_seed ? t.pos_of.p : nullptr; A.tgt_n = (int)t.n;
   A.prof = nullptr;
 #ifdef B2R_KNN_PROFILE
   static long long* d_cprof = nullptr;
@@ -531,7 +533,14 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
     k_gicp_correspond<kNnCopies><<<kNnCopies * nb, kLinThreads, 0, h->st>>>(A, P);
     TEL_END(&h->tel, KC_GICP_CORR, 1, h->st); }
   { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_accumulate<<<(unsigned)((size_t)s.nsup * 1024 / kAccThreads), kAccThreads, 0, h->st>>>(A, P);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)((size_t)s.nsup * 1024 / kAccThreads)); lc.blockDim = dim3(kAccThreads); lc.dynamicSmemBytes = 0; lc.stream = h->st;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    la[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !getenv("B2R_NO_PDL");
+    lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
+    B2R_CUDA(cudaLaunchKernelEx(&lc, k_gicp_accumulate, A, P));
     TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
 #ifdef B2R_KNN_PROFILE
@@ -547,7 +556,7 @@ static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, 
   }
 #endif
   h->tel.d2h += kAcc * sizeof(double);
-  { int wrc = wait_host_flag(h->h_flag, A.seq, h->st); if (wrc) return wrc; }
+  { int wrc = wait_host_result(h->h_flag, A.seq, h->h_out, kAcc, false, h->st); if (wrc) return wrc; }
   // unpack the upper triangle
   int k = 0;
   for (int r = 0; r < 6; r++)
@@ -573,7 +582,7 @@ static int gicp_error(b2r_handle* h, const double* xi, double* y) {
     TEL_END(&h->tel, KC_GICP_ERR, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
   h->tel.d2h += sizeof(double);
-  { int wrc = wait_host_flag(h->h_flag + 1, A.seq, h->st); if (wrc) return wrc; }
+  { int wrc = wait_host_result(h->h_flag + 1, A.seq, h->h_out + 32, 1, false, h->st); if (wrc) return wrc; }
   *y = h->h_out[32];
   return B2R_OK;
 }

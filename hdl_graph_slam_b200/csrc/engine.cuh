@@ -104,13 +104,24 @@ struct Telemetry {
 #define TEL_BEGIN(tel, st) cudaEvent_t _tel_ev = (tel) ? (tel)->begin(st) : nullptr
 #define TEL_END(tel, cls, n, st) do { if (tel) (tel)->end(_tel_ev, cls, n, st); } while (0)
 
-// spin on a host-mapped flag written by the last block of a reduction kernel (finish_partials); falls back to querying the
-// stream every few thousand spins so that a failed launch or a device fault still surfaces as an error
-inline int wait_host_flag(const unsigned long long* flag, unsigned long long seq, cudaStream_t st) {
+// Wait for the result message of a reduction kernel (finish_partials) in host-mapped memory: `nv` result words at out[0..nv),
+// one more word at out[nv] (the optional `extra`, included only if has_extra), the checksum seq ^ xor(words) at out[nv+1], and
+// `flag` = seq.  The device publishes them without system-scope fences, so the words may land in any order: the message is
+// accepted only when it is self-consistent.  Falls back to querying / synchronising the stream so that a failed launch or a
+// device fault still surfaces as an error (after a synchronise every store has landed).
+inline int wait_host_result(const unsigned long long* flag, unsigned long long seq, const double* out, int nv, bool has_extra, cudaStream_t st) {
   const volatile unsigned long long* f = flag;
+  const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(out);
+  auto consistent = [&]() {
+    if (*f != seq) return false;
+    unsigned long long x = seq;
+    for (int i = 0; i < nv; i++) x ^= w[i];
+    if (has_extra) x ^= w[nv];
+    return x == w[nv + 1];
+  };
   static const unsigned long spin_limit = [] { const char* e = getenv("B2R_SPIN_LIMIT"); return e ? strtoul(e, nullptr, 10) : 200000ul; }();
   for (unsigned long spins = 1; spins < spin_limit; spins++) {  // ~100-200 us of spinning covers a single in-flight kernel
-    if (*f == seq) return B2R_OK;
+    if (consistent()) return B2R_OK;
     if ((spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(st);
       if (e == cudaSuccess) break;
@@ -120,7 +131,7 @@ inline int wait_host_flag(const unsigned long long* flag, unsigned long long seq
   // long wait (other streams' work is ahead of ours on the device): stop burning a core and block
   cudaError_t e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
-  if (*f == seq) return B2R_OK;
+  if (consistent()) return B2R_OK;
   return fail(B2R_ECUDA, "reduction kernel finished without signalling its result");
 }
 

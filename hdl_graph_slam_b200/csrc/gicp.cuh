@@ -262,12 +262,13 @@ __device__ __forceinline__ void block_reduce(double* v, double* smem /* NV * 32 
 }
 
 // last-block-done final reduction: partials [gridDim][NV] -> out[NV], summed in a fixed order.
-// `out` may live in host-mapped pinned memory: the result then lands in host memory straight from the kernel and `flag`
-// (also host-mapped) is set to `seq` afterwards, so the host can spin on it instead of paying a memcpy + stream sync.
+// `out` may live in host-mapped pinned memory: the result then lands in host memory straight from the kernel together with a
+// checksum word (out[NV+1]; out[NV] carries `extra` or is unused) and `flag` = `seq`, so the host can spin on it instead of paying a
+// memcpy + stream sync.
 template <int NV>
 __device__ __forceinline__ void finish_partials(const double* v, double* partials, double* out, unsigned int* counter,
                                                 unsigned long long* flag = nullptr, unsigned long long seq = 0,
-                                                const unsigned long long* extra = nullptr) {
+                                                unsigned long long* extra = nullptr) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -302,22 +303,28 @@ __device__ __forceinline__ void finish_partials(const double* v, double* partial
       }
     }
     __syncthreads();
-    bool wrote = false;
     for (int i = threadIdx.x; i < NV; i += blockDim.x) {
       double s = 0.0;
       for (int w = 0; w < nw; w++) s += fin[w * NV + i];
       out[i] = s;
-      wrote = true;
+      fin[i] = s;  // column i of `fin` is read by this thread only: slot [0][i] is free again and carries the value to thread 0
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
       *counter = 0;
-      if (extra) { reinterpret_cast<unsigned long long*>(out)[NV] = *reinterpret_cast<const volatile unsigned long long*>(extra); wrote = true; }
-    }
-    if (flag) {  // release: the threads that wrote result words fence at system scope, the block meets, thread 0 publishes the flag
-      if (wrote) __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence_system();
+      unsigned long long x = seq;
+      if (extra) {
+        const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(extra);
+        *extra = 0;  // device-side counter accumulated with atomics during this launch: read once, re-armed for the next launch
+        reinterpret_cast<unsigned long long*>(out)[NV] = e;
+        x ^= e;
+      }
+      if (flag) {
+        // Publication without system-scope fences (each costs a PCIe round trip): the host accepts the result words only when
+        // flag == seq AND the checksum word equals seq ^ xor(result words), so the order in which these stores land in host memory
+        // does not matter (wait_host_result re-reads until the message is self-consistent).
+        for (int i = 0; i < NV; i++) x ^= (unsigned long long)__double_as_longlong(fin[i]);
+        reinterpret_cast<unsigned long long*>(out)[NV + 1] = x;
         *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
       }
     }
@@ -344,6 +351,8 @@ struct LinArgs {
   unsigned long long* flag;    // host-mapped completion flag (see finish_partials)
   unsigned long long seq;
   int use_seed;                // 1: cpos[] holds last iteration's correspondences -> seed the search bound
+  const int* tgt_pos_of;       // first iteration of an align (no correspondences yet): the target point with the SAME original index
+  int tgt_n;                   //   is the seed — consecutive scans of a spinning LiDAR share their firing order, so it is a near neighbour
   long long* prof;             // B2R_KNN_PROFILE builds only
 };
 
@@ -374,8 +383,11 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
     qz = xform_row(P.Tf[8], P.Tf[9], P.Tf[10], P.Tf[11], p.x, p.y, p.z);
     if (finite3(qx, qy, qz)) {
       active = true;
-      if (A.use_seed) {  // last iteration's correspondent is a real candidate: a tight, exact upper bound
-        sp0 = A.cpos_prev[s];
+      // a seed is a REAL candidate (its exact distance and index enter the visitor like any other): a tight upper bound from the
+      // last iteration's correspondent, or a heuristic one from the firing order on the first iteration — never a guess about the answer
+      if (A.use_seed) sp0 = A.cpos_prev[s];
+      else if (A.tgt_pos_of) { const int oi = idx_bits(p.w); if (oi < A.tgt_n) sp0 = A.tgt_pos_of[oi]; }
+      {
         if (sp0 >= 0) {
           float4 t = A.tgt.sp[sp0];
           v.seed(dist2_f32(qx, qy, qz, t.x, t.y, t.z), idx_bits(t.w), sp0);
@@ -410,6 +422,9 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
 // linearize over the correspondences just written (float64), fused with the trial cost compute_error over the PREVIOUS set.
 __global__ void __launch_bounds__(kAccThreads, 512 / kAccThreads) k_gicp_accumulate(const __grid_constant__ LinArgs A, const __grid_constant__ PoseArg P) {
   __shared__ double red[kAcc * 32];
+  // launched with programmatic stream serialization right behind k_gicp_correspond: the blocks may be scheduled while the search
+  // kernel drains, and wait here until it has completed and its cpos / corr / d2 writes are visible
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[kAcc];
 #pragma unroll

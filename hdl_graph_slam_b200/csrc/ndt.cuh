@@ -441,6 +441,7 @@ inline int ndt_init_work(NdtWork& W) {
   B2R_CUDA(cudaMalloc(&W.d_counter, 4 * sizeof(unsigned int)));
   B2R_CUDA(cudaMemset(W.d_counter, 0, 4 * sizeof(unsigned int)));
   B2R_CUDA(cudaMalloc(&W.d_pairs, sizeof(unsigned long long)));
+  B2R_CUDA(cudaMemset(W.d_pairs, 0, sizeof(unsigned long long)));
   B2R_CUDA(cudaHostAlloc(&W.h_out, 72 * sizeof(double), cudaHostAllocMapped));
   B2R_CUDA(cudaHostGetDevicePointer((void**)&W.h_out_dev, W.h_out, 0));
   W.h_flag = reinterpret_cast<unsigned long long*>(W.h_out + 64);
@@ -730,18 +731,17 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
       TEL_END(W.tel, KC_NDT_HESS, 1, st); }
     if (W.tel) W.tel->d2h += 36 * sizeof(double);
     B2R_CUDA(cudaGetLastError());
-    int rc = wait_host_flag(W.h_flag, A.seq, st);
+    int rc = wait_host_result(W.h_flag, A.seq, W.h_out, 36, false, st);
     if (rc) return rc;
     std::memcpy(out->H, W.h_out, 36 * sizeof(double));
     return B2R_OK;
   }
-  B2R_CUDA(cudaMemsetAsync(W.d_pairs, 0, sizeof(unsigned long long), st));
-  { TEL_BEGIN(W.tel, st);
+  { TEL_BEGIN(W.tel, st);  // W.d_pairs is zero here: allocated zeroed, and the last block of every pass resets it after reading it
     k_ndt_derivatives<<<nb, kNdtThreads, 0, st>>>(A);
     TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
   if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());
-  int rc = wait_host_flag(W.h_flag, A.seq, st);
+  int rc = wait_host_result(W.h_flag, A.seq, W.h_out, kNdtAcc, true, st);
   if (rc) return rc;
   out->score = W.h_out[0];
   std::memcpy(out->g, W.h_out + 1, 6 * sizeof(double));

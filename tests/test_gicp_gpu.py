@@ -50,6 +50,20 @@ def test_covariances(reg, pair, oracle):
         assert np.max(np.abs(got - np.transpose(got, (0, 2, 1)))) == 0.0
 
 
+@pytest.mark.parametrize("k", [5, 12, 33])
+def test_covariances_other_k(pair, oracle, k):
+    """reg_correspondence_randomness != 20 takes the shared-memory list kernel (k_knn_cov) instead of the register one"""
+    src, _ = pair
+    r = pkg.select_registration_method({"registration_method": "FAST_GICP", "reg_correspondence_randomness": k})
+    try:
+        r.setInputSource(src)
+        got = r.getCovariances(0, src.shape[0])
+        want = oracle.gicp_covariances(src, k)
+        assert np.max(np.abs(got - want)) < 1e-8
+    finally:
+        r.close()
+
+
 def test_linearize_and_error(reg, pair, oracle):
     src, tgt = pair
     reg.setInputTarget(tgt)
