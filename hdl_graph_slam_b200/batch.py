@@ -198,24 +198,34 @@ def bench_loop_batch(args, rank, world, local_rank):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
-    best, records, slot = lb.run(targets, candidates, rank, world, dev)
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # the batch is driven by host threads (one per handle), so a single pass is at the mercy of the host scheduler: time the whole
+    # batch `reps` times (identical inputs, every pass redoes all uploads / builds / aligns / the all-gather) and report the median
+    reps = 3
+    times = []
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        best, records, slot = lb.run(targets, candidates, rank, world, dev)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        times.append(float(tt.item()))
+    t = torch.tensor([sorted(times)[reps // 2]], dtype=torch.float64, device=dev)
     if rank == 0:
         n_pairs = n_groups * group
         conv = sum(int(r["converged"].sum()) for r in records)
         iters = sum(int(r["iterations"].sum()) for r in records)
         print(json.dumps({
-            "metric": "registrations/sec", "value": n_pairs / (t.item() * 1e-3), "unit": "registrations/s", "n_gpus": world, "steps": 1, "warmup": 1,
+            "metric": "registrations/sec", "value": n_pairs / (t.item() * 1e-3), "unit": "registrations/s", "n_gpus": world, "steps": reps, "warmup": 1,
             "ms_per_step": t.item(), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 NN / f64 accumulate",
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[3]: loop-closure candidate batch (GICP, 64k-pt VLP-16 pairs, targets shared by 8 candidates)",
                        "pairs_total": n_pairs, "pairs_per_gpu": per_gpu, "collective": "one NCCL all-gather of 80-byte records",
-                       "streams_per_gpu": n_streams, "timing": "host clock around the whole batch incl. H2D, max over ranks (host-driven)"},
+                       "streams_per_gpu": n_streams, "timing": "host clock around the whole batch incl. H2D, max over ranks (host-driven); median of the passes", "pass_ms": [round(x, 2) for x in times]},
             "converged": conv, "mean_iterations": iters / n_pairs, "loops_found": int(sum(1 for b in best if b >= 0)), "groups": n_groups,
         }), flush=True)
     lb.close()

@@ -395,10 +395,13 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_gicp_correspond(const __grid
       }
     }
   }
-  // traversal hint: the leaf of the middle seeded lane's correspondent (Hilbert order: the group's answers sit around it)
+  // traversal hint: the leaf of the middle seeded lane's correspondent (Hilbert order: the group's answers sit around it).  A
+  // firing-order seed is only trusted as a starting point when it is close (odometry: consecutive scans); for unrelated scan
+  // pairs (loop closure) it is a far point and the centre-nearest leaf lookup is the better start — the bound it gives is kept.
   int hint = -1;
   {
-    const unsigned hm = __ballot_sync(0xffffffffu, sp0 >= 0);
+    const bool good = sp0 >= 0 && (A.use_seed || v.bd2 < 1.0f);
+    const unsigned hm = __ballot_sync(0xffffffffu, good);
     if (hm) hint = __shfl_sync(0xffffffffu, sp0, __fns(hm, 0, (__popc(hm) + 1) / 2)) >> 5;
   }
 #ifdef B2R_KNN_PROFILE
