@@ -13,7 +13,7 @@ tail -3 $O/bench_err.log
 echo "=== ncu launch list"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/launches.csv python bench.py --steps 12 --warmup 3 --cpu-sample 0 --no-profile > $O/ncu_bench.log 2>&1
 python tools/agg_launches.py $O/launches.csv | tee $O/launches.md
-exit 0
+[ -z "$NCU_FULL" ] && exit 0
 echo "=== ncu full"
 ncu --set full --clock-control none --import-source on -k regex:"k_gicp_correspond|k_knn_cov_reg|k_gicp_accumulate" -c 6 -o $O/prof_final python tools/prof_one.py > $O/ncu_full.log 2>&1
 tail -2 $O/ncu_full.log
