@@ -19,6 +19,12 @@
 #pragma once
 #include "common.cuh"
 
+// The warp-level code below is device code; tests/warp_harness.cpp also compiles it for the CPU on an emulated 32-lane warp
+// (tests/warp_emu.hpp supplies the built-ins) with -DB2R_WARP_EMU.
+#if defined(__CUDACC__) || defined(B2R_WARP_EMU)
+#define B2R_WARP_CODE 1
+#endif
+
 namespace b2r {
 
 constexpr int kLeaf = 32;
@@ -113,7 +119,7 @@ struct Nn1 {
   }
   B2R_HD float best_d2() const { return bd2; }
   B2R_HD int best_idx() const { return bidx; }
-#ifdef __CUDACC__
+#ifdef B2R_WARP_CODE
   // C copies of one query sit in lanes q, q + 32/C, ...; each saw a different 1/C of the candidates: all adopt the best result
   template <int C>
   __device__ __forceinline__ void merge_copies() {
@@ -151,7 +157,7 @@ B2R_HD void bvh_search_one(const Bvh& b, float qx, float qy, float qz, Visitor& 
   }
 }
 
-#ifdef __CUDACC__
+#ifdef B2R_WARP_CODE
 // ------------------------------------------------------------------------------------------------ build kernels
 __global__ void k_morton_keys(const float* __restrict__ raw, int stride_f, int n, const int* __restrict__ mm, unsigned int* keys, int* vals) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
