@@ -672,6 +672,11 @@ inline void ndt_svd6_solve(const double* H, const double* rhs, double* x) {
     for (int p = 0; p < 6; p++)
       for (int q = p + 1; q < 6; q++) off += A[p * 6 + q] * A[p * 6 + q];
     if (off == 0.0) break;
+    {  // converged to working precision (same rule as the oracle's 6x6 solve): off-diagonal mass below 1e-34 of the diagonal's
+      double dg = 0.0;
+      for (int p = 0; p < 6; p++) dg += A[p * 6 + p] * A[p * 6 + p];
+      if (off <= 1e-34 * dg) break;
+    }
     for (int p = 0; p < 6; p++)
       for (int q = p + 1; q < 6; q++) {
         double apq = A[p * 6 + q];

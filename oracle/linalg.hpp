@@ -14,8 +14,11 @@ namespace orc {
 
 // ---------------------------------------------------------------- cyclic Jacobi eigen-solver (symmetric, n<=6)
 // A: n*n row-major symmetric.  On return w[i] ascending, V column i = eigenvector i (row-major n*n).
+// stop_converged: also stop once the off-diagonal mass is below 1e-34 of the diagonal's (off-diagonal entries ~1e-17 relative,
+// i.e. below double precision: further sweeps only move rounding noise).  Used by the 6x6 solve, which otherwise spends all 64
+// sweeps waiting for the off-diagonal to underflow to an exact zero; the 3x3 users keep the run-to-exact-zero rule.
 template <int N>
-inline void sym_eigen(const double* A_in, double* w, double* V) {
+inline void sym_eigen(const double* A_in, double* w, double* V, bool stop_converged = false) {
   double A[N * N];
   std::memcpy(A, A_in, sizeof(A));
   for (int i = 0; i < N; i++)
@@ -25,6 +28,11 @@ inline void sym_eigen(const double* A_in, double* w, double* V) {
     for (int p = 0; p < N; p++)
       for (int q = p + 1; q < N; q++) off += A[p * N + q] * A[p * N + q];
     if (off == 0.0) break;
+    if (stop_converged) {
+      double dg = 0.0;
+      for (int p = 0; p < N; p++) dg += A[p * N + p] * A[p * N + p];
+      if (off <= 1e-34 * dg) break;
+    }
     for (int p = 0; p < N; p++) {
       for (int q = p + 1; q < N; q++) {
         double apq = A[p * N + q];
@@ -126,7 +134,7 @@ inline bool ldlt6_solve(const double* A, const double* b, double* x) {
 // (singular values = |eigenvalues|), with Eigen's default rank threshold diagSize*eps*max_sv.
 inline void svd6_solve_sym(const double* H, const double* rhs, double* x) {
   double w[6], V[36];
-  sym_eigen<6>(H, w, V);
+  sym_eigen<6>(H, w, V, true);
   double smax = 0.0;
   for (int i = 0; i < 6; i++) smax = std::max(smax, std::fabs(w[i]));
   double thr = std::max(smax * 6.0 * 2.220446049250313e-16, 2.2250738585072014e-308);
