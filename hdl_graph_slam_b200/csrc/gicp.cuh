@@ -1,14 +1,14 @@
-// gicp.cuh — GICP kernels: k-NN covariances, fused correspondence + linearisation, LM trial cost.
+// gicp.cuh — GICP kernels: k-NN covariances, correspondences, linearisation (+ fused LM trial cost), final trial cost.
 //
 // Re-creates, B200-first, the arithmetic of fast_gicp::FastGICP that the reference selects at
 // /root/reference/src/hdl_graph_slam/registrations.cpp:27-36 and runs from apps/scan_matching_odometry_nodelet.cpp:177,210
 // and include/hdl_graph_slam/loop_detector.hpp:136,143:
-//   k_knn_cov          <- FastGICP::calculate_covariances (k exact NN, PLANE regularisation)
-//   k_gicp_correspond  <- FastGICP::update_correspondences (exact seeded 1-NN, float32)
+//   k_knn_cov_reg<20>  <- FastGICP::calculate_covariances (k = 20 exact NN in registers, PLANE regularisation); k_knn_cov: any k
+//   k_gicp_correspond  <- FastGICP::update_correspondences (exact seeded 1-NN, float32, kNnCopies lanes per query)
 //   k_gicp_accumulate  <- FastGICP::linearize (float64; M_i kept) fused with FastGICP::compute_error of the previous set (trial cost)
 //   k_gicp_error       <- FastGICP::compute_error
-// All per-cloud arrays live in the BVH's sorted order (Morton key, then original index): a warp = one 32-point leaf, so its
-// queries are spatial neighbours; block partials are combined in a fixed order => bitwise reproducible results.
+// All per-cloud arrays live in the BVH's sorted order (Hilbert key, then original index), so consecutive threads hold spatial
+// neighbours; block partials are combined in a fixed order => bitwise reproducible results.
 #pragma once
 #include "common.cuh"
 #include "bvh.cuh"
@@ -21,7 +21,7 @@ constexpr int kLinThreads = 128;
 #ifndef B2R_ACC_THREADS
 #define B2R_ACC_THREADS 256
 #endif
-constexpr int kAccThreads = B2R_ACC_THREADS;  // k_gicp_accumulate: ~120 registers per thread, small blocks slot in beside the k-NN kernel
+constexpr int kAccThreads = B2R_ACC_THREADS;  // k_gicp_accumulate: ~126 registers per thread; 256 rows of partials for the final reduction
 constexpr int kAcc = 29;  // 21 (upper H) + 6 (b) + 1 (cost) + 1 (trial cost at this pose with the PREVIOUS correspondences)
 
 // ---------------------------------------------------------------- k-NN covariance
