@@ -53,3 +53,18 @@ def test_warp_group_traversal_on_emulated_warp(warp_harness, mode, copies):
     out = subprocess.run([warp_harness, "6000", "24", str(mode), str(copies)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
+
+
+@pytest.mark.parametrize("copies", [1, 4])
+def test_warp_group_traversal_on_lidar_scans(warp_harness, synth, tmp_path, copies):
+    """same check on two real synthetic VLP-16 scans (rings, sparse far field) related by the odometry guess of the trajectory"""
+    import numpy as np
+    tgt = synth.scan("vlp16_16k", frame=5, stride=4)
+    src = synth.scan("vlp16_16k", frame=7, stride=4)
+    rel = (np.linalg.inv(synth.pose_matrix(5)) @ synth.pose_matrix(6)).astype(np.float32)  # guess: the previous frame's pose
+    tgt.tofile(tmp_path / "t.f32")
+    src.tofile(tmp_path / "s.f32")
+    out = subprocess.run([warp_harness, str(tgt.shape[0]), "24", "3", str(copies), str(tmp_path / "t.f32"), str(tmp_path / "s.f32")]
+                         + [repr(float(x)) for x in rel[:3, :].reshape(-1)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout

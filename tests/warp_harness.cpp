@@ -3,7 +3,7 @@
 // 32-lane warp (tests/warp_emu.hpp), checked bit-for-bit against the oracle's exact k-NN.  Test infrastructure: built with g++ by
 // tests/test_host_logic.py, never shipped.
 //
-//   warp_harness <n_target> <n_groups> <mode> <copies>
+//   warp_harness <n_points> <n_groups> <mode> <copies> [target.f32 source.f32 pose x12]     (mode 3: two scans from files)
 // 1-NN part mirrors k_gicp_correspond: a warp carries 32/copies consecutive (Hilbert-sorted) points of a SOURCE cloud, transformed
 // by a pose; variants: unseeded, seeded with a real candidate (+ hinted start leaf), range-limited (GICP's 2.5 m), groups that
 // straddle far-apart regions, inactive lanes.  k-NN part mirrors k_knn_cov: a warp = one leaf of the cloud against itself.
@@ -173,17 +173,29 @@ int main(int argc, char** argv) {
   const int mode = argc > 3 ? atoi(argv[3]) : 0;
   const int copies = argc > 4 ? atoi(argv[4]) : 4;
   unsigned long long s = 4242 + mode;
-  std::vector<float> tp = make_points(n, mode, s);
-  // the source cloud: the same surface sampled again (jittered), so that most queries have a neighbour within range
-  std::vector<float> sp((size_t)n * 4);
-  for (int i = 0; i < n; i++) {
-    const double j = mode == 1 ? 0.0 : 0.15;
-    sp[i * 4] = tp[i * 4] + (float)((urand(s) - 0.5) * j); sp[i * 4 + 1] = tp[i * 4 + 1] + (float)((urand(s) - 0.5) * j);
-    sp[i * 4 + 2] = tp[i * 4 + 2] + (float)((urand(s) - 0.5) * j); sp[i * 4 + 3] = 1.f;
+  std::vector<float> tp, sp((size_t)n * 4);
+  float Tf[12];
+  if (mode == 3) {
+    // two real synthetic LiDAR scans (float32 x,y,z,1 records) written by the test: argv[5] target, argv[6] source, argv[7..18] pose rows
+    if (argc < 19) { fprintf(stderr, "mode 3 needs target.f32 source.f32 and 12 pose floats\n"); return 2; }
+    tp.resize((size_t)n * 4);
+    FILE* ft = fopen(argv[5], "rb"); FILE* fs = fopen(argv[6], "rb");
+    if (!ft || !fs || fread(tp.data(), 4, tp.size(), ft) != tp.size() || fread(sp.data(), 4, sp.size(), fs) != sp.size()) { fprintf(stderr, "cannot read the scans\n"); return 2; }
+    fclose(ft); fclose(fs);
+    for (int i = 0; i < 12; i++) Tf[i] = (float)atof(argv[7 + i]);
+  } else {
+    tp = make_points(n, mode, s);
+    // the source cloud: the same surface sampled again (jittered), so that most queries have a neighbour within range
+    for (int i = 0; i < n; i++) {
+      const double j = mode == 1 ? 0.0 : 0.15;
+      sp[i * 4] = tp[i * 4] + (float)((urand(s) - 0.5) * j); sp[i * 4 + 1] = tp[i * 4 + 1] + (float)((urand(s) - 0.5) * j);
+      sp[i * 4 + 2] = tp[i * 4 + 2] + (float)((urand(s) - 0.5) * j); sp[i * 4 + 3] = 1.f;
+    }
+    const float c = std::cos(0.02f), sn = std::sin(0.02f);
+    const float T0[12] = {c, -sn, 0.f, 0.35f, sn, c, 0.f, -0.2f, 0.f, 0.f, 1.f, 0.05f};
+    for (int i = 0; i < 12; i++) Tf[i] = T0[i];
   }
   HostBvh T = build(tp, n), S = build(sp, n);
-  const float c = std::cos(0.02f), sn = std::sin(0.02f);
-  const float Tf[12] = {c, -sn, 0.f, 0.35f, sn, c, 0.f, -0.2f, 0.f, 0.f, 1.f, 0.05f};
   long checked = 0, bad1 = 0;
   switch (copies) {
     case 1: bad1 = all_1nn<1>(T, S, n, Tf, groups, tp, n, &checked); break;
