@@ -267,12 +267,19 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   const int lane = threadIdx.x & 31;
   unsigned mask = __ballot_sync(FULL, pass);
   constexpr int Q = 32 / C;                                                        // distinct queries per warp
+#ifdef B2R_TILE_AT  // offline experiments (tools/warp_cost.cpp)
+  constexpr int kTile = B2R_TILE_AT;
+#else
   constexpr int kTile = C == 1 ? Visitor::kTileLanes : (Visitor::kTileLanes / C > 1 ? Visitor::kTileLanes / C : 1);
+#endif
   if (C > 1) mask &= (Q == 32 ? 0xffffffffu : ((1u << Q) - 1u));
   if (mask == 0) return false;  // warp-uniform: nobody wanted the leaf
   const float4* __restrict__ lp = b.sp + (size_t)l * kLeaf;
 #ifdef B2R_KNN_PROFILE
   if (__popc(mask) >= kTile) v.n_tile++; else v.n_coop += __popc(mask);
+#ifdef B2R_WARP_EMU
+  if (lane == 0) g_visit_hist[__popc(mask)]++;  // offline model only (tools/warp_cost.cpp): how many queries wanted each visited leaf
+#endif
 #endif
   if (__popc(mask) >= kTile) {
     if constexpr (C > 1) {

@@ -13,6 +13,7 @@
 #include "../tests/warp_emu.hpp"
 #define B2R_WARP_EMU 1
 #define B2R_KNN_PROFILE 1
+static long g_visit_hist[33];
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
 #include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 
@@ -116,6 +117,9 @@ static void run_1nn(const HostBvh& T, const HostBvh& S, const float* Tf, int mod
     rows.push_back({w, coll, tile, coop, tries, 0, cost});
   }
   report(rows, mode ? "1-NN seeded" : "1-NN unseeded");
+  printf("  visited leaves by number of interested queries:");
+  for (int i = 1; i <= Q; i++) printf(" %d:%ld", i, g_visit_hist[i]);
+  printf("\n");
 }
 
 static void run_knn(const HostBvh& H, int stride_warps) {
