@@ -64,7 +64,7 @@ struct b2r_handle {
     int* mm = nullptr;
     void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
   } bc[2];
-  bool knn_smem_attr = false, stat_smem_attr = false, knn_pad_attr = false;
+  bool knn_smem_attr = false, stat_smem_attr = false;
   int n_sm = 148;
   // last result
   float final_T[16];                // row-major
@@ -336,16 +336,7 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
 #endif
     TEL_BEGIN(&h->tel, st);
     if (k == kKnnRegK) {  // the reference's default reg_correspondence_randomness: lists live in registers
-      // A prefetch (ctx 1) runs beside the align chain of the current frame and has slack: unused dynamic shared memory caps
-      // it at `pf_blocks` blocks per SM so that the chain's kernels always find free registers (profiles/r01_g).
-      static const int pf_blocks = [] { const char* e = getenv("B2R_KNN_PREFETCH_BLOCKS"); return e ? atoi(e) : 4; }();
-      size_t pad = 0;
-      if (ctx == 1 && pf_blocks >= 1 && pf_blocks < 4) pad = (size_t)(227 * 1024) / pf_blocks - 12 * 1024 - 1024;  // static 11 KB + 1 KB reserved per block
-      if (pad > 0 && !h->knn_pad_attr) {
-        B2R_CUDA(cudaFuncSetAttribute(k_knn_cov_reg<kKnnRegK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024));
-        h->knn_pad_attr = true;
-      }
-      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, pad, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
+      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, 0, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
     } else {
       if (smem > 48 * 1024 && !h->knn_smem_attr) {
         B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
