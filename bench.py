@@ -130,6 +130,15 @@ def best_thread_count(orc, frames, method, params):
     return best
 
 
+def single_thread_figure(orc, frames, method, params):
+    """the CPU figure on ONE thread as well (one registration of the same sequence); None if it cannot be taken"""
+    try:
+        tt = oracle_odometry(orc, frames[:2], method, params, 1)[1:]
+        return len(tt) / sum(tt)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def make_frames(sensor, first, count, stride=8):
     from hdl_graph_slam_b200 import synth
     return [synth.scan(sensor, frame=first + k, stride=stride) for k in range(count)]
@@ -187,6 +196,7 @@ def run_reference(args, wl, rank):
         "dtype": "f32 NN / f64 accumulate", "data": "synthetic",
         "config": {"workload": f"BASELINE configs[{wl['config_index']}]: {args.workload}", "points_per_scan": int(frames[0].shape[0])},
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
+                         "value_1thread": single_thread_figure(orc, frames[args.warmup:], wl["method"], wl["params"]),
                          "sample": f"{len(times)} consecutive frames of the same sequence (of --steps {args.steps}); oracle = from-scratch restatement of fast_gicp/ndt_omp (upstream binaries cannot be built here)"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -355,6 +365,7 @@ def run_b200(args, wl, rank, world, local_rank):
         cores = best_thread_count(orc, sample, wl["method"], wl["params"])
         tt = oracle_odometry(orc, sample, wl["method"], wl["params"], cores)[1:]
         cpu = {"value": len(tt) / sum(tt), "unit": "registrations/s", "cores": cores, "host_threads_available": host_threads(), "kind": "port",
+               "value_1thread": single_thread_figure(orc, sample, wl["method"], wl["params"]),
                "sample": f"{len(tt)} consecutive frames of the timed sequence on the host cores (OpenMP oracle restating fast_gicp/ndt_omp; the upstream "
                          f"binaries cannot be built here)"}
     line = {
