@@ -116,6 +116,17 @@ static void run_1nn(const HostBvh& T, const HostBvh& S, const float* Tf, int mod
     const double cost = 6400.0 + 3200.0 * (2.0 / C + 0.35) / 1.35 * tile + 440.0 * coop + 380.0 * tries;
     rows.push_back({w, coll, tile, coop, tries, 0, cost});
   }
+  if (const char* dump = getenv("WARP_COST_DUMP")) {  // per-warp model cost + extent of the warp's source leaf, for scheduling studies
+    if (FILE* f = fopen(dump, "w")) {
+      for (auto& r : rows) {
+        const int leaf = (r.warp * Q) / kLeaf;
+        const float4 lo = S.llo[leaf], hi = S.lhi[leaf];
+        const double diag = std::sqrt((double)(hi.x - lo.x) * (hi.x - lo.x) + (double)(hi.y - lo.y) * (hi.y - lo.y) + (double)(hi.z - lo.z) * (hi.z - lo.z));
+        fprintf(f, "%d %.1f %d %.4f\n", r.warp, r.cost, leaf, diag);
+      }
+      fclose(f);
+    }
+  }
   report(rows, mode ? "1-NN seeded" : "1-NN unseeded");
   printf("  visited leaves by number of interested queries:");
   for (int i = 1; i <= Q; i++) printf(" %d:%ld", i, g_visit_hist[i]);
