@@ -365,7 +365,11 @@ __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, floa
 #endif
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
+#ifdef B2R_LEAF_OBB  // offline experiment (tools/warp_cost.cpp): a second-stage bound from an oriented box per leaf, supplied by the tool
+  const bool pass = active && !(lb > v.worst()) && (lb < v.limit()) && b2r_leaf_obb_pass(l, qx, qy, qz, v.worst(), v.limit());
+#else
   const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+#endif
   return bvh_visit_leaf<C>(b, l, qx, qy, qz, pass, v);
 }
 

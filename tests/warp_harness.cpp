@@ -14,6 +14,11 @@
 #include <cmath>
 #include "warp_emu.hpp"
 #define B2R_WARP_EMU 1
+#ifdef B2R_LEAF_OBB  // offline experiment, see tests/leaf_obb.hpp
+#define LEAF_OBB_PART 1
+#include "leaf_obb.hpp"
+#undef LEAF_OBB_PART
+#endif
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
 #include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 #include "../oracle/oracle.h"
@@ -21,6 +26,11 @@
 using namespace b2r;
 
 #include "host_bvh.hpp"
+#ifdef B2R_LEAF_OBB
+#define LEAF_OBB_PART 2
+#include "leaf_obb.hpp"
+#undef LEAF_OBB_PART
+#endif
 
 // list visitor with the interface of the engine's KnnList / KnnRegs (sorted packed (d2, idx) keys, two-phase tile visits)
 struct EmuKnn {
@@ -196,6 +206,10 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 12; i++) Tf[i] = T0[i];
   }
   HostBvh T = build(tp, n), S = build(sp, n);
+#ifdef B2R_LEAF_OBB
+  static std::vector<LeafObb> obbT = make_obbs(T);
+  g_obb = &obbT;  // 1-NN searches and the 20-NN self search both run against T
+#endif
   long checked = 0, bad1 = 0;
   switch (copies) {
     case 1: bad1 = all_1nn<1>(T, S, n, Tf, groups, tp, n, &checked); break;

@@ -14,12 +14,22 @@
 #define B2R_WARP_EMU 1
 #define B2R_KNN_PROFILE 1
 static long g_visit_hist[33];
+#ifdef B2R_LEAF_OBB
+#define LEAF_OBB_PART 1
+#include "../tests/leaf_obb.hpp"
+#undef LEAF_OBB_PART
+#endif
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
 #include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 
 using namespace b2r;
 
 #include "../tests/host_bvh.hpp"
+#ifdef B2R_LEAF_OBB
+#define LEAF_OBB_PART 2
+#include "../tests/leaf_obb.hpp"
+#undef LEAF_OBB_PART
+#endif
 
 struct EmuKnn {
   static constexpr int kTileLanes = 3;
@@ -72,6 +82,10 @@ static void run_1nn(const HostBvh& T, const HostBvh& S, const float* Tf, int mod
   constexpr int Q = 32 / C;
   const int nwarps = (S.b.nleaf * kLeaf) / Q;
   std::vector<Row> rows;
+  struct Ex { float nnmax, gdiag, range; };
+  std::vector<Ex> extra;
+  static float nn_d[32], gq[32][3], g_nnmax, g_gdiag, g_range;
+  static bool gact[32];
   // steady-state seeds: the exact answer of a slightly different pose (like the previous LM iteration)
   float Tp[12];
   for (int i = 0; i < 12; i++) Tp[i] = Tf[i];
@@ -110,8 +124,18 @@ static void run_1nn(const HostBvh& T, const HostBvh& S, const float* Tf, int mod
       if (hm) hint = __shfl_sync(0xffffffffu, sp0, (int)__fns(hm, 0, (__popc(hm) + 1) / 2)) >> 5;
       bvh_group_search<C>(T.b, qx, qy, qz, act, v, -1, hint);
       if (l == 0) { tile = v.n_tile; coop = v.n_coop; tries = v.n_try; coll = (long)wemu::g()->ncoll[0]; }
+      nn_d[l] = act ? std::sqrt(v.bd2) : 0.f;
+      gq[l][0] = qx; gq[l][1] = qy; gq[l][2] = qz; gact[l] = act;
     });
     (void)wp;
+    {
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      g_nnmax = 0.f;
+      for (int l = 0; l < Q; l++) if (gact[l]) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], gq[l][a]); hi[a] = std::max(hi[a], gq[l][a]); } if (std::isfinite(nn_d[l])) g_nnmax = std::max(g_nnmax, nn_d[l]); }
+      g_gdiag = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+      g_range = std::sqrt(gq[0][0] * gq[0][0] + gq[0][1] * gq[0][1]);
+      extra.push_back({g_nnmax, g_gdiag, g_range});
+    }
     // cycles ~ fit of profiles/r01_g (seeded, 2 lanes per query), tile cost scaled by the lanes per query
     const double cost = 6400.0 + 3200.0 * (2.0 / C + 0.35) / 1.35 * tile + 440.0 * coop + 380.0 * tries;
     rows.push_back({w, coll, tile, coop, tries, 0, cost});
@@ -122,7 +146,8 @@ static void run_1nn(const HostBvh& T, const HostBvh& S, const float* Tf, int mod
         const int leaf = (r.warp * Q) / kLeaf;
         const float4 lo = S.llo[leaf], hi = S.lhi[leaf];
         const double diag = std::sqrt((double)(hi.x - lo.x) * (hi.x - lo.x) + (double)(hi.y - lo.y) * (hi.y - lo.y) + (double)(hi.z - lo.z) * (hi.z - lo.z));
-        fprintf(f, "%d %.1f %d %.4f\n", r.warp, r.cost, leaf, diag);
+        const Ex& e = extra[&r - &rows[0]];
+        fprintf(f, "%d %.1f %d %.4f %.3f %.3f %.2f %d %d\n", r.warp, r.cost, leaf, diag, e.nnmax, e.gdiag, e.range, r.tile, r.tries);
       }
       fclose(f);
     }
@@ -164,6 +189,10 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 12; i++) if (!f || fscanf(f, "%f", &Tf[i]) != 1) { fprintf(stderr, "bad pose file\n"); return 2; }
   fclose(f);
   HostBvh T = build(tp, n), S = build(sp, n);
+#ifdef B2R_LEAF_OBB
+  static std::vector<LeafObb> obbT = make_obbs(T), obbS = make_obbs(S);
+  g_obb = (mode == 2) ? &obbS : &obbT;
+#endif
   if (mode == 2) { run_knn(S, stride); return 0; }
   switch (copies) {
     case 1: run_1nn<1>(T, S, Tf, mode, stride); break;
@@ -172,5 +201,8 @@ int main(int argc, char** argv) {
     case 8: run_1nn<8>(T, S, Tf, mode, stride); break;
     default: return 2;
   }
+#ifdef B2R_LEAF_OBB
+  printf("  oriented-box second stage: %ld tests, %ld leaves rejected (%.1f %%)\n", g_obb_tests, g_obb_rejects, g_obb_tests ? 100.0 * g_obb_rejects / g_obb_tests : 0.0);
+#endif
   return 0;
 }
