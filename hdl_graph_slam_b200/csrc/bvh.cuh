@@ -24,6 +24,9 @@
 #if defined(__CUDACC__) || defined(B2R_WARP_EMU)
 #define B2R_WARP_CODE 1
 #endif
+#ifdef B2R_LEAF_OBB
+#include "leaf_obb.cuh"
+#endif
 
 namespace b2r {
 
@@ -38,6 +41,9 @@ struct Bvh {
   const float4* sup_lo;   // [nsup]
   const float4* sup_hi;
   int nleaf, nsup, n;
+#ifdef B2R_LEAF_OBB
+  const float4* leaf_obb;  // [4*nleaf] oriented boxes (leaf_obb.cuh) or nullptr — experimental builds only
+#endif
 };
 
 // 30-bit 3-D Hilbert index of 10-bit cell coordinates (Skilling's transpose algorithm).  A Hilbert curve has no long jumps,
@@ -103,7 +109,7 @@ struct Nn1 {
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   static constexpr bool kTwoPhase = false;
 #ifdef B2R_KNN_PROFILE
-  int n_tile = 0, n_coop = 0, n_try = 0;
+  int n_tile = 0, n_coop = 0, n_try = 0, n_obb = 0;
 #endif
   float bd2;       // +inf = nothing yet
   int bidx;        // kPadIdx = nothing yet
@@ -365,8 +371,16 @@ __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, floa
 #endif
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-#ifdef B2R_LEAF_OBB  // offline experiment (tools/warp_cost.cpp): a second-stage bound from an oriented box per leaf, supplied by the tool
-  const bool pass = active && !(lb > v.worst()) && (lb < v.limit()) && b2r_leaf_obb_pass(l, qx, qy, qz, v.worst(), v.limit());
+#ifdef B2R_LEAF_OBB  // experimental second-stage bound (leaf_obb.cuh), not compiled into the product
+  bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+  if (b.leaf_obb != nullptr && __any_sync(0xffffffffu, pass)) {
+    const float4* r = b.leaf_obb + 4 * (size_t)l;
+    const float lb2 = leaf_obb_bound2(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), qx, qy, qz);
+#ifdef B2R_KNN_PROFILE
+    if ((threadIdx.x & 31) == 0) v.n_obb++;
+#endif
+    pass = pass && !(lb2 > v.worst()) && (lb2 < v.limit());
+  }
 #else
   const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
 #endif

@@ -160,6 +160,9 @@ struct Cloud {
     Bvh b;
     b.sp = sorted.p; b.leaf_lo = leaf_lo.p; b.leaf_hi = leaf_hi.p; b.sup_lo = sup_lo.p; b.sup_hi = sup_hi.p;
     b.nsup = nsup; b.nleaf = nsup * kSuper; b.n = (int)n;
+#ifdef B2R_LEAF_OBB
+    b.leaf_obb = nullptr;  // experimental builds: no oriented boxes until k_bvh_leaves produces them
+#endif
     return b;
   }
 };

@@ -14,11 +14,6 @@
 #include <cmath>
 #include "warp_emu.hpp"
 #define B2R_WARP_EMU 1
-#ifdef B2R_LEAF_OBB  // offline experiment, see tests/leaf_obb.hpp
-#define LEAF_OBB_PART 1
-#include "leaf_obb.hpp"
-#undef LEAF_OBB_PART
-#endif
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
 #include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 #include "../oracle/oracle.h"
@@ -26,12 +21,6 @@
 using namespace b2r;
 
 #include "host_bvh.hpp"
-#ifdef B2R_LEAF_OBB
-#define LEAF_OBB_PART 2
-#include "leaf_obb.hpp"
-#undef LEAF_OBB_PART
-#endif
-
 // list visitor with the interface of the engine's KnnList / KnnRegs (sorted packed (d2, idx) keys, two-phase tile visits)
 struct EmuKnn {
   static constexpr int kTileLanes = 3;
@@ -206,9 +195,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 12; i++) Tf[i] = T0[i];
   }
   HostBvh T = build(tp, n), S = build(sp, n);
-#ifdef B2R_LEAF_OBB
-  static std::vector<LeafObb> obbT = make_obbs(T);
-  g_obb = &obbT;  // 1-NN searches and the 20-NN self search both run against T
+#ifdef B2R_LEAF_OBB  // experimental oriented leaf boxes (csrc/leaf_obb.cuh): 1-NN and the 20-NN self search both run against T
+  static std::vector<float4> obbT = build_leaf_obbs(T);
+  T.b.leaf_obb = obbT.data();
+  {  // every point of a leaf lies inside its widened box
+    long outside = 0;
+    for (int l = 0; l < T.b.nleaf; l++)
+      for (int t = 0; t < kLeaf; t++) {
+        const float4 p = T.sp[(size_t)l * kLeaf + t];
+        if (idx_bits(p.w) == kPadIdx) continue;
+        if (leaf_obb_bound2(obbT[4 * l], obbT[4 * l + 1], obbT[4 * l + 2], obbT[4 * l + 3], p.x, p.y, p.z) != 0.f) outside++;
+      }
+    printf("oriented boxes: %d leaves, points outside their own box: %ld\n", T.b.nleaf, outside);
+    if (outside) return 1;
+  }
 #endif
   long checked = 0, bad1 = 0;
   switch (copies) {

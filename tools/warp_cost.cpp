@@ -14,22 +14,12 @@
 #define B2R_WARP_EMU 1
 #define B2R_KNN_PROFILE 1
 static long g_visit_hist[33];
-#ifdef B2R_LEAF_OBB
-#define LEAF_OBB_PART 1
-#include "../tests/leaf_obb.hpp"
-#undef LEAF_OBB_PART
-#endif
 #include "../hdl_graph_slam_b200/csrc/common.cuh"
 #include "../hdl_graph_slam_b200/csrc/bvh.cuh"
 
 using namespace b2r;
 
 #include "../tests/host_bvh.hpp"
-#ifdef B2R_LEAF_OBB
-#define LEAF_OBB_PART 2
-#include "../tests/leaf_obb.hpp"
-#undef LEAF_OBB_PART
-#endif
 
 struct EmuKnn {
   static constexpr int kTileLanes = 3;
@@ -37,7 +27,7 @@ struct EmuKnn {
   static constexpr bool kTwoPhase = true;
   static constexpr int K = 20;
   unsigned long long key[K];
-  int n_tile = 0, n_coop = 0, n_try = 0, n_ins = 0;
+  int n_tile = 0, n_coop = 0, n_try = 0, n_ins = 0, n_obb = 0;
   void reset() { for (int j = 0; j < K; j++) key[j] = kKeyInf; }
   float worst() const { return nn_key_d2(key[K - 1]); }
   float limit() const { return INFINITY; }
@@ -190,8 +180,8 @@ int main(int argc, char** argv) {
   fclose(f);
   HostBvh T = build(tp, n), S = build(sp, n);
 #ifdef B2R_LEAF_OBB
-  static std::vector<LeafObb> obbT = make_obbs(T), obbS = make_obbs(S);
-  g_obb = (mode == 2) ? &obbS : &obbT;
+  static std::vector<float4> obbT = build_leaf_obbs(T), obbS = build_leaf_obbs(S);
+  T.b.leaf_obb = obbT.data(); S.b.leaf_obb = obbS.data();
 #endif
   if (mode == 2) { run_knn(S, stride); return 0; }
   switch (copies) {
@@ -201,8 +191,5 @@ int main(int argc, char** argv) {
     case 8: run_1nn<8>(T, S, Tf, mode, stride); break;
     default: return 2;
   }
-#ifdef B2R_LEAF_OBB
-  printf("  oriented-box second stage: %ld tests, %ld leaves rejected (%.1f %%)\n", g_obb_tests, g_obb_rejects, g_obb_tests ? 100.0 * g_obb_rejects / g_obb_tests : 0.0);
-#endif
   return 0;
 }
