@@ -230,6 +230,17 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
   }
 }
 
+#if defined(B2R_LEAF_OBB) && defined(__CUDACC__)
+// experimental: oriented box of every leaf (one warp per leaf), launched behind k_bvh_leaves
+__global__ void __launch_bounds__(256) k_leaf_obbs(const float4* __restrict__ sorted, int nleaf, float4* obb) {
+  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (leaf >= nleaf) return;  // whole warps only
+  const float4 p = sorted[(size_t)leaf * kLeaf + (threadIdx.x & 31)];
+  const bool valid = idx_bits(p.w) != kPadIdx;
+  leaf_obb_build_warp(valid ? p.x : 0.f, valid ? p.y : 0.f, valid ? p.z : 0.f, valid, obb + 4 * (size_t)leaf);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------ warp-group traversal
 // Group-level masks are cheap but only as good as the group's box: a group that straddles a jump of the Hilbert curve has a box
 // of tens of metres and would send every leaf in range to bvh_try_leaf (profiles/r01_g: one such warp, 900 leaf tests, set the
