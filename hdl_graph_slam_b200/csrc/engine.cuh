@@ -109,16 +109,20 @@ struct Telemetry {
 // `flag` = seq.  The device publishes them without system-scope fences, so the words may land in any order: the message is
 // accepted only when it is self-consistent.  Falls back to querying / synchronising the stream so that a failed launch or a
 // device fault still surfaces as an error (after a synchronise every store has landed).
+// the acceptance test of a result message: flag == seq and checksum word == seq ^ xor(result words [^ extra word])
+inline bool result_message_consistent(const volatile unsigned long long* flag, unsigned long long seq, const volatile unsigned long long* w, int nv,
+                                      bool has_extra) {
+  if (*flag != seq) return false;
+  unsigned long long x = seq;
+  for (int i = 0; i < nv; i++) x ^= w[i];
+  if (has_extra) x ^= w[nv];
+  return x == w[nv + 1];
+}
+
 inline int wait_host_result(const unsigned long long* flag, unsigned long long seq, const double* out, int nv, bool has_extra, cudaStream_t st) {
   const volatile unsigned long long* f = flag;
   const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(out);
-  auto consistent = [&]() {
-    if (*f != seq) return false;
-    unsigned long long x = seq;
-    for (int i = 0; i < nv; i++) x ^= w[i];
-    if (has_extra) x ^= w[nv];
-    return x == w[nv + 1];
-  };
+  auto consistent = [&]() { return result_message_consistent(f, seq, w, nv, has_extra); };
   static const unsigned long spin_limit = [] { const char* e = getenv("B2R_SPIN_LIMIT"); return e ? strtoul(e, nullptr, 10) : 200000ul; }();
   for (unsigned long spins = 1; spins < spin_limit; spins++) {  // ~100-200 us of spinning covers a single in-flight kernel
     if (consistent()) return B2R_OK;

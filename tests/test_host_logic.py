@@ -82,3 +82,14 @@ def test_experimental_leaf_obb_keeps_results_exact(oracle):
         out = subprocess.run([exe, "6000", "16", str(mode), "4"], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
         assert "points outside their own box: 0" in out.stdout and "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
+
+
+def test_result_message_protocol(tmp_path):
+    """the fence-free result publication (engine.cuh): a message is accepted iff flag, checksum and all words are of the same launch,
+    for every order in which the stores can land"""
+    exe = tmp_path / "msg_harness"
+    subprocess.check_call(["nvcc", "-O1", "-std=c++17", "-w", "-Wno-deprecated-gpu-targets", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                           "-o", str(exe), os.path.join(ROOT, "tests", "msg_harness.cu")])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "accepted_partial=0" in out.stdout and "rejected_complete=0" in out.stdout
