@@ -30,3 +30,22 @@ def test_whole_step_algorithmic_throughput():
     assert per_step == want / 200 and unknown == ["misc"]
     assert abs(gbs - want / 92.6e-3 / 1e9) < 1e-9
     assert b.whole_step_algorithmic_gbs(calls, n, n, 32, 0.0, 200) is None
+
+
+def test_reference_arm_line_has_the_contract_keys(oracle, synth):
+    """`bench.py --impl reference` (the CPU oracle replaying the same workload) prints ONE JSON line with the driver's keys"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "gicp_odometry_vlp16_64k"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "registrations/sec" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
