@@ -55,6 +55,14 @@ def test_warp_group_traversal_on_emulated_warp(warp_harness, mode, copies):
     assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
 
 
+@pytest.mark.parametrize("n", [1, 5, 33, 1024, 1025, 2049])
+def test_warp_group_traversal_edge_sizes(warp_harness, n):
+    """clouds of 1 point, less than a leaf, one leaf + 1, exactly one super-node, one super-node + 1, two + 1 — on the lattice (ties)"""
+    out = subprocess.run([warp_harness, str(n), "8", "1", "4"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
+
+
 @pytest.mark.parametrize("copies", [1, 4])
 def test_warp_group_traversal_on_lidar_scans(warp_harness, synth, tmp_path, copies):
     """same check on two real synthetic VLP-16 scans (rings, sparse far field) related by the odometry guess of the trajectory"""
