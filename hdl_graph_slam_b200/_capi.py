@@ -24,6 +24,10 @@ class Result(C.Structure):
     _fields_ = [("T", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32), ("iterations", C.c_int32)]
 
 
+class Pair(C.Structure):
+    _fields_ = [("source", C.c_int32), ("target", C.c_int32), ("guess", C.c_float * 16)]
+
+
 class OdometryParams(C.Structure):
     _fields_ = [
         ("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double),
@@ -88,6 +92,21 @@ SYMBOLS = [
     ("b2r_odometry_matching_device", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),
     ("b2r_loop_matching", C.c_int, [_VP, _VP, _SZ, _SZ, C.POINTER(_VP), C.POINTER(_SZ), _SZ, _F32P, C.c_double, C.c_double,
                                     C.POINTER(Result), _I32P]),
+    ("b2r_batch_create", C.c_int, [C.POINTER(Config), C.POINTER(_VP)]),
+    ("b2r_batch_destroy", None, [_VP]),
+    ("b2r_batch_get_engine", C.c_int, [_VP, C.POINTER(_VP)]),
+    ("b2r_batch_add_cloud", C.c_int, [_VP, _VP, _SZ, _SZ, _I32P]),
+    ("b2r_batch_add_cloud_device", C.c_int, [_VP, _VP, _SZ, _SZ, _I32P]),
+    ("b2r_batch_remove_cloud", C.c_int, [_VP, C.c_int32]),
+    ("b2r_batch_cloud_count", C.c_int, [_VP]),
+    ("b2r_batch_synchronize", C.c_int, [_VP]),
+    ("b2r_batch_align", C.c_int, [_VP, C.POINTER(Pair), _SZ, C.c_int, C.c_double, C.POINTER(Result)]),
+    ("b2r_batch_last_rounds", C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("b2r_loop_argmin", C.c_int, [C.POINTER(Result), _SZ, C.c_double, _I32P]),
+    ("b2r_nccl_unique_id", C.c_int, [_VP, _SZ]),
+    ("b2r_batch_comm_init", C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    ("b2r_shard_range", C.c_int, [_SZ, C.c_int, C.c_int, C.POINTER(_SZ), C.POINTER(_SZ)]),
+    ("b2r_batch_loop_detect", C.c_int, [_VP, C.POINTER(Pair), _SZ, C.POINTER(C.c_int64), _SZ, C.c_double, C.c_double, C.POINTER(Result), _I32P]),
 ]
 
 _lib = None

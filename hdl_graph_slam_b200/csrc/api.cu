@@ -19,6 +19,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "engine.cuh"
 #include "gicp.cuh"
+#include "pair_engine.cuh"
 #include "fitness.cuh"
 #include "ndt.cuh"
 #include "voxelgrid.cuh"
@@ -44,6 +45,13 @@ struct b2r_handle {
   DevBuf<float> d2;
   DevBuf<double> mahal[2], partials;
   int cur = 0;                      // buffer set holding the correspondences of the last ACCEPTED linearisation
+  // device-resident LM (pair_engine.cuh): the handle's single pair record and its host-mapped mailbox
+  PairDev* d_pair = nullptr;
+  PairReport* h_rep = nullptr; PairReport* h_rep_dev = nullptr;          // report record (128 B, checksummed message)
+  unsigned long long* h_pflag = nullptr; unsigned long long* h_pflag_dev = nullptr;  // [0] publication flag, [1] progress word
+  double* h_tap = nullptr; double* h_tap_dev = nullptr;                  // parity taps: 29 reduced values
+  int last_rounds = 0;              // rounds the previous align needed: that many (+1) are enqueued up front by the next one
+  struct b2r_batch* loop_batch = nullptr;  // b2r_loop_matching runs the candidates of a keyframe as one batch (created on first use)
   double* d_out = nullptr;          // 64 doubles
   unsigned int* d_counter = nullptr;
   double* h_out = nullptr;          // pinned + mapped, 64 doubles + flags: reduction kernels write results here directly
@@ -184,6 +192,16 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   h->h_flag = reinterpret_cast<unsigned long long*>(h->h_out + 64);
   h->h_flag_dev = reinterpret_cast<unsigned long long*>(h->h_out_dev + 64);
   h->h_flag[0] = h->h_flag[1] = h->h_flag[2] = 0;
+  {  // mailbox of the device-resident LM: [0,128) report, [128,144) flag + progress, [256,512) tap values
+    char* mb = nullptr; char* mb_dev = nullptr;
+    if (cudaMalloc(&h->d_pair, sizeof(PairDev)) != cudaSuccess || cudaHostAlloc(&mb, 512, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&mb_dev, mb, 0) != cudaSuccess)
+      return bail(fail(B2R_ECUDA, "device allocation failed"));
+    std::memset(mb, 0, 512);
+    h->h_rep = reinterpret_cast<PairReport*>(mb); h->h_rep_dev = reinterpret_cast<PairReport*>(mb_dev);
+    h->h_pflag = reinterpret_cast<unsigned long long*>(mb + 128); h->h_pflag_dev = reinterpret_cast<unsigned long long*>(mb_dev + 128);
+    h->h_tap = reinterpret_cast<double*>(mb + 256); h->h_tap_dev = reinterpret_cast<double*>(mb_dev + 256);
+  }
   cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
@@ -194,8 +212,10 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   return B2R_OK;
 }
 
+extern "C" void b2r_batch_destroy(struct b2r_batch* b);
 extern "C" void b2r_destroy(b2r_handle* h) {
   if (!h) return;
+  if (h->loop_batch) { b2r_batch_destroy(h->loop_batch); h->loop_batch = nullptr; }
   cudaSetDevice(h->cfg.device_id);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st2) cudaStreamSynchronize(h->st2);
@@ -227,6 +247,8 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->d_out) cudaFree(h->d_out);
   if (h->d_counter) cudaFree(h->d_counter);
   if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_rep) cudaFreeHost(h->h_rep);
+  if (h->d_pair) cudaFree(h->d_pair);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
@@ -286,10 +308,9 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
   return B2R_OK;
 }
 
-static int ensure_grid(b2r_handle* h, Cloud& c, int ctx = 0) {  // builds the implicit BVH (name kept from the first design)
+// builds the implicit BVH of a cloud on stream `st` with build scratch `B` (one scratch per stream)
+static int build_bvh(b2r_handle* h, Cloud& c, b2r_handle::BuildCtx& B, cudaStream_t st) {
   if (c.bvh_ready) return B2R_OK;
-  auto& B = h->bc[ctx];
-  cudaStream_t st = ctx ? h->st2 : h->st;
   const size_t n = c.n;
   const int N = (int)n;
   c.nsup = (int)((n + 1023) / 1024);
@@ -327,9 +348,10 @@ static int ensure_grid(b2r_handle* h, Cloud& c, int ctx = 0) {  // builds the im
   return B2R_OK;
 }
 
-static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
-  cudaStream_t st = ctx ? h->st2 : h->st;
-  int rc = ensure_grid(h, c, ctx);
+static int ensure_grid(b2r_handle* h, Cloud& c, int ctx = 0) { return build_bvh(h, c, h->bc[ctx], ctx ? h->st2 : h->st); }
+
+static int build_cov(b2r_handle* h, Cloud& c, b2r_handle::BuildCtx& B, cudaStream_t st) {
+  int rc = build_bvh(h, c, B, st);
   if (rc) return rc;
   if (c.cov_ready) return B2R_OK;
   const size_t padded = (size_t)c.nsup * 1024;
@@ -380,6 +402,8 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) {
   c.cov_ready = true;
   return B2R_OK;
 }
+
+static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) { return build_cov(h, c, h->bc[ctx], ctx ? h->st2 : h->st); }
 
 static int preprocess(b2r_handle* h, int which, bool is_target) {
   Cloud& c = h->clouds[which];
@@ -483,9 +507,6 @@ static void colmajor_f_to_row_d(const float* g, double* x) {
   for (int r = 0; r < 4; r++)
     for (int c = 0; c < 4; c++) x[r * 4 + c] = (double)g[c * 4 + r];
 }
-static void make_pose(const double* x, PoseArg& P) {
-  for (int i = 0; i < 12; i++) { P.T[i] = x[i]; P.Tf[i] = (float)x[i]; }
-}
 
 static int ensure_align_ws(b2r_handle* h, size_t n_in) {
   const size_t n = ((n_in + 1023) / 1024) * 1024;
@@ -496,95 +517,155 @@ static int ensure_align_ws(b2r_handle* h, size_t n_in) {
   }
   B2R_CUDA(h->d2.reserve(n + 1));
   size_t nb = (n + kAccThreads - 1) / kAccThreads + 1;
-  B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));  // linearize partials, then the trial-cost partials
+  B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));
   return B2R_OK;
 }
 
-// One fused pass at pose x: update_correspondences + linearize into buffer set `wset`; seeds (and, if fuse_error, the trial cost
-// of FastGICP::compute_error) come from buffer set `rset`.  *y_prev receives the trial cost when fuse_error.
-static int gicp_linearize(b2r_handle* h, const double* x0, bool seed, int wset, int rset, bool fuse_error, double* H, double* b, double* y,
-                          double* y_prev) {
-  Cloud& s = SRC(h);
-  Cloud& t = TGT(h);
-  LinArgs A;
-  A.src = s.bvh(); A.scov = s.cov.p;
-  A.tgt = t.bvh(); A.tcov = t.cov.p;
-  const double thr = h->cfg.max_correspondence_distance;
-  A.thr2 = thr * thr;
-  float lim = (float)A.thr2;
-  if ((double)lim < A.thr2) lim = std::nextafterf(lim, INFINITY);
-  A.lim = lim;
-  A.corr = h->corr[wset].p; A.cpos = h->cpos[wset].p; A.d2 = h->d2.p; A.mahal = h->mahal[wset].p;
-  A.cpos_prev = h->cpos[rset].p; A.mahal_prev = h->mahal[rset].p; A.fuse_error = fuse_error ? 1 : 0;
-  A.partials = h->partials.p; A.out = h->h_out_dev; A.counter = h->d_counter;
-  A.flag = h->h_flag_dev; A.seq = ++h->seq;
-  A.use_seed = seed ? 1 : 0;
+static LmCfg make_lm_cfg(const b2r_config& cfg, bool want_fitness, double fit_max_range) {
+  LmCfg c;
+  c.max_iterations = cfg.max_iterations;
+  c.rot_eps = cfg.rotation_epsilon;
+  c.trans_eps = cfg.transformation_epsilon;
+  const double thr = cfg.max_correspondence_distance;
+  c.thr2 = thr * thr;
+  float lim = (float)c.thr2;
+  if ((double)lim < c.thr2) lim = std::nextafterf(lim, INFINITY);
+  c.lim = lim;
+  c.want_fitness = want_fitness ? 1 : 0;
+  c.fit_max_range = fit_max_range;
+  // the fitness search must reach every neighbour with d2 <= max_range: its limit is the next float ABOVE max_range
+  float fl = (fit_max_range >= (double)FLT_MAX) ? INFINITY : (float)fit_max_range;
+  if (fl < INFINITY) { if ((double)fl < fit_max_range) fl = std::nextafterf(fl, INFINITY); fl = std::nextafterf(fl, INFINITY); }
+  c.fit_lim = fl;
   static const bool index_seed = !getenv("B2R_NO_INDEX_SEED");
-  A.tgt_pos_of = index_seed ? t.pos_of.p : nullptr; A.tgt_n = (int)t.n;
-  A.prof = nullptr;
-#ifdef B2R_KNN_PROFILE
-  static long long* d_cprof = nullptr;
-  if (!d_cprof) cudaMalloc(&d_cprof, (size_t)(1 << 17) * 4 * sizeof(long long));
-  A.prof = d_cprof;
-#endif
-  PoseArg P;
-  make_pose(x0, P);
-  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kLinThreads);
-  { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_correspond<kNnCopies><<<kNnCopies * nb, kLinThreads, 0, h->st>>>(A, P);
-    TEL_END(&h->tel, KC_GICP_CORR, 1, h->st); }
-  { TEL_BEGIN(&h->tel, h->st);
+  c.index_seed = index_seed ? 1 : 0;
+  return c;
+}
+
+// PairDev of one (source, target) with the handle-independent parts filled in
+static void fill_pair_geometry(PairDev& P, const Cloud& s, const Cloud& t) {
+  std::memset(&P, 0, sizeof(P));
+  P.src = s.bvh(); P.scov = s.cov.p;
+  P.tgt = t.bvh(); P.tcov = t.cov.p;
+  P.tgt_pos_of = t.pos_of.p; P.tgt_n = (int)t.n;
+  P.nblk_acc = (int)((size_t)s.nsup * 1024 / kAccThreads);
+}
+static void fill_pair_start(PairDev& P, const double* x_row12, int mode) {
+  for (int i = 0; i < 12; i++) { P.xe[i] = x_row12[i]; P.x0[i] = x_row12[i]; }
+  P.mode = mode;
+  P.lambda = -1.0; P.nu = 2.0;
+}
+
+template <int C>
+static cudaError_t launch_search(PairDev* d_pairs, const int* d_active, unsigned n_slots, unsigned max_sorted, const LmCfg& cfg, cudaStream_t st, bool pdl) {
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3((unsigned)((size_t)max_sorted * C / kLinThreads), n_slots);
+  lc.blockDim = dim3(kLinThreads); lc.dynamicSmemBytes = 0; lc.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  la[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&lc, k_pair_search<C>, d_pairs, d_active, cfg);
+}
+
+// one round (update_correspondences + linearize/compute_error + LM step) over n_slots pair slots
+static int launch_round(PairDev* d_pairs, const int* d_active, unsigned n_slots, unsigned max_sorted, int copies, const LmCfg& cfg, cudaStream_t st,
+                        Telemetry* tel, bool search = true) {
+  static const bool pdl = !getenv("B2R_NO_PDL");
+  if (search) {
+    TEL_BEGIN(tel, st);
+    cudaError_t e = copies == 1 ? launch_search<1>(d_pairs, d_active, n_slots, max_sorted, cfg, st, pdl)
+                  : copies == 2 ? launch_search<2>(d_pairs, d_active, n_slots, max_sorted, cfg, st, pdl)
+                                : launch_search<4>(d_pairs, d_active, n_slots, max_sorted, cfg, st, pdl);
+    B2R_CUDA(e);
+    TEL_END(tel, KC_GICP_CORR, 1, st);
+  }
+  {
+    TEL_BEGIN(tel, st);
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3((unsigned)((size_t)s.nsup * 1024 / kAccThreads)); lc.blockDim = dim3(kAccThreads); lc.dynamicSmemBytes = 0; lc.stream = h->st;
+    lc.gridDim = dim3((unsigned)(max_sorted / kAccThreads), n_slots); lc.blockDim = dim3(kAccThreads); lc.dynamicSmemBytes = 0; lc.stream = st;
     cudaLaunchAttribute la[1];
     la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     la[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool pdl = !getenv("B2R_NO_PDL");
     lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
-    B2R_CUDA(cudaLaunchKernelEx(&lc, k_gicp_accumulate, A, P));
-    TEL_END(&h->tel, KC_GICP_LIN, 1, h->st); }
-  B2R_CUDA(cudaGetLastError());
-#ifdef B2R_KNN_PROFILE
-  {
-    cudaStreamSynchronize(h->st);
-    const size_t nwarp = (size_t)kNnCopies * nb * kLinThreads / 32;
-    std::vector<long long> hp(nwarp * 4);
-    cudaMemcpy(hp.data(), d_cprof, nwarp * 4 * sizeof(long long), cudaMemcpyDeviceToHost);
-    if (FILE* f = fopen(seed ? "gpurun_out/corr_prof_seeded.bin" : "gpurun_out/corr_prof_first.bin", "wb")) {
-      fwrite(hp.data(), sizeof(long long), nwarp * 4, f);
-      fclose(f);
-    }
+    B2R_CUDA(cudaLaunchKernelEx(&lc, k_pair_accumulate, d_pairs, d_active, cfg));
+    TEL_END(tel, KC_GICP_LIN, 1, st);
   }
-#endif
-  h->tel.d2h += kAcc * sizeof(double);
-  { int wrc = wait_host_result(h->h_flag, A.seq, h->h_out, kAcc, false, h->st); if (wrc) return wrc; }
-  // unpack the upper triangle
-  int k = 0;
-  for (int r = 0; r < 6; r++)
-    for (int c = r; c < 6; c++) { H[r * 6 + c] = H[c * 6 + r] = h->h_out[k++]; }
-  for (int i = 0; i < 6; i++) b[i] = h->h_out[21 + i];
-  *y = h->h_out[27];
-  if (y_prev) *y_prev = h->h_out[28];
   return B2R_OK;
 }
 
-static int gicp_error(b2r_handle* h, const double* xi, double* y) {
+__global__ void k_pair_init(const __grid_constant__ PairDev init, PairDev* dst) {
+  // the whole record travels as a kernel parameter: no DMA, no staging buffer (single-pair path)
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(&init);
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / 8); i += blockDim.x) d[i] = s[i];
+}
+static_assert(sizeof(PairDev) % 8 == 0, "PairDev is copied in 64-bit words");
+
+// the acceptance test of a report message: flag == seq and word 15 == seq ^ mix(words 0..14)
+static bool report_consistent(const volatile unsigned long long* flag, unsigned long long seq, const volatile unsigned long long* w) {
+  if (*flag != seq) return false;
+  unsigned long long x = seq;
+  for (int i = 0; i < 15; i++) x ^= msg_mix(w[i], i);
+  return x == w[15];
+}
+
+// Run the handle's single pair from `mode` at pose x (row-major 3x4 in x[0..11]) until its report lands in mapped memory.
+// Rounds are enqueued ahead of the device (no host wait per iteration); a finished pair's remaining rounds exit at once.
+static int run_single_pair(b2r_handle* h, const double* x, int mode, int tap, const LmCfg& cfg, int first_batch) {
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
-  ErrArgs A;
-  A.ssp = s.sorted.p; A.n_sorted = s.nsup * 1024; A.tsp = t.sorted.p; A.cpos = h->cpos[h->cur].p; A.mahal = h->mahal[h->cur].p;
-  A.partials = h->partials.p + ((size_t)s.nsup * 1024 / kAccThreads + 1) * kAcc; A.out = h->h_out_dev + 32; A.counter = h->d_counter + 1;
-  A.flag = h->h_flag_dev + 1; A.seq = ++h->seq;
-  PoseArg P;
-  make_pose(xi, P);
-  const unsigned nb = (unsigned)((size_t)s.nsup * 1024 / kErrThreads);
-  { TEL_BEGIN(&h->tel, h->st);
-    k_gicp_error<<<nb, kErrThreads, 0, h->st>>>(A, P);
-    TEL_END(&h->tel, KC_GICP_ERR, 1, h->st); }
+  PairDev P;
+  fill_pair_geometry(P, s, t);
+  fill_pair_start(P, x, mode);
+  for (int i = 0; i < 2; i++) { P.corr[i] = h->corr[i].p; P.cpos[i] = h->cpos[i].p; P.mahal[i] = h->mahal[i].p; }
+  P.d2 = h->d2.p; P.partials = h->partials.p;
+  P.report = h->h_rep_dev; P.flag = h->h_pflag_dev; P.progress = h->h_pflag_dev + 1; P.tap_out = h->h_tap_dev;
+  P.seq = ++h->seq;
+  P.tap = tap;
+  P.cur = (mode == PM_FIRST) ? 0 : h->cur;
+  const unsigned long long seq = P.seq;
+  k_pair_init<<<1, 128, 0, h->st>>>(P, h->d_pair);
   B2R_CUDA(cudaGetLastError());
-  h->tel.d2h += sizeof(double);
-  { int wrc = wait_host_result(h->h_flag + 1, A.seq, h->h_out + 32, 1, false, h->st); if (wrc) return wrc; }
-  *y = h->h_out[32];
+  const unsigned max_sorted = (unsigned)((size_t)s.nsup * 1024);
+  static const int copies = [] { const char* e = getenv("B2R_NN_COPIES"); int c = e ? atoi(e) : 4; return (c == 1 || c == 2) ? c : 4; }();
+  int enq = 0;
+  auto enqueue = [&](int n) -> int {
+    for (int i = 0; i < n; i++) {
+      int rc = launch_round(h->d_pair, nullptr, 1, max_sorted, copies, cfg, h->st, &h->tel, true);
+      if (rc) return rc;
+      enq++;
+    }
+    return B2R_OK;
+  };
+  int rc = enqueue(first_batch);
+  if (rc) return rc;
+  const volatile unsigned long long* flag = h->h_pflag;
+  const volatile unsigned long long* prog = h->h_pflag + 1;
+  const volatile unsigned long long* w = reinterpret_cast<const volatile unsigned long long*>(h->h_rep);
+  static const unsigned long spin_limit = [] { const char* e = getenv("B2R_SPIN_LIMIT"); return e ? strtoul(e, nullptr, 10) : 4000000ul; }();
+  unsigned long spins = 0;
+  for (;;) {
+    if (report_consistent(flag, seq, w)) break;
+    const unsigned long long pw = *prog;
+    const int done = ((pw >> 16) == (seq & 0xffffffffffffull)) ? (int)(pw & 0xffff) : 0;
+    if (enq - done < 2 && !tap) { rc = enqueue(2); if (rc) return rc; }
+    if ((++spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(h->st);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
+      if (e == cudaSuccess && !report_consistent(flag, seq, w)) {  // everything enqueued has run and the pair is not finished
+        if (tap) return fail(B2R_ECUDA, "tap round finished without signalling its result");
+        rc = enqueue(2);
+        if (rc) return rc;
+      }
+      if (spins > spin_limit) {  // other streams' work is ahead of ours: stop burning a core and block
+        B2R_CUDA(cudaStreamSynchronize(h->st));
+        spins = 0;
+      }
+    }
+  }
+  h->last_rounds = h->h_rep->rounds;
+  h->tel.d2h += sizeof(PairReport);
   return B2R_OK;
 }
 
@@ -618,71 +699,21 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
   if (rc) return rc;
   rc = ensure_align_ws(h, s.n);
   if (rc) return rc;
-  const b2r_config& cfg = h->cfg;
-  double lambda = -1.0;
-  bool converged = false;
-  int it = 0;
-  // fast_gicp's LM loop (LsqRegistration::computeTransformation / step_lm) with ONE kernel per iteration:
-  // the trial cost compute_error(xi) of iteration i and the linearisation linearize(xi) of iteration i+1 walk the same
-  // points at the same pose, so they are fused into one pass that writes the NEW correspondences into the other buffer
-  // set; the set is adopted only if the step is accepted (rho >= 0), so a rejected trial leaves iteration i's data intact.
-  double H[36], b[6], y0;
-  h->cur = 0;
-  rc = gicp_linearize(h, x0, false, h->cur, h->cur, false, H, b, &y0, nullptr);
+  // fast_gicp's LM loop (LsqRegistration::computeTransformation / step_lm) runs ON THE DEVICE (pair_engine.cuh):
+  // one search + one accumulate launch per LM trial, the accumulate kernel's last block takes the LM step.  The trial cost
+  // compute_error(xi) of iteration i and the linearisation linearize(xi) of iteration i+1 walk the same points at the same pose,
+  // so they are one pass that writes the NEW correspondences into the other buffer set, adopted only if rho >= 0.
+  const LmCfg cfg = make_lm_cfg(h->cfg, false, DBL_MAX);
+  const int predicted = h->last_rounds > 0 ? h->last_rounds + 1 : 4;
+  rc = run_single_pair(h, x0, PM_FIRST, 0, cfg, predicted < 2 ? 2 : predicted);
   if (rc) return rc;
+  const PairReport& rep = *h->h_rep;
+  h->cur = rep.cur;
   h->corr_valid = true;
-  for (it = 0; it < cfg.max_iterations && !converged; it++) {
-    double delta[16];
-    if (lambda < 0.0) {
-      double mx = 0;
-      for (int i = 0; i < 6; i++) mx = std::max(mx, std::fabs(H[i * 6 + i]));
-      lambda = 1e-9 * mx;
-    }
-    double nu = 2.0;
-    bool ok = false;
-    for (int li = 0; li < 10; li++) {
-      double A[36], nb[6], d[6];
-      for (int i = 0; i < 36; i++) A[i] = H[i] + ((i % 7 == 0) ? lambda : 0.0);
-      for (int i = 0; i < 6; i++) nb[i] = -b[i];
-      bool solved = ldlt6_solve(A, nb, d);
-      for (int i = 0; i < 6; i++) solved &= std::isfinite(d[i]);
-      if (!solved) break;  // singular / non-finite step: "lm not converged", pose keeps its last valid value (oracle/gicp.cpp)
-      se3_exp(d, delta);
-      double xi[16], yi;
-      mul_iso(delta, x0, xi);
-      // the next iteration exists only if this step does not converge and the iteration cap is not reached
-      const bool will_continue = !gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon) && (it + 1 < cfg.max_iterations);
-      double Hn[36], bn[6], yn = 0;
-      if (will_continue) rc = gicp_linearize(h, xi, true, h->cur ^ 1, h->cur, true, Hn, bn, &yn, &yi);
-      else rc = gicp_error(h, xi, &yi);
-      if (rc) return rc;
-      double den = 0;
-      for (int i = 0; i < 6; i++) den += d[i] * (lambda * d[i] - b[i]);
-      double rho = (y0 - yi) / den;
-      if (rho < 0) {
-        if (gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon)) { ok = true; break; }
-        lambda = nu * lambda;
-        nu = 2 * nu;
-        continue;  // the speculative linearisation (other buffer set) is simply dropped
-      }
-      double tt = 2 * rho - 1;
-      lambda = lambda * std::max(1.0 / 3.0, 1 - tt * tt * tt);
-      std::memcpy(x0, xi, sizeof(xi));
-      if (will_continue) {  // adopt the linearisation at the accepted pose: it IS the next iteration's linearize(x0)
-        h->cur ^= 1;
-        std::memcpy(H, Hn, sizeof(H));
-        std::memcpy(b, bn, sizeof(b));
-        y0 = yn;
-      }
-      ok = true;
-      break;
-    }
-    if (!ok) { it++; break; }  // "lm not converged!!"
-    converged = gicp_is_converged(delta, cfg.rotation_epsilon, cfg.transformation_epsilon);
-  }
   float Tf[16];
-  for (int i = 0; i < 16; i++) Tf[i] = (float)x0[i];
-  store_result(h, Tf, converged, it, out);
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) Tf[r * 4 + c] = rep.r.T[c * 4 + r];
+  store_result(h, Tf, rep.r.converged != 0, rep.r.iterations, out);
   return B2R_OK;
 }
 
@@ -853,10 +884,18 @@ extern "C" int b2r_gicp_linearize_at(b2r_handle* h, const double T[16], double* 
   double x[16];
   for (int r = 0; r < 4; r++)
     for (int c = 0; c < 4; c++) x[r * 4 + c] = T[c * 4 + r];
+  const LmCfg cfg = make_lm_cfg(h->cfg, false, DBL_MAX);
+  rc = run_single_pair(h, x, PM_FIRST, 1, cfg, 1);  // one update_correspondences + linearize round, reduced values tapped
+  if (rc) return rc;
+  B2R_CUDA(cudaStreamSynchronize(h->st));  // the tap words carry no checksum: wait for the stream
   h->cur = 0;
-  rc = gicp_linearize(h, x, false, 0, 0, false, H, b, err, nullptr);
-  if (rc == B2R_OK) h->corr_valid = true;
-  return rc;
+  h->corr_valid = true;
+  int k = 0;
+  for (int r = 0; r < 6; r++)
+    for (int c = r; c < 6; c++) { H[r * 6 + c] = H[c * 6 + r] = h->h_tap[k++]; }
+  for (int i = 0; i < 6; i++) b[i] = h->h_tap[21 + i];
+  *err = h->h_tap[27];
+  return B2R_OK;
 }
 
 extern "C" int b2r_gicp_error_at(b2r_handle* h, const double T[16], double* err) {
@@ -866,7 +905,12 @@ extern "C" int b2r_gicp_error_at(b2r_handle* h, const double T[16], double* err)
   double x[16];
   for (int r = 0; r < 4; r++)
     for (int c = 0; c < 4; c++) x[r * 4 + c] = T[c * 4 + r];
-  return gicp_error(h, x, err);
+  const LmCfg cfg = make_lm_cfg(h->cfg, false, DBL_MAX);
+  int rc = run_single_pair(h, x, PM_ERR, 1, cfg, 1);  // compute_error with the correspondences of the last linearisation
+  if (rc) return rc;
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  *err = h->h_tap[28];
+  return B2R_OK;
 }
 
 extern "C" int b2r_ndt_get_voxels(b2r_handle* h, size_t capacity, size_t* n_voxels, int64_t* keys, int32_t* npts, double* mean,
@@ -1203,7 +1247,9 @@ static int odometry_matching_impl(b2r_odometry* o, double stamp, const void* clo
   return B2R_OK;
 }
 
-// ------------------------------------------------------------------------------------------------ loop-closure mirror
+// ------------------------------------------------------------------------------------------------ batched path + loop-closure mirror
+#include "batch.cuh"
+
 extern "C" int b2r_loop_matching(b2r_handle* h, const void* new_keyframe, size_t n_new, size_t stride_bytes, const void* const* candidates,
                                  const size_t* n_candidates_pts, size_t n_candidates, const float* guesses, double fitness_score_max_range,
                                  double fitness_score_thresh, b2r_result* results, int32_t* best) {
@@ -1211,26 +1257,46 @@ extern "C" int b2r_loop_matching(b2r_handle* h, const void* new_keyframe, size_t
   *best = -1;
   if (n_candidates == 0) return B2R_OK;  // loop_detector.hpp:118-120
   if (!candidates || !n_candidates_pts || !guesses) return fail(B2R_EINVAL, "NULL argument");
-  int rc = b2r_set_target(h, new_keyframe, n_new, stride_bytes);  // :122
-  if (rc) return rc;
-  double best_score = DBL_MAX;
-  int best_i = -1;
-  for (size_t i = 0; i < n_candidates; i++) {  // :135-154
-    rc = b2r_set_source(h, candidates[i], n_candidates_pts[i], stride_bytes);
+  if (h->cfg.method != B2R_METHOD_GICP) {  // NDT handle: the reference's sequential loop, one align + getFitnessScore per candidate
+    int rc = b2r_set_target(h, new_keyframe, n_new, stride_bytes);  // :122
     if (rc) return rc;
-    b2r_result r;
-    rc = b2r_align(h, guesses + i * 16, &r);
-    if (rc) return rc;
-    double score;
-    rc = b2r_fitness(h, nullptr, fitness_score_max_range, 0.25f, &score, nullptr, nullptr);
-    if (rc) return rc;
-    r.fitness = score;
-    if (results) results[i] = r;
-    if (!r.converged || score > best_score) continue;  // :147
-    best_score = score;
-    best_i = (int)i;
+    std::vector<b2r_result> rs(n_candidates);
+    for (size_t i = 0; i < n_candidates; i++) {  // :135-154
+      rc = b2r_set_source(h, candidates[i], n_candidates_pts[i], stride_bytes);
+      if (rc) return rc;
+      rc = b2r_align(h, guesses + i * 16, &rs[i]);
+      if (rc) return rc;
+      double score;
+      rc = b2r_fitness(h, nullptr, fitness_score_max_range, 0.25f, &score, nullptr, nullptr);
+      if (rc) return rc;
+      rs[i].fitness = score;
+      if (results) results[i] = rs[i];
+    }
+    return b2r_loop_argmin(rs.data(), n_candidates, fitness_score_thresh, best);
   }
-  if (best_score > fitness_score_thresh) best_i = -1;  // :160-163
-  *best = best_i;
-  return B2R_OK;
+  // GICP: the candidate loop is ONE batched registration — all candidates of the new keyframe share the target (:122) and only
+  // couple through the argmin (:147), so every LM iteration of every candidate is one pair of launches (pair_engine.cuh)
+  if (!h->loop_batch) {
+    int rc = b2r_batch_create(&h->cfg, &h->loop_batch);
+    if (rc) return rc;
+  }
+  b2r_batch* b = h->loop_batch;
+  std::vector<int32_t> ids(n_candidates + 1, -1);
+  auto cleanup = [&]() { for (int32_t id : ids) if (id >= 0) b2r_batch_remove_cloud(b, id); };
+  int rc = b2r_batch_add_cloud(b, new_keyframe, n_new, stride_bytes, &ids[0]);
+  for (size_t i = 0; i < n_candidates && !rc; i++) rc = b2r_batch_add_cloud(b, candidates[i], n_candidates_pts[i], stride_bytes, &ids[i + 1]);
+  std::vector<b2r_pair> pairs(n_candidates);
+  std::vector<b2r_result> rs(n_candidates);
+  if (!rc) {
+    for (size_t i = 0; i < n_candidates; i++) {
+      pairs[i].source = ids[i + 1];
+      pairs[i].target = ids[0];
+      std::memcpy(pairs[i].guess, guesses + i * 16, 16 * sizeof(float));
+    }
+    rc = b2r_batch_align(b, pairs.data(), n_candidates, 1, fitness_score_max_range, rs.data());
+  }
+  if (rc) { const std::string msg = g_last_error; cleanup(); g_last_error = msg; return rc; }
+  cleanup();
+  if (results) for (size_t i = 0; i < n_candidates; i++) results[i] = rs[i];
+  return b2r_loop_argmin(rs.data(), n_candidates, fitness_score_thresh, best);
 }

@@ -17,7 +17,7 @@ library; nothing here computes.
 import ctypes as C
 import numpy as np
 from . import _capi
-from ._capi import Config, Result, OdometryParams, OdometryStatus, Stats, check, B2R_METHOD_GICP, B2R_METHOD_NDT
+from ._capi import Config, Result, Pair, OdometryParams, OdometryStatus, Stats, check, B2R_METHOD_GICP, B2R_METHOD_NDT
 
 
 def _cloud(a):
@@ -340,3 +340,126 @@ class LoopDetector:
                                           res, C.byref(best)))
         results = [dict(T=_from_colmajor(r.T), fitness=r.fitness, converged=bool(r.converged), iterations=r.iterations) for r in res[:m]]
         return best.value, results
+
+
+def _result_dict(r):
+    return dict(T=_from_colmajor(r.T), fitness=r.fitness, converged=bool(r.converged), iterations=r.iterations)
+
+
+def shard_range(n_groups, world, rank):
+    """contiguous block of groups owned by `rank` (b2r_shard_range)"""
+    g0, g1 = C.c_size_t(), C.c_size_t()
+    check(_capi.load().b2r_shard_range(n_groups, world, rank, C.byref(g0), C.byref(g1)))
+    return g0.value, g1.value
+
+
+def loop_argmin(results, fitness_score_thresh):
+    """LoopDetector::matching's selection over one group's Result records (b2r_loop_argmin)"""
+    arr = (Result * max(len(results), 1))(*results)
+    best = C.c_int32(-1)
+    check(_capi.load().b2r_loop_argmin(arr, len(results), fitness_score_thresh, C.byref(best)))
+    return best.value
+
+
+class RegistrationBatch:
+    """Batched, device-resident GICP registration (include/b200reg.h: b2r_batch_*): keyframe clouds are registered once and many
+    (source, target, guess) pairs are aligned per launch — the candidate loop of LoopDetector::matching
+    (include/hdl_graph_slam/loop_detector.hpp:135-154) for one or many new keyframes."""
+
+    def __init__(self, cfg=None, params=None, device_id=0):
+        self._lib = _capi.load()
+        if cfg is None:
+            reg = select_registration_method(params or {"registration_method": "FAST_GICP"}, device_id=device_id)
+            cfg = reg.config
+            reg.close()
+        self._b = C.c_void_p()
+        check(self._lib.b2r_batch_create(C.byref(cfg), C.byref(self._b)))
+        eng = C.c_void_p()
+        check(self._lib.b2r_batch_get_engine(self._b, C.byref(eng)))
+        self.engine = Registration(_handle=eng)
+        self.engine.close = lambda: None  # owned by the batch
+        self._keep = {}
+
+    def close(self):
+        if self._b:
+            self.engine._h = C.c_void_p()
+            self._lib.b2r_batch_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def addCloud(self, cloud):
+        a, n, s = _cloud(cloud)
+        cid = C.c_int32(-1)
+        check(self._lib.b2r_batch_add_cloud(self._b, a.ctypes.data_as(C.c_void_p), n, s, C.byref(cid)))
+        self._keep[cid.value] = a
+        return cid.value
+
+    def addCloudRaw(self, ptr, n, stride_bytes, device=False):
+        cid = C.c_int32(-1)
+        fn = self._lib.b2r_batch_add_cloud_device if device else self._lib.b2r_batch_add_cloud
+        check(fn(self._b, C.c_void_p(ptr), n, stride_bytes, C.byref(cid)))
+        return cid.value
+
+    def removeCloud(self, cid):
+        check(self._lib.b2r_batch_remove_cloud(self._b, cid))
+        self._keep.pop(cid, None)
+
+    def cloudCount(self):
+        return self._lib.b2r_batch_cloud_count(self._b)
+
+    def synchronize(self):
+        check(self._lib.b2r_batch_synchronize(self._b))
+
+    @staticmethod
+    def _pairs(pairs):
+        arr = (Pair * max(len(pairs), 1))()
+        for i, (s, t, g) in enumerate(pairs):
+            arr[i].source, arr[i].target = int(s), int(t)
+            gc = _colmajor(np.eye(4) if g is None else g)
+            for k in range(16):
+                arr[i].guess[k] = gc[k]
+        return arr
+
+    def align(self, pairs, want_fitness=True, fitness_max_range=np.finfo(np.float64).max, raw=False):
+        """pairs: list of (source id, target id, 4x4 guess) -> list of result dicts (or the ctypes Result array when raw)"""
+        arr = pairs if isinstance(pairs, C.Array) else self._pairs(pairs)
+        n = len(arr) if isinstance(pairs, C.Array) else len(pairs)
+        res = (Result * max(n, 1))()
+        check(self._lib.b2r_batch_align(self._b, arr, n, int(bool(want_fitness)), fitness_max_range, res))
+        if raw:
+            return res
+        return [_result_dict(r) for r in res[:n]]
+
+    def lastRounds(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self._lib.b2r_batch_last_rounds(self._b, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # --- multi-GPU
+    @staticmethod
+    def ncclUniqueId():
+        buf = (C.c_char * 128)()
+        check(_capi.load().b2r_nccl_unique_id(buf, 128))
+        return bytes(buf)
+
+    def commInit(self, unique_id, rank, world):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        check(self._lib.b2r_batch_comm_init(self._b, buf, rank, world))
+
+    def loopDetect(self, pairs, group_first, fitness_score_max_range=np.finfo(np.float64).max, fitness_score_thresh=0.5, raw=False):
+        """LoopDetector::matching for many new keyframes, sharded over the communicator's ranks (b2r_batch_loop_detect)"""
+        arr = pairs if isinstance(pairs, C.Array) else self._pairs(pairs)
+        n = int(group_first[-1])
+        gf = (C.c_int64 * len(group_first))(*[int(x) for x in group_first])
+        ng = len(group_first) - 1
+        res = (Result * max(n, 1))()
+        best = (C.c_int32 * max(ng, 1))()
+        check(self._lib.b2r_batch_loop_detect(self._b, arr, n, gf, ng, fitness_score_max_range, fitness_score_thresh, res, best))
+        if raw:
+            return list(best[:ng]), res
+        return list(best[:ng]), [_result_dict(r) for r in res[:n]]

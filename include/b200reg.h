@@ -212,6 +212,54 @@ int b2r_loop_matching(b2r_handle* h, const void* new_keyframe, size_t n_new, siz
                       const size_t* n_candidates_pts, size_t n_candidates, const float* guesses, double fitness_score_max_range,
                       double fitness_score_thresh, b2r_result* results, int32_t* best);
 
+
+/* ---- batched, device-resident registration (north_star's multi-GPU split; loop_detector.hpp:135-154) --------------------
+ * A b2r_batch lives on ONE GPU (cfg->device_id).  Keyframe clouds are registered once (b2r_batch_add_cloud: upload, search
+ * structure, GICP covariances) and named by id; b2r_batch_align runs MANY (source, target, guess) registrations at once:
+ * one pair of kernel launches per LM iteration covers every pair still in flight, the LM step (6x6 solve, se3_exp, rho test,
+ * convergence) runs on the device, and the host reads the 80-byte records back once per batch.  Results are bitwise identical
+ * to running each pair alone through b2r_set_target / b2r_set_source / b2r_align (+ b2r_fitness-equivalent score).
+ * GICP engine only (the reference's loop closure uses FAST_GICP: launch/hdl_graph_slam.launch:127).
+ *
+ * Host buffers passed to b2r_batch_add_cloud may be pageable (copied before the call returns) or pinned (DMA'd in place:
+ * keep them unmodified until the next b2r_batch_align / b2r_batch_loop_detect / b2r_batch_synchronize returns). */
+typedef struct b2r_batch b2r_batch;
+typedef struct b2r_pair {
+  int32_t source;  /* cloud id: setInputSource(candidate->cloud)   loop_detector.hpp:136 */
+  int32_t target;  /* cloud id: setInputTarget(new_keyframe->cloud) loop_detector.hpp:122 */
+  float guess[16]; /* column-major initial guess                     loop_detector.hpp:139-143 */
+} b2r_pair;
+int b2r_batch_create(const b2r_config* cfg, b2r_batch** out);
+void b2r_batch_destroy(b2r_batch* b);
+/* the engine handle behind the batch (telemetry / stream access: b2r_get_stats, b2r_set_profiling, b2r_get_stream) */
+int b2r_batch_get_engine(b2r_batch* b, b2r_handle** out);
+int b2r_batch_add_cloud(b2r_batch* b, const void* points, size_t n, size_t stride_bytes, int32_t* cloud_id);
+int b2r_batch_add_cloud_device(b2r_batch* b, const void* d_points, size_t n, size_t stride_bytes, int32_t* cloud_id);
+int b2r_batch_remove_cloud(b2r_batch* b, int32_t cloud_id);
+int b2r_batch_cloud_count(const b2r_batch* b);
+int b2r_batch_synchronize(b2r_batch* b);
+/* align every pair; want_fitness != 0 also evaluates getFitnessScore(fitness_max_range) at each final pose (loop_detector.hpp:146;
+ * max_range is compared with the SQUARED distance as in information_matrix_calculator.cpp:69), else fitness = NaN */
+int b2r_batch_align(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, int want_fitness, double fitness_max_range, b2r_result* out);
+/* rounds (launch pairs) and pair-rounds (sum over rounds of the pairs in flight) of the last batch: the work the roofline divides by */
+int b2r_batch_last_rounds(const b2r_batch* b, uint64_t* rounds, uint64_t* pair_rounds);
+/* the selection of LoopDetector::matching over one group's records (loop_detector.hpp:147,160-163): index of the best converged
+ * candidate (a later candidate with an EQUAL score wins) or -1 when nothing converged or the best score exceeds the threshold */
+int b2r_loop_argmin(const b2r_result* results, size_t n, double fitness_score_thresh, int32_t* best);
+
+/* multi-GPU: one process per GPU; rank 0 creates the id, every rank receives it through the launcher's own channel
+ * (bench.py: torch.distributed broadcast) and joins.  The library links NCCL itself. */
+int b2r_nccl_unique_id(void* out128, size_t capacity);
+int b2r_batch_comm_init(b2r_batch* b, const void* unique_id128, int rank, int world);
+/* contiguous block of groups owned by `rank` (neighbouring groups share candidate keyframes: each is built on one GPU only) */
+int b2r_shard_range(size_t n_groups, int world, int rank, size_t* g0, size_t* g1);
+/* LoopDetector::matching for n_groups new keyframes at once.  pairs[group_first[g] .. group_first[g+1]) are the candidates of
+ * group g in the reference's order.  Every rank passes the SAME pair list; cloud ids are only read for the rank's own groups
+ * (b2r_shard_range).  Each rank aligns its share, ONE ncclAllGather moves the 80-byte records (padded to the largest share),
+ * then every rank holds all_results[n_pairs] and best[n_groups] (index inside the group, or -1). */
+int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, const int64_t* group_first, size_t n_groups,
+                          double fitness_score_max_range, double fitness_score_thresh, b2r_result* all_results, int32_t* best);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,16 +262,76 @@ static void mul4_iso(const double* A, const double* B, double* O) {  // Isometry
   O[15] = 1;
 }
 
+// fast_gicp keeps the target's kd-tree and covariances for as long as the same target cloud is set (setInputTarget early-outs on
+// the same pointer; A.4): a target context holds them across align() calls — used by the CPU baseline so that the per-frame /
+// per-candidate cost is what the reference pays (source kd-tree + source covariances + align), not a rebuilt target tree.
+struct orc_gicp_target {
+  KdTree tree;
+  std::vector<double> cov;
+  const float* pts;
+  size_t m, stride;
+};
+
+static void align_impl(const KdTree& ttree, const float* src, size_t n, size_t sstride, const double* src_cov_in, const float* tgt, size_t m,
+                       size_t tstride, const double* tgt_cov_in, const orc_gicp_config* cfg, const float* guess,
+                       orc_gicp_result* res, double* trace_H, double* trace_b, double* trace_y, int32_t* corr_out);
+
+extern "C" orc_gicp_target* orc_gicp_target_create(const float* tgt, size_t m, size_t stride, int k, int threads) {
+  orc_gicp_target* t = new orc_gicp_target();
+  t->pts = tgt; t->m = m; t->stride = stride;
+  if (m) {
+    t->tree.build(tgt, m, stride);
+    t->cov.resize(m * 9);
+    covariances(t->tree, tgt, m, stride, k, t->cov.data(), threads);
+  }
+  return t;
+}
+extern "C" void orc_gicp_target_free(orc_gicp_target* t) { delete t; }
+extern "C" void orc_gicp_align_to(const orc_gicp_target* t, const float* src, size_t n, size_t sstride, const double* src_cov, const orc_gicp_config* cfg,
+                                  const float* guess, orc_gicp_result* res, int32_t* corr_out) {
+  std::memset(res, 0, sizeof(*res));
+  for (int i = 0; i < 16; i++) { res->T[i] = guess[i]; res->T64[i] = (double)guess[i]; }
+  if (n == 0 || t->m == 0) return;
+  align_impl(t->tree, src, n, sstride, src_cov, t->pts, t->m, t->stride, t->cov.data(), cfg, guess, res, nullptr, nullptr, nullptr, corr_out);
+}
+// getFitnessScore against a kept target (same arithmetic as orc_fitness)
+extern "C" double orc_gicp_target_fitness(const orc_gicp_target* t, const float* src, size_t n, size_t sstride, const float* T, double max_range, int threads) {
+  std::vector<float> d2(n);
+  std::vector<int32_t> idx(n);
+#pragma omp parallel for num_threads(nthreads(threads)) schedule(static)
+  for (long i = 0; i < (long)n; i++) {
+    float q[3];
+    xform_f32(T, src + (size_t)i * sstride, q);
+    int id = -1;
+    float d = INFINITY;
+    t->tree.knn(q, 1, &id, &d);
+    d2[i] = d;
+    idx[i] = id;
+  }
+  double sum = 0;
+  uint32_t nr = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (idx[i] < 0) continue;
+    if ((double)d2[i] <= max_range) { sum += (double)d2[i]; nr++; }
+  }
+  return nr > 0 ? sum / nr : DBL_MAX;
+}
+
 extern "C" void orc_gicp_align(const float* src, size_t n, size_t sstride, const double* src_cov_in, const float* tgt, size_t m,
                                size_t tstride, const double* tgt_cov_in, const orc_gicp_config* cfg, const float* guess,
                                orc_gicp_result* res, double* trace_H, double* trace_b, double* trace_y, int32_t* corr_out) {
-  const int threads = cfg->num_threads;
   std::memset(res, 0, sizeof(*res));
   for (int i = 0; i < 16; i++) { res->T[i] = guess[i]; res->T64[i] = (double)guess[i]; }
   if (n == 0 || m == 0) return;  // pcl::Registration::initCompute fails silently -> converged_ stays false
-
   KdTree ttree;
   ttree.build(tgt, m, tstride);
+  align_impl(ttree, src, n, sstride, src_cov_in, tgt, m, tstride, tgt_cov_in, cfg, guess, res, trace_H, trace_b, trace_y, corr_out);
+}
+
+static void align_impl(const KdTree& ttree, const float* src, size_t n, size_t sstride, const double* src_cov_in, const float* tgt, size_t m,
+                       size_t tstride, const double* tgt_cov_in, const orc_gicp_config* cfg, const float* guess,
+                       orc_gicp_result* res, double* trace_H, double* trace_b, double* trace_y, int32_t* corr_out) {
+  const int threads = cfg->num_threads;
   std::vector<double> scov_s, tcov_s;
   const double* scov = src_cov_in;
   const double* tcov = tgt_cov_in;

@@ -72,6 +72,15 @@ void orc_gicp_align(const float* src, size_t n, size_t sstride, const double* sr
                     size_t tstride, const double* tgt_cov, const orc_gicp_config* cfg, const float* guess,
                     orc_gicp_result* res, double* trace_H, double* trace_b, double* trace_y, int32_t* corr_out);
 
+/* A kept target: fast_gicp holds the target's kd-tree and covariances while the same target cloud stays set, so
+ * the per-frame / per-candidate cost of the reference is source kd-tree + source covariances + align.  `tgt` must outlive it. */
+typedef struct orc_gicp_target orc_gicp_target;
+orc_gicp_target* orc_gicp_target_create(const float* tgt, size_t m, size_t stride, int k, int threads);
+void orc_gicp_target_free(orc_gicp_target* t);
+void orc_gicp_align_to(const orc_gicp_target* t, const float* src, size_t n, size_t sstride, const double* src_cov /* or NULL */,
+                       const orc_gicp_config* cfg, const float* guess, orc_gicp_result* res, int32_t* corr_out);
+double orc_gicp_target_fitness(const orc_gicp_target* t, const float* src, size_t n, size_t sstride, const float* T, double max_range, int threads);
+
 /* pcl::Registration::getFitnessScore(max_range) twin (information_matrix_calculator.cpp:49-80) plus the
  * inlier loop of scan_matching_odometry_nodelet.cpp:309-320.  T is float32 row-major. nn_idx/nn_d2 may be NULL. */
 void orc_fitness(const float* tgt, size_t m, size_t tstride, const float* src, size_t n, size_t sstride, const float* T,

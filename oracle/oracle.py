@@ -52,6 +52,8 @@ def lib():
         _lib.orc_ndt_build.restype = C.c_void_p
         _lib.orc_ndt_dump.restype = C.c_size_t
         _lib.orc_max_threads.restype = C.c_int
+        _lib.orc_gicp_target_create.restype = C.c_void_p
+        _lib.orc_gicp_target_fitness.restype = C.c_double
     return _lib
 
 
@@ -129,6 +131,38 @@ def gicp_align(src, tgt, guess=None, max_iterations=64, transformation_epsilon=0
     if trace:
         out.update(trace_H=tH, trace_b=tb, trace_y=ty)
     return out
+
+
+class GicpTarget:
+    """a kept target (kd-tree + covariances built once), as fast_gicp keeps it while the same target cloud stays set"""
+
+    def __init__(self, tgt, k=20, threads=0):
+        ta, tp, m, ts = _f32(tgt)
+        self._keep = ta
+        self._t = C.c_void_p(lib().orc_gicp_target_create(tp, C.c_size_t(m), C.c_size_t(ts), k, threads))
+
+    def __del__(self):
+        try:
+            lib().orc_gicp_target_free(self._t)
+        except Exception:
+            pass
+
+    def align(self, src, guess=None, max_iterations=64, transformation_epsilon=0.01, rotation_epsilon=2e-3, max_corr_dist=2.5, k=20, threads=0,
+              src_cov=None):
+        sa, sp, n, ss = _f32(src)
+        cfg = GicpConfig(max_iterations, transformation_epsilon, rotation_epsilon, max_corr_dist, k, threads)
+        g = np.ascontiguousarray(np.eye(4) if guess is None else guess, np.float32)
+        res = GicpResult()
+        vp = C.c_void_p
+        corr = np.empty(max(n, 1), np.int32)
+        scp = np.ascontiguousarray(src_cov, np.float64).ctypes.data_as(vp) if src_cov is not None else None
+        lib().orc_gicp_align_to(self._t, sp, C.c_size_t(n), C.c_size_t(ss), scp, C.byref(cfg), g.ctypes.data_as(vp), C.byref(res), corr.ctypes.data_as(vp))
+        return dict(T=np.array(res.T, np.float32).reshape(4, 4), converged=bool(res.converged), iterations=res.iterations, corr=corr[:n])
+
+    def fitness(self, src, T, max_range=np.finfo(np.float64).max, threads=0):
+        sa, sp, n, ss = _f32(src)
+        T = np.ascontiguousarray(T, np.float32)
+        return lib().orc_gicp_target_fitness(self._t, sp, C.c_size_t(n), C.c_size_t(ss), T.ctypes.data_as(C.c_void_p), C.c_double(max_range), threads)
 
 
 def fitness(tgt, src, T, max_range=np.finfo(np.float64).max, inlier_thresh_sq=0.25, threads=0, want_nn=False):

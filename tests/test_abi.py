@@ -27,13 +27,13 @@ def test_struct_layouts_match_header(tmp_path):
     import ctypes as C
     from hdl_graph_slam_b200 import _capi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "b200reg.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(b2r_config), sizeof(b2r_result),'
-                   ' sizeof(b2r_odometry_params), sizeof(b2r_odometry_status));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "b200reg.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(b2r_config), sizeof(b2r_result),'
+                   ' sizeof(b2r_odometry_params), sizeof(b2r_odometry_status), sizeof(b2r_pair));return 0;}\n')
     exe = tmp_path / "sz"
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    assert sizes == [C.sizeof(_capi.Config), C.sizeof(_capi.Result), C.sizeof(_capi.OdometryParams), C.sizeof(_capi.OdometryStatus)]
+    assert sizes == [C.sizeof(_capi.Config), C.sizeof(_capi.Result), C.sizeof(_capi.OdometryParams), C.sizeof(_capi.OdometryStatus), C.sizeof(_capi.Pair)]
     assert C.sizeof(_capi.Result) == 80          # the record all-gathered across GPUs
 
 

@@ -1,20 +1,20 @@
-"""CPU-only (gloo, world_size 2): sharding, the single fixed-size all-gather and the per-group argmin of the loop-closure
-batch give the same answer as a single process; the tie rule follows loop_detector.hpp:147."""
+"""CPU-only (gloo, world_size 2): the sharding map, the single fixed-size all-gather and the per-group argmin of the loop-closure
+batch give the same answer as a single process; the Python mirror of the layout equals the library's own b2r_shard_range /
+b2r_loop_argmin (host-only entry points: they run without a GPU); the tie rule follows loop_detector.hpp:147."""
 import os
 import socket
 import numpy as np
-import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-from hdl_graph_slam_b200 import batch
+import hdl_graph_slam_b200 as pkg
+from hdl_graph_slam_b200 import batch, _capi
 
 
-def fake_records(group_sizes, groups):
+def fake_records(group_first, g0, g1):
     """deterministic stand-in for the GPU work: a record that depends only on (group, candidate)"""
     recs = []
-    for g in groups:
-        for c in range(group_sizes[g]):
+    for g in range(g0, g1):
+        for c in range(group_first[g + 1] - group_first[g]):
             r = np.zeros((), batch.RECORD_DTYPE)
             r["T"] = np.arange(16, dtype=np.float32) + 100 * g + c
             r["fitness"] = ((g * 7919 + c * 104729) % 1000) / 1000.0 + 0.01
@@ -24,55 +24,71 @@ def fake_records(group_sizes, groups):
     return np.array(recs, batch.RECORD_DTYPE) if recs else np.zeros(0, batch.RECORD_DTYPE)
 
 
-def _worker(rank, world, port, group_sizes, q):
+def _worker(rank, world, port, group_first, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    counts, slot = batch.layout(group_sizes, world)
-    mine = batch.shard_groups(len(group_sizes), world)[rank]
-    local = fake_records(group_sizes, mine)
-    records = batch.gather_records(local, counts, rank, world, None)
-    best = batch.argmin_per_group(records, group_sizes, slot, 0.5)
-    flat = [(g, c, records[slot[(g, c)][0]][slot[(g, c)][1]].tobytes()) for g in range(len(group_sizes)) for c in range(group_sizes[g])]
-    q.put((rank, best, flat))
+    M, ranges = batch.layout(group_first, world)
+    g0, g1 = batch.shard_range(len(group_first) - 1, world, rank)
+    local = fake_records(group_first, g0, g1)
+    assert len(local) == ranges[rank][1] - ranges[rank][0]
+    gathered = batch.gather_records_torch(local, M, world, None)
+    records = batch.unpack_gathered(gathered, group_first, world)
+    best = batch.argmin_per_group(records, group_first, 0.5)
+    q.put((rank, best, records.tobytes()))
     dist.destroy_process_group()
 
 
 def test_two_rank_gather_equals_single_process():
-    group_sizes = [8, 3, 0, 5, 8, 1, 7]
+    sizes = [8, 3, 0, 5, 8, 1, 7]
+    group_first = [0] + list(np.cumsum(sizes))
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, group_sizes, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, group_first, q)) for r in range(2)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # single-process reference
-    counts1, slot1 = batch.layout(group_sizes, 1)
-    rec1 = [fake_records(group_sizes, list(range(len(group_sizes))))]
-    best1 = batch.argmin_per_group(rec1, group_sizes, slot1, 0.5)
-    flat1 = [(g, c, rec1[0][slot1[(g, c)][1]].tobytes()) for g in range(len(group_sizes)) for c in range(group_sizes[g])]
+    rec1 = fake_records(group_first, 0, len(sizes))
+    best1 = batch.argmin_per_group(rec1, group_first, 0.5)
     for rank, best, flat in outs:
         assert best == best1
-        assert flat == flat1  # every rank holds every pair's record, bit-identical to the 1-process run
+        assert flat == rec1.tobytes()  # every rank holds every pair's record, bit-identical to the 1-process run
 
 
-def test_layout_and_tie_rule():
-    counts, slot = batch.layout([2, 2, 2], 2)
-    assert counts == [4, 2] and slot[(2, 1)] == (0, 3) and slot[(1, 0)] == (1, 0)
-    recs = np.zeros(3, batch.RECORD_DTYPE)
-    recs["fitness"] = [0.2, 0.2, 0.3]
-    recs["converged"] = [1, 1, 1]
-    _, slot = batch.layout([3], 1)
+def test_layout_mirror_equals_library():
+    for n_groups in (0, 1, 7, 8, 256, 257):
+        for world in (1, 2, 3, 4, 8):
+            covered = []
+            for rank in range(world):
+                assert batch.shard_range(n_groups, world, rank) == pkg.shard_range(n_groups, world, rank)
+                covered.append(batch.shard_range(n_groups, world, rank))
+            assert covered[0][0] == 0 and covered[-1][1] == n_groups and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    M, ranges = batch.layout([0, 2, 4, 6], 2)
+    assert M == 4 and ranges == [(0, 2), (2, 6)]
+
+
+def test_argmin_tie_rule_library_and_mirror():
+    def both(fit, conv, thresh=0.5):
+        recs = np.zeros(len(fit), batch.RECORD_DTYPE)
+        recs["fitness"], recs["converged"] = fit, conv
+        rs = []
+        for f, c in zip(fit, conv):
+            r = _capi.Result()
+            r.fitness, r.converged = f, c
+            rs.append(r)
+        a = batch.argmin_per_group(recs, [0, len(fit)], thresh)[0]
+        b = pkg.loop_argmin(rs, thresh)
+        assert a == b
+        return a
     # `score > best_score -> continue`: an equal score REPLACES the earlier candidate (loop_detector.hpp:147)
-    assert batch.argmin_per_group([recs], [3], slot, 0.5) == [1]
-    recs["converged"] = [1, 0, 1]
-    assert batch.argmin_per_group([recs], [3], slot, 0.5) == [0]
-    recs["fitness"] = [0.7, 0.6, 0.9]
-    assert batch.argmin_per_group([recs], [3], slot, 0.5) == [-1]  # best above fitness_score_thresh: "loop not found"
-    assert batch.argmin_per_group([np.zeros(0, batch.RECORD_DTYPE)], [0], {}, 0.5) == [-1]
+    assert both([0.2, 0.2, 0.3], [1, 1, 1]) == 1
+    assert both([0.2, 0.2, 0.3], [1, 0, 1]) == 0
+    assert both([0.7, 0.6, 0.9], [1, 1, 1]) == -1  # best above fitness_score_thresh: "loop not found"
+    assert both([], []) == -1
+    assert both([0.1, 0.2], [0, 0]) == -1

@@ -82,34 +82,6 @@ def test_loop_matching_matches_oracle(synth, oracle):
     reg.close()
 
 
-def test_loop_batch_equals_sequential_matching(synth):
-    """hdl_graph_slam_b200.batch.LoopBatch (several handles/streams, record layout, argmin) == b2r_loop_matching per group"""
-    from hdl_graph_slam_b200 import batch
-    targets = [synth.scan("vlp16_16k", frame=f, stride=8) for f in (0, 10)]
-    candidates = []
-    for gi, tf in enumerate((0, 10)):
-        cs = []
-        for j, sf in enumerate((tf + 1, tf + 251, tf + 2)):
-            rel = np.linalg.inv(synth.pose_matrix(tf)) @ synth.pose_matrix(sf)
-            g = (rel @ perturb(60 + 7 * gi + j, 0.2, 1.0)).astype(np.float32)
-            g[2, 3] = 0.0
-            cs.append((synth.scan("vlp16_16k", frame=sf, stride=8), g))
-        candidates.append(cs)
-    lb = batch.LoopBatch({"registration_method": "FAST_GICP"}, streams_per_gpu=2, fitness_score_max_range=2.5, fitness_score_thresh=0.5)
-    best, records, slot = lb.run(targets, candidates)
-    lb.close()
-    reg = pkg.select_registration_method({"registration_method": "FAST_GICP"})
-    det = pkg.LoopDetector(reg, fitness_score_max_range=2.5, fitness_score_thresh=0.5)
-    for g in range(2):
-        b, res = det.matching([c for c, _ in candidates[g]], targets[g], [gg for _, gg in candidates[g]])
-        assert b == best[g]
-        for c, r in enumerate(res):
-            rec = records[slot[(g, c)][0]][slot[(g, c)][1]]
-            assert np.array_equal(np.asarray(rec["T"]).reshape(4, 4).T, r["T"]) and rec["fitness"] == r["fitness"]
-            assert bool(rec["converged"]) == r["converged"] and int(rec["iterations"]) == r["iterations"]
-    reg.close()
-
-
 def test_prefetch_pipeline_gives_identical_odometry(synth):
     """announcing the next scan (software pipelining on a second stream) must not change a single bit of the results"""
     frames = [synth.scan("vlp16_16k", frame=k, stride=8) for k in range(7)]

@@ -101,3 +101,42 @@ def test_result_message_protocol(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "accepted_partial=0" in out.stdout and "rejected_complete=0" in out.stdout
+
+
+@pytest.fixture(scope="module")
+def lm_harness(oracle):
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    exe = os.path.join(ROOT, "build", "lm_harness")
+    subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-w", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                           "-Xcompiler", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "lm_harness.cu"),
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Xlinker", "-rpath=" + os.path.join(ROOT, "oracle")])
+    return exe
+
+
+@pytest.mark.parametrize("case", ["odometry", "loop_perturbed", "iteration_cap", "far_guess", "tight_epsilon"])
+def test_device_lm_state_machine_equals_oracle_step_lm(lm_harness, synth, tmp_path, case):
+    """The LM step the GPU runs in k_pair_accumulate's last block (pair_engine.cuh: lm_advance / lm_propose / lm_begin_outer), driven on
+    the CPU with the oracle's linearize / compute_error as the two kernels of a round: same iterations, trials, convergence flag,
+    final pose and last correspondences as the oracle's own LsqRegistration loop — including rejected trials (rho < 0), the
+    iteration cap and the 'converged by a rejected tiny step' exit."""
+    import numpy as np
+    from common import perturb
+    tgt = synth.scan("vlp16_16k", frame=5, stride=4)
+    src = synth.scan("vlp16_16k", frame=7 if case != "loop_perturbed" else 9, stride=4)
+    max_it, eps, dist = 64, 0.01, 2.5
+    guess = np.eye(4)
+    if case == "loop_perturbed":
+        guess = np.linalg.inv(synth.pose_matrix(5)) @ synth.pose_matrix(9) @ perturb(3, 0.5, 3.0)
+    elif case == "iteration_cap":
+        max_it = 2
+    elif case == "far_guess":
+        guess = perturb(11, 2.0, 8.0)  # many correspondences beyond 2.5 m: rejected trials and lambda growth
+    elif case == "tight_epsilon":
+        eps = 1e-5
+    tgt.tofile(tmp_path / "t.f32")
+    src.tofile(tmp_path / "s.f32")
+    g = np.asarray(guess, np.float32)
+    out = subprocess.run([lm_harness, str(tmp_path / "s.f32"), str(tmp_path / "t.f32"), "4", str(max_it), repr(eps), repr(dist)]
+                         + [repr(float(x)) for x in g.reshape(-1)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "mismatches=0" in out.stdout
