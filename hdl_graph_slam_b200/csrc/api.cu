@@ -649,7 +649,7 @@ static int run_single_pair(b2r_handle* h, const double* x, int mode, int tap, co
     if (report_consistent(flag, seq, w)) break;
     const unsigned long long pw = *prog;
     const int done = ((pw >> 16) == (seq & 0xffffffffffffull)) ? (int)(pw & 0xffff) : 0;
-    if (enq - done < 2 && !tap) { rc = enqueue(2); if (rc) return rc; }
+    if (enq - done < 1 && !tap) { rc = enqueue(1); if (rc) return rc; }  // the prediction fell short: keep one round ahead of the device
     if ((++spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(h->st);
       if (e != cudaSuccess && e != cudaErrorNotReady) return fail(B2R_ECUDA, std::string("stream error: ") + cudaGetErrorString(e));
@@ -704,7 +704,9 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
   // compute_error(xi) of iteration i and the linearisation linearize(xi) of iteration i+1 walk the same points at the same pose,
   // so they are one pass that writes the NEW correspondences into the other buffer set, adopted only if rho >= 0.
   const LmCfg cfg = make_lm_cfg(h->cfg, false, DBL_MAX);
-  const int predicted = h->last_rounds > 0 ? h->last_rounds + 1 : 4;
+  // enqueue as many rounds as the previous align needed (consecutive frames need the same number almost always): a finished
+  // pair's surplus rounds exit at once, a shortfall is topped up while the device works
+  const int predicted = h->last_rounds > 0 ? h->last_rounds : 5;
   rc = run_single_pair(h, x0, PM_FIRST, 0, cfg, predicted < 2 ? 2 : predicted);
   if (rc) return rc;
   const PairReport& rep = *h->h_rep;

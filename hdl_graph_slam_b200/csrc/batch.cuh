@@ -28,7 +28,7 @@ struct b2r_batch {
   PairDev* h_pairs = nullptr;       // pinned staging
   PairReport* h_reports = nullptr;  // pinned staging
   size_t h_cap = 0;
-  unsigned long long* h_word = nullptr;  // host-mapped: (seq << 32) | pairs still active
+  unsigned long long* h_word = nullptr;  // host-mapped: [0] = (seq << 32) | pairs still active, [1] = sum of the pairs' executed rounds
   unsigned long long* h_word_dev = nullptr;
   unsigned long long seq = 0;
   size_t max_chunk = 1024;  // pairs in flight per launch sequence (~7.7 MB of workspace per 64k-point pair)
@@ -95,7 +95,7 @@ extern "C" int b2r_batch_create(const b2r_config* cfg, b2r_batch** out) {
   }
   if (cudaHostAlloc(&b->h_word, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer((void**)&b->h_word_dev, b->h_word, 0) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "host allocation failed"));
-  b->h_word[0] = 0;
+  b->h_word[0] = b->h_word[1] = 0;
   if (const char* e = getenv("B2R_BATCH_COPIES")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4) b->copies = c; }
   if (const char* e = getenv("B2R_BATCH_CHUNK")) { const long c = atol(e); if (c > 0) b->max_chunk = (size_t)c; }
   *out = b;
@@ -290,7 +290,6 @@ static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const 
     int rc = launch_round(b->d_pairs.p, b->d_active.p, (unsigned)known, (unsigned)max_pad, b->copies, cfg, st, &h->tel, true);
     if (rc) return rc;
     b->last_rounds++;
-    b->last_pair_rounds += known;
     const unsigned long long sq = ++b->seq;
     {
       cudaLaunchConfig_t lc = {};
@@ -310,11 +309,11 @@ static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const 
   return B2R_OK;
 }
 
-__global__ void k_pack_results(const PairReport* rep, int n, b2r_result* out, int n_out) {
+__global__ void k_pack_results(const PairReport* rep, int n, b2r_result* out, int n_out, unsigned long long* round_sum) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_out) return;
   b2r_result r;
-  if (i < n) r = rep[i].r;
+  if (i < n) { r = rep[i].r; atomicAdd(round_sum, (unsigned long long)rep[i].rounds); }
   else { for (int k = 0; k < 16; k++) r.T[k] = 0.f; r.fitness = 0.0; r.converged = 0; r.iterations = 0; }
   out[i] = r;
 }
@@ -354,8 +353,10 @@ extern "C" int b2r_batch_align(b2r_batch* b, const b2r_pair* pairs, size_t n_pai
   B2R_CUDA(cudaMemcpyAsync(b->h_reports, b->d_reports.p, n_pairs * sizeof(PairReport), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));
   b->eng->tel.d2h += n_pairs * sizeof(PairReport);
+  b->last_pair_rounds = 0;
   for (size_t i = 0; i < n_pairs; i++) {
     out[i] = b->h_reports[i].r;
+    b->last_pair_rounds += (unsigned long long)b->h_reports[i].rounds;
     if (!want_fitness) out[i].fitness = NAN;
   }
   return B2R_OK;
@@ -442,7 +443,8 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
     b->h_gather_cap = M * (size_t)b->world;
   }
   B2R_CUDA(b->d_reports.reserve(1));
-  k_pack_results<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(b->d_reports.p, (int)mine, b->d_send.p, (int)M);
+  b->h_word[1] = 0;
+  k_pack_results<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(b->d_reports.p, (int)mine, b->d_send.p, (int)M, b->h_word_dev + 1);
   B2R_CUDA(cudaGetLastError());
   const b2r_result* gathered = b->d_send.p;
   if (b->world > 1) {
@@ -454,6 +456,7 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
   B2R_CUDA(cudaMemcpyAsync(b->h_gather, gathered, M * (size_t)b->world * sizeof(b2r_result), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));
   b->eng->tel.d2h += M * (size_t)b->world * sizeof(b2r_result);
+  b->last_pair_rounds = b->h_word[1];  // exact: every pair's own round count (the stream has been synchronised)
   for (int r = 0; r < b->world; r++)
     for (size_t i = p0[r]; i < p1[r]; i++) all_results[i] = b->h_gather[(size_t)r * M + (i - p0[r])];
   for (size_t g = 0; g < n_groups; g++) {

@@ -157,29 +157,43 @@ B2R_HD void mul3(const double* a, const double* b, double* o) {
 // ---- 6x6 host/device helpers used by the LM / Newton drivers -----------------------------------------------------
 // LDL^T solve (fast_gicp: Eigen::LDLT(H + lambda I).solve(-b)).  Returns false on a zero/NaN pivot.
 B2R_HD bool ldlt6_solve(const double* A, const double* b, double* x) {
+  // every loop has a compile-time trip count and is fully unrolled: on the device L, D, y live in registers (the LM step runs in
+  // ONE thread at the tail of k_pair_accumulate — dynamically indexed local arrays tripled its latency)
   double L[36], D[6];
+#pragma unroll
   for (int i = 0; i < 36; i++) L[i] = 0.0;
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     double d = A[j * 6 + j];
+#pragma unroll
     for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
     D[j] = d;
-    if (d == 0.0 || d != d) return false;
+    if (d == 0.0 || d != d) ok = false;
     L[j * 6 + j] = 1.0;
+#pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double s = A[i * 6 + j];
+#pragma unroll
       for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k] * D[k];
       L[i * 6 + j] = s / d;
     }
   }
+  if (!ok) return false;  // a zero / NaN pivot: the caller treats the step as not solvable (values computed past it are discarded)
   double y[6];
+#pragma unroll
   for (int i = 0; i < 6; i++) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; k++) s -= L[i * 6 + k] * y[k];
     y[i] = s;
   }
+#pragma unroll
   for (int i = 0; i < 6; i++) y[i] /= D[i];
+#pragma unroll
   for (int i = 5; i >= 0; i--) {
     double s = y[i];
+#pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * x[k];
     x[i] = s;
   }
@@ -213,14 +227,19 @@ B2R_HD void se3_exp(const double* a, double* D) {
   mul3(Om, Om, Om2);
   double V[9];
   if (theta < 1e-10) {
+#pragma unroll
     for (int i = 0; i < 9; i++) V[i] = R[i];
   } else {
     double c1 = (1.0 - cos(theta)) / theta_sq;
     double c2 = (theta - sin(theta)) / (theta_sq * theta);
+#pragma unroll
     for (int i = 0; i < 9; i++) V[i] = ((i % 4 == 0) ? 1.0 : 0.0) + c1 * Om[i] + c2 * Om2[i];
   }
+#pragma unroll
   for (int i = 0; i < 16; i++) D[i] = 0;
+#pragma unroll
   for (int r = 0; r < 3; r++) {
+#pragma unroll
     for (int c = 0; c < 3; c++) D[r * 4 + c] = R[r * 3 + c];
     D[r * 4 + 3] = V[r * 3 + 0] * a[3] + V[r * 3 + 1] * a[4] + V[r * 3 + 2] * a[5];
   }
@@ -230,7 +249,9 @@ B2R_HD void se3_exp(const double* a, double* D) {
 // Isometry product O = A * B (affine 3x4 part; last row 0 0 0 1)
 B2R_HD void mul_iso(const double* A, const double* B, double* O) {
   double T[16];
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = 0; c < 4; c++) {
       double s = A[r * 4 + 0] * B[0 * 4 + c] + A[r * 4 + 1] * B[1 * 4 + c] + A[r * 4 + 2] * B[2 * 4 + c];
       if (c == 3) s += A[r * 4 + 3];
@@ -238,12 +259,15 @@ B2R_HD void mul_iso(const double* A, const double* B, double* O) {
     }
   T[12] = T[13] = T[14] = 0;
   T[15] = 1;
+#pragma unroll
   for (int i = 0; i < 16; i++) O[i] = T[i];
 }
 
 B2R_HD bool gicp_is_converged(const double* D, double rot_eps, double trans_eps) {
   double mr = 0, mt = 0;
+#pragma unroll
   for (int r = 0; r < 3; r++) {
+#pragma unroll
     for (int c = 0; c < 3; c++) {
       double v = 1.0 / rot_eps * fabs(D[r * 4 + c] - (r == c ? 1.0 : 0.0));
       mr = v > mr ? v : mr;

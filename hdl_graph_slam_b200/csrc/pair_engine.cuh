@@ -137,24 +137,35 @@ __host__ __device__ inline void lm_publish(PairDev& p, double fitness) {
 // solve (H + lambda I) d = -b, delta = se3_exp(d), xi = delta * x0; false = singular / non-finite step
 __host__ __device__ inline bool lm_propose(PairDev& p, const LmCfg& c) {
   double A[36], nb[6], d[6];
-  int k = 0;
+#pragma unroll
   for (int r = 0; r < 6; r++)
-    for (int cc = r; cc < 6; cc++) { A[r * 6 + cc] = p.H[k]; A[cc * 6 + r] = p.H[k]; k++; }
+#pragma unroll
+    for (int cc = r; cc < 6; cc++) {
+      const double v = p.H[r * 6 - r * (r - 1) / 2 + (cc - r)];  // upper-triangle packing: row r starts at 6r - r(r-1)/2
+      A[r * 6 + cc] = v; A[cc * 6 + r] = v;
+    }
+#pragma unroll
   for (int i = 0; i < 6; i++) { A[i * 7] += p.lambda; nb[i] = -p.b[i]; }
   bool solved = ldlt6_solve(A, nb, d);
+#pragma unroll
   for (int i = 0; i < 6; i++) solved = solved && isfinite(d[i]);
   if (!solved) return false;
   double delta[16], x0[16], xi[16];
   se3_exp(d, delta);
+#pragma unroll
   for (int i = 0; i < 12; i++) x0[i] = p.x0[i];
   x0[12] = x0[13] = x0[14] = 0.0; x0[15] = 1.0;
   mul_iso(delta, x0, xi);
+#pragma unroll
   for (int i = 0; i < 12; i++) p.xe[i] = xi[i];
+#pragma unroll
   for (int i = 0; i < 6; i++) p.d[i] = d[i];
   p.delta_conv = gicp_is_converged(delta, c.rot_eps, c.trans_eps) ? 1 : 0;
   // the next linearisation exists only if this step does not converge and the iteration cap is not reached: then the trial
   // cost and the next linearize(xi) are one fused pass, otherwise only compute_error(xi) runs
   p.wc = (!p.delta_conv && (p.it + 1 < c.max_iterations)) ? 1 : 0;
+  // PM_ERR = the LAST trial of the registration unless it is rejected: with want_fitness its round also searches at xi (as the
+  // fitness round would) so an accepted final step needs no separate getFitnessScore round
   p.mode = p.wc ? PM_FUSED : PM_ERR;
   return true;
 }
@@ -200,10 +211,11 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
     lm_begin_outer(p, c);
   } else {  // PM_FUSED / PM_ERR: one LM trial has been evaluated at xe
     const double yi = r[28];
+    const bool fit_ready = (mode == PM_ERR) && c.want_fitness;  // r[0], r[1] = fitness sums at xe (valid if xe becomes the final pose)
     double den = 0.0;
     for (int i = 0; i < 6; i++) den += p.d[i] * (p.lambda * p.d[i] - p.b[i]);
     const double rho = (p.y0 - yi) / den;
-    bool outer_done = false;
+    bool outer_done = false, accepted = false;
     if (rho < 0.0) {
       if (p.delta_conv) {
         outer_done = true;  // ok = true, x0 unchanged
@@ -222,6 +234,7 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
       const double tt = 2.0 * rho - 1.0;
       const double f = 1.0 - tt * tt * tt;
       p.lambda = p.lambda * ((1.0 / 3.0 < f) ? f : 1.0 / 3.0);
+      accepted = true;
       for (int i = 0; i < 12; i++) p.x0[i] = p.xe[i];
       if (p.wc) {  // adopt the linearisation at the accepted pose: it IS the next iteration's linearize(x0)
         p.cur ^= 1;
@@ -235,6 +248,13 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
       p.converged = p.delta_conv;
       p.it++;
       lm_begin_outer(p, c);
+      // the registration ended with xe accepted as the final pose: its fitness sums are already in hand
+      if (p.mode == PM_FIT && fit_ready && accepted) {
+        p.mode = PM_DONE;
+        lm_publish(p, r[1] > 0.0 ? r[0] / r[1] : DBL_MAX);
+        if (p.progress) *reinterpret_cast<volatile unsigned long long*>(p.progress) = (p.seq << 16) | (unsigned long long)(p.rounds & 0xffff);
+        return;
+      }
     }
   }
   if (p.mode == PM_DONE) lm_publish(p, NAN);
@@ -255,7 +275,9 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, 
   if (active && (int)blockIdx.y >= active[0]) return;
   PairDev& p = pairs[active ? active[1 + blockIdx.y] : blockIdx.y];
   const int mode = p.mode;
-  if (mode != PM_FIRST && mode != PM_FUSED && mode != PM_FIT) return;
+  // PM_ERR (compute_error only) has no correspondence update; with want_fitness it runs the fitness search at the same pose
+  const bool fit_search = mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness);
+  if (mode != PM_FIRST && mode != PM_FUSED && !fit_search) return;
   constexpr int Q = 32 / C;
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   const int n_sorted = p.src.nleaf * kLeaf;
@@ -265,8 +287,8 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, 
   const int cur = p.cur;
   const int wset = (mode == PM_FIRST) ? cur : (cur ^ 1);
   const bool use_seed = mode != PM_FIRST;
-  const float lim = (mode == PM_FIT) ? cfg.fit_lim : cfg.lim;
-  const double thr2 = (mode == PM_FIT) ? (double)INFINITY : cfg.thr2;
+  const float lim = fit_search ? cfg.fit_lim : cfg.lim;
+  const double thr2 = fit_search ? (double)INFINITY : cfg.thr2;
   Bvh tgt = p.tgt;
   const float4 pt = p.src.sp[s];
   const bool is_point = idx_bits(pt.w) != kPadIdx;
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, 
   bvh_group_search<C>(tgt, qx, qy, qz, active_q, v, -1, hint);  // all 32 lanes participate
   if (is_point && writer) {
     const bool valid = active_q && (v.best_pos >= 0) && ((double)v.best_d2() < thr2);
-    if (mode != PM_FIT) p.corr[wset][idx_bits(pt.w)] = valid ? v.best_idx() : -1;
+    if (!fit_search) p.corr[wset][idx_bits(pt.w)] = valid ? v.best_idx() : -1;
     p.cpos[wset][s] = valid ? v.best_pos : -1;
     p.d2[s] = v.best_d2();
   }
@@ -334,13 +356,14 @@ __global__ void __launch_bounds__(kAccThreads, 512 / kAccThreads) k_pair_accumul
   double T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = p.xe[i];
-  if (mode == PM_FIT) {
+  if (mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness)) {
     // getFitnessScore: mean of the squared NN distances with d2 <= max_range (information_matrix_calculator.cpp:66-75)
     if (is_point && p.cpos[wset][s] >= 0) {
       const float dd = p.d2[s];
       if ((double)dd <= cfg.fit_max_range) { acc[0] = (double)dd; acc[1] = 1.0; }
     }
-  } else {
+  }
+  if (mode != PM_FIT) {
     if ((mode == PM_FUSED || mode == PM_ERR) && is_point) {  // FastGICP::compute_error at xe with the previous correspondences
       const int tp = p.cpos[cur][s];
       if (tp >= 0) {
