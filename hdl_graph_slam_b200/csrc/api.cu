@@ -39,7 +39,6 @@ struct b2r_handle {
   cudaStream_t st2 = nullptr;       // prefetch stream (upload + BVH + covariances of the next source overlap the current align)
   cudaEvent_t ev_prefetch = nullptr;
   bool prefetched = false;
-  Scratch scr;
   // per-align workspaces (sized by the source)
   DevBuf<int> corr[2], cpos[2];     // double-buffered: a speculative linearisation writes the other set
   DevBuf<float> d2;
@@ -65,13 +64,7 @@ struct b2r_handle {
   DevBuf<float> tmp_f;
   DevBuf<int> tmp_i;
   DevBuf<float4> tmp_f4;
-  struct BuildCtx {  // per-stream build scratch
-    DevBuf<unsigned int> keys_a, keys_b;
-    DevBuf<int> vals_a, vals_b;
-    DevBuf<char> sort_tmp;
-    int* mm = nullptr;
-    void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
-  } bc[2];
+  BuildCtx bc[2];                   // per-stream build scratch (main stream, prefetch stream)
   bool knn_smem_attr = false, stat_smem_attr = false;
   int n_sm = 148;
   // last result
@@ -185,7 +178,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   }
   for (int i = 0; i < 2; i++)
     if (cudaMalloc(&h->bc[i].mm, 8 * sizeof(int)) != cudaSuccess) return bail(fail(B2R_ECUDA, "device allocation failed"));
-  if (cudaMalloc(&h->scr.mm, 8 * sizeof(int)) != cudaSuccess || cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess ||
+  if (cudaMalloc(&h->d_out, 64 * sizeof(double)) != cudaSuccess ||
       cudaMalloc(&h->d_counter, 4 * sizeof(unsigned int)) != cudaSuccess || cudaHostAlloc(&h->h_out, 72 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
       cudaHostGetDevicePointer((void**)&h->h_out_dev, h->h_out, 0) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "device allocation failed"));
@@ -205,7 +198,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   cudaMemsetAsync(h->d_counter, 0, 4 * sizeof(unsigned int), h->st);
   if (cudaStreamSynchronize(h->st) != cudaSuccess) return bail(fail(B2R_ECUDA, "initialisation failed"));
   for (int i = 0; i < 16; i++) h->final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
-  h->ndt_work.scr = &h->scr;
+  h->ndt_work.bc = &h->bc[0];
   h->ndt_work.tel = &h->tel;
   h->vg_work.tel = &h->tel;
   *out = h;
@@ -233,11 +226,6 @@ extern "C" void b2r_destroy(b2r_handle* h) {
     if (h->staging[i]) cudaFreeHost(h->staging[i]);
     if (h->staging_ev[i]) cudaEventDestroy(h->staging_ev[i]);
   }
-  if (h->scr.mm) cudaFree(h->scr.mm);
-  if (h->scr.counts) cudaFree(h->scr.counts);
-  if (h->scr.cursor) cudaFree(h->scr.cursor);
-  if (h->scr.bsum) cudaFree(h->scr.bsum);
-  h->scr.cell_of.release(); h->scr.tmp_idx.release();
   for (int i = 0; i < 2; i++) { h->corr[i].release(); h->cpos[i].release(); h->mahal[i].release(); }
   h->d2.release(); h->partials.release();
   h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->bc[0].release(); h->bc[1].release();
@@ -309,7 +297,7 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
 }
 
 // builds the implicit BVH of a cloud on stream `st` with build scratch `B` (one scratch per stream)
-static int build_bvh(b2r_handle* h, Cloud& c, b2r_handle::BuildCtx& B, cudaStream_t st) {
+static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   if (c.bvh_ready) return B2R_OK;
   const size_t n = c.n;
   const int N = (int)n;
@@ -350,7 +338,7 @@ static int build_bvh(b2r_handle* h, Cloud& c, b2r_handle::BuildCtx& B, cudaStrea
 
 static int ensure_grid(b2r_handle* h, Cloud& c, int ctx = 0) { return build_bvh(h, c, h->bc[ctx], ctx ? h->st2 : h->st); }
 
-static int build_cov(b2r_handle* h, Cloud& c, b2r_handle::BuildCtx& B, cudaStream_t st) {
+static int build_cov(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   int rc = build_bvh(h, c, B, st);
   if (rc) return rc;
   if (c.cov_ready) return B2R_OK;
@@ -408,9 +396,10 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) { return build_cov(h
 static int preprocess(b2r_handle* h, int which, bool is_target) {
   Cloud& c = h->clouds[which];
   if (h->cfg.method == B2R_METHOD_GICP) return ensure_cov(h, c);
-  // NDT: the target needs the voxel Gaussians; the source needs nothing beyond the upload
+  // NDT: the target needs the voxel Gaussians; the source is put in Hilbert order (the BVH build's sorted array) so that the
+  // 128 points of a derivative block are spatial neighbours and share their voxel cells
   if (is_target) return ndt_ensure_map(h->cfg, c, h->ndt_work, h->st);
-  return B2R_OK;
+  return ensure_grid(h, c);
 }
 
 static int set_cloud(b2r_handle* h, bool is_target, const void* pts, size_t n, size_t stride, bool dev) {
@@ -589,7 +578,9 @@ static int launch_round(PairDev* d_pairs, const int* d_active, unsigned n_slots,
     la[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
     B2R_CUDA(cudaLaunchKernelEx(&lc, k_pair_accumulate, d_pairs, d_active, cfg));
-    TEL_END(tel, KC_GICP_LIN, 1, st);
+    lc.gridDim = dim3(n_slots); lc.blockDim = dim3(kLmThreads);
+    B2R_CUDA(cudaLaunchKernelEx(&lc, k_pair_lm, d_pairs, d_active, cfg));
+    TEL_END(tel, KC_GICP_LIN, 2, st);
   }
   return B2R_OK;
 }
@@ -728,7 +719,8 @@ extern "C" int b2r_align(b2r_handle* h, const float guess[16], b2r_result* out) 
     float Tfinal[16];
     bool conv = false;
     int iters = 0;
-    rc = ndt_align(h->cfg, SRC(h), TGT(h), h->ndt_work, h->st, guess, Tfinal, &conv, &iters);
+    rc = ensure_grid(h, SRC(h));  // Hilbert-ordered source points for the derivative passes
+    if (rc == B2R_OK) rc = ndt_align(h->cfg, SRC(h), TGT(h), h->ndt_work, h->st, guess, Tfinal, &conv, &iters);
     if (rc == B2R_OK) store_result(h, Tfinal, conv, iters, out);
   }
   if (rc != B2R_OK && out) {
@@ -931,6 +923,8 @@ extern "C" int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* 
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   if (SRC(h).n == 0 || TGT(h).n == 0) return fail(B2R_ESTATE, "source/target not set");
   int rc = ndt_ensure_map(h->cfg, TGT(h), h->ndt_work, h->st);
+  if (rc) return rc;
+  rc = ensure_grid(h, SRC(h));
   if (rc) return rc;
   return ndt_derivatives_at(h->cfg, SRC(h), TGT(h), h->ndt_work, h->st, p, score, g, H, n_pairs);
 }

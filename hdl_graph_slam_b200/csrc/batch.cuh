@@ -14,7 +14,7 @@ struct b2r_batch {
   b2r_handle* eng = nullptr;  // engine context of this device: config, main stream, telemetry
   static constexpr int kBuildStreams = 4;
   cudaStream_t bst[kBuildStreams] = {nullptr, nullptr, nullptr, nullptr};
-  b2r_handle::BuildCtx bctx[kBuildStreams];
+  BuildCtx bctx[kBuildStreams];
   cudaEvent_t bev[kBuildStreams] = {nullptr, nullptr, nullptr, nullptr};
   int next_stream = 0;
   std::vector<Cloud*> clouds;

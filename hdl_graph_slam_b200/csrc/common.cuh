@@ -8,19 +8,6 @@
 
 namespace b2r {
 
-// Uniform search grid over one cloud.  h is a power of two and the origin a multiple of h, so that
-// floor((p - o) * inv_h) is the exact geometric cell of p and every cell face o + k*h is exactly representable:
-// the float32 lower bounds used for pruning are then provably <= any computed float32 distance (monotone rounding).
-struct Grid {
-  float ox, oy, oz;
-  float h, inv_h;
-  int nx, ny, nz;
-  int ncell;
-  int n;        // number of points in the cloud
-  int n_valid;  // finite points (sorted array length)
-  int pad;
-};
-
 // float <-> order-preserving int (for atomicMin/atomicMax on floats)
 B2R_HD int f2ord(float f) {
   int i;
@@ -92,14 +79,5 @@ B2R_HD bool finite3(float x, float y, float z) {
 }
 
 B2R_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// cell coordinate of a coordinate value along one axis (clamped into the grid)
-B2R_HD int cell_coord(float v, float o, float inv_h, int n) {
-  float t = fmul(fsub(v, o), inv_h);
-  // floorf of huge/NaN values: clamp first in float to avoid UB in the int conversion
-  if (!(t > -1.0f)) return 0;  // also catches NaN
-  if (t >= (float)n) return n - 1;
-  return clampi((int)floorf(t), 0, n - 1);
-}
 
 }  // namespace b2r

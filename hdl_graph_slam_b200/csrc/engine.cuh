@@ -174,12 +174,13 @@ struct Cloud {
   }
 };
 
-struct Scratch {  // build scratch shared by all builds of a handle (stream-ordered); the dense tables serve the NDT voxel build only
+// per-stream build scratch (BVH builds, NDT voxel-map builds): keys / values / radix-sort space, min-max cell
+struct BuildCtx {
+  DevBuf<unsigned int> keys_a, keys_b;
+  DevBuf<int> vals_a, vals_b;
+  DevBuf<char> sort_tmp;
   int* mm = nullptr;
-  int* counts = nullptr;
-  int* cursor = nullptr;
-  int* bsum = nullptr;
-  DevBuf<int> cell_of, tmp_idx;
+  void release() { keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); sort_tmp.release(); if (mm) cudaFree(mm); mm = nullptr; }
 };
 
 }  // namespace b2r

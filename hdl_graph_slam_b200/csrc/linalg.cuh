@@ -159,9 +159,7 @@ B2R_HD void mul3(const double* a, const double* b, double* o) {
 B2R_HD bool ldlt6_solve(const double* A, const double* b, double* x) {
   // every loop has a compile-time trip count and is fully unrolled: on the device L, D, y live in registers (the LM step runs in
   // ONE thread at the tail of k_pair_accumulate — dynamically indexed local arrays tripled its latency)
-  double L[36], D[6];
-#pragma unroll
-  for (int i = 0; i < 36; i++) L[i] = 0.0;
+  double L[36], D[6];  // only the strict lower triangle of L is ever read
   bool ok = true;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
@@ -170,7 +168,6 @@ B2R_HD bool ldlt6_solve(const double* A, const double* b, double* x) {
     for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
     D[j] = d;
     if (d == 0.0 || d != d) ok = false;
-    L[j * 6 + j] = 1.0;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double s = A[i * 6 + j];

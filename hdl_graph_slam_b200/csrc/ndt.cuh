@@ -23,26 +23,40 @@ namespace b2r {
 struct VoxGeom {
   float leaf, inv_leaf;
   int min_b[3], max_b[3], div_b[3];
-  int ok;       // 0: dense table would exceed kCellCap
+  int ok;       // 0: dx*dy*dz exceeds int32 (PCL's own limit: "Leaf size is too small for the input dataset")
   int empty;    // no finite points
 };
 
-struct __align__(16) NdtVoxel {
+struct __align__(16) NdtVoxel {  // full float64 record (parity dump, float64 Hessian pass)
   double mean[3];
   double icov[9];
   int npts;     // number of points, -1 = invalidated (bad eigenvalues / infinite icov)
   int pad[3];
 };  // 112 bytes
 
+struct __align__(16) NdtCell {   // what a derivative pass reads per (point, cell): 64 bytes, staged in shared memory
+  double mean[3];
+  float icov[9];                 // (float)icov: exactly the cast ndt_omp / the oracle apply per (point, cell)
+  int npts;
+};
+static_assert(sizeof(NdtCell) == 64, "NdtCell layout");
+
+constexpr unsigned long long kNdtEmpty = 0xffffffffffffffffull;
+
+// Sparse voxel map: the reference's VoxelGridCovariance keeps its leaves in a std::map keyed by the linearised ijk, limited only by
+// int32 indices.  Here: points radix-sorted by that key, one record per occupied voxel at the sorted position of its first point,
+// and an open-addressing hash table (key -> position).  No dense table: a 200 m extent at 0.5 m resolution (16 M cells, the
+// effective setting of hdl_graph_slam_imu.launch) costs what its ~10^4 occupied voxels cost.
 struct NdtVoxelMap {
   VoxGeom* geom = nullptr;      // device
   VoxGeom h_geom;               // host copy (valid after ndt_sync_geom)
   bool h_geom_valid = false;
-  Grid* grid = nullptr;         // device (ncell / n_valid for the shared scan kernels)
-  DevBuf<int> cell_start;       // ncell + 1
+  DevBuf<unsigned int> keys;    // sorted voxel keys (n), 0xffffffff = dropped (non-finite) point
   DevBuf<float4> sorted;        // (x,y,z,bits(idx)) ascending (voxel key, index)
-  DevBuf<int> pos_of;
   DevBuf<NdtVoxel> vox;         // record of a voxel lives at the sorted position of its first point
+  DevBuf<NdtCell> cells;        // compact twin of vox
+  DevBuf<unsigned long long> table;  // (pos << 32) | key, kNdtEmpty = free
+  unsigned int mask = 0;
   size_t n = 0;
 };
 
@@ -55,10 +69,8 @@ struct NdtWork {
   unsigned long long* h_flag = nullptr; unsigned long long* h_flag_dev = nullptr; unsigned long long seq = 0;
   VoxGeom* h_geom_pinned = nullptr;
   unsigned long long* d_pairs = nullptr;
-  Scratch* scr = nullptr;         // shared build scratch of the handle (set by ndt_ensure_map's caller)
+  BuildCtx* bc = nullptr;         // build scratch of the handle's main stream (keys / values / sort space)
   Telemetry* tel = nullptr;
-  Scratch own;                    // used when no shared scratch is provided
-  bool own_init = false;
   void release() {
     partials.release();
     if (d_out) cudaFree(d_out);
@@ -66,37 +78,29 @@ struct NdtWork {
     if (h_out) cudaFreeHost(h_out);
     if (h_geom_pinned) cudaFreeHost(h_geom_pinned);
     if (d_pairs) cudaFree(d_pairs);
-    if (own_init) {
-      cudaFree(own.mm); cudaFree(own.counts); cudaFree(own.cursor); cudaFree(own.bsum);
-      own.cell_of.release(); own.tmp_idx.release();
-    }
-    d_out = nullptr; d_counter = nullptr; h_out = nullptr; h_geom_pinned = nullptr; d_pairs = nullptr; own_init = false;
+    d_out = nullptr; d_counter = nullptr; h_out = nullptr; h_geom_pinned = nullptr; d_pairs = nullptr;
   }
 };
 
 inline void ndt_free_map(NdtVoxelMap* m) {
   if (!m) return;
   if (m->geom) cudaFree(m->geom);
-  if (m->grid) cudaFree(m->grid);
-  m->cell_start.release(); m->sorted.release(); m->pos_of.release(); m->vox.release();
+  m->keys.release(); m->sorted.release(); m->vox.release(); m->cells.release(); m->table.release();
   delete m;
 }
 
 // ------------------------------------------------------------------------------------------------ voxel build kernels
 // VoxelGridCovariance::applyFilter geometry (A.3): min_b = floor(min_p * inv_leaf) ...
-__global__ void k_vox_params(const int* mm, VoxGeom* vg, Grid* g, int n, float leaf) {
+__global__ void k_vox_params(const int* mm, VoxGeom* vg, int n, float leaf) {
   VoxGeom V;
   V.leaf = leaf;
   V.inv_leaf = 1.0f / leaf;
   V.ok = 1;
   V.empty = 0;
-  Grid G;
-  G.ox = G.oy = G.oz = 0.f; G.h = leaf; G.inv_h = V.inv_leaf; G.n = n; G.n_valid = 0; G.pad = 0;
   if (n <= 0 || mm[0] == 0x7fffffff) {
     V.empty = 1;
     for (int d = 0; d < 3; d++) { V.min_b[d] = 0; V.max_b[d] = 0; V.div_b[d] = 1; }
-    G.nx = G.ny = G.nz = 1; G.ncell = 1;
-    *vg = V; *g = G;
+    *vg = V;
     return;
   }
   double cells = 1.0;
@@ -109,54 +113,63 @@ __global__ void k_vox_params(const int* mm, VoxGeom* vg, Grid* g, int n, float l
     V.div_b[d] = V.max_b[d] - V.min_b[d] + 1;
     cells *= (double)V.div_b[d];
   }
-  if (cells > (double)kCellCap) V.ok = 0;
-  if (V.ok) { G.nx = V.div_b[0]; G.ny = V.div_b[1]; G.nz = V.div_b[2]; G.ncell = G.nx * G.ny * G.nz; }
-  else { G.nx = G.ny = G.nz = 1; G.ncell = 1; }
-  *vg = V; *g = G;
+  if (cells > 2147483647.0) V.ok = 0;  // int32 linear index, as PCL
+  *vg = V;
 }
 
-__device__ __forceinline__ int vox_cell_of_point(const VoxGeom& V, float x, float y, float z) {
+__device__ __forceinline__ unsigned int vox_key_of_point(const VoxGeom& V, float x, float y, float z) {
   // ijk = (int)(floor(p * inv_leaf) - (float)min_b)   (float32, as in VoxelGridCovariance / VoxelGrid)
   int i0 = (int)fsub(floorf(fmul(x, V.inv_leaf)), (float)V.min_b[0]);
   int i1 = (int)fsub(floorf(fmul(y, V.inv_leaf)), (float)V.min_b[1]);
   int i2 = (int)fsub(floorf(fmul(z, V.inv_leaf)), (float)V.min_b[2]);
   i0 = clampi(i0, 0, V.div_b[0] - 1); i1 = clampi(i1, 0, V.div_b[1] - 1); i2 = clampi(i2, 0, V.div_b[2] - 1);
-  return i0 + i1 * V.div_b[0] + i2 * V.div_b[0] * V.div_b[1];
+  return (unsigned int)i0 + (unsigned int)i1 * (unsigned int)V.div_b[0] + (unsigned int)i2 * (unsigned int)V.div_b[0] * (unsigned int)V.div_b[1];
 }
 
-__global__ void k_count_vox(const float* __restrict__ raw, int stride_f, int n, const VoxGeom* __restrict__ vg, int* counts, int* cell_of) {
+__global__ void k_vox_keys(const float* __restrict__ raw, int stride_f, int n, const VoxGeom* __restrict__ vg, unsigned int* keys, int* vals) {
   const VoxGeom V = *vg;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* p = raw + (size_t)i * stride_f;
-    float x = p[0], y = p[1], z = p[2];
-    int c = -1;
-    if (finite3(x, y, z)) {
-      c = V.ok ? vox_cell_of_point(V, x, y, z) : 0;
-      atomicAdd(&counts[c], 1);
-    }
-    cell_of[i] = c;
+    const float x = p[0], y = p[1], z = p[2];
+    unsigned int k = 0xffffffffu;  // dropped points sort last
+    if (finite3(x, y, z)) k = V.ok ? vox_key_of_point(V, x, y, z) : 0u;
+    keys[i] = k;
+    vals[i] = i;
   }
 }
 
-// One thread per voxel (the thread whose sorted position is the voxel's first point): sequential float64 moments in
-// ascending point index, then the finalisation of VoxelGridCovariance::applyFilter.
-__global__ void k_vox_finalize(const Grid* __restrict__ gp, const int* __restrict__ cell_of, const int* __restrict__ cell_start,
-                               const float4* __restrict__ sorted, NdtVoxel* vox, int n) {
+__global__ void k_vox_gather(const float* __restrict__ raw, int stride_f, int n, const unsigned int* __restrict__ keys_sorted, const int* __restrict__ vals_sorted,
+                             float4* sorted) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+    const int i = vals_sorted[s];
+    const float* p = raw + (size_t)i * stride_f;
+    sorted[s] = (keys_sorted[s] != 0xffffffffu) ? make_float4(p[0], p[1], p[2], bits_idx(i)) : make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  }
+}
+
+__device__ __forceinline__ unsigned int ndt_hash(unsigned int key) {
+  key ^= key >> 16; key *= 0x7feb352du; key ^= key >> 15; key *= 0x846ca68bu; key ^= key >> 16;
+  return key;
+}
+
+// One thread per voxel (the thread at the sorted position of the voxel's first point): sequential float64 moments in
+// ascending point index, the finalisation of VoxelGridCovariance::applyFilter, and the hash-table insert.
+__global__ void k_vox_finalize(const unsigned int* __restrict__ keys_sorted, const float4* __restrict__ sorted, NdtVoxel* vox, NdtCell* cells,
+                               unsigned long long* table, unsigned int mask, int n) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= gp->n_valid) return;
-  const float4 p0 = sorted[s];
-  const int c = cell_of[idx_bits(p0.w)];
-  const int b = cell_start[c];
-  if (b != s) return;
-  const int e = cell_start[c + 1];
-  const int cnt = e - b;
+  if (s >= n) return;
+  const unsigned int key = keys_sorted[s];
+  if (key == 0xffffffffu) return;
+  if (s > 0 && keys_sorted[s - 1] == key) return;  // not the first point of its voxel
+  int cnt = 0;
   double sx = 0, sy = 0, sz = 0, cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
-  for (int j = b; j < e; j++) {
+  for (int j = s; j < n && keys_sorted[j] == key; j++) {
     const float4 p = sorted[j];
     const double x = (double)p.x, y = (double)p.y, z = (double)p.z;
     sx += x; sy += y; sz += z;
     // products of two float32 values are exact in float64, so contraction cannot change these sums
     cxx += x * x; cxy += x * y; cxz += x * z; cyy += y * y; cyz += y * z; czz += z * z;
+    cnt++;
   }
   NdtVoxel R;
   const double nn = (double)cnt;
@@ -205,18 +218,30 @@ __global__ void k_vox_finalize(const Grid* __restrict__ gp, const int* __restric
     }
   }
   vox[s] = R;
+  NdtCell C;
+  C.mean[0] = R.mean[0]; C.mean[1] = R.mean[1]; C.mean[2] = R.mean[2];
+#pragma unroll
+  for (int k = 0; k < 9; k++) C.icov[k] = (float)R.icov[k];
+  C.npts = R.npts;
+  cells[s] = C;
+  // insert (key -> s): every key is inserted exactly once, so the first free slot of the probe sequence is taken with one CAS
+  const unsigned long long entry = ((unsigned long long)(unsigned int)s << 32) | (unsigned long long)key;
+  unsigned int h = ndt_hash(key) & mask;
+  while (atomicCAS(table + h, kNdtEmpty, entry) != kNdtEmpty) h = (h + 1) & mask;
 }
 
 // ------------------------------------------------------------------------------------------------ derivative kernel
 constexpr int kNdtThreads = 128;
-constexpr int kNdtAcc = 43;  // score, g[6], H[36]
+constexpr int kNdtAcc = 28;    // score, g[6], upper triangle of H (21)
+constexpr int kNdtSlots = 320; // voxel records staged per block (20 KB)
 
 struct NdtArgs {
-  const float* src_raw;
-  int src_stride_f;
-  int n;
+  const float4* src;           // the source's Hilbert-sorted points (bvh.cuh): a block's 128 points are spatial neighbours
+  int n_sorted;
   const VoxGeom* geom;
-  const int* cell_start;
+  const unsigned long long* table;
+  unsigned int mask;
+  const NdtCell* cells;
   const NdtVoxel* vox;
   float Tf[12];
   float jang[8][3];
@@ -240,126 +265,186 @@ __device__ __forceinline__ float dot3f(const float* a, float x, float y, float z
 
 __constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
 
-#ifndef B2R_NDT_MINBLOCKS
-#define B2R_NDT_MINBLOCKS 3
-#endif
-__global__ void __launch_bounds__(kNdtThreads, B2R_NDT_MINBLOCKS) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
+// VoxelGridCovariance::getNeighborhoodAtPoint's leaf lookup: in-bounds test against min_b / max_b, then leaves_.find(idx).
+// Returns the position of the voxel record or -1.
+__device__ __forceinline__ int ndt_find(const unsigned long long* __restrict__ table, unsigned int mask, const VoxGeom& V, int cx, int cy, int cz) {
+  if (cx < V.min_b[0] || cx > V.max_b[0] || cy < V.min_b[1] || cy > V.max_b[1] || cz < V.min_b[2] || cz > V.max_b[2]) return -1;
+  const unsigned int key = (unsigned int)(cx - V.min_b[0]) + (unsigned int)(cy - V.min_b[1]) * (unsigned int)V.div_b[0] +
+                           (unsigned int)(cz - V.min_b[2]) * (unsigned int)V.div_b[0] * (unsigned int)V.div_b[1];
+  unsigned int h = ndt_hash(key) & mask;
+  for (;;) {
+    const unsigned long long e = __ldg(table + h);
+    if ((unsigned int)e == key) return (int)(e >> 32);
+    if (e == kNdtEmpty) return -1;
+    h = (h + 1) & mask;
+  }
+}
+
+// computeDerivatives (DIRECT1 / DIRECT7) over the Hilbert-sorted source.  A block's 128 points are neighbours in space, so
+// the voxel records they need (<= 7 per point) form a small box of cells: the block looks every cell of that box up ONCE,
+// stages the 64-byte records in shared memory, and the per-(point, cell) loop then runs without a global load.  Blocks
+// whose points are spread too wide for the staging area (far-field leaves, jumps of the curve) fall back to direct lookups.
+template <bool HESS>
+__global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
+  __shared__ NdtCell s_cell[kNdtSlots];
   __shared__ double red[kNdtAcc * 32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_box[6];
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   double acc[kNdtAcc];
 #pragma unroll
   for (int k = 0; k < kNdtAcc; k++) acc[k] = 0.0;
   unsigned int npairs = 0;
-  if (i < A.n) {
-    const VoxGeom V = *A.geom;
-    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
-    const float x = p[0], y = p[1], z = p[2];
-    const float xt = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], x, y, z);
-    const float yt = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], x, y, z);
-    const float zt = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], x, y, z);
-    if (!V.empty && V.ok && finite3(xt, yt, zt)) {
+  const VoxGeom V = *A.geom;
+  float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  if (s < A.n_sorted) pt = A.src[s];
+  const float x = pt.x, y = pt.y, z = pt.z;
+  float xt = 0.f, yt = 0.f, zt = 0.f;
+  int ci = 0, cj = 0, ck = 0;
+  bool valid = false;
+  if (idx_bits(pt.w) != kPadIdx && !V.empty && V.ok) {
+    xt = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], x, y, z);
+    yt = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], x, y, z);
+    zt = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], x, y, z);
+    if (finite3(xt, yt, zt)) {
       // getNeighborhoodAtPoint{1,7}: ijk = floor(pt / leaf)   (float32 DIVISION here, multiply-by-inverse at build)
       const float fi = floorf(__fdiv_rn(xt, V.leaf)), fj = floorf(__fdiv_rn(yt, V.leaf)), fk = floorf(__fdiv_rn(zt, V.leaf));
-      if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f && fabsf(fk) < 1.0e9f) {
-        const int ci = (int)fi, cj = (int)fj, ck = (int)fk;
-        bool have_pd = false;
-        float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
-        float ha1 = 0, ha2 = 0, hb1 = 0, hb2 = 0, hc1 = 0, hc2 = 0, hd0 = 0, hd1 = 0, hd2 = 0, he0 = 0, he1 = 0, he2 = 0, hf0 = 0, hf1 = 0, hf2 = 0;
-        const float d2f = (float)A.d2;
-        for (int c = 0; c < A.ncell_search; c++) {
-          const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
-          if (cx < V.min_b[0] || cx > V.max_b[0] || cy < V.min_b[1] || cy > V.max_b[1] || cz < V.min_b[2] || cz > V.max_b[2]) continue;
-          const int cell = (cx - V.min_b[0]) + (cy - V.min_b[1]) * V.div_b[0] + (cz - V.min_b[2]) * V.div_b[0] * V.div_b[1];
-          const int s = A.cell_start[cell], e = A.cell_start[cell + 1];
-          if (e - s < 6) continue;
-          const NdtVoxel* L = A.vox + s;
-          if (L->npts < 6) continue;
-          npairs++;
-          if (!have_pd) {  // computePointDerivatives(x): original point only
-            j13 = dot3f(A.jang[0], x, y, z); j23 = dot3f(A.jang[1], x, y, z);
-            j04 = dot3f(A.jang[2], x, y, z); j14 = dot3f(A.jang[3], x, y, z); j24 = dot3f(A.jang[4], x, y, z);
-            j05 = dot3f(A.jang[5], x, y, z); j15 = dot3f(A.jang[6], x, y, z); j25 = dot3f(A.jang[7], x, y, z);
-            if (A.compute_hessian) {
-              ha1 = dot3f(A.hang[0], x, y, z); ha2 = dot3f(A.hang[1], x, y, z);
-              hb1 = dot3f(A.hang[2], x, y, z); hb2 = dot3f(A.hang[3], x, y, z);
-              hc1 = dot3f(A.hang[4], x, y, z); hc2 = dot3f(A.hang[5], x, y, z);
-              hd0 = dot3f(A.hang[6], x, y, z); hd1 = dot3f(A.hang[7], x, y, z); hd2 = dot3f(A.hang[8], x, y, z);
-              he0 = dot3f(A.hang[9], x, y, z); he1 = dot3f(A.hang[10], x, y, z); he2 = dot3f(A.hang[11], x, y, z);
-              hf0 = dot3f(A.hang[12], x, y, z); hf1 = dot3f(A.hang[13], x, y, z); hf2 = dot3f(A.hang[14], x, y, z);
-            }
-            have_pd = true;
-          }
-          const float q0 = (float)((double)xt - L->mean[0]), q1 = (float)((double)yt - L->mean[1]), q2 = (float)((double)zt - L->mean[2]);
-          float C[9];
+      if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f && fabsf(fk) < 1.0e9f) { ci = (int)fi; cj = (int)fj; ck = (int)fk; valid = true; }
+    }
+  }
+  // ---- the block's box of base cells (+-1 for the face neighbours)
+  if (threadIdx.x < 6) s_box[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
+  __syncthreads();
+  {
+    int lo0 = valid ? ci : 0x7fffffff, lo1 = valid ? cj : 0x7fffffff, lo2 = valid ? ck : 0x7fffffff;
+    int hi0 = valid ? ci : (int)0x80000000, hi1 = valid ? cj : (int)0x80000000, hi2 = valid ? ck : (int)0x80000000;
+    lo0 = __reduce_min_sync(0xffffffffu, lo0); lo1 = __reduce_min_sync(0xffffffffu, lo1); lo2 = __reduce_min_sync(0xffffffffu, lo2);
+    hi0 = __reduce_max_sync(0xffffffffu, hi0); hi1 = __reduce_max_sync(0xffffffffu, hi1); hi2 = __reduce_max_sync(0xffffffffu, hi2);
+    if (lane == 0 && lo0 <= hi0) {
+      atomicMin(&s_box[0], lo0); atomicMin(&s_box[1], lo1); atomicMin(&s_box[2], lo2);
+      atomicMax(&s_box[3], hi0); atomicMax(&s_box[4], hi1); atomicMax(&s_box[5], hi2);
+    }
+  }
+  __syncthreads();
+  const bool any = s_box[0] <= s_box[3];
+  const int bx0 = s_box[0] - 1, by0 = s_box[1] - 1, bz0 = s_box[2] - 1;
+  const long long ex = any ? (long long)s_box[3] - s_box[0] + 3 : 0, ey = any ? (long long)s_box[4] - s_box[1] + 3 : 0, ez = any ? (long long)s_box[5] - s_box[2] + 3 : 0;
+  const bool staged = any && ex <= kNdtSlots && ey <= kNdtSlots && ez <= kNdtSlots && ex * ey * ez <= kNdtSlots;
+  const int dx = (int)ex, dxy = (int)(ex * ey);
+  if (staged) {
+    const int vol = dxy * (int)ez;
+    for (int slot = threadIdx.x; slot < vol; slot += blockDim.x) {
+      const int cz = slot / dxy, r = slot - cz * dxy, cy = r / dx, cx = r - cy * dx;
+      const int pos = ndt_find(A.table, A.mask, V, bx0 + cx, by0 + cy, bz0 + cz);
+      if (pos >= 0) {
+        const uint4* g = reinterpret_cast<const uint4*>(A.cells + pos);
+        uint4* d = reinterpret_cast<uint4*>(&s_cell[slot]);
+        d[0] = __ldg(g); d[1] = __ldg(g + 1); d[2] = __ldg(g + 2); d[3] = __ldg(g + 3);
+      } else {
+        s_cell[slot].npts = -1;
+      }
+    }
+  }
+  __syncthreads();
+  if (valid) {
+    bool have_pd = false;
+    float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
+    float ha1 = 0, ha2 = 0, hb1 = 0, hb2 = 0, hc1 = 0, hc2 = 0, hd0 = 0, hd1 = 0, hd2 = 0, he0 = 0, he1 = 0, he2 = 0, hf0 = 0, hf1 = 0, hf2 = 0;
+    const float d2f = (float)A.d2;
+    for (int c = 0; c < A.ncell_search; c++) {
+      const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
+      const NdtCell* L;
+      if (staged) {
+        L = &s_cell[(cx - bx0) + (cy - by0) * dx + (cz - bz0) * dxy];
+      } else {
+        const int pos = ndt_find(A.table, A.mask, V, cx, cy, cz);
+        if (pos < 0) continue;
+        L = A.cells + pos;
+      }
+      if (L->npts < 6) continue;  // fewer than min_points_per_voxel, or invalidated (bad eigenvalues / infinite icov)
+      npairs++;
+      if (!have_pd) {  // computePointDerivatives(x): original point only
+        j13 = dot3f(A.jang[0], x, y, z); j23 = dot3f(A.jang[1], x, y, z);
+        j04 = dot3f(A.jang[2], x, y, z); j14 = dot3f(A.jang[3], x, y, z); j24 = dot3f(A.jang[4], x, y, z);
+        j05 = dot3f(A.jang[5], x, y, z); j15 = dot3f(A.jang[6], x, y, z); j25 = dot3f(A.jang[7], x, y, z);
+        if (HESS) {
+          ha1 = dot3f(A.hang[0], x, y, z); ha2 = dot3f(A.hang[1], x, y, z);
+          hb1 = dot3f(A.hang[2], x, y, z); hb2 = dot3f(A.hang[3], x, y, z);
+          hc1 = dot3f(A.hang[4], x, y, z); hc2 = dot3f(A.hang[5], x, y, z);
+          hd0 = dot3f(A.hang[6], x, y, z); hd1 = dot3f(A.hang[7], x, y, z); hd2 = dot3f(A.hang[8], x, y, z);
+          he0 = dot3f(A.hang[9], x, y, z); he1 = dot3f(A.hang[10], x, y, z); he2 = dot3f(A.hang[11], x, y, z);
+          hf0 = dot3f(A.hang[12], x, y, z); hf1 = dot3f(A.hang[13], x, y, z); hf2 = dot3f(A.hang[14], x, y, z);
+        }
+        have_pd = true;
+      }
+      const float q0 = (float)((double)xt - L->mean[0]), q1 = (float)((double)yt - L->mean[1]), q2 = (float)((double)zt - L->mean[2]);
+      float C[9];
 #pragma unroll
-          for (int k = 0; k < 9; k++) C[k] = (float)L->icov[k];
-          // qC = q^T C ; gq[0..2] == qC
-          float gq[6];
+      for (int k = 0; k < 9; k++) C[k] = L->icov[k];
+      // qC = q^T C ; gq[0..2] == qC
+      float gq[6];
 #pragma unroll
-          for (int j = 0; j < 3; j++) gq[j] = fadd(fadd(fmul(q0, C[0 * 3 + j]), fmul(q1, C[1 * 3 + j])), fmul(q2, C[2 * 3 + j]));
-          const float qCq = fadd(fadd(fmul(q0, gq[0]), fmul(q1, gq[1])), fmul(q2, gq[2]));
-          const float arg = fmul(fmul(-d2f, qCq), 0.5f);
-          float ex = (float)exp((double)arg);
-          const float score_inc = (float)(-A.d1 * (double)ex);
-          ex = fmul(d2f, ex);
-          if (ex > 1.f || ex < 0.f || ex != ex) continue;  // contributes nothing (score_inc dropped as well)
-          ex = (float)((double)ex * A.d1);
-          // CJ columns 3..5 (columns 0..2 are C itself)
-          float CJ3[3], CJ4[3], CJ5[3];
+      for (int j = 0; j < 3; j++) gq[j] = fadd(fadd(fmul(q0, C[0 * 3 + j]), fmul(q1, C[1 * 3 + j])), fmul(q2, C[2 * 3 + j]));
+      const float qCq = fadd(fadd(fmul(q0, gq[0]), fmul(q1, gq[1])), fmul(q2, gq[2]));
+      const float arg = fmul(fmul(-d2f, qCq), 0.5f);
+      float exv = (float)exp((double)arg);
+      const float score_inc = (float)(-A.d1 * (double)exv);
+      exv = fmul(d2f, exv);
+      if (exv > 1.f || exv < 0.f || exv != exv) continue;  // contributes nothing (score_inc dropped as well)
+      exv = (float)((double)exv * A.d1);
+      // CJ columns 3..5 (columns 0..2 are C itself)
+      float CJ3[3], CJ4[3], CJ5[3];
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            CJ3[r] = fadd(fmul(C[r * 3 + 1], j13), fmul(C[r * 3 + 2], j23));
-            CJ4[r] = fadd(fadd(fmul(C[r * 3 + 0], j04), fmul(C[r * 3 + 1], j14)), fmul(C[r * 3 + 2], j24));
-            CJ5[r] = fadd(fadd(fmul(C[r * 3 + 0], j05), fmul(C[r * 3 + 1], j15)), fmul(C[r * 3 + 2], j25));
-          }
-          gq[3] = fadd(fadd(fmul(q0, CJ3[0]), fmul(q1, CJ3[1])), fmul(q2, CJ3[2]));
-          gq[4] = fadd(fadd(fmul(q0, CJ4[0]), fmul(q1, CJ4[1])), fmul(q2, CJ4[2]));
-          gq[5] = fadd(fadd(fmul(q0, CJ5[0]), fmul(q1, CJ5[1])), fmul(q2, CJ5[2]));
-          acc[0] += (double)score_inc;
+      for (int r = 0; r < 3; r++) {
+        CJ3[r] = fadd(fmul(C[r * 3 + 1], j13), fmul(C[r * 3 + 2], j23));
+        CJ4[r] = fadd(fadd(fmul(C[r * 3 + 0], j04), fmul(C[r * 3 + 1], j14)), fmul(C[r * 3 + 2], j24));
+        CJ5[r] = fadd(fadd(fmul(C[r * 3 + 0], j05), fmul(C[r * 3 + 1], j15)), fmul(C[r * 3 + 2], j25));
+      }
+      gq[3] = fadd(fadd(fmul(q0, CJ3[0]), fmul(q1, CJ3[1])), fmul(q2, CJ3[2]));
+      gq[4] = fadd(fadd(fmul(q0, CJ4[0]), fmul(q1, CJ4[1])), fmul(q2, CJ4[2]));
+      gq[5] = fadd(fadd(fmul(q0, CJ5[0]), fmul(q1, CJ5[1])), fmul(q2, CJ5[2]));
+      acc[0] += (double)score_inc;
 #pragma unroll
-          for (int k = 0; k < 6; k++) acc[1 + k] += (double)fmul(ex, gq[k]);
-          if (A.compute_hessian) {
-            // P[a][b] = J[:,a] . CJ[:,b]
-            // CJ[r][b]: b<3 -> C[r][b]; b=3 -> CJ3[r]; b=4 -> CJ4[r]; b=5 -> CJ5[r]
+      for (int k = 0; k < 6; k++) acc[1 + k] += (double)fmul(exv, gq[k]);
+      if (HESS) {
+        // H(ii, jj) for ii <= jj only (the lower triangle is mirrored on the host; float32 rounding makes ndt_omp's own two
+        // halves differ by ~1e-8 relative per term — see DESIGN.md).  The term J_jj^T C J_ii is P[jj][ii] with
+        // P[a][b] = J[:,a] . CJ[:,b], CJ[r][b]: b<3 -> C[r][b]; b=3 -> CJ3[r]; b=4 -> CJ4[r]; b=5 -> CJ5[r]
 #define B2R_CJ(r, b) ((b) < 3 ? C[(r) * 3 + (b)] : ((b) == 3 ? CJ3[r] : ((b) == 4 ? CJ4[r] : CJ5[r])))
-            float P[6][6];
+        // second-derivative terms qC . v_ij  (i,j in 3..5); a=(0,ha1,ha2) b=(0,hb1,hb2) c=(0,hc1,hc2) d,e,f full
+        const float xa = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], ha1)), fmul(gq[2], ha2));
+        const float xb = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hb1)), fmul(gq[2], hb2));
+        const float xc = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hc1)), fmul(gq[2], hc2));
+        const float xd = fadd(fadd(fmul(gq[0], hd0), fmul(gq[1], hd1)), fmul(gq[2], hd2));
+        const float xe = fadd(fadd(fmul(gq[0], he0), fmul(gq[1], he1)), fmul(gq[2], he2));
+        const float xf = fadd(fadd(fmul(gq[0], hf0), fmul(gq[1], hf1)), fmul(gq[2], hf2));
+        const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
+        int hk = 7;
 #pragma unroll
-            for (int b = 0; b < 6; b++) {
-              P[0][b] = B2R_CJ(0, b);
-              P[1][b] = B2R_CJ(1, b);
-              P[2][b] = B2R_CJ(2, b);
-              P[3][b] = fadd(fmul(j13, B2R_CJ(1, b)), fmul(j23, B2R_CJ(2, b)));
-              P[4][b] = fadd(fadd(fmul(j04, B2R_CJ(0, b)), fmul(j14, B2R_CJ(1, b))), fmul(j24, B2R_CJ(2, b)));
-              P[5][b] = fadd(fadd(fmul(j05, B2R_CJ(0, b)), fmul(j15, B2R_CJ(1, b))), fmul(j25, B2R_CJ(2, b)));
-            }
-#undef B2R_CJ
-            // second-derivative terms qC . v_ij  (i,j in 3..5); a=(0,ha1,ha2) b=(0,hb1,hb2) c=(0,hc1,hc2) d,e,f full
-            const float xa = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], ha1)), fmul(gq[2], ha2));
-            const float xb = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hb1)), fmul(gq[2], hb2));
-            const float xc = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hc1)), fmul(gq[2], hc2));
-            const float xd = fadd(fadd(fmul(gq[0], hd0), fmul(gq[1], hd1)), fmul(gq[2], hd2));
-            const float xe = fadd(fadd(fmul(gq[0], he0), fmul(gq[1], he1)), fmul(gq[2], he2));
-            const float xf = fadd(fadd(fmul(gq[0], hf0), fmul(gq[1], hf1)), fmul(gq[2], hf2));
-            const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
+        for (int ii = 0; ii < 6; ii++) {
 #pragma unroll
-            for (int ii = 0; ii < 6; ii++) {
-#pragma unroll
-              for (int jj = 0; jj < 6; jj++) {
-                float u = fmul(fmul(-d2f, gq[ii]), gq[jj]);
-                const float xh = (ii >= 3 && jj >= 3) ? XH[ii - 3][jj - 3] : 0.f;
-                u = fadd(u, xh);
-                u = fadd(u, P[jj][ii]);
-                acc[7 + ii * 6 + jj] += (double)fmul(ex, u);
-              }
-            }
+          for (int jj = ii; jj < 6; jj++) {
+            float u = fmul(fmul(-d2f, gq[ii]), gq[jj]);
+            const float xh = (ii >= 3 && jj >= 3) ? XH[ii - 3][jj - 3] : 0.f;
+            u = fadd(u, xh);
+            // P[jj][ii], jj >= ii
+            float pj;
+            if (jj < 3) pj = B2R_CJ(jj, ii);
+            else if (jj == 3) pj = fadd(fmul(j13, B2R_CJ(1, ii)), fmul(j23, B2R_CJ(2, ii)));
+            else if (jj == 4) pj = fadd(fadd(fmul(j04, B2R_CJ(0, ii)), fmul(j14, B2R_CJ(1, ii))), fmul(j24, B2R_CJ(2, ii)));
+            else pj = fadd(fadd(fmul(j05, B2R_CJ(0, ii)), fmul(j15, B2R_CJ(1, ii))), fmul(j25, B2R_CJ(2, ii)));
+            u = fadd(u, pj);
+            acc[hk] += (double)fmul(exv, u);
+            hk++;
           }
         }
+#undef B2R_CJ
       }
     }
   }
   // pair count (integer, exact) through a warp reduction + one atomic per warp
-  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-  if ((threadIdx.x & 31) == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
+  npairs = __reduce_add_sync(0xffffffffu, npairs);
+  if (lane == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
   block_reduce<kNdtAcc>(acc, red);
   finish_partials<kNdtAcc>(acc, A.partials, A.out, A.counter, A.flag, A.seq, A.pairs);
 }
@@ -367,14 +452,15 @@ __global__ void __launch_bounds__(kNdtThreads, B2R_NDT_MINBLOCKS) k_ndt_derivati
 // float64 Hessian-only pass (ndt_omp computeHessian/updateHessian)
 __global__ void __launch_bounds__(kNdtThreads) k_ndt_hessian(const __grid_constant__ NdtArgs A) {
   __shared__ double red[36 * 32];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   double acc[36];
 #pragma unroll
   for (int k = 0; k < 36; k++) acc[k] = 0.0;
-  if (i < A.n) {
+  float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
+  if (s < A.n_sorted) pt = A.src[s];
+  if (idx_bits(pt.w) != kPadIdx) {
     const VoxGeom V = *A.geom;
-    const float* p = A.src_raw + (size_t)i * A.src_stride_f;
-    const float xf = p[0], yf = p[1], zf = p[2];
+    const float xf = pt.x, yf = pt.y, zf = pt.z;
     const float xt = xform_row(A.Tf[0], A.Tf[1], A.Tf[2], A.Tf[3], xf, yf, zf);
     const float yt = xform_row(A.Tf[4], A.Tf[5], A.Tf[6], A.Tf[7], xf, yf, zf);
     const float zt = xform_row(A.Tf[8], A.Tf[9], A.Tf[10], A.Tf[11], xf, yf, zf);
@@ -393,12 +479,9 @@ __global__ void __launch_bounds__(kNdtThreads) k_ndt_hessian(const __grid_consta
 #undef B2R_DJ
 #undef B2R_DH
         for (int c = 0; c < A.ncell_search; c++) {
-          const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
-          if (cx < V.min_b[0] || cx > V.max_b[0] || cy < V.min_b[1] || cy > V.max_b[1] || cz < V.min_b[2] || cz > V.max_b[2]) continue;
-          const int cell = (cx - V.min_b[0]) + (cy - V.min_b[1]) * V.div_b[0] + (cz - V.min_b[2]) * V.div_b[0] * V.div_b[1];
-          const int s = A.cell_start[cell], e = A.cell_start[cell + 1];
-          if (e - s < 6) continue;
-          const NdtVoxel* L = A.vox + s;
+          const int pos = ndt_find(A.table, A.mask, V, ci + c_off7[c][0], cj + c_off7[c][1], ck + c_off7[c][2]);
+          if (pos < 0) continue;
+          const NdtVoxel* L = A.vox + pos;
           if (L->npts < 6) continue;
           const double q[3] = {(double)xt - L->mean[0], (double)yt - L->mean[1], (double)zt - L->mean[2]};
           const double* C = L->icov;
@@ -455,48 +538,44 @@ inline int ndt_ensure_map(const b2r_config& cfg, Cloud& c, NdtWork& W, cudaStrea
   if (c.ndt_ready) return B2R_OK;
   int rc = ndt_init_work(W);
   if (rc) return rc;
-  Scratch* S = W.scr;
-  if (!S) return fail(B2R_ESTATE, "internal: NDT scratch not attached");
-  if (!S->counts) {  // dense voxel tables: allocated on first NDT use only (GICP handles stay light)
-    B2R_CUDA(cudaMalloc(&S->counts, (size_t)kCellCap * sizeof(int)));
-    B2R_CUDA(cudaMalloc(&S->cursor, (size_t)kCellCap * sizeof(int)));
-    B2R_CUDA(cudaMalloc(&S->bsum, (size_t)kScanBlocks * sizeof(int)));
-    B2R_CUDA(cudaMemsetAsync(S->counts, 0, (size_t)kCellCap * sizeof(int), st));
-  }
+  BuildCtx* B = W.bc;
+  if (!B) return fail(B2R_ESTATE, "internal: NDT build scratch not attached");
   if (!c.ndt) {
     c.ndt = new NdtVoxelMap();
     B2R_CUDA(cudaMalloc(&c.ndt->geom, sizeof(VoxGeom)));
-    B2R_CUDA(cudaMalloc(&c.ndt->grid, sizeof(Grid)));
-    B2R_CUDA(c.ndt->cell_start.reserve(kCellCap + 1 - 72));
   }
   NdtVoxelMap& M = *c.ndt;
   const int n = (int)c.n;
   M.n = c.n;
   M.h_geom_valid = false;
+  size_t tsize = 1024;
+  while (tsize < 2 * c.n) tsize <<= 1;
+  M.mask = (unsigned int)(tsize - 1);
+  B2R_CUDA(M.keys.reserve(c.n + 1));
   B2R_CUDA(M.sorted.reserve(c.n + 1));
-  B2R_CUDA(M.pos_of.reserve(c.n + 1));
   B2R_CUDA(M.vox.reserve(c.n + 1));
-  B2R_CUDA(S->cell_of.reserve(c.n + 1));
-  B2R_CUDA(S->tmp_idx.reserve(c.n + 1));
+  B2R_CUDA(M.cells.reserve(c.n + 1));
+  B2R_CUDA(M.table.reserve(tsize));
+  B2R_CUDA(B->keys_a.reserve(c.n + 1)); B2R_CUDA(B->vals_a.reserve(c.n + 1)); B2R_CUDA(B->vals_b.reserve(c.n + 1));
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, B->keys_a.p, M.keys.p, B->vals_a.p, B->vals_b.p, n, 0, 32, st);
+  B2R_CUDA(B->sort_tmp.reserve(tmp_bytes + 256));
   TEL_BEGIN(W.tel, st);
-  k_grid_reset<<<1, 32, 0, st>>>(S->mm);
+  k_grid_reset<<<1, 32, 0, st>>>(B->mm);
   int nb = n > 0 ? (n + 255) / 256 : 1;
   if (nb > 1184) nb = 1184;
-  if (n > 0) k_bbox<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, S->mm);
-  k_vox_params<<<1, 1, 0, st>>>(S->mm, M.geom, M.grid, n, (float)cfg.ndt_resolution);
+  if (n > 0) k_bbox<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, B->mm);
+  k_vox_params<<<1, 1, 0, st>>>(B->mm, M.geom, n, (float)cfg.ndt_resolution);
+  B2R_CUDA(cudaMemsetAsync(M.table.p, 0xff, tsize * sizeof(unsigned long long), st));
   if (n > 0) {
-    k_fill_i32<<<nb, 256, 0, st>>>(M.pos_of.p, n, -1);
-    k_count_vox<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.geom, S->counts, S->cell_of.p);
+    k_vox_keys<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.geom, B->keys_a.p, B->vals_a.p);
+    size_t tb = B->sort_tmp.cap;
+    // stable LSD radix sort by voxel key: inside a voxel the points stay in ascending index, the order the moments are summed in
+    cub::DeviceRadixSort::SortPairs(B->sort_tmp.p, tb, B->keys_a.p, M.keys.p, B->vals_a.p, B->vals_b.p, n, 0, 32, st);
+    k_vox_gather<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.keys.p, B->vals_b.p, M.sorted.p);
+    k_vox_finalize<<<(n + 127) / 128, 128, 0, st>>>(M.keys.p, M.sorted.p, M.vox.p, M.cells.p, M.table.p, M.mask, n);
   }
-  k_scan_a<<<kScanBlocks, kScanThreads, 0, st>>>(S->counts, M.grid, S->bsum);
-  k_scan_b<<<1, 1024, 0, st>>>(S->bsum, M.grid, M.cell_start.p);
-  k_scan_c<<<kScanBlocks, kScanThreads, 0, st>>>(S->counts, M.grid, S->bsum, M.cell_start.p, S->cursor);
-  if (n > 0) {
-    k_scatter<<<nb, 256, 0, st>>>(n, S->cell_of.p, S->cursor, S->tmp_idx.p);
-    k_canon<<<nb, 256, 0, st>>>(c.raw_view, c.stride_f, n, M.grid, S->cell_of.p, M.cell_start.p, S->tmp_idx.p, M.sorted.p, M.pos_of.p);
-    k_vox_finalize<<<(n + 127) / 128, 128, 0, st>>>(M.grid, S->cell_of.p, M.cell_start.p, M.sorted.p, M.vox.p, n);
-  }
-  TEL_END(W.tel, KC_NDT_BUILD, n > 0 ? 11 : 5, st);
+  TEL_END(W.tel, KC_NDT_BUILD, n > 0 ? 10 : 4, st);
   B2R_CUDA(cudaGetLastError());
   c.ndt_ready = true;
   return B2R_OK;
@@ -508,7 +587,7 @@ inline int ndt_sync_geom(NdtVoxelMap& M, NdtWork& W, cudaStream_t st) {
   B2R_CUDA(cudaStreamSynchronize(st));
   M.h_geom = *W.h_geom_pinned;
   M.h_geom_valid = true;
-  if (!M.h_geom.ok) return fail(B2R_EUNSUPPORTED, "NDT voxel grid exceeds the dense table capacity (extent / resolution too large)");
+  if (!M.h_geom.ok) return fail(B2R_EUNSUPPORTED, "NDT voxel grid exceeds int32 indices (leaf size too small for the extent; PCL refuses the same input)");
   return B2R_OK;
 }
 
@@ -517,21 +596,20 @@ inline int ndt_dump(Cloud& c, NdtWork& W, cudaStream_t st, size_t capacity, size
   NdtVoxelMap& M = *c.ndt;
   int rc = ndt_sync_geom(M, W, st);
   if (rc) return rc;
-  Grid G;
-  B2R_CUDA(cudaMemcpyAsync(&G, M.grid, sizeof(Grid), cudaMemcpyDeviceToHost, st));
-  B2R_CUDA(cudaStreamSynchronize(st));
-  std::vector<int> cs((size_t)G.ncell + 1);
+  std::vector<unsigned int> ks(M.n + 1);
   std::vector<NdtVoxel> vox(M.n + 1);
-  B2R_CUDA(cudaMemcpyAsync(cs.data(), M.cell_start.p, cs.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (M.n) B2R_CUDA(cudaMemcpyAsync(vox.data(), M.vox.p, M.n * sizeof(NdtVoxel), cudaMemcpyDeviceToHost, st));
+  if (M.n) {
+    B2R_CUDA(cudaMemcpyAsync(ks.data(), M.keys.p, M.n * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    B2R_CUDA(cudaMemcpyAsync(vox.data(), M.vox.p, M.n * sizeof(NdtVoxel), cudaMemcpyDeviceToHost, st));
+  }
   B2R_CUDA(cudaStreamSynchronize(st));
   size_t V = 0;
-  for (int cell = 0; cell < G.ncell; cell++) {
-    int s = cs[cell], e = cs[cell + 1];
-    if (e <= s) continue;
+  for (size_t s = 0; s < M.n; s++) {  // keys ascending: one record per run of equal keys, at the run's first position
+    if (ks[s] == 0xffffffffu) break;
+    if (s > 0 && ks[s - 1] == ks[s]) continue;
     if (V < capacity) {
       const NdtVoxel& L = vox[s];
-      if (keys) keys[V] = cell;
+      if (keys) keys[V] = (int64_t)ks[s];
       if (npts) npts[V] = L.npts;
       if (mean) std::memcpy(mean + V * 3, L.mean, 3 * sizeof(double));
       if (icov) std::memcpy(icov + V * 9, L.icov, 9 * sizeof(double));
@@ -718,16 +796,16 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
                         bool compute_hessian, bool hessian_only, NdtPass* out) {
   NdtVoxelMap& M = *tgt.ndt;
   NdtArgs A;
-  A.src_raw = src.raw_view; A.src_stride_f = src.stride_f; A.n = (int)src.n;
-  A.geom = M.geom; A.cell_start = M.cell_start.p; A.vox = M.vox.p;
+  A.src = src.sorted.p; A.n_sorted = src.nsup * 1024;
+  A.geom = M.geom; A.table = M.table.p; A.mask = M.mask; A.cells = M.cells.p; A.vox = M.vox.p;
   for (int i = 0; i < 12; i++) A.Tf[i] = Tf_row[i];
   std::memcpy(A.jang, K.jang, sizeof(A.jang)); std::memcpy(A.hang, K.hang, sizeof(A.hang));
   std::memcpy(A.jang_d, K.jang_d, sizeof(A.jang_d)); std::memcpy(A.hang_d, K.hang_d, sizeof(A.hang_d));
   A.d1 = K.d1; A.d2 = K.d2;
   A.ncell_search = (cfg.ndt_search_method == 1) ? 1 : 7;
   A.compute_hessian = compute_hessian ? 1 : 0;
-  const unsigned nb = (unsigned)((src.n + kNdtThreads - 1) / kNdtThreads);
-  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));
+  const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);
+  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * 36));
   A.partials = W.partials.p; A.out = W.h_out_dev; A.counter = W.d_counter; A.pairs = W.d_pairs;
   A.flag = W.h_flag_dev; A.seq = ++W.seq;
   if (hessian_only) {
@@ -742,7 +820,8 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
     return B2R_OK;
   }
   { TEL_BEGIN(W.tel, st);  // W.d_pairs is zero here: allocated zeroed, and the last block of every pass resets it after reading it
-    k_ndt_derivatives<<<nb, kNdtThreads, 0, st>>>(A);
+    if (compute_hessian) k_ndt_derivatives<true><<<nb, kNdtThreads, 0, st>>>(A);
+    else k_ndt_derivatives<false><<<nb, kNdtThreads, 0, st>>>(A);
     TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
   if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());
@@ -750,7 +829,11 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   if (rc) return rc;
   out->score = W.h_out[0];
   std::memcpy(out->g, W.h_out + 1, 6 * sizeof(double));
-  if (compute_hessian) std::memcpy(out->H, W.h_out + 7, 36 * sizeof(double));
+  if (compute_hessian) {
+    int k = 7;
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) { out->H[r * 6 + c] = out->H[c * 6 + r] = W.h_out[k++]; }
+  }
   std::memcpy(&out->pairs, W.h_out + kNdtAcc, sizeof(unsigned long long));
   return B2R_OK;
 }

@@ -8,10 +8,10 @@
 // Design (B200-first, SURVEY.md §0.5 / §7 "iteration control on device"):
 //   * every pair in flight owns a PairDev record in HBM: the two clouds' search structures, its double-buffered
 //     correspondence sets, and the COMPLETE Levenberg-Marquardt state (pose, H, b, lambda, nu, counters);
-//   * ONE round = two launches that cover ALL active pairs (blockIdx.y = slot): k_pair_search (exact seeded 1-NN of every
-//     transformed source point) and k_pair_accumulate (float64 linearisation fused with the trial cost of the previous
-//     correspondence set).  The LAST block of each pair reduces that pair's partials in a fixed order and then runs the LM
-//     step itself (6x6 LDL^T, se3_exp, rho test, lambda update, convergence test) — the host never sees H or b;
+//   * ONE round = three launches that cover ALL active pairs (blockIdx.y = slot): k_pair_search (exact seeded 1-NN of every
+//     transformed source point), k_pair_accumulate (float64 linearisation fused with the trial cost of the previous
+//     correspondence set; block partials) and k_pair_lm (one small block per pair: adds the pair's partials in a fixed order
+//     and runs the LM step itself — 6x6 LDL^T, se3_exp, rho test, lambda update, convergence test).  The host never sees H or b;
 //   * rounds are enqueued ahead; a finished pair's blocks exit at once.  The host reads back one word per round (batch mode:
 //     number of pairs still active) or nothing at all until the result record lands in mapped memory (single-pair mode);
 //   * reductions depend only on the pair's own geometry, so a pair's result is bitwise identical whether it runs alone
@@ -269,7 +269,6 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
 template <int C>
 __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;");
   // batch mode: active[0] = number of pairs still in flight, active[1..] = their indices (k_pair_compact, previous round); the host
   // sizes grid.y from a count that may be one round stale, so surplus rows exit here
   if (active && (int)blockIdx.y >= active[0]) return;
@@ -329,15 +328,22 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, 
   }
 }
 
-// linearize (float64) at xe into the write set + compute_error of the previous set, per active pair; the pair's last block
-// reduces in a fixed order and advances the pair's LM state.
-__global__ void __launch_bounds__(kAccThreads, 512 / kAccThreads) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active,
-                                                                                     const __grid_constant__ LmCfg cfg) {
-  __shared__ double red[kAcc * 32];
-  __shared__ double fin[8 * kAcc];
-  __shared__ bool is_last;
+// One value of the block reduction, consumed as soon as it is produced: butterfly over the warp, lane 0 parks the warp's sum
+// in shared memory.  (Streaming the 29 values instead of holding 29 float64 accumulators until the end keeps the kernel under
+// 96 registers: 3 blocks of 256 threads per SM instead of 2 — the pass is bound by gather latency, so residency is throughput.)
+__device__ __forceinline__ void red_emit(double v, int i, double* red, int lane, int warp) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[i * 8 + warp] = v;
+}
+
+// linearize (float64) at xe into the write set + compute_error of the previous set, per active pair.  Every block leaves its
+// 29 partial sums in the pair's `partials`; k_pair_lm (next launch) adds them in a fixed order and takes the LM step.
+__global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
+  __shared__ double red[kAcc * 8];
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;");
+  // single-pair mode: let the (tiny) LM kernel of this round become resident now, so that it starts the moment this grid drains
+  if (!active) asm volatile("griddepcontrol.launch_dependents;");
   if (active && (int)blockIdx.y >= active[0]) return;
   PairDev& p = pairs[active ? active[1 + blockIdx.y] : blockIdx.y];
   const int mode = p.mode;
@@ -345,149 +351,170 @@ __global__ void __launch_bounds__(kAccThreads, 512 / kAccThreads) k_pair_accumul
   const int nblk = p.nblk_acc;
   if ((int)blockIdx.x >= nblk) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cur = p.cur;
   const int wset = (mode == PM_FIRST) ? cur : (cur ^ 1);
-  double acc[kAcc];
-#pragma unroll
-  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < p.src.nleaf * kLeaf) pt = p.src.sp[s];
   const bool is_point = idx_bits(pt.w) != kPadIdx;
   double T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = p.xe[i];
-  if (mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness)) {
-    // getFitnessScore: mean of the squared NN distances with d2 <= max_range (information_matrix_calculator.cpp:66-75)
-    if (is_point && p.cpos[wset][s] >= 0) {
-      const float dd = p.d2[s];
-      if ((double)dd <= cfg.fit_max_range) { acc[0] = (double)dd; acc[1] = 1.0; }
+  const double ax = (double)pt.x, ay = (double)pt.y, az = (double)pt.z;
+  const double tx = T[0] * ax + T[1] * ay + T[2] * az + T[3];
+  const double ty = T[4] * ax + T[5] * ay + T[6] * az + T[7];
+  const double tz = T[8] * ax + T[9] * ay + T[10] * az + T[11];
+  // ---- trial cost: FastGICP::compute_error at xe with the previous correspondences / mahalanobis
+  double trial = 0.0;
+  if ((mode == PM_FUSED || mode == PM_ERR) && is_point) {
+    const int tp = p.cpos[cur][s];
+    if (tp >= 0) {
+      const float4 tb = p.tgt.sp[tp];
+      const double* m = p.mahal[cur] + (size_t)s * 6;
+      const double ex = (double)tb.x - tx, ey = (double)tb.y - ty, ez = (double)tb.z - tz;
+      const double Mex = m[0] * ex + m[1] * ey + m[2] * ez;
+      const double Mey = m[1] * ex + m[3] * ey + m[4] * ez;
+      const double Mez = m[2] * ex + m[4] * ey + m[5] * ez;
+      trial = ex * Mex + ey * Mey + ez * Mez;
     }
   }
-  if (mode != PM_FIT) {
-    if ((mode == PM_FUSED || mode == PM_ERR) && is_point) {  // FastGICP::compute_error at xe with the previous correspondences
-      const int tp = p.cpos[cur][s];
-      if (tp >= 0) {
-        const float4 tb = p.tgt.sp[tp];
-        const double* m = p.mahal[cur] + (size_t)s * 6;
-        const double ax = (double)pt.x, ay = (double)pt.y, az = (double)pt.z;
-        const double ex = (double)tb.x - (T[0] * ax + T[1] * ay + T[2] * az + T[3]);
-        const double ey = (double)tb.y - (T[4] * ax + T[5] * ay + T[6] * az + T[7]);
-        const double ez = (double)tb.z - (T[8] * ax + T[9] * ay + T[10] * az + T[11]);
-        const double Mex = m[0] * ex + m[1] * ey + m[2] * ez;
-        const double Mey = m[1] * ex + m[3] * ey + m[4] * ez;
-        const double Mez = m[2] * ex + m[4] * ey + m[5] * ez;
-        acc[28] = ex * Mex + ey * Mey + ez * Mez;
-      }
-    }
-    if (mode != PM_ERR && is_point) {  // FastGICP::linearize over the correspondences just written
-      const int best_pos = p.cpos[wset][s];
-      if (best_pos >= 0) {
-        const double* ca = p.scov + (size_t)s * 6;
-        const double* cb = p.tcov + (size_t)best_pos * 6;
-        const double CA[9] = {ca[0], ca[1], ca[2], ca[1], ca[3], ca[4], ca[2], ca[4], ca[5]};
-        const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
-        double tmp[9], rcr[9], M[9];
-        mul3(R, CA, tmp);
-        // rcr = CB + tmp * R^T  (symmetric; build the upper part and mirror so the inverse is exactly symmetric)
-        double u[6];
-        u[0] = tmp[0] * R[0] + tmp[1] * R[1] + tmp[2] * R[2];
-        u[1] = tmp[0] * R[3] + tmp[1] * R[4] + tmp[2] * R[5];
-        u[2] = tmp[0] * R[6] + tmp[1] * R[7] + tmp[2] * R[8];
-        u[3] = tmp[3] * R[3] + tmp[4] * R[4] + tmp[5] * R[5];
-        u[4] = tmp[3] * R[6] + tmp[4] * R[7] + tmp[5] * R[8];
-        u[5] = tmp[6] * R[6] + tmp[7] * R[7] + tmp[8] * R[8];
-        rcr[0] = cb[0] + u[0]; rcr[1] = cb[1] + u[1]; rcr[2] = cb[2] + u[2];
-        rcr[4] = cb[3] + u[3]; rcr[5] = cb[4] + u[4]; rcr[8] = cb[5] + u[5];
-        rcr[3] = rcr[1]; rcr[6] = rcr[2]; rcr[7] = rcr[5];
-        inv3(rcr, M);
-        double* mo = p.mahal[wset] + (size_t)s * 6;
-        mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
-        const float4 tb = p.tgt.sp[best_pos];
-        const double ax = (double)pt.x, ay = (double)pt.y, az = (double)pt.z;
-        const double tx = T[0] * ax + T[1] * ay + T[2] * az + T[3];
-        const double ty = T[4] * ax + T[5] * ay + T[6] * az + T[7];
-        const double tz = T[8] * ax + T[9] * ay + T[10] * az + T[11];
-        const double ex = (double)tb.x - tx, ey = (double)tb.y - ty, ez = (double)tb.z - tz;
-        const double m00 = M[0], m01 = M[1], m02 = M[2], m11 = M[4], m12 = M[5], m22 = M[8];
-        const double Mex = m00 * ex + m01 * ey + m02 * ez;
-        const double Mey = m01 * ex + m11 * ey + m12 * ez;
-        const double Mez = m02 * ex + m12 * ey + m22 * ez;
-        acc[27] = ex * Mex + ey * Mey + ez * Mez;
-        // S = skew(tA) = [[0,-tz,ty],[tz,0,-tx],[-ty,tx,0]];  MS = M*S
-        const double ms00 = m01 * tz - m02 * ty, ms01 = -m00 * tz + m02 * tx, ms02 = m00 * ty - m01 * tx;
-        const double ms10 = m11 * tz - m12 * ty, ms11 = -m01 * tz + m12 * tx, ms12 = m01 * ty - m11 * tx;
-        const double ms20 = m12 * tz - m22 * ty, ms21 = -m02 * tz + m22 * tx, ms22 = m02 * ty - m12 * tx;
-        // S^T * MS (upper): S^T = [[0,tz,-ty],[-tz,0,tx],[ty,-tx,0]]
-        acc[0] = tz * ms10 - ty * ms20;   // (0,0)
-        acc[1] = tz * ms11 - ty * ms21;   // (0,1)
-        acc[2] = tz * ms12 - ty * ms22;   // (0,2)
-        acc[3] = -ms00;                   // (0,3) = -(MS)[0][0]
-        acc[4] = -ms10;                   // (0,4)
-        acc[5] = -ms20;                   // (0,5)
-        acc[6] = -tz * ms01 + tx * ms21;  // (1,1)
-        acc[7] = -tz * ms02 + tx * ms22;  // (1,2)
-        acc[8] = -ms01;                   // (1,3)
-        acc[9] = -ms11;                   // (1,4)
-        acc[10] = -ms21;                  // (1,5)
-        acc[11] = ty * ms02 - tx * ms12;  // (2,2)
-        acc[12] = -ms02;                  // (2,3)
-        acc[13] = -ms12;                  // (2,4)
-        acc[14] = -ms22;                  // (2,5)
-        acc[15] = m00; acc[16] = m01; acc[17] = m02;  // (3,3..5)
-        acc[18] = m11; acc[19] = m12;                 // (4,4..5)
-        acc[20] = m22;                                // (5,5)
-        // b = J^T M e = [S^T Me ; -Me]
-        acc[21] = tz * Mey - ty * Mez;
-        acc[22] = -tz * Mex + tx * Mez;
-        acc[23] = ty * Mex - tx * Mey;
-        acc[24] = -Mex; acc[25] = -Mey; acc[26] = -Mez;
-      }
+  // ---- getFitnessScore sums (fitness round, or the final compute_error round of a registration that wants its fitness):
+  // mean of the squared NN distances with d2 <= max_range (information_matrix_calculator.cpp:66-75)
+  double fit_sum = 0.0, fit_cnt = 0.0;
+  const bool fit = mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness);
+  if (fit && is_point && p.cpos[wset][s] >= 0) {
+    const float dd = p.d2[s];
+    if ((double)dd <= cfg.fit_max_range) { fit_sum = (double)dd; fit_cnt = 1.0; }
+  }
+  // ---- FastGICP::linearize over the correspondences just written
+  double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, ex = 0, ey = 0, ez = 0;
+  if ((mode == PM_FIRST || mode == PM_FUSED) && is_point) {
+    const int best_pos = p.cpos[wset][s];
+    if (best_pos >= 0) {
+      const double* ca = p.scov + (size_t)s * 6;
+      const double* cb = p.tcov + (size_t)best_pos * 6;
+      const float4 tb = p.tgt.sp[best_pos];
+      const double CA[9] = {ca[0], ca[1], ca[2], ca[1], ca[3], ca[4], ca[2], ca[4], ca[5]};
+      const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+      double tmp[9], rcr[9], M[9];
+      mul3(R, CA, tmp);
+      // rcr = CB + tmp * R^T  (symmetric; build the upper part and mirror so the inverse is exactly symmetric)
+      double u[6];
+      u[0] = tmp[0] * R[0] + tmp[1] * R[1] + tmp[2] * R[2];
+      u[1] = tmp[0] * R[3] + tmp[1] * R[4] + tmp[2] * R[5];
+      u[2] = tmp[0] * R[6] + tmp[1] * R[7] + tmp[2] * R[8];
+      u[3] = tmp[3] * R[3] + tmp[4] * R[4] + tmp[5] * R[5];
+      u[4] = tmp[3] * R[6] + tmp[4] * R[7] + tmp[5] * R[8];
+      u[5] = tmp[6] * R[6] + tmp[7] * R[7] + tmp[8] * R[8];
+      rcr[0] = cb[0] + u[0]; rcr[1] = cb[1] + u[1]; rcr[2] = cb[2] + u[2];
+      rcr[4] = cb[3] + u[3]; rcr[5] = cb[4] + u[4]; rcr[8] = cb[5] + u[5];
+      rcr[3] = rcr[1]; rcr[6] = rcr[2]; rcr[7] = rcr[5];
+      inv3(rcr, M);
+      double* mo = p.mahal[wset] + (size_t)s * 6;
+      mo[0] = M[0]; mo[1] = M[1]; mo[2] = M[2]; mo[3] = M[4]; mo[4] = M[5]; mo[5] = M[8];
+      m00 = M[0]; m01 = M[1]; m02 = M[2]; m11 = M[4]; m12 = M[5]; m22 = M[8];
+      ex = (double)tb.x - tx; ey = (double)tb.y - ty; ez = (double)tb.z - tz;
     }
   }
-  block_reduce<kAcc>(acc, red);
-  // per-pair last-block-done reduction (fixed order: depends only on this pair's block count => bitwise reproducible and
-  // independent of which other pairs share the launch)
-  double* partials = p.partials;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < kAcc; i++) partials[(size_t)blockIdx.x * kAcc + i] = acc[i];
-    __threadfence();
-    const unsigned int t = atomicAdd(&p.counter, 1u);
-    is_last = (t == (unsigned int)nblk - 1u);
-  }
+  // a point without correspondence has M = 0, e = 0: every term below is an exact zero, as if it had been skipped
+  const double Mex = m00 * ex + m01 * ey + m02 * ez;
+  const double Mey = m01 * ex + m11 * ey + m12 * ez;
+  const double Mez = m02 * ex + m12 * ey + m22 * ez;
+  // S = skew(tA) = [[0,-tz,ty],[tz,0,-tx],[-ty,tx,0]];  MS = M*S;  H = [S^T M S, -S^T M; -M S, M] (upper), b = J^T M e = [S^T Me ; -Me]
+  const double ms00 = m01 * tz - m02 * ty, ms01 = -m00 * tz + m02 * tx, ms02 = m00 * ty - m01 * tx;
+  const double ms10 = m11 * tz - m12 * ty, ms11 = -m01 * tz + m12 * tx, ms12 = m01 * ty - m11 * tx;
+  const double ms20 = m12 * tz - m22 * ty, ms21 = -m02 * tz + m22 * tx, ms22 = m02 * ty - m12 * tx;
+  const bool lin = mode == PM_FIRST || mode == PM_FUSED;
+  // slots 0 and 1 carry the fitness sums in the rounds that do not linearise (PM_FIT, PM_ERR)
+  red_emit(lin ? tz * ms10 - ty * ms20 : fit_sum, 0, red, lane, warp);   // (0,0)
+  red_emit(lin ? tz * ms11 - ty * ms21 : fit_cnt, 1, red, lane, warp);   // (0,1)
+  red_emit(tz * ms12 - ty * ms22, 2, red, lane, warp);   // (0,2)
+  red_emit(-ms00, 3, red, lane, warp);                   // (0,3) = -(MS)[0][0]
+  red_emit(-ms10, 4, red, lane, warp);                   // (0,4)
+  red_emit(-ms20, 5, red, lane, warp);                   // (0,5)
+  red_emit(-tz * ms01 + tx * ms21, 6, red, lane, warp);  // (1,1)
+  red_emit(-tz * ms02 + tx * ms22, 7, red, lane, warp);  // (1,2)
+  red_emit(-ms01, 8, red, lane, warp);                   // (1,3)
+  red_emit(-ms11, 9, red, lane, warp);                   // (1,4)
+  red_emit(-ms21, 10, red, lane, warp);                  // (1,5)
+  red_emit(ty * ms02 - tx * ms12, 11, red, lane, warp);  // (2,2)
+  red_emit(-ms02, 12, red, lane, warp);                  // (2,3)
+  red_emit(-ms12, 13, red, lane, warp);                  // (2,4)
+  red_emit(-ms22, 14, red, lane, warp);                  // (2,5)
+  red_emit(m00, 15, red, lane, warp); red_emit(m01, 16, red, lane, warp); red_emit(m02, 17, red, lane, warp);  // (3,3..5)
+  red_emit(m11, 18, red, lane, warp); red_emit(m12, 19, red, lane, warp);                                      // (4,4..5)
+  red_emit(m22, 20, red, lane, warp);                                                                         // (5,5)
+  red_emit(tz * Mey - ty * Mez, 21, red, lane, warp);
+  red_emit(-tz * Mex + tx * Mez, 22, red, lane, warp);
+  red_emit(ty * Mex - tx * Mey, 23, red, lane, warp);
+  red_emit(-Mex, 24, red, lane, warp); red_emit(-Mey, 25, red, lane, warp); red_emit(-Mez, 26, red, lane, warp);
+  red_emit(ex * Mex + ey * Mey + ez * Mez, 27, red, lane, warp);
+  red_emit(trial, 28, red, lane, warp);
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  // the block's sums: value i = sum over the 8 warps, added in warp order by one thread each
+  if (threadIdx.x < kAcc) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kAccThreads / 32; w++) v += red[threadIdx.x * 8 + w];
+    p.partials[(size_t)blockIdx.x * kAcc + threadIdx.x] = v;
+  }
+}
+static_assert(kAccThreads == 256, "red_emit parks 8 warp sums per value");
+
+// The LM step of every active pair (one block per pair): add the pair's block partials in a fixed order (depends only on the
+// pair's own block count => bitwise reproducible, independent of which other pairs share the launch), then thread 0 runs
+// fast_gicp's step_lm logic on a SHARED-MEMORY copy of the pair's state (one coalesced load, one coalesced store; the scalar
+// chain itself never waits on HBM) and publishes the record when the registration ends.
+constexpr int kLmThreads = 256;
+__global__ void __launch_bounds__(kLmThreads, 1) k_pair_lm(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
+  __shared__ double fin[8 * kAcc];
+  __shared__ double r[kAcc];
+  __shared__ PairDev sp;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (!active) asm volatile("griddepcontrol.launch_dependents;");  // single pair: the next round's search may queue up behind this block
+  if (active && (int)blockIdx.x >= active[0]) return;
+  PairDev* gp = pairs + (active ? active[1 + blockIdx.x] : blockIdx.x);
+  const int mode = gp->mode;
+  if (mode < PM_FIRST || mode > PM_FIT) return;
   {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sp);
+    for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / 8); i += blockDim.x) dst[i] = src[i];
+  }
+  const double* partials = gp->partials;
+  const unsigned int nrow = (unsigned int)gp->nblk_acc;
+  {
+    // warp w adds rows w, w+8, ... (lane = value: one coalesced row per load, 8 loads in flight), then thread i adds the 8 warp sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nw = (blockDim.x >> 5) < 8 ? (int)(blockDim.x >> 5) : 8;
-    const unsigned int nrow = (unsigned int)nblk;
-    if (warp < nw) {
-      for (int i = lane; i < kAcc; i += 32) {
-        double sacc = 0.0;
-        unsigned int r = warp;
-        for (; r + 7 * nw < nrow; r += 8 * nw) {
-          double t[8];
-#pragma unroll
-          for (int u = 0; u < 8; u++) t[u] = __ldcg(partials + (size_t)(r + u * nw) * kAcc + i);
-#pragma unroll
-          for (int u = 0; u < 8; u++) sacc += t[u];
-        }
-        for (; r < nrow; r += nw) sacc += __ldcg(partials + (size_t)r * kAcc + i);
-        fin[warp * kAcc + i] = sacc;
-      }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kAcc; i += blockDim.x) {
+    constexpr int nw = kLmThreads / 32;
+    if (lane < kAcc) {
       double sacc = 0.0;
-      for (int w = 0; w < nw; w++) sacc += fin[w * kAcc + i];
-      fin[i] = sacc;  // column i is read by this thread only
+      unsigned int row = warp;
+      for (; row + 7 * nw < nrow; row += 8 * nw) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(partials + (size_t)(row + u * nw) * kAcc + lane);
+#pragma unroll
+        for (int u = 0; u < 8; u++) sacc += t[u];
+      }
+      for (; row < nrow; row += nw) sacc += __ldcg(partials + (size_t)row * kAcc + lane);
+      fin[warp * kAcc + lane] = sacc;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      p.counter = 0;
-      lm_advance(p, fin, cfg);
+    if (threadIdx.x < kAcc) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w = 0; w < nw; w++) sacc += fin[w * kAcc + threadIdx.x];
+      r[threadIdx.x] = sacc;
     }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) lm_advance(sp, r, cfg);
+  __syncthreads();
+  {
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(&sp);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(gp);
+    for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / 8); i += blockDim.x) dst[i] = src[i];
   }
 }
 

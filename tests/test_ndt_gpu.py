@@ -122,3 +122,35 @@ def test_fitness_through_ndt_handle(pair, oracle):
     os_, on, oi = oracle.fitness(tgt, src, T)
     assert used == on and inl == oi and abs(score - os_) <= 1e-12 * abs(os_)
     r.close()
+
+
+def test_large_extent_at_factory_resolution(pair, oracle):
+    """reg_resolution = 0.5 (the factory default, registrations.cpp:93) over a 300 m x 300 m extent: 600 x 600 x ~50 = 18 M cells.
+    The reference's VoxelGridCovariance keeps its leaves in a map and is limited only by int32 indices; the engine's voxel map is
+    sparse too (sorted keys + hash table), so this must simply work — same voxels, same derivative pass, same align."""
+    src, tgt = pair
+    far = np.zeros((64, tgt.shape[1]), np.float32)
+    rng = np.random.default_rng(5)
+    far[:, 0] = np.where(np.arange(64) % 2 == 0, 150.0, -150.0) + rng.uniform(-0.2, 0.2, 64)
+    far[:, 1] = np.where((np.arange(64) // 2) % 2 == 0, 150.0, -150.0) + rng.uniform(-0.2, 0.2, 64)
+    far[:, 2] = rng.uniform(-0.2, 0.2, 64)
+    far[:, 3] = 1.0
+    big = np.concatenate([tgt, far]).astype(np.float32)
+    r = make(0.5)
+    r.setInputTarget(big)
+    got = r.ndtGetVoxels()
+    m = oracle.NdtMap(big, 0.5)
+    want = m.dump()
+    assert int(np.prod(want["div_b"].astype(np.int64))) > (1 << 23)  # beyond the old dense-table capacity
+    assert np.array_equal(got["div_b"], want["div_b"]) and np.array_equal(got["keys"], want["keys"]) and np.array_equal(got["npts"], want["npts"])
+    r.setInputSource(src)
+    p = np.array([0.1, -0.05, 0.02, 0.005, -0.01, 0.02])
+    score, g, H, npairs = r.ndtDerivativesAt(p)
+    o = m.derivatives(src, p)
+    assert npairs == o["n_pairs"] and abs(score - o["score"]) <= 1e-9 * abs(o["score"])
+    assert relrel(g, o["g"]) < 1e-9 and relrel(H, o["H"]) < 1e-9
+    r.align(np.eye(4, dtype=np.float32))
+    oa = m.align(src, np.eye(4, dtype=np.float32))
+    assert r.hasConverged() == oa["converged"] and r.nr_iterations == oa["iterations"]
+    assert trans_err(r.getFinalTransformation(), oa["T"]) < 1e-4 and rot_err(r.getFinalTransformation(), oa["T"]) < 1e-4
+    r.close()
