@@ -20,6 +20,7 @@
 #include "engine.cuh"
 #include "gicp.cuh"
 #include "pair_engine.cuh"
+#include "bvh_build.cuh"
 #include "fitness.cuh"
 #include "ndt.cuh"
 #include "voxelgrid.cuh"
@@ -296,11 +297,9 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
   return B2R_OK;
 }
 
-// builds the implicit BVH of a cloud on stream `st` with build scratch `B` (one scratch per stream)
-static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
-  if (c.bvh_ready) return B2R_OK;
+// ---- cluster build (bvh_build.cuh): one launch builds the whole structure of one cloud — or of a set of clouds
+static int bvh_alloc(Cloud& c) {
   const size_t n = c.n;
-  const int N = (int)n;
   c.nsup = (int)((n + 1023) / 1024);
   const size_t padded = (size_t)c.nsup * 1024;
   B2R_CUDA(c.sorted.reserve(padded + 32));
@@ -309,7 +308,65 @@ static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   B2R_CUDA(c.leaf_hi.reserve((size_t)c.nsup * kSuper + 1));
   B2R_CUDA(c.sup_lo.reserve(c.nsup + 1));
   B2R_CUDA(c.sup_hi.reserve(c.nsup + 1));
+  return B2R_OK;
+}
+static BuildItem build_item(const Cloud& c) {
+  BuildItem it;
+  it.raw = c.raw_view; it.sorted = c.sorted.p; it.pos_of = c.pos_of.p; it.leaf_lo = c.leaf_lo.p; it.leaf_hi = c.leaf_hi.p;
+  it.sup_lo = c.sup_lo.p; it.sup_hi = c.sup_hi.p; it.stride_f = c.stride_f; it.n = (int)c.n;
+  return it;
+}
+static int cluster_size_for(size_t n) {  // smallest cluster whose distributed shared memory holds the cloud; 0 = too large
+  for (int cl = 1; cl <= 8; cl *= 2)
+    if (n <= (size_t)cl * kBuildCap) return cl;
+  return 0;
+}
+static bool use_cluster_build() {
+  static const bool on = !getenv("B2R_CUB_SORT");
+  return on;
+}
+template <int CL>
+static cudaError_t launch_cluster_build_t(const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(n_clouds * CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = kBuildSmem; lc.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  lc.attrs = la; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, k_bvh_build_cluster<CL>, d_items, single);
+}
+static cudaError_t launch_cluster_build(int cl, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
+  switch (cl) {
+    case 1: return launch_cluster_build_t<1>(d_items, single, n_clouds, st);
+    case 2: return launch_cluster_build_t<2>(d_items, single, n_clouds, st);
+    case 4: return launch_cluster_build_t<4>(d_items, single, n_clouds, st);
+    default: return launch_cluster_build_t<8>(d_items, single, n_clouds, st);
+  }
+}
+
+// builds the implicit BVH of a cloud on stream `st` with build scratch `B` (one scratch per stream)
+static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
+  if (c.bvh_ready) return B2R_OK;
+  const size_t n = c.n;
+  const int N = (int)n;
+  int arc = bvh_alloc(c);
+  if (arc) return arc;
   if (n == 0) { c.bvh_ready = true; return B2R_OK; }
+  const int cl = cluster_size_for(n);
+  if (cl && use_cluster_build()) {  // the whole build as ONE kernel on a cluster of `cl` CTAs (the cloud lives in distributed shared memory)
+    TEL_BEGIN(&h->tel, st);
+    B2R_CUDA(launch_cluster_build(cl, nullptr, build_item(c), 1, st));
+    TEL_END(&h->tel, KC_GRID, 1, st);
+    c.bvh_ready = true;
+    return B2R_OK;
+  }
+  // clouds beyond 131 072 points: bounding box, keys, toolkit radix sort, leaves
   B2R_CUDA(B.keys_a.reserve(n)); B2R_CUDA(B.keys_b.reserve(n)); B2R_CUDA(B.vals_a.reserve(n)); B2R_CUDA(B.vals_b.reserve(n));
   size_t tmp_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, B.keys_a.p, B.keys_b.p, B.vals_a.p, B.vals_b.p, N, 0, 30, st);

@@ -37,6 +37,12 @@ struct b2r_batch {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
   DevBuf<b2r_result> d_send, d_recv;
+  DevBuf<BuildItem> d_build;        // descriptor list of the batched cluster builds
+  BuildItem* h_build = nullptr;     // pinned staging
+  size_t h_build_cap = 0;
+  DevBuf<KnnBatchItem> d_knn;       // descriptor list of one batched k-NN covariance launch
+  KnnBatchItem* h_knn = nullptr;    // pinned staging
+  size_t h_knn_cap = 0;
   b2r_result* h_gather = nullptr;
   size_t h_gather_cap = 0;
   // telemetry of the last b2r_batch_align
@@ -76,6 +82,9 @@ extern "C" void b2r_batch_destroy(b2r_batch* b) {
   if (b->h_reports) cudaFreeHost(b->h_reports);
   if (b->h_word) cudaFreeHost(b->h_word);
   if (b->h_gather) cudaFreeHost(b->h_gather);
+  if (b->h_knn) cudaFreeHost(b->h_knn);
+  if (b->h_build) cudaFreeHost(b->h_build);
+  b->d_knn.release(); b->d_build.release();
   if (b->eng) b2r_destroy(b->eng);
   delete b;
 }
@@ -136,9 +145,8 @@ static int batch_add(b2r_batch* b, const void* pts, size_t n, size_t stride_byte
       b->eng->tel.h2d += n * stride_bytes;
     }
   }
-  // search structure + covariances right behind the upload, on the same build stream (4 streams: builds of different clouds overlap)
-  int rc = build_cov(b->eng, *c, b->bctx[si], st);
-  if (rc) { free_cloud(c); return rc; }
+  // the upload is all that happens here (4 copy streams); the search structures and k-NN covariances of ALL new clouds are built
+  // together at the next align: one cluster-build launch per cluster size and one k-NN launch (batch_build_structures)
   int id;
   if (!b->free_ids.empty()) { id = b->free_ids.back(); b->free_ids.pop_back(); b->clouds[id] = c; }
   else { id = (int)b->clouds.size(); b->clouds.push_back(c); }
@@ -182,6 +190,83 @@ extern "C" int b2r_batch_remove_cloud(b2r_batch* b, int32_t id) {
 extern "C" int b2r_batch_cloud_count(const b2r_batch* b) {
   if (!b) return 0;
   return (int)(b->clouds.size() - b->free_ids.size());
+}
+
+// Search structure (bvh_build.cuh) + FastGICP::calculate_covariances for every cloud a batch names that does not have them yet:
+// one cluster-build launch per cluster size and one k-NN launch for all of them (what setInputSource / setInputTarget make the
+// reference pay per call: kd-tree build + covariances, loop_detector.hpp:122,136)
+static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs) {
+  b2r_handle* h = b->eng;
+  cudaStream_t st = h->st;
+  std::vector<Cloud*> todo;
+  for (size_t i = 0; i < n_pairs; i++)
+    for (int32_t id : {pairs[i].source, pairs[i].target}) {
+      Cloud* c = b->clouds[id];
+      if (c->cov_ready || c->n == 0) continue;
+      c->cov_ready = true;  // marks "queued" for the de-duplication; the launches below are stream-ordered before any use
+      todo.push_back(c);
+    }
+  if (todo.empty()) return B2R_OK;
+  {  // ---- structures
+    std::vector<Cloud*> by_cl[4];  // cluster sizes 1, 2, 4, 8
+    for (Cloud* c : todo) {
+      if (c->bvh_ready) continue;
+      const int cl = cluster_size_for(c->n);
+      if (!cl || !use_cluster_build()) { c->cov_ready = false; int rc = build_bvh(h, *c, h->bc[0], st); c->cov_ready = true; if (rc) return rc; continue; }
+      int rc = bvh_alloc(*c);
+      if (rc) return rc;
+      by_cl[cl == 1 ? 0 : cl == 2 ? 1 : cl == 4 ? 2 : 3].push_back(c);
+    }
+    size_t total = by_cl[0].size() + by_cl[1].size() + by_cl[2].size() + by_cl[3].size();
+    if (total) {
+      B2R_CUDA(b->d_build.reserve(total));
+      if (b->h_build_cap < total) {
+        if (b->h_build) cudaFreeHost(b->h_build);
+        b->h_build = nullptr; b->h_build_cap = 0;
+        B2R_CUDA(cudaMallocHost(&b->h_build, (total + 64) * sizeof(BuildItem)));
+        b->h_build_cap = total + 64;
+      }
+      size_t k0 = 0;
+      for (int g = 0; g < 4; g++)
+        for (Cloud* c : by_cl[g]) b->h_build[k0++] = build_item(*c);
+      B2R_CUDA(cudaMemcpyAsync(b->d_build.p, b->h_build, total * sizeof(BuildItem), cudaMemcpyHostToDevice, st));
+      k0 = 0;
+      for (int g = 0; g < 4; g++) {
+        if (by_cl[g].empty()) continue;
+        TEL_BEGIN(&h->tel, st);
+        B2R_CUDA(launch_cluster_build(1 << g, b->d_build.p + k0, BuildItem(), (unsigned)by_cl[g].size(), st));
+        TEL_END(&h->tel, KC_GRID, 1, st);
+        for (Cloud* c : by_cl[g]) c->bvh_ready = true;
+        k0 += by_cl[g].size();
+      }
+    }
+  }
+  const int k = h->cfg.k_correspondences;
+  for (Cloud* c : todo) B2R_CUDA(c->cov.reserve((size_t)c->nsup * 1024 * 6 + 6));
+  if (k != kKnnRegK) {  // other k: the generic shared-memory-list kernel, one launch per cloud
+    for (Cloud* c : todo) { c->cov_ready = false; int rc = build_cov(h, *c, h->bc[0], st); if (rc) return rc; }
+    return B2R_OK;
+  }
+  B2R_CUDA(b->d_knn.reserve(todo.size()));
+  if (b->h_knn_cap < todo.size()) {
+    if (b->h_knn) cudaFreeHost(b->h_knn);
+    b->h_knn = nullptr; b->h_knn_cap = 0;
+    B2R_CUDA(cudaMallocHost(&b->h_knn, (todo.size() + 64) * sizeof(KnnBatchItem)));
+    b->h_knn_cap = todo.size() + 64;
+  }
+  unsigned max_blocks = 0;
+  for (size_t i = 0; i < todo.size(); i++) {
+    Cloud* c = todo[i];
+    KnnBatchItem& it = b->h_knn[i];
+    it.b = c->bvh(); it.raw = c->raw_view; it.cov = c->cov.p; it.stride_f = c->stride_f; it.pad = 0;
+    max_blocks = std::max(max_blocks, (unsigned)((size_t)c->nsup * 1024 / kKnnThreads));
+  }
+  B2R_CUDA(cudaMemcpyAsync(b->d_knn.p, b->h_knn, todo.size() * sizeof(KnnBatchItem), cudaMemcpyHostToDevice, st));
+  { TEL_BEGIN(&h->tel, st);
+    k_knn_cov_reg_batch<kKnnRegK><<<dim3(max_blocks, (unsigned)todo.size()), kKnnThreads, 0, st>>>(b->d_knn.p);
+    TEL_END(&h->tel, KC_KNN_COV, 1, st); }
+  B2R_CUDA(cudaGetLastError());
+  return B2R_OK;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -329,6 +414,8 @@ static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool w
       return fail(B2R_EINVAL, "pair names an unknown cloud id");
   }
   int rc = batch_sync_builds(b, false);  // the main stream waits for every outstanding upload / build
+  if (rc) return rc;
+  rc = batch_build_structures(b, pairs, n_pairs);
   if (rc) return rc;
   const size_t chunk = std::min(b->max_chunk, std::max<size_t>(n_pairs, 1));
   rc = batch_host_staging(b, std::max(chunk, n_pairs));

@@ -1,0 +1,237 @@
+// bvh_build.cuh — the whole implicit-BVH build of a cloud as ONE kernel on a thread-block cluster.
+//
+// What it replaces: the kd-tree builds the reference pays at every setInputSource / setInputTarget (pcl::search::KdTree inside
+// fast_gicp, pcl::Registration::initCompute's FLANN tree; call sites /root/reference/apps/scan_matching_odometry_nodelet.cpp:
+// 172,177,246 and /root/reference/include/hdl_graph_slam/loop_detector.hpp:122,136) — and, in this engine, a chain of eleven
+// launches (bbox, fill, keys, six cub::DeviceRadixSort kernels, leaves).
+//
+// B200-first design: a cloud of up to 131 072 points lives ENTIRELY in the distributed shared memory of one cluster
+// (CL = 1/2/4/8 CTAs x 16 384 (key, index) pairs = 128 KB each).  The cluster computes the bounding box, the 30-bit Hilbert
+// keys, runs a stable 4-pass LSD radix sort whose scatter writes straight into the PEER CTAs' shared memory (DSMEM stores,
+// cluster barriers between passes — no global-memory round trip, no histogram/offset kernels), and finally each CTA emits its
+// contiguous 16 384-position slice of the structure: sorted float4 points, pos_of, 512 leaf boxes, 16 super-node boxes.
+// blockIdx.x / CL selects the cloud: a whole set of keyframe clouds is built by one launch (37 clouds at a time at CL = 4).
+//
+// Order contract (unchanged): ascending (Hilbert key, original index); non-finite points dropped (pos_of = -1); padding
+// entries (+inf, kPadIdx) up to a multiple of 1024.
+#pragma once
+#include <cooperative_groups.h>
+#include "bvh.cuh"
+#include "grid.cuh"
+
+namespace b2r {
+
+constexpr int kBuildCap = 16384;      // (key, index) pairs held by one CTA
+constexpr int kBuildThreads = 1024;
+constexpr int kBuildPer = kBuildCap / kBuildThreads;  // 16 elements per thread
+constexpr size_t kBuildSmem = (size_t)kBuildCap * 8 + 32 * 256 * 2 + 256 * 4 * 2 + 64 * 4;
+
+struct BuildItem {   // one cloud of a batched build
+  const float* raw;
+  float4* sorted;
+  int* pos_of;
+  float4* leaf_lo;
+  float4* leaf_hi;
+  float4* sup_lo;
+  float4* sup_hi;
+  int stride_f;
+  int n;
+};
+
+#ifdef __CUDACC__
+namespace cg = cooperative_groups;
+
+template <int CL>
+__global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const BuildItem* __restrict__ items, const __grid_constant__ BuildItem single) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint2* buf = reinterpret_cast<uint2*>(smem_raw);                                    // [kBuildCap] (key, original index)
+  unsigned short* wh = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kBuildCap * 8);  // [32 warps][256 digits]
+  int* cta_cnt = reinterpret_cast<int*>(smem_raw + (size_t)kBuildCap * 8 + 32 * 256 * 2);    // [256] digit counts of this CTA
+  int* base = cta_cnt + 256;                                                           // [256] first destination of (digit, this CTA)
+  int* s_mm = base + 256;                                                              // [6] bbox as ordered ints, [8..] scratch
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const BuildItem it = items ? items[blockIdx.x / CL] : single;  // a lone cloud travels as a kernel parameter (no descriptor upload)
+  const int n = it.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int padded = ((n + 1023) / 1024) * 1024;
+  const int g0 = rank * kBuildCap;  // first global position / element index of this CTA's slice
+
+  // ---- bounding box over the finite points (k_bbox's arithmetic), cluster-wide
+  if (tid < 6) s_mm[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
+  __syncthreads();
+  {
+    int mn0 = 0x7fffffff, mn1 = 0x7fffffff, mn2 = 0x7fffffff, mx0 = (int)0x80000000, mx1 = (int)0x80000000, mx2 = (int)0x80000000;
+#pragma unroll 4
+    for (int b = 0; b < kBuildPer; b++) {
+      const int i = g0 + warp * (32 * kBuildPer) + b * 32 + lane;
+      if (i < n) {
+        const float* p = it.raw + (size_t)i * it.stride_f;
+        const float x = p[0], y = p[1], z = p[2];
+        if (finite3(x, y, z)) {
+          const int ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
+          mn0 = min(mn0, ox); mn1 = min(mn1, oy); mn2 = min(mn2, oz);
+          mx0 = max(mx0, ox); mx1 = max(mx1, oy); mx2 = max(mx2, oz);
+        }
+      }
+    }
+    mn0 = __reduce_min_sync(0xffffffffu, mn0); mn1 = __reduce_min_sync(0xffffffffu, mn1); mn2 = __reduce_min_sync(0xffffffffu, mn2);
+    mx0 = __reduce_max_sync(0xffffffffu, mx0); mx1 = __reduce_max_sync(0xffffffffu, mx1); mx2 = __reduce_max_sync(0xffffffffu, mx2);
+    if (lane == 0) {
+      atomicMin(&s_mm[0], mn0); atomicMin(&s_mm[1], mn1); atomicMin(&s_mm[2], mn2);
+      atomicMax(&s_mm[3], mx0); atomicMax(&s_mm[4], mx1); atomicMax(&s_mm[5], mx2);
+    }
+  }
+  cluster.sync();
+  int mm[6];
+  {
+#pragma unroll
+    for (int d = 0; d < 6; d++) mm[d] = d < 3 ? 0x7fffffff : (int)0x80000000;
+    for (int c = 0; c < CL; c++) {
+      const int* peer = cluster.map_shared_rank(s_mm, c);
+#pragma unroll
+      for (int d = 0; d < 3; d++) { mm[d] = min(mm[d], peer[d]); mm[3 + d] = max(mm[3 + d], peer[3 + d]); }
+    }
+  }
+  // ---- 30-bit Hilbert keys (k_morton_keys's arithmetic) into this CTA's slice
+  {
+    const float mnx = ord2f(mm[0]), mny = ord2f(mm[1]), mnz = ord2f(mm[2]);
+    const float ext = fmaxf(fmaxf(ord2f(mm[3]) - mnx, ord2f(mm[4]) - mny), fmaxf(ord2f(mm[5]) - mnz, 1.0e-6f));
+    const float sc = 1023.0f / ext;
+#pragma unroll 4
+    for (int b = 0; b < kBuildPer; b++) {
+      const int e = warp * (32 * kBuildPer) + b * 32 + lane;
+      const int i = g0 + e;
+      unsigned int key = 0xffffffffu;  // non-finite points and the padding sort last
+      if (i < n) {
+        const float* p = it.raw + (size_t)i * it.stride_f;
+        const float x = p[0], y = p[1], z = p[2];
+        if (finite3(x, y, z)) {
+          const unsigned int ix = (unsigned int)fminf(fmaxf((x - mnx) * sc, 0.f), 1023.f);
+          const unsigned int iy = (unsigned int)fminf(fmaxf((y - mny) * sc, 0.f), 1023.f);
+          const unsigned int iz = (unsigned int)fminf(fmaxf((z - mnz) * sc, 0.f), 1023.f);
+          key = hilbert30(ix, iy, iz);
+        }
+      }
+      buf[e] = make_uint2(key, i < n ? (unsigned int)i : 0xffffffffu);
+    }
+  }
+  __syncthreads();
+
+  // ---- stable LSD radix sort, 4 passes of 8 bits, scatter through distributed shared memory
+  const unsigned int lt = (1u << lane) - 1u;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 8 * pass;
+    for (int i = tid; i < 32 * 256 / 2; i += kBuildThreads) reinterpret_cast<unsigned int*>(wh)[i] = 0u;
+    __syncthreads();
+    // every warp ranks its own contiguous 512 elements in order, 32 at a time: rank inside (warp, digit) = running count of the
+    // digit in this warp + number of equal digits in lower lanes (stable)
+    uint2 e[kBuildPer];
+    unsigned short off[kBuildPer];
+    unsigned short* mywh = wh + warp * 256;
+#pragma unroll
+    for (int b = 0; b < kBuildPer; b++) {
+      e[b] = buf[warp * (32 * kBuildPer) + b * 32 + lane];
+      const unsigned int d = (e[b].x >> shift) & 255u;
+      const unsigned int peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      unsigned int bs = 0;
+      if (lane == leader) { bs = mywh[d]; mywh[d] = (unsigned short)(bs + __popc(peers)); }
+      bs = __shfl_sync(0xffffffffu, bs, leader);
+      off[b] = (unsigned short)(bs + __popc(peers & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over the warps (in place) and the CTA's count
+    if (tid < 256) {
+      int run = 0;
+#pragma unroll 8
+      for (int w = 0; w < 32; w++) { const int c = wh[w * 256 + tid]; wh[w * 256 + tid] = (unsigned short)run; run += c; }
+      cta_cnt[tid] = run;
+    }
+    cluster.sync();  // every CTA has its elements in registers (its buffer may be overwritten) and its digit counts published
+    if (tid < 256) {
+      int tot = 0, before = 0;
+      for (int c = 0; c < CL; c++) {
+        const int v = cluster.map_shared_rank(cta_cnt, c)[tid];
+        tot += v;
+        if (c < rank) before += v;
+      }
+      // exclusive scan of the digit totals over the 256 digits (8 warps)
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      if (lane == 31) s_mm[8 + warp] = inc;
+      // (threads 0..255 are warps 0..7: a named barrier over them would do; the block barrier below is simpler)
+      base[tid] = inc - tot + before;  // completed with the warp offsets after the barrier
+    }
+    __syncthreads();
+    if (tid < 256) {
+      int woff = 0;
+      for (int w = 0; w < warp; w++) woff += s_mm[8 + w];
+      base[tid] += woff;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < kBuildPer; b++) {
+      const unsigned int d = (e[b].x >> shift) & 255u;
+      const int dst = base[d] + (int)mywh[d] + (int)off[b];
+      uint2* peer = cluster.map_shared_rank(buf, dst / kBuildCap);
+      peer[dst % kBuildCap] = e[b];
+    }
+    cluster.sync();  // all scatters have landed before anybody reads its buffer again
+  }
+
+  // ---- emit this CTA's slice of the structure (k_bvh_leaves's work): one super-node (1024 positions, 32 leaves) per step
+  float* s_lo = reinterpret_cast<float*>(wh);        // [32][3] leaf boxes of the current super-node (the histogram area is free now)
+  float* s_hi = s_lo + 96;
+  for (int j = 0; j < kBuildCap / 1024; j++) {
+    const int sg = g0 + j * 1024 + tid;              // global sorted position
+    if (g0 + j * 1024 >= padded) break;              // uniform over the block
+    const uint2 kv = buf[j * 1024 + tid];
+    float x = INFINITY, y = INFINITY, z = INFINITY;
+    int idx = kPadIdx;
+    if (kv.x != 0xffffffffu) {
+      idx = (int)kv.y;
+      const float* p = it.raw + (size_t)idx * it.stride_f;
+      x = p[0]; y = p[1]; z = p[2];
+      it.pos_of[idx] = sg;
+    } else if (kv.y != 0xffffffffu) {
+      it.pos_of[kv.y] = -1;                          // a non-finite point of the cloud: dropped from the structure
+    }
+    it.sorted[sg] = make_float4(x, y, z, bits_idx(idx));
+    const bool valid = idx != kPadIdx;
+    float lx = valid ? x : INFINITY, ly = valid ? y : INFINITY, lz = valid ? z : INFINITY;
+    float hx = valid ? x : -INFINITY, hy = valid ? y : -INFINITY, hz = valid ? z : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lx = fminf(lx, __shfl_xor_sync(0xffffffffu, lx, o)); ly = fminf(ly, __shfl_xor_sync(0xffffffffu, ly, o)); lz = fminf(lz, __shfl_xor_sync(0xffffffffu, lz, o));
+      hx = fmaxf(hx, __shfl_xor_sync(0xffffffffu, hx, o)); hy = fmaxf(hy, __shfl_xor_sync(0xffffffffu, hy, o)); hz = fmaxf(hz, __shfl_xor_sync(0xffffffffu, hz, o));
+    }
+    const int leaf = sg >> 5;
+    if (lane == 0) {
+      it.leaf_lo[leaf] = make_float4(lx, ly, lz, 0.f);
+      it.leaf_hi[leaf] = make_float4(hx, hy, hz, 0.f);
+      s_lo[warp * 3 + 0] = lx; s_lo[warp * 3 + 1] = ly; s_lo[warp * 3 + 2] = lz;
+      s_hi[warp * 3 + 0] = hx; s_hi[warp * 3 + 1] = hy; s_hi[warp * 3 + 2] = hz;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float ax = s_lo[lane * 3 + 0], ay = s_lo[lane * 3 + 1], az = s_lo[lane * 3 + 2], bx = s_hi[lane * 3 + 0], by = s_hi[lane * 3 + 1], bz = s_hi[lane * 3 + 2];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ax = fminf(ax, __shfl_xor_sync(0xffffffffu, ax, o)); ay = fminf(ay, __shfl_xor_sync(0xffffffffu, ay, o)); az = fminf(az, __shfl_xor_sync(0xffffffffu, az, o));
+        bx = fmaxf(bx, __shfl_xor_sync(0xffffffffu, bx, o)); by = fmaxf(by, __shfl_xor_sync(0xffffffffu, by, o)); bz = fmaxf(bz, __shfl_xor_sync(0xffffffffu, bz, o));
+      }
+      if (lane == 0) {
+        it.sup_lo[sg >> 10] = make_float4(ax, ay, az, 0.f);
+        it.sup_hi[sg >> 10] = make_float4(bx, by, bz, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace b2r

@@ -188,10 +188,9 @@ struct KnnRegs {
 constexpr int kKnnRegK = 20;
 
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
-                                                                long long* prof) {
-  __shared__ int nbr[K][kKnnThreads];  // neighbour indices, ascending (d2, idx), for the covariance pass
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void knn_cov_reg_body(const Bvh& b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov, int block_x, int (*nbr)[kKnnThreads],
+                                                 long long* prof) {
+  const int s = block_x * blockDim.x + threadIdx.x;
   const int leaf = s >> 5;
   if (leaf >= b.nleaf) return;  // whole warps only
   const float4 q = b.sp[s];
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const flo
       v[2] = max(v[2], __shfl_xor_sync(F, v[2], o));
     }
     const int ntile = __shfl_sync(F, L.n_tile, 0), ncoop = __shfl_sync(F, L.n_coop, 0);
-    if ((threadIdx.x & 31) == 0) {
+    if ((threadIdx.x & 31) == 0 && prof) {
       long long* o = prof + (size_t)leaf * 8;
       o[0] = t1 - t0; o[1] = ntile; o[2] = ncoop; o[3] = v[0]; o[4] = v[1]; o[5] = 0; o[6] = v[2]; o[7] = 0;
     }
@@ -226,6 +225,29 @@ __global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const flo
     const float* p = raw + (size_t)nbr[j][tx] * stride_f;
     return make_float3(p[0], p[1], p[2]);
   }, cov + (size_t)s * 6);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
+                                                                long long* prof) {
+  __shared__ int nbr[K][kKnnThreads];  // neighbour indices, ascending (d2, idx), for the covariance pass
+  knn_cov_reg_body<K>(b, raw, stride_f, cov, blockIdx.x, nbr, prof);
+}
+
+// the same for MANY clouds in one launch (blockIdx.y = cloud): the batched path registers a whole set of keyframe clouds at once,
+// and one cloud alone fills less than a wave (0.86) with a 3x tail — together the clouds keep every SM busy
+struct KnnBatchItem {
+  Bvh b;
+  const float* raw;
+  double* cov;
+  int stride_f;
+  int pad;
+};
+template <int K>
+__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg_batch(const KnnBatchItem* __restrict__ items) {
+  __shared__ int nbr[K][kKnnThreads];
+  const KnnBatchItem it = items[blockIdx.y];
+  knn_cov_reg_body<K>(it.b, it.raw, it.stride_f, it.cov, blockIdx.x, nbr, nullptr);
 }
 
 // deterministic block reduction of NV doubles per thread; result valid in thread 0
@@ -257,14 +279,27 @@ __device__ __forceinline__ void block_reduce(double* v, double* smem /* NV * 32 
 // `out` may live in host-mapped pinned memory: the result then lands in host memory straight from the kernel together with a
 // checksum word (out[NV+1]; out[NV] carries `extra` or is unused) and `flag` = `seq`, so the host can spin on it instead of paying a
 // memcpy + stream sync.
+// finish_stored: thread 0 of every block has already written the block's NV sums to partials[blockIdx.x][0..NV)
+template <int NV>
+__device__ __forceinline__ void finish_stored(double* partials, double* out, unsigned int* counter, unsigned long long* flag = nullptr,
+                                              unsigned long long seq = 0, unsigned long long* extra = nullptr);
+
 template <int NV>
 __device__ __forceinline__ void finish_partials(const double* v, double* partials, double* out, unsigned int* counter,
                                                 unsigned long long* flag = nullptr, unsigned long long seq = 0,
                                                 unsigned long long* extra = nullptr) {
-  __shared__ bool is_last;
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < NV; i++) partials[(size_t)blockIdx.x * NV + i] = v[i];
+  }
+  finish_stored<NV>(partials, out, counter, flag, seq, extra);
+}
+
+template <int NV>
+__device__ __forceinline__ void finish_stored(double* partials, double* out, unsigned int* counter, unsigned long long* flag,
+                                              unsigned long long seq, unsigned long long* extra) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
     __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     is_last = (t == gridDim.x - 1);

@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < p.src.nleaf * kLeaf) pt = p.src.sp[s];
   const bool is_point = idx_bits(pt.w) != kPadIdx;
+  if (!is_point) { pt.x = 0.f; pt.y = 0.f; pt.z = 0.f; }  // padding entries carry +inf coordinates: inf * 0 would poison the sums below
   double T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = p.xe[i];
