@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libb200reg.so")
+# B2R_LIB selects an A/B build variant of the same ABI (tools/build_variant.sh); the product library is the default
+LIB_PATH = os.environ.get("B2R_LIB") or os.path.join(_HERE, "_lib", "libb200reg.so")
 
 B2R_OK = 0
 B2R_EINVAL, B2R_ENODEVICE, B2R_ECUDA, B2R_ESTATE, B2R_EUNSUPPORTED, B2R_ENCCL = -1, -2, -3, -4, -5, -6
@@ -26,6 +27,12 @@ class Result(C.Structure):
 
 class Pair(C.Structure):
     _fields_ = [("source", C.c_int32), ("target", C.c_int32), ("guess", C.c_float * 16)]
+
+
+class InformationParams(C.Structure):
+    _fields_ = [("use_const_inf_matrix", C.c_int32), ("reserved", C.c_int32), ("const_stddev_x", C.c_double), ("const_stddev_q", C.c_double),
+                ("var_gain_a", C.c_double), ("min_stddev_x", C.c_double), ("max_stddev_x", C.c_double), ("min_stddev_q", C.c_double),
+                ("max_stddev_q", C.c_double), ("fitness_score_thresh", C.c_double)]
 
 
 class OdometryParams(C.Structure):
@@ -101,6 +108,9 @@ SYMBOLS = [
     ("b2r_batch_cloud_count", C.c_int, [_VP]),
     ("b2r_batch_synchronize", C.c_int, [_VP]),
     ("b2r_batch_align", C.c_int, [_VP, C.POINTER(Pair), _SZ, C.c_int, C.c_double, C.POINTER(Result)]),
+    ("b2r_batch_calc_fitness_score", C.c_int, [_VP, C.POINTER(Pair), _SZ, C.c_double, _F64P]),
+    ("b2r_information_params_default", C.c_int, [C.POINTER(InformationParams)]),
+    ("b2r_information_from_fitness", C.c_int, [C.POINTER(InformationParams), C.c_double, _F64P]),
     ("b2r_batch_last_rounds", C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("b2r_loop_argmin", C.c_int, [C.POINTER(Result), _SZ, C.c_double, _I32P]),
     ("b2r_nccl_unique_id", C.c_int, [_VP, _SZ]),

@@ -325,11 +325,11 @@ static bool use_cluster_build() {
   static const bool on = !getenv("B2R_CUB_SORT");
   return on;
 }
-template <int CL>
+template <int CL, bool SINGLE>
 static cudaError_t launch_cluster_build_t(const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -339,14 +339,22 @@ static cudaError_t launch_cluster_build_t(const BuildItem* d_items, const BuildI
   la[0].id = cudaLaunchAttributeClusterDimension;
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   lc.attrs = la; lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, k_bvh_build_cluster<CL>, d_items, single);
+  return cudaLaunchKernelEx(&lc, k_bvh_build_cluster<CL, SINGLE>, d_items, single);
 }
 static cudaError_t launch_cluster_build(int cl, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
+  if (d_items) {
+    switch (cl) {
+      case 1: return launch_cluster_build_t<1, false>(d_items, single, n_clouds, st);
+      case 2: return launch_cluster_build_t<2, false>(d_items, single, n_clouds, st);
+      case 4: return launch_cluster_build_t<4, false>(d_items, single, n_clouds, st);
+      default: return launch_cluster_build_t<8, false>(d_items, single, n_clouds, st);
+    }
+  }
   switch (cl) {
-    case 1: return launch_cluster_build_t<1>(d_items, single, n_clouds, st);
-    case 2: return launch_cluster_build_t<2>(d_items, single, n_clouds, st);
-    case 4: return launch_cluster_build_t<4>(d_items, single, n_clouds, st);
-    default: return launch_cluster_build_t<8>(d_items, single, n_clouds, st);
+    case 1: return launch_cluster_build_t<1, true>(d_items, single, n_clouds, st);
+    case 2: return launch_cluster_build_t<2, true>(d_items, single, n_clouds, st);
+    case 4: return launch_cluster_build_t<4, true>(d_items, single, n_clouds, st);
+    default: return launch_cluster_build_t<8, true>(d_items, single, n_clouds, st);
   }
 }
 

@@ -195,15 +195,16 @@ extern "C" int b2r_batch_cloud_count(const b2r_batch* b) {
 // Search structure (bvh_build.cuh) + FastGICP::calculate_covariances for every cloud a batch names that does not have them yet:
 // one cluster-build launch per cluster size and one k-NN launch for all of them (what setInputSource / setInputTarget make the
 // reference pay per call: kd-tree build + covariances, loop_detector.hpp:122,136)
-static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs) {
+static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool need_cov) {
   b2r_handle* h = b->eng;
   cudaStream_t st = h->st;
   std::vector<Cloud*> todo;
+  std::vector<char> queued(b->clouds.size(), 0);
   for (size_t i = 0; i < n_pairs; i++)
     for (int32_t id : {pairs[i].source, pairs[i].target}) {
       Cloud* c = b->clouds[id];
-      if (c->cov_ready || c->n == 0) continue;
-      c->cov_ready = true;  // marks "queued" for the de-duplication; the launches below are stream-ordered before any use
+      if (queued[id] || c->n == 0 || (c->bvh_ready && (c->cov_ready || !need_cov))) continue;
+      queued[id] = 1;
       todo.push_back(c);
     }
   if (todo.empty()) return B2R_OK;
@@ -212,7 +213,7 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
     for (Cloud* c : todo) {
       if (c->bvh_ready) continue;
       const int cl = cluster_size_for(c->n);
-      if (!cl || !use_cluster_build()) { c->cov_ready = false; int rc = build_bvh(h, *c, h->bc[0], st); c->cov_ready = true; if (rc) return rc; continue; }
+      if (!cl || !use_cluster_build()) { int rc = build_bvh(h, *c, h->bc[0], st); if (rc) return rc; continue; }
       int rc = bvh_alloc(*c);
       if (rc) return rc;
       by_cl[cl == 1 ? 0 : cl == 2 ? 1 : cl == 4 ? 2 : 3].push_back(c);
@@ -229,6 +230,10 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
       size_t k0 = 0;
       for (int g = 0; g < 4; g++)
         for (Cloud* c : by_cl[g]) b->h_build[k0++] = build_item(*c);
+      if (getenv("B2R_DEBUG_BUILD"))
+        for (size_t i = 0; i < total; i++)
+          fprintf(stderr, "build item %zu: raw %p sorted %p pos_of %p n %d stride %d (d_build %p)\n", i, (const void*)b->h_build[i].raw, (void*)b->h_build[i].sorted,
+                  (void*)b->h_build[i].pos_of, b->h_build[i].n, b->h_build[i].stride_f, (void*)b->d_build.p);
       B2R_CUDA(cudaMemcpyAsync(b->d_build.p, b->h_build, total * sizeof(BuildItem), cudaMemcpyHostToDevice, st));
       k0 = 0;
       for (int g = 0; g < 4; g++) {
@@ -241,10 +246,17 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
       }
     }
   }
+  if (!need_cov) return B2R_OK;
+  {
+    std::vector<Cloud*> need;
+    for (Cloud* c : todo) if (!c->cov_ready) need.push_back(c);
+    todo.swap(need);
+  }
+  if (todo.empty()) return B2R_OK;
   const int k = h->cfg.k_correspondences;
   for (Cloud* c : todo) B2R_CUDA(c->cov.reserve((size_t)c->nsup * 1024 * 6 + 6));
   if (k != kKnnRegK) {  // other k: the generic shared-memory-list kernel, one launch per cloud
-    for (Cloud* c : todo) { c->cov_ready = false; int rc = build_cov(h, *c, h->bc[0], st); if (rc) return rc; }
+    for (Cloud* c : todo) { int rc = build_cov(h, *c, h->bc[0], st); if (rc) return rc; }
     return B2R_OK;
   }
   B2R_CUDA(b->d_knn.reserve(todo.size()));
@@ -266,15 +278,18 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
     k_knn_cov_reg_batch<kKnnRegK><<<dim3(max_blocks, (unsigned)todo.size()), kKnnThreads, 0, st>>>(b->d_knn.p);
     TEL_END(&h->tel, KC_KNN_COV, 1, st); }
   B2R_CUDA(cudaGetLastError());
+  for (Cloud* c : todo) c->cov_ready = true;
   return B2R_OK;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static size_t pair_ws_bytes(size_t n_pad) {
+static size_t pair_ws_bytes(size_t n_pad, bool fit_only) {
   size_t t = 0;
-  t += 2 * align_up(n_pad * sizeof(int), 256);          // corr
   t += 2 * align_up(n_pad * sizeof(int), 256);          // cpos
-  t += 2 * align_up(n_pad * 6 * sizeof(double), 256);   // mahal
+  if (!fit_only) {
+    t += 2 * align_up(n_pad * sizeof(int), 256);          // corr
+    t += 2 * align_up(n_pad * 6 * sizeof(double), 256);   // mahal
+  }
   t += align_up(n_pad * sizeof(float), 256);            // d2
   t += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);  // partials
   return t;
@@ -320,7 +335,7 @@ static int wait_word(b2r_batch* b, unsigned long long need_seq, size_t* count) {
 }
 
 // One chunk: pairs[0..m) -> d_rep[0..m) (device).  Every pair of the chunk is in flight at once; rounds cover all of them.
-static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const LmCfg& cfg, PairReport* d_rep) {
+static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const LmCfg& cfg, PairReport* d_rep, bool fit_only) {
   b2r_handle* h = b->eng;
   cudaStream_t st = h->st;
   size_t ws_total = 0, max_pad = 0;
@@ -329,7 +344,7 @@ static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const 
     const Cloud& t = *b->clouds[pairs[i].target];
     if (s.n == 0 || t.n == 0) continue;
     const size_t n_pad = (size_t)s.nsup * 1024;
-    ws_total += pair_ws_bytes(n_pad);
+    ws_total += pair_ws_bytes(n_pad, fit_only);
     if (n_pad > max_pad) max_pad = n_pad;
   }
   B2R_CUDA(b->ws.reserve(ws_total + 256));
@@ -352,11 +367,14 @@ static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const 
     fill_pair_geometry(P, s, t);
     double x[16];
     colmajor_f_to_row_d(pairs[i].guess, x);
-    fill_pair_start(P, x, PM_FIRST);
+    // a stand-alone fitness evaluation (calc_fitness_score) is a pair that starts in its fitness round at the given pose
+    fill_pair_start(P, x, fit_only ? PM_FIT : PM_FIRST);
     const size_t n_pad = (size_t)s.nsup * 1024;
-    for (int k = 0; k < 2; k++) { P.corr[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
     for (int k = 0; k < 2; k++) { P.cpos[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
-    for (int k = 0; k < 2; k++) { P.mahal[k] = reinterpret_cast<double*>(wp); wp += align_up(n_pad * 6 * sizeof(double), 256); }
+    if (!fit_only) {
+      for (int k = 0; k < 2; k++) { P.corr[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
+      for (int k = 0; k < 2; k++) { P.mahal[k] = reinterpret_cast<double*>(wp); wp += align_up(n_pad * 6 * sizeof(double), 256); }
+    }
     P.d2 = reinterpret_cast<float*>(wp); wp += align_up(n_pad * sizeof(float), 256);
     P.partials = reinterpret_cast<double*>(wp); wp += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);
     P.report = d_rep + i;
@@ -404,7 +422,7 @@ __global__ void k_pack_results(const PairReport* rep, int n, b2r_result* out, in
 }
 
 // pairs[0..n) -> d_reports[0..n) on the device (no host copy of the results)
-static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool want_fitness, double fit_max_range) {
+static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool want_fitness, double fit_max_range, bool fit_only = false) {
   b2r_handle* h = b->eng;
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   for (size_t i = 0; i < n_pairs; i++) {
@@ -415,7 +433,7 @@ static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool w
   }
   int rc = batch_sync_builds(b, false);  // the main stream waits for every outstanding upload / build
   if (rc) return rc;
-  rc = batch_build_structures(b, pairs, n_pairs);
+  rc = batch_build_structures(b, pairs, n_pairs, !fit_only);
   if (rc) return rc;
   const size_t chunk = std::min(b->max_chunk, std::max<size_t>(n_pairs, 1));
   rc = batch_host_staging(b, std::max(chunk, n_pairs));
@@ -425,7 +443,7 @@ static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool w
   b->last_rounds = b->last_pair_rounds = 0;
   for (size_t c0 = 0; c0 < n_pairs; c0 += chunk) {
     const size_t m = std::min(chunk, n_pairs - c0);
-    rc = batch_run_chunk(b, pairs + c0, m, cfg, b->d_reports.p + c0);
+    rc = batch_run_chunk(b, pairs + c0, m, cfg, b->d_reports.p + c0, fit_only);
     if (rc) return rc;
   }
   return B2R_OK;
@@ -446,6 +464,53 @@ extern "C" int b2r_batch_align(b2r_batch* b, const b2r_pair* pairs, size_t n_pai
     b->last_pair_rounds += (unsigned long long)b->h_reports[i].rounds;
     if (!want_fitness) out[i].fitness = NAN;
   }
+  return B2R_OK;
+}
+
+// InformationMatrixCalculator::calc_fitness_score(cloud1, cloud2, relpose, max_range)
+// (/root/reference/src/hdl_graph_slam/information_matrix_calculator.cpp:49-80; callers apps/hdl_graph_slam_nodelet.cpp:235,569):
+// kd-tree on cloud1, cloud2 transformed by relpose.cast<float>(), mean of the squared NN distances <= max_range, DBL_MAX if none.
+// Here for MANY edges at once, on the keyframes' cached search structures (pair.target = cloud1, pair.source = cloud2,
+// pair.guess = relpose as float): one search + one reduction launch covers all of them.
+extern "C" int b2r_batch_calc_fitness_score(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, double max_range, double* scores) {
+  if (!b || (n_pairs && (!pairs || !scores))) return fail(B2R_EINVAL, "NULL argument");
+  if (n_pairs == 0) return B2R_OK;
+  int rc = batch_run(b, pairs, n_pairs, true, max_range, true);
+  if (rc) return rc;
+  cudaStream_t st = b->eng->st;
+  B2R_CUDA(cudaMemcpyAsync(b->h_reports, b->d_reports.p, n_pairs * sizeof(PairReport), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  b->eng->tel.d2h += n_pairs * sizeof(PairReport);
+  for (size_t i = 0; i < n_pairs; i++) scores[i] = b->h_reports[i].r.fitness;
+  return B2R_OK;
+}
+
+// InformationMatrixCalculator::calc_information_matrix's mapping from a fitness score to the edge information
+// (information_matrix_calculator.cpp:25-47, weight(): information_matrix_calculator.hpp:39-42): inf = diag(1/w_x x3, 1/w_q x3)
+extern "C" int b2r_information_params_default(b2r_information_params* p) {
+  if (!p) return fail(B2R_EINVAL, "NULL argument");
+  p->use_const_inf_matrix = 0; p->reserved = 0;
+  p->const_stddev_x = 0.5; p->const_stddev_q = 0.1; p->var_gain_a = 20.0;
+  p->min_stddev_x = 0.1; p->max_stddev_x = 5.0; p->min_stddev_q = 0.05; p->max_stddev_q = 0.2;
+  p->fitness_score_thresh = 0.5;
+  return B2R_OK;
+}
+
+extern "C" int b2r_information_from_fitness(const b2r_information_params* p, double fitness_score, double inf_diag[6]) {
+  if (!p || !inf_diag) return fail(B2R_EINVAL, "NULL argument");
+  double wx, wq;
+  if (p->use_const_inf_matrix) {
+    wx = p->const_stddev_x; wq = p->const_stddev_q;  // :26-31 (divides by the stddev itself, as the reference does)
+  } else {
+    auto weight = [](double a, double max_x, double min_y, double max_y, double x) {
+      const double y = (1.0 - std::exp(-a * x)) / (1.0 - std::exp(-a * max_x));
+      return min_y + (max_y - min_y) * y;
+    };
+    // float w_x = weight(...): the reference narrows the weights to float before dividing (:40-41)
+    wx = (double)(float)weight(p->var_gain_a, p->fitness_score_thresh, p->min_stddev_x * p->min_stddev_x, p->max_stddev_x * p->max_stddev_x, fitness_score);
+    wq = (double)(float)weight(p->var_gain_a, p->fitness_score_thresh, p->min_stddev_q * p->min_stddev_q, p->max_stddev_q * p->max_stddev_q, fitness_score);
+  }
+  for (int i = 0; i < 3; i++) { inf_diag[i] = 1.0 / wx; inf_diag[3 + i] = 1.0 / wq; }
   return B2R_OK;
 }
 

@@ -41,7 +41,9 @@ struct BuildItem {   // one cloud of a batched build
 #ifdef __CUDACC__
 namespace cg = cooperative_groups;
 
-template <int CL>
+// SINGLE: the one cloud travels as a kernel parameter (no descriptor upload); else blockIdx.x / CL indexes the descriptor list.
+// (Two instantiations rather than a run-time select between a parameter-space struct and a global one.)
+template <int CL, bool SINGLE>
 __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const BuildItem* __restrict__ items, const __grid_constant__ BuildItem single) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint2* buf = reinterpret_cast<uint2*>(smem_raw);                                    // [kBuildCap] (key, original index)
@@ -51,7 +53,9 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
   int* s_mm = base + 256;                                                              // [6] bbox as ordered ints, [8..] scratch
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const BuildItem it = items ? items[blockIdx.x / CL] : single;  // a lone cloud travels as a kernel parameter (no descriptor upload)
+  BuildItem it;
+  if constexpr (SINGLE) it = single;
+  else it = items[blockIdx.x / CL];
   const int n = it.n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int padded = ((n + 1023) / 1024) * 1024;

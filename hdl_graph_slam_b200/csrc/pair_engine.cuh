@@ -78,7 +78,8 @@ struct PairDev {
   double x0[12];           // last accepted pose
   double H[21], b[6], d[6];
   double y0, lambda, nu;
-  int it, li, cur, wc, delta_conv, converged, lm_failed, pad1;
+  int it, li, cur, wc, delta_conv, converged, lm_failed;
+  int have_seed;           // 1 once a correspondence set exists in buffer set `cur` (seeds of the next search)
 };
 
 // ------------------------------------------------------------------------------------------------ message publication
@@ -205,6 +206,7 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
     return;
   }
   if (mode == PM_FIRST) {
+    p.have_seed = 1;
     for (int i = 0; i < 21; i++) p.H[i] = r[i];
     for (int i = 0; i < 6; i++) p.b[i] = r[21 + i];
     p.y0 = r[27];
@@ -266,8 +268,11 @@ __host__ __device__ inline void lm_advance(PairDev& p, const double* r, const Lm
 // update_correspondences for every active pair: exact 1-NN of every transformed source point in the pair's target.
 // C lanes per query (bvh.cuh): C = 4 shortens the per-warp chain (single pair: the kernel time is the slowest warp),
 // C = 1 minimises instructions per query (batches: thousands of warps per SM-slot, throughput is what counts).
+#ifndef B2R_SEARCH_MINBLOCKS
+#define B2R_SEARCH_MINBLOCKS 8
+#endif
 template <int C>
-__global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
+__global__ void __launch_bounds__(kLinThreads, B2R_SEARCH_MINBLOCKS) k_pair_search(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // batch mode: active[0] = number of pairs still in flight, active[1..] = their indices (k_pair_compact, previous round); the host
   // sizes grid.y from a count that may be one round stale, so surplus rows exit here
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kLinThreads, 8) k_pair_search(PairDev* pairs, 
   const bool writer = (gt & 31) < Q;
   const int cur = p.cur;
   const int wset = (mode == PM_FIRST) ? cur : (cur ^ 1);
-  const bool use_seed = mode != PM_FIRST;
+  const bool use_seed = p.have_seed != 0;  // false in the first round of an align and in a stand-alone fitness evaluation
   const float lim = fit_search ? cfg.fit_lim : cfg.lim;
   const double thr2 = fit_search ? (double)INFINITY : cfg.thr2;
   Bvh tgt = p.tgt;

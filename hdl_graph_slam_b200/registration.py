@@ -435,6 +435,13 @@ class RegistrationBatch:
             return res
         return [_result_dict(r) for r in res[:n]]
 
+    def calcFitnessScore(self, edges, max_range=np.finfo(np.float64).max):
+        """InformationMatrixCalculator::calc_fitness_score for many edges: edges = list of (cloud1 id, cloud2 id, relpose 4x4) -> scores"""
+        arr = self._pairs([(c2, c1, rel) for c1, c2, rel in edges])
+        out = np.empty(max(len(edges), 1), np.float64)
+        check(self._lib.b2r_batch_calc_fitness_score(self._b, arr, len(edges), max_range, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out[: len(edges)]
+
     def lastRounds(self):
         a, b = C.c_uint64(), C.c_uint64()
         check(self._lib.b2r_batch_last_rounds(self._b, C.byref(a), C.byref(b)))
@@ -463,3 +470,15 @@ class RegistrationBatch:
         if raw:
             return list(best[:ng]), res
         return list(best[:ng]), [_result_dict(r) for r in res[:n]]
+
+
+def information_from_fitness(fitness_score, **params):
+    """InformationMatrixCalculator::calc_information_matrix after the fitness score: diagonal of the 6x6 information matrix"""
+    lib = _capi.load()
+    p = _capi.InformationParams()
+    check(lib.b2r_information_params_default(C.byref(p)))
+    for k, v in params.items():
+        setattr(p, k, v)
+    out = np.empty(6, np.float64)
+    check(lib.b2r_information_from_fitness(C.byref(p), float(fitness_score), out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out

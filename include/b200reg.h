@@ -241,6 +241,29 @@ int b2r_batch_synchronize(b2r_batch* b);
 /* align every pair; want_fitness != 0 also evaluates getFitnessScore(fitness_max_range) at each final pose (loop_detector.hpp:146;
  * max_range is compared with the SQUARED distance as in information_matrix_calculator.cpp:69), else fitness = NaN */
 int b2r_batch_align(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, int want_fitness, double fitness_max_range, b2r_result* out);
+/* replaces InformationMatrixCalculator::calc_fitness_score(cloud1, cloud2, relpose, max_range)
+ * (src/hdl_graph_slam/information_matrix_calculator.cpp:49-80; called per odometry edge and per accepted loop,
+ * apps/hdl_graph_slam_nodelet.cpp:235,569) for MANY edges at once on the keyframes' cached search structures:
+ * pairs[i].target = cloud1 (the tree), pairs[i].source = cloud2 (transformed), pairs[i].guess = relpose.cast<float>() column-major.
+ * scores[i] = mean squared NN distance over the neighbours with d2 <= max_range, DBL_MAX when there is none. */
+int b2r_batch_calc_fitness_score(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, double max_range, double* scores);
+/* the rest of InformationMatrixCalculator::calc_information_matrix (information_matrix_calculator.cpp:25-47, weight() at
+ * information_matrix_calculator.hpp:39-42): fitness score -> diagonal of the 6x6 information matrix (x,y,z, then rotation).
+ * Defaults of the reference's rosparams: b2r_information_params_default. */
+typedef struct b2r_information_params {
+  int32_t use_const_inf_matrix; /* false */
+  int32_t reserved;
+  double const_stddev_x;        /* 0.5  */
+  double const_stddev_q;        /* 0.1  */
+  double var_gain_a;            /* 20.0 */
+  double min_stddev_x;          /* 0.1  */
+  double max_stddev_x;          /* 5.0  */
+  double min_stddev_q;          /* 0.05 */
+  double max_stddev_q;          /* 0.2  */
+  double fitness_score_thresh;  /* 0.5 (information_matrix_calculator.cpp:21; 2.5 in the header's template load(), :31) */
+} b2r_information_params;
+int b2r_information_params_default(b2r_information_params* p);
+int b2r_information_from_fitness(const b2r_information_params* p, double fitness_score, double inf_diag[6]);
 /* rounds (launch pairs) and pair-rounds (sum over rounds of the pairs in flight) of the last batch: the work the roofline divides by */
 int b2r_batch_last_rounds(const b2r_batch* b, uint64_t* rounds, uint64_t* pair_rounds);
 /* the selection of LoopDetector::matching over one group's records (loop_detector.hpp:147,160-163): index of the best converged

@@ -92,3 +92,16 @@ def test_argmin_tie_rule_library_and_mirror():
     assert both([0.7, 0.6, 0.9], [1, 1, 1]) == -1  # best above fitness_score_thresh: "loop not found"
     assert both([], []) == -1
     assert both([0.1, 0.2], [0, 0]) == -1
+
+
+def test_information_matrix_from_fitness_matches_reference_formula():
+    """information_matrix_calculator.cpp:25-47 + weight() (information_matrix_calculator.hpp:39-42), restated with numpy"""
+    def ref(f, a=20.0, thr=0.5, mnx=0.1, mxx=5.0, mnq=0.05, mxq=0.2):
+        def w(min_y, max_y):
+            y = (1.0 - np.exp(-a * f)) / (1.0 - np.exp(-a * thr))
+            return np.float32(min_y + (max_y - min_y) * y)
+        return np.array([1.0 / np.float64(w(mnx ** 2, mxx ** 2))] * 3 + [1.0 / np.float64(w(mnq ** 2, mxq ** 2))] * 3)
+    for f in (0.0, 0.01, 0.2, 0.5, 3.0):
+        assert np.allclose(pkg.information_from_fitness(f), ref(f), rtol=1e-15, atol=0)
+    assert np.allclose(pkg.information_from_fitness(0.3, fitness_score_thresh=2.5, var_gain_a=10.0), ref(0.3, a=10.0, thr=2.5), rtol=1e-15)
+    assert np.allclose(pkg.information_from_fitness(0.3, use_const_inf_matrix=1), [2.0, 2.0, 2.0, 10.0, 10.0, 10.0])

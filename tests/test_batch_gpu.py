@@ -157,3 +157,26 @@ def test_loop_detect_single_rank_equals_align_plus_argmin(synth):
         assert best[g] == pkg.loop_argmin([_as_result(q) for q in res[group_first[g]: group_first[g + 1]]], 0.5)
     assert any(b >= 0 for b in best)
     lb.close()
+
+
+def test_calc_fitness_score_batched_on_cached_keyframes(synth, oracle):
+    """InformationMatrixCalculator::calc_fitness_score(cloud1, cloud2, relpose, max_range)
+    (src/hdl_graph_slam/information_matrix_calculator.cpp:49-80) for several edges at once, on keyframe clouds registered once:
+    kd-tree on cloud1, cloud2 transformed by relpose.cast<float>(), mean squared NN distance over d2 <= max_range."""
+    frames = {f: synth.scan("vlp16_16k", frame=f, stride=8) for f in (0, 1, 2, 30)}
+    lb = pkg.RegistrationBatch(params={"registration_method": "FAST_GICP"})
+    ids = {f: lb.addCloud(c) for f, c in frames.items()}
+    edges = []
+    for (a, b_) in ((0, 1), (1, 2), (0, 2), (2, 0), (0, 30)):
+        rel = (np.linalg.inv(synth.pose_matrix(a)) @ synth.pose_matrix(b_) @ perturb(a * 7 + b_, 0.05, 0.5)).astype(np.float32)
+        edges.append((a, b_, rel))
+    for max_range in (np.finfo(np.float64).max, 2.0, 0.01):
+        got = lb.calcFitnessScore([(ids[a], ids[b_], rel) for a, b_, rel in edges], max_range)
+        for (a, b_, rel), g in zip(edges, got):
+            want, used, _ = oracle.fitness(frames[a], frames[b_], rel, max_range)
+            assert (g == want == np.finfo(np.float64).max) if used == 0 else abs(g - want) <= 1e-12 * want
+    # the clouds stay usable for registrations afterwards (covariances are built on demand), and an align leaves the scores unchanged
+    again = lb.calcFitnessScore([(ids[0], ids[1], edges[0][2])], 2.0)
+    lb.align([(ids[1], ids[0], edges[0][2])], True, 2.0)
+    assert lb.calcFitnessScore([(ids[0], ids[1], edges[0][2])], 2.0)[0] == again[0]
+    lb.close()
