@@ -35,6 +35,14 @@ class InformationParams(C.Structure):
                 ("max_stddev_q", C.c_double), ("fitness_score_thresh", C.c_double)]
 
 
+class PrefilterParams(C.Structure):
+    _fields_ = [("deskewing", C.c_int32), ("use_base_link_transform", C.c_int32), ("scan_period", C.c_double), ("angular_velocity", C.c_float * 3),
+                ("base_link_transform", C.c_float * 16), ("use_distance_filter", C.c_int32), ("distance_near_thresh", C.c_double),
+                ("distance_far_thresh", C.c_double), ("downsample_method", C.c_int32), ("downsample_resolution", C.c_float),
+                ("outlier_removal_method", C.c_int32), ("statistical_mean_k", C.c_int32), ("statistical_stddev", C.c_double),
+                ("radius_radius", C.c_double), ("radius_min_neighbors", C.c_int32), ("reserved", C.c_int32)]
+
+
 class OdometryParams(C.Structure):
     _fields_ = [
         ("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double),
@@ -90,9 +98,13 @@ SYMBOLS = [
     ("b2r_ndt_get_voxels", C.c_int, [_VP, _SZ, C.POINTER(_SZ), C.POINTER(C.c_int64), _I32P, _F64P, _F64P, _I32P, _I32P]),
     ("b2r_ndt_derivatives_at", C.c_int, [_VP, _F64P, _F64P, _F64P, _F64P, C.POINTER(C.c_uint64)]),
     ("b2r_voxelgrid", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_float, _VP, C.POINTER(_SZ), _I32P, _I32P]),
+    ("b2r_voxelgrid_device", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_float, C.POINTER(_VP), C.POINTER(_SZ)]),
     ("b2r_distance_filter", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, C.c_double, _VP, C.POINTER(_SZ)]),
     ("b2r_radius_outlier_removal", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, C.c_int, _VP, C.POINTER(_SZ)]),
     ("b2r_statistical_outlier_removal", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_int, C.c_double, _VP, C.POINTER(_SZ)]),
+    ("b2r_deskew", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, _F32P, _VP]),
+    ("b2r_prefilter_params_default", C.c_int, [C.POINTER(PrefilterParams)]),
+    ("b2r_prefilter", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_int, C.POINTER(PrefilterParams), _VP, C.POINTER(_VP), C.POINTER(_SZ)]),
     ("b2r_odometry_create", C.c_int, [_VP, C.POINTER(OdometryParams), C.POINTER(_VP)]),
     ("b2r_odometry_destroy", None, [_VP]),
     ("b2r_odometry_matching", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),

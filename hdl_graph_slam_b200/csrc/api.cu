@@ -65,6 +65,13 @@ struct b2r_handle {
   DevBuf<float> tmp_f;
   DevBuf<int> tmp_i;
   DevBuf<float4> tmp_f4;
+  // device-resident prefilter chain: ping-pong record buffers, keep flags, compaction scratch
+  DevBuf<float> pf_buf[2];
+  DevBuf<unsigned char> pf_flags;
+  DevBuf<int> pf_blocks;
+  SorStats* pf_stats = nullptr;
+  int* pf_total = nullptr;
+  int* pf_h_total = nullptr; int* pf_h_total_dev = nullptr;
   BuildCtx bc[2];                   // per-stream build scratch (main stream, prefetch stream)
   bool knn_smem_attr = false, stat_smem_attr = false;
   int n_sm = 148;
@@ -230,6 +237,10 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   for (int i = 0; i < 2; i++) { h->corr[i].release(); h->cpos[i].release(); h->mahal[i].release(); }
   h->d2.release(); h->partials.release();
   h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->bc[0].release(); h->bc[1].release();
+  h->pf_buf[0].release(); h->pf_buf[1].release(); h->pf_flags.release(); h->pf_blocks.release();
+  if (h->pf_stats) cudaFree(h->pf_stats);
+  if (h->pf_total) cudaFree(h->pf_total);
+  if (h->pf_h_total) cudaFreeHost(h->pf_h_total);
   h->ndt_work.release();
   h->vg_work.release();
   h->tel.release();
@@ -1003,121 +1014,257 @@ extern "C" int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t str
   return voxelgrid_filter(h->vg_work, h->st, in, n, stride_bytes, leaf, out, n_out, out_keys, out_counts);
 }
 
-// ------------------------------------------------------------------------------------------------ prefilter chain (next rows)
-static int upload_aux(b2r_handle* h, const void* in, size_t n, size_t stride_bytes) {
+extern "C" int b2r_voxelgrid_device(b2r_handle* h, const void* d_in, size_t n, size_t stride_bytes, float leaf, const void** d_out, size_t* n_out) {
+  if (!h || !n_out || !d_out || (n && !d_in)) return fail(B2R_EINVAL, "NULL argument");
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  if (!(leaf > 0.f)) return fail(B2R_EINVAL, "leaf must be positive");
   if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
-  Cloud& c = h->aux;
-  c.n = n;
-  c.stride_f = (int)(stride_bytes / 4);
-  c.invalidate();
-  B2R_CUDA(c.raw.reserve(n * c.stride_f + 4));
-  c.raw_view = c.raw.p;
-  if (n) B2R_CUDA(cudaMemcpyAsync(c.raw.p, in, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
-  h->tel.h2d += n * stride_bytes;
-  return B2R_OK;
-}
-
-static size_t compact_records(const void* in, size_t n, size_t stride_bytes, const unsigned char* keep, void* out) {
-  size_t m = 0;
-  const char* src = (const char*)in;
-  char* dst = (char*)out;
-  for (size_t i = 0; i < n; i++)
-    if (keep[i]) { std::memcpy(dst + m * stride_bytes, src + i * stride_bytes, stride_bytes); m++; }
-  return m;
-}
-
-extern "C" int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, void* out,
-                                   size_t* n_out) {
-  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
-  *n_out = 0;
+  *d_out = nullptr; *n_out = 0;
   if (n == 0) return B2R_OK;
-  int rc = upload_aux(h, in, n, stride_bytes);
+  size_t m = 0;
+  int overflow = 0;
+  int rc = voxelgrid_device(h->vg_work, h->st, (const float*)d_in, n, stride_bytes, leaf, &m, &overflow);
   if (rc) return rc;
-  B2R_CUDA(h->tmp_i.reserve(n / 4 + 4));
-  unsigned char* d_flags = reinterpret_cast<unsigned char*>(h->tmp_i.p);
-  { TEL_BEGIN(&h->tel, h->st);
-    k_distance_flags<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->aux.raw_view, h->aux.stride_f, (int)n, near_thresh, far_thresh, d_flags);
-    TEL_END(&h->tel, KC_MISC, 1, h->st); }
-  B2R_CUDA(cudaGetLastError());
-  std::vector<unsigned char> keep(n);
-  B2R_CUDA(cudaMemcpyAsync(keep.data(), d_flags, n, cudaMemcpyDeviceToHost, h->st));
-  B2R_CUDA(cudaStreamSynchronize(h->st));
-  h->tel.d2h += n;
-  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
+  h->tel.d2h += 8;
+  if (overflow) { *d_out = d_in; *n_out = n; return 1; }  // PCL: "Leaf size is too small": the input passes through
+  *d_out = h->vg_work.out.p;
+  *n_out = m;
   return B2R_OK;
 }
 
-static int knn_stat(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int k, int mode, std::vector<float>& vals) {
+// ------------------------------------------------------------------------------------------------ prefilter chain (next rows)
+// Every stage is device -> device: records in an engine buffer, keep flags and the order-preserving compaction on the GPU; only
+// the 4-byte count of a stage comes back (host-mapped word) because the next stage's launch geometry needs it.
+static int pf_reserve(b2r_handle* h, size_t n, int sf) {
+  B2R_CUDA(h->pf_buf[0].reserve(n * sf + 8));
+  B2R_CUDA(h->pf_buf[1].reserve(n * sf + 8));
+  B2R_CUDA(h->pf_flags.reserve(n + 8));
+  B2R_CUDA(h->pf_blocks.reserve((n + kCompactBlock - 1) / kCompactBlock + 8));
+  B2R_CUDA(h->tmp_f.reserve(n + 8));
+  if (!h->pf_stats) {
+    B2R_CUDA(cudaMalloc(&h->pf_stats, sizeof(SorStats)));
+    B2R_CUDA(cudaMalloc(&h->pf_total, 4 * sizeof(int)));
+    B2R_CUDA(cudaHostAlloc(&h->pf_h_total, 4 * sizeof(int), cudaHostAllocMapped));
+    B2R_CUDA(cudaHostGetDevicePointer((void**)&h->pf_h_total_dev, h->pf_h_total, 0));
+  }
+  return B2R_OK;
+}
+
+// records d_in[0..n) with flags (already on the device) -> d_out, *m = kept count
+static int pf_compact(b2r_handle* h, const float* d_in, size_t n, int sf, float* d_out, size_t* m) {
+  const unsigned nb = (unsigned)((n + kCompactBlock - 1) / kCompactBlock);
+  unsigned char* flags = h->pf_flags.p;
+  { TEL_BEGIN(&h->tel, h->st);
+    k_compact_count<<<nb, kCompactBlock, 0, h->st>>>(flags, (int)n, h->pf_blocks.p);
+    k_compact_scan<<<1, 1024, 0, h->st>>>(h->pf_blocks.p, (int)nb, h->pf_total, h->pf_h_total_dev);
+    k_compact_scatter<<<nb, kCompactBlock, 0, h->st>>>(d_in, sf, flags, (int)n, h->pf_blocks.p, d_out);
+    TEL_END(&h->tel, KC_MISC, 3, h->st); }
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaStreamSynchronize(h->st));
+  h->tel.d2h += 4;
+  *m = (size_t)h->pf_h_total[0];
+  return B2R_OK;
+}
+
+// PrefilteringNodelet::distance_filter (apps/prefiltering_nodelet.cpp:164-180)
+static int pf_distance(b2r_handle* h, const float* d_in, size_t n, int sf, double near_t, double far_t, float* d_out, size_t* m) {
+  { TEL_BEGIN(&h->tel, h->st);
+    k_distance_flags<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(d_in, sf, (int)n, near_t, far_t, h->pf_flags.p);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  return pf_compact(h, d_in, n, sf, d_out, m);
+}
+
+// per-point neighbour statistic of the cloud against itself (k-th squared distance, or mean distance to the k-1 nearest others)
+static int pf_knn_stat(b2r_handle* h, const float* d_in, size_t n, int sf, int k, int mode) {
   if (k < 1 || k > 64) return fail(B2R_EINVAL, "neighbour count must be in [1,64]");
-  int rc = upload_aux(h, in, n, stride_bytes);
+  Cloud& c = h->aux;
+  c.n = n; c.stride_f = sf; c.invalidate();
+  c.raw_view = d_in;
+  int rc = ensure_grid(h, c);
   if (rc) return rc;
-  rc = ensure_grid(h, h->aux);
-  if (rc) return rc;
-  B2R_CUDA(h->tmp_f.reserve(n + 1));
-  k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<int*>(h->tmp_f.p), (int)n, 0x7fc00000);  // NaN = dropped (non-finite) point
+  k_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(reinterpret_cast<int*>(h->tmp_f.p), (int)n, 0x7fc00000);  // NaN = non-finite point
   const size_t smem = (size_t)k * kKnnThreads * sizeof(unsigned long long);
   if (smem > 48 * 1024 && !h->stat_smem_attr) {
     B2R_CUDA(cudaFuncSetAttribute(k_knn_stat, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
     h->stat_smem_attr = true;
   }
-  const size_t padded = (size_t)h->aux.nsup * 1024;
+  const size_t padded = (size_t)c.nsup * 1024;
   { TEL_BEGIN(&h->tel, h->st);
-    k_knn_stat<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(h->aux.bvh(), k, mode, h->tmp_f.p);
+    k_knn_stat<<<(unsigned)(padded / kKnnThreads), kKnnThreads, smem, h->st>>>(c.bvh(), k, mode, h->tmp_f.p);
     TEL_END(&h->tel, KC_MISC, 1, h->st); }
   B2R_CUDA(cudaGetLastError());
-  vals.resize(n);
-  B2R_CUDA(cudaMemcpyAsync(vals.data(), h->tmp_f.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-  B2R_CUDA(cudaStreamSynchronize(h->st));
-  h->tel.d2h += n * sizeof(float);
   return B2R_OK;
+}
+
+// pcl::RadiusOutlierRemoval (apps/prefiltering_nodelet.cpp:83-90,151-162)
+static int pf_radius(b2r_handle* h, const float* d_in, size_t n, int sf, double radius, int min_neighbors, float* d_out, size_t* m) {
+  int rc = pf_knn_stat(h, d_in, n, sf, min_neighbors + 1, 0);
+  if (rc) return rc;
+  k_radius_flags<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, (int)n, radius * radius, h->pf_flags.p);
+  return pf_compact(h, d_in, n, sf, d_out, m);
+}
+
+// pcl::StatisticalOutlierRemoval (apps/prefiltering_nodelet.cpp:73-81,151-162)
+static int pf_statistical(b2r_handle* h, const float* d_in, size_t n, int sf, int mean_k, double stddev_mul, float* d_out, size_t* m) {
+  int rc = pf_knn_stat(h, d_in, n, sf, mean_k + 1, 1);
+  if (rc) return rc;
+  k_sor_stats<<<1, 1024, 0, h->st>>>(h->tmp_f.p, (int)n, stddev_mul, h->pf_stats);
+  k_sor_flags<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->tmp_f.p, (int)n, h->pf_stats, h->pf_flags.p);
+  return pf_compact(h, d_in, n, sf, d_out, m);
+}
+
+static int pf_check(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, const void* out, const size_t* n_out) {
+  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  return B2R_OK;
+}
+// host records -> pf_buf[0]
+static int pf_upload(b2r_handle* h, const void* in, size_t n, size_t stride_bytes) {
+  int rc = pf_reserve(h, n, (int)(stride_bytes / 4));
+  if (rc) return rc;
+  B2R_CUDA(cudaMemcpyAsync(h->pf_buf[0].p, in, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
+  h->tel.h2d += n * stride_bytes;
+  return B2R_OK;
+}
+static int pf_download(b2r_handle* h, const float* d, size_t m, size_t stride_bytes, void* out) {
+  if (m) {
+    B2R_CUDA(cudaMemcpyAsync(out, d, m * stride_bytes, cudaMemcpyDeviceToHost, h->st));
+    B2R_CUDA(cudaStreamSynchronize(h->st));
+    h->tel.d2h += m * stride_bytes;
+  }
+  return B2R_OK;
+}
+
+extern "C" int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, void* out,
+                                   size_t* n_out) {
+  int rc = pf_check(h, in, n, stride_bytes, out, n_out);
+  if (rc) return rc;
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *n_out = 0;
+  if (n == 0) return B2R_OK;
+  rc = pf_upload(h, in, n, stride_bytes);
+  if (!rc) rc = pf_distance(h, h->pf_buf[0].p, n, (int)(stride_bytes / 4), near_thresh, far_thresh, h->pf_buf[1].p, n_out);
+  if (!rc) rc = pf_download(h, h->pf_buf[1].p, *n_out, stride_bytes, out);
+  return rc;
 }
 
 extern "C" int b2r_radius_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double radius, int min_neighbors, void* out,
                                           size_t* n_out) {
-  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  int rc = pf_check(h, in, n, stride_bytes, out, n_out);
+  if (rc) return rc;
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   *n_out = 0;
   if (n == 0) return B2R_OK;
-  std::vector<float> kth;
-  int rc = knn_stat(h, in, n, stride_bytes, min_neighbors + 1, 0, kth);
-  if (rc) return rc;
-  std::vector<unsigned char> keep(n);
-  const double r2 = radius * radius;
-  // PCL RadiusOutlierRemoval (dense path): outlier iff the (min_pts+1)-th neighbour is missing or farther than the radius
-  for (size_t i = 0; i < n; i++) keep[i] = (kth[i] == kth[i] && !std::isinf(kth[i]) && !((double)kth[i] > r2)) ? 1 : 0;
-  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
-  return B2R_OK;
+  rc = pf_upload(h, in, n, stride_bytes);
+  if (!rc) rc = pf_radius(h, h->pf_buf[0].p, n, (int)(stride_bytes / 4), radius, min_neighbors, h->pf_buf[1].p, n_out);
+  if (!rc) rc = pf_download(h, h->pf_buf[1].p, *n_out, stride_bytes, out);
+  return rc;
 }
 
 extern "C" int b2r_statistical_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, void* out,
                                                size_t* n_out) {
-  if (!h || !n_out || (n && (!in || !out))) return fail(B2R_EINVAL, "NULL argument");
+  int rc = pf_check(h, in, n, stride_bytes, out, n_out);
+  if (rc) return rc;
   B2R_CUDA(cudaSetDevice(h->cfg.device_id));
   *n_out = 0;
   if (n == 0) return B2R_OK;
-  std::vector<float> dist;
-  int rc = knn_stat(h, in, n, stride_bytes, mean_k + 1, 1, dist);
+  rc = pf_upload(h, in, n, stride_bytes);
+  if (!rc) rc = pf_statistical(h, h->pf_buf[0].p, n, (int)(stride_bytes / 4), mean_k, stddev_mul, h->pf_buf[1].p, n_out);
+  if (!rc) rc = pf_download(h, h->pf_buf[1].p, *n_out, stride_bytes, out);
+  return rc;
+}
+
+extern "C" int b2r_deskew(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double scan_period, const float angular_velocity[3], void* out) {
+  size_t dummy = 0;
+  int rc = pf_check(h, in, n, stride_bytes, out, &dummy);
   if (rc) return rc;
-  // PCL StatisticalOutlierRemoval::applyFilterIndices: double sums over the valid points in index order
-  double sum = 0, sq_sum = 0;
-  size_t valid = 0;
-  for (size_t i = 0; i < n; i++) {
-    if (dist[i] != dist[i]) continue;
-    sum += (double)dist[i];
-    sq_sum += (double)dist[i] * (double)dist[i];
-    valid++;
+  if (!angular_velocity) return fail(B2R_EINVAL, "NULL argument");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  if (n == 0) return B2R_OK;
+  rc = pf_upload(h, in, n, stride_bytes);
+  if (rc) return rc;
+  // ang_v *= -1 (prefiltering_nodelet.cpp:217)
+  k_deskew<<<(unsigned)((n + 255) / 256), 256, 0, h->st>>>(h->pf_buf[0].p, (int)(stride_bytes / 4), (int)n, scan_period, -angular_velocity[0], -angular_velocity[1],
+                                                          -angular_velocity[2], h->pf_buf[1].p);
+  B2R_CUDA(cudaGetLastError());
+  return pf_download(h, h->pf_buf[1].p, n, stride_bytes, out);
+}
+
+extern "C" int b2r_prefilter_params_default(b2r_prefilter_params* p) {
+  if (!p) return fail(B2R_EINVAL, "NULL argument");
+  std::memset(p, 0, sizeof(*p));
+  p->deskewing = 0; p->scan_period = 0.1;                              // prefiltering_nodelet.cpp:36,234
+  p->use_distance_filter = 1; p->distance_near_thresh = 1.0; p->distance_far_thresh = 100.0;  // :96-98
+  p->downsample_method = B2R_DOWNSAMPLE_VOXELGRID; p->downsample_resolution = 0.1f;            // :51-52
+  p->outlier_removal_method = B2R_OUTLIER_STATISTICAL;                  // :71
+  p->statistical_mean_k = 20; p->statistical_stddev = 1.0;              // :73-74
+  p->radius_radius = 0.8; p->radius_min_neighbors = 2;                  // :83-84
+  return B2R_OK;
+}
+
+// PrefilteringNodelet::cloud_callback (apps/prefiltering_nodelet.cpp:106-136): deskewing -> [base_link transform] -> distance_filter ->
+// downsample -> outlier_removal, the cloud never leaving HBM between the stages
+extern "C" int b2r_prefilter(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int device_input, const b2r_prefilter_params* p,
+                             void* out_host, const void** d_out, size_t* n_out) {
+  if (!h || !p || !n_out || (n && !points)) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *n_out = 0;
+  if (d_out) *d_out = nullptr;
+  if (n == 0) return B2R_OK;  // cloud_callback returns on an empty cloud (:108-110)
+  const int sf = (int)(stride_bytes / 4);
+  int rc = pf_reserve(h, n, sf);
+  if (rc) return rc;
+  const float* cur = nullptr;
+  int nxt = 0;  // index of the free ping-pong buffer
+  if (device_input) cur = (const float*)points;
+  else {
+    B2R_CUDA(cudaMemcpyAsync(h->pf_buf[0].p, points, n * stride_bytes, cudaMemcpyHostToDevice, h->st));
+    h->tel.h2d += n * stride_bytes;
+    cur = h->pf_buf[0].p; nxt = 1;
   }
-  std::vector<unsigned char> keep(n, 0);
-  if (valid > 0) {
-    const double mean = sum / (double)valid;
-    const double variance = (sq_sum - sum * sum / (double)valid) / ((double)valid - 1.0);
-    const double stddev = std::sqrt(variance);
-    const double thresh = mean + stddev_mul * stddev;
-    for (size_t i = 0; i < n; i++) keep[i] = (dist[i] == dist[i] && !((double)dist[i] > thresh)) ? 1 : 0;
+  size_t m = n;
+  auto advance = [&]() { cur = h->pf_buf[nxt].p; nxt ^= 1; };
+  const unsigned nb256 = (unsigned)((n + 255) / 256);
+  if (p->deskewing) {  // :182-243
+    k_deskew<<<nb256, 256, 0, h->st>>>(cur, sf, (int)m, p->scan_period, -p->angular_velocity[0], -p->angular_velocity[1], -p->angular_velocity[2], h->pf_buf[nxt].p);
+    advance();
   }
-  *n_out = compact_records(in, n, stride_bytes, keep.data(), out);
+  if (p->use_base_link_transform) {  // :114-129
+    XfArgPF X;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) X.Tf[r * 4 + c] = p->base_link_transform[c * 4 + r];
+    k_transform_records<<<nb256, 256, 0, h->st>>>(cur, sf, (int)m, X, h->pf_buf[nxt].p);
+    advance();
+  }
+  if (p->use_distance_filter) {  // :131
+    rc = pf_distance(h, cur, m, sf, p->distance_near_thresh, p->distance_far_thresh, h->pf_buf[nxt].p, &m);
+    if (rc) return rc;
+    advance();
+  }
+  if (p->downsample_method == B2R_DOWNSAMPLE_VOXELGRID && m) {  // :132
+    size_t mv = 0;
+    int overflow = 0;
+    rc = voxelgrid_device(h->vg_work, h->st, cur, m, stride_bytes, p->downsample_resolution, &mv, &overflow);
+    if (rc) return rc;
+    if (!overflow) { cur = h->vg_work.out.p; m = mv; }  // (the voxel grid writes its own buffer: the ping-pong pair stays free)
+  }
+  if (p->outlier_removal_method == B2R_OUTLIER_STATISTICAL && m) {  // :133
+    rc = pf_statistical(h, cur, m, sf, p->statistical_mean_k, p->statistical_stddev, h->pf_buf[nxt].p, &m);
+    if (rc) return rc;
+    advance();
+  } else if (p->outlier_removal_method == B2R_OUTLIER_RADIUS && m) {
+    rc = pf_radius(h, cur, m, sf, p->radius_radius, p->radius_min_neighbors, h->pf_buf[nxt].p, &m);
+    if (rc) return rc;
+    advance();
+  }
+  B2R_CUDA(cudaGetLastError());
+  *n_out = m;
+  if (d_out) *d_out = cur;
+  if (out_host) return pf_download(h, cur, m, stride_bytes, out_host);
+  B2R_CUDA(cudaStreamSynchronize(h->st));
   return B2R_OK;
 }
 

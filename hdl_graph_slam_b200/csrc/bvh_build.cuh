@@ -41,27 +41,29 @@ struct BuildItem {   // one cloud of a batched build
 #ifdef __CUDACC__
 namespace cg = cooperative_groups;
 
-// SINGLE: the one cloud travels as a kernel parameter (no descriptor upload); else blockIdx.x / CL indexes the descriptor list.
-// (Two instantiations rather than a run-time select between a parameter-space struct and a global one.)
-template <int CL, bool SINGLE>
-__global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const BuildItem* __restrict__ items, const __grid_constant__ BuildItem single) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint2* buf = reinterpret_cast<uint2*>(smem_raw);                                    // [kBuildCap] (key, original index)
-  unsigned short* wh = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kBuildCap * 8);  // [32 warps][256 digits]
-  int* cta_cnt = reinterpret_cast<int*>(smem_raw + (size_t)kBuildCap * 8 + 32 * 256 * 2);    // [256] digit counts of this CTA
-  int* base = cta_cnt + 256;                                                           // [256] first destination of (digit, this CTA)
-  int* s_mm = base + 256;                                                              // [6] bbox as ordered ints, [8..] scratch
-  cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
-  BuildItem it;
-  if constexpr (SINGLE) it = single;
-  else it = items[blockIdx.x / CL];
-  const int n = it.n;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int padded = ((n + 1023) / 1024) * 1024;
-  const int g0 = rank * kBuildCap;  // first global position / element index of this CTA's slice
+// ---- shared-memory layout and the two cluster-wide building blocks (also used by the voxel-grid kernel, voxelgrid.cuh)
+struct ClusterSmem {
+  uint2* buf;            // [kBuildCap] (key, original index)
+  unsigned short* wh;    // [32 warps][256 digits]
+  int* cta_cnt;          // [256] digit counts of this CTA
+  int* base;             // [256] first destination of (digit, this CTA)
+  int* s_mm;             // [6] bbox as ordered ints, [8..63] scratch
+};
+__device__ __forceinline__ ClusterSmem cluster_smem(unsigned char* smem_raw) {
+  ClusterSmem S;
+  S.buf = reinterpret_cast<uint2*>(smem_raw);
+  S.wh = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kBuildCap * 8);
+  S.cta_cnt = reinterpret_cast<int*>(smem_raw + (size_t)kBuildCap * 8 + 32 * 256 * 2);
+  S.base = S.cta_cnt + 256;
+  S.s_mm = S.base + 256;
+  return S;
+}
 
-  // ---- bounding box over the finite points (k_bbox's arithmetic), cluster-wide
+// bounding box of the finite points of a cloud spread over the cluster (element i of CTA `rank` = point g0 + i), as ordered ints
+template <int CL>
+__device__ __forceinline__ void cluster_bbox(cg::cluster_group& cluster, const ClusterSmem& S, const float* __restrict__ raw, int stride_f, int n, int g0, int* mm) {
+  int* s_mm = S.s_mm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < 6) s_mm[tid] = tid < 3 ? 0x7fffffff : (int)0x80000000;
   __syncthreads();
   {
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     for (int b = 0; b < kBuildPer; b++) {
       const int i = g0 + warp * (32 * kBuildPer) + b * 32 + lane;
       if (i < n) {
-        const float* p = it.raw + (size_t)i * it.stride_f;
+        const float* p = raw + (size_t)i * stride_f;
         const float x = p[0], y = p[1], z = p[2];
         if (finite3(x, y, z)) {
           const int ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
@@ -87,7 +89,6 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     }
   }
   cluster.sync();
-  int mm[6];
   {
 #pragma unroll
     for (int d = 0; d < 6; d++) mm[d] = d < 3 ? 0x7fffffff : (int)0x80000000;
@@ -97,32 +98,18 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
       for (int d = 0; d < 3; d++) { mm[d] = min(mm[d], peer[d]); mm[3 + d] = max(mm[3 + d], peer[3 + d]); }
     }
   }
-  // ---- 30-bit Hilbert keys (k_morton_keys's arithmetic) into this CTA's slice
-  {
-    const float mnx = ord2f(mm[0]), mny = ord2f(mm[1]), mnz = ord2f(mm[2]);
-    const float ext = fmaxf(fmaxf(ord2f(mm[3]) - mnx, ord2f(mm[4]) - mny), fmaxf(ord2f(mm[5]) - mnz, 1.0e-6f));
-    const float sc = 1023.0f / ext;
-#pragma unroll 4
-    for (int b = 0; b < kBuildPer; b++) {
-      const int e = warp * (32 * kBuildPer) + b * 32 + lane;
-      const int i = g0 + e;
-      unsigned int key = 0xffffffffu;  // non-finite points and the padding sort last
-      if (i < n) {
-        const float* p = it.raw + (size_t)i * it.stride_f;
-        const float x = p[0], y = p[1], z = p[2];
-        if (finite3(x, y, z)) {
-          const unsigned int ix = (unsigned int)fminf(fmaxf((x - mnx) * sc, 0.f), 1023.f);
-          const unsigned int iy = (unsigned int)fminf(fmaxf((y - mny) * sc, 0.f), 1023.f);
-          const unsigned int iz = (unsigned int)fminf(fmaxf((z - mnz) * sc, 0.f), 1023.f);
-          key = hilbert30(ix, iy, iz);
-        }
-      }
-      buf[e] = make_uint2(key, i < n ? (unsigned int)i : 0xffffffffu);
-    }
-  }
-  __syncthreads();
+}
 
-  // ---- stable LSD radix sort, 4 passes of 8 bits, scatter through distributed shared memory
+// stable LSD radix sort of the (key, value) pairs held in the cluster's distributed shared memory (CL x kBuildCap pairs, every CTA
+// full), ascending by the 32-bit key: 4 passes of 8 bits; the scatter writes straight into the peer CTAs' shared memory
+template <int CL>
+__device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, const ClusterSmem& S, int rank) {
+  uint2* buf = S.buf;
+  unsigned short* wh = S.wh;
+  int* cta_cnt = S.cta_cnt;
+  int* base = S.base;
+  int* s_mm = S.s_mm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll 1
   for (int pass = 0; pass < 4; pass++) {
@@ -186,6 +173,55 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     }
     cluster.sync();  // all scatters have landed before anybody reads its buffer again
   }
+
+}
+
+// SINGLE: the one cloud travels as a kernel parameter (no descriptor upload); else blockIdx.x / CL indexes the descriptor list.
+// (Two instantiations rather than a run-time select between a parameter-space struct and a global one.)
+template <int CL, bool SINGLE>
+__global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const BuildItem* __restrict__ items, const __grid_constant__ BuildItem single) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ClusterSmem S = cluster_smem(smem_raw);
+  uint2* buf = S.buf;
+  unsigned short* wh = S.wh;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  BuildItem it;
+  if constexpr (SINGLE) it = single;
+  else it = items[blockIdx.x / CL];
+  const int n = it.n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int padded = ((n + 1023) / 1024) * 1024;
+  const int g0 = rank * kBuildCap;  // first global position / element index of this CTA's slice
+
+  int mm[6];
+  cluster_bbox<CL>(cluster, S, it.raw, it.stride_f, n, g0, mm);
+  // ---- 30-bit Hilbert keys (k_morton_keys's arithmetic) into this CTA's slice
+  {
+    const float mnx = ord2f(mm[0]), mny = ord2f(mm[1]), mnz = ord2f(mm[2]);
+    const float ext = fmaxf(fmaxf(ord2f(mm[3]) - mnx, ord2f(mm[4]) - mny), fmaxf(ord2f(mm[5]) - mnz, 1.0e-6f));
+    const float sc = 1023.0f / ext;
+#pragma unroll 4
+    for (int b = 0; b < kBuildPer; b++) {
+      const int e = warp * (32 * kBuildPer) + b * 32 + lane;
+      const int i = g0 + e;
+      unsigned int key = 0xffffffffu;  // non-finite points and the padding sort last
+      if (i < n) {
+        const float* p = it.raw + (size_t)i * it.stride_f;
+        const float x = p[0], y = p[1], z = p[2];
+        if (finite3(x, y, z)) {
+          const unsigned int ix = (unsigned int)fminf(fmaxf((x - mnx) * sc, 0.f), 1023.f);
+          const unsigned int iy = (unsigned int)fminf(fmaxf((y - mny) * sc, 0.f), 1023.f);
+          const unsigned int iz = (unsigned int)fminf(fmaxf((z - mnz) * sc, 0.f), 1023.f);
+          key = hilbert30(ix, iy, iz);
+        }
+      }
+      buf[e] = make_uint2(key, i < n ? (unsigned int)i : 0xffffffffu);
+    }
+  }
+  __syncthreads();
+
+  cluster_radix_sort<CL>(cluster, S, rank);
 
   // ---- emit this CTA's slice of the structure (k_bvh_leaves's work): one super-node (1024 positions, 32 leaves) per step
   float* s_lo = reinterpret_cast<float*>(wh);        // [32][3] leaf boxes of the current super-node (the histogram area is free now)

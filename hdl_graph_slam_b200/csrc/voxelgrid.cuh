@@ -9,14 +9,17 @@
 //   k_vg_centroid  <- one thread per voxel, sequential float32 sums of x,y,z,intensity in that order, / count
 // Output order = ascending voxel key (as PCL).  Keys, counts and ordering are bit-exact against the oracle; centroids too,
 // because the within-voxel summation order is pinned (PCL leaves it implementation-defined).
-// The sort is the CUDA toolkit's cub::DeviceRadixSort (a library primitive, like a plain cuBLAS call); every other stage
-// is hand-written.
+// Clouds of up to 131 072 points (every scan of the BASELINE configs) take ONE kernel on a thread-block cluster
+// (k_voxelgrid_cluster): bounding box, keys, the radix sort through distributed shared memory of bvh_build.cuh, head scan and
+// centroids without leaving the cluster, output left in device memory.  Larger inputs fall back to the kernel chain below, whose
+// sort and scan are the CUDA toolkit's cub::DeviceRadixSort / DeviceScan.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <climits>
 #include <vector>
 #include "engine.cuh"
+#include "bvh_build.cuh"
 
 namespace b2r {
 
@@ -35,7 +38,8 @@ struct VoxelWork {
   int* mm = nullptr;
   VgGeom* geom = nullptr;
   VgGeom* h_geom = nullptr;  // pinned
-  int* h_total = nullptr;    // pinned
+  int* h_total = nullptr;    // pinned + mapped: [0] voxel count, [1] overflow flag
+  int* h_total_dev = nullptr;
   Telemetry* tel = nullptr;
   void release() {
     in.release(); out.release(); keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); flags.release(); slots.release();
@@ -130,55 +134,264 @@ __global__ void k_vg_centroid(const float* __restrict__ raw, int stride_f, int n
   ocounts[slot] = e - s;
 }
 
-inline int voxelgrid_filter(VoxelWork& W, cudaStream_t st, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
-                            size_t* n_out, int32_t* out_keys, int32_t* out_counts) {
-  *n_out = 0;
-  if (n == 0) return B2R_OK;
-  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+// ------------------------------------------------------------------------------------------------ one-kernel cluster path
+struct VgArgs {
+  const float* in;     // device records
+  int stride_f;
+  int n;
+  float leaf;
+  float* out;          // device, same record layout as the input
+  int* okeys;          // device (may be null)
+  int* ocounts;        // device (may be null)
+  int* total;          // device: [0] voxel count, [1] overflow flag
+  volatile int* h_total;  // host-mapped twin of `total` (or null): the count reaches the host without a copy
+};
+
+template <int CL>
+__global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __grid_constant__ VgArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ClusterSmem S = cluster_smem(smem_raw);
+  uint2* buf = S.buf;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = A.n;
+  const int g0 = rank * kBuildCap;
+  int mm[6];
+  cluster_bbox<CL>(cluster, S, A.in, A.stride_f, n, g0, mm);
+  // ---- geometry (k_vg_params), computed redundantly by every thread from the cluster-wide bounding box
+  const float inv_leaf = 1.0f / A.leaf;
+  int min_b[3] = {0, 0, 0}, div_b[3] = {1, 1, 1};
+  bool overflow = false, empty = (n <= 0 || mm[0] == 0x7fffffff);
+  if (!empty) {
+    long long vol = 1;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const float mn = ord2f(mm[d]), mx = ord2f(mm[3 + d]);
+      const float ext = fmul(fsub(mx, mn), inv_leaf);
+      if (!(ext < 4.0e9f)) { overflow = true; continue; }
+      const long long dd = (long long)ext + 1;  // static_cast<int64>((max - min) * inv_leaf) + 1
+      vol *= dd;
+      if (vol > (long long)INT_MAX) overflow = true;
+    }
+    if (!overflow) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        min_b[d] = (int)floorf(fmul(ord2f(mm[d]), inv_leaf));
+        div_b[d] = (int)floorf(fmul(ord2f(mm[3 + d]), inv_leaf)) - min_b[d] + 1;
+      }
+    }
+  }
+  if (overflow || empty) {  // uniform over the whole cluster: nobody has touched a peer's memory since the bbox barrier
+    if (rank == 0 && tid == 0) {
+      A.total[0] = 0; A.total[1] = overflow ? 1 : 0;
+      if (A.h_total) { A.h_total[1] = overflow ? 1 : 0; A.h_total[0] = 0; }
+    }
+    cluster.sync();
+    return;
+  }
+  const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
+  // ---- keys (k_vg_keys): int32 voxel index; non-finite points 0x7fffffff, padding 0xffffffff (both sort behind every voxel)
+#pragma unroll 4
+  for (int b = 0; b < kBuildPer; b++) {
+    const int e = warp * (32 * kBuildPer) + b * 32 + lane;
+    const int i = g0 + e;
+    unsigned int key = 0xffffffffu;
+    if (i < n) {
+      const float* p = A.in + (size_t)i * A.stride_f;
+      const float x = p[0], y = p[1], z = p[2];
+      key = 0x7fffffffu;
+      if (finite3(x, y, z)) {
+        const int i0 = (int)fsub(floorf(fmul(x, inv_leaf)), (float)min_b[0]);
+        const int i1 = (int)fsub(floorf(fmul(y, inv_leaf)), (float)min_b[1]);
+        const int i2 = (int)fsub(floorf(fmul(z, inv_leaf)), (float)min_b[2]);
+        key = (unsigned int)(i0 + i1 * mul1 + i2 * mul2);
+      }
+    }
+    buf[e] = make_uint2(key, (unsigned int)i);
+  }
+  __syncthreads();
+  cluster_radix_sort<CL>(cluster, S, rank);  // ends with a cluster barrier: every slice is final and visible
+  // ---- heads: thread t owns the 16 consecutive positions t*16 .. t*16+15 of this CTA's slice
+  const int e0 = tid * kBuildPer;
+  unsigned int prev = 0xffffffffu;  // key before position e0 (none for the very first position of the cloud)
+  if (e0 > 0) prev = buf[e0 - 1].x;
+  else if (rank > 0) prev = cluster.map_shared_rank(buf, rank - 1)[kBuildCap - 1].x;
+  unsigned int headmask = 0;
+  {
+    unsigned int pk = prev;
+    const bool first_of_cloud = (rank == 0 && e0 == 0);
+#pragma unroll
+    for (int j = 0; j < kBuildPer; j++) {
+      const unsigned int k = buf[e0 + j].x;
+      if (k < 0x7fffffffu && ((first_of_cloud && j == 0) || k != pk)) headmask |= 1u << j;
+      pk = k;
+    }
+  }
+  const int mine = __popc(headmask);
+  // block exclusive scan of `mine`, then the cluster-wide offset of this CTA
+  int* scr = S.base;  // [32] warp totals (the radix-sort scratch is free now)
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) scr[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = scr[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+    scr[lane] = winc - w;
+    if (lane == 31) S.cta_cnt[0] = winc;  // heads in this CTA's slice
+  }
+  cluster.sync();
+  int slot = inc - mine + scr[warp];
+  int total = 0;
+  for (int c = 0; c < CL; c++) {
+    const int v = cluster.map_shared_rank(S.cta_cnt, c)[0];
+    total += v;
+    if (c < rank) slot += v;
+  }
+  if (rank == 0 && tid == 0) {
+    A.total[0] = total; A.total[1] = 0;
+    if (A.h_total) { A.h_total[1] = 0; A.h_total[0] = total; }
+  }
+  // ---- centroids (k_vg_centroid): one thread per voxel, sequential float32 sums in ascending point index; a voxel's run may
+  // continue into the next CTAs' slices (read through distributed shared memory)
+  const bool has_i = A.stride_f >= 5;
+  const int cap_all = CL * kBuildCap;
+  while (headmask) {
+    const int j = __ffs(headmask) - 1;
+    headmask &= headmask - 1;
+    const unsigned int k = buf[e0 + j].x;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int g = g0 + e0 + j, cnt = 0;
+    for (;;) {
+      const uint2 kv = (g >> 14) == rank ? buf[g & (kBuildCap - 1)] : cluster.map_shared_rank(buf, g >> 14)[g & (kBuildCap - 1)];
+      if (kv.x != k) break;
+      const float* p = A.in + (size_t)kv.y * A.stride_f;
+      sx = fadd(sx, p[0]); sy = fadd(sy, p[1]); sz = fadd(sz, p[2]);
+      si = fadd(si, has_i ? p[4] : 0.f);
+      cnt++;
+      if (++g >= cap_all) break;
+    }
+    const float fc = (float)cnt;
+    float* o = A.out + (size_t)slot * A.stride_f;
+    o[0] = __fdiv_rn(sx, fc); o[1] = __fdiv_rn(sy, fc); o[2] = __fdiv_rn(sz, fc);
+    if (A.stride_f >= 4) o[3] = 1.0f;
+    if (A.stride_f >= 5) o[4] = __fdiv_rn(si, fc);
+    for (int q = 5; q < A.stride_f; q++) o[q] = 0.f;
+    if (A.okeys) A.okeys[slot] = (int)k;
+    if (A.ocounts) A.ocounts[slot] = cnt;
+    slot++;
+  }
+  cluster.sync();  // no CTA may retire while a peer still walks a run that continues in its slice
+}
+
+template <int CL>
+static cudaError_t launch_voxelgrid_cluster_t(const VgArgs& A, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_voxelgrid_cluster<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = kBuildSmem; lc.stream = st;
+  cudaLaunchAttribute la[1];
+  la[0].id = cudaLaunchAttributeClusterDimension;
+  la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+  lc.attrs = la; lc.numAttrs = 1;
+  return cudaLaunchKernelEx(&lc, k_voxelgrid_cluster<CL>, A);
+}
+static cudaError_t launch_voxelgrid_cluster(int cl, const VgArgs& A, cudaStream_t st) {
+  switch (cl) {
+    case 1: return launch_voxelgrid_cluster_t<1>(A, st);
+    case 2: return launch_voxelgrid_cluster_t<2>(A, st);
+    case 4: return launch_voxelgrid_cluster_t<4>(A, st);
+    default: return launch_voxelgrid_cluster_t<8>(A, st);
+  }
+}
+
+// device-resident voxel grid: d_in (device records) -> W.out / W.okeys / W.ocounts (device); *m = voxel count, *overflow = PCL's
+// "leaf size too small" condition (output then undefined: the caller passes the input through)
+inline int voxelgrid_device(VoxelWork& W, cudaStream_t st, const float* d_in, size_t n, size_t stride_bytes, float leaf, size_t* m, int* overflow) {
   const int sf = (int)(stride_bytes / 4);
   const int N = (int)n;
   if (!W.mm) {
     B2R_CUDA(cudaMalloc(&W.mm, 8 * sizeof(int)));
     B2R_CUDA(cudaMalloc(&W.geom, sizeof(VgGeom)));
     B2R_CUDA(cudaMallocHost(&W.h_geom, sizeof(VgGeom)));
-    B2R_CUDA(cudaMallocHost(&W.h_total, sizeof(int)));
+    B2R_CUDA(cudaHostAlloc(&W.h_total, 4 * sizeof(int), cudaHostAllocMapped));
+    B2R_CUDA(cudaHostGetDevicePointer((void**)&W.h_total_dev, W.h_total, 0));
   }
-  B2R_CUDA(W.in.reserve(n * sf));
-  B2R_CUDA(W.out.reserve(n * sf));
+  B2R_CUDA(W.out.reserve(n * sf + 8));
+  B2R_CUDA(W.okeys.reserve(n + 1)); B2R_CUDA(W.ocounts.reserve(n + 1));
+  int cl = 0;
+  for (int c = 1; c <= 8; c *= 2) if (n <= (size_t)c * kBuildCap) { cl = c; break; }
+  static const bool cluster_ok = !getenv("B2R_CUB_SORT");
+  if (cl && cluster_ok) {
+    VgArgs A;
+    A.in = d_in; A.stride_f = sf; A.n = N; A.leaf = leaf; A.out = W.out.p; A.okeys = W.okeys.p; A.ocounts = W.ocounts.p;
+    A.total = W.mm + 6; A.h_total = W.h_total_dev;
+    W.h_total[0] = -1;  // the kernel's count lands here (host-mapped); -1 = not yet
+    TEL_BEGIN(W.tel, st);
+    B2R_CUDA(launch_voxelgrid_cluster(cl, A, st));
+    TEL_END(W.tel, KC_VOXELGRID, 1, st);
+    B2R_CUDA(cudaStreamSynchronize(st));
+    *m = (size_t)(W.h_total[0] < 0 ? 0 : W.h_total[0]);
+    *overflow = W.h_total[1];
+    return B2R_OK;
+  }
+  // ---- inputs beyond 131 072 points: the kernel chain with the toolkit's radix sort / scan
   B2R_CUDA(W.keys_a.reserve(n)); B2R_CUDA(W.keys_b.reserve(n)); B2R_CUDA(W.vals_a.reserve(n)); B2R_CUDA(W.vals_b.reserve(n));
-  B2R_CUDA(W.flags.reserve(n)); B2R_CUDA(W.slots.reserve(n)); B2R_CUDA(W.okeys.reserve(n)); B2R_CUDA(W.ocounts.reserve(n));
+  B2R_CUDA(W.flags.reserve(n)); B2R_CUDA(W.slots.reserve(n));
   size_t tmp_sort = 0, tmp_scan = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, W.keys_a.p, W.keys_b.p, W.vals_a.p, W.vals_b.p, N, 0, 32, st);
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, W.flags.p, W.slots.p, N, st);
   B2R_CUDA(W.tmp.reserve(std::max(tmp_sort, tmp_scan) + 256));
-  B2R_CUDA(cudaMemcpyAsync(W.in.p, in, n * stride_bytes, cudaMemcpyHostToDevice, st));
   const unsigned nb = (unsigned)((n + 255) / 256);
-  if (W.tel) W.tel->h2d += n * stride_bytes;
   TEL_BEGIN(W.tel, st);
   k_grid_reset<<<1, 32, 0, st>>>(W.mm);
-  k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, st>>>(W.in.p, sf, N, W.mm);
+  k_bbox<<<nb > 1184 ? 1184 : nb, 256, 0, st>>>(d_in, sf, N, W.mm);
   k_vg_params<<<1, 1, 0, st>>>(W.mm, W.geom, N, leaf);
   B2R_CUDA(cudaMemcpyAsync(W.h_geom, W.geom, sizeof(VgGeom), cudaMemcpyDeviceToHost, st));
-  k_vg_keys<<<nb, 256, 0, st>>>(W.in.p, sf, N, W.geom, W.keys_a.p, W.vals_a.p);
+  k_vg_keys<<<nb, 256, 0, st>>>(d_in, sf, N, W.geom, W.keys_a.p, W.vals_a.p);
   size_t tb = W.tmp.cap;
   cub::DeviceRadixSort::SortPairs(W.tmp.p, tb, W.keys_a.p, W.keys_b.p, W.vals_a.p, W.vals_b.p, N, 0, 32, st);
   k_vg_heads<<<nb, 256, 0, st>>>(W.keys_b.p, N, W.flags.p);
   tb = W.tmp.cap;
   cub::DeviceScan::ExclusiveSum(W.tmp.p, tb, W.flags.p, W.slots.p, N, st);
-  k_vg_centroid<<<nb, 256, 0, st>>>(W.in.p, sf, N, W.keys_b.p, W.vals_b.p, W.flags.p, W.slots.p, W.out.p, sf, W.okeys.p, W.ocounts.p,
+  k_vg_centroid<<<nb, 256, 0, st>>>(d_in, sf, N, W.keys_b.p, W.vals_b.p, W.flags.p, W.slots.p, W.out.p, sf, W.okeys.p, W.ocounts.p,
                                     (int*)(W.mm + 6));
   TEL_END(W.tel, KC_VOXELGRID, 14, st);
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(W.h_total, W.mm + 6, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));
-  if (W.h_geom->overflow) {  // PCL: warn and pass the input through unchanged
+  *m = (size_t)W.h_total[0];
+  *overflow = W.h_geom->overflow;
+  return B2R_OK;
+}
+
+inline int voxelgrid_filter(VoxelWork& W, cudaStream_t st, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
+                            size_t* n_out, int32_t* out_keys, int32_t* out_counts) {
+  *n_out = 0;
+  if (n == 0) return B2R_OK;
+  if (n > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  const int sf = (int)(stride_bytes / 4);
+  B2R_CUDA(W.in.reserve(n * sf));
+  B2R_CUDA(cudaMemcpyAsync(W.in.p, in, n * stride_bytes, cudaMemcpyHostToDevice, st));
+  if (W.tel) W.tel->h2d += n * stride_bytes;
+  size_t m = 0;
+  int overflow = 0;
+  int rc = voxelgrid_device(W, st, W.in.p, n, stride_bytes, leaf, &m, &overflow);
+  if (rc) return rc;
+  if (overflow) {  // PCL: warn and pass the input through unchanged
     std::memcpy(out, in, n * stride_bytes);
     *n_out = n;
     if (out_keys) for (size_t i = 0; i < n; i++) out_keys[i] = -1;
     if (out_counts) for (size_t i = 0; i < n; i++) out_counts[i] = 1;
     return 1;
   }
-  const size_t m = (size_t)*W.h_total;
   if (m) {
     B2R_CUDA(cudaMemcpyAsync(out, W.out.p, m * stride_bytes, cudaMemcpyDeviceToHost, st));
     if (out_keys) B2R_CUDA(cudaMemcpyAsync(out_keys, W.okeys.p, m * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -243,6 +243,39 @@ class Registration:
     def statisticalOutlierRemoval(self, cloud, mean_k, stddev_mul):
         return self._filter(self._lib.b2r_statistical_outlier_removal, cloud, int(mean_k), float(stddev_mul))
 
+    def deskew(self, cloud, scan_period, angular_velocity):
+        a, n, s = _cloud(cloud)
+        out = np.zeros_like(a)
+        w = np.ascontiguousarray(angular_velocity, np.float32)
+        check(self._lib.b2r_deskew(self._h, a.ctypes.data_as(C.c_void_p), n, s, float(scan_period), w.ctypes.data_as(C.POINTER(C.c_float)),
+                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def prefilter(self, cloud, want_host=True, **params):
+        """PrefilteringNodelet::cloud_callback in one call (b2r_prefilter): returns (host array or None, device pointer, count)"""
+        a, n, s = _cloud(cloud)
+        p = _capi.PrefilterParams()
+        check(self._lib.b2r_prefilter_params_default(C.byref(p)))
+        for k, v in params.items():
+            if k in ("angular_velocity", "base_link_transform"):
+                arr = getattr(p, k)
+                vals = _colmajor(v) if k == "base_link_transform" else np.asarray(v, np.float32)
+                for i, x in enumerate(vals):
+                    arr[i] = float(x)
+            else:
+                setattr(p, k, v)
+        out = np.zeros_like(a) if want_host else None
+        dptr, m = C.c_void_p(), C.c_size_t()
+        check(self._lib.b2r_prefilter(self._h, a.ctypes.data_as(C.c_void_p), n, s, 0, C.byref(p), out.ctypes.data_as(C.c_void_p) if want_host else None,
+                                      C.byref(dptr), C.byref(m)))
+        return (out[: m.value] if want_host else None), dptr.value, m.value
+
+    def voxelGridFilterDevice(self, d_ptr, n, stride_bytes, leaf):
+        """device pointer in -> (device pointer out, voxel count, rc): the result stays in HBM (b2r_voxelgrid_device)"""
+        out, m = C.c_void_p(), C.c_size_t()
+        rc = check(self._lib.b2r_voxelgrid_device(self._h, C.c_void_p(d_ptr), n, stride_bytes, leaf, C.byref(out), C.byref(m)))
+        return out.value, m.value, rc
+
     def voxelGridFilter(self, cloud, leaf, with_keys=False):
         a, n, s = _cloud(cloud)
         out = np.zeros_like(a)

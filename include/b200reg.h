@@ -159,6 +159,12 @@ int b2r_ndt_derivatives_at(b2r_handle* h, const double p[6], double* score, doub
 int b2r_voxelgrid(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out, size_t* n_out,
                   int32_t* out_keys, int32_t* out_counts);
 
+/* the same filter with input and output resident in device memory: *d_out receives an engine-owned device buffer of *n_out records
+ * (same record layout as the input; valid until the next voxel-grid call on this handle) that can go straight into
+ * b2r_set_source_device / b2r_set_target_device / b2r_batch_add_cloud_device / b2r_odometry_matching_device — downsample ->
+ * registration without leaving HBM.  Returns 1 with *d_out = d_in when the leaf is too small (pass-through). */
+int b2r_voxelgrid_device(b2r_handle* h, const void* d_in, size_t n, size_t stride_bytes, float leaf, const void** d_out, size_t* n_out);
+
 /* ---- "next" rows: the rest of the prefilter chain.  Records are copied whole; kept points stay in input order.
  * PrefilteringNodelet::distance_filter (apps/prefiltering_nodelet.cpp:164-180): keep near < ||p|| < far (float32 norm). */
 int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double near_thresh, double far_thresh, void* out, size_t* n_out);
@@ -166,6 +172,44 @@ int b2r_distance_filter(b2r_handle* h, const void* in, size_t n, size_t stride_b
 int b2r_radius_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double radius, int min_neighbors, void* out, size_t* n_out);
 /* pcl::StatisticalOutlierRemoval with setMeanK / setStddevMulThresh (apps/prefiltering_nodelet.cpp:73-81,151-162) */
 int b2r_statistical_outlier_removal(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, int mean_k, double stddev_mul, void* out, size_t* n_out);
+
+/* PrefilteringNodelet::deskewing (apps/prefiltering_nodelet.cpp:182-243): point i rotated back by the gyro rate over its share of
+ * the scan period (float32, Eigen's quaternion arithmetic; the quaternion (1, dt/2 w) is not normalised, as in the reference).
+ * angular_velocity = the IMU message's angular_velocity (the engine negates it, :217).  out: n records. */
+int b2r_deskew(b2r_handle* h, const void* in, size_t n, size_t stride_bytes, double scan_period, const float angular_velocity[3], void* out);
+
+/* PrefilteringNodelet::cloud_callback (apps/prefiltering_nodelet.cpp:106-136) as ONE call with the cloud resident in HBM between the
+ * stages: deskewing -> [base_link transform] -> distance_filter -> downsample -> outlier_removal.  Keep flags, the statistical
+ * filter's mean / stddev and the compactions are computed on the device.  points: host records, or device records when
+ * device_input != 0.  The result stays in an engine-owned device buffer (*d_out, valid until the next prefilter / voxel-grid call
+ * on this handle; pass it to b2r_set_source_device / b2r_odometry_matching_device) and is also copied to out_host when that is
+ * not NULL (capacity n records). */
+#define B2R_DOWNSAMPLE_NONE 0
+#define B2R_DOWNSAMPLE_VOXELGRID 1
+#define B2R_OUTLIER_NONE 0
+#define B2R_OUTLIER_STATISTICAL 1
+#define B2R_OUTLIER_RADIUS 2
+typedef struct b2r_prefilter_params {
+  int32_t deskewing;              /* "deskewing" (false)                                   prefiltering_nodelet.cpp:36  */
+  int32_t use_base_link_transform;/* base_link_frame set                                    :114                         */
+  double scan_period;             /* "scan_period" (0.1)                                    :234                         */
+  float angular_velocity[3];      /* imu_msg->angular_velocity of the scan's stamp          :215                         */
+  float base_link_transform[16];  /* column-major sensor -> base_link                       :121-126                     */
+  int32_t use_distance_filter;    /* "use_distance_filter" (true)                           :96                          */
+  double distance_near_thresh;    /* 1.0                                                    :97                          */
+  double distance_far_thresh;     /* 100.0                                                  :98                          */
+  int32_t downsample_method;      /* "downsample_method" VOXELGRID                          :51                          */
+  float downsample_resolution;    /* 0.1                                                    :52                          */
+  int32_t outlier_removal_method; /* "outlier_removal_method" STATISTICAL                   :71                          */
+  int32_t statistical_mean_k;     /* 20                                                     :73                          */
+  double statistical_stddev;      /* 1.0                                                    :74                          */
+  double radius_radius;           /* 0.8                                                    :83                          */
+  int32_t radius_min_neighbors;   /* 2                                                      :84                          */
+  int32_t reserved;
+} b2r_prefilter_params;
+int b2r_prefilter_params_default(b2r_prefilter_params* p);
+int b2r_prefilter(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int device_input, const b2r_prefilter_params* p,
+                  void* out_host, const void** d_out, size_t* n_out);
 
 /* ---- host mirrors of the two callers (logic identical to the reference; only the handle is ours) ---------------- */
 typedef struct b2r_odometry b2r_odometry;

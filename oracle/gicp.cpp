@@ -491,11 +491,54 @@ extern "C" void orc_statistical_outlier(const float* pts, size_t n, size_t strid
     for (int j = 1; j < c; j++) s += (double)std::sqrt(d2[j]);  // first neighbour is the point itself
     dist[i] = (float)(s / (double)mean_k);
   }
+  // pcl::StatisticalOutlierRemoval::applyFilterIndices: a non-finite point gets distance 0.0 and is not counted as valid;
+  // `sq_sum += distance * distance` multiplies two floats (float32 product, then widened)
   double sum = 0, sq = 0;
-  for (size_t i = 0; i < n; i++) { sum += (double)dist[i]; sq += (double)dist[i] * (double)dist[i]; }
-  double mean = sum / (double)n;
-  double variance = (sq - sum * sum / (double)n) / ((double)n - 1.0);
+  size_t valid = 0;
+  for (size_t i = 0; i < n; i++) {
+    const float* p = pts + i * stride;
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) { dist[i] = 0.0f; continue; }
+    valid++;
+    const float d = dist[i];
+    volatile float dd = d * d;
+    sum += (double)d;
+    sq += (double)dd;
+  }
+  double mean = sum / (double)valid;
+  double variance = (sq - sum * sum / (double)valid) / ((double)valid - 1.0);
   double thresh = mean + stddev_mul * std::sqrt(variance);
-  for (size_t i = 0; i < n; i++) keep[i] = !((double)dist[i] > thresh) ? 1 : 0;
+  for (size_t i = 0; i < n; i++) keep[i] = (valid > 0 && !((double)dist[i] > thresh)) ? 1 : 0;
   if (dist_out) std::memcpy(dist_out, dist.data(), n * sizeof(float));
+}
+
+// PrefilteringNodelet::deskewing (/root/reference/apps/prefiltering_nodelet.cpp:182-243), float32 in Eigen's evaluation order:
+// delta_q = Quaternionf(1, dt/2 wx, dt/2 wy, dt/2 wz) with ang_v already negated (:217); pt_ = delta_q.inverse() * pt
+// (inverse = conjugate / squaredNorm; rotation v + w * (2 q x v) + q x (2 q x v)).  angular_velocity = the IMU message's value.
+extern "C" void orc_deskew(const float* pts, size_t n, size_t stride, double scan_period, const float* angular_velocity, float* out) {
+  const float wx = -angular_velocity[0], wy = -angular_velocity[1], wz = -angular_velocity[2];
+  for (size_t i = 0; i < n; i++) {
+    const float* p = pts + i * stride;
+    float* o = out + i * stride;
+    for (size_t k = 0; k < stride; k++) o[k] = p[k];
+    const double delta_t = scan_period * (double)i / (double)n;
+    const double half = delta_t / 2.0;
+    const float qw = 1.0f, qx = (float)(half * (double)wx), qy = (float)(half * (double)wy), qz = (float)(half * (double)wz);
+    volatile float a = qx * qx, b = qy * qy, c = qz * qz, d = qw * qw;
+    volatile float ab = a + b;
+    volatile float abc = ab + c;
+    const float n2 = abc + d;
+    const float iw = qw / n2, ix = -qx / n2, iy = -qy / n2, iz = -qz / n2;
+    const float vx = p[0], vy = p[1], vz = p[2];
+    auto cross = [](float ax, float ay, float az, float bx, float by, float bz, float* r) {
+      volatile float t0 = ay * bz, t1 = az * by, t2 = az * bx, t3 = ax * bz, t4 = ax * by, t5 = ay * bx;
+      r[0] = t0 - t1; r[1] = t2 - t3; r[2] = t4 - t5;
+    };
+    float u[3], cc[3];
+    cross(ix, iy, iz, vx, vy, vz, u);
+    u[0] = u[0] + u[0]; u[1] = u[1] + u[1]; u[2] = u[2] + u[2];
+    cross(ix, iy, iz, u[0], u[1], u[2], cc);
+    volatile float w0 = iw * u[0], w1 = iw * u[1], w2 = iw * u[2];
+    volatile float s0 = vx + w0, s1 = vy + w1, s2 = vz + w2;
+    o[0] = s0 + cc[0]; o[1] = s1 + cc[1]; o[2] = s2 + cc[2];
+  }
 }

@@ -101,6 +101,9 @@ void orc_radius_outlier(const float* pts, size_t n, size_t stride, double radius
 void orc_statistical_outlier(const float* pts, size_t n, size_t stride, int mean_k, double stddev_mul, unsigned char* keep, float* dist_out,
                              int threads);
 
+/* PrefilteringNodelet::deskewing (apps/prefiltering_nodelet.cpp:182-243); out: n records of `stride` floats */
+void orc_deskew(const float* pts, size_t n, size_t stride, double scan_period, const float* angular_velocity, float* out);
+
 /* ---- NDT (pclomp::NormalDistributionsTransform + VoxelGridCovariance) ---- */
 typedef struct orc_ndt_map orc_ndt_map;
 orc_ndt_map* orc_ndt_build(const float* tgt, size_t m, size_t stride, float resolution);

@@ -215,6 +215,14 @@ def statistical_outlier(cloud, mean_k, stddev_mul, threads=0):
     return keep[:n].astype(bool), dist[:n]
 
 
+def deskew(cloud, scan_period, angular_velocity):
+    a, ap, n, s = _f32(cloud)
+    out = np.zeros_like(a)
+    w = np.ascontiguousarray(angular_velocity, np.float32)
+    lib().orc_deskew(ap, C.c_size_t(n), C.c_size_t(s), C.c_double(scan_period), w.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 class NdtMap:
     def __init__(self, tgt, resolution):
         ta, tp, m, ts = _f32(tgt)

@@ -48,3 +48,50 @@ def test_prefilter_edge_cases(reg, oracle):
     out = reg.radiusOutlierRemoval(few, 0.5, 1)
     assert np.array_equal(out, few[oracle.radius_outlier(few, 0.5, 1)]) and out.shape[0] == 2
     assert reg.radiusOutlierRemoval(few, 0.5, 5).shape[0] == 0   # fewer points than min_neighbors + 1: everything is an outlier
+
+
+def test_deskew_matches_oracle(reg, synth, oracle):
+    """PrefilteringNodelet::deskewing (apps/prefiltering_nodelet.cpp:182-243): bit-exact float32 quaternion arithmetic"""
+    cloud = synth.scan("vlp16", frame=4, stride=8)
+    for w in ((0.0, 0.0, 0.0), (0.02, -0.01, 0.35), (1.5, 2.0, -3.0)):
+        got = reg.deskew(cloud, 0.1, w)
+        want = oracle.deskew(cloud, 0.1, w)
+        assert np.array_equal(got, want)
+    assert np.array_equal(reg.deskew(cloud, 0.1, (0, 0, 0))[:, :3], cloud[:, :3])  # no rotation: points unchanged
+    assert np.max(np.abs(reg.deskew(cloud, 0.1, (0, 0, 0.5))[:, :3] - cloud[:, :3])) > 1e-3
+
+
+@pytest.mark.parametrize("outlier", ["STATISTICAL", "RADIUS", "NONE"])
+def test_prefilter_chain_equals_stagewise_oracle(reg, synth, oracle, outlier):
+    """b2r_prefilter = PrefilteringNodelet::cloud_callback (apps/prefiltering_nodelet.cpp:106-136) with the cloud resident in HBM between
+    the stages: deskew -> distance filter -> voxel grid -> outlier removal == the oracle's stages composed on the host"""
+    raw = synth.scan("vlp16", frame=9, stride=8)
+    w = (0.01, -0.02, 0.3)
+    method = {"NONE": 0, "STATISTICAL": 1, "RADIUS": 2}[outlier]
+    out, dptr, m = reg.prefilter(raw, deskewing=1, scan_period=0.1, angular_velocity=w, distance_near_thresh=1.0, distance_far_thresh=60.0,
+                                 downsample_resolution=0.1, outlier_removal_method=method, radius_radius=0.5, radius_min_neighbors=2)
+    c = oracle.deskew(raw, 0.1, w)
+    c = c[oracle.distance_filter(c, 1.0, 60.0)]
+    xyzi, _, _, rc = oracle.voxelgrid(c, 0.1)
+    ds = np.zeros((xyzi.shape[0], 8), np.float32)
+    ds[:, :3], ds[:, 3], ds[:, 4] = xyzi[:, :3], 1.0, xyzi[:, 3]
+    if outlier == "STATISTICAL":
+        ds = ds[oracle.statistical_outlier(ds, 20, 1.0)[0]]
+    elif outlier == "RADIUS":
+        ds = ds[oracle.radius_outlier(ds, 0.5, 2)]
+    assert m == ds.shape[0] and dptr
+    assert np.array_equal(out, ds)
+    # the device-resident result feeds the registration directly
+    reg.setInputTargetDevice(dptr, m, raw.shape[1] * 4)
+    idx, d2 = reg.nearestKSearch(ds[:100])
+    assert np.array_equal(idx, np.arange(100)) and np.all(d2 == 0)
+
+
+def test_statistical_outlier_keeps_nonfinite_points_like_pcl(reg, synth, oracle):
+    cloud = reg.voxelGridFilter(synth.scan("vlp16_16k", frame=6, stride=8), 0.1)[:3000].copy()
+    cloud[10, 0] = np.nan
+    cloud[20, 2] = np.inf
+    out = reg.statisticalOutlierRemoval(cloud, 20, 1.0)
+    keep, _ = oracle.statistical_outlier(cloud, 20, 1.0)
+    assert keep[10] and keep[20]  # pcl: a non-finite point has distance 0 and passes the threshold
+    assert np.array_equal(np.nan_to_num(out, nan=-7.0, posinf=-8.0), np.nan_to_num(cloud[keep], nan=-7.0, posinf=-8.0))
