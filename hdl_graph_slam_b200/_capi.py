@@ -43,6 +43,15 @@ class PrefilterParams(C.Structure):
                 ("radius_radius", C.c_double), ("radius_min_neighbors", C.c_int32), ("reserved", C.c_int32)]
 
 
+class KeyframeSnapshot(C.Structure):
+    _fields_ = [("points", C.c_void_p), ("n", C.c_size_t), ("pose", C.c_float * 16)]
+
+
+class PointLayout(C.Structure):
+    _fields_ = [("point_step", C.c_uint32), ("off_x", C.c_uint32), ("off_y", C.c_uint32), ("off_z", C.c_uint32), ("off_intensity", C.c_uint32),
+                ("intensity_datatype", C.c_uint32), ("is_bigendian", C.c_uint32)]
+
+
 class OdometryParams(C.Structure):
     _fields_ = [
         ("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double),
@@ -105,6 +114,10 @@ SYMBOLS = [
     ("b2r_deskew", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_double, _F32P, _VP]),
     ("b2r_prefilter_params_default", C.c_int, [C.POINTER(PrefilterParams)]),
     ("b2r_prefilter", C.c_int, [_VP, _VP, _SZ, _SZ, C.c_int, C.POINTER(PrefilterParams), _VP, C.POINTER(_VP), C.POINTER(_SZ)]),
+    ("b2r_ingest_pointcloud2", C.c_int, [_VP, _VP, _SZ, C.POINTER(PointLayout), C.POINTER(_VP)]),
+    ("b2r_pcd_read_header", C.c_int, [C.c_char_p, C.POINTER(PointLayout), C.POINTER(_SZ), C.POINTER(_SZ)]),
+    ("b2r_ingest_pcd", C.c_int, [_VP, C.c_char_p, C.POINTER(_VP), C.POINTER(_SZ)]),
+    ("b2r_map_cloud_generate", C.c_int, [_VP, C.POINTER(KeyframeSnapshot), _SZ, _SZ, C.c_double, _VP, _SZ, C.POINTER(_SZ)]),
     ("b2r_odometry_create", C.c_int, [_VP, C.POINTER(OdometryParams), C.POINTER(_VP)]),
     ("b2r_odometry_destroy", None, [_VP]),
     ("b2r_odometry_matching", C.c_int, [_VP, C.c_double, _VP, _SZ, _SZ, _F32P, C.POINTER(OdometryStatus)]),

@@ -25,6 +25,8 @@
 #include "ndt.cuh"
 #include "voxelgrid.cuh"
 #include "prefilter.cuh"
+#include "map_cloud.cuh"
+#include "ingest.cuh"
 
 namespace b2r {
 thread_local std::string g_last_error;
@@ -69,6 +71,13 @@ struct b2r_handle {
   DevBuf<float> pf_buf[2];
   DevBuf<unsigned char> pf_flags;
   DevBuf<int> pf_blocks;
+  DevBuf<char> ingest_blob;         // PointCloud2 / PCD bodies as uploaded, and their PointXYZI unpacking
+  DevBuf<float> ingest_out;
+  void* ingest_pinned = nullptr; size_t ingest_pinned_cap = 0;
+  DevBuf<char> map_kf;              // MapCloudGenerator: keyframe descriptors, voxel keys
+  DevBuf<unsigned long long> map_keys[2];
+  MapGeom* map_geom = nullptr;
+  int* map_h = nullptr;
   SorStats* pf_stats = nullptr;
   int* pf_total = nullptr;
   int* pf_h_total = nullptr; int* pf_h_total_dev = nullptr;
@@ -238,6 +247,11 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   h->d2.release(); h->partials.release();
   h->tmp_f.release(); h->tmp_i.release(); h->tmp_f4.release(); h->bc[0].release(); h->bc[1].release();
   h->pf_buf[0].release(); h->pf_buf[1].release(); h->pf_flags.release(); h->pf_blocks.release();
+  h->ingest_blob.release(); h->ingest_out.release();
+  if (h->ingest_pinned) cudaFreeHost(h->ingest_pinned);
+  h->map_kf.release(); h->map_keys[0].release(); h->map_keys[1].release();
+  if (h->map_geom) cudaFree(h->map_geom);
+  if (h->map_h) cudaFreeHost(h->map_h);
   if (h->pf_stats) cudaFree(h->pf_stats);
   if (h->pf_total) cudaFree(h->pf_total);
   if (h->pf_h_total) cudaFreeHost(h->pf_h_total);
@@ -1265,6 +1279,206 @@ extern "C" int b2r_prefilter(b2r_handle* h, const void* points, size_t n, size_t
   if (d_out) *d_out = cur;
   if (out_host) return pf_download(h, cur, m, stride_bytes, out_host);
   B2R_CUDA(cudaStreamSynchronize(h->st));
+  return B2R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ wire / disk ingest ("next" row f-4)
+static int ingest_device(b2r_handle* h, const unsigned char* d_blob, size_t n, const b2r_point_layout& L, const void** d_out) {
+  B2R_CUDA(h->ingest_out.reserve(n * 8 + 8));
+  UnpackArgs A;
+  A.data = d_blob; A.n = (long long)n; A.point_step = L.point_step; A.off_x = L.off_x; A.off_y = L.off_y; A.off_z = L.off_z;
+  A.off_i = L.off_intensity; A.type_i = L.intensity_datatype; A.bigendian = L.is_bigendian; A.out = h->ingest_out.p;
+  { TEL_BEGIN(&h->tel, h->st);
+    k_unpack_points<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, h->st>>>(A);
+    TEL_END(&h->tel, KC_MISC, 1, h->st); }
+  B2R_CUDA(cudaGetLastError());
+  *d_out = h->ingest_out.p;
+  return B2R_OK;
+}
+static int layout_check(const b2r_point_layout* L) {
+  if (!L) return fail(B2R_EINVAL, "NULL layout");
+  if (L->point_step < 12) return fail(B2R_EINVAL, "point_step too small");
+  const unsigned int need[3] = {L->off_x, L->off_y, L->off_z};
+  for (unsigned int o : need) if (o + 4 > L->point_step) return fail(B2R_EINVAL, "field offset beyond point_step");
+  if (L->off_intensity != 0xffffffffu) {
+    const unsigned int t = L->intensity_datatype;
+    const unsigned int sz = (t == 1 || t == 2) ? 1 : (t == 3 || t == 4) ? 2 : (t == 8) ? 8 : 4;
+    if (t < 1 || t > 8) return fail(B2R_EINVAL, "unknown PointField datatype");
+    if (L->off_intensity + sz > L->point_step) return fail(B2R_EINVAL, "intensity offset beyond point_step");
+  }
+  return B2R_OK;
+}
+
+extern "C" int b2r_ingest_pointcloud2(b2r_handle* h, const void* data, size_t n_points, const b2r_point_layout* layout, const void** d_points) {
+  if (!h || !d_points || (n_points && !data)) return fail(B2R_EINVAL, "NULL argument");
+  int rc = layout_check(layout);
+  if (rc) return rc;
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *d_points = nullptr;
+  if (n_points == 0) return B2R_OK;
+  if (n_points > (size_t)0x3fffffff) return fail(B2R_EINVAL, "too many points");
+  const size_t bytes = n_points * layout->point_step;
+  B2R_CUDA(h->ingest_blob.reserve(bytes + 16));
+  B2R_CUDA(cudaMemcpyAsync(h->ingest_blob.p, data, bytes, cudaMemcpyHostToDevice, h->st));  // the message's data[] goes up unconverted
+  h->tel.h2d += bytes;
+  return ingest_device(h, reinterpret_cast<const unsigned char*>(h->ingest_blob.p), n_points, *layout, d_points);
+}
+
+extern "C" int b2r_pcd_read_header(const char* path, b2r_point_layout* layout, size_t* n_points, size_t* data_offset) {
+  if (!path || !layout || !n_points) return fail(B2R_EINVAL, "NULL argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(B2R_EINVAL, std::string("cannot open ") + path);
+  PcdHeader H;
+  const bool ok = pcd_parse_header(f, H);
+  fclose(f);
+  if (!ok) return fail(B2R_EINVAL, "not a PCD header");
+  if (H.data != "binary") return fail(B2R_EUNSUPPORTED, "only DATA binary is read directly (KeyFrame::save writes savePCDFileBinary)");
+  std::memset(layout, 0, sizeof(*layout));
+  layout->off_intensity = 0xffffffffu; layout->intensity_datatype = 7;
+  unsigned int off = 0, found = 0;
+  for (size_t i = 0; i < H.fields.size(); i++) {
+    const unsigned int sz = (unsigned int)(H.size[i] * H.count[i]);
+    const bool f32 = H.type[i] == 'F' && H.size[i] == 4;
+    if (H.fields[i] == "x" && f32) { layout->off_x = off; found |= 1; }
+    else if (H.fields[i] == "y" && f32) { layout->off_y = off; found |= 2; }
+    else if (H.fields[i] == "z" && f32) { layout->off_z = off; found |= 4; }
+    else if (H.fields[i] == "intensity") {
+      layout->off_intensity = off;
+      const char t = H.type[i];
+      layout->intensity_datatype = (t == 'F') ? (H.size[i] == 8 ? 8 : 7) : (t == 'U') ? (H.size[i] == 1 ? 2 : H.size[i] == 2 ? 4 : 6) : (H.size[i] == 1 ? 1 : H.size[i] == 2 ? 3 : 5);
+    }
+    off += sz;
+  }
+  if (found != 7) return fail(B2R_EINVAL, "PCD has no float32 x / y / z fields");
+  layout->point_step = off;
+  *n_points = H.points;
+  if (data_offset) *data_offset = H.data_offset;
+  return B2R_OK;
+}
+
+extern "C" int b2r_ingest_pcd(b2r_handle* h, const char* path, const void** d_points, size_t* n_points) {
+  if (!h || !d_points || !n_points) return fail(B2R_EINVAL, "NULL argument");
+  b2r_point_layout L;
+  size_t n = 0, off = 0;
+  int rc = b2r_pcd_read_header(path, &L, &n, &off);
+  if (rc) return rc;
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  *d_points = nullptr; *n_points = 0;
+  if (n == 0) return B2R_OK;
+  const size_t bytes = n * L.point_step;
+  if (h->ingest_pinned_cap < bytes) {  // the file body is read straight into pinned memory: no intermediate PointCloud, no repack
+    if (h->ingest_pinned) cudaFreeHost(h->ingest_pinned);
+    h->ingest_pinned = nullptr; h->ingest_pinned_cap = 0;
+    B2R_CUDA(cudaMallocHost(&h->ingest_pinned, bytes + bytes / 4 + 4096));
+    h->ingest_pinned_cap = bytes + bytes / 4 + 4096;
+  } else {
+    B2R_CUDA(cudaStreamSynchronize(h->st));  // a previous upload from this buffer may still be in flight
+  }
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(B2R_EINVAL, std::string("cannot open ") + path);
+  bool ok = fseek(f, (long)off, SEEK_SET) == 0 && fread(h->ingest_pinned, 1, bytes, f) == bytes;
+  fclose(f);
+  if (!ok) return fail(B2R_EINVAL, "PCD body shorter than its header says");
+  B2R_CUDA(h->ingest_blob.reserve(bytes + 16));
+  B2R_CUDA(cudaMemcpyAsync(h->ingest_blob.p, h->ingest_pinned, bytes, cudaMemcpyHostToDevice, h->st));
+  h->tel.h2d += bytes;
+  rc = ingest_device(h, reinterpret_cast<const unsigned char*>(h->ingest_blob.p), n, L, d_points);
+  if (rc) return rc;
+  *n_points = n;
+  return B2R_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ map cloud ("next" row f-3)
+extern "C" int b2r_map_cloud_generate(b2r_handle* h, const b2r_keyframe_snapshot* keyframes, size_t n_keyframes, size_t stride_bytes, double resolution,
+                                      void* out, size_t out_capacity, size_t* n_out) {
+  if (!h || !n_out) return fail(B2R_EINVAL, "NULL argument");
+  *n_out = 0;
+  if (n_keyframes == 0) return 1;  // "warning: keyframes empty!!" -> nullptr (map_cloud_generator.cpp:14-17)
+  if (!keyframes || !out) return fail(B2R_EINVAL, "NULL argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(B2R_EINVAL, "bad stride");
+  B2R_CUDA(cudaSetDevice(h->cfg.device_id));
+  const int sf = (int)(stride_bytes / 4);
+  size_t total = 0;
+  for (size_t k = 0; k < n_keyframes; k++) {
+    if (keyframes[k].n && !keyframes[k].points) return fail(B2R_EINVAL, "keyframe cloud is NULL");
+    total += keyframes[k].n;
+  }
+  if (total >= (size_t)0x7fffffff) return fail(B2R_EINVAL, "map cloud too large (>= 2^31 points)");
+  if (total == 0) return B2R_OK;
+  cudaStream_t st = h->st;
+  // upload: all keyframe clouds back to back + their descriptors
+  DevBuf<float>& src = h->pf_buf[0];
+  DevBuf<float>& cloud = h->pf_buf[1];
+  B2R_CUDA(src.reserve(total * sf + 8));
+  B2R_CUDA(cloud.reserve(total * sf + 8));
+  std::vector<MapKf> kf(n_keyframes);
+  size_t first = 0;
+  for (size_t k = 0; k < n_keyframes; k++) {
+    kf[k].pts = src.p + first * sf; kf[k].first = (long long)first; kf[k].n = (int)keyframes[k].n; kf[k].pad = 0;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) kf[k].T[r * 4 + c] = keyframes[k].pose[c * 4 + r];
+    if (keyframes[k].n) B2R_CUDA(cudaMemcpyAsync(src.p + first * sf, keyframes[k].points, keyframes[k].n * stride_bytes, cudaMemcpyHostToDevice, st));
+    first += keyframes[k].n;
+  }
+  h->tel.h2d += total * stride_bytes;
+  // empty keyframes must not shadow their successors in the binary search: drop them from the descriptor list
+  std::vector<MapKf> kf2;
+  for (auto& k : kf) if (k.n > 0) kf2.push_back(k);
+  B2R_CUDA(h->map_kf.reserve(kf2.size() * sizeof(MapKf) + 64));
+  B2R_CUDA(cudaMemcpyAsync(h->map_kf.p, kf2.data(), kf2.size() * sizeof(MapKf), cudaMemcpyHostToDevice, st));
+  B2R_CUDA(cudaStreamSynchronize(st));  // kf2 is pageable host memory on the stack of this call
+  const long long T = (long long)total;
+  unsigned nb = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  { TEL_BEGIN(&h->tel, st);
+    k_map_transform<<<nb, 256, 0, st>>>(reinterpret_cast<const MapKf*>(h->map_kf.p), (int)kf2.size(), sf, T, cloud.p);
+    TEL_END(&h->tel, KC_MISC, 1, st); }
+  if (!(resolution > 0.0)) {  // "To get unfiltered point cloud with intensity" (:39-40)
+    if (out_capacity < total) return fail(B2R_EINVAL, "output capacity too small");
+    B2R_CUDA(cudaMemcpyAsync(out, cloud.p, total * stride_bytes, cudaMemcpyDeviceToHost, st));
+    B2R_CUDA(cudaStreamSynchronize(st));
+    h->tel.d2h += total * stride_bytes;
+    *n_out = total;
+    return B2R_OK;
+  }
+  // voxel keys -> sort -> unique -> centres
+  B2R_CUDA(h->map_keys[0].reserve(total + 8));
+  B2R_CUDA(h->map_keys[1].reserve(total + 8));
+  B2R_CUDA(h->tmp_i.reserve(2 * total + 16));
+  int* flags = h->tmp_i.p;
+  int* slots = h->tmp_i.p + total + 8;
+  size_t tmp_sort = 0, tmp_scan = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, h->map_keys[0].p, h->map_keys[1].p, (int)total, 0, 64, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, flags, slots, (int)total, st);
+  B2R_CUDA(h->bc[0].sort_tmp.reserve(std::max(tmp_sort, tmp_scan) + 256));
+  if (!h->map_geom) {
+    B2R_CUDA(cudaMalloc(&h->map_geom, sizeof(MapGeom) + 64));
+    B2R_CUDA(cudaMallocHost(&h->map_h, 64));
+  }
+  unsigned long long* first_idx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->map_geom) + sizeof(MapGeom));
+  int* n_dev = reinterpret_cast<int*>(first_idx + 1);
+  { TEL_BEGIN(&h->tel, st);
+    B2R_CUDA(cudaMemsetAsync(first_idx, 0xff, sizeof(unsigned long long), st));
+    k_grid_reset<<<1, 32, 0, st>>>(h->bc[0].mm);
+    k_map_first_and_bbox<<<nb, 256, 0, st>>>(cloud.p, sf, T, first_idx, h->bc[0].mm);
+    k_map_geom<<<1, 1, 0, st>>>(cloud.p, sf, first_idx, h->bc[0].mm, resolution, h->map_geom);
+    k_map_keys<<<nb, 256, 0, st>>>(cloud.p, sf, T, h->map_geom, h->map_keys[0].p);
+    size_t tb = h->bc[0].sort_tmp.cap;
+    cub::DeviceRadixSort::SortKeys(h->bc[0].sort_tmp.p, tb, h->map_keys[0].p, h->map_keys[1].p, (int)total, 0, 64, st);
+    k_map_heads<<<nb, 256, 0, st>>>(h->map_keys[1].p, T, flags);
+    tb = h->bc[0].sort_tmp.cap;
+    cub::DeviceScan::ExclusiveSum(h->bc[0].sort_tmp.p, tb, flags, slots, (int)total, st);
+    k_map_centers<<<nb, 256, 0, st>>>(h->map_keys[1].p, flags, slots, T, h->map_geom, sf, src.p, n_dev);
+    TEL_END(&h->tel, KC_MISC, 12, st); }
+  B2R_CUDA(cudaGetLastError());
+  B2R_CUDA(cudaMemcpyAsync(h->map_h, n_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B2R_CUDA(cudaStreamSynchronize(st));
+  const size_t m = (size_t)h->map_h[0];
+  if (out_capacity < m) return fail(B2R_EINVAL, "output capacity too small");
+  if (m) {
+    B2R_CUDA(cudaMemcpyAsync(out, src.p, m * stride_bytes, cudaMemcpyDeviceToHost, st));
+    B2R_CUDA(cudaStreamSynchronize(st));
+    h->tel.d2h += m * stride_bytes;
+  }
+  *n_out = m;
   return B2R_OK;
 }
 

@@ -270,6 +270,37 @@ class Registration:
                                       C.byref(dptr), C.byref(m)))
         return (out[: m.value] if want_host else None), dptr.value, m.value
 
+    def ingestPointCloud2(self, blob, n_points, point_step, off_x=0, off_y=4, off_z=8, off_intensity=0xffffffff, intensity_datatype=7, is_bigendian=False):
+        """sensor_msgs/PointCloud2 data[] -> device PointXYZI records (b2r_ingest_pointcloud2); returns the device pointer"""
+        buf = np.frombuffer(blob, np.uint8) if not isinstance(blob, np.ndarray) else blob.view(np.uint8).reshape(-1)
+        self._keep["pc2"] = buf
+        L = _capi.PointLayout(point_step, off_x, off_y, off_z, off_intensity, intensity_datatype, int(is_bigendian))
+        out = C.c_void_p()
+        check(self._lib.b2r_ingest_pointcloud2(self._h, buf.ctypes.data_as(C.c_void_p), n_points, C.byref(L), C.byref(out)))
+        return out.value
+
+    def ingestPcd(self, path):
+        """binary PCD file -> (device pointer to PointXYZI records, point count) (b2r_ingest_pcd)"""
+        out, n = C.c_void_p(), C.c_size_t()
+        check(self._lib.b2r_ingest_pcd(self._h, str(path).encode(), C.byref(out), C.byref(n)))
+        return out.value, n.value
+
+    def mapCloudGenerate(self, keyframes, resolution):
+        """MapCloudGenerator::generate: keyframes = list of (cloud, 4x4 pose) -> map cloud (b2r_map_cloud_generate); None if empty"""
+        arrs = [_cloud(c)[0] for c, _ in keyframes]
+        kf = (_capi.KeyframeSnapshot * max(len(arrs), 1))()
+        for i, (a, (_, pose)) in enumerate(zip(arrs, keyframes)):
+            kf[i].points, kf[i].n = a.ctypes.data, a.shape[0]
+            pc = _colmajor(pose)
+            for k in range(16):
+                kf[i].pose[k] = pc[k]
+        total = sum(a.shape[0] for a in arrs)
+        stride_f = arrs[0].shape[1] if arrs else 8
+        out = np.zeros((max(total, 1), stride_f), np.float32)
+        m = C.c_size_t()
+        rc = check(self._lib.b2r_map_cloud_generate(self._h, kf, len(arrs), stride_f * 4, float(resolution), out.ctypes.data_as(C.c_void_p), total, C.byref(m)))
+        return None if rc == 1 else out[: m.value]
+
     def voxelGridFilterDevice(self, d_ptr, n, stride_bytes, leaf):
         """device pointer in -> (device pointer out, voxel count, rc): the result stays in HBM (b2r_voxelgrid_device)"""
         out, m = C.c_void_p(), C.c_size_t()

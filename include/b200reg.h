@@ -211,6 +211,39 @@ int b2r_prefilter_params_default(b2r_prefilter_params* p);
 int b2r_prefilter(b2r_handle* h, const void* points, size_t n, size_t stride_bytes, int device_input, const b2r_prefilter_params* p,
                   void* out_host, const void** d_out, size_t* n_out);
 
+/* replaces MapCloudGenerator::generate(keyframes, resolution) (src/hdl_graph_slam/map_cloud_generator.cpp:13-51; called at
+ * apps/hdl_graph_slam_nodelet.cpp:528,989): every keyframe cloud transformed by its optimised pose (float32), all concatenated;
+ * resolution <= 0 returns that cloud (intensity kept), otherwise the centres of the occupied voxels of a
+ * pcl::octree::OctreePointCloud(resolution) — the same SET of centres as PCL's lattice (anchored at the first finite point),
+ * emitted in ascending key order instead of octree traversal order; x,y,z,1 with intensity 0.
+ * Returns 1 with *n_out = 0 when there is no keyframe ("warning: keyframes empty!!").  out: capacity out_capacity records. */
+typedef struct b2r_keyframe_snapshot {
+  const void* points;  /* KeyFrameSnapshot::cloud: n records of stride_bytes */
+  size_t n;
+  float pose[16];      /* KeyFrameSnapshot::pose.matrix().cast<float>(), column-major */
+} b2r_keyframe_snapshot;
+int b2r_map_cloud_generate(b2r_handle* h, const b2r_keyframe_snapshot* keyframes, size_t n_keyframes, size_t stride_bytes, double resolution,
+                           void* out, size_t out_capacity, size_t* n_out);
+
+/* ---- wire / disk formats at the seam ----------------------------------------------------------------
+ * A sensor_msgs/PointCloud2 data[] blob (or a binary PCD body) goes to the device unconverted and is unpacked there into
+ * pcl::PointXYZI records (32 bytes: x y z 1 | intensity 0 0 0) — the work of pcl::fromROSMsg at
+ * apps/scan_matching_odometry_nodelet.cpp:118-119 and apps/hdl_graph_slam_nodelet.cpp:153-154, and of pcl::io::loadPCDFile at
+ * src/hdl_graph_slam/keyframe.cpp:141.  *d_points is an engine-owned device buffer (valid until the next ingest call on this
+ * handle) for b2r_set_source_device / b2r_set_target_device / b2r_prefilter(device_input = 1) / b2r_batch_add_cloud_device. */
+typedef struct b2r_point_layout {
+  uint32_t point_step;         /* PointCloud2.point_step */
+  uint32_t off_x, off_y, off_z;/* byte offsets of the FLOAT32 fields "x", "y", "z" */
+  uint32_t off_intensity;      /* byte offset of "intensity", 0xffffffff = absent (intensity 0) */
+  uint32_t intensity_datatype; /* sensor_msgs/PointField datatype of "intensity": 1 INT8 2 UINT8 3 INT16 4 UINT16 5 INT32 6 UINT32 7 FLOAT32 8 FLOAT64 */
+  uint32_t is_bigendian;       /* PointCloud2.is_bigendian */
+} b2r_point_layout;
+int b2r_ingest_pointcloud2(b2r_handle* h, const void* data, size_t n_points, const b2r_point_layout* layout, const void** d_points);
+/* header of a binary PCD file (the cloud.pcd KeyFrame::save writes with pcl::io::savePCDFileBinary, keyframe.cpp:57) */
+int b2r_pcd_read_header(const char* path, b2r_point_layout* layout, size_t* n_points, size_t* data_offset);
+/* header parse + fread of the body straight into pinned memory + H2D + device unpack */
+int b2r_ingest_pcd(b2r_handle* h, const char* path, const void** d_points, size_t* n_points);
+
 /* ---- host mirrors of the two callers (logic identical to the reference; only the handle is ours) ---------------- */
 typedef struct b2r_odometry b2r_odometry;
 typedef struct b2r_odometry_params {

@@ -223,6 +223,62 @@ def deskew(cloud, scan_period, angular_velocity):
     return out
 
 
+def map_cloud_generate(keyframes, resolution):
+    """MapCloudGenerator::generate (/root/reference/src/hdl_graph_slam/map_cloud_generator.cpp:13-51) restated with numpy, including
+    pcl::octree::OctreePointCloud's SEQUENTIAL bounding-box growth (adoptBoundingBoxToPoint, UPSTREAM-RECALL of PCL 1.10): the box
+    starts at p0 -+ resolution/2 and doubles towards each violating point; keys are (point - min) / resolution in float64; centres
+    (key + 0.5) * resolution + min with the FINAL min.  Returns the concatenated cloud (n, 5: x y z 1 intensity) when
+    resolution <= 0, else the occupied voxel centres (m, 3) as float32, in ascending lexicographic order."""
+    pts = []
+    for cloud, pose in keyframes:
+        c = np.asarray(cloud, np.float32)
+        P = np.asarray(pose, np.float64).astype(np.float32)
+        x, y, z = c[:, 0], c[:, 1], c[:, 2]
+        o = np.zeros((c.shape[0], 5), np.float32)
+        for r in range(3):  # ((m0 x + m1 y) + m2 z) + m3, float32
+            o[:, r] = ((P[r, 0] * x + P[r, 1] * y).astype(np.float32) + (P[r, 2] * z).astype(np.float32)).astype(np.float32) + P[r, 3]
+        o[:, 3] = 1.0
+        o[:, 4] = c[:, 4] if c.shape[1] > 4 else 0.0
+        pts.append(o)
+    cloud = np.concatenate(pts) if pts else np.zeros((0, 5), np.float32)
+    if not (resolution > 0):
+        return cloud
+    res = float(resolution)
+    eps = float(np.finfo(np.float32).eps)
+    mn, mx, depth, defined = np.zeros(3), np.zeros(3), 0, False
+    xyz = cloud[:, :3].astype(np.float64)
+    finite = np.isfinite(xyz).all(axis=1)
+    # points that violate the current box are rare after the first few: scan in chunks and only loop over violators
+    i, n = 0, xyz.shape[0]
+    while i < n:
+        if not finite[i]:
+            i += 1
+            continue
+        p = xyz[i]
+        while True:
+            lower, upper = p < mn, p >= mx
+            if defined and not (lower.any() or upper.any()):
+                break
+            if defined:
+                side = float(1 << depth) * res
+                mn = np.where(~upper, mn - side, mn)
+                depth += 1
+                side = float(1 << depth) * res - eps
+                mx = mn + side
+            else:
+                mn, mx, defined = p - res / 2, p + res / 2, True
+        # skip ahead to the next violator
+        rest = xyz[i + 1:]
+        bad = ((rest < mn) | (rest >= mx)).any(axis=1) & finite[i + 1:]
+        nxt = np.flatnonzero(bad)
+        i = i + 1 + (int(nxt[0]) if nxt.size else rest.shape[0])
+    keys = np.floor((xyz[finite] - mn) / res).astype(np.int64)
+    uniq = np.unique(keys, axis=0)
+    centres = ((uniq.astype(np.float64) + 0.5) * res + mn).astype(np.float32)
+    order = np.lexsort((centres[:, 0], centres[:, 1], centres[:, 2]))
+    return centres[order]
+
+
 class NdtMap:
     def __init__(self, tgt, resolution):
         ta, tp, m, ts = _f32(tgt)

@@ -66,3 +66,17 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_pcd_header_parser_runs_without_gpu(tmp_path):
+    """b2r_pcd_read_header is host-only: layout of the binary PCD KeyFrame::save writes (packed x y z intensity, 16-byte step)"""
+    import ctypes as C
+    from hdl_graph_slam_b200 import _capi
+    lib = _capi.load()
+    p = tmp_path / "c.pcd"
+    p.write_bytes(b"# .PCD v0.7\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH 3\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 3\nDATA binary\n" + bytes(48))
+    L, n, off = _capi.PointLayout(), C.c_size_t(), C.c_size_t()
+    assert lib.b2r_pcd_read_header(str(p).encode(), C.byref(L), C.byref(n), C.byref(off)) == 0
+    assert (L.point_step, L.off_x, L.off_y, L.off_z, L.off_intensity, L.intensity_datatype, n.value) == (16, 0, 4, 8, 12, 7, 3)
+    assert off.value == p.stat().st_size - 48
+    assert lib.b2r_pcd_read_header(str(tmp_path / "nope.pcd").encode(), C.byref(L), C.byref(n), C.byref(off)) == _capi.B2R_EINVAL
