@@ -290,6 +290,7 @@ template <bool HESS>
 __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
   __shared__ NdtCell s_cell[kNdtSlots];
   __shared__ double red[kNdtAccA * 32];
+  __shared__ double s_low[kNdtAccB][kNdtThreads];  // strict lower triangle of H: one float64 column per thread (no conflicts, no sync)
   __shared__ int s_box[6];
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
@@ -348,12 +349,13 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
     }
   }
   __syncthreads();
-  // per cell: did it contribute (bit c) and with which weight (second sweep)
-  unsigned int used = 0;
-  float exw[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
+  if (HESS) {
+#pragma unroll
+    for (int q = 0; q < kNdtAccB; q++) s_low[q][threadIdx.x] = 0.0;
+  }
   if (valid) {
     bool have_pd = false;
+    float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
     float ha1 = 0, ha2 = 0, hb1 = 0, hb2 = 0, hc1 = 0, hc2 = 0, hd0 = 0, hd1 = 0, hd2 = 0, he0 = 0, he1 = 0, he2 = 0, hf0 = 0, hf1 = 0, hf2 = 0;
     const float d2f = (float)A.d2;
     for (int c = 0; c < A.ncell_search; c++) {
@@ -397,11 +399,6 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
       exv = fmul(d2f, exv);
       if (exv > 1.f || exv < 0.f || exv != exv) continue;  // contributes nothing (score_inc dropped as well)
       exv = (float)((double)exv * A.d1);
-      if (HESS) {
-        used |= 1u << c;
-#pragma unroll
-        for (int k = 0; k < 7; k++) if (k == c) exw[k] = exv;
-      }
       // CJ columns 3..5 (columns 0..2 are C itself)
       float CJ3[3], CJ4[3], CJ5[3];
 #pragma unroll
@@ -417,10 +414,10 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
 #pragma unroll
       for (int k = 0; k < 6; k++) acc[1 + k] += (double)fmul(exv, gq[k]);
       if (HESS) {
-        // H(ii, jj) for ii <= jj in this sweep, ii > jj in the second one: ndt_omp's float32 expression is not symmetric to the
-        // last bit ((-d2 g_i) g_j vs (-d2 g_j) g_i, J_j^T C J_i vs J_i^T C J_j) and the Newton iteration is sensitive to it, so all
-        // 36 entries are computed exactly as written there — in two sweeps, so that only 28 (then 15) float64 accumulators are
-        // live at a time.  The term J_jj^T C J_ii is P[jj][ii] with
+        // All 36 entries of H exactly as ndt_omp writes them: its float32 expression is not symmetric to the last bit
+        // ((-d2 g_i) g_j vs (-d2 g_j) g_i, J_j^T C J_i vs J_i^T C J_j) and the Newton iteration is sensitive to it.  The 21 upper
+        // entries accumulate in float64 registers, the 15 strictly lower ones in a float64 shared-memory column per thread (43
+        // register accumulators would spill).  The term J_jj^T C J_ii is P[jj][ii] with
         // P[a][b] = J[:,a] . CJ[:,b], CJ[r][b]: b<3 -> C[r][b]; b=3 -> CJ3[r]; b=4 -> CJ4[r]; b=5 -> CJ5[r]
 #define B2R_CJ(r, b) ((b) < 3 ? C[(r) * 3 + (b)] : ((b) == 3 ? CJ3[r] : ((b) == 4 ? CJ4[r] : CJ5[r])))
         // second-derivative terms qC . v_ij  (i,j in 3..5); a=(0,ha1,ha2) b=(0,hb1,hb2) c=(0,hc1,hc2) d,e,f full
@@ -431,23 +428,24 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
         const float xe = fadd(fadd(fmul(gq[0], he0), fmul(gq[1], he1)), fmul(gq[2], he2));
         const float xf = fadd(fadd(fmul(gq[0], hf0), fmul(gq[1], hf1)), fmul(gq[2], hf2));
         const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
-        int hk = 7;
+        int hk = 7, lk = 0;
 #pragma unroll
         for (int ii = 0; ii < 6; ii++) {
 #pragma unroll
-          for (int jj = ii; jj < 6; jj++) {
+          for (int jj = 0; jj < 6; jj++) {
             float u = fmul(fmul(-d2f, gq[ii]), gq[jj]);
             const float xh = (ii >= 3 && jj >= 3) ? XH[ii - 3][jj - 3] : 0.f;
             u = fadd(u, xh);
-            // P[jj][ii], jj >= ii
+            // P[jj][ii] = J[:,jj] . CJ[:,ii]
             float pj;
             if (jj < 3) pj = B2R_CJ(jj, ii);
             else if (jj == 3) pj = fadd(fmul(j13, B2R_CJ(1, ii)), fmul(j23, B2R_CJ(2, ii)));
             else if (jj == 4) pj = fadd(fadd(fmul(j04, B2R_CJ(0, ii)), fmul(j14, B2R_CJ(1, ii))), fmul(j24, B2R_CJ(2, ii)));
             else pj = fadd(fadd(fmul(j05, B2R_CJ(0, ii)), fmul(j15, B2R_CJ(1, ii))), fmul(j25, B2R_CJ(2, ii)));
             u = fadd(u, pj);
-            acc[hk] += (double)fmul(exv, u);
-            hk++;
+            const double w = (double)fmul(exv, u);
+            if (jj >= ii) { acc[hk] += w; hk++; }                     // upper triangle + diagonal: registers
+            else { s_low[lk][threadIdx.x] += w; lk++; }              // strict lower triangle: this thread's shared-memory column
           }
         }
 #undef B2R_CJ
@@ -462,71 +460,9 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
 #pragma unroll
     for (int i = 0; i < kNdtAccA; i++) A.partials[(size_t)blockIdx.x * kNdtAcc + i] = acc[i];
   }
-  // ---- second sweep: the strict lower triangle of H over the same (point, cell) pairs, same float32 expressions
   double accb[kNdtAccB];
 #pragma unroll
-  for (int k = 0; k < kNdtAccB; k++) accb[k] = 0.0;
-  if (HESS && used) {
-    const float ha1 = dot3f(A.hang[0], x, y, z), ha2 = dot3f(A.hang[1], x, y, z);
-    const float hb1 = dot3f(A.hang[2], x, y, z), hb2 = dot3f(A.hang[3], x, y, z);
-    const float hc1 = dot3f(A.hang[4], x, y, z), hc2 = dot3f(A.hang[5], x, y, z);
-    const float hd0 = dot3f(A.hang[6], x, y, z), hd1 = dot3f(A.hang[7], x, y, z), hd2 = dot3f(A.hang[8], x, y, z);
-    const float he0 = dot3f(A.hang[9], x, y, z), he1 = dot3f(A.hang[10], x, y, z), he2 = dot3f(A.hang[11], x, y, z);
-    const float hf0 = dot3f(A.hang[12], x, y, z), hf1 = dot3f(A.hang[13], x, y, z), hf2 = dot3f(A.hang[14], x, y, z);
-    const float d2f = (float)A.d2;
-    for (int c = 0; c < A.ncell_search; c++) {
-      if (!((used >> c) & 1u)) continue;
-      const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
-      const NdtCell* L = staged ? &s_cell[(cx - bx0) + (cy - by0) * dx + (cz - bz0) * dxy] : A.cells + ndt_find(A.table, A.mask, V, cx, cy, cz);
-      float exv = 0.f;
-#pragma unroll
-      for (int k = 0; k < 7; k++) if (k == c) exv = exw[k];
-      const float q0 = (float)((double)xt - L->mean[0]), q1 = (float)((double)yt - L->mean[1]), q2 = (float)((double)zt - L->mean[2]);
-      float C[9];
-#pragma unroll
-      for (int k = 0; k < 9; k++) C[k] = L->icov[k];
-      float gq[6];
-#pragma unroll
-      for (int j = 0; j < 3; j++) gq[j] = fadd(fadd(fmul(q0, C[0 * 3 + j]), fmul(q1, C[1 * 3 + j])), fmul(q2, C[2 * 3 + j]));
-      float CJ3[3], CJ4[3], CJ5[3];
-#pragma unroll
-      for (int r = 0; r < 3; r++) {
-        CJ3[r] = fadd(fmul(C[r * 3 + 1], j13), fmul(C[r * 3 + 2], j23));
-        CJ4[r] = fadd(fadd(fmul(C[r * 3 + 0], j04), fmul(C[r * 3 + 1], j14)), fmul(C[r * 3 + 2], j24));
-        CJ5[r] = fadd(fadd(fmul(C[r * 3 + 0], j05), fmul(C[r * 3 + 1], j15)), fmul(C[r * 3 + 2], j25));
-      }
-      gq[3] = fadd(fadd(fmul(q0, CJ3[0]), fmul(q1, CJ3[1])), fmul(q2, CJ3[2]));
-      gq[4] = fadd(fadd(fmul(q0, CJ4[0]), fmul(q1, CJ4[1])), fmul(q2, CJ4[2]));
-      gq[5] = fadd(fadd(fmul(q0, CJ5[0]), fmul(q1, CJ5[1])), fmul(q2, CJ5[2]));
-#define B2R_CJ(r, b) ((b) < 3 ? C[(r) * 3 + (b)] : ((b) == 3 ? CJ3[r] : ((b) == 4 ? CJ4[r] : CJ5[r])))
-      const float xa = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], ha1)), fmul(gq[2], ha2));
-      const float xb = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hb1)), fmul(gq[2], hb2));
-      const float xc = fadd(fadd(fmul(gq[0], 0.f), fmul(gq[1], hc1)), fmul(gq[2], hc2));
-      const float xd = fadd(fadd(fmul(gq[0], hd0), fmul(gq[1], hd1)), fmul(gq[2], hd2));
-      const float xe = fadd(fadd(fmul(gq[0], he0), fmul(gq[1], he1)), fmul(gq[2], he2));
-      const float xf = fadd(fadd(fmul(gq[0], hf0), fmul(gq[1], hf1)), fmul(gq[2], hf2));
-      const float XH[3][3] = {{xa, xb, xc}, {xb, xd, xe}, {xc, xe, xf}};
-      int hk = 0;
-#pragma unroll
-      for (int ii = 1; ii < 6; ii++) {
-#pragma unroll
-        for (int jj = 0; jj < ii; jj++) {
-          float u = fmul(fmul(-d2f, gq[ii]), gq[jj]);
-          const float xh = (ii >= 3 && jj >= 3) ? XH[ii - 3][jj - 3] : 0.f;
-          u = fadd(u, xh);
-          // P[jj][ii], jj < ii
-          float pj;
-          if (jj < 3) pj = B2R_CJ(jj, ii);
-          else if (jj == 3) pj = fadd(fmul(j13, B2R_CJ(1, ii)), fmul(j23, B2R_CJ(2, ii)));
-          else pj = fadd(fadd(fmul(j04, B2R_CJ(0, ii)), fmul(j14, B2R_CJ(1, ii))), fmul(j24, B2R_CJ(2, ii)));
-          u = fadd(u, pj);
-          accb[hk] += (double)fmul(exv, u);
-          hk++;
-        }
-      }
-#undef B2R_CJ
-    }
-  }
+  for (int q = 0; q < kNdtAccB; q++) accb[q] = HESS ? s_low[q][threadIdx.x] : 0.0;
   __syncthreads();  // `red` is reused
   block_reduce<kNdtAccB>(accb, red);
   if (threadIdx.x == 0) {

@@ -38,11 +38,16 @@ struct KdTree {
     pts = points;
     stride = stride_floats;
     n = n_;
-    perm.resize(n);
-    for (size_t i = 0; i < n; i++) perm[i] = (int)i;
+    // pcl::KdTreeFLANN::convertCloudToArray indexes the FINITE points only (non-dense clouds): a NaN / inf point is never a neighbour
+    perm.clear();
+    perm.reserve(n);
+    for (size_t i = 0; i < n; i++) {
+      const float* p = points + i * stride_floats;
+      if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) perm.push_back((int)i);
+    }
     nodes.clear();
     nodes.reserve(n / 4 + 16);
-    if (n > 0) build_rec(0, (int)n);
+    if (!perm.empty()) build_rec(0, (int)perm.size());
   }
 
   int build_rec(int b, int e) {
@@ -140,7 +145,8 @@ struct KdTree {
   // returns number found (min(k, n)); out_idx/out_d2 ascending by (d2, idx)
   int knn(const float* q, int k, int* out_idx, float* out_d2) const {
     Heap h{k, 0, out_d2, out_idx};
-    if (n == 0) return 0;
+    if (nodes.empty()) return 0;
+    if (!(std::isfinite(q[0]) && std::isfinite(q[1]) && std::isfinite(q[2]))) return 0;  // PCL: a non-finite query finds nothing
     search_rec(0, q, h);
     return h.cnt;
   }
