@@ -123,6 +123,12 @@ struct Nn1 {
     // padding entries carry (+inf, kPadIdx): never better than anything, so no explicit padding test is needed
     if (d2 < bd2 || (d2 == bd2 && idx < bidx)) { bd2 = d2; bidx = idx; best_pos = pos; }
   }
+  // the same as a predicated update (three selects, no branch): the all-pairs tile loop runs it 32 times per lane and visited leaf,
+  // and a divergent `if` there costs a BSSY / BRA / BSYNC triple per candidate (ncu: 20 % of the search kernel's instructions)
+  B2R_HD void visit_if(bool on, float d2, int idx, int pos) {
+    const bool b = on & ((d2 < bd2) | ((d2 == bd2) & (idx < bidx)));
+    bd2 = b ? d2 : bd2; bidx = b ? idx : bidx; best_pos = b ? pos : best_pos;
+  }
   B2R_HD float best_d2() const { return bd2; }
   B2R_HD int best_idx() const { return bidx; }
 #ifdef B2R_WARP_CODE
@@ -304,7 +310,7 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #pragma unroll
       for (int t = 0; t < kLeaf / C; t++) {
         const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
-        if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
       }
       v.template merge_copies<C>();
     } else if constexpr (Visitor::kTwoPhase) {
@@ -332,7 +338,7 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #pragma unroll Visitor::kTileUnroll
       for (int t = 0; t < kLeaf; t++) {
         const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-        if (pass) v.visit(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
       }
     }
     return true;
