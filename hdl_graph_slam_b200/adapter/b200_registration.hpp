@@ -76,20 +76,20 @@ public:
       cache_cursor_ = 0;
     }
     const size_t n = cache_cloud_.points.size();
-    for (int attempt = 0; attempt < 2; attempt++) {  // the sweep restarts from 0 for the second consumer (inlier loop)
-      const size_t c = attempt == 0 ? cache_cursor_ : 0;
-      if (c < n) {
-        const PointT& q = cache_cloud_.points[c];
-        if (q.x == p.x && q.y == p.y && q.z == p.z) {
-          *idx = cache_idx_[c];
-          *d2 = cache_d2_[c];
-          cache_cursor_ = c + 1;
-          return true;
-        }
-      }
+    // the consumers sweep the cloud in order: try the cursor, then the start (second consumer), then a short window ahead of the
+    // cursor (a consumer that skipped points); a miss moves the cursor on, so one odd point cannot turn the rest of the sweep
+    // into single-query launches
+    const size_t tries[2] = {cache_cursor_, 0};
+    for (size_t c : tries) {
+      if (c < n && same_point(cache_cloud_.points[c], p)) { *idx = cache_idx_[c]; *d2 = cache_d2_[c]; cache_cursor_ = c + 1; return true; }
     }
+    for (size_t c = cache_cursor_ + 1; c < n && c < cache_cursor_ + 64; c++) {
+      if (same_point(cache_cloud_.points[c], p)) { *idx = cache_idx_[c]; *d2 = cache_d2_[c]; cache_cursor_ = c + 1; return true; }
+    }
+    if (cache_cursor_ < n) cache_cursor_++;
     return false;
   }
+  static bool same_point(const PointT& q, const PointT& p) { return q.x == p.x && q.y == p.y && q.z == p.z; }
 
   explicit B200Registration(const b2r_config& cfg) {
     if (b2r_create(&cfg, &h_) != B2R_OK) throw std::runtime_error(std::string("b200reg: ") + b2r_last_error());
@@ -138,8 +138,11 @@ protected:
     this->nr_iterations_ = r.iterations;
     for (int i = 0; i < 16; i++) this->final_transformation_.data()[i] = r.T[i];
     this->transformation_ = this->final_transformation_;
-    // `output` feeds the inlier loop of the status publisher (scan_matching_odometry_nodelet.cpp:314-316)
-    if (rc == B2R_OK && !output.points.empty()) b2r_get_aligned(h_, output.points.data(), output.points.size(), sizeof(PointT));
+    // `output` feeds the inlier loop of the status publisher (scan_matching_odometry_nodelet.cpp:314-316), which looks every
+    // one of its points up through tree_->nearestKSearch.  It is produced by PCL's OWN pcl::transformPointCloud — the very call
+    // that seeds the nearest-neighbour cache (cachedNearest) — so the two clouds are bit-identical by construction, whatever
+    // association / SIMD path the installed PCL uses for the 4x4 product, and the sweep is served from the cache.
+    if (rc == B2R_OK && this->input_ && !this->input_->points.empty()) pcl::transformPointCloud(*this->input_, output, this->final_transformation_);
   }
 
 private:

@@ -42,6 +42,9 @@ struct b2r_handle {
   cudaStream_t st2 = nullptr;       // prefetch stream (upload + BVH + covariances of the next source overlap the current align)
   cudaEvent_t ev_prefetch = nullptr;
   bool prefetched = false;
+  unsigned long long prefetch_stamp = 0;   // content stamp of the prefetched host cloud (content_stamp)
+  cudaEvent_t upload_ev = nullptr;         // end of the last DMA out of a caller-owned pinned buffer
+  bool upload_pending = false;
   // per-align workspaces (sized by the source)
   DevBuf<int> corr[2], cpos[2];     // double-buffered: a speculative linearisation writes the other set
   DevBuf<float> d2;
@@ -188,6 +191,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     if (cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
   }
   if (cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
+  if (cudaEventCreateWithFlags(&h->upload_ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 3; i++) {
     int rc = alloc_cloud(h->clouds[i]);
     if (rc) return bail(rc);
@@ -266,6 +270,7 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+  if (h->upload_ev) cudaEventDestroy(h->upload_ev);
   delete h;
 }
 
@@ -300,7 +305,11 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
     c.raw_view = c.raw.p;
     if (bytes > 0) {
       if (is_pinned_host(pts)) {
+        // DMA straight from the caller's pinned buffer; `upload_ev` marks the end of that copy so that a synchronous entry point
+        // (b2r_set_source / b2r_set_target) can hand the buffer back to the caller on return, as b200reg.h promises
         B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyHostToDevice, st));
+        B2R_CUDA(cudaEventRecord(h->upload_ev, st));
+        h->upload_pending = true;
         h->tel.h2d += bytes;
       } else {
         int sidx = which;
@@ -492,12 +501,29 @@ static int preprocess(b2r_handle* h, int which, bool is_target) {
   return ensure_grid(h, c);
 }
 
+// cheap identity of a host cloud's CONTENT: FNV-1a over 64 records spread evenly over the buffer (plus n and stride)
+static unsigned long long content_stamp(const void* pts, size_t n, size_t stride) {
+  unsigned long long x = 1469598103934665603ull ^ (unsigned long long)n * 1099511628211ull ^ (unsigned long long)stride;
+  if (!pts || n == 0) return x;
+  const unsigned char* b = (const unsigned char*)pts;
+  const size_t step = n > 64 ? n / 64 : 1;
+  for (size_t i = 0; i < n; i += step) {
+    const unsigned char* r = b + i * stride;
+    for (int k = 0; k < 12; k++) { x ^= r[k]; x *= 1099511628211ull; }
+  }
+  const unsigned char* last = b + (n - 1) * stride;
+  for (int k = 0; k < 12; k++) { x ^= last[k]; x *= 1099511628211ull; }
+  return x;
+}
+
 static int set_cloud(b2r_handle* h, bool is_target, const void* pts, size_t n, size_t stride, bool dev) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
   if (!is_target && h->prefetched) {
     Cloud& nx = h->clouds[h->nxt];
     h->prefetched = false;
-    if (nx.host_ptr == pts && nx.n == n && (size_t)nx.stride_f * 4 == stride) {  // this is the cloud we prefetched: adopt it
+    // adopt the prefetched cloud only if it is still THE cloud: same buffer, same shape and the same content stamp (a caller that
+    // recycles one staging buffer and has rewritten it since the prefetch gets a fresh upload instead of the previous scan)
+    if (nx.host_ptr == pts && nx.n == n && (size_t)nx.stride_f * 4 == stride && (dev || content_stamp(pts, n, stride) == h->prefetch_stamp)) {
       B2R_CUDA(cudaSetDevice(h->cfg.device_id));
       std::swap(h->src, h->nxt);
       B2R_CUDA(cudaStreamWaitEvent(h->st, h->ev_prefetch, 0));
@@ -506,14 +532,22 @@ static int set_cloud(b2r_handle* h, bool is_target, const void* pts, size_t n, s
     }
   }
   int which = is_target ? h->tgt : h->src;
+  h->upload_pending = false;
   int rc = upload(h, which, pts, n, stride, dev, h->st);
   if (rc) return rc;
   h->corr_valid = false;
-  return preprocess(h, which, is_target);
+  rc = preprocess(h, which, is_target);  // the structure builds are enqueued behind the copy before the host waits for it
+  if (h->upload_pending) {
+    // the caller keeps ownership of its (pinned) buffer: the copy out of it has finished when this call returns
+    B2R_CUDA(cudaEventSynchronize(h->upload_ev));
+    h->upload_pending = false;
+  }
+  return rc;
 }
 
 static int prefetch_source(b2r_handle* h, const void* pts, size_t n, size_t stride, bool dev) {
   if (!h) return fail(B2R_EINVAL, "handle is NULL");
+  if (!dev && pts) h->prefetch_stamp = content_stamp(pts, n, stride);
   // the buffers of the `nxt` slot may still be read by kernels enqueued on the main stream (it was the source of an earlier
   // align that has completed: b2r_align synchronises), so they are free to be overwritten here
   int rc = upload(h, h->nxt, pts, n, stride, dev, h->st2);
@@ -1456,10 +1490,13 @@ extern "C" int b2r_map_cloud_generate(b2r_handle* h, const b2r_keyframe_snapshot
   unsigned long long* first_idx = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->map_geom) + sizeof(MapGeom));
   int* n_dev = reinterpret_cast<int*>(first_idx + 1);
   { TEL_BEGIN(&h->tel, st);
-    B2R_CUDA(cudaMemsetAsync(first_idx, 0xff, sizeof(unsigned long long), st));
-    k_grid_reset<<<1, 32, 0, st>>>(h->bc[0].mm);
-    k_map_first_and_bbox<<<nb, 256, 0, st>>>(cloud.p, sf, T, first_idx, h->bc[0].mm);
-    k_map_geom<<<1, 1, 0, st>>>(cloud.p, sf, first_idx, h->bc[0].mm, resolution, h->map_geom);
+    // replay of the octree's bounding-box growth: each round finds the first point outside the box and grows the box for it; the
+    // box settles after ~log2(extent / resolution) rounds, further rounds exit at once (G.done)
+    k_oct_init<<<1, 1, 0, st>>>(h->map_geom, resolution, first_idx);
+    for (int round = 0; round < 48; round++) {
+      k_oct_first_violator<<<nb, 256, 0, st>>>(cloud.p, sf, T, h->map_geom, first_idx);
+      k_oct_grow<<<1, 1, 0, st>>>(cloud.p, sf, h->map_geom, first_idx);
+    }
     k_map_keys<<<nb, 256, 0, st>>>(cloud.p, sf, T, h->map_geom, h->map_keys[0].p);
     size_t tb = h->bc[0].sort_tmp.cap;
     cub::DeviceRadixSort::SortKeys(h->bc[0].sort_tmp.p, tb, h->map_keys[0].p, h->map_keys[1].p, (int)total, 0, 64, st);
@@ -1467,7 +1504,7 @@ extern "C" int b2r_map_cloud_generate(b2r_handle* h, const b2r_keyframe_snapshot
     tb = h->bc[0].sort_tmp.cap;
     cub::DeviceScan::ExclusiveSum(h->bc[0].sort_tmp.p, tb, flags, slots, (int)total, st);
     k_map_centers<<<nb, 256, 0, st>>>(h->map_keys[1].p, flags, slots, T, h->map_geom, sf, src.p, n_dev);
-    TEL_END(&h->tel, KC_MISC, 12, st); }
+    TEL_END(&h->tel, KC_MISC, 106, st); }
   B2R_CUDA(cudaGetLastError());
   B2R_CUDA(cudaMemcpyAsync(h->map_h, n_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));

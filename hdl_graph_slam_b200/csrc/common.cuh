@@ -80,4 +80,11 @@ B2R_HD bool finite3(float x, float y, float z) {
 
 B2R_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Position-dependent checksum term of the fence-free result messages (engine.cuh, pair_engine.cuh): word i enters rotated by
+// (7 i + 1) bits, so two stale words cannot cancel each other (an xor of plain words ignores position).
+B2R_HD unsigned long long msg_mix(unsigned long long w, int i) {
+  const int r = (7 * i + 1) & 63;
+  return (w << r) | (w >> ((64 - r) & 63));
+}
+
 }  // namespace b2r

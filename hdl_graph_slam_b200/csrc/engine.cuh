@@ -105,17 +105,17 @@ struct Telemetry {
 #define TEL_END(tel, cls, n, st) do { if (tel) (tel)->end(_tel_ev, cls, n, st); } while (0)
 
 // Wait for the result message of a reduction kernel (finish_partials) in host-mapped memory: `nv` result words at out[0..nv),
-// one more word at out[nv] (the optional `extra`, included only if has_extra), the checksum seq ^ xor(words) at out[nv+1], and
+// one more word at out[nv] (the optional `extra`, included only if has_extra), the checksum seq ^ xor(mix(word_i, i)) at out[nv+1], and
 // `flag` = seq.  The device publishes them without system-scope fences, so the words may land in any order: the message is
 // accepted only when it is self-consistent.  Falls back to querying / synchronising the stream so that a failed launch or a
 // device fault still surfaces as an error (after a synchronise every store has landed).
-// the acceptance test of a result message: flag == seq and checksum word == seq ^ xor(result words [^ extra word])
+// the acceptance test of a result message: flag == seq and checksum word == seq ^ xor(msg_mix(word_i, i)) over the result words [and the extra word]
 inline bool result_message_consistent(const volatile unsigned long long* flag, unsigned long long seq, const volatile unsigned long long* w, int nv,
                                       bool has_extra) {
   if (*flag != seq) return false;
   unsigned long long x = seq;
-  for (int i = 0; i < nv; i++) x ^= w[i];
-  if (has_extra) x ^= w[nv];
+  for (int i = 0; i < nv; i++) x ^= msg_mix(w[i], i);
+  if (has_extra) x ^= msg_mix(w[nv], nv);
   return x == w[nv + 1];
 }
 

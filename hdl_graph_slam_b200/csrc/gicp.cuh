@@ -344,13 +344,13 @@ __device__ __forceinline__ void finish_stored(double* partials, double* out, uns
         const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(extra);
         *extra = 0;  // device-side counter accumulated with atomics during this launch: read once, re-armed for the next launch
         reinterpret_cast<unsigned long long*>(out)[NV] = e;
-        x ^= e;
+        x ^= msg_mix(e, NV);
       }
       if (flag) {
         // Publication without system-scope fences (each costs a PCIe round trip): the host accepts the result words only when
         // flag == seq AND the checksum word equals seq ^ xor(result words), so the order in which these stores land in host memory
         // does not matter (wait_host_result re-reads until the message is self-consistent).
-        for (int i = 0; i < NV; i++) x ^= (unsigned long long)__double_as_longlong(fin[i]);
+        for (int i = 0; i < NV; i++) x ^= msg_mix((unsigned long long)__double_as_longlong(fin[i]), i);
         reinterpret_cast<unsigned long long*>(out)[NV + 1] = x;
         *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
       }

@@ -4,13 +4,12 @@
 //   for every keyframe snapshot: dst = pose.cast<float>() * src (Vector4f, w = 1), intensity copied, all keyframes concatenated;
 //   resolution <= 0: that cloud is the result; otherwise pcl::octree::OctreePointCloud(resolution).addPointsFromInputCloud() and
 //   getOccupiedVoxelCenters().
-// The octree's voxel lattice is anchored at the FIRST finite point (its bounding box starts as p0 -+ resolution/2 and only ever
-// grows by whole multiples of the voxel size), so the set of occupied voxel centres is
-//     { (floor((p - a) / r) + 0.5) r + a },  a = p0 - r/2  (float64, as PCL keeps min_x_/resolution_)
-// independent of the insertion order.  Here: one transform kernel over all keyframes, 3 x 21-bit voxel keys, a radix sort of the
-// keys (cub::DeviceRadixSort — 10^7..10^8 keys, far beyond the cluster sort's reach), unique, centres.  The result is the same SET
-// of centres as PCL's (float rounding of the centre aside); PCL emits them in octree traversal order, here they come out in
-// ascending (z, y, x) key order — the consumers (rviz, save_map) do not depend on the order.
+// The octree's bounding box (its float64 min corner defines the voxel lattice) is grown in insertion order; that sequential process
+// is replayed exactly on the device (k_oct_first_violator / k_oct_grow: only the few dozen points that ever violate the box
+// matter).  Then: one transform kernel over all keyframes, 3 x 21-bit voxel keys (point - min) / resolution in float64, a radix
+// sort of the keys (cub::DeviceRadixSort — 10^7..10^8 keys, far beyond the cluster sort's reach), unique, centres
+// (key + 0.5) resolution + min.  The result is the same SET of centres as PCL's; PCL emits them in octree traversal order, here
+// they come out in ascending (z, y, x) key order — the consumers (rviz, save_map) do not depend on the order.
 #pragma once
 #include <cub/device/device_radix_sort.cuh>
 #include "engine.cuh"
@@ -25,12 +24,14 @@ struct MapKf {            // one keyframe snapshot on the device
   float T[12];            // rows 0..2 of pose.cast<float>()
 };
 
+// pcl::octree::OctreePointCloud's bounding box (float64 min / max / resolution, as PCL keeps them) and its growth state
 struct MapGeom {
-  double a[3];            // lattice anchor p0 - r/2
+  double mn[3], mx[3];
   double r;
-  long long kmin[3];      // smallest voxel coordinate per axis
-  int has_anchor;
-  int overflow;           // extent / resolution does not fit 21 bits per axis
+  int depth;
+  int defined;
+  int done;
+  int overflow;           // depth beyond 21 bits per axis
 };
 
 // dst = pose * src (Eigen Matrix4f * Vector4f, column accumulation ((m0 x + m1 y) + m2 z) + m3, w = 1), other fields copied
@@ -50,49 +51,61 @@ __global__ void k_map_transform(const MapKf* __restrict__ kfs, int n_kf, int str
   }
 }
 
-// first finite point (lowest index) and the bounding box of the finite points (ordered ints)
-__global__ void k_map_first_and_bbox(const float* __restrict__ cloud, int stride_f, long long total, unsigned long long* first_idx, int* mm) {
-  int mn[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff};
-  int mx[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+// The box is grown exactly as addPointsFromInputCloud grows it (adoptBoundingBoxToPoint, UPSTREAM-RECALL of PCL 1.10): points are
+// inserted in index order; the first finite point defines min/max = p -+ resolution/2; a point outside [min, max) doubles the box
+// (depth + 1) towards itself until it fits.  Only the violators matter, so the sequential process is replayed as: find the FIRST
+// point (lowest index) outside the current box (parallel, atomicMin), grow the box for it (one thread), repeat until nothing
+// violates.
+__global__ void k_oct_init(MapGeom* g, double r, unsigned long long* first_idx) {
+  MapGeom G;
+  for (int d = 0; d < 3; d++) { G.mn[d] = 0; G.mx[d] = 0; }
+  G.r = r; G.depth = 0; G.defined = 0; G.done = 0; G.overflow = 0;
+  *g = G;
+  *first_idx = 0xffffffffffffffffull;
+}
+
+__global__ void k_oct_first_violator(const float* __restrict__ cloud, int stride_f, long long total, const MapGeom* __restrict__ gp, unsigned long long* first_idx) {
+  const MapGeom G = *gp;
+  if (G.done) return;
   unsigned long long fi = 0xffffffffffffffffull;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     const float* p = cloud + (size_t)g * stride_f;
     const float x = p[0], y = p[1], z = p[2];
     if (!finite3(x, y, z)) continue;
-    if ((unsigned long long)g < fi) fi = (unsigned long long)g;
-    const int ox = f2ord(x), oy = f2ord(y), oz = f2ord(z);
-    mn[0] = min(mn[0], ox); mn[1] = min(mn[1], oy); mn[2] = min(mn[2], oz);
-    mx[0] = max(mx[0], ox); mx[1] = max(mx[1], oy); mx[2] = max(mx[2], oz);
+    const bool out = !G.defined || (double)x < G.mn[0] || (double)y < G.mn[1] || (double)z < G.mn[2] || (double)x >= G.mx[0] || (double)y >= G.mx[1] || (double)z >= G.mx[2];
+    if (out) { fi = (unsigned long long)g; break; }  // this thread's indices ascend: its first violator is its lowest
   }
-#pragma unroll
-  for (int d = 0; d < 3; d++) { mn[d] = __reduce_min_sync(0xffffffffu, mn[d]); mx[d] = __reduce_max_sync(0xffffffffu, mx[d]); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, fi, o); fi = t < fi ? t : fi; }
-  if ((threadIdx.x & 31) == 0) {
-    if (fi != 0xffffffffffffffffull) atomicMin(first_idx, fi);
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      if (mn[d] != 0x7fffffff) atomicMin(&mm[d], mn[d]);
-      if (mx[d] != (int)0x80000000) atomicMax(&mm[3 + d], mx[d]);
-    }
-  }
+  if ((threadIdx.x & 31) == 0 && fi != 0xffffffffffffffffull) atomicMin(first_idx, fi);
 }
 
-__global__ void k_map_geom(const float* __restrict__ cloud, int stride_f, const unsigned long long* first_idx, const int* mm, double r, MapGeom* g) {
-  MapGeom G;
-  G.r = r; G.has_anchor = 0; G.overflow = 0;
-  for (int d = 0; d < 3; d++) { G.a[d] = 0; G.kmin[d] = 0; }
-  if (*first_idx != 0xffffffffffffffffull) {
-    const float* p = cloud + (size_t)(*first_idx) * stride_f;
-    G.has_anchor = 1;
-    for (int d = 0; d < 3; d++) {
-      G.a[d] = (double)p[d] - r / 2;  // OctreePointCloud::adoptBoundingBoxToPoint, first point: min = point - resolution / 2
-      const double lo = floor(((double)ord2f(mm[d]) - G.a[d]) / r), hi = floor(((double)ord2f(mm[3 + d]) - G.a[d]) / r);
-      G.kmin[d] = (long long)lo;
-      if (!(hi - lo < 2097151.0)) G.overflow = 1;
+__global__ void k_oct_grow(const float* __restrict__ cloud, int stride_f, MapGeom* gp, unsigned long long* first_idx) {
+  MapGeom G = *gp;
+  if (G.done) return;
+  const unsigned long long idx = *first_idx;
+  *first_idx = 0xffffffffffffffffull;
+  if (idx == 0xffffffffffffffffull) { G.done = 1; *gp = G; return; }
+  const float* p = cloud + (size_t)idx * stride_f;
+  const double q[3] = {(double)p[0], (double)p[1], (double)p[2]};
+  const double eps = (double)1.1920928955078125e-07f;  // std::numeric_limits<float>::epsilon()
+  for (int guard = 0; guard < 64; guard++) {
+    bool lower[3], upper[3], any = false;
+    for (int d = 0; d < 3; d++) { lower[d] = q[d] < G.mn[d]; upper[d] = q[d] >= G.mx[d]; any |= lower[d] | upper[d]; }
+    if (G.defined && !any) break;
+    if (G.defined) {
+      double side = (double)(1 << G.depth) * G.r;
+      for (int d = 0; d < 3; d++) if (!upper[d]) G.mn[d] -= side;
+      G.depth++;
+      side = (double)(1 << G.depth) * G.r - eps;
+      for (int d = 0; d < 3; d++) G.mx[d] = G.mn[d] + side;
+      if (G.depth > 21) { G.overflow = 1; G.done = 1; break; }
+    } else {
+      for (int d = 0; d < 3; d++) { G.mn[d] = q[d] - G.r / 2; G.mx[d] = q[d] + G.r / 2; }
+      G.defined = 1;
     }
   }
-  *g = G;
+  *gp = G;
 }
 
 __global__ void k_map_keys(const float* __restrict__ cloud, int stride_f, long long total, const MapGeom* __restrict__ gp, unsigned long long* keys) {
@@ -101,11 +114,11 @@ __global__ void k_map_keys(const float* __restrict__ cloud, int stride_f, long l
     const float* p = cloud + (size_t)g * stride_f;
     const float x = p[0], y = p[1], z = p[2];
     unsigned long long key = 0xffffffffffffffffull;  // non-finite points are not inserted (OctreePointCloud::addPointsFromInputCloud)
-    if (finite3(x, y, z) && G.has_anchor && !G.overflow) {
-      // genOctreeKeyforPoint: key = (unsigned)((point - min) / resolution) in float64; min = a - (whole voxels)
-      const unsigned long long kx = (unsigned long long)((long long)floor(((double)x - G.a[0]) / G.r) - G.kmin[0]);
-      const unsigned long long ky = (unsigned long long)((long long)floor(((double)y - G.a[1]) / G.r) - G.kmin[1]);
-      const unsigned long long kz = (unsigned long long)((long long)floor(((double)z - G.a[2]) / G.r) - G.kmin[2]);
+    if (finite3(x, y, z) && G.defined && !G.overflow) {
+      // genOctreeKeyforPoint: key = static_cast<unsigned int>((point - min) / resolution), float64
+      const unsigned long long kx = (unsigned long long)(((double)x - G.mn[0]) / G.r);
+      const unsigned long long ky = (unsigned long long)(((double)y - G.mn[1]) / G.r);
+      const unsigned long long kz = (unsigned long long)(((double)z - G.mn[2]) / G.r);
       key = (kz << 42) | (ky << 21) | kx;
     }
     keys[g] = key;
@@ -127,11 +140,12 @@ __global__ void k_map_centers(const unsigned long long* __restrict__ keys, const
     if (g == total - 1) *n_out = slots[g] + flags[g];
     if (!flags[g]) continue;
     const unsigned long long k = keys[g];
-    const long long kx = (long long)(k & 0x1fffffull) + G.kmin[0], ky = (long long)((k >> 21) & 0x1fffffull) + G.kmin[1], kz = (long long)(k >> 42) + G.kmin[2];
+    const unsigned long long kx = k & 0x1fffffull, ky = (k >> 21) & 0x1fffffull, kz = k >> 42;
     float* o = out + (size_t)slots[g] * stride_f;
-    o[0] = (float)(((double)kx + 0.5) * G.r + G.a[0]);
-    o[1] = (float)(((double)ky + 0.5) * G.r + G.a[1]);
-    o[2] = (float)(((double)kz + 0.5) * G.r + G.a[2]);
+    // genLeafNodeCenterFromOctreeKey: (key + 0.5f) * resolution + min, float64, narrowed to float
+    o[0] = (float)(((double)kx + 0.5) * G.r + G.mn[0]);
+    o[1] = (float)(((double)ky + 0.5) * G.r + G.mn[1]);
+    o[2] = (float)(((double)kz + 0.5) * G.r + G.mn[2]);
     if (stride_f >= 4) o[3] = 1.0f;
     for (int q = 4; q < stride_f; q++) o[q] = 0.f;
   }

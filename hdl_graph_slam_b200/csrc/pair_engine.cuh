@@ -83,12 +83,7 @@ struct PairDev {
 };
 
 // ------------------------------------------------------------------------------------------------ message publication
-// Position-dependent checksum: word i enters rotated by (7 i + 1) bits, so two stale words cannot cancel each other
-// (an xor of plain words ignores position).
-B2R_HD unsigned long long msg_mix(unsigned long long w, int i) {
-  const int r = (7 * i + 1) & 63;
-  return (w << r) | (w >> ((64 - r) & 63));
-}
+// (msg_mix, the position-dependent checksum term, lives in common.cuh)
 
 // The LM step functions below are __host__ __device__: the device runs them in the last block of k_pair_accumulate, and
 // tests/lm_harness.cu drives the very same state machine on the CPU against the oracle's step_lm (no GPU needed).

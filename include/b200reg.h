@@ -10,7 +10,12 @@
  * Conventions
  *   - Point records: float32 x,y,z at byte offsets 0,4,8 of a record `stride_bytes` long (16 = packed float4,
  *     32 = pcl::PointXYZI with intensity at offset 16).  Host pointers may be pageable or pinned (pinned buffers
- *     are DMA'd directly); the engine copies, the caller keeps ownership.
+ *     are DMA'd directly); the engine copies, the caller keeps ownership: when b2r_set_source / b2r_set_target /
+ *     b2r_odometry_matching / b2r_loop_matching return, the copy out of the caller's buffer has finished and the buffer may be
+ *     reused.  Only the explicitly asynchronous entry points keep reading it after they return: b2r_prefetch_source /
+ *     b2r_odometry_prefetch (until the b2r_set_source that adopts the cloud returns; a buffer rewritten in between is detected by
+ *     a content stamp and uploaded afresh) and b2r_batch_add_cloud with pinned memory (until the next b2r_batch_* call that
+ *     aligns or synchronises returns).
  *   - 4x4 matrices are COLUMN-major (what Eigen::Matrix4f::data() / Eigen::Matrix4d::data() hand out).
  *   - Every function returns 0 on success or a negative B2R_E* code; nothing throws or aborts; on failure
  *     b2r_last_error() holds a message and results report converged = 0 (the reference's failure signal,

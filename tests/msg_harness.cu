@@ -23,9 +23,9 @@ int main() {
       // the new message, as the device would store it
       std::vector<unsigned long long> msg(nv + 2);
       unsigned long long x = seq;
-      for (int i = 0; i < nv; i++) { msg[i] = bits(rnd() * 1e3); x ^= msg[i]; }
+      for (int i = 0; i < nv; i++) { msg[i] = bits(rnd() * 1e3); x ^= msg_mix(msg[i], i); }
       msg[nv] = has_extra ? (unsigned long long)(seq * 7919) : mem[nv];
-      if (has_extra) x ^= msg[nv];
+      if (has_extra) x ^= msg_mix(msg[nv], nv);
       msg[nv + 1] = x;
       // stores land one by one in a random order; index nv + 2 stands for the flag
       std::vector<int> order(nv + 3);
@@ -46,6 +46,18 @@ int main() {
       if (!result_message_consistent(&flag, seq, mem.data(), nv, has_extra != 0)) bad++;   // complete message must be accepted
       if (result_message_consistent(&flag, seq + 1, mem.data(), nv, has_extra != 0)) bad++;  // and only for its own sequence number
     }
+  }
+  {  // two stale words whose old ^ new deltas are equal would cancel in a plain xor checksum; with the position mix they do not
+    const int nv2 = 4;
+    unsigned long long w[nv2 + 2] = {5, 9, 100, 200, 0, 0};
+    unsigned long long flag2 = 7, x = 7;
+    for (int i = 0; i < nv2; i++) x ^= msg_mix(w[i], i);
+    w[nv2 + 1] = x;
+    if (!result_message_consistent(&flag2, 7, w, nv2, false)) bad++;
+    unsigned long long stale[nv2 + 2];
+    std::memcpy(stale, w, sizeof(w));
+    stale[0] ^= 0x33; stale[1] ^= 0x33;  // both words stale by the same delta
+    if (result_message_consistent(&flag2, 7, stale, nv2, false)) bad++;
   }
   printf("trials=%ld accepted_partial=%ld rejected_complete=%ld\n", trials, accepted_partial, bad);
   return (bad || accepted_partial) ? 1 : 0;
