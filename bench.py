@@ -19,7 +19,9 @@ chain only replicates.  The N = 1 line carries that workload's 1-GPU figure unde
 and the strict call-by-call odometry figure (no announced next frame: what the pcl::Registration adapter can issue) under
 config.strict_chain_value.
 
-Other workloads: --workload ndt_odometry_hdl32e_128k (configs[2]), --workload loop_batch (configs[3]), --workload gicp_odometry_vlp16_64k.
+Other workloads: --workload ndt_odometry_hdl32e_128k (configs[2]), --workload loop_batch (configs[3]), --workload gicp_odometry_vlp16_64k,
+--workload voxelgrid (SURVEY §8 row a5 alone), --workload kitti_pipeline (configs[4]'s per-scan chain: prefilter -> odometry in HBM); the last
+two live in bench_workloads.py.
 """
 import argparse
 import json
@@ -47,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=None, choices=list(WORKLOADS) + ["loop_batch"],
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS) + ["loop_batch", "voxelgrid", "kitti_pipeline"],
                     help="default: gicp_odometry_vlp16_64k at 1 GPU, loop_batch (the sharded path) at N > 1")
     ap.add_argument("--cpu-sample", type=int, default=6, help="frames of the same workload timed on the CPU oracle (cpu_baseline)")
     ap.add_argument("--pairs", type=int, default=256, help="loop_batch: candidate pairs per GPU")
@@ -506,6 +508,14 @@ def main():
             args.steps = 5  # default: 5 timed passes of the whole batch
         args.warmup = max(args.warmup, 3) if args.warmup != 5 else 3
         return batch.bench_loop_batch(args, rank, world, local_rank)
+    if args.workload in ("voxelgrid", "kitti_pipeline"):
+        import bench_workloads
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": f"--workload {args.workload}: the CPU figure is this workload's own cpu_baseline object"}), flush=True)
+            return
+        fn = bench_workloads.bench_voxelgrid if args.workload == "voxelgrid" else bench_workloads.bench_kitti_pipeline
+        return fn(args, rank, world, local_rank)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl, rank)

@@ -298,8 +298,14 @@ static int upload(b2r_handle* h, int which, const void* pts, size_t n, size_t st
   c.host_ptr = pts;  // identity of the caller's buffer (host or device): used to recognise a prefetched cloud
   c.invalidate();
   const size_t bytes = n * stride_bytes;
-  if (device_ptr) {
-    c.raw_view = (const float*)pts;
+  if (device_ptr && h->cfg.method == B2R_METHOD_NDT) {
+    // an NDT cloud's voxel map is built lazily, when the cloud has become the TARGET (possibly many calls later): the engine
+    // keeps its own copy (device-to-device, ~1 us per MB) so the caller's buffer is free once the call that first uses it returns
+    B2R_CUDA(c.raw.reserve(n * c.stride_f + 4));
+    c.raw_view = c.raw.p;
+    if (bytes > 0) B2R_CUDA(cudaMemcpyAsync(c.raw.p, pts, bytes, cudaMemcpyDeviceToDevice, st));
+  } else if (device_ptr) {
+    c.raw_view = (const float*)pts;  // GICP: read while the structures are built, i.e. until the align / matching call that first uses the cloud returns
   } else {
     B2R_CUDA(c.raw.reserve(n * c.stride_f + 4));
     c.raw_view = c.raw.p;

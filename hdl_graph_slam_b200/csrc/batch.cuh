@@ -20,17 +20,29 @@ struct b2r_batch {
   std::vector<Cloud*> clouds;
   std::vector<int> free_ids;
   std::vector<Cloud*> recycled;  // removed clouds keep their device buffers for the next add (no cudaMalloc churn per keyframe)
-  // pair slots
-  DevBuf<PairDev> d_pairs;
-  DevBuf<int> d_active;
+  // pair slots.  A chunk of pairs is split over kLanes independent round sequences ("lanes"), each on its own stream: a lane's
+  // search kernel (instruction-issue bound) runs beside the other lane's accumulate kernel (gather-latency bound), and a lane's
+  // thin tail rounds overlap the other's fat ones.  Lane 0 runs on the engine's main stream.
+  static constexpr int kLanes = 2;
+  struct Lane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    DevBuf<PairDev> d_pairs;
+    DevBuf<int> d_active;
+    unsigned long long* h_word = nullptr;  // host-mapped: (seq << 32) | pairs still active
+    unsigned long long* h_word_dev = nullptr;
+    unsigned long long seq = 0;
+  };
+  Lane lane[kLanes];
+  cudaEvent_t fork_ev = nullptr;
+  int n_lanes = kLanes;
   DevBuf<PairReport> d_reports;
   DevBuf<char> ws;
   PairDev* h_pairs = nullptr;       // pinned staging
   PairReport* h_reports = nullptr;  // pinned staging
   size_t h_cap = 0;
-  unsigned long long* h_word = nullptr;  // host-mapped: [0] = (seq << 32) | pairs still active, [1] = sum of the pairs' executed rounds
+  unsigned long long* h_word = nullptr;  // host-mapped: [0..kLanes) = the lanes' words, [kLanes] = sum of the pairs' executed rounds
   unsigned long long* h_word_dev = nullptr;
-  unsigned long long seq = 0;
   size_t max_chunk = 1024;  // pairs in flight per launch sequence (~7.7 MB of workspace per 64k-point pair)
   int copies = 1;           // lanes per query of the batched 1-NN search
   // multi-GPU
@@ -77,7 +89,14 @@ extern "C" void b2r_batch_destroy(b2r_batch* b) {
   if (b->comm) ncclCommDestroy(b->comm);
   for (Cloud* c : b->clouds) free_cloud(c);
   for (Cloud* c : b->recycled) free_cloud(c);
-  b->d_pairs.release(); b->d_active.release(); b->d_reports.release(); b->ws.release(); b->d_send.release(); b->d_recv.release();
+  for (int l = 0; l < b2r_batch::kLanes; l++) {
+    b2r_batch::Lane& L = b->lane[l];
+    if (l > 0 && L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
+    if (L.ev) cudaEventDestroy(L.ev);
+    L.d_pairs.release(); L.d_active.release();
+  }
+  if (b->fork_ev) cudaEventDestroy(b->fork_ev);
+  b->d_reports.release(); b->ws.release(); b->d_send.release(); b->d_recv.release();
   if (b->h_pairs) cudaFreeHost(b->h_pairs);
   if (b->h_reports) cudaFreeHost(b->h_reports);
   if (b->h_word) cudaFreeHost(b->h_word);
@@ -104,7 +123,16 @@ extern "C" int b2r_batch_create(const b2r_config* cfg, b2r_batch** out) {
   }
   if (cudaHostAlloc(&b->h_word, 64, cudaHostAllocMapped) != cudaSuccess || cudaHostGetDevicePointer((void**)&b->h_word_dev, b->h_word, 0) != cudaSuccess)
     return bail(fail(B2R_ECUDA, "host allocation failed"));
-  b->h_word[0] = b->h_word[1] = 0;
+  for (int i = 0; i < 8; i++) b->h_word[i] = 0;
+  if (cudaEventCreateWithFlags(&b->fork_ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "event creation failed"));
+  for (int l = 0; l < b2r_batch::kLanes; l++) {
+    b2r_batch::Lane& L = b->lane[l];
+    L.h_word = b->h_word + l; L.h_word_dev = b->h_word_dev + l;
+    if (l == 0) L.st = b->eng->st;
+    else if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(B2R_ECUDA, "stream creation failed"));
+    if (cudaEventCreateWithFlags(&L.ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "event creation failed"));
+  }
+  if (const char* e = getenv("B2R_BATCH_LANES")) { const int c = atoi(e); if (c >= 1 && c <= b2r_batch::kLanes) b->n_lanes = c; }
   if (const char* e = getenv("B2R_BATCH_COPIES")) { const int c = atoi(e); if (c == 1 || c == 2 || c == 4) b->copies = c; }
   if (const char* e = getenv("B2R_BATCH_CHUNK")) { const long c = atol(e); if (c > 0) b->max_chunk = (size_t)c; }
   *out = b;
@@ -316,14 +344,14 @@ static int batch_host_staging(b2r_batch* b, size_t n) {
   return B2R_OK;
 }
 
-static int wait_word(b2r_batch* b, unsigned long long need_seq, size_t* count) {
-  const volatile unsigned long long* w = b->h_word;
+static int wait_word(const b2r_batch::Lane& L, unsigned long long need_seq, size_t* count) {
+  const volatile unsigned long long* w = L.h_word;
   unsigned long spins = 0;
   for (;;) {
     const unsigned long long v = *w;
     if ((v >> 32) >= need_seq) { *count = (size_t)(v & 0xffffffffull); return B2R_OK; }
     if ((++spins & 0xffff) == 0) {
-      cudaError_t e = cudaStreamQuery(b->eng->st);
+      cudaError_t e = cudaStreamQuery(L.st);
       if (e == cudaSuccess) {  // everything has run: the word must be there now
         const unsigned long long v2 = *w;
         if ((v2 >> 32) >= need_seq) { *count = (size_t)(v2 & 0xffffffffull); return B2R_OK; }
@@ -334,80 +362,107 @@ static int wait_word(b2r_batch* b, unsigned long long need_seq, size_t* count) {
   }
 }
 
-// One chunk: pairs[0..m) -> d_rep[0..m) (device).  Every pair of the chunk is in flight at once; rounds cover all of them.
+// One chunk: pairs[0..m) -> d_rep[0..m) (device).  Every pair of the chunk is in flight at once, split over the lanes; a lane's
+// rounds cover all of its pairs.
 static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const LmCfg& cfg, PairReport* d_rep, bool fit_only) {
   b2r_handle* h = b->eng;
   cudaStream_t st = h->st;
-  size_t ws_total = 0, max_pad = 0;
+  // per-launch kernel timing (b2r_set_profiling) wants every kernel alone on the device; tiny chunks are not worth a second stream
+  const int n_lanes = (h->tel.on || m < 16) ? 1 : b->n_lanes;
+  size_t ws_total = 0;
   for (size_t i = 0; i < m; i++) {
     const Cloud& s = *b->clouds[pairs[i].source];
     const Cloud& t = *b->clouds[pairs[i].target];
     if (s.n == 0 || t.n == 0) continue;
-    const size_t n_pad = (size_t)s.nsup * 1024;
-    ws_total += pair_ws_bytes(n_pad, fit_only);
-    if (n_pad > max_pad) max_pad = n_pad;
+    ws_total += pair_ws_bytes((size_t)s.nsup * 1024, fit_only);
   }
   B2R_CUDA(b->ws.reserve(ws_total + 256));
-  B2R_CUDA(b->d_pairs.reserve(m));
-  B2R_CUDA(b->d_active.reserve(m + 1));
   char* wp = b->ws.p;
   wp = reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(wp), 256));
-  size_t n_live = 0;
-  for (size_t i = 0; i < m; i++) {
-    PairDev& P = b->h_pairs[i];
-    const Cloud& s = *b->clouds[pairs[i].source];
-    const Cloud& t = *b->clouds[pairs[i].target];
-    if (s.n == 0 || t.n == 0) {
-      std::memset(&P, 0, sizeof(P));
-      P.mode = PM_DONE;
-      degenerate_report(b->h_reports[i], pairs[i].guess);
-      B2R_CUDA(cudaMemcpyAsync(d_rep + i, &b->h_reports[i], sizeof(PairReport), cudaMemcpyHostToDevice, st));
-      continue;
-    }
-    fill_pair_geometry(P, s, t);
-    double x[16];
-    colmajor_f_to_row_d(pairs[i].guess, x);
-    // a stand-alone fitness evaluation (calc_fitness_score) is a pair that starts in its fitness round at the given pose
-    fill_pair_start(P, x, fit_only ? PM_FIT : PM_FIRST);
-    const size_t n_pad = (size_t)s.nsup * 1024;
-    for (int k = 0; k < 2; k++) { P.cpos[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
-    if (!fit_only) {
-      for (int k = 0; k < 2; k++) { P.corr[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
-      for (int k = 0; k < 2; k++) { P.mahal[k] = reinterpret_cast<double*>(wp); wp += align_up(n_pad * 6 * sizeof(double), 256); }
-    }
-    P.d2 = reinterpret_cast<float*>(wp); wp += align_up(n_pad * sizeof(float), 256);
-    P.partials = reinterpret_cast<double*>(wp); wp += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);
-    P.report = d_rep + i;
-    n_live++;
+  struct LaneRun { size_t i0 = 0, m = 0, known = 0, max_pad = 0; unsigned long long seq_prev = 0; };
+  LaneRun run[b2r_batch::kLanes];
+  if (n_lanes > 1) {
+    B2R_CUDA(cudaEventRecord(b->fork_ev, st));  // the other lanes start after everything the main stream holds so far (uploads, builds, the previous chunk)
+    for (int l = 1; l < n_lanes; l++) B2R_CUDA(cudaStreamWaitEvent(b->lane[l].st, b->fork_ev, 0));
   }
-  B2R_CUDA(cudaMemcpyAsync(b->d_pairs.p, b->h_pairs, m * sizeof(PairDev), cudaMemcpyHostToDevice, st));
-  h->tel.h2d += m * sizeof(PairDev);
-  k_pair_compact<<<1, 1024, 0, st>>>(b->d_pairs.p, (int)m, b->d_active.p, b->h_word_dev, ++b->seq);
-  B2R_CUDA(cudaGetLastError());
+  for (int l = 0; l < n_lanes; l++) {
+    b2r_batch::Lane& L = b->lane[l];
+    LaneRun& R = run[l];
+    R.i0 = m * (size_t)l / (size_t)n_lanes;
+    R.m = m * (size_t)(l + 1) / (size_t)n_lanes - R.i0;
+    if (R.m == 0) continue;
+    B2R_CUDA(L.d_pairs.reserve(R.m));
+    B2R_CUDA(L.d_active.reserve(R.m + 1));
+    for (size_t i = R.i0; i < R.i0 + R.m; i++) {
+      PairDev& P = b->h_pairs[i];
+      const Cloud& s = *b->clouds[pairs[i].source];
+      const Cloud& t = *b->clouds[pairs[i].target];
+      if (s.n == 0 || t.n == 0) {
+        std::memset(&P, 0, sizeof(P));
+        P.mode = PM_DONE;
+        degenerate_report(b->h_reports[i], pairs[i].guess);
+        B2R_CUDA(cudaMemcpyAsync(d_rep + i, &b->h_reports[i], sizeof(PairReport), cudaMemcpyHostToDevice, L.st));
+        continue;
+      }
+      fill_pair_geometry(P, s, t);
+      double x[16];
+      colmajor_f_to_row_d(pairs[i].guess, x);
+      // a stand-alone fitness evaluation (calc_fitness_score) is a pair that starts in its fitness round at the given pose
+      fill_pair_start(P, x, fit_only ? PM_FIT : PM_FIRST);
+      const size_t n_pad = (size_t)s.nsup * 1024;
+      for (int k = 0; k < 2; k++) { P.cpos[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
+      if (!fit_only) {
+        for (int k = 0; k < 2; k++) { P.corr[k] = reinterpret_cast<int*>(wp); wp += align_up(n_pad * sizeof(int), 256); }
+        for (int k = 0; k < 2; k++) { P.mahal[k] = reinterpret_cast<double*>(wp); wp += align_up(n_pad * 6 * sizeof(double), 256); }
+      }
+      P.d2 = reinterpret_cast<float*>(wp); wp += align_up(n_pad * sizeof(float), 256);
+      P.partials = reinterpret_cast<double*>(wp); wp += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);
+      P.report = d_rep + i;
+      R.known++;
+      if (n_pad > R.max_pad) R.max_pad = n_pad;
+    }
+    B2R_CUDA(cudaMemcpyAsync(L.d_pairs.p, b->h_pairs + R.i0, R.m * sizeof(PairDev), cudaMemcpyHostToDevice, L.st));
+    h->tel.h2d += R.m * sizeof(PairDev);
+    k_pair_compact<<<1, 1024, 0, L.st>>>(L.d_pairs.p, (int)R.m, L.d_active.p, L.h_word_dev, ++L.seq);
+    B2R_CUDA(cudaGetLastError());
+  }
   // rounds: the host enqueues round r+1 while the device runs round r and consumes the active count of round r-1 (lag 1), so
-  // grid.y shrinks as pairs converge and the device never waits for the host
-  size_t known = n_live;
-  unsigned long long seq_prev = 0;
+  // grid.y shrinks as pairs converge and the device never waits for the host.  The lanes' rounds are enqueued alternately.
   static const bool pdl = !getenv("B2R_NO_PDL");
-  while (known > 0) {
-    int rc = launch_round(b->d_pairs.p, b->d_active.p, (unsigned)known, (unsigned)max_pad, b->copies, cfg, st, &h->tel, true);
-    if (rc) return rc;
-    b->last_rounds++;
-    const unsigned long long sq = ++b->seq;
-    {
+  for (;;) {
+    bool any = false;
+    unsigned long long sq[b2r_batch::kLanes] = {};
+    for (int l = 0; l < n_lanes; l++) {
+      b2r_batch::Lane& L = b->lane[l];
+      LaneRun& R = run[l];
+      if (R.known == 0) continue;
+      any = true;
+      int rc = launch_round(L.d_pairs.p, L.d_active.p, (unsigned)R.known, (unsigned)R.max_pad, b->copies, cfg, L.st, &h->tel, true);
+      if (rc) return rc;
+      b->last_rounds++;
+      sq[l] = ++L.seq;
       cudaLaunchConfig_t lc = {};
-      lc.gridDim = dim3(1); lc.blockDim = dim3(1024); lc.dynamicSmemBytes = 0; lc.stream = st;
+      lc.gridDim = dim3(1); lc.blockDim = dim3(1024); lc.dynamicSmemBytes = 0; lc.stream = L.st;
       cudaLaunchAttribute la[1];
       la[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       la[0].val.programmaticStreamSerializationAllowed = 1;
       lc.attrs = la; lc.numAttrs = pdl ? 1 : 0;
-      B2R_CUDA(cudaLaunchKernelEx(&lc, k_pair_compact, (const PairDev*)b->d_pairs.p, (int)m, b->d_active.p, b->h_word_dev, sq));
+      B2R_CUDA(cudaLaunchKernelEx(&lc, k_pair_compact, (const PairDev*)L.d_pairs.p, (int)R.m, L.d_active.p, L.h_word_dev, sq[l]));
     }
-    if (seq_prev) {
-      rc = wait_word(b, seq_prev, &known);
-      if (rc) return rc;
+    if (!any) break;
+    for (int l = 0; l < n_lanes; l++) {
+      if (!sq[l]) continue;
+      LaneRun& R = run[l];
+      if (R.seq_prev) {
+        int rc = wait_word(b->lane[l], R.seq_prev, &R.known);
+        if (rc) return rc;
+      }
+      R.seq_prev = sq[l];
     }
-    seq_prev = sq;
+  }
+  for (int l = 1; l < n_lanes; l++) {  // join: whatever follows on the main stream sees every lane's reports
+    B2R_CUDA(cudaEventRecord(b->lane[l].ev, b->lane[l].st));
+    B2R_CUDA(cudaStreamWaitEvent(st, b->lane[l].ev, 0));
   }
   return B2R_OK;
 }
@@ -595,8 +650,8 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
     b->h_gather_cap = M * (size_t)b->world;
   }
   B2R_CUDA(b->d_reports.reserve(1));
-  b->h_word[1] = 0;
-  k_pack_results<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(b->d_reports.p, (int)mine, b->d_send.p, (int)M, b->h_word_dev + 1);
+  b->h_word[b2r_batch::kLanes] = 0;
+  k_pack_results<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(b->d_reports.p, (int)mine, b->d_send.p, (int)M, b->h_word_dev + b2r_batch::kLanes);
   B2R_CUDA(cudaGetLastError());
   const b2r_result* gathered = b->d_send.p;
   if (b->world > 1) {
@@ -608,7 +663,7 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
   B2R_CUDA(cudaMemcpyAsync(b->h_gather, gathered, M * (size_t)b->world * sizeof(b2r_result), cudaMemcpyDeviceToHost, st));
   B2R_CUDA(cudaStreamSynchronize(st));
   b->eng->tel.d2h += M * (size_t)b->world * sizeof(b2r_result);
-  b->last_pair_rounds = b->h_word[1];  // exact: every pair's own round count (the stream has been synchronised)
+  b->last_pair_rounds = b->h_word[b2r_batch::kLanes];  // exact: every pair's own round count (the stream has been synchronised)
   for (int r = 0; r < b->world; r++)
     for (size_t i = p0[r]; i < p1[r]; i++) all_results[i] = b->h_gather[(size_t)r * M + (i - p0[r])];
   for (size_t g = 0; g < n_groups; g++) {

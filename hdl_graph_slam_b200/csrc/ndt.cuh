@@ -292,13 +292,24 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
   __shared__ double red[kNdtAccA * 32];
   __shared__ double s_low[kNdtAccB][kNdtThreads];  // strict lower triangle of H: one float64 column per thread (no conflicts, no sync)
   __shared__ int s_box[6];
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   double acc[kNdtAccA];
 #pragma unroll
   for (int k = 0; k < kNdtAccA; k++) acc[k] = 0.0;
+  if (HESS) {
+#pragma unroll
+    for (int q = 0; q < kNdtAccB; q++) s_low[q][threadIdx.x] = 0.0;
+  }
   unsigned int npairs = 0;
   const VoxGeom V = *A.geom;
+  // Persistent grid: the launch holds at most one resident wave of blocks (ndt_run_pass sizes it from the occupancy) and block b
+  // takes the chunks b, b + gridDim.x, ... of 128 Hilbert-consecutive points.  A cloud of 128k points is 1.7 waves of one-chunk
+  // blocks: launched that way, the second wave's stragglers set the pass time (slowest SM sub-partition 121k cycles against a mean
+  // of 68k, profiles/r02_g).  The per-thread sums run on across the chunks (static assignment => fixed summation order), so the
+  // block reduction is paid once per block instead of once per chunk.
+  const int n_chunks = A.n_sorted / kNdtThreads;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+  const int s = chunk * kNdtThreads + threadIdx.x;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < A.n_sorted) pt = A.src[s];
   const float x = pt.x, y = pt.y, z = pt.z;
@@ -349,10 +360,6 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
     }
   }
   __syncthreads();
-  if (HESS) {
-#pragma unroll
-    for (int q = 0; q < kNdtAccB; q++) s_low[q][threadIdx.x] = 0.0;
-  }
   if (valid) {
     bool have_pd = false;
     float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
@@ -451,6 +458,8 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
 #undef B2R_CJ
       }
     }
+  }
+  __syncthreads();  // s_box / s_cell are re-staged by the next chunk
   }
   // pair count (integer, exact) through a warp reduction + one atomic per warp
   npairs = __reduce_add_sync(0xffffffffu, npairs);
@@ -816,6 +825,22 @@ struct NdtPass {
   unsigned long long pairs;
 };
 
+// blocks of k_ndt_derivatives the device holds at once (occupancy x SM count), asked once per process
+inline unsigned ndt_resident_blocks(bool hess) {
+  static unsigned cached[2] = {0, 0};
+  unsigned& c = cached[hess ? 1 : 0];
+  if (c == 0) {
+    int dev = 0, sms = 148, per = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (hess) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ndt_derivatives<true>, kNdtThreads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_ndt_derivatives<false>, kNdtThreads, 0);
+    if (const char* e = getenv("B2R_NDT_WAVES")) { const double w = atof(e); if (w > 0) per = std::max(1, (int)(per * w)); }
+    c = (unsigned)std::max(1, sms * std::max(per, 1));
+  }
+  return c;
+}
+
 inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& W, cudaStream_t st, const NdtScalars& K, const float* Tf_row,
                         bool compute_hessian, bool hessian_only, NdtPass* out) {
   NdtVoxelMap& M = *tgt.ndt;
@@ -844,8 +869,9 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
     return B2R_OK;
   }
   { TEL_BEGIN(W.tel, st);  // W.d_pairs is zero here: allocated zeroed, and the last block of every pass resets it after reading it
-    if (compute_hessian) k_ndt_derivatives<true><<<nb, kNdtThreads, 0, st>>>(A);
-    else k_ndt_derivatives<false><<<nb, kNdtThreads, 0, st>>>(A);
+    const unsigned ng = std::min(nb, ndt_resident_blocks(compute_hessian));
+    if (compute_hessian) k_ndt_derivatives<true><<<ng, kNdtThreads, 0, st>>>(A);
+    else k_ndt_derivatives<false><<<ng, kNdtThreads, 0, st>>>(A);
     TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
   if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());

@@ -270,6 +270,16 @@ class Registration:
                                       C.byref(dptr), C.byref(m)))
         return (out[: m.value] if want_host else None), dptr.value, m.value
 
+    def prefilter_raw(self, ptr, n, stride_bytes, device=False, **params):
+        """b2r_prefilter on a raw (host or device) pointer; the result stays in HBM: returns (None, device pointer, count)"""
+        p = _capi.PrefilterParams()
+        check(self._lib.b2r_prefilter_params_default(C.byref(p)))
+        for k, v in params.items():
+            setattr(p, k, v)
+        dptr, m = C.c_void_p(), C.c_size_t()
+        check(self._lib.b2r_prefilter(self._h, C.c_void_p(ptr), n, stride_bytes, int(device), C.byref(p), None, C.byref(dptr), C.byref(m)))
+        return None, dptr.value, m.value
+
     def ingestPointCloud2(self, blob, n_points, point_step, off_x=0, off_y=4, off_z=8, off_intensity=0xffffffff, intensity_datatype=7, is_bigendian=False):
         """sensor_msgs/PointCloud2 data[] -> device PointXYZI records (b2r_ingest_pointcloud2); returns the device pointer"""
         buf = np.frombuffer(blob, np.uint8) if not isinstance(blob, np.ndarray) else blob.view(np.uint8).reshape(-1)

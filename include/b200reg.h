@@ -15,7 +15,11 @@
  *     reused.  Only the explicitly asynchronous entry points keep reading it after they return: b2r_prefetch_source /
  *     b2r_odometry_prefetch (until the b2r_set_source that adopts the cloud returns; a buffer rewritten in between is detected by
  *     a content stamp and uploaded afresh) and b2r_batch_add_cloud with pinned memory (until the next b2r_batch_* call that
- *     aligns or synchronises returns).
+ *     aligns or synchronises returns).  DEVICE pointers (b2r_set_*_device, b2r_odometry_matching_device, b2r_*_add_cloud_device) are
+ *     read in place, never copied, while the cloud's search structure and covariances are built: keep them valid and unmodified
+ *     until the align / matching / batch call that first uses the cloud returns (an NDT handle takes a device-to-device copy instead,
+ *     because a target's voxel map is built only when the cloud has been promoted to target).  b2r_get_aligned re-reads the
+ *     source buffer.
  *   - 4x4 matrices are COLUMN-major (what Eigen::Matrix4f::data() / Eigen::Matrix4d::data() hand out).
  *   - Every function returns 0 on success or a negative B2R_E* code; nothing throws or aborts; on failure
  *     b2r_last_error() holds a message and results report converged = 0 (the reference's failure signal,
