@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=256, help="loop_batch: candidate pairs per GPU")
     ap.add_argument("--fitness-max-range", type=float, default=2.5, help="loop_batch: fitness_score_max_range (hdl_graph_slam_400/kitti.launch)")
     ap.add_argument("--ref-pairs", type=int, default=16, help="--impl reference on loop_batch: candidate pairs per step on the CPU oracle")
+    ap.add_argument("--distinct-shards", action="store_true", help="loop_batch at N > 1: every rank gets different keyframe groups (default: identical shards)")
     ap.add_argument("--no-anchor", action="store_true", help="N = 1 odometry line: skip the loop_batch_n1 / strict-chain extras")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="strict call-by-call chain: do not announce the next frame (no software pipelining)")

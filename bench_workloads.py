@@ -33,7 +33,7 @@ def _setup(args, rank, world, local_rank):
 
 
 def _frames(torch, dev, rank, count=N_FRAMES):
-    from . import synth
+    from hdl_graph_slam_b200 import synth
     first = synth.scan("kitti", frame=rank * 1000, stride=8)
     n, stride_f = first.shape
     host = torch.empty((count, n, stride_f), dtype=torch.float32, pin_memory=True)

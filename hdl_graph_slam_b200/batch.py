@@ -18,6 +18,7 @@ argmin.  So the batch shards naturally:
 import ctypes as C
 import json
 import os
+import sys
 import time
 import numpy as np
 
@@ -89,11 +90,18 @@ LAP = 251  # frames per lap of the synthetic circuit: frame f + LAP revisits the
 GROUP = 8
 
 
-def loop_workload(n_groups, sensor="vlp16", seed=1234):
+def loop_workload(n_groups, sensor="vlp16", seed=1234, period=None):
     """n_groups new keyframes, each with GROUP candidates one lap later, a few metres around the new keyframe's pose; initial
     guess = true relative pose o perturbation U(+-0.5 m, +-3 deg), z zeroed as loop_detector.hpp:141-142.
+    period: the workload repeats after `period` groups (group g is the same keyframes and guesses as group g - period), so that
+    contiguous shards of `period` groups are IDENTICAL work — weak scaling with exactly fixed per-GPU work.
     Returns (frames needed per group [(target frame, [source frames])], guesses (n_pairs, 4, 4) float32, group_first)."""
     from . import synth
+    if period and n_groups > period:
+        base_groups, base_guesses, _ = loop_workload(period, sensor, seed)
+        groups = [base_groups[g % period] for g in range(n_groups)]
+        guesses = np.concatenate([base_guesses[(g % period) * GROUP:(g % period + 1) * GROUP] for g in range(n_groups)])
+        return groups, guesses, [GROUP * g for g in range(n_groups + 1)]
     rng = np.random.default_rng(seed)
     groups, guesses, group_first = [], [], [0]
     for g in range(n_groups):
@@ -136,7 +144,8 @@ def run_loop_batch(args, rank, world, local_rank, quiet=False):
     K, W = max(1, args.steps), max(0, args.warmup)
     per_gpu = args.pairs
     n_groups = max(1, per_gpu // GROUP) * world
-    groups, guesses, group_first = loop_workload(n_groups, "vlp16")
+    distinct = bool(getattr(args, "distinct_shards", False))
+    groups, guesses, group_first = loop_workload(n_groups, "vlp16", period=None if distinct else n_groups // world)
     n_pairs = group_first[-1]
     g0, g1 = shard_range(n_groups, world, rank)
     # the keyframe clouds THIS rank needs (its own groups only), pinned on the host and resident copies in HBM
@@ -167,17 +176,25 @@ def run_loop_batch(args, rank, world, local_rank, quiet=False):
         pairs[p].source = pairs[p].target = -1
     max_range, thresh = args.fitness_max_range, 0.5
 
+    dbg = bool(os.environ.get("B2R_DEBUG_TIMING"))
+
     def one_pass(device_arm):
+        t0 = time.perf_counter()
         base = devbuf.data_ptr() if device_arm else host.data_ptr()
         ids = {f: lb.addCloudRaw(base + slot[f] * fbytes, n, stride_f * 4, device=device_arm) for f in needed}
         for g in range(g0, g1):
             tf, sfs = groups[g]
             for c, sf in enumerate(sfs):
                 pairs[group_first[g] + c].source, pairs[group_first[g] + c].target = ids[sf], ids[tf]
+        t1 = time.perf_counter()
         best, res = lb.loopDetect(pairs, group_first, max_range, thresh, raw=True)
+        t2 = time.perf_counter()
         rounds = lb.lastRounds()
         for cid in ids.values():
             lb.removeCloud(cid)
+        if dbg:
+            print(f"[rank {rank}] pass: add clouds {1e3 * (t1 - t0):.3f} ms, loopDetect {1e3 * (t2 - t1):.3f} ms, remove {1e3 * (time.perf_counter() - t2):.3f} ms",
+                  file=sys.stderr, flush=True)
         return best, res, rounds
 
     results = {}
@@ -257,7 +274,10 @@ def run_loop_batch(args, rank, world, local_rank, quiet=False):
         "dtype": "f32 NN / f64 accumulate", "data": "synthetic",
         "config": {"workload": "BASELINE configs[3]: loop-closure candidate batch (GICP, 64k-pt VLP-16 pairs, 8 candidates per new keyframe), sharded by keyframe group",
                    "pairs_total": n_pairs, "pairs_per_gpu": per_gpu, "points_per_scan": N, "groups": n_groups,
-                   "unique_clouds_per_gpu": len(needed), "cloud_cache": "each keyframe cloud is uploaded and preprocessed once per pass and shared by the pairs that name it",
+                   "unique_clouds_per_gpu": len(needed),
+                   "shards": ("distinct keyframe groups per rank (per-GPU work varies with the shard's iteration counts)" if distinct else
+                              "every rank's shard is the same keyframe groups and guesses: per-GPU work exactly fixed (weak scaling); --distinct-shards gives every rank "
+                              "different places of the circuit, where the MAX over ranks follows the heaviest shard (r2i: 2 x B200 = 1.65 x with identical kernel time on rank 0)"), "cloud_cache": "each keyframe cloud is uploaded and preprocessed once per pass and shared by the pairs that name it",
                    "step": "one pass = register the rank's keyframe clouds (upload + search structure + covariances), align + fitness of all its pairs, one ncclAllGather, argmin",
                    "collective": "one ncclAllGather of 80-byte records, issued by libb200reg (in-library NCCL)", "fitness_max_range": max_range,
                    "l2": "inputs larger than L2: a pass streams the rank's keyframe clouds (2 MiB each) and ~7.7 MB of workspace per pair",

@@ -36,9 +36,15 @@ def build_engine(force=False, verbose=False):
     out = os.path.join(LIB, "libb200reg.so")
     if force or _newer(out, srcs):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        tmp = out + f".tmp{os.getpid()}"  # link under another name, then rename: a reader (or a repo snapshot) never sees a half-written library
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-              "-o", out, os.path.join(csrc, "api.cu"), "-lnccl"]
-        subprocess.check_call(cmd)
+              "-o", tmp, os.path.join(csrc, "api.cu"), "-lnccl"]
+        try:
+            subprocess.check_call(cmd)
+            os.replace(tmp, out)
+        finally:
+            if os.path.exists(tmp):
+                os.remove(tmp)
     return out
 
 

@@ -9,6 +9,7 @@
 //                           ONE ncclAllGather of 80-byte b2r_result records, per-group argmin with the reference's tie rule (:147,160)
 #pragma once
 #include <nccl.h>
+#include <chrono>
 
 struct b2r_batch {
   b2r_handle* eng = nullptr;  // engine context of this device: config, main stream, telemetry
@@ -20,9 +21,11 @@ struct b2r_batch {
   std::vector<Cloud*> clouds;
   std::vector<int> free_ids;
   std::vector<Cloud*> recycled;  // removed clouds keep their device buffers for the next add (no cudaMalloc churn per keyframe)
-  // pair slots.  A chunk of pairs is split over kLanes independent round sequences ("lanes"), each on its own stream: a lane's
-  // search kernel (instruction-issue bound) runs beside the other lane's accumulate kernel (gather-latency bound), and a lane's
-  // thin tail rounds overlap the other's fat ones.  Lane 0 runs on the engine's main stream.
+  // pair slots.  A chunk of pairs can be split over kLanes independent round sequences ("lanes"), each on its own stream, so that a
+  // lane's search kernel (instruction-issue bound) runs beside the other lane's accumulate kernel and a lane's thin tail rounds
+  // overlap the other's fat ones.  Measured on B200 (256 pairs x 64k points): 6688 pairs/s with two lanes, 6713 with one — the block
+  // scheduler drains one kernel's grid before it starts the next stream's, so the overlap is confined to the tails; the default
+  // is ONE lane (B2R_BATCH_LANES=2 enables the second).  Lane 0 runs on the engine's main stream.
   static constexpr int kLanes = 2;
   struct Lane {
     cudaStream_t st = nullptr;
@@ -35,7 +38,7 @@ struct b2r_batch {
   };
   Lane lane[kLanes];
   cudaEvent_t fork_ev = nullptr;
-  int n_lanes = kLanes;
+  int n_lanes = 1;
   DevBuf<PairReport> d_reports;
   DevBuf<char> ws;
   PairDev* h_pairs = nullptr;       // pinned staging
@@ -486,10 +489,13 @@ static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool w
         !b->clouds[pr.target])
       return fail(B2R_EINVAL, "pair names an unknown cloud id");
   }
+  static const bool dbg = getenv("B2R_DEBUG_TIMING") != nullptr;
+  const auto t_a = std::chrono::steady_clock::now();
   int rc = batch_sync_builds(b, false);  // the main stream waits for every outstanding upload / build
   if (rc) return rc;
   rc = batch_build_structures(b, pairs, n_pairs, !fit_only);
   if (rc) return rc;
+  const auto t_b = std::chrono::steady_clock::now();
   const size_t chunk = std::min(b->max_chunk, std::max<size_t>(n_pairs, 1));
   rc = batch_host_staging(b, std::max(chunk, n_pairs));
   if (rc) return rc;
@@ -500,6 +506,11 @@ static int batch_run(b2r_batch* b, const b2r_pair* pairs, size_t n_pairs, bool w
     const size_t m = std::min(chunk, n_pairs - c0);
     rc = batch_run_chunk(b, pairs + c0, m, cfg, b->d_reports.p + c0, fit_only);
     if (rc) return rc;
+  }
+  if (dbg) {
+    const auto t_c = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b2r rank %d] batch_run: build enqueue %.3f ms, rounds (host follows the device) %.3f ms, %llu rounds\n", b->rank,
+            std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count(), b->last_rounds);
   }
   return B2R_OK;
 }
@@ -639,8 +650,12 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
   my_p0 = p0[b->rank]; my_p1 = p1[b->rank];
   const size_t mine = my_p1 - my_p0;
   if (M == 0) { for (size_t g = 0; g < n_groups; g++) best[g] = -1; return B2R_OK; }
+  static const bool dbg = getenv("B2R_DEBUG_TIMING") != nullptr;
+  const auto t_a = std::chrono::steady_clock::now();
   int rc = mine ? batch_run(b, pairs + my_p0, mine, true, fitness_score_max_range) : B2R_OK;
   if (rc) return rc;
+  if (dbg) cudaStreamSynchronize(st);
+  const auto t_b = std::chrono::steady_clock::now();
   B2R_CUDA(b->d_send.reserve(M));
   B2R_CUDA(b->d_recv.reserve(M * (size_t)b->world));
   if (b->h_gather_cap < M * (size_t)b->world) {
@@ -664,6 +679,11 @@ extern "C" int b2r_batch_loop_detect(b2r_batch* b, const b2r_pair* pairs, size_t
   B2R_CUDA(cudaStreamSynchronize(st));
   b->eng->tel.d2h += M * (size_t)b->world * sizeof(b2r_result);
   b->last_pair_rounds = b->h_word[b2r_batch::kLanes];  // exact: every pair's own round count (the stream has been synchronised)
+  if (dbg) {
+    const auto t_c = std::chrono::steady_clock::now();
+    fprintf(stderr, "[b2r rank %d] loop_detect: batch_run + sync %.3f ms, pack + all-gather + readback %.3f ms\n", b->rank,
+            std::chrono::duration<double, std::milli>(t_b - t_a).count(), std::chrono::duration<double, std::milli>(t_c - t_b).count());
+  }
   for (int r = 0; r < b->world; r++)
     for (size_t i = p0[r]; i < p1[r]; i++) all_results[i] = b->h_gather[(size_t)r * M + (i - p0[r])];
   for (size_t g = 0; g < n_groups; g++) {

@@ -328,19 +328,39 @@ __global__ void __launch_bounds__(kLinThreads, B2R_SEARCH_MINBLOCKS) k_pair_sear
   }
 }
 
-// One value of the block reduction, consumed as soon as it is produced: butterfly over the warp, lane 0 parks the warp's sum
-// in shared memory.  (Streaming the 29 values instead of holding 29 float64 accumulators until the end keeps the kernel under
-// 96 registers: 3 blocks of 256 threads per SM instead of 2 — the pass is bound by gather latency, so residency is throughput.)
-__device__ __forceinline__ void red_emit(double v, int i, double* red, int lane, int warp) {
+// One value of the block reduction, consumed as soon as it is produced.  (Streaming the 29 values instead of holding 29 float64
+// accumulators until the end keeps the kernel under 96 registers: 3 blocks of 256 threads per SM instead of 2 — the pass is
+// bound by gather latency, so residency is throughput.)  A butterfly per value is 10 SHFL per lane and value: 290 per warp, which
+// saturated the shared-memory / shuffle data path (ncu r2g: l1tex data-pipe wavefronts 81 % of peak, half of them shuffles).
+// Instead the warp TRANSPOSES through shared memory: every lane stores its value into row (i mod 8) of the warp's tile; after 8
+// values, lane l adds elements q, q + 4, ..., q + 28 (q = l & 3) of row l >> 2 and two shuffle levels join the four partial
+// sums — 2 store + 2 load + 0.5 shuffle wavefronts per value instead of 10.  The order of the additions is fixed.
+constexpr int kRedRow = 36;  // float64 elements per tile row: rows 0..3 of a half-warp start 4 banks apart
+__device__ __forceinline__ void red_flush(int phase, int count, double* tile, double* red, int lane, int warp) {
+  __syncwarp();
+  const int r = lane >> 2, q = lane & 3;
+  double v = 0.0;
+  if (r < count) {
+    const double* row = tile + r * kRedRow + q;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  if (lane == 0) red[i * 8 + warp] = v;
+    for (int t = 0; t < 8; t++) v += row[4 * t];
+  }
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  if (q == 0 && r < count) red[(phase * 8 + r) * 8 + warp] = v;
+  __syncwarp();
+}
+template <int I, int LAST>
+__device__ __forceinline__ void red_emit(double v, double* tile, double* red, int lane, int warp) {
+  tile[(I & 7) * kRedRow + lane] = v;
+  if ((I & 7) == 7 || I == LAST) red_flush(I >> 3, (I & 7) + 1, tile, red, lane, warp);
 }
 
 // linearize (float64) at xe into the write set + compute_error of the previous set, per active pair.  Every block leaves its
 // 29 partial sums in the pair's `partials`; k_pair_lm (next launch) adds them in a fixed order and takes the LM step.
 __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
   __shared__ double red[kAcc * 8];
+  __shared__ double tiles[(kAccThreads / 32) * 8 * kRedRow];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   // single-pair mode: let the (tiny) LM kernel of this round become resident now, so that it starts the moment this grid drains
   if (!active) asm volatile("griddepcontrol.launch_dependents;");
@@ -352,6 +372,7 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   if ((int)blockIdx.x >= nblk) return;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* tile = tiles + warp * 8 * kRedRow;
   const int cur = p.cur;
   const int wset = (mode == PM_FIRST) ? cur : (cur ^ 1);
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
@@ -427,30 +448,30 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   const double ms20 = m12 * tz - m22 * ty, ms21 = -m02 * tz + m22 * tx, ms22 = m02 * ty - m12 * tx;
   const bool lin = mode == PM_FIRST || mode == PM_FUSED;
   // slots 0 and 1 carry the fitness sums in the rounds that do not linearise (PM_FIT, PM_ERR)
-  red_emit(lin ? tz * ms10 - ty * ms20 : fit_sum, 0, red, lane, warp);   // (0,0)
-  red_emit(lin ? tz * ms11 - ty * ms21 : fit_cnt, 1, red, lane, warp);   // (0,1)
-  red_emit(tz * ms12 - ty * ms22, 2, red, lane, warp);   // (0,2)
-  red_emit(-ms00, 3, red, lane, warp);                   // (0,3) = -(MS)[0][0]
-  red_emit(-ms10, 4, red, lane, warp);                   // (0,4)
-  red_emit(-ms20, 5, red, lane, warp);                   // (0,5)
-  red_emit(-tz * ms01 + tx * ms21, 6, red, lane, warp);  // (1,1)
-  red_emit(-tz * ms02 + tx * ms22, 7, red, lane, warp);  // (1,2)
-  red_emit(-ms01, 8, red, lane, warp);                   // (1,3)
-  red_emit(-ms11, 9, red, lane, warp);                   // (1,4)
-  red_emit(-ms21, 10, red, lane, warp);                  // (1,5)
-  red_emit(ty * ms02 - tx * ms12, 11, red, lane, warp);  // (2,2)
-  red_emit(-ms02, 12, red, lane, warp);                  // (2,3)
-  red_emit(-ms12, 13, red, lane, warp);                  // (2,4)
-  red_emit(-ms22, 14, red, lane, warp);                  // (2,5)
-  red_emit(m00, 15, red, lane, warp); red_emit(m01, 16, red, lane, warp); red_emit(m02, 17, red, lane, warp);  // (3,3..5)
-  red_emit(m11, 18, red, lane, warp); red_emit(m12, 19, red, lane, warp);                                      // (4,4..5)
-  red_emit(m22, 20, red, lane, warp);                                                                         // (5,5)
-  red_emit(tz * Mey - ty * Mez, 21, red, lane, warp);
-  red_emit(-tz * Mex + tx * Mez, 22, red, lane, warp);
-  red_emit(ty * Mex - tx * Mey, 23, red, lane, warp);
-  red_emit(-Mex, 24, red, lane, warp); red_emit(-Mey, 25, red, lane, warp); red_emit(-Mez, 26, red, lane, warp);
-  red_emit(ex * Mex + ey * Mey + ez * Mez, 27, red, lane, warp);
-  red_emit(trial, 28, red, lane, warp);
+  red_emit<0, 28>(lin ? tz * ms10 - ty * ms20 : fit_sum, tile, red, lane, warp);   // (0,0)
+  red_emit<1, 28>(lin ? tz * ms11 - ty * ms21 : fit_cnt, tile, red, lane, warp);   // (0,1)
+  red_emit<2, 28>(tz * ms12 - ty * ms22, tile, red, lane, warp);   // (0,2)
+  red_emit<3, 28>(-ms00, tile, red, lane, warp);                   // (0,3) = -(MS)[0][0]
+  red_emit<4, 28>(-ms10, tile, red, lane, warp);                   // (0,4)
+  red_emit<5, 28>(-ms20, tile, red, lane, warp);                   // (0,5)
+  red_emit<6, 28>(-tz * ms01 + tx * ms21, tile, red, lane, warp);  // (1,1)
+  red_emit<7, 28>(-tz * ms02 + tx * ms22, tile, red, lane, warp);  // (1,2)
+  red_emit<8, 28>(-ms01, tile, red, lane, warp);                   // (1,3)
+  red_emit<9, 28>(-ms11, tile, red, lane, warp);                   // (1,4)
+  red_emit<10, 28>(-ms21, tile, red, lane, warp);                  // (1,5)
+  red_emit<11, 28>(ty * ms02 - tx * ms12, tile, red, lane, warp);  // (2,2)
+  red_emit<12, 28>(-ms02, tile, red, lane, warp);                  // (2,3)
+  red_emit<13, 28>(-ms12, tile, red, lane, warp);                  // (2,4)
+  red_emit<14, 28>(-ms22, tile, red, lane, warp);                  // (2,5)
+  red_emit<15, 28>(m00, tile, red, lane, warp); red_emit<16, 28>(m01, tile, red, lane, warp); red_emit<17, 28>(m02, tile, red, lane, warp);  // (3,3..5)
+  red_emit<18, 28>(m11, tile, red, lane, warp); red_emit<19, 28>(m12, tile, red, lane, warp);                                      // (4,4..5)
+  red_emit<20, 28>(m22, tile, red, lane, warp);                                                                         // (5,5)
+  red_emit<21, 28>(tz * Mey - ty * Mez, tile, red, lane, warp);
+  red_emit<22, 28>(-tz * Mex + tx * Mez, tile, red, lane, warp);
+  red_emit<23, 28>(ty * Mex - tx * Mey, tile, red, lane, warp);
+  red_emit<24, 28>(-Mex, tile, red, lane, warp); red_emit<25, 28>(-Mey, tile, red, lane, warp); red_emit<26, 28>(-Mez, tile, red, lane, warp);
+  red_emit<27, 28>(ex * Mex + ey * Mey + ez * Mez, tile, red, lane, warp);
+  red_emit<28, 28>(trial, tile, red, lane, warp);
   __syncthreads();
   // the block's sums: value i = sum over the 8 warps, added in warp order by one thread each
   if (threadIdx.x < kAcc) {

@@ -95,3 +95,44 @@ def test_statistical_outlier_keeps_nonfinite_points_like_pcl(reg, synth, oracle)
     keep, _ = oracle.statistical_outlier(cloud, 20, 1.0)
     assert keep[10] and keep[20]  # pcl: a non-finite point has distance 0 and passes the threshold
     assert np.array_equal(np.nan_to_num(out, nan=-7.0, posinf=-8.0), np.nan_to_num(cloud[keep], nan=-7.0, posinf=-8.0))
+
+
+def test_kitti_chain_in_hbm_equals_the_host_hand_off(synth, oracle):
+    """BASELINE configs[4], per-scan chain (bench.py --workload kitti_pipeline): raw 120k-point scan -> b2r_prefilter (distance, voxel grid
+    0.25, radius outlier removal) -> b2r_odometry_matching_device on the filtered cloud WHERE IT LIES in HBM, against the reference's hand-off
+    (filtered cloud back on the host, then matching): same filtered clouds (vs the stage-wise oracle), same poses, same keyframe decisions."""
+    import torch
+    pre = dict(use_distance_filter=1, distance_near_thresh=0.1, distance_far_thresh=100.0, downsample_method=1, downsample_resolution=0.25,
+               outlier_removal_method=2, radius_radius=0.5, radius_min_neighbors=2)
+    par = {"registration_method": "FAST_GICP", "reg_transformation_epsilon": 0.1, "reg_max_correspondence_distance": 2.0}
+    raws = [synth.scan("kitti", frame=f, stride=8) for f in range(4)]
+    # host hand-off
+    reg = pkg.select_registration_method(dict(par))
+    odo = pkg.ScanMatchingOdometry(reg, keyframe_delta_trans=5.0, keyframe_delta_angle=2.0, keyframe_delta_time=10000.0)
+    host_out, host_clouds = [], []
+    for k, raw in enumerate(raws):
+        filt, _, m = reg.prefilter(raw, **pre)
+        host_clouds.append(filt.copy())
+        host_out.append(odo.matching(0.1 * k, filt))
+    odo.close()
+    reg.close()
+    # stage-wise oracle of the first scan
+    c = raws[0][oracle.distance_filter(raws[0], 0.1, 100.0)]
+    v = oracle.voxelgrid(c, 0.25)[0]
+    full = np.zeros((v.shape[0], 8), np.float32)
+    full[:, :3], full[:, 3], full[:, 4] = v[:, :3], 1.0, v[:, 3]
+    full = full[oracle.radius_outlier(full, 0.5, 2)]
+    assert np.array_equal(host_clouds[0][:, :3], full[:, :3]) and np.array_equal(host_clouds[0][:, 4], full[:, 4])
+    # device chain
+    reg = pkg.select_registration_method(dict(par))
+    odo = pkg.ScanMatchingOdometry(reg, keyframe_delta_trans=5.0, keyframe_delta_angle=2.0, keyframe_delta_time=10000.0)
+    for k, raw in enumerate(raws):
+        d = torch.from_numpy(raw).cuda()
+        torch.cuda.synchronize()
+        _, dptr, m = reg.prefilter_raw(d.data_ptr(), d.shape[0], d.shape[1] * 4, device=True, **pre)
+        assert m == host_clouds[k].shape[0]
+        st = odo.matching_raw(0.1 * k, dptr, m, raw.shape[1] * 4, device=True)
+        assert np.array_equal(st["odom"], host_out[k]["odom"]) and st["iterations"] == host_out[k]["iterations"]
+        assert st["keyframe_updated"] == host_out[k]["keyframe_updated"] and st["converged"] == host_out[k]["converged"]
+    odo.close()
+    reg.close()
