@@ -160,7 +160,6 @@ extern "C" int b2r_select_registration_method(const char* const* keys, const cha
   return b2r_create(&c, out);
 }
 
-static int alloc_cloud(Cloud&) { return B2R_OK; }
 
 extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   if (!cfg || !out) return fail(B2R_EINVAL, "NULL argument");
@@ -193,8 +192,6 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   if (cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   if (cudaEventCreateWithFlags(&h->upload_ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 3; i++) {
-    int rc = alloc_cloud(h->clouds[i]);
-    if (rc) return bail(rc);
     if (cudaEventCreateWithFlags(&h->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   }
   for (int i = 0; i < 2; i++)
@@ -234,15 +231,9 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st2) cudaStreamSynchronize(h->st2);
   h->aux.raw.release(); h->aux.sorted.release(); h->aux.leaf_lo.release(); h->aux.leaf_hi.release(); h->aux.sup_lo.release(); h->aux.sup_hi.release(); h->aux.pos_of.release(); h->aux.cov.release();
-#ifdef B2R_LEAF_OBB
-  h->aux.leaf_obb.release();
-#endif
   for (int i = 0; i < 3; i++) {
     Cloud& c = h->clouds[i];
     c.raw.release(); c.sorted.release(); c.leaf_lo.release(); c.leaf_hi.release(); c.sup_lo.release(); c.sup_hi.release(); c.pos_of.release(); c.cov.release();
-#ifdef B2R_LEAF_OBB
-    c.leaf_obb.release();
-#endif
     ndt_free_map(c.ndt);
     if (h->staging[i]) cudaFreeHost(h->staging[i]);
     if (h->staging_ev[i]) cudaEventDestroy(h->staging_ev[i]);
@@ -431,10 +422,6 @@ static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   cub::DeviceRadixSort::SortPairs(B.sort_tmp.p, tb, B.keys_a.p, B.keys_b.p, B.vals_a.p, B.vals_b.p, N, 0, 32, st);
   k_bvh_leaves<<<c.nsup, 1024, 0, st>>>(c.raw_view, c.stride_f, N, B.keys_b.p, B.vals_b.p, c.sorted.p, c.pos_of.p, c.leaf_lo.p, c.leaf_hi.p,
                                         c.sup_lo.p, c.sup_hi.p);
-#ifdef B2R_LEAF_OBB
-  B2R_CUDA(c.leaf_obb.reserve((size_t)4 * c.nsup * kSuper + 4));
-  k_leaf_obbs<<<(unsigned)((size_t)c.nsup * kSuper * 32 / 256), 256, 0, st>>>(c.sorted.p, c.nsup * kSuper, c.leaf_obb.p);
-#endif
   TEL_END(&h->tel, KC_GRID, 10, st);
   B2R_CUDA(cudaGetLastError());
   c.bvh_ready = true;

@@ -73,9 +73,6 @@ struct b2r_batch {
 static void free_cloud(Cloud* c) {
   if (!c) return;
   c->raw.release(); c->sorted.release(); c->leaf_lo.release(); c->leaf_hi.release(); c->sup_lo.release(); c->sup_hi.release(); c->pos_of.release(); c->cov.release();
-#ifdef B2R_LEAF_OBB
-  c->leaf_obb.release();
-#endif
   ndt_free_map(c->ndt);
   delete c;
 }
@@ -261,10 +258,6 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
       size_t k0 = 0;
       for (int g = 0; g < 4; g++)
         for (Cloud* c : by_cl[g]) b->h_build[k0++] = build_item(*c);
-      if (getenv("B2R_DEBUG_BUILD"))
-        for (size_t i = 0; i < total; i++)
-          fprintf(stderr, "build item %zu: raw %p sorted %p pos_of %p n %d stride %d (d_build %p)\n", i, (const void*)b->h_build[i].raw, (void*)b->h_build[i].sorted,
-                  (void*)b->h_build[i].pos_of, b->h_build[i].n, b->h_build[i].stride_f, (void*)b->d_build.p);
       B2R_CUDA(cudaMemcpyAsync(b->d_build.p, b->h_build, total * sizeof(BuildItem), cudaMemcpyHostToDevice, st));
       k0 = 0;
       for (int g = 0; g < 4; g++) {

@@ -24,9 +24,6 @@
 #if defined(__CUDACC__) || defined(B2R_WARP_EMU)
 #define B2R_WARP_CODE 1
 #endif
-#ifdef B2R_LEAF_OBB
-#include "leaf_obb.cuh"
-#endif
 
 namespace b2r {
 
@@ -41,9 +38,6 @@ struct Bvh {
   const float4* sup_lo;   // [nsup]
   const float4* sup_hi;
   int nleaf, nsup, n;
-#ifdef B2R_LEAF_OBB
-  const float4* leaf_obb;  // [4*nleaf] oriented boxes (leaf_obb.cuh) or nullptr — experimental builds only
-#endif
 };
 
 // 30-bit 3-D Hilbert index of 10-bit cell coordinates (Skilling's transpose algorithm).  A Hilbert curve has no long jumps,
@@ -109,7 +103,7 @@ struct Nn1 {
   static constexpr int kTileUnroll = 8;  // tiny visitor body: unroll the all-pairs tile loop
   static constexpr bool kTwoPhase = false;
 #ifdef B2R_KNN_PROFILE
-  int n_tile = 0, n_coop = 0, n_try = 0, n_obb = 0;
+  int n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   float bd2;       // +inf = nothing yet
   int bidx;        // kPadIdx = nothing yet
@@ -236,16 +230,6 @@ __global__ void __launch_bounds__(1024) k_bvh_leaves(const float* __restrict__ r
   }
 }
 
-#if defined(B2R_LEAF_OBB) && defined(__CUDACC__)
-// experimental: oriented box of every leaf (one warp per leaf), launched behind k_bvh_leaves
-__global__ void __launch_bounds__(256) k_leaf_obbs(const float4* __restrict__ sorted, int nleaf, float4* obb) {
-  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (leaf >= nleaf) return;  // whole warps only
-  const float4 p = sorted[(size_t)leaf * kLeaf + (threadIdx.x & 31)];
-  const bool valid = idx_bits(p.w) != kPadIdx;
-  leaf_obb_build_warp(valid ? p.x : 0.f, valid ? p.y : 0.f, valid ? p.z : 0.f, valid, obb + 4 * (size_t)leaf);
-}
-#endif
 
 // ------------------------------------------------------------------------------------------------ warp-group traversal
 // Group-level masks are cheap but only as good as the group's box: a group that straddles a jump of the Hilbert curve has a box
@@ -388,19 +372,7 @@ __device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, floa
 #endif
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-#ifdef B2R_LEAF_OBB  // experimental second-stage bound (leaf_obb.cuh), not compiled into the product
-  bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-  if (b.leaf_obb != nullptr && __any_sync(0xffffffffu, pass)) {
-    const float4* r = b.leaf_obb + 4 * (size_t)l;
-    const float lb2 = leaf_obb_bound2(__ldg(r), __ldg(r + 1), __ldg(r + 2), __ldg(r + 3), qx, qy, qz);
-#ifdef B2R_KNN_PROFILE
-    if ((threadIdx.x & 31) == 0) v.n_obb++;
-#endif
-    pass = pass && !(lb2 > v.worst()) && (lb2 < v.limit());
-  }
-#else
   const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
-#endif
   return bvh_visit_leaf<C>(b, l, qx, qy, qz, pass, v);
 }
 

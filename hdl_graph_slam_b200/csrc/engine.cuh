@@ -150,9 +150,6 @@ struct Cloud {
   const float* raw_view = nullptr; // == raw.p, or a caller-owned device pointer (set_*_device)
   // implicit BVH (bvh.cuh)
   DevBuf<float4> sorted, leaf_lo, leaf_hi, sup_lo, sup_hi;
-#ifdef B2R_LEAF_OBB
-  DevBuf<float4> leaf_obb;         // experimental: 4 float4 per leaf (leaf_obb.cuh)
-#endif
   DevBuf<int> pos_of;
   int nsup = 0;
   bool bvh_ready = false;
@@ -167,9 +164,6 @@ struct Cloud {
     Bvh b;
     b.sp = sorted.p; b.leaf_lo = leaf_lo.p; b.leaf_hi = leaf_hi.p; b.sup_lo = sup_lo.p; b.sup_hi = sup_hi.p;
     b.nsup = nsup; b.nleaf = nsup * kSuper; b.n = (int)n;
-#ifdef B2R_LEAF_OBB
-    b.leaf_obb = leaf_obb.p;  // experimental builds; nullptr until the first build
-#endif
     return b;
   }
 };

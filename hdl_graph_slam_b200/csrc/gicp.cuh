@@ -33,7 +33,7 @@ struct KnnList {
   int k, cnt, stride;
   unsigned long long wkey;  // key[k-1] once the list is full, else kKeyInf
 #ifdef B2R_KNN_PROFILE
-  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0, n_obb = 0;
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   __device__ __forceinline__ float worst() const { return nn_key_d2(wkey); }
   __device__ __forceinline__ float limit() const { return INFINITY; }
@@ -150,7 +150,7 @@ struct KnnRegs {
   static constexpr bool kTwoPhase = true;
   unsigned long long key[K];
 #ifdef B2R_KNN_PROFILE
-  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0, n_obb = 0;
+  int n_test = 0, n_ins = 0, n_shift = 0, n_tile = 0, n_coop = 0, n_try = 0;
 #endif
   __device__ __forceinline__ void reset() {
 #pragma unroll

@@ -40,25 +40,9 @@ static HostBvh build(const std::vector<float>& pts, int n) {
   }
   H.b.sp = H.sp.data(); H.b.leaf_lo = H.llo.data(); H.b.leaf_hi = H.lhi.data(); H.b.sup_lo = H.slo.data(); H.b.sup_hi = H.shi.data();
   H.b.nleaf = nleaf; H.b.nsup = nsup; H.b.n = n;
-#ifdef B2R_LEAF_OBB
-  H.b.leaf_obb = nullptr;
-#endif
   return H;
 }
 
-#if defined(B2R_LEAF_OBB) && defined(B2R_WARP_EMU)
-// experimental oriented leaf boxes: the engine's warp-level builder (csrc/leaf_obb.cuh) run on the emulated warp, one leaf at a time
-static std::vector<float4> build_leaf_obbs(HostBvh& H) {
-  std::vector<float4> rec((size_t)4 * H.b.nleaf);
-  for (int leaf = 0; leaf < H.b.nleaf; leaf++)
-    wemu::run_warp(0, [&](int l) {
-      const float4 p = H.sp[(size_t)leaf * kLeaf + l];
-      const bool valid = idx_bits(p.w) != kPadIdx;
-      leaf_obb_build_warp(valid ? p.x : 0.f, valid ? p.y : 0.f, valid ? p.z : 0.f, valid, rec.data() + (size_t)4 * leaf);
-    });
-  return rec;
-}
-#endif
 
 static double urand(unsigned long long& s) {
   s = s * 6364136223846793005ull + 1442695040888963407ull;

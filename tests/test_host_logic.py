@@ -78,20 +78,6 @@ def test_warp_group_traversal_on_lidar_scans(warp_harness, synth, tmp_path, copi
     assert "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
 
 
-def test_experimental_leaf_obb_keeps_results_exact(oracle):
-    """round-2 candidate (csrc/leaf_obb.cuh, compiled out of the product): with the oriented-box second-stage bound switched on the
-    emulated traversal still returns the oracle's answers, and every point lies inside its own leaf's widened box"""
-    exe = os.path.join(ROOT, "build", "warp_harness_obb")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1", "-w", "-ffp-contract=off", "-DB2R_LEAF_OBB",
-                           "-I" + cuda_inc, "-o", exe, os.path.join(ROOT, "tests", "warp_harness.cpp"),
-                           "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath=" + os.path.join(ROOT, "oracle")])
-    for mode in (0, 1):
-        out = subprocess.run([exe, "6000", "16", str(mode), "4"], capture_output=True, text=True)
-        assert out.returncode == 0, out.stdout + out.stderr
-        assert "points outside their own box: 0" in out.stdout and "1nn_mismatch=0" in out.stdout and "knn_mismatch=0" in out.stdout
-
-
 def test_result_message_protocol(tmp_path):
     """the fence-free result publication (engine.cuh): a message is accepted iff flag, checksum and all words are of the same launch,
     for every order in which the stores can land"""

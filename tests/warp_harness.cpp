@@ -195,21 +195,6 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 12; i++) Tf[i] = T0[i];
   }
   HostBvh T = build(tp, n), S = build(sp, n);
-#ifdef B2R_LEAF_OBB  // experimental oriented leaf boxes (csrc/leaf_obb.cuh): 1-NN and the 20-NN self search both run against T
-  static std::vector<float4> obbT = build_leaf_obbs(T);
-  T.b.leaf_obb = obbT.data();
-  {  // every point of a leaf lies inside its widened box
-    long outside = 0;
-    for (int l = 0; l < T.b.nleaf; l++)
-      for (int t = 0; t < kLeaf; t++) {
-        const float4 p = T.sp[(size_t)l * kLeaf + t];
-        if (idx_bits(p.w) == kPadIdx) continue;
-        if (leaf_obb_bound2(obbT[4 * l], obbT[4 * l + 1], obbT[4 * l + 2], obbT[4 * l + 3], p.x, p.y, p.z) != 0.f) outside++;
-      }
-    printf("oriented boxes: %d leaves, points outside their own box: %ld\n", T.b.nleaf, outside);
-    if (outside) return 1;
-  }
-#endif
   long checked = 0, bad1 = 0;
   switch (copies) {
     case 1: bad1 = all_1nn<1>(T, S, n, Tf, groups, tp, n, &checked); break;

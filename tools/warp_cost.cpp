@@ -27,7 +27,7 @@ struct EmuKnn {
   static constexpr bool kTwoPhase = true;
   static constexpr int K = 20;
   unsigned long long key[K];
-  int n_tile = 0, n_coop = 0, n_try = 0, n_ins = 0, n_obb = 0;
+  int n_tile = 0, n_coop = 0, n_try = 0, n_ins = 0;
   void reset() { for (int j = 0; j < K; j++) key[j] = kKeyInf; }
   float worst() const { return nn_key_d2(key[K - 1]); }
   float limit() const { return INFINITY; }
@@ -179,10 +179,6 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 12; i++) if (!f || fscanf(f, "%f", &Tf[i]) != 1) { fprintf(stderr, "bad pose file\n"); return 2; }
   fclose(f);
   HostBvh T = build(tp, n), S = build(sp, n);
-#ifdef B2R_LEAF_OBB
-  static std::vector<float4> obbT = build_leaf_obbs(T), obbS = build_leaf_obbs(S);
-  T.b.leaf_obb = obbT.data(); S.b.leaf_obb = obbS.data();
-#endif
   if (mode == 2) { run_knn(S, stride); return 0; }
   switch (copies) {
     case 1: run_1nn<1>(T, S, Tf, mode, stride); break;
