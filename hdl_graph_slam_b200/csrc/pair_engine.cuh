@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kLinThreads, B2R_SEARCH_MINBLOCKS) k_pair_sear
 // Instead the warp TRANSPOSES through shared memory: every lane stores its value into row (i mod 8) of the warp's tile; after 8
 // values, lane l adds elements q, q + 4, ..., q + 28 (q = l & 3) of row l >> 2 and two shuffle levels join the four partial
 // sums — 2 store + 2 load + 0.5 shuffle wavefronts per value instead of 10.  The order of the additions is fixed.
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr int kRedRow = 36;  // float64 elements per tile row: rows 0..3 of a half-warp start 4 banks apart
 __device__ __forceinline__ void red_flush(int phase, int count, double* tile, double* red, int lane, int warp) {
   __syncwarp();
@@ -379,6 +380,26 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   if (s < p.src.nleaf * kLeaf) pt = p.src.sp[s];
   const bool is_point = idx_bits(pt.w) != kPadIdx;
   if (!is_point) { pt.x = 0.f; pt.y = 0.f; pt.z = 0.f; }  // padding entries carry +inf coordinates: inf * 0 would poison the sums below
+  // The pass is bound by memory latency (ncu r2k: long-scoreboard stalls 16 per issued instruction): a point's loads form the chain
+  // pair record -> cpos -> gathers (target point, target covariance), twice (trial cost, then linearisation).  Read both cpos
+  // entries first and PREFETCH every record the two parts will touch, so the chain is paid once, not per part.
+  const bool do_trial = (mode == PM_FUSED || mode == PM_ERR) && is_point;
+  const bool do_lin = (mode == PM_FIRST || mode == PM_FUSED) && is_point;
+  const bool fit = mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness);
+  const int tp = do_trial ? p.cpos[cur][s] : -1;
+  const int wpos = ((do_lin || fit) && is_point) ? p.cpos[wset][s] : -1;
+  if (tp >= 0) {
+    prefetch_l1(p.tgt.sp + tp);
+    prefetch_l1(p.mahal[cur] + (size_t)s * 6);
+    prefetch_l1(p.mahal[cur] + (size_t)s * 6 + 5);
+  }
+  if (do_lin && wpos >= 0) {
+    prefetch_l1(p.tgt.sp + wpos);
+    prefetch_l1(p.tcov + (size_t)wpos * 6);
+    prefetch_l1(p.tcov + (size_t)wpos * 6 + 5);  // a 48-byte record can straddle two 32-byte sectors
+    prefetch_l1(p.scov + (size_t)s * 6);
+    prefetch_l1(p.scov + (size_t)s * 6 + 5);
+  }
   double T[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) T[i] = p.xe[i];
@@ -388,8 +409,7 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   const double tz = T[8] * ax + T[9] * ay + T[10] * az + T[11];
   // ---- trial cost: FastGICP::compute_error at xe with the previous correspondences / mahalanobis
   double trial = 0.0;
-  if ((mode == PM_FUSED || mode == PM_ERR) && is_point) {
-    const int tp = p.cpos[cur][s];
+  {
     if (tp >= 0) {
       const float4 tb = p.tgt.sp[tp];
       const double* m = p.mahal[cur] + (size_t)s * 6;
@@ -403,15 +423,14 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
   // ---- getFitnessScore sums (fitness round, or the final compute_error round of a registration that wants its fitness):
   // mean of the squared NN distances with d2 <= max_range (information_matrix_calculator.cpp:66-75)
   double fit_sum = 0.0, fit_cnt = 0.0;
-  const bool fit = mode == PM_FIT || (mode == PM_ERR && cfg.want_fitness);
-  if (fit && is_point && p.cpos[wset][s] >= 0) {
+  if (fit && wpos >= 0) {
     const float dd = p.d2[s];
     if ((double)dd <= cfg.fit_max_range) { fit_sum = (double)dd; fit_cnt = 1.0; }
   }
   // ---- FastGICP::linearize over the correspondences just written
   double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, ex = 0, ey = 0, ez = 0;
-  if ((mode == PM_FIRST || mode == PM_FUSED) && is_point) {
-    const int best_pos = p.cpos[wset][s];
+  if (do_lin) {
+    const int best_pos = wpos;
     if (best_pos >= 0) {
       const double* ca = p.scov + (size_t)s * 6;
       const double* cb = p.tcov + (size_t)best_pos * 6;
