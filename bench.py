@@ -221,6 +221,20 @@ def loop_thread_count(orc, groups, guesses, group_first, max_range):
     return best, {str(k): round(v, 2) for k, v in table.items()}
 
 
+def cpu_baseline_loop(groups, guesses, group_first, max_range, sample_groups=3):
+    """cpu_baseline object of the loop-batch line: the oracle on a bounded sample (a thread sweep on group 0, then `sample_groups` groups)"""
+    from oracle import oracle as orc
+    orc.build()
+    cores, table = loop_thread_count(orc, groups, guesses, group_first, max_range)
+    g_list = [(1 + i) % len(groups) for i in range(sample_groups)]
+    tt = oracle_loop_pairs(orc, groups, guesses, group_first, g_list, cores, max_range)
+    n_pairs = sum(group_first[g + 1] - group_first[g] for g in g_list)
+    return {"value": n_pairs / sum(tt), "unit": "registrations/s", "cores": cores, "host_threads_available": host_threads(), "thread_sweep_pairs_per_s": table,
+            "kind": "port",
+            "sample": f"{n_pairs} candidate pairs ({len(g_list)} keyframe groups) of the same workload: per group one kept target (kd-tree + covariances), per candidate "
+                      f"source kd-tree + covariances + align + getFitnessScore, as LoopDetector::matching does; oracle = from-scratch OpenMP restatement of fast_gicp"}
+
+
 def run_reference_loop(args, rank):
     """--impl reference on the loop-closure batch: the CPU oracle on a bounded sample of the same candidate pairs per step"""
     if rank != 0:
@@ -482,7 +496,7 @@ def run_b200(args, wl, rank, world, local_rank):
         try:
             import types
             from hdl_graph_slam_b200 import batch
-            a = types.SimpleNamespace(steps=3, warmup=1, pairs=args.pairs, fitness_max_range=args.fitness_max_range, no_profile=False)
+            a = types.SimpleNamespace(steps=3, warmup=3, pairs=args.pairs, fitness_max_range=args.fitness_max_range, no_profile=False)
             lb = batch.run_loop_batch(a, 0, 1, local_rank)
             line["loop_batch_n1"] = {k: lb[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "e2e", "roofline", "gpu_launches",
                                                          "kernel_ms_in_timed_region")}

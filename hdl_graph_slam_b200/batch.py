@@ -293,6 +293,8 @@ def run_loop_batch(args, rank, world, local_rank, quiet=False):
         "wall_ms_per_step": rv["wall_ms"] / K,
         "per_rank_ms_per_step": [round(x / K, 3) for x in rv["per_rank_ms"]],
     }
+    if world == 1 and getattr(args, "cpu_sample", 0) > 0 and not quiet:
+        line["cpu_baseline"] = bench.cpu_baseline_loop(groups, guesses, group_first, max_range)
     return line
 
 
