@@ -290,13 +290,27 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #endif
   if (__popc(mask) >= kTile) {
     if constexpr (C > 1) {
+      // 1-NN: a visited leaf rarely holds an improvement (the seed usually IS the answer and the leaf only has to be ruled out), so
+      // the first sweep keeps nothing but the smallest distance of the lane's share — 8 flops + 1 FMNMX per candidate instead of
+      // 8 flops + 2 compares + logic + 3 selects — and the exact (d2, index) sweep runs only if some lane saw d2 <= its best.
+      // No lane updating means the copies' states are still identical: the merge is skipped as well.  Same candidates, same tie
+      // rule, same result.
       const int t0 = (lane / Q) * (kLeaf / C);
+      float m = INFINITY;
 #pragma unroll
       for (int t = 0; t < kLeaf / C; t++) {
         const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
-        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+        m = fminf(m, dist2_f32(qx, qy, qz, p.x, p.y, p.z));
       }
-      v.template merge_copies<C>();
+      const bool need = pass && !(m > v.worst());
+      if (__any_sync(FULL, need)) {
+#pragma unroll
+        for (int t = 0; t < kLeaf / C; t++) {
+          const float4 p = __ldg(lp + t0 + t);
+          v.visit_if(need, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+        }
+        v.template merge_copies<C>();
+      }
     } else if constexpr (Visitor::kTwoPhase) {
       // list visitors (an accepted candidate costs ~100 instructions for the whole warp): first mark the candidates that can
       // still beat the lane's current worst (cheap, branch-free), then let every lane walk ITS OWN marks — the number of
@@ -319,10 +333,20 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
         }
       }
     } else {
+      // (minimum-first sweep as above; padding = (+inf, kPadIdx): never the minimum of a leaf that holds a point, rejected by the visitor)
+      float m = INFINITY;
 #pragma unroll Visitor::kTileUnroll
       for (int t = 0; t < kLeaf; t++) {
         const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+        m = fminf(m, dist2_f32(qx, qy, qz, p.x, p.y, p.z));
+      }
+      const bool need = pass && !(m > v.worst());
+      if (__any_sync(FULL, need)) {
+#pragma unroll Visitor::kTileUnroll
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);
+          v.visit_if(need, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);
+        }
       }
     }
     return true;
