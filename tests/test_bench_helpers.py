@@ -49,3 +49,31 @@ def test_reference_arm_line_has_the_contract_keys(oracle, synth):
     assert d["impl"] == "reference" and d["metric"] == "registrations/sec" and d["higher_is_better"] is True and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+
+
+def test_loop_workload_identical_shards_for_weak_scaling():
+    """bench.py --gpus N: every rank's contiguous shard of the loop-closure batch is the same keyframe groups and guesses (per-GPU work
+    exactly fixed), and the N = 1 workload is untouched by the option"""
+    import numpy as np
+    from hdl_graph_slam_b200 import batch
+    g1, q1, f1 = batch.loop_workload(4)
+    g1b, q1b, f1b = batch.loop_workload(4, period=4)
+    assert g1 == g1b and np.array_equal(q1, q1b) and f1 == f1b
+    g, q, f = batch.loop_workload(12, period=4)
+    assert f == [8 * i for i in range(13)]
+    for r in range(3):
+        g0, gend = batch.shard_range(12, 3, r)
+        assert (g0, gend) == (4 * r, 4 * r + 4)
+        assert g[g0:gend] == g1 and np.array_equal(q[f[g0]:f[gend]], q1)
+
+
+def test_auxiliary_workloads_have_no_reference_arm_but_say_so():
+    """the voxel-grid / KITTI-chain workloads carry their CPU figure as cpu_baseline; --impl reference answers with one JSON line"""
+    import json
+    import subprocess
+    import sys
+    for wl in ("voxelgrid", "kitti_pipeline"):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", wl], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and "unavailable" in line
