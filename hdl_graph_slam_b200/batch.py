@@ -299,9 +299,31 @@ def run_loop_batch(args, rank, world, local_rank, quiet=False):
 
 
 def bench_loop_batch(args, rank, world, local_rank):
+    import torch
     import torch.distributed as dist
+    anchor = None
+    if world > 1:
+        # the 1-GPU figure of the SAME workload, taken by rank 0 alone on the same box right before the N-GPU passes (the default
+        # N = 1 bench line is the odometry chain, BASELINE configs[1]; this makes every N > 1 line carry its own scaling anchor)
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=dev)
+        if rank == 0 and not getattr(args, "no_anchor", False):
+            import types
+            a = types.SimpleNamespace(steps=3, warmup=3, pairs=args.pairs, fitness_max_range=args.fitness_max_range, no_profile=True)
+            try:
+                one = run_loop_batch(a, 0, 1, local_rank, quiet=True)
+                anchor = {"value": one["value"], "unit": one["unit"], "ms_per_step": one["ms_per_step"], "steps": 3, "warmup": 3,
+                          "e2e": one["e2e"]["value"], "pairs": one["config"]["pairs_total"],
+                          "note": "same workload on ONE GPU of this box (rank 0 alone, before the N-GPU passes): efficiency = value / (n_gpus x this)"}
+            except Exception as e:  # noqa: BLE001
+                anchor = {"error": repr(e)}
+        dist.barrier()
     line = run_loop_batch(args, rank, world, local_rank)
     if rank == 0:
+        if anchor is not None:
+            line["anchor_n1"] = anchor
         print(json.dumps(line), flush=True)
     if world > 1 and dist.is_initialized():
         dist.destroy_process_group()

@@ -296,11 +296,15 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
       // No lane updating means the copies' states are still identical: the merge is skipped as well.  Same candidates, same tie
       // rule, same result.
       const int t0 = (lane / Q) * (kLeaf / C);
+      // the lane's current best (the seed, usually) is itself a candidate of the leaf it lives in and would tie with itself: it is
+      // left out of the minimum, so `m <= best` means ANOTHER candidate improves on it or ties with it
+      const int ts = ((v.best_pos >> 5) == l ? (v.best_pos & 31) : -1) - t0;
       float m = INFINITY;
 #pragma unroll
       for (int t = 0; t < kLeaf / C; t++) {
         const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
-        m = fminf(m, dist2_f32(qx, qy, qz, p.x, p.y, p.z));
+        const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
+        m = fminf(m, t == ts ? INFINITY : d);
       }
       const bool need = pass && !(m > v.worst());
       if (__any_sync(FULL, need)) {
@@ -334,11 +338,13 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
       }
     } else {
       // (minimum-first sweep as above; padding = (+inf, kPadIdx): never the minimum of a leaf that holds a point, rejected by the visitor)
+      const int ts = (v.best_pos >> 5) == l ? (v.best_pos & 31) : -1;  // the lane's current best, if it lives in this leaf: left out (see above)
       float m = INFINITY;
 #pragma unroll Visitor::kTileUnroll
       for (int t = 0; t < kLeaf; t++) {
         const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-        m = fminf(m, dist2_f32(qx, qy, qz, p.x, p.y, p.z));
+        const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
+        m = fminf(m, t == ts ? INFINITY : d);
       }
       const bool need = pass && !(m > v.worst());
       if (__any_sync(FULL, need)) {

@@ -41,6 +41,17 @@ struct BuildItem {   // one cloud of a batched build
 #ifdef __CUDACC__
 namespace cg = cooperative_groups;
 
+// -DB2R_BUILD_PROFILE (tools/build_variant.sh): thread 0 of CTA 0 prints the cycles between the marks of one build
+#ifdef B2R_BUILD_PROFILE
+#define B2R_MARK(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) b2r_marks[k] = clock64(); } while (0)
+#else
+#define B2R_MARK(k) do { } while (0)
+#endif
+
+#ifdef B2R_BUILD_PROFILE
+__device__ long long b2r_marks[16];
+#endif
+
 // ---- shared-memory layout and the two cluster-wide building blocks (also used by the voxel-grid kernel, voxelgrid.cuh)
 struct ClusterSmem {
   uint2* buf;            // [kBuildCap] (key, original index)
@@ -114,6 +125,9 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
 #pragma unroll 1
   for (int pass = 0; pass < 4; pass++) {
     const int shift = 8 * pass;
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(3);
+#endif
     for (int i = tid; i < 32 * 256 / 2; i += kBuildThreads) reinterpret_cast<unsigned int*>(wh)[i] = 0u;
     __syncthreads();
     // every warp ranks its own contiguous 512 elements in order, 32 at a time: rank inside (warp, digit) = running count of the
@@ -135,6 +149,9 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
       __syncwarp();
     }
     __syncthreads();
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(4);
+#endif
     // per digit: exclusive prefix over the warps (in place) and the CTA's count
     if (tid < 256) {
       int run = 0;
@@ -142,7 +159,13 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
       for (int w = 0; w < 32; w++) { const int c = wh[w * 256 + tid]; wh[w * 256 + tid] = (unsigned short)run; run += c; }
       cta_cnt[tid] = run;
     }
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(5);
+#endif
     cluster.sync();  // every CTA has its elements in registers (its buffer may be overwritten) and its digit counts published
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(6);
+#endif
     if (tid < 256) {
       int tot = 0, before = 0;
       for (int c = 0; c < CL; c++) {
@@ -165,6 +188,9 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
       base[tid] += woff;
     }
     __syncthreads();
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(7);
+#endif
 #pragma unroll
     for (int b = 0; b < kBuildPer; b++) {
       const unsigned int d = (e[b].x >> shift) & 255u;
@@ -172,7 +198,13 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
       uint2* peer = cluster.map_shared_rank(buf, dst / kBuildCap);
       peer[dst % kBuildCap] = e[b];
     }
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(8);
+#endif
     cluster.sync();  // all scatters have landed before anybody reads its buffer again
+#ifdef B2R_BUILD_PROFILE
+    if (pass == 0) B2R_MARK(9);
+#endif
   }
 
 }
@@ -195,8 +227,10 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
   const int padded = ((n + 1023) / 1024) * 1024;
   const int g0 = rank * kBuildCap;  // first global position / element index of this CTA's slice
 
+  B2R_MARK(0);
   int mm[6];
   cluster_bbox<CL>(cluster, S, it.raw, it.stride_f, n, g0, mm);
+  B2R_MARK(1);
   // ---- 30-bit Hilbert keys (k_morton_keys's arithmetic) into this CTA's slice
   {
     const float mnx = ord2f(mm[0]), mny = ord2f(mm[1]), mnz = ord2f(mm[2]);
@@ -221,8 +255,10 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     }
   }
   __syncthreads();
+  B2R_MARK(2);
 
   cluster_radix_sort<CL>(cluster, S, rank);
+  B2R_MARK(10);
 
   // ---- emit this CTA's slice of the structure (k_bvh_leaves's work): one super-node (1024 positions, 32 leaves) per step.
   // The point of step j + 1 is gathered while step j is reduced (the gather is an L2 round trip), and the boxes are reduced with
@@ -278,6 +314,14 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     }
     __syncthreads();
   }
+#ifdef B2R_BUILD_PROFILE
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const long long t = clock64();
+    printf("build n=%d CL=%d cycles: bbox %lld keys %lld | pass0: zero+rank %lld warp-prefix %lld sync %lld digit-scan %lld scatter %lld sync %lld | sort total %lld | emit %lld | all %lld\n",
+           n, CL, b2r_marks[1] - b2r_marks[0], b2r_marks[2] - b2r_marks[1], b2r_marks[4] - b2r_marks[3], b2r_marks[5] - b2r_marks[4], b2r_marks[6] - b2r_marks[5],
+           b2r_marks[7] - b2r_marks[6], b2r_marks[8] - b2r_marks[7], b2r_marks[9] - b2r_marks[8], b2r_marks[10] - b2r_marks[2], t - b2r_marks[10], t - b2r_marks[0]);
+  }
+#endif
 }
 #endif  // __CUDACC__
 
