@@ -290,31 +290,13 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #endif
   if (__popc(mask) >= kTile) {
     if constexpr (C > 1) {
-      // 1-NN: a visited leaf rarely holds an improvement (the seed usually IS the answer and the leaf only has to be ruled out), so
-      // the first sweep keeps nothing but the smallest distance of the lane's share — 8 flops + 1 FMNMX per candidate instead of
-      // 8 flops + 2 compares + logic + 3 selects — and the exact (d2, index) sweep runs only if some lane saw d2 <= its best.
-      // No lane updating means the copies' states are still identical: the merge is skipped as well.  Same candidates, same tie
-      // rule, same result.
       const int t0 = (lane / Q) * (kLeaf / C);
-      // the lane's current best (the seed, usually) is itself a candidate of the leaf it lives in and would tie with itself: it is
-      // left out of the minimum, so `m <= best` means ANOTHER candidate improves on it or ties with it
-      const int ts = ((v.best_pos >> 5) == l ? (v.best_pos & 31) : -1) - t0;
-      float m = INFINITY;
 #pragma unroll
       for (int t = 0; t < kLeaf / C; t++) {
         const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
-        const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-        m = fminf(m, t == ts ? INFINITY : d);
+        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
       }
-      const bool need = pass && !(m > v.worst());
-      if (__any_sync(FULL, need)) {
-#pragma unroll
-        for (int t = 0; t < kLeaf / C; t++) {
-          const float4 p = __ldg(lp + t0 + t);
-          v.visit_if(need, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
-        }
-        v.template merge_copies<C>();
-      }
+      v.template merge_copies<C>();
     } else if constexpr (Visitor::kTwoPhase) {
       // list visitors (an accepted candidate costs ~100 instructions for the whole warp): first mark the candidates that can
       // still beat the lane's current worst (cheap, branch-free), then let every lane walk ITS OWN marks — the number of
@@ -337,22 +319,13 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
         }
       }
     } else {
-      // (minimum-first sweep as above; padding = (+inf, kPadIdx): never the minimum of a leaf that holds a point, rejected by the visitor)
-      const int ts = (v.best_pos >> 5) == l ? (v.best_pos & 31) : -1;  // the lane's current best, if it lives in this leaf: left out (see above)
-      float m = INFINITY;
+      // (a minimum-first variant — one sweep that keeps only the smallest distance, the exact (d2, index) sweep only when some lane can
+      // improve — was measured: neutral on the 4-lane odometry search, 15 % slower on the 1-lane batch search, where some lane of
+      // the 32 nearly always needs the second sweep: profiles/r02_n)
 #pragma unroll Visitor::kTileUnroll
       for (int t = 0; t < kLeaf; t++) {
         const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-        const float d = dist2_f32(qx, qy, qz, p.x, p.y, p.z);
-        m = fminf(m, t == ts ? INFINITY : d);
-      }
-      const bool need = pass && !(m > v.worst());
-      if (__any_sync(FULL, need)) {
-#pragma unroll Visitor::kTileUnroll
-        for (int t = 0; t < kLeaf; t++) {
-          const float4 p = __ldg(lp + t);
-          v.visit_if(need, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);
-        }
+        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
       }
     }
     return true;
