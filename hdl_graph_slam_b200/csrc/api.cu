@@ -347,46 +347,42 @@ static BuildItem build_item(const Cloud& c) {
   it.sup_lo = c.sup_lo.p; it.sup_hi = c.sup_hi.p; it.stride_f = c.stride_f; it.n = (int)c.n;
   return it;
 }
-static int cluster_size_for(size_t n) {  // smallest cluster whose distributed shared memory holds the cloud; 0 = too large
-  for (int cl = 1; cl <= 8; cl *= 2)
-    if (n <= (size_t)cl * kBuildCap) return cl;
-  return 0;
-}
 static bool use_cluster_build() {
   static const bool on = !getenv("B2R_CUB_SORT");
   return on;
 }
-template <int CL, bool SINGLE>
+template <int CL, int PER, bool SINGLE>
 static cudaError_t launch_cluster_build_t(const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL, PER, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BuildGeom<PER>::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(n_clouds * CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = kBuildSmem; lc.stream = st;
+  lc.gridDim = dim3(n_clouds * CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = BuildGeom<PER>::kSmem; lc.stream = st;
   cudaLaunchAttribute la[1];
   la[0].id = cudaLaunchAttributeClusterDimension;
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   lc.attrs = la; lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, k_bvh_build_cluster<CL, SINGLE>, d_items, single);
+  return cudaLaunchKernelEx(&lc, k_bvh_build_cluster<CL, PER, SINGLE>, d_items, single);
 }
-static cudaError_t launch_cluster_build(int cl, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
-  if (d_items) {
-    switch (cl) {
-      case 1: return launch_cluster_build_t<1, false>(d_items, single, n_clouds, st);
-      case 2: return launch_cluster_build_t<2, false>(d_items, single, n_clouds, st);
-      case 4: return launch_cluster_build_t<4, false>(d_items, single, n_clouds, st);
-      default: return launch_cluster_build_t<8, false>(d_items, single, n_clouds, st);
-    }
+template <bool SINGLE>
+static cudaError_t launch_cluster_build_s(int shape_index, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
+  switch (shape_index) {  // build_shape_index(): (cluster size, pairs per thread)
+    case 0: return launch_cluster_build_t<1, 1, SINGLE>(d_items, single, n_clouds, st);
+    case 1: return launch_cluster_build_t<2, 1, SINGLE>(d_items, single, n_clouds, st);
+    case 2: return launch_cluster_build_t<4, 1, SINGLE>(d_items, single, n_clouds, st);
+    case 3: return launch_cluster_build_t<8, 1, SINGLE>(d_items, single, n_clouds, st);
+    case 4: return launch_cluster_build_t<8, 2, SINGLE>(d_items, single, n_clouds, st);
+    case 5: return launch_cluster_build_t<8, 4, SINGLE>(d_items, single, n_clouds, st);
+    case 6: return launch_cluster_build_t<8, 8, SINGLE>(d_items, single, n_clouds, st);
+    default: return launch_cluster_build_t<8, 16, SINGLE>(d_items, single, n_clouds, st);
   }
-  switch (cl) {
-    case 1: return launch_cluster_build_t<1, true>(d_items, single, n_clouds, st);
-    case 2: return launch_cluster_build_t<2, true>(d_items, single, n_clouds, st);
-    case 4: return launch_cluster_build_t<4, true>(d_items, single, n_clouds, st);
-    default: return launch_cluster_build_t<8, true>(d_items, single, n_clouds, st);
-  }
+}
+// one launch builds `n_clouds` clouds of the same shape: the descriptor list d_items, or (d_items == nullptr) the one cloud `single`
+static cudaError_t launch_cluster_build(int shape_index, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
+  return d_items ? launch_cluster_build_s<false>(shape_index, d_items, single, n_clouds, st) : launch_cluster_build_s<true>(shape_index, d_items, single, n_clouds, st);
 }
 
 // builds the implicit BVH of a cloud on stream `st` with build scratch `B` (one scratch per stream)
@@ -397,10 +393,10 @@ static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   int arc = bvh_alloc(c);
   if (arc) return arc;
   if (n == 0) { c.bvh_ready = true; return B2R_OK; }
-  const int cl = cluster_size_for(n);
-  if (cl && use_cluster_build()) {  // the whole build as ONE kernel on a cluster of `cl` CTAs (the cloud lives in distributed shared memory)
+  const BuildShape shape = build_shape_for(n);
+  if (shape.cl && use_cluster_build()) {  // the whole build as ONE kernel on a cluster (the cloud lives in distributed shared memory)
     TEL_BEGIN(&h->tel, st);
-    B2R_CUDA(launch_cluster_build(cl, nullptr, build_item(c), 1, st));
+    B2R_CUDA(launch_cluster_build(build_shape_index(shape), nullptr, build_item(c), 1, st));
     TEL_END(&h->tel, KC_GRID, 1, st);
     c.bvh_ready = true;
     return B2R_OK;

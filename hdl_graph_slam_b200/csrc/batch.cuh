@@ -237,16 +237,17 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
     }
   if (todo.empty()) return B2R_OK;
   {  // ---- structures
-    std::vector<Cloud*> by_cl[4];  // cluster sizes 1, 2, 4, 8
+    std::vector<Cloud*> by_cl[kBuildShapes];  // one launch per (cluster size, pairs per thread) shape
+    size_t total = 0;
     for (Cloud* c : todo) {
       if (c->bvh_ready) continue;
-      const int cl = cluster_size_for(c->n);
-      if (!cl || !use_cluster_build()) { int rc = build_bvh(h, *c, h->bc[0], st); if (rc) return rc; continue; }
+      const BuildShape shape = build_shape_for(c->n);
+      if (!shape.cl || !use_cluster_build()) { int rc = build_bvh(h, *c, h->bc[0], st); if (rc) return rc; continue; }
       int rc = bvh_alloc(*c);
       if (rc) return rc;
-      by_cl[cl == 1 ? 0 : cl == 2 ? 1 : cl == 4 ? 2 : 3].push_back(c);
+      by_cl[build_shape_index(shape)].push_back(c);
+      total++;
     }
-    size_t total = by_cl[0].size() + by_cl[1].size() + by_cl[2].size() + by_cl[3].size();
     if (total) {
       B2R_CUDA(b->d_build.reserve(total));
       if (b->h_build_cap < total) {
@@ -256,14 +257,14 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
         b->h_build_cap = total + 64;
       }
       size_t k0 = 0;
-      for (int g = 0; g < 4; g++)
+      for (int g = 0; g < kBuildShapes; g++)
         for (Cloud* c : by_cl[g]) b->h_build[k0++] = build_item(*c);
       B2R_CUDA(cudaMemcpyAsync(b->d_build.p, b->h_build, total * sizeof(BuildItem), cudaMemcpyHostToDevice, st));
       k0 = 0;
-      for (int g = 0; g < 4; g++) {
+      for (int g = 0; g < kBuildShapes; g++) {
         if (by_cl[g].empty()) continue;
         TEL_BEGIN(&h->tel, st);
-        B2R_CUDA(launch_cluster_build(1 << g, b->d_build.p + k0, BuildItem(), (unsigned)by_cl[g].size(), st));
+        B2R_CUDA(launch_cluster_build(g, b->d_build.p + k0, BuildItem(), (unsigned)by_cl[g].size(), st));
         TEL_END(&h->tel, KC_GRID, 1, st);
         for (Cloud* c : by_cl[g]) c->bvh_ready = true;
         k0 += by_cl[g].size();

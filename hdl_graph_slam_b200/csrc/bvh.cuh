@@ -43,30 +43,29 @@ struct Bvh {
 // 30-bit 3-D Hilbert index of 10-bit cell coordinates (Skilling's transpose algorithm).  A Hilbert curve has no long jumps,
 // so 32 consecutive points stay compact (CPU probe on a VLP-16 frame: max leaf visits per group 74 vs 386 with Morton).
 // The key only ORDERS points; exactness never depends on it.
+B2R_HD unsigned int hilbert_spread10(unsigned int v) {  // bit i of v -> bit 3 i
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
 B2R_HD unsigned int hilbert30(unsigned int x, unsigned int y, unsigned int z) {
-  unsigned int X[3] = {x & 0x3ffu, y & 0x3ffu, z & 0x3ffu};
-  const unsigned int M = 1u << 9;
-  for (unsigned int Q = M; Q > 1; Q >>= 1) {
-    const unsigned int P = Q - 1;
+  unsigned int X0 = x & 0x3ffu, X1 = y & 0x3ffu, X2 = z & 0x3ffu;
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      if (X[i] & Q) X[0] ^= P;
-      else { const unsigned int t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
-    }
+  for (unsigned int Q = 1u << 9; Q > 1; Q >>= 1) {  // inverse undo of the excess work (Skilling): per level, per axis, invert or exchange the low bits
+    const unsigned int P = Q - 1;
+    if (X0 & Q) X0 ^= P;
+    if (X1 & Q) X0 ^= P; else { const unsigned int t = (X0 ^ X1) & P; X0 ^= t; X1 ^= t; }
+    if (X2 & Q) X0 ^= P; else { const unsigned int t = (X0 ^ X2) & P; X0 ^= t; X2 ^= t; }
   }
-  X[1] ^= X[0];
-  X[2] ^= X[1];
-  unsigned int t = 0;
-  for (unsigned int Q = M; Q > 1; Q >>= 1)
-    if (X[2] & Q) t ^= Q - 1;
-  X[0] ^= t; X[1] ^= t; X[2] ^= t;
-  unsigned int h = 0;
-  for (int bit = 9; bit >= 0; bit--) {
-    h = (h << 1) | ((X[0] >> bit) & 1u);
-    h = (h << 1) | ((X[1] >> bit) & 1u);
-    h = (h << 1) | ((X[2] >> bit) & 1u);
-  }
-  return h;
+  X1 ^= X0;  // Gray encode
+  X2 ^= X1;
+  unsigned int t = X2 >> 1;  // bit j of t = xor of the bits of X2 above j: a prefix xor from the top
+  t ^= t >> 1; t ^= t >> 2; t ^= t >> 4; t ^= t >> 8;
+  X0 ^= t; X1 ^= t; X2 ^= t;
+  return (hilbert_spread10(X0) << 2) | (hilbert_spread10(X1) << 1) | hilbert_spread10(X2);  // x bit above y bit above z bit, level by level
 }
 
 // lower bound of dist2_f32(q, p) for every p inside [lo, hi] (same association as dist2_f32)

@@ -6,11 +6,11 @@
 // launches (bbox, fill, keys, six cub::DeviceRadixSort kernels, leaves).
 //
 // B200-first design: a cloud of up to 131 072 points lives ENTIRELY in the distributed shared memory of one cluster
-// (CL = 1/2/4/8 CTAs x 16 384 (key, index) pairs = 128 KB each).  The cluster computes the bounding box, the 30-bit Hilbert
+// (CL = 1/2/4/8 CTAs x PER = 1..16 (key, index) pairs per thread, at most 128 KB per CTA).  The cluster computes the bounding box, the 30-bit Hilbert
 // keys, runs a stable 4-pass LSD radix sort whose scatter writes straight into the PEER CTAs' shared memory (DSMEM stores,
 // cluster barriers between passes — no global-memory round trip, no histogram/offset kernels), and finally each CTA emits its
-// contiguous 16 384-position slice of the structure: sorted float4 points, pos_of, 512 leaf boxes, 16 super-node boxes.
-// blockIdx.x / CL selects the cloud: a whole set of keyframe clouds is built by one launch (37 clouds at a time at CL = 4).
+// contiguous slice of the structure: sorted float4 points, pos_of, leaf boxes, super-node boxes.
+// blockIdx.x / CL selects the cloud: a whole set of keyframe clouds is built by one launch.
 //
 // Order contract (unchanged): ascending (Hilbert key, original index); non-finite points dropped (pos_of = -1); padding
 // entries (+inf, kPadIdx) up to a multiple of 1024.
@@ -21,10 +21,34 @@
 
 namespace b2r {
 
-constexpr int kBuildCap = 16384;      // (key, index) pairs held by one CTA
 constexpr int kBuildThreads = 1024;
-constexpr int kBuildPer = kBuildCap / kBuildThreads;  // 16 elements per thread
-constexpr size_t kBuildSmem = (size_t)kBuildCap * 8 + 32 * 256 * 2 + 256 * 4 * 2 + 64 * 4;
+constexpr int kBuildMaxPer = 16;                        // (key, index) pairs per thread at most: 16 384 per CTA, 128 KB of shared memory
+constexpr int kBuildMaxPoints = 8 * kBuildMaxPer * kBuildThreads;  // 131 072: the largest cloud a cluster of 8 holds
+// PER pairs per thread => a CTA holds PER * 1024 pairs.  The kernels are latency bound (one cluster per cloud), so a cloud is spread over
+// as MANY CTAs as the portable cluster size allows (8) with as FEW pairs per thread as that needs: 65 536 points = 8 CTAs x 8 per
+// thread, 24 000 points = 8 x 4 (measured phase cycles, profiles/r02_o_build_phase_cycles.txt: every phase except the barriers scales
+// with the pairs per thread).
+template <int PER>
+struct BuildGeom {
+  static_assert(PER == 1 || PER == 2 || PER == 4 || PER == 8 || PER == 16, "pairs per thread: a power of two up to 16");
+  static constexpr int kCap = PER * kBuildThreads;                                                     // pairs held by one CTA
+  static constexpr int kShift = PER == 1 ? 10 : PER == 2 ? 11 : PER == 4 ? 12 : PER == 8 ? 13 : 14;     // log2(kCap)
+  static constexpr size_t kSmem = (size_t)kCap * 8 + 32 * 256 * 2 + 256 * 4 * 2 + 64 * 4;
+};
+// the (cluster size, pairs per thread) of a cloud of n points: 0 = too large for a cluster
+struct BuildShape { int cl, per; };
+inline BuildShape build_shape_for(size_t n) {
+  if (n > (size_t)kBuildMaxPoints) return {0, 0};
+  const int slices = (int)((n + kBuildThreads - 1) / kBuildThreads) > 0 ? (int)((n + kBuildThreads - 1) / kBuildThreads) : 1;
+  int per = 1;
+  while (per * 8 < slices) per *= 2;
+  int cl = 1;
+  while (cl * per < slices) cl *= 2;
+  return {cl, per};
+}
+// index of a shape in the instantiation table: (1,1) (2,1) (4,1) (8,1) (8,2) (8,4) (8,8) (8,16)
+inline int build_shape_index(BuildShape s) { return s.per == 1 ? (s.cl == 1 ? 0 : s.cl == 2 ? 1 : s.cl == 4 ? 2 : 3) : (s.per == 2 ? 4 : s.per == 4 ? 5 : s.per == 8 ? 6 : 7); }
+constexpr int kBuildShapes = 8;
 
 struct BuildItem {   // one cloud of a batched build
   const float* raw;
@@ -54,24 +78,26 @@ __device__ long long b2r_marks[16];
 
 // ---- shared-memory layout and the two cluster-wide building blocks (also used by the voxel-grid kernel, voxelgrid.cuh)
 struct ClusterSmem {
-  uint2* buf;            // [kBuildCap] (key, original index)
+  uint2* buf;            // [PER * 1024] (key, original index)
   unsigned short* wh;    // [32 warps][256 digits]
   int* cta_cnt;          // [256] digit counts of this CTA
   int* base;             // [256] first destination of (digit, this CTA)
   int* s_mm;             // [6] bbox as ordered ints, [8..63] scratch
 };
+template <int PER>
 __device__ __forceinline__ ClusterSmem cluster_smem(unsigned char* smem_raw) {
+  constexpr size_t cap = BuildGeom<PER>::kCap;
   ClusterSmem S;
   S.buf = reinterpret_cast<uint2*>(smem_raw);
-  S.wh = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kBuildCap * 8);
-  S.cta_cnt = reinterpret_cast<int*>(smem_raw + (size_t)kBuildCap * 8 + 32 * 256 * 2);
+  S.wh = reinterpret_cast<unsigned short*>(smem_raw + cap * 8);
+  S.cta_cnt = reinterpret_cast<int*>(smem_raw + cap * 8 + 32 * 256 * 2);
   S.base = S.cta_cnt + 256;
   S.s_mm = S.base + 256;
   return S;
 }
 
 // bounding box of the finite points of a cloud spread over the cluster (element i of CTA `rank` = point g0 + i), as ordered ints
-template <int CL>
+template <int CL, int PER>
 __device__ __forceinline__ void cluster_bbox(cg::cluster_group& cluster, const ClusterSmem& S, const float* __restrict__ raw, int stride_f, int n, int g0, int* mm) {
   int* s_mm = S.s_mm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,9 +105,9 @@ __device__ __forceinline__ void cluster_bbox(cg::cluster_group& cluster, const C
   __syncthreads();
   {
     int mn0 = 0x7fffffff, mn1 = 0x7fffffff, mn2 = 0x7fffffff, mx0 = (int)0x80000000, mx1 = (int)0x80000000, mx2 = (int)0x80000000;
-#pragma unroll 4
-    for (int b = 0; b < kBuildPer; b++) {
-      const int i = g0 + warp * (32 * kBuildPer) + b * 32 + lane;
+#pragma unroll
+    for (int b = 0; b < PER; b++) {
+      const int i = g0 + warp * (32 * PER) + b * 32 + lane;
       if (i < n) {
         const float* p = raw + (size_t)i * stride_f;
         const float x = p[0], y = p[1], z = p[2];
@@ -111,9 +137,9 @@ __device__ __forceinline__ void cluster_bbox(cg::cluster_group& cluster, const C
   }
 }
 
-// stable LSD radix sort of the (key, value) pairs held in the cluster's distributed shared memory (CL x kBuildCap pairs, every CTA
+// stable LSD radix sort of the (key, value) pairs held in the cluster's distributed shared memory (CL x PER x 1024 pairs, every CTA
 // full), ascending by the 32-bit key: 4 passes of 8 bits; the scatter writes straight into the peer CTAs' shared memory
-template <int CL>
+template <int CL, int PER>
 __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, const ClusterSmem& S, int rank) {
   uint2* buf = S.buf;
   unsigned short* wh = S.wh;
@@ -130,23 +156,33 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
 #endif
     for (int i = tid; i < 32 * 256 / 2; i += kBuildThreads) reinterpret_cast<unsigned int*>(wh)[i] = 0u;
     __syncthreads();
-    // every warp ranks its own contiguous 512 elements in order, 32 at a time: rank inside (warp, digit) = running count of the
-    // digit in this warp + number of equal digits in lower lanes (stable)
-    uint2 e[kBuildPer];
-    unsigned short off[kBuildPer];
+    // every warp ranks its own contiguous 32 * PER elements in order, 32 at a time: rank inside (warp, digit) = running count of the
+    // digit in this warp + number of equal digits in lower lanes (stable).  The MATCH.ANY of a step does not depend on the running
+    // counts, so the masks of up to 8 steps are taken first (independent, pipelined) and only the count updates — a shared-memory
+    // read-modify-write by the digit's leader lane — run one after the other (measured: the serial match + update chain was 13 us
+    // of a 31 us pass at 16 pairs per thread).
+    uint2 e[PER];
+    unsigned short off[PER];
     unsigned short* mywh = wh + warp * 256;
+    constexpr int kHalf = PER < 8 ? PER : 8;
 #pragma unroll
-    for (int b = 0; b < kBuildPer; b++) {
-      e[b] = buf[warp * (32 * kBuildPer) + b * 32 + lane];
-      const unsigned int d = (e[b].x >> shift) & 255u;
-      // (a ballot-per-bit construction of the same mask was measured 5 % slower than MATCH.ANY: profiles/r02_m)
-      const unsigned int peers = __match_any_sync(0xffffffffu, d);
-      const int leader = __ffs(peers) - 1;
-      unsigned int bs = 0;
-      if (lane == leader) { bs = mywh[d]; mywh[d] = (unsigned short)(bs + __popc(peers)); }
-      bs = __shfl_sync(0xffffffffu, bs, leader);
-      off[b] = (unsigned short)(bs + __popc(peers & lt));
-      __syncwarp();
+    for (int b0 = 0; b0 < PER; b0 += kHalf) {
+      unsigned int peers[kHalf];
+#pragma unroll
+      for (int k = 0; k < kHalf; k++) {
+        e[b0 + k] = buf[warp * (32 * PER) + (b0 + k) * 32 + lane];
+        peers[k] = __match_any_sync(0xffffffffu, (e[b0 + k].x >> shift) & 255u);
+      }
+#pragma unroll
+      for (int k = 0; k < kHalf; k++) {
+        const unsigned int d = (e[b0 + k].x >> shift) & 255u;
+        const int leader = __ffs(peers[k]) - 1;
+        unsigned int bs = 0;
+        if (lane == leader) { bs = mywh[d]; mywh[d] = (unsigned short)(bs + __popc(peers[k])); }
+        bs = __shfl_sync(0xffffffffu, bs, leader);
+        off[b0 + k] = (unsigned short)(bs + __popc(peers[k] & lt));
+        __syncwarp();
+      }
     }
     __syncthreads();
 #ifdef B2R_BUILD_PROFILE
@@ -192,11 +228,11 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
     if (pass == 0) B2R_MARK(7);
 #endif
 #pragma unroll
-    for (int b = 0; b < kBuildPer; b++) {
+    for (int b = 0; b < PER; b++) {
       const unsigned int d = (e[b].x >> shift) & 255u;
       const int dst = base[d] + (int)mywh[d] + (int)off[b];
-      uint2* peer = cluster.map_shared_rank(buf, dst / kBuildCap);
-      peer[dst % kBuildCap] = e[b];
+      uint2* peer = cluster.map_shared_rank(buf, dst >> BuildGeom<PER>::kShift);
+      peer[dst & (BuildGeom<PER>::kCap - 1)] = e[b];
     }
 #ifdef B2R_BUILD_PROFILE
     if (pass == 0) B2R_MARK(8);
@@ -211,10 +247,11 @@ __device__ __forceinline__ void cluster_radix_sort(cg::cluster_group& cluster, c
 
 // SINGLE: the one cloud travels as a kernel parameter (no descriptor upload); else blockIdx.x / CL indexes the descriptor list.
 // (Two instantiations rather than a run-time select between a parameter-space struct and a global one.)
-template <int CL, bool SINGLE>
+template <int CL, int PER, bool SINGLE>
 __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const BuildItem* __restrict__ items, const __grid_constant__ BuildItem single) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ClusterSmem S = cluster_smem(smem_raw);
+  constexpr int kCap = BuildGeom<PER>::kCap;
+  const ClusterSmem S = cluster_smem<PER>(smem_raw);
   uint2* buf = S.buf;
   unsigned short* wh = S.wh;
   cg::cluster_group cluster = cg::this_cluster();
@@ -225,11 +262,11 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
   const int n = it.n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int padded = ((n + 1023) / 1024) * 1024;
-  const int g0 = rank * kBuildCap;  // first global position / element index of this CTA's slice
+  const int g0 = rank * kCap;  // first global position / element index of this CTA's slice
 
   B2R_MARK(0);
   int mm[6];
-  cluster_bbox<CL>(cluster, S, it.raw, it.stride_f, n, g0, mm);
+  cluster_bbox<CL, PER>(cluster, S, it.raw, it.stride_f, n, g0, mm);
   B2R_MARK(1);
   // ---- 30-bit Hilbert keys (k_morton_keys's arithmetic) into this CTA's slice
   {
@@ -237,8 +274,8 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
     const float ext = fmaxf(fmaxf(ord2f(mm[3]) - mnx, ord2f(mm[4]) - mny), fmaxf(ord2f(mm[5]) - mnz, 1.0e-6f));
     const float sc = 1023.0f / ext;
 #pragma unroll 4
-    for (int b = 0; b < kBuildPer; b++) {
-      const int e = warp * (32 * kBuildPer) + b * 32 + lane;
+    for (int b = 0; b < PER; b++) {
+      const int e = warp * (32 * PER) + b * 32 + lane;
       const int i = g0 + e;
       unsigned int key = 0xffffffffu;  // non-finite points and the padding sort last
       if (i < n) {
@@ -257,7 +294,7 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
   __syncthreads();
   B2R_MARK(2);
 
-  cluster_radix_sort<CL>(cluster, S, rank);
+  cluster_radix_sort<CL, PER>(cluster, S, rank);
   B2R_MARK(10);
 
   // ---- emit this CTA's slice of the structure (k_bvh_leaves's work): one super-node (1024 positions, 32 leaves) per step.
@@ -265,7 +302,7 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
   // REDUX on order-preserving ints: 6 instructions per warp instead of 30 shuffle + min/max pairs (min / max are exact either way).
   float* s_lo = reinterpret_cast<float*>(wh);        // [32][3] leaf boxes of the current super-node (the histogram area is free now)
   float* s_hi = s_lo + 96;
-  const int nstep = min(kBuildCap / 1024, max(0, (padded - g0 + 1023) / 1024));
+  const int nstep = min(kCap / 1024, max(0, (padded - g0 + 1023) / 1024));
   uint2 kv = nstep > 0 ? buf[tid] : make_uint2(0xffffffffu, 0xffffffffu);
   float nx = INFINITY, ny = INFINITY, nz = INFINITY;
   if (kv.x != 0xffffffffu) { const float* p = it.raw + (size_t)kv.y * it.stride_f; nx = p[0]; ny = p[1]; nz = p[2]; }
@@ -317,8 +354,8 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_bvh_build_cluster(const Bu
 #ifdef B2R_BUILD_PROFILE
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const long long t = clock64();
-    printf("build n=%d CL=%d cycles: bbox %lld keys %lld | pass0: zero+rank %lld warp-prefix %lld sync %lld digit-scan %lld scatter %lld sync %lld | sort total %lld | emit %lld | all %lld\n",
-           n, CL, b2r_marks[1] - b2r_marks[0], b2r_marks[2] - b2r_marks[1], b2r_marks[4] - b2r_marks[3], b2r_marks[5] - b2r_marks[4], b2r_marks[6] - b2r_marks[5],
+    printf("build n=%d CL=%d PER=%d cycles: bbox %lld keys %lld | pass0: zero+rank %lld warp-prefix %lld sync %lld digit-scan %lld scatter %lld sync %lld | sort total %lld | emit %lld | all %lld\n",
+           n, CL, PER, b2r_marks[1] - b2r_marks[0], b2r_marks[2] - b2r_marks[1], b2r_marks[4] - b2r_marks[3], b2r_marks[5] - b2r_marks[4], b2r_marks[6] - b2r_marks[5],
            b2r_marks[7] - b2r_marks[6], b2r_marks[8] - b2r_marks[7], b2r_marks[9] - b2r_marks[8], b2r_marks[10] - b2r_marks[2], t - b2r_marks[10], t - b2r_marks[0]);
   }
 #endif

@@ -147,18 +147,20 @@ struct VgArgs {
   volatile int* h_total;  // host-mapped twin of `total` (or null): the count reaches the host without a copy
 };
 
-template <int CL>
+template <int CL, int PER>
 __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __grid_constant__ VgArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const ClusterSmem S = cluster_smem(smem_raw);
+  constexpr int kCap = BuildGeom<PER>::kCap;
+  constexpr int kShift = BuildGeom<PER>::kShift;
+  const ClusterSmem S = cluster_smem<PER>(smem_raw);
   uint2* buf = S.buf;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = A.n;
-  const int g0 = rank * kBuildCap;
+  const int g0 = rank * kCap;
   int mm[6];
-  cluster_bbox<CL>(cluster, S, A.in, A.stride_f, n, g0, mm);
+  cluster_bbox<CL, PER>(cluster, S, A.in, A.stride_f, n, g0, mm);
   // ---- geometry (k_vg_params), computed redundantly by every thread from the cluster-wide bounding box
   const float inv_leaf = 1.0f / A.leaf;
   int min_b[3] = {0, 0, 0}, div_b[3] = {1, 1, 1};
@@ -193,8 +195,8 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __
   const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
   // ---- keys (k_vg_keys): int32 voxel index; non-finite points 0x7fffffff, padding 0xffffffff (both sort behind every voxel)
 #pragma unroll 4
-  for (int b = 0; b < kBuildPer; b++) {
-    const int e = warp * (32 * kBuildPer) + b * 32 + lane;
+  for (int b = 0; b < PER; b++) {
+    const int e = warp * (32 * PER) + b * 32 + lane;
     const int i = g0 + e;
     unsigned int key = 0xffffffffu;
     if (i < n) {
@@ -211,18 +213,18 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __
     buf[e] = make_uint2(key, (unsigned int)i);
   }
   __syncthreads();
-  cluster_radix_sort<CL>(cluster, S, rank);  // ends with a cluster barrier: every slice is final and visible
-  // ---- heads: thread t owns the 16 consecutive positions t*16 .. t*16+15 of this CTA's slice
-  const int e0 = tid * kBuildPer;
+  cluster_radix_sort<CL, PER>(cluster, S, rank);  // ends with a cluster barrier: every slice is final and visible
+  // ---- heads: thread t owns the PER consecutive positions t*PER .. t*PER+PER-1 of this CTA's slice
+  const int e0 = tid * PER;
   unsigned int prev = 0xffffffffu;  // key before position e0 (none for the very first position of the cloud)
   if (e0 > 0) prev = buf[e0 - 1].x;
-  else if (rank > 0) prev = cluster.map_shared_rank(buf, rank - 1)[kBuildCap - 1].x;
+  else if (rank > 0) prev = cluster.map_shared_rank(buf, rank - 1)[kCap - 1].x;
   unsigned int headmask = 0;
   {
     unsigned int pk = prev;
     const bool first_of_cloud = (rank == 0 && e0 == 0);
 #pragma unroll
-    for (int j = 0; j < kBuildPer; j++) {
+    for (int j = 0; j < PER; j++) {
       const unsigned int k = buf[e0 + j].x;
       if (k < 0x7fffffffu && ((first_of_cloud && j == 0) || k != pk)) headmask |= 1u << j;
       pk = k;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __
   // ---- centroids (k_vg_centroid): one thread per voxel, sequential float32 sums in ascending point index; a voxel's run may
   // continue into the next CTAs' slices (read through distributed shared memory)
   const bool has_i = A.stride_f >= 5;
-  const int cap_all = CL * kBuildCap;
+  const int cap_all = CL * kCap;
   while (headmask) {
     const int j = __ffs(headmask) - 1;
     headmask &= headmask - 1;
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
     int g = g0 + e0 + j, cnt = 0;
     for (;;) {
-      const uint2 kv = (g >> 14) == rank ? buf[g & (kBuildCap - 1)] : cluster.map_shared_rank(buf, g >> 14)[g & (kBuildCap - 1)];
+      const uint2 kv = (g >> kShift) == rank ? buf[g & (kCap - 1)] : cluster.map_shared_rank(buf, g >> kShift)[g & (kCap - 1)];
       if (kv.x != k) break;
       const float* p = A.in + (size_t)kv.y * A.stride_f;
       sx = fadd(sx, p[0]); sy = fadd(sy, p[1]); sz = fadd(sz, p[2]);
@@ -287,28 +289,32 @@ __global__ void __launch_bounds__(kBuildThreads, 1) k_voxelgrid_cluster(const __
   cluster.sync();  // no CTA may retire while a peer still walks a run that continues in its slice
 }
 
-template <int CL>
+template <int CL, int PER>
 static cudaError_t launch_voxelgrid_cluster_t(const VgArgs& A, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_voxelgrid_cluster<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBuildSmem);
+    cudaError_t e = cudaFuncSetAttribute(k_voxelgrid_cluster<CL, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BuildGeom<PER>::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t lc = {};
-  lc.gridDim = dim3(CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = kBuildSmem; lc.stream = st;
+  lc.gridDim = dim3(CL); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = BuildGeom<PER>::kSmem; lc.stream = st;
   cudaLaunchAttribute la[1];
   la[0].id = cudaLaunchAttributeClusterDimension;
   la[0].val.clusterDim.x = CL; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
   lc.attrs = la; lc.numAttrs = 1;
-  return cudaLaunchKernelEx(&lc, k_voxelgrid_cluster<CL>, A);
+  return cudaLaunchKernelEx(&lc, k_voxelgrid_cluster<CL, PER>, A);
 }
-static cudaError_t launch_voxelgrid_cluster(int cl, const VgArgs& A, cudaStream_t st) {
-  switch (cl) {
-    case 1: return launch_voxelgrid_cluster_t<1>(A, st);
-    case 2: return launch_voxelgrid_cluster_t<2>(A, st);
-    case 4: return launch_voxelgrid_cluster_t<4>(A, st);
-    default: return launch_voxelgrid_cluster_t<8>(A, st);
+static cudaError_t launch_voxelgrid_cluster(int shape_index, const VgArgs& A, cudaStream_t st) {
+  switch (shape_index) {  // build_shape_index(): (cluster size, pairs per thread)
+    case 0: return launch_voxelgrid_cluster_t<1, 1>(A, st);
+    case 1: return launch_voxelgrid_cluster_t<2, 1>(A, st);
+    case 2: return launch_voxelgrid_cluster_t<4, 1>(A, st);
+    case 3: return launch_voxelgrid_cluster_t<8, 1>(A, st);
+    case 4: return launch_voxelgrid_cluster_t<8, 2>(A, st);
+    case 5: return launch_voxelgrid_cluster_t<8, 4>(A, st);
+    case 6: return launch_voxelgrid_cluster_t<8, 8>(A, st);
+    default: return launch_voxelgrid_cluster_t<8, 16>(A, st);
   }
 }
 
@@ -326,16 +332,15 @@ inline int voxelgrid_device(VoxelWork& W, cudaStream_t st, const float* d_in, si
   }
   B2R_CUDA(W.out.reserve(n * sf + 8));
   B2R_CUDA(W.okeys.reserve(n + 1)); B2R_CUDA(W.ocounts.reserve(n + 1));
-  int cl = 0;
-  for (int c = 1; c <= 8; c *= 2) if (n <= (size_t)c * kBuildCap) { cl = c; break; }
+  const BuildShape shape = build_shape_for(n);
   static const bool cluster_ok = !getenv("B2R_CUB_SORT");
-  if (cl && cluster_ok) {
+  if (shape.cl && cluster_ok) {
     VgArgs A;
     A.in = d_in; A.stride_f = sf; A.n = N; A.leaf = leaf; A.out = W.out.p; A.okeys = W.okeys.p; A.ocounts = W.ocounts.p;
     A.total = W.mm + 6; A.h_total = W.h_total_dev;
     W.h_total[0] = -1;  // the kernel's count lands here (host-mapped); -1 = not yet
     TEL_BEGIN(W.tel, st);
-    B2R_CUDA(launch_voxelgrid_cluster(cl, A, st));
+    B2R_CUDA(launch_voxelgrid_cluster(build_shape_index(shape), A, st));
     TEL_END(W.tel, KC_VOXELGRID, 1, st);
     B2R_CUDA(cudaStreamSynchronize(st));
     *m = (size_t)(W.h_total[0] < 0 ? 0 : W.h_total[0]);

@@ -1,12 +1,15 @@
 #!/bin/bash
-# 1 GPU: minimum-first sweep with the lane's own best left out — suite, loop batch, odometry; phase cycles of the cluster build (instrumented variant)
-O=gpurun_out/r2o; mkdir -p $O
+# 1 GPU: cluster build / voxel grid templated on pairs per thread (8 CTAs x fewest pairs) with pipelined MATCH.ANY — suite, latency-sensitive benches, phase cycles (instrumented variant)
+O=gpurun_out/r2p; mkdir -p $O
 md5sum hdl_graph_slam_b200/_lib/libb200reg.so > $O/lib.md5
 timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.txt 2>&1; echo "pytest exit $?" >> $O/pytest_gpu.txt
 tail -4 $O/pytest_gpu.txt
 timeout 400 python bench.py --workload loop_batch --cpu-sample 0 > $O/bench_loop_n1.json 2> $O/bench_loop_n1.err
 timeout 600 python bench.py --steps 200 --warmup 5 --cpu-sample 0 --no-anchor > $O/bench_n1.json 2> $O/bench_n1.err
-for f in bench_loop_n1 bench_n1; do python - <<PY
+timeout 600 python bench.py --workload ndt_odometry_hdl32e_128k --steps 50 --warmup 5 --cpu-sample 0 --no-anchor > $O/bench_ndt_n1.json 2> $O/bench_ndt_n1.err
+timeout 600 python bench.py --workload voxelgrid --steps 200 --warmup 5 --cpu-sample 0 > $O/bench_voxelgrid.json 2> $O/bench_voxelgrid.err
+timeout 900 python bench.py --workload kitti_pipeline --steps 100 --warmup 5 --cpu-sample 0 > $O/bench_kitti.json 2> $O/bench_kitti.err
+for f in bench_loop_n1 bench_n1 bench_ndt_n1 bench_voxelgrid bench_kitti; do python - <<PY
 import json
 try:
     d=json.loads(open("$O/$f.json").read().strip().splitlines()[-1]); print("$f", round(d["value"],1), round(d["e2e"]["value"],1), d["ms_per_step"], d["config"].get("strict_chain_value"), d.get("kernel_ms_in_timed_region"))
