@@ -41,6 +41,7 @@ struct b2r_handle {
   int src = 0, tgt = 1, nxt = 2;   // nxt: cloud being prefetched for the next set_source (software pipelining)
   cudaStream_t st2 = nullptr;       // prefetch stream (upload + BVH + covariances of the next source overlap the current align)
   cudaEvent_t ev_prefetch = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // first LM round beside the source's k-NN covariance kernel (run_single_pair)
   bool prefetched = false;
   unsigned long long prefetch_stamp = 0;   // content stamp of the prefetched host cloud (content_stamp)
   cudaEvent_t upload_ev = nullptr;         // end of the last DMA out of a caller-owned pinned buffer
@@ -161,6 +162,10 @@ extern "C" int b2r_select_registration_method(const char* const* keys, const cha
 }
 
 
+// may this device run the 16-CTA cluster kernels?  (cluster size 16 is "non-portable": opted into per kernel and probed with the
+// occupancy query; B2R_NO_CLUSTER16 forces the portable shapes)
+static bool cluster16_allowed();
+
 extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   if (!cfg || !out) return fail(B2R_EINVAL, "NULL argument");
   *out = nullptr;
@@ -190,6 +195,8 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     if (cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
   }
   if (cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
+    return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   if (cudaEventCreateWithFlags(&h->upload_ev, cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
   for (int i = 0; i < 3; i++) {
     if (cudaEventCreateWithFlags(&h->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaEventCreate failed"));
@@ -219,6 +226,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
   h->ndt_work.bc = &h->bc[0];
   h->ndt_work.tel = &h->tel;
   h->vg_work.tel = &h->tel;
+  h->vg_work.wide_clusters = cluster16_allowed();
   *out = h;
   return B2R_OK;
 }
@@ -261,6 +269,8 @@ extern "C" void b2r_destroy(b2r_handle* h) {
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);
   if (h->ev_prefetch) cudaEventDestroy(h->ev_prefetch);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->upload_ev) cudaEventDestroy(h->upload_ev);
   delete h;
 }
@@ -357,6 +367,10 @@ static cudaError_t launch_cluster_build_t(const BuildItem* d_items, const BuildI
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_bvh_build_cluster<CL, PER, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BuildGeom<PER>::kSmem);
     if (e != cudaSuccess) return e;
+    if (CL > 8) {
+      e = cudaFuncSetAttribute(k_bvh_build_cluster<CL, PER, SINGLE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   cudaLaunchConfig_t lc = {};
@@ -377,8 +391,31 @@ static cudaError_t launch_cluster_build_s(int shape_index, const BuildItem* d_it
     case 4: return launch_cluster_build_t<8, 2, SINGLE>(d_items, single, n_clouds, st);
     case 5: return launch_cluster_build_t<8, 4, SINGLE>(d_items, single, n_clouds, st);
     case 6: return launch_cluster_build_t<8, 8, SINGLE>(d_items, single, n_clouds, st);
-    default: return launch_cluster_build_t<8, 16, SINGLE>(d_items, single, n_clouds, st);
+    case 7: return launch_cluster_build_t<8, 16, SINGLE>(d_items, single, n_clouds, st);
+    default: return launch_cluster_build_t<16, 8, SINGLE>(d_items, single, n_clouds, st);
   }
+}
+static bool cluster16_allowed() {
+  static int ok = -1;
+  if (ok < 0) {
+    ok = 0;
+    if (!getenv("B2R_NO_CLUSTER16")) {
+      auto* fn = k_bvh_build_cluster<16, 8, true>;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BuildGeom<8>::kSmem) == cudaSuccess &&
+          cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(16); lc.blockDim = dim3(kBuildThreads); lc.dynamicSmemBytes = BuildGeom<8>::kSmem;
+        cudaLaunchAttribute la[1];
+        la[0].id = cudaLaunchAttributeClusterDimension;
+        la[0].val.clusterDim.x = 16; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+        lc.attrs = la; lc.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fn, &lc) == cudaSuccess && n > 0) ok = 1;
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  return ok == 1;
 }
 // one launch builds `n_clouds` clouds of the same shape: the descriptor list d_items, or (d_items == nullptr) the one cloud `single`
 static cudaError_t launch_cluster_build(int shape_index, const BuildItem* d_items, const BuildItem& single, unsigned n_clouds, cudaStream_t st) {
@@ -393,7 +430,7 @@ static int build_bvh(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
   int arc = bvh_alloc(c);
   if (arc) return arc;
   if (n == 0) { c.bvh_ready = true; return B2R_OK; }
-  const BuildShape shape = build_shape_for(n);
+  const BuildShape shape = build_shape_for(n, cluster16_allowed());
   if (shape.cl && use_cluster_build()) {  // the whole build as ONE kernel on a cluster (the cloud lives in distributed shared memory)
     TEL_BEGIN(&h->tel, st);
     B2R_CUDA(launch_cluster_build(build_shape_index(shape), nullptr, build_item(c), 1, st));
@@ -483,7 +520,13 @@ static int ensure_cov(b2r_handle* h, Cloud& c, int ctx = 0) { return build_cov(h
 
 static int preprocess(b2r_handle* h, int which, bool is_target) {
   Cloud& c = h->clouds[which];
-  if (h->cfg.method == B2R_METHOD_GICP) return ensure_cov(h, c);
+  if (h->cfg.method == B2R_METHOD_GICP) {
+    // a target gets its covariances now; a SOURCE only its search structure: its k-NN covariance kernel is launched by the align,
+    // beside the first correspondence search, which does not read it (run_single_pair) — unless the cloud arrives through the
+    // prefetch path, where both have been built ahead on the second stream
+    static const bool overlap = !getenv("B2R_NO_COV_OVERLAP");
+    return (is_target || !overlap) ? ensure_cov(h, c) : ensure_grid(h, c);
+  }
   // NDT: the target needs the voxel Gaussians; the source is put in Hilbert order (the BVH build's sorted array) so that the
   // 128 points of a derivative block are spatial neighbours and share their voxel cells
   if (is_target) return ndt_ensure_map(h->cfg, c, h->ndt_work, h->st);
@@ -716,7 +759,7 @@ static bool report_consistent(const volatile unsigned long long* flag, unsigned 
 
 // Run the handle's single pair from `mode` at pose x (row-major 3x4 in x[0..11]) until its report lands in mapped memory.
 // Rounds are enqueued ahead of the device (no host wait per iteration); a finished pair's remaining rounds exit at once.
-static int run_single_pair(b2r_handle* h, const double* x, int mode, int tap, const LmCfg& cfg, int first_batch) {
+static int run_single_pair(b2r_handle* h, const double* x, int mode, int tap, const LmCfg& cfg, int first_batch, bool cov_beside_first_search = false) {
   Cloud& s = SRC(h);
   Cloud& t = TGT(h);
   PairDev P;
@@ -729,11 +772,37 @@ static int run_single_pair(b2r_handle* h, const double* x, int mode, int tap, co
   P.tap = tap;
   P.cur = (mode == PM_FIRST) ? 0 : h->cur;
   const unsigned long long seq = P.seq;
-  k_pair_init<<<1, 128, 0, h->st>>>(P, h->d_pair);
-  B2R_CUDA(cudaGetLastError());
   const unsigned max_sorted = (unsigned)((size_t)s.nsup * 1024);
   static const int copies = [] { const char* e = getenv("B2R_NN_COPIES"); int c = e ? atoi(e) : 4; return (c == 1 || c == 2) ? c : 4; }();
   int enq = 0;
+  if (cov_beside_first_search) {
+    // The source's covariances do not exist yet (strict call-by-call chain: no prefetch).  The first round's correspondence search
+    // reads only the source's sorted points and the target's structure, so it runs on the SECOND (low-priority) stream while the
+    // k-NN covariance kernel runs on the main one: that kernel's grid is under one wave with a long tail of single heavy warps
+    // (profiles/r01_g), and the search's blocks fill the SMs as its blocks retire.  The accumulate kernel, the first reader of the
+    // covariances, waits for both.
+    B2R_CUDA(cudaEventRecord(h->ev_fork, h->st));  // behind the structure build and whatever the previous align left on the main stream
+    B2R_CUDA(cudaStreamWaitEvent(h->st2, h->ev_fork, 0));
+    k_pair_init<<<1, 128, 0, h->st2>>>(P, h->d_pair);
+    B2R_CUDA(cudaGetLastError());
+    { TEL_BEGIN(&h->tel, h->st2);
+      cudaError_t e = copies == 1 ? launch_search<1>(h->d_pair, nullptr, 1, max_sorted, cfg, h->st2, false)
+                    : copies == 2 ? launch_search<2>(h->d_pair, nullptr, 1, max_sorted, cfg, h->st2, false)
+                                  : launch_search<4>(h->d_pair, nullptr, 1, max_sorted, cfg, h->st2, false);
+      B2R_CUDA(e);
+      TEL_END(&h->tel, KC_GICP_CORR, 1, h->st2); }
+    B2R_CUDA(cudaEventRecord(h->ev_join, h->st2));
+    int rc0 = ensure_cov(h, s);  // main stream: the k-NN covariance kernel
+    if (rc0) return rc0;
+    B2R_CUDA(cudaStreamWaitEvent(h->st, h->ev_join, 0));
+    rc0 = launch_round(h->d_pair, nullptr, 1, max_sorted, copies, cfg, h->st, &h->tel, false);  // accumulate + LM step of round 1
+    if (rc0) return rc0;
+    enq = 1;
+    first_batch--;
+  } else {
+    k_pair_init<<<1, 128, 0, h->st>>>(P, h->d_pair);
+    B2R_CUDA(cudaGetLastError());
+  }
   auto enqueue = [&](int n) -> int {
     for (int i = 0; i < n; i++) {
       int rc = launch_round(h->d_pair, nullptr, 1, max_sorted, copies, cfg, h->st, &h->tel, true);
@@ -797,7 +866,9 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
     store_result(h, Tg, false, 0, out);
     return B2R_OK;
   }
-  int rc = ensure_cov(h, s);
+  static const bool overlap = !getenv("B2R_NO_COV_OVERLAP");
+  const bool cov_beside = overlap && !s.cov_ready;  // see run_single_pair
+  int rc = cov_beside ? ensure_grid(h, s) : ensure_cov(h, s);
   if (rc) return rc;
   rc = ensure_cov(h, t);
   if (rc) return rc;
@@ -811,7 +882,7 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
   // enqueue as many rounds as the previous align needed (consecutive frames need the same number almost always): a finished
   // pair's surplus rounds exit at once, a shortfall is topped up while the device works
   const int predicted = h->last_rounds > 0 ? h->last_rounds : 5;
-  rc = run_single_pair(h, x0, PM_FIRST, 0, cfg, predicted < 2 ? 2 : predicted);
+  rc = run_single_pair(h, x0, PM_FIRST, 0, cfg, predicted < 2 ? 2 : predicted, cov_beside);
   if (rc) return rc;
   const PairReport& rep = *h->h_rep;
   h->cur = rep.cur;

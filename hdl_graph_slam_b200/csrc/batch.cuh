@@ -241,7 +241,7 @@ static int batch_build_structures(b2r_batch* b, const b2r_pair* pairs, size_t n_
     size_t total = 0;
     for (Cloud* c : todo) {
       if (c->bvh_ready) continue;
-      const BuildShape shape = build_shape_for(c->n);
+      const BuildShape shape = build_shape_for(c->n, cluster16_allowed());
       if (!shape.cl || !use_cluster_build()) { int rc = build_bvh(h, *c, h->bc[0], st); if (rc) return rc; continue; }
       int rc = bvh_alloc(*c);
       if (rc) return rc;

@@ -35,20 +35,26 @@ struct BuildGeom {
   static constexpr int kShift = PER == 1 ? 10 : PER == 2 ? 11 : PER == 4 ? 12 : PER == 8 ? 13 : 14;     // log2(kCap)
   static constexpr size_t kSmem = (size_t)kCap * 8 + 32 * 256 * 2 + 256 * 4 * 2 + 64 * 4;
 };
-// the (cluster size, pairs per thread) of a cloud of n points: 0 = too large for a cluster
+// the (cluster size, pairs per thread) of a cloud of n points: 0 = too large for a cluster.  `wide` = clusters of 16 CTAs may be
+// launched (non-portable size, opt-in per kernel, probed once: cluster16_allowed()): clouds above 65 536 points then take
+// 16 CTAs x 8 pairs instead of 8 x 16.
 struct BuildShape { int cl, per; };
-inline BuildShape build_shape_for(size_t n) {
+inline BuildShape build_shape_for(size_t n, bool wide) {
   if (n > (size_t)kBuildMaxPoints) return {0, 0};
   const int slices = (int)((n + kBuildThreads - 1) / kBuildThreads) > 0 ? (int)((n + kBuildThreads - 1) / kBuildThreads) : 1;
+  if (wide && slices > 64) return {16, 8};
   int per = 1;
   while (per * 8 < slices) per *= 2;
   int cl = 1;
   while (cl * per < slices) cl *= 2;
   return {cl, per};
 }
-// index of a shape in the instantiation table: (1,1) (2,1) (4,1) (8,1) (8,2) (8,4) (8,8) (8,16)
-inline int build_shape_index(BuildShape s) { return s.per == 1 ? (s.cl == 1 ? 0 : s.cl == 2 ? 1 : s.cl == 4 ? 2 : 3) : (s.per == 2 ? 4 : s.per == 4 ? 5 : s.per == 8 ? 6 : 7); }
-constexpr int kBuildShapes = 8;
+// index of a shape in the instantiation table: (1,1) (2,1) (4,1) (8,1) (8,2) (8,4) (8,8) (8,16) (16,8)
+inline int build_shape_index(BuildShape s) {
+  if (s.cl == 16) return 8;
+  return s.per == 1 ? (s.cl == 1 ? 0 : s.cl == 2 ? 1 : s.cl == 4 ? 2 : 3) : (s.per == 2 ? 4 : s.per == 4 ? 5 : s.per == 8 ? 6 : 7);
+}
+constexpr int kBuildShapes = 9;
 
 struct BuildItem {   // one cloud of a batched build
   const float* raw;

@@ -41,6 +41,7 @@ struct VoxelWork {
   int* h_total = nullptr;    // pinned + mapped: [0] voxel count, [1] overflow flag
   int* h_total_dev = nullptr;
   Telemetry* tel = nullptr;
+  bool wide_clusters = false;  // 16-CTA clusters may be launched on this device (set by the handle: cluster16_allowed())
   void release() {
     in.release(); out.release(); keys_a.release(); keys_b.release(); vals_a.release(); vals_b.release(); flags.release(); slots.release();
     okeys.release(); ocounts.release(); tmp.release();
@@ -295,6 +296,10 @@ static cudaError_t launch_voxelgrid_cluster_t(const VgArgs& A, cudaStream_t st) 
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_voxelgrid_cluster<CL, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BuildGeom<PER>::kSmem);
     if (e != cudaSuccess) return e;
+    if (CL > 8) {
+      e = cudaFuncSetAttribute(k_voxelgrid_cluster<CL, PER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   cudaLaunchConfig_t lc = {};
@@ -314,7 +319,8 @@ static cudaError_t launch_voxelgrid_cluster(int shape_index, const VgArgs& A, cu
     case 4: return launch_voxelgrid_cluster_t<8, 2>(A, st);
     case 5: return launch_voxelgrid_cluster_t<8, 4>(A, st);
     case 6: return launch_voxelgrid_cluster_t<8, 8>(A, st);
-    default: return launch_voxelgrid_cluster_t<8, 16>(A, st);
+    case 7: return launch_voxelgrid_cluster_t<8, 16>(A, st);
+    default: return launch_voxelgrid_cluster_t<16, 8>(A, st);
   }
 }
 
@@ -332,7 +338,7 @@ inline int voxelgrid_device(VoxelWork& W, cudaStream_t st, const float* d_in, si
   }
   B2R_CUDA(W.out.reserve(n * sf + 8));
   B2R_CUDA(W.okeys.reserve(n + 1)); B2R_CUDA(W.ocounts.reserve(n + 1));
-  const BuildShape shape = build_shape_for(n);
+  const BuildShape shape = build_shape_for(n, W.wide_clusters);
   static const bool cluster_ok = !getenv("B2R_CUB_SORT");
   if (shape.cl && cluster_ok) {
     VgArgs A;
