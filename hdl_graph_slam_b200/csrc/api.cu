@@ -870,6 +870,7 @@ static int gicp_align(b2r_handle* h, const float* guess, b2r_result* out) {
   const bool cov_beside = overlap && !s.cov_ready;  // see run_single_pair
   int rc = cov_beside ? ensure_grid(h, s) : ensure_cov(h, s);
   if (rc) return rc;
+  if (cov_beside) B2R_CUDA(s.cov.reserve((size_t)s.nsup * 1024 * 6 + 6));  // the pair record takes the buffer's address before the kernel that fills it is launched
   rc = ensure_cov(h, t);
   if (rc) return rc;
   rc = ensure_align_ws(h, s.n);

@@ -1,11 +1,11 @@
 #!/bin/bash
 # 1 GPU: faster hilbert30, first search beside the source k-NN covariance kernel (strict chain), optional 16-CTA clusters — suite, benches, phase cycles
-O=gpurun_out/r2q; mkdir -p $O
+O=gpurun_out/r2r; mkdir -p $O
 md5sum hdl_graph_slam_b200/_lib/libb200reg.so > $O/lib.md5
 timeout 900 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.txt 2>&1; echo "pytest exit $?" >> $O/pytest_gpu.txt
 tail -4 $O/pytest_gpu.txt
 timeout 400 python bench.py --workload loop_batch --cpu-sample 0 > $O/bench_loop_n1.json 2> $O/bench_loop_n1.err
-timeout 600 python bench.py --steps 200 --warmup 5 --cpu-sample 0 --no-anchor > $O/bench_n1.json 2> $O/bench_n1.err
+timeout 600 python bench.py --steps 200 --warmup 5 --cpu-sample 0 > $O/bench_n1.json 2> $O/bench_n1.err
 timeout 600 python bench.py --workload ndt_odometry_hdl32e_128k --steps 50 --warmup 5 --cpu-sample 0 --no-anchor > $O/bench_ndt_n1.json 2> $O/bench_ndt_n1.err
 timeout 600 python bench.py --workload voxelgrid --steps 200 --warmup 5 --cpu-sample 0 > $O/bench_voxelgrid.json 2> $O/bench_voxelgrid.err
 timeout 900 python bench.py --workload kitti_pipeline --steps 100 --warmup 5 --cpu-sample 0 > $O/bench_kitti.json 2> $O/bench_kitti.err
