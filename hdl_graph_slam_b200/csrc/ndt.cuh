@@ -302,16 +302,18 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
   }
   unsigned int npairs = 0;
   const VoxGeom V = *A.geom;
-  // Persistent grid: the launch holds at most one resident wave of blocks (ndt_run_pass sizes it from the occupancy) and block b
-  // takes the chunks b, b + gridDim.x, ... of 128 Hilbert-consecutive points.  A cloud of 128k points is 1.7 waves of one-chunk
-  // blocks: launched that way, the second wave's stragglers set the pass time (slowest SM sub-partition 121k cycles against a mean
-  // of 68k, profiles/r02_g).  The per-thread sums run on across the chunks (static assignment => fixed summation order), so the
-  // block reduction is paid once per block instead of once per chunk.
-  const int n_chunks = A.n_sorted / kNdtThreads;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-  const int s = chunk * kNdtThreads + threadIdx.x;
+  // Persistent grid: the launch holds at most one resident wave of blocks (ndt_run_pass sizes it from the occupancy).  A cloud of
+  // 128k points is 1.7 waves of one-chunk blocks: launched that way, the second wave's stragglers set the pass time (slowest SM
+  // sub-partition 121k cycles against a mean of 68k, profiles/r02_g).  The per-thread sums run on across the block's chunks (static
+  // assignment => fixed summation order), so the block reduction is paid once per block instead of once per chunk.
+  // Block b owns the contiguous range [b n / G, (b + 1) n / G) of the Hilbert-sorted source and walks it 128 points at a time: every
+  // block gets the same number of points (a whole number of 128-point chunks per block would leave 432 blocks with two chunks
+  // and 160 with one at 131 072 points on 592 resident blocks).
+  const int p0 = (int)((long long)blockIdx.x * A.n_sorted / gridDim.x), p1 = (int)((long long)(blockIdx.x + 1) * A.n_sorted / gridDim.x);
+  for (int base = p0; base < p1; base += kNdtThreads) {
+  const int s = base + threadIdx.x;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
-  if (s < A.n_sorted) pt = A.src[s];
+  if (s < p1) pt = A.src[s];
   const float x = pt.x, y = pt.y, z = pt.z;
   float xt = 0.f, yt = 0.f, zt = 0.f;
   int ci = 0, cj = 0, ck = 0;
