@@ -662,7 +662,7 @@ static int ensure_align_ws(b2r_handle* h, size_t n_in) {
   }
   B2R_CUDA(h->d2.reserve(n + 1));
   size_t nb = (n + kAccThreads - 1) / kAccThreads + 1;
-  B2R_CUDA(h->partials.reserve(nb * kAcc + nb + 64));
+  B2R_CUDA(h->partials.reserve((nb + 32) * kAcc + 64));  // [kAcc][blocks rounded up to 32]
   return B2R_OK;
 }
 

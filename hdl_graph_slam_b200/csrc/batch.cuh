@@ -316,7 +316,7 @@ static size_t pair_ws_bytes(size_t n_pad, bool fit_only) {
     t += 2 * align_up(n_pad * 6 * sizeof(double), 256);   // mahal
   }
   t += align_up(n_pad * sizeof(float), 256);            // d2
-  t += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);  // partials
+  t += align_up((n_pad / kAccThreads + 32) * kAcc * sizeof(double), 256);  // partials: [kAcc][blocks rounded up to 32]
   return t;
 }
 
@@ -413,7 +413,7 @@ static int batch_run_chunk(b2r_batch* b, const b2r_pair* pairs, size_t m, const 
         for (int k = 0; k < 2; k++) { P.mahal[k] = reinterpret_cast<double*>(wp); wp += align_up(n_pad * 6 * sizeof(double), 256); }
       }
       P.d2 = reinterpret_cast<float*>(wp); wp += align_up(n_pad * sizeof(float), 256);
-      P.partials = reinterpret_cast<double*>(wp); wp += align_up((n_pad / kAccThreads + 1) * kAcc * sizeof(double), 256);
+      P.partials = reinterpret_cast<double*>(wp); wp += align_up((n_pad / kAccThreads + 32) * kAcc * sizeof(double), 256);
       P.report = d_rep + i;
       R.known++;
       if (n_pad > R.max_pad) R.max_pad = n_pad;

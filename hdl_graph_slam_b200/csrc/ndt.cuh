@@ -253,6 +253,7 @@ struct NdtArgs {
   double d1, d2;
   int ncell_search;  // 1 or 7
   int compute_hessian;
+  int even_split;   // contiguous n / G points per block instead of 128-point chunks b, b + G, ... (diagnostic, B2R_NDT_EVEN)
   double* partials;
   double* out;
   unsigned int* counter;
@@ -306,11 +307,13 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
   // 128k points is 1.7 waves of one-chunk blocks: launched that way, the second wave's stragglers set the pass time (slowest SM
   // sub-partition 121k cycles against a mean of 68k, profiles/r02_g).  The per-thread sums run on across the block's chunks (static
   // assignment => fixed summation order), so the block reduction is paid once per block instead of once per chunk.
-  // Block b owns the contiguous range [b n / G, (b + 1) n / G) of the Hilbert-sorted source and walks it 128 points at a time: every
-  // block gets the same number of points (a whole number of 128-point chunks per block would leave 432 blocks with two chunks
-  // and 160 with one at 131 072 points on 592 resident blocks).
-  const int p0 = (int)((long long)blockIdx.x * A.n_sorted / gridDim.x), p1 = (int)((long long)(blockIdx.x + 1) * A.n_sorted / gridDim.x);
-  for (int base = p0; base < p1; base += kNdtThreads) {
+  // Block b takes the 128-point chunks b, b + G, ... of the Hilbert-sorted source (G = gridDim.x).  (A/B, profiles/r02_s: giving every
+  // block one contiguous range of n / G points instead — 1.73 chunks each rather than two for 432 blocks and one for 160 — measured
+  // 52.5 vs 50.7 us per pass: the pass is not bound by that count but by single heavy blocks and, before finish_stored_t, by the
+  // final reduction.  B2R_NDT_EVEN=1 selects the contiguous split.)
+  const int p1 = A.even_split ? (int)((long long)(blockIdx.x + 1) * A.n_sorted / gridDim.x) : A.n_sorted;
+  const int step = A.even_split ? kNdtThreads : (int)gridDim.x * kNdtThreads;
+  for (int base = A.even_split ? (int)((long long)blockIdx.x * A.n_sorted / gridDim.x) : (int)blockIdx.x * kNdtThreads; base < p1; base += step) {
   const int s = base + threadIdx.x;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < p1) pt = A.src[s];
@@ -466,10 +469,11 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
   // pair count (integer, exact) through a warp reduction + one atomic per warp
   npairs = __reduce_add_sync(0xffffffffu, npairs);
   if (lane == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
+  const unsigned int pstride = (gridDim.x + 31u) & ~31u;  // partials are stored transposed: value i of block b at [i * pstride + b] (finish_stored_t)
   block_reduce<kNdtAccA>(acc, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < kNdtAccA; i++) A.partials[(size_t)blockIdx.x * kNdtAcc + i] = acc[i];
+    for (int i = 0; i < kNdtAccA; i++) A.partials[(size_t)i * pstride + blockIdx.x] = acc[i];
   }
   double accb[kNdtAccB];
 #pragma unroll
@@ -478,9 +482,9 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
   block_reduce<kNdtAccB>(accb, red);
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int i = 0; i < kNdtAccB; i++) A.partials[(size_t)blockIdx.x * kNdtAcc + kNdtAccA + i] = accb[i];
+    for (int i = 0; i < kNdtAccB; i++) A.partials[(size_t)(kNdtAccA + i) * pstride + blockIdx.x] = accb[i];
   }
-  finish_stored<kNdtAcc>(A.partials, A.out, A.counter, A.flag, A.seq, A.pairs);
+  finish_stored_t<kNdtAcc>(A.partials, pstride, A.out, A.counter, A.flag, A.seq, A.pairs);
 }
 
 
@@ -855,8 +859,10 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   A.d1 = K.d1; A.d2 = K.d2;
   A.ncell_search = (cfg.ndt_search_method == 1) ? 1 : 7;
   A.compute_hessian = compute_hessian ? 1 : 0;
+  static const int even_split = getenv("B2R_NDT_EVEN") ? 1 : 0;
+  A.even_split = even_split;
   const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);
-  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));
+  B2R_CUDA(W.partials.reserve((size_t)(nb + 64) * kNdtAcc));  // derivative pass: [kNdtAcc][blocks rounded up to 32]; Hessian pass: [blocks][36]
   A.partials = W.partials.p; A.out = W.h_out_dev; A.counter = W.d_counter; A.pairs = W.d_pairs;
   A.flag = W.h_flag_dev; A.seq = ++W.seq;
   if (hessian_only) {

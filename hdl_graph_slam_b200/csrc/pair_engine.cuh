@@ -61,7 +61,7 @@ struct PairDev {
   int* cpos[2];
   double* mahal[2];
   float* d2;
-  double* partials;        // [nblk_acc][kAcc]
+  double* partials;        // [kAcc][nblk_acc rounded up to 32] (transposed)
   // where results go
   PairReport* report;      // device memory (batch) or host-mapped memory (single pair)
   unsigned long long* flag;      // host-mapped: publication flag of `report` (checksummed message), or nullptr
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pai
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kAccThreads / 32; w++) v += red[threadIdx.x * 8 + w];
-    p.partials[(size_t)blockIdx.x * kAcc + threadIdx.x] = v;
+    p.partials[(size_t)threadIdx.x * (((unsigned)nblk + 31u) & ~31u) + blockIdx.x] = v;  // transposed: value i of block b at [i * stride + b] (k_pair_lm)
   }
 }
 static_assert(kAccThreads == 256, "red_emit parks 8 warp sums per value");
@@ -508,7 +508,6 @@ static_assert(kAccThreads == 256, "red_emit parks 8 warp sums per value");
 // chain itself never waits on HBM) and publishes the record when the registration ends.
 constexpr int kLmThreads = 256;
 __global__ void __launch_bounds__(kLmThreads, 1) k_pair_lm(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
-  __shared__ double fin[8 * kAcc];
   __shared__ double r[kAcc];
   __shared__ PairDev sp;
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -525,28 +524,27 @@ __global__ void __launch_bounds__(kLmThreads, 1) k_pair_lm(PairDev* pairs, const
   const double* partials = gp->partials;
   const unsigned int nrow = (unsigned int)gp->nblk_acc;
   {
-    // warp w adds rows w, w+8, ... (lane = value: one coalesced row per load, 8 loads in flight), then thread i adds the 8 warp sums
+    // the partials are stored transposed ([value][block], stride = blocks rounded up to 32): warp w sums the values w, w + 8, ...;
+    // one coalesced load covers 32 blocks of a value, all loads of a value are independent, lane l adds blocks l, l + 32, ... in
+    // ascending order and a fixed butterfly joins the lanes — a couple of memory round trips for the whole reduction
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nw = kLmThreads / 32;
-    if (lane < kAcc) {
+    const unsigned int stride = (nrow + 31u) & ~31u;
+    for (int i = warp; i < kAcc; i += nw) {
+      const double* col = partials + (size_t)i * stride;
       double sacc = 0.0;
-      unsigned int row = warp;
-      for (; row + 7 * nw < nrow; row += 8 * nw) {
+      unsigned int row = lane;
+      for (; row + 7 * 32 < nrow; row += 8 * 32) {
         double t[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = __ldcg(partials + (size_t)(row + u * nw) * kAcc + lane);
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(col + row + u * 32);
 #pragma unroll
         for (int u = 0; u < 8; u++) sacc += t[u];
       }
-      for (; row < nrow; row += nw) sacc += __ldcg(partials + (size_t)row * kAcc + lane);
-      fin[warp * kAcc + lane] = sacc;
-    }
-    __syncthreads();
-    if (threadIdx.x < kAcc) {
-      double sacc = 0.0;
+      for (; row < nrow; row += 32) sacc += __ldcg(col + row);
 #pragma unroll
-      for (int w = 0; w < nw; w++) sacc += fin[w * kAcc + threadIdx.x];
-      r[threadIdx.x] = sacc;
+      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+      if (lane == 0) r[i] = sacc;
     }
     __syncthreads();
   }
