@@ -167,15 +167,51 @@ struct KnnRegs {
 #ifdef B2R_KNN_PROFILE
     n_ins++;
 #endif
-    bool pj = true;  // p_j = old key[j] > kq, monotone in j; p_{K-1} holds (tested above)
+    if constexpr (K == 20) {
+      insert20(kq);
+    } else {
+      bool pj = true;  // p_j = old key[j] > kq, monotone in j; p_{K-1} holds (tested above)
 #pragma unroll
-    for (int j = K - 1; j > 0; j--) {  // descending: key[j-1] is still the old value when slot j is rewritten
-      const unsigned long long lo = key[j - 1];
-      const bool pl = lo > kq;
-      if (pj) key[j] = pl ? lo : kq;   // slot j changes only if p_j: takes its left neighbour, or the new key at the boundary
-      pj = pl;
+      for (int j = K - 1; j > 0; j--) {  // descending: key[j-1] is still the old value when slot j is rewritten
+        const unsigned long long lo = key[j - 1];
+        const bool pl = lo > kq;
+        if (pj) key[j] = pl ? lo : kq;   // slot j changes only if p_j: takes its left neighbour, or the new key at the boundary
+        pj = pl;
+      }
+      if (pj) key[0] = kq;
     }
-    if (pj) key[0] = kq;
+  }
+  // The same network for K = 20 written out in PTX.  From the C++ loop above ptxas evaluates every 64-bit compare TWICE (once as
+  // the guard of slot j, once as the selector of slot j + 1: 4 ISETP + 2 SEL per slot, 118 instructions per insertion); here each
+  // compare is one setp.u64 whose predicate serves both uses: 2 ISETP + 2 SEL per slot, 80 instructions.  Same decisions, same list.
+  __device__ __forceinline__ void insert20(unsigned long long kq) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .pred pa, pb;\n\t"
+        "setp.gt.u64 pa, %18, %20;\n\t selp.b64 %19, %18, %20, pa;\n\t"
+        "setp.gt.u64 pb, %17, %20;\n\t @pa selp.b64 %18, %17, %20, pb;\n\t"
+        "setp.gt.u64 pa, %16, %20;\n\t @pb selp.b64 %17, %16, %20, pa;\n\t"
+        "setp.gt.u64 pb, %15, %20;\n\t @pa selp.b64 %16, %15, %20, pb;\n\t"
+        "setp.gt.u64 pa, %14, %20;\n\t @pb selp.b64 %15, %14, %20, pa;\n\t"
+        "setp.gt.u64 pb, %13, %20;\n\t @pa selp.b64 %14, %13, %20, pb;\n\t"
+        "setp.gt.u64 pa, %12, %20;\n\t @pb selp.b64 %13, %12, %20, pa;\n\t"
+        "setp.gt.u64 pb, %11, %20;\n\t @pa selp.b64 %12, %11, %20, pb;\n\t"
+        "setp.gt.u64 pa, %10, %20;\n\t @pb selp.b64 %11, %10, %20, pa;\n\t"
+        "setp.gt.u64 pb, %9, %20;\n\t @pa selp.b64 %10, %9, %20, pb;\n\t"
+        "setp.gt.u64 pa, %8, %20;\n\t @pb selp.b64 %9, %8, %20, pa;\n\t"
+        "setp.gt.u64 pb, %7, %20;\n\t @pa selp.b64 %8, %7, %20, pb;\n\t"
+        "setp.gt.u64 pa, %6, %20;\n\t @pb selp.b64 %7, %6, %20, pa;\n\t"
+        "setp.gt.u64 pb, %5, %20;\n\t @pa selp.b64 %6, %5, %20, pb;\n\t"
+        "setp.gt.u64 pa, %4, %20;\n\t @pb selp.b64 %5, %4, %20, pa;\n\t"
+        "setp.gt.u64 pb, %3, %20;\n\t @pa selp.b64 %4, %3, %20, pb;\n\t"
+        "setp.gt.u64 pa, %2, %20;\n\t @pb selp.b64 %3, %2, %20, pa;\n\t"
+        "setp.gt.u64 pb, %1, %20;\n\t @pa selp.b64 %2, %1, %20, pb;\n\t"
+        "setp.gt.u64 pa, %0, %20;\n\t @pb selp.b64 %1, %0, %20, pa;\n\t"
+        "@pa mov.b64 %0, %20;\n\t}"
+        : "+l"(key[0]), "+l"(key[1]), "+l"(key[2]), "+l"(key[3]), "+l"(key[4]), "+l"(key[5]), "+l"(key[6]), "+l"(key[7]), "+l"(key[8]),
+          "+l"(key[9]), "+l"(key[10]), "+l"(key[11]), "+l"(key[12]), "+l"(key[13]), "+l"(key[14]), "+l"(key[15]), "+l"(key[16]),
+          "+l"(key[17]), "+l"(key[18]), "+l"(key[19])
+        : "l"(kq));
+#endif
   }
   __device__ __forceinline__ int count() const {
     int c = 0;

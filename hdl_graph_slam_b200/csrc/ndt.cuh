@@ -62,6 +62,10 @@ struct NdtVoxelMap {
 
 struct NdtWork {
   DevBuf<double> partials;
+  DevBuf<double> grows;           // derivative pass: group rows of the two-level sum
+  DevBuf<unsigned int> gcount;    // derivative pass: per-group arrival counters (zero between launches)
+  unsigned long long* d_queue = nullptr;  // chunk ticket counter, monotone over launches
+  unsigned long long qnext = 0;   // first ticket of the next launch
   double* d_out = nullptr;        // 64 doubles
   unsigned int* d_counter = nullptr;
   double* h_out = nullptr;        // pinned + mapped: kernels write their results here directly
@@ -72,7 +76,9 @@ struct NdtWork {
   BuildCtx* bc = nullptr;         // build scratch of the handle's main stream (keys / values / sort space)
   Telemetry* tel = nullptr;
   void release() {
-    partials.release();
+    partials.release(); grows.release(); gcount.release();
+    if (d_queue) cudaFree(d_queue);
+    d_queue = nullptr;
     if (d_out) cudaFree(d_out);
     if (d_counter) cudaFree(d_counter);
     if (h_out) cudaFreeHost(h_out);
@@ -253,8 +259,11 @@ struct NdtArgs {
   double d1, d2;
   int ncell_search;  // 1 or 7
   int compute_hessian;
-  int even_split;   // contiguous n / G points per block instead of 128-point chunks b, b + G, ... (diagnostic, B2R_NDT_EVEN)
-  double* partials;
+  double* partials;            // derivative pass: one row of kNdtAcc sums per 128-point chunk; Hessian pass: [blocks][36]
+  double* grows;               // derivative pass: one row per group of 32 chunks
+  unsigned int* gcount;        // chunks of a group that have delivered their row (zero between launches)
+  unsigned long long* queue;   // chunk tickets: monotone over launches, this launch's start at qbase
+  unsigned long long qbase;
   double* out;
   unsigned int* counter;
   unsigned long long* pairs;
@@ -287,13 +296,50 @@ __device__ __forceinline__ int ndt_find(const unsigned long long* __restrict__ t
 // the voxel records they need (<= 7 per point) form a small box of cells: the block looks every cell of that box up ONCE,
 // stages the 64-byte records in shared memory, and the per-(point, cell) loop then runs without a global load.  Blocks
 // whose points are spread too wide for the staging area (far-field leaves, jumps of the curve) fall back to direct lookups.
+//
+// Work distribution and summation order (round 2, late): the 128-point CHUNKS of the source are handed out through a ticket
+// counter (a resident block takes the next chunk when it is done with its own), every chunk reduces to its OWN row of 43
+// float64 sums, and the rows are added by a fixed two-level tree (32 chunk rows -> one group row by whichever block completes
+// the group, group rows -> result by whichever block completes the last group).  The sums therefore do not depend on which
+// block processed which chunk — bitwise reproducible — while no SM waits for a statically assigned heavy block (ncu, static
+// persistent grid: slowest SM sub-partition 99 k cycles against a mean of 56 k, a quarter of it the single last block adding 592
+// rows of partials in 38 dependent memory round trips; profiles/r02_t).
+constexpr int kNdtRow = 136;  // float64 elements per shared-memory row of per-thread values (128 + 8: half-warps hit distinct banks)
+
+// sums of R (<= 16) rows of 128 per-thread values -> dst[0..R): thread (row = tid >> 3, part = tid & 7) adds the elements part,
+// part + 8, ... of its row in ascending order, three butterfly levels join the 8 parts.  The order is fixed.
+__device__ __forceinline__ void ndt_rows_sum(const double* rows, int R, double* dst) {
+  const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
+  double s = 0.0;
+  if (row < R) {
+    const double* p = rows + row * kNdtRow + part;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += p[8 * j];
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (row < R && part == 0) dst[row] = s;
+}
+
 template <bool HESS>
 __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
-  __shared__ NdtCell s_cell[kNdtSlots];
-  __shared__ double red[kNdtAccA * 32];
-  __shared__ double s_low[kNdtAccB][kNdtThreads];  // strict lower triangle of H: one float64 column per thread (no conflicts, no sync)
+  __shared__ __align__(16) NdtCell s_cell[kNdtSlots];  // staged voxel records; after the pair loop: rows of the register sums
+  __shared__ double s_low[kNdtAccB][kNdtRow];          // strict lower triangle of H: one float64 column per thread (no conflicts, no sync)
+  __shared__ double s_fin[kNdtAcc];
   __shared__ int s_box[6];
+  __shared__ int s_chunk, s_role;
+  static_assert(sizeof(NdtCell) * kNdtSlots >= sizeof(double) * 14 * kNdtRow, "the reduction rows reuse the staging area");
+  constexpr int NV = HESS ? kNdtAcc : 7;  // values that carry information (score + gradient without the Hessian)
   const int lane = threadIdx.x & 31;
+  const VoxGeom V = *A.geom;
+  const int nchunks = A.n_sorted / kNdtThreads;  // n_sorted is a multiple of 1024
+  const int p1 = A.n_sorted;
+  for (;;) {
+  if (threadIdx.x == 0) s_chunk = (int)(atomicAdd(A.queue, 1ull) - A.qbase);  // tickets of this launch start at qbase (ndt_run_pass)
+  __syncthreads();
+  const int chunk = s_chunk;
+  if (chunk >= nchunks) break;  // block-uniform
   double acc[kNdtAccA];
 #pragma unroll
   for (int k = 0; k < kNdtAccA; k++) acc[k] = 0.0;
@@ -302,18 +348,7 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
     for (int q = 0; q < kNdtAccB; q++) s_low[q][threadIdx.x] = 0.0;
   }
   unsigned int npairs = 0;
-  const VoxGeom V = *A.geom;
-  // Persistent grid: the launch holds at most one resident wave of blocks (ndt_run_pass sizes it from the occupancy).  A cloud of
-  // 128k points is 1.7 waves of one-chunk blocks: launched that way, the second wave's stragglers set the pass time (slowest SM
-  // sub-partition 121k cycles against a mean of 68k, profiles/r02_g).  The per-thread sums run on across the block's chunks (static
-  // assignment => fixed summation order), so the block reduction is paid once per block instead of once per chunk.
-  // Block b takes the 128-point chunks b, b + G, ... of the Hilbert-sorted source (G = gridDim.x).  (A/B, profiles/r02_s: giving every
-  // block one contiguous range of n / G points instead — 1.73 chunks each rather than two for 432 blocks and one for 160 — measured
-  // 52.5 vs 50.7 us per pass: the pass is not bound by that count but by single heavy blocks and, before finish_stored_t, by the
-  // final reduction.  B2R_NDT_EVEN=1 selects the contiguous split.)
-  const int p1 = A.even_split ? (int)((long long)(blockIdx.x + 1) * A.n_sorted / gridDim.x) : A.n_sorted;
-  const int step = A.even_split ? kNdtThreads : (int)gridDim.x * kNdtThreads;
-  for (int base = A.even_split ? (int)((long long)blockIdx.x * A.n_sorted / gridDim.x) : (int)blockIdx.x * kNdtThreads; base < p1; base += step) {
+  const int base = chunk * kNdtThreads;
   const int s = base + threadIdx.x;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < p1) pt = A.src[s];
@@ -464,27 +499,92 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
       }
     }
   }
-  __syncthreads();  // s_box / s_cell are re-staged by the next chunk
-  }
+  __syncthreads();  // the pair loop is over: s_cell becomes the reduction rows
   // pair count (integer, exact) through a warp reduction + one atomic per warp
   npairs = __reduce_add_sync(0xffffffffu, npairs);
   if (lane == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
-  const unsigned int pstride = (gridDim.x + 31u) & ~31u;  // partials are stored transposed: value i of block b at [i * pstride + b] (finish_stored_t)
-  block_reduce<kNdtAccA>(acc, red);
-  if (threadIdx.x == 0) {
+  // ---- this chunk's row of sums
+  double* tile = reinterpret_cast<double*>(s_cell);
+  double* my_row = A.partials + (size_t)chunk * kNdtAcc;
 #pragma unroll
-    for (int i = 0; i < kNdtAccA; i++) A.partials[(size_t)i * pstride + blockIdx.x] = acc[i];
+  for (int k = 0; k < 14; k++) tile[k * kNdtRow + threadIdx.x] = acc[k];
+  __syncthreads();
+  ndt_rows_sum(tile, HESS ? 14 : 7, my_row);
+  if (HESS) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 14; k++) tile[k * kNdtRow + threadIdx.x] = acc[14 + k];
+    __syncthreads();
+    ndt_rows_sum(tile, 14, my_row + 14);
+    ndt_rows_sum(&s_low[0][0], kNdtAccB, my_row + kNdtAccA);
   }
-  double accb[kNdtAccB];
-#pragma unroll
-  for (int q = 0; q < kNdtAccB; q++) accb[q] = HESS ? s_low[q][threadIdx.x] : 0.0;
-  __syncthreads();  // `red` is reused
-  block_reduce<kNdtAccB>(accb, red);
+  __syncthreads();  // the row is written (by several threads); s_cell / s_low / s_box are free for the next chunk
+  // ---- fixed two-level tree over the chunk rows
+  const int g = chunk >> 5;
+  const int gsize = min(32, nchunks - (g << 5));
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < kNdtAccB; i++) A.partials[(size_t)(kNdtAccA + i) * pstride + blockIdx.x] = accb[i];
+    __threadfence();
+    const unsigned int t = atomicAdd(A.gcount + g, 1u);
+    const bool closes = t == (unsigned int)(gsize - 1);
+    if (closes) A.gcount[g] = 0;  // all increments of this group are in: ready for the next launch
+    s_role = closes ? 1 : 0;
   }
-  finish_stored_t<kNdtAcc>(A.partials, pstride, A.out, A.counter, A.flag, A.seq, A.pairs);
+  __syncthreads();
+  if (s_role) {  // block-uniform: this block completed group g and adds its rows in ascending chunk order
+    __threadfence();
+    if (threadIdx.x < NV) {
+      const double* col = A.partials + (size_t)(g << 5) * kNdtAcc + threadIdx.x;
+      double t[32];
+#pragma unroll
+      for (int u = 0; u < 32; u++) t[u] = (u < gsize) ? __ldcg(col + (size_t)u * kNdtAcc) : 0.0;  // 32 independent loads: one round trip
+      double sum = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32; u++) sum += t[u];
+      A.grows[(size_t)g * kNdtAcc + threadIdx.x] = sum;
+    }
+    __syncthreads();
+    const unsigned int ngroups = (unsigned int)((nchunks + 31) >> 5);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t2 = atomicAdd(A.counter, 1u);
+      const bool last = t2 == ngroups - 1;
+      if (last) *A.counter = 0;
+      s_role = last ? 2 : 0;
+    }
+    __syncthreads();
+    if (s_role == 2) {  // the last group is in: add the group rows in ascending order and publish
+      __threadfence();
+      if (threadIdx.x < kNdtAcc) {
+        double sum = 0.0;
+        if (threadIdx.x < NV) {
+          const double* col = A.grows + threadIdx.x;
+          unsigned int r = 0;
+          for (; r + 32 <= ngroups; r += 32) {
+            double t[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) t[u] = __ldcg(col + (size_t)(r + u) * kNdtAcc);
+#pragma unroll
+            for (int u = 0; u < 32; u++) sum += t[u];
+          }
+          for (; r < ngroups; r++) sum += __ldcg(col + (size_t)r * kNdtAcc);
+        }
+        A.out[threadIdx.x] = sum;
+        s_fin[threadIdx.x] = sum;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long x = A.seq;
+        const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(A.pairs);
+        *A.pairs = 0;
+        reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc] = e;
+        x ^= msg_mix(e, kNdtAcc);
+        for (int i = 0; i < kNdtAcc; i++) x ^= msg_mix((unsigned long long)__double_as_longlong(s_fin[i]), i);
+        reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc + 1] = x;
+        *reinterpret_cast<volatile unsigned long long*>(A.flag) = A.seq;
+      }
+    }
+  }
+  }
 }
 
 
@@ -564,6 +664,9 @@ inline int ndt_init_work(NdtWork& W) {
   B2R_CUDA(cudaMemset(W.d_counter, 0, 4 * sizeof(unsigned int)));
   B2R_CUDA(cudaMalloc(&W.d_pairs, sizeof(unsigned long long)));
   B2R_CUDA(cudaMemset(W.d_pairs, 0, sizeof(unsigned long long)));
+  B2R_CUDA(cudaMalloc(&W.d_queue, sizeof(unsigned long long)));
+  B2R_CUDA(cudaMemset(W.d_queue, 0, sizeof(unsigned long long)));
+  W.qnext = 0;
   B2R_CUDA(cudaHostAlloc(&W.h_out, 72 * sizeof(double), cudaHostAllocMapped));
   B2R_CUDA(cudaHostGetDevicePointer((void**)&W.h_out_dev, W.h_out, 0));
   W.h_flag = reinterpret_cast<unsigned long long*>(W.h_out + 64);
@@ -859,11 +962,16 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   A.d1 = K.d1; A.d2 = K.d2;
   A.ncell_search = (cfg.ndt_search_method == 1) ? 1 : 7;
   A.compute_hessian = compute_hessian ? 1 : 0;
-  static const int even_split = getenv("B2R_NDT_EVEN") ? 1 : 0;
-  A.even_split = even_split;
-  const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);
-  B2R_CUDA(W.partials.reserve((size_t)(nb + 64) * kNdtAcc));  // derivative pass: [kNdtAcc][blocks rounded up to 32]; Hessian pass: [blocks][36]
-  A.partials = W.partials.p; A.out = W.h_out_dev; A.counter = W.d_counter; A.pairs = W.d_pairs;
+  const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);  // 128-point chunks of the source
+  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));  // derivative pass: [chunks][kNdtAcc]; Hessian pass: [blocks][36]
+  const unsigned ngroups = (nb + 31) / 32;
+  B2R_CUDA(W.grows.reserve((size_t)ngroups * kNdtAcc));
+  if (ngroups > W.gcount.cap) {
+    B2R_CUDA(W.gcount.reserve(ngroups));
+    B2R_CUDA(cudaMemsetAsync(W.gcount.p, 0, W.gcount.cap * sizeof(unsigned int), st));  // every launch leaves the counters at zero
+  }
+  A.partials = W.partials.p; A.grows = W.grows.p; A.gcount = W.gcount.p; A.queue = W.d_queue; A.qbase = 0;
+  A.out = W.h_out_dev; A.counter = W.d_counter; A.pairs = W.d_pairs;
   A.flag = W.h_flag_dev; A.seq = ++W.seq;
   if (hessian_only) {
     { TEL_BEGIN(W.tel, st);
@@ -878,9 +986,13 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   }
   { TEL_BEGIN(W.tel, st);  // W.d_pairs is zero here: allocated zeroed, and the last block of every pass resets it after reading it
     const unsigned ng = std::min(nb, ndt_resident_blocks(compute_hessian));
+    A.qbase = W.qnext;
+    W.qnext += (unsigned long long)nb + ng;  // every block draws tickets until its first one past the last chunk: nb + ng draws per launch
     if (compute_hessian) k_ndt_derivatives<true><<<ng, kNdtThreads, 0, st>>>(A);
     else k_ndt_derivatives<false><<<ng, kNdtThreads, 0, st>>>(A);
-    TEL_END(W.tel, KC_NDT_DERIV, 1, st); }
+    TEL_END(W.tel, KC_NDT_DERIV, 1, st);
+    if (cudaPeekAtLastError() != cudaSuccess) W.qnext = A.qbase;  // nothing ran: no ticket was drawn
+  }
   if (W.tel) W.tel->d2h += kNdtAcc * sizeof(double) + 8;
   B2R_CUDA(cudaGetLastError());
   int rc = wait_host_result(W.h_flag, A.seq, W.h_out, kNdtAcc, true, st);

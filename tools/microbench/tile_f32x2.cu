@@ -1,0 +1,127 @@
+// Micro-benchmark (development aid, not part of the product): cost per (lane, candidate) of the all-pairs 1-NN tile sweep
+//   v0  scalar float math, (d2, idx, pos) visitor with the `pass` predicate        (the round-2 k_pair_search loop)
+//   v1  scalar float math, one 64-bit (d2 bits << 32 | idx) key, pass folded into the start key
+//   v2  packed f32x2 math on a pair-interleaved leaf layout + the 64-bit key
+// and a bit-exactness check of v1 / v2 against v0.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tile_f32x2 tile_f32x2.cu
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float dist2(float qx, float qy, float qz, float x, float y, float z) {
+  const float dx = fsub(qx, x), dy = fsub(qy, y), dz = fsub(qz, z);
+  return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// square as fma(d, d, +0): ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would skip the
+// rounding of the product; an FFMA2 cannot be contracted into the following add, and d*d + (+0) == rn(d*d) for every d
+__device__ __forceinline__ u64 sq2(u64 a) { u64 r; const u64 z = 0ull; asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(z)); return r; }
+__device__ __forceinline__ u64 pack2(float lo, float hi) { return ((u64)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
+
+constexpr int kLeaf = 32;
+template <int V>
+__global__ void __launch_bounds__(128) k(const float4* __restrict__ sp, const float4* __restrict__ sp2, int nleaf, int reps, const float4* __restrict__ q,
+                                        float* od2, int* oidx) {
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  const float4 qq = q[gt];
+  const float qx = qq.x, qy = qq.y, qz = qq.z;
+  const bool pass = (gt % 7) != 3;
+  float bd2 = INFINITY; int bidx = 0x7fffffff, bpos = -1;
+  u64 bkey = 0x7f8000007fffffffull;
+  const u64 qx2 = pack2(qx, qx), qy2 = pack2(qy, qy), qz2 = pack2(qz, qz);
+  for (int r = 0; r < reps; r++) {
+    for (int l = 0; l < nleaf; l++) {
+      if (V == 0) {
+        const float4* lp = sp + l * kLeaf;
+#pragma unroll 8
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);
+          const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+          const int idx = __float_as_int(p.w);
+          const bool b = pass & ((d2 < bd2) | ((d2 == bd2) & (idx < bidx)));
+          bd2 = b ? d2 : bd2; bidx = b ? idx : bidx; bpos = b ? l * kLeaf + t : bpos;
+        }
+      } else if (V == 1) {
+        const float4* lp = sp + l * kLeaf;
+        u64 k = pass ? bkey : 0ull;
+#pragma unroll 8
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);
+          const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+          const u64 kq = ((u64)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+          k = kq < k ? kq : k;
+        }
+        bkey = pass ? k : bkey;
+      } else {
+        const float4* lp = sp2 + l * kLeaf;
+        u64 k = pass ? bkey : 0ull;
+#pragma unroll 8
+        for (int t = 0; t < kLeaf / 2; t++) {
+          const float4 a = __ldg(lp + 2 * t), b = __ldg(lp + 2 * t + 1);  // {x0,x1,y0,y1} {z0,z1,w0,w1}
+          const u64 dx = sub2(qx2, pack2(a.x, a.y)), dy = sub2(qy2, pack2(a.z, a.w)), dz = sub2(qz2, pack2(b.x, b.y));
+          const u64 s = add2(add2(sq2(dx), sq2(dy)), sq2(dz));
+          const u64 k0 = ((s & 0xffffffffull) << 32) | __float_as_uint(b.z);
+          const u64 k1 = (s & 0xffffffff00000000ull) | __float_as_uint(b.w);
+          k = k0 < k ? k0 : k;
+          k = k1 < k ? k1 : k;
+        }
+        bkey = pass ? k : bkey;
+      }
+    }
+  }
+  if (V == 0) { od2[gt] = bd2; oidx[gt] = bidx; if (bpos == -12345) od2[gt] = 0; }
+  else { od2[gt] = __uint_as_float((unsigned)(bkey >> 32)); oidx[gt] = (int)(unsigned)bkey; }
+}
+
+int main(int argc, char** argv) {
+  const int nleaf = 64, nthreads = 148 * 8 * 128, reps = argc > 1 ? atoi(argv[1]) : 40;
+  std::vector<float4> sp(nleaf * kLeaf), sp2(nleaf * kLeaf), q(nthreads);
+  srand(7);
+  auto rnd = []() { return (float)rand() / RAND_MAX; };
+  for (int i = 0; i < nleaf * kLeaf; i++) {
+    // a coarse lattice so that exact distance ties happen (index tie rule exercised); last leaf half padded
+    sp[i] = make_float4(floorf(rnd() * 16) * 0.25f, floorf(rnd() * 16) * 0.25f, floorf(rnd() * 8) * 0.25f, 0.f);
+    int idx = (i * 7919) % (nleaf * kLeaf);
+    if (i >= nleaf * kLeaf - 16) { sp[i] = make_float4(INFINITY, INFINITY, INFINITY, 0.f); idx = 0x7fffffff; }
+    sp[i].w = *reinterpret_cast<float*>(&idx);
+  }
+  for (int l = 0; l < nleaf; l++)
+    for (int j = 0; j < kLeaf / 2; j++) {
+      const float4 a = sp[l * kLeaf + 2 * j], b = sp[l * kLeaf + 2 * j + 1];
+      sp2[l * kLeaf + 2 * j] = make_float4(a.x, b.x, a.y, b.y);
+      sp2[l * kLeaf + 2 * j + 1] = make_float4(a.z, b.z, a.w, b.w);
+    }
+  for (int i = 0; i < nthreads; i++) q[i] = make_float4(floorf(rnd() * 33) * 0.125f, floorf(rnd() * 33) * 0.125f, rnd() * 2.f, 0.f);
+  float4 *dsp, *dsp2, *dq; float* dd2[3]; int* didx[3];
+  cudaMalloc(&dsp, sp.size() * 16); cudaMalloc(&dsp2, sp2.size() * 16); cudaMalloc(&dq, q.size() * 16);
+  for (int v = 0; v < 3; v++) { cudaMalloc(&dd2[v], nthreads * 4); cudaMalloc(&didx[v], nthreads * 4); }
+  cudaMemcpy(dsp, sp.data(), sp.size() * 16, cudaMemcpyHostToDevice); cudaMemcpy(dsp2, sp2.data(), sp2.size() * 16, cudaMemcpyHostToDevice);
+  cudaMemcpy(dq, q.data(), q.size() * 16, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int v = 0; v < 3; v++) {
+    float best = 1e30f;
+    for (int it = 0; it < 4; it++) {
+      cudaEventRecord(e0);
+      if (v == 0) k<0><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
+      if (v == 1) k<1><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
+      if (v == 2) k<2><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
+      cudaEventRecord(e1); cudaEventSynchronize(e1);
+      float ms; cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best) best = ms;
+    }
+    const double cand = (double)nthreads * reps * nleaf * kLeaf;
+    printf("v%d: %.3f ms, %.2f ps per lane-candidate, %.1f G lane-candidates/s  (%s)\n", v, best, best * 1e9 / cand, cand / best * 1e-6, cudaGetErrorString(cudaGetLastError()));
+  }
+  std::vector<float> h0(nthreads), h(nthreads); std::vector<int> i0(nthreads), ii(nthreads);
+  cudaMemcpy(h0.data(), dd2[0], nthreads * 4, cudaMemcpyDeviceToHost); cudaMemcpy(i0.data(), didx[0], nthreads * 4, cudaMemcpyDeviceToHost);
+  for (int v = 1; v < 3; v++) {
+    cudaMemcpy(h.data(), dd2[v], nthreads * 4, cudaMemcpyDeviceToHost); cudaMemcpy(ii.data(), didx[v], nthreads * 4, cudaMemcpyDeviceToHost);
+    long bad = 0;
+    for (int i = 0; i < nthreads; i++) bad += (memcmp(&h[i], &h0[i], 4) != 0) || (ii[i] != i0[i]);
+    printf("v%d vs v0: %ld mismatches of %d\n", v, bad, nthreads);
+  }
+  return 0;
+}
