@@ -17,6 +17,7 @@
 // bound > worst (strict) — equal-distance lower-index candidates stay reachable.  No cell quantisation is involved in the
 // decision logic (the Morton key only orders the points), so no representability argument is needed.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 // The warp-level code below is device code; tests/warp_harness.cpp also compiles it for the CPU on an emulated 32-lane warp
@@ -138,6 +139,48 @@ struct Nn1 {
   }
 #endif
 };
+
+// 1-NN visitor on ONE packed key (nn_key): the lexicographic (d2, index) rule is a single unsigned 64-bit compare, so the all-pairs
+// tile loop costs 2 ISETP + 2 SEL per candidate instead of FSETP.NEU + ISETP + FSETP.LT + PLOP3 + FSEL + SEL (+ SEL for the position);
+// the `pass` predicate is folded into the start key (key 0 beats everything) instead of being and-ed into every candidate's
+// decision.  No position is tracked: the caller maps the winning index through the target's pos_of table.  Same candidates, same
+// rule => the same answers as Nn1 (tests/warp_harness.cpp runs both on the emulated warp).
+struct Nn1K {
+  static constexpr int kTileLanes = 8;
+  static constexpr int kTileUnroll = 8;
+  static constexpr bool kTwoPhase = false;
+  static constexpr bool kKeyed = true;
+#ifdef B2R_KNN_PROFILE
+  int n_tile = 0, n_coop = 0, n_try = 0;
+#endif
+  unsigned long long key;  // kKeyInf = nothing yet
+  float lim;
+  B2R_HD void reset(float limit_) { key = kKeyInf; lim = limit_; }
+  B2R_HD void seed(float d2, int idx, int) { key = nn_key(d2, idx); }
+  B2R_HD float worst() const { return nn_key_d2(key); }
+  B2R_HD float limit() const { return lim; }
+  B2R_HD void visit(float d2, int idx, int) {
+    const unsigned long long kq = nn_key(d2, idx);  // padding = kKeyInf: never below any key
+    key = kq < key ? kq : key;
+  }
+  B2R_HD unsigned long long tile_begin(bool pass) const { return pass ? key : 0ull; }
+  B2R_HD void tile_end(bool pass, unsigned long long k) { key = pass ? k : key; }
+  B2R_HD float best_d2() const { return nn_key_d2(key); }
+  B2R_HD int best_idx() const { return (int)(unsigned int)(key & 0xffffffffull); }
+  B2R_HD bool found() const { return (unsigned int)(key & 0xffffffffull) != (unsigned int)kPadIdx; }
+#ifdef B2R_WARP_CODE
+  template <int C>
+  __device__ __forceinline__ void merge_copies() {
+#pragma unroll
+    for (int off = 32 / C; off < 32; off <<= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, off);
+      key = o < key ? o : key;
+    }
+  }
+#endif
+};
+template <class V, class = void> struct keyed_visitor : std::false_type {};
+template <class V> struct keyed_visitor<V, std::void_t<decltype(V::kKeyed)>> : std::integral_constant<bool, V::kKeyed> {};
 
 // host/device serial reference of the traversal for ONE query (used by tests/host_harness.cu and as documentation of the
 // pruning rule; the device path below makes the same per-lane decisions, only warp-wide)
@@ -290,10 +333,21 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
   if (__popc(mask) >= kTile) {
     if constexpr (C > 1) {
       const int t0 = (lane / Q) * (kLeaf / C);
+      if constexpr (keyed_visitor<Visitor>::value) {
+        unsigned long long k = v.tile_begin(pass);
 #pragma unroll
-      for (int t = 0; t < kLeaf / C; t++) {
-        const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
-        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+        for (int t = 0; t < kLeaf / C; t++) {
+          const float4 p = __ldg(lp + t0 + t);
+          const unsigned long long kq = nn_key(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w));
+          k = kq < k ? kq : k;
+        }
+        v.tile_end(pass, k);
+      } else {
+#pragma unroll
+        for (int t = 0; t < kLeaf / C; t++) {
+          const float4 p = __ldg(lp + t0 + t);  // C addresses per warp
+          v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t0 + t);
+        }
       }
       v.template merge_copies<C>();
     } else if constexpr (Visitor::kTwoPhase) {
@@ -321,10 +375,21 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
       // (a minimum-first variant — one sweep that keeps only the smallest distance, the exact (d2, index) sweep only when some lane can
       // improve — was measured: neutral on the 4-lane odometry search, 15 % slower on the 1-lane batch search, where some lane of
       // the 32 nearly always needs the second sweep: profiles/r02_n)
+      if constexpr (keyed_visitor<Visitor>::value) {
+        unsigned long long k = v.tile_begin(pass);
 #pragma unroll Visitor::kTileUnroll
-      for (int t = 0; t < kLeaf; t++) {
-        const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
-        v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);
+          const unsigned long long kq = nn_key(dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w));
+          k = kq < k ? kq : k;
+        }
+        v.tile_end(pass, k);
+      } else {
+#pragma unroll Visitor::kTileUnroll
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);  // same address on every lane: one broadcast transaction
+          v.visit_if(pass, dist2_f32(qx, qy, qz, p.x, p.y, p.z), idx_bits(p.w), l * kLeaf + t);  // padding = (+inf, kPadIdx): rejected by the visitor
+        }
       }
     }
     return true;

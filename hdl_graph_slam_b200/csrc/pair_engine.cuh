@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kLinThreads, B2R_SEARCH_MINBLOCKS) k_pair_sear
   const float4 pt = p.src.sp[s];
   const bool is_point = idx_bits(pt.w) != kPadIdx;
   float qx = 0.f, qy = 0.f, qz = 0.f;
-  Nn1 v;
+  Nn1K v;  // packed-key visitor: the position of the winner comes from the target's pos_of table afterwards
   v.reset(lim);
   bool active_q = false;
   int sp0 = -1;
@@ -315,15 +315,15 @@ __global__ void __launch_bounds__(kLinThreads, B2R_SEARCH_MINBLOCKS) k_pair_sear
   }
   int hint = -1;
   {
-    const bool good = sp0 >= 0 && (use_seed || v.bd2 < 1.0f);
+    const bool good = sp0 >= 0 && (use_seed || v.best_d2() < 1.0f);
     const unsigned hm = __ballot_sync(0xffffffffu, good);
     if (hm) hint = __shfl_sync(0xffffffffu, sp0, __fns(hm, 0, (__popc(hm) + 1) / 2)) >> 5;
   }
   bvh_group_search<C>(tgt, qx, qy, qz, active_q, v, -1, hint);  // all 32 lanes participate
   if (is_point && writer) {
-    const bool valid = active_q && (v.best_pos >= 0) && ((double)v.best_d2() < thr2);
+    const bool valid = active_q && v.found() && ((double)v.best_d2() < thr2);
     if (!fit_search) p.corr[wset][idx_bits(pt.w)] = valid ? v.best_idx() : -1;
-    p.cpos[wset][s] = valid ? v.best_pos : -1;
+    p.cpos[wset][s] = valid ? p.tgt_pos_of[v.best_idx()] : -1;
     p.d2[s] = v.best_d2();
   }
 }

@@ -45,7 +45,12 @@ struct EmuKnn {
   }
 };
 
-template <int C>
+// V = Nn1 (float distance + index + position) or Nn1K (one packed key, what k_pair_search carries)
+static bool nn_found(const Nn1& v) { return v.best_pos >= 0; }
+static bool nn_found(const Nn1K& v) { return v.found(); }
+static bool nn_pos_ok(const HostBvh& T, const Nn1& v, int want) { return idx_bits(T.sp[v.best_pos].w) == want; }
+static bool nn_pos_ok(const HostBvh&, const Nn1K&, int) { return true; }
+template <int C, class V>
 static long run_1nn(const HostBvh& T, const HostBvh& S, int n_src, const float* Tf, int n_groups, float lim, int variant, const std::vector<float>& tgt_pts,
                     int n_tgt, long* checked) {
   constexpr int Q = 32 / C;
@@ -87,9 +92,9 @@ static long run_1nn(const HostBvh& T, const HostBvh& S, int n_src, const float* 
         seed_pos[l] = sp;
       }
     }
-    Nn1 res[32];
+    V res[32];
     wemu::run_warp((unsigned)(gi % 4) * 32, [&](int l) {
-      Nn1 v;
+      V v;
       v.reset(lim);
       int sp0 = seed_pos[l];
       if (act[l] && sp0 >= 0) {
@@ -108,11 +113,11 @@ static long run_1nn(const HostBvh& T, const HostBvh& S, int n_src, const float* 
       if (!act[l]) continue;
       (*checked)++;
       const bool want_valid = od[l] < lim;
-      const bool got_valid = res[l].best_pos >= 0 && res[l].best_d2() < lim;
+      const bool got_valid = nn_found(res[l]) && res[l].best_d2() < lim;
       bool ok = want_valid == got_valid;
-      if (ok && want_valid) ok = res[l].best_idx() == oi[l] && res[l].best_d2() == od[l] && idx_bits(T.sp[res[l].best_pos].w) == oi[l];
+      if (ok && want_valid) ok = res[l].best_idx() == oi[l] && res[l].best_d2() == od[l] && nn_pos_ok(T, res[l], oi[l]);
       // copies of one query must agree with each other exactly
-      if (ok && C > 1) { const Nn1& a = res[l & (Q - 1)]; ok = a.best_idx() == res[l].best_idx() && a.best_d2() == res[l].best_d2(); }
+      if (ok && C > 1) { const V& a = res[l & (Q - 1)]; ok = a.best_idx() == res[l].best_idx() && a.best_d2() == res[l].best_d2(); }
       if (!ok) {
         if (bad < 5) printf("1nn mismatch C=%d variant=%d group=%d lane=%d: got (%g,%d) want (%g,%d)\n", C, variant, gi, l, res[l].best_d2(), res[l].best_idx(), od[l], oi[l]);
         bad++;
@@ -162,7 +167,10 @@ template <int C>
 static long all_1nn(const HostBvh& T, const HostBvh& S, int n_src, const float* Tf, int groups, const std::vector<float>& tp, int nt, long* checked) {
   long bad = 0;
   for (int variant = 0; variant <= 4; variant++)
-    for (float lim : {INFINITY, 6.25f}) bad += run_1nn<C>(T, S, n_src, Tf, groups, lim, variant, tp, nt, checked);
+    for (float lim : {INFINITY, 6.25f}) {
+      bad += run_1nn<C, Nn1>(T, S, n_src, Tf, groups, lim, variant, tp, nt, checked);
+      bad += run_1nn<C, Nn1K>(T, S, n_src, Tf, groups, lim, variant, tp, nt, checked);
+    }
   return bad;
 }
 
