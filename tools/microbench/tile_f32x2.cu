@@ -2,6 +2,7 @@
 //   v0  scalar float math, (d2, idx, pos) visitor with the `pass` predicate        (the round-2 k_pair_search loop)
 //   v1  scalar float math, one 64-bit (d2 bits << 32 | idx) key, pass folded into the start key
 //   v2  packed f32x2 math on a pair-interleaved leaf layout + the 64-bit key
+//   v3  v1 with every FADD / FMUL written as an FFMA with an immediate operand (same roundings)
 // and a bit-exactness check of v1 / v2 against v0.   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tile_f32x2 tile_f32x2.cu
 #include <cstdio>
 #include <cstdlib>
@@ -22,6 +23,14 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 sq2(u64 a) { u64 r; const u64 z = 0ull; asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(a), "l"(z)); return r; }
 __device__ __forceinline__ u64 pack2(float lo, float hi) { return ((u64)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
 
+// the same roundings through FFMA with an immediate operand: a + b == fma(a, 1, b), a * b == fma(a, b, -0)  (exact identities)
+__device__ __forceinline__ float fadd_i(float a, float b) { float r; asm("fma.rn.f32 %0, %1, 0f3F800000, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fsub_i(float a, float b) { float r; asm("fma.rn.f32 %0, %1, 0fBF800000, %2;" : "=f"(r) : "f"(b), "f"(a)); return r; }
+__device__ __forceinline__ float fmul_i(float a, float b) { float r; asm("fma.rn.f32 %0, %1, %2, 0f80000000;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float dist2_i(float qx, float qy, float qz, float x, float y, float z) {
+  const float dx = fsub_i(qx, x), dy = fsub_i(qy, y), dz = fsub_i(qz, z);
+  return fadd_i(fadd_i(fmul_i(dx, dx), fmul_i(dy, dy)), fmul_i(dz, dz));
+}
 constexpr int kLeaf = 32;
 template <int V>
 __global__ void __launch_bounds__(128) k(const float4* __restrict__ sp, const float4* __restrict__ sp2, int nleaf, int reps, const float4* __restrict__ q,
@@ -52,6 +61,17 @@ __global__ void __launch_bounds__(128) k(const float4* __restrict__ sp, const fl
         for (int t = 0; t < kLeaf; t++) {
           const float4 p = __ldg(lp + t);
           const float d2 = dist2(qx, qy, qz, p.x, p.y, p.z);
+          const u64 kq = ((u64)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
+          k = kq < k ? kq : k;
+        }
+        bkey = pass ? k : bkey;
+      } else if (V == 3) {
+        const float4* lp = sp + l * kLeaf;
+        u64 k = pass ? bkey : 0ull;
+#pragma unroll 8
+        for (int t = 0; t < kLeaf; t++) {
+          const float4 p = __ldg(lp + t);
+          const float d2 = dist2_i(qx, qy, qz, p.x, p.y, p.z);
           const u64 kq = ((u64)__float_as_uint(d2) << 32) | (unsigned)__float_as_int(p.w);
           k = kq < k ? kq : k;
         }
@@ -96,19 +116,20 @@ int main(int argc, char** argv) {
       sp2[l * kLeaf + 2 * j + 1] = make_float4(a.z, b.z, a.w, b.w);
     }
   for (int i = 0; i < nthreads; i++) q[i] = make_float4(floorf(rnd() * 33) * 0.125f, floorf(rnd() * 33) * 0.125f, rnd() * 2.f, 0.f);
-  float4 *dsp, *dsp2, *dq; float* dd2[3]; int* didx[3];
+  float4 *dsp, *dsp2, *dq; float* dd2[4]; int* didx[4];
   cudaMalloc(&dsp, sp.size() * 16); cudaMalloc(&dsp2, sp2.size() * 16); cudaMalloc(&dq, q.size() * 16);
-  for (int v = 0; v < 3; v++) { cudaMalloc(&dd2[v], nthreads * 4); cudaMalloc(&didx[v], nthreads * 4); }
+  for (int v = 0; v < 4; v++) { cudaMalloc(&dd2[v], nthreads * 4); cudaMalloc(&didx[v], nthreads * 4); }
   cudaMemcpy(dsp, sp.data(), sp.size() * 16, cudaMemcpyHostToDevice); cudaMemcpy(dsp2, sp2.data(), sp2.size() * 16, cudaMemcpyHostToDevice);
   cudaMemcpy(dq, q.data(), q.size() * 16, cudaMemcpyHostToDevice);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int v = 0; v < 3; v++) {
+  for (int v = 0; v < 4; v++) {
     float best = 1e30f;
     for (int it = 0; it < 4; it++) {
       cudaEventRecord(e0);
       if (v == 0) k<0><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
       if (v == 1) k<1><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
       if (v == 2) k<2><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
+      if (v == 3) k<3><<<nthreads / 128, 128>>>(dsp, dsp2, nleaf, reps, dq, dd2[v], didx[v]);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1); if (it && ms < best) best = ms;
     }
@@ -117,7 +138,7 @@ int main(int argc, char** argv) {
   }
   std::vector<float> h0(nthreads), h(nthreads); std::vector<int> i0(nthreads), ii(nthreads);
   cudaMemcpy(h0.data(), dd2[0], nthreads * 4, cudaMemcpyDeviceToHost); cudaMemcpy(i0.data(), didx[0], nthreads * 4, cudaMemcpyDeviceToHost);
-  for (int v = 1; v < 3; v++) {
+  for (int v = 1; v < 4; v++) {
     cudaMemcpy(h.data(), dd2[v], nthreads * 4, cudaMemcpyDeviceToHost); cudaMemcpy(ii.data(), didx[v], nthreads * 4, cudaMemcpyDeviceToHost);
     long bad = 0;
     for (int i = 0; i < nthreads; i++) bad += (memcmp(&h[i], &h0[i], 4) != 0) || (ii[i] != i0[i]);
