@@ -82,23 +82,59 @@ def peaks():
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    """nvidia-smi clocks / throttle reasons under the benchmark's load.  nvidia-smi needs ~0.1-0.3 s to deliver its first sample and the
+    default timed region is shorter than that (20 steps of 0.4 ms), so the caller (1) starts the sampler, (2) calls begin() when the timed
+    region starts, (3) after the timed region keeps issuing UNTIMED steps of the same workload until `hold_needed()` says enough wall time
+    has passed under load, (4) stop() keeps the samples whose timestamps lie between begin() and the end of the hold.  The metric is
+    never taken from the hold steps; `window` in the result says how long the sampled window was and how many extra steps it held."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    MIN_WINDOW_S = 0.7
 
     def __init__(self, dev):
         self.dev, self.p, self.path = dev, None, f"/tmp/b2r_clocks_{os.getpid()}.csv"
+        self.t0 = self.t1 = None
+        self.extra_steps = 0
 
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.dev)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.dev)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.p = None
+        self.begin()
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def hold_needed(self):
+        """True while the window under load is still too short for nvidia-smi to have sampled it"""
+        return self.p is not None and self.t0 is not None and (time.time() - self.t0) < self.MIN_WINDOW_S
+
+    def hold(self, body, sync, max_steps=100000):
+        """body(k): one more untimed step of the same workload; sync(): drain the device"""
+        k = 0
+        while self.hold_needed() and k < max_steps:
+            body(k)
+            k += 1
+            if (k & 15) == 0:
+                sync()
+        sync()
+        self.extra_steps += k
+
+    @staticmethod
+    def _ts(txt):
+        import datetime
+        try:
+            return datetime.datetime.strptime(txt.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:  # noqa: BLE001
+            return None
 
     def stop(self):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        self.t1 = time.time()
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -110,6 +146,9 @@ class ClockSampler:
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
+            ts = self._ts(c[0])
+            if ts is not None and self.t0 is not None and not (self.t0 - 0.02 <= ts <= self.t1 + 0.02):
+                continue  # taken before the timed region started
             try:
                 sm.append(float(c[1])); mx.append(float(c[2]))
             except ValueError:
@@ -118,7 +157,9 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm),
+                "window": f"{self.t1 - self.t0:.2f} s under load = the timed region + {self.extra_steps} untimed steps of the same workload "
+                          "(nvidia-smi delivers a sample every 50 ms after a ~0.2 s start-up; the timed region alone can be shorter than that)"}
 
 
 def host_threads():
@@ -404,7 +445,6 @@ def run_b200(args, wl, rank, world, local_rank):
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        clocks = sampler.stop() if (rank == 0 and arm == "value") else None
         ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         per_rank = [ms]
@@ -416,6 +456,10 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         stats = reg.getStats()
         reg.setProfiling(False)
+        clocks = None
+        if rank == 0 and arm == "value":  # keep the same chain running (untimed) until nvidia-smi has sampled the load, then read the clocks
+            sampler.hold(lambda k: step(W + 1 + (k % K)), reg.synchronize)
+            clocks = sampler.stop()
         results[arm] = dict(ms=float(t.item()), per_rank_ms=per_rank, wall_ms=wall * 1e3, stats=stats, iters=iters, conv=conv, kf=kf, clocks=clocks,
                             last_odom=st["odom"])
         odo.close()

@@ -58,7 +58,10 @@ def _timed(torch, dist, dev, world, stream, K, body, sampler=None):
     e1.record(stream)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if sampler else None
+    clocks = None
+    if sampler:  # untimed steps of the same workload until nvidia-smi has sampled the load (bench.ClockSampler)
+        sampler.hold(lambda k: body(k % K), torch.cuda.synchronize)
+        clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -191,6 +191,7 @@ extern "C" int b2r_create(const b2r_config* cfg, b2r_handle** out) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (getenv("B2R_NO_PRIORITY")) lo = hi = 0;
+    if (getenv("B2R_PREFETCH_PRIORITY")) { const int t = lo; lo = hi; hi = t; }  // diagnostic: the prefetch path outranks the align chain
     if (cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, hi) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
     if (cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail(B2R_ECUDA, "cudaStreamCreate failed"));
   }

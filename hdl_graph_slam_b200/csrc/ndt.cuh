@@ -241,6 +241,7 @@ constexpr int kNdtThreads = 128;
 constexpr int kNdtAccA = 28;   // first sweep over a point's cells: score, g[6], upper triangle of H (21)
 constexpr int kNdtAccB = 15;   // second sweep: strict lower triangle of H (ndt_omp's float32 Hessian is NOT symmetric to the last bit)
 constexpr int kNdtAcc = kNdtAccA + kNdtAccB;
+constexpr int kNdtSlots = 320; // voxel records staged per block (20 KB)
 
 struct NdtArgs {
   const float4* src;           // the source's Hilbert-sorted points (bvh.cuh): a block's 128 points are spatial neighbours
@@ -296,93 +297,66 @@ __device__ __forceinline__ int ndt_find(const unsigned long long* __restrict__ t
 // stages the 64-byte records in shared memory, and the per-(point, cell) loop then runs without a global load.  Blocks
 // whose points are spread too wide for the staging area (far-field leaves, jumps of the curve) fall back to direct lookups.
 //
-// Work distribution and summation order (round 2, late): every WARP is autonomous.  It takes a 32-point sub-chunk (one leaf of the
-// Hilbert-sorted source; the first one is its own index in the grid, the following ones come from a ticket counter), stages the voxel
-// records of its own little box of cells, accumulates, and reduces to the sub-chunk's OWN row of 43 float64 sums — no block barrier
-// anywhere, so a warp never waits for the slowest of its block (ncu on the 128-point block version: barrier 1.35 of 6.7 stall
-// cycles per issued instruction, slowest SM sub-partition 72 k cycles against a mean of 53 k: the tail is one 128-point chunk).
-// The rows are added by a fixed three-level tree (32 rows -> group row -> super row -> result), each node by whichever warp
-// delivers its last input: the sums do not depend on which warp processed which sub-chunk — bitwise reproducible.
-// (History: static persistent grid 55 us per pass at 131 072 points; block-level tickets + two-level tree 37 us; profiles/r02_t, r02_u.)
-constexpr int kNdtWarpSlots = 120;  // voxel records staged per warp (7.5 KB)
-constexpr int kNdtWRow = 34;        // float64 elements per shared-memory row of a warp's per-lane values (32 + 2: conflict-free half-warps)
-constexpr int kNdtWarps = kNdtThreads / 32;
+// Work distribution and summation order (round 2, late): the 128-point CHUNKS of the source are handed out through a ticket
+// counter (a resident block takes the next chunk when it is done with its own), every chunk reduces to its OWN row of 43
+// float64 sums, and the rows are added by a fixed two-level tree (32 chunk rows -> one group row by whichever block completes
+// the group, group rows -> result by whichever block completes the last group).  The sums therefore do not depend on which
+// block processed which chunk — bitwise reproducible — while no SM waits for a statically assigned heavy block (ncu, static
+// persistent grid: slowest SM sub-partition 99 k cycles against a mean of 56 k, a quarter of it the single last block adding 592
+// rows of partials in 38 dependent memory round trips; profiles/r02_t).
+// (Measured and dropped, profiles/r02_w: fully warp-autonomous 32-point sub-chunks with warp tickets and a three-level tree — no block
+// barrier at all — 40.1 us per pass against 36.9 us for this version: the barrier stalls turn into long-scoreboard and fence stalls, and
+// the tail does not shrink because it is set by work units per resident slot (1.73 in both versions), not by the unit's size.)
+constexpr int kNdtRow = 136;  // float64 elements per shared-memory row of per-thread values (128 + 8: half-warps hit distinct banks)
 
-// sums of R (<= 16) rows of 32 per-lane values -> dst[0..R): lane (row = lane >> 1, part = lane & 1) adds the elements part,
-// part + 2, ... of its row in ascending order, one butterfly level joins the two parts.  The order is fixed.
-__device__ __forceinline__ void ndt_wrows_sum(const double* rows, int R, double* dst, int lane) {
-  const int row = lane >> 1, part = lane & 1;
+// sums of R (<= 16) rows of 128 per-thread values -> dst[0..R): thread (row = tid >> 3, part = tid & 7) adds the elements part,
+// part + 8, ... of its row in ascending order, three butterfly levels join the 8 parts.  The order is fixed.
+__device__ __forceinline__ void ndt_rows_sum(const double* rows, int R, double* dst) {
+  const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
   double s = 0.0;
   if (row < R) {
-    const double* p = rows + row * kNdtWRow + part;
+    const double* p = rows + row * kNdtRow + part;
 #pragma unroll
-    for (int j = 0; j < 16; j++) s += p[2 * j];
+    for (int j = 0; j < 16; j++) s += p[8 * j];
   }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   if (row < R && part == 0) dst[row] = s;
 }
 
-// one node of the summation tree: adds `cnt` (<= 32) consecutive rows of kNdtAcc values starting at `rows` in ascending order;
-// lane l returns value l in a and value l + 32 in b (NV values carry information).  All loads of a value are independent.
-template <int NV>
-__device__ __forceinline__ void ndt_tree_node(const double* rows, int cnt, int lane, double& a, double& b) {
-  a = 0.0; b = 0.0;
-  if (lane < NV) {
-    double t[32];
-#pragma unroll
-    for (int u = 0; u < 32; u++) t[u] = (u < cnt) ? __ldcg(rows + (size_t)u * kNdtAcc + lane) : 0.0;
-#pragma unroll
-    for (int u = 0; u < 32; u++) a += t[u];
-  }
-  if (NV > 32 && lane + 32 < NV) {
-    double t[32];
-#pragma unroll
-    for (int u = 0; u < 32; u++) t[u] = (u < cnt) ? __ldcg(rows + (size_t)u * kNdtAcc + 32 + lane) : 0.0;
-#pragma unroll
-    for (int u = 0; u < 32; u++) b += t[u];
-  }
-}
-
-// lane 0 announces one delivered input of a tree node; true (on every lane) if it was the node's last one
-__device__ __forceinline__ bool ndt_tree_arrive(unsigned int* counter, int expected, int lane) {
-  __syncwarp();  // the row was written by several lanes
-  unsigned int closes = 0;
-  if (lane == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(counter, 1u);
-    closes = t == (unsigned int)(expected - 1);
-    if (closes) *counter = 0;  // every input is in: ready for the next launch
-  }
-  closes = __shfl_sync(0xffffffffu, closes, 0);
-  if (closes) __threadfence();
-  return closes != 0;
-}
-
 template <bool HESS>
 __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid_constant__ NdtArgs A) {
-  __shared__ __align__(16) NdtCell s_cell[kNdtWarps][kNdtWarpSlots];  // staged voxel records; after the pair loop: rows of the register sums
-  __shared__ double s_low[kNdtWarps][kNdtAccB * kNdtWRow];           // strict lower triangle of H: one float64 column per lane (no conflicts, no sync)
-  static_assert(sizeof(NdtCell) * kNdtWarpSlots >= sizeof(double) * (14 * kNdtWRow + kNdtAcc), "the reduction rows reuse the staging area");
+  __shared__ __align__(16) NdtCell s_cell[kNdtSlots];  // staged voxel records; after the pair loop: rows of the register sums
+  __shared__ double s_low[kNdtAccB][kNdtRow];          // strict lower triangle of H: one float64 column per thread (no conflicts, no sync)
+  __shared__ double s_fin[kNdtAcc];
+  __shared__ int s_box[6];
+  __shared__ int s_chunk, s_role;
+  static_assert(sizeof(NdtCell) * kNdtSlots >= sizeof(double) * 14 * kNdtRow, "the reduction rows reuse the staging area");
   constexpr int NV = HESS ? kNdtAcc : 7;  // values that carry information (score + gradient without the Hessian)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  NdtCell* const cell = s_cell[warp];
-  double* const slow = s_low[warp];
-  double* const tile = reinterpret_cast<double*>(cell);
+  const int lane = threadIdx.x & 31;
   const VoxGeom V = *A.geom;
-  const int nsub = A.n_sorted / kLeaf;  // n_sorted is a multiple of 1024
-  const int nwarps = (int)gridDim.x * kNdtWarps;
+  const int nchunks = A.n_sorted / kNdtThreads;  // n_sorted is a multiple of 1024
   const int p1 = A.n_sorted;
-  for (int sub = (int)blockIdx.x * kNdtWarps + warp; sub < nsub;) {
+  for (;;) {
+  if (threadIdx.x == 0) s_chunk = (int)(atomicAdd(A.queue, 1ull) - A.qbase);  // tickets of this launch start at qbase (ndt_run_pass)
+  __syncthreads();
+#ifdef B2R_NDT_STRIDE  // experiment: visit the chunks in a scattered order (heavy regions of the Hilbert order spread over the pass)
+  const int chunk = s_chunk >= nchunks ? s_chunk : (int)(((long long)s_chunk * B2R_NDT_STRIDE) % nchunks);
+#else
+  const int chunk = s_chunk;
+#endif
+  if (chunk >= nchunks) break;  // block-uniform
   double acc[kNdtAccA];
 #pragma unroll
   for (int k = 0; k < kNdtAccA; k++) acc[k] = 0.0;
   if (HESS) {
 #pragma unroll
-    for (int q = 0; q < kNdtAccB; q++) slow[q * kNdtWRow + lane] = 0.0;
+    for (int q = 0; q < kNdtAccB; q++) s_low[q][threadIdx.x] = 0.0;
   }
   unsigned int npairs = 0;
-  const int base = sub * kLeaf;
-  const int s = base + lane;
+  const int base = chunk * kNdtThreads;
+  const int s = base + threadIdx.x;
   float4 pt = make_float4(0.f, 0.f, 0.f, bits_idx(kPadIdx));
   if (s < p1) pt = A.src[s];
   const float x = pt.x, y = pt.y, z = pt.z;
@@ -399,31 +373,40 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
       if (fabsf(fi) < 1.0e9f && fabsf(fj) < 1.0e9f && fabsf(fk) < 1.0e9f) { ci = (int)fi; cj = (int)fj; ck = (int)fk; valid = true; }
     }
   }
-  // ---- the warp's box of base cells (+-1 for the face neighbours)
-  const int lo0 = __reduce_min_sync(0xffffffffu, valid ? ci : 0x7fffffff), lo1 = __reduce_min_sync(0xffffffffu, valid ? cj : 0x7fffffff),
-            lo2 = __reduce_min_sync(0xffffffffu, valid ? ck : 0x7fffffff);
-  const int hi0 = __reduce_max_sync(0xffffffffu, valid ? ci : (int)0x80000000), hi1 = __reduce_max_sync(0xffffffffu, valid ? cj : (int)0x80000000),
-            hi2 = __reduce_max_sync(0xffffffffu, valid ? ck : (int)0x80000000);
-  const bool any = lo0 <= hi0;
-  const int bx0 = lo0 - 1, by0 = lo1 - 1, bz0 = lo2 - 1;
-  const long long ex = any ? (long long)hi0 - lo0 + 3 : 0, ey = any ? (long long)hi1 - lo1 + 3 : 0, ez = any ? (long long)hi2 - lo2 + 3 : 0;
-  const bool staged = any && ex <= kNdtWarpSlots && ey <= kNdtWarpSlots && ez <= kNdtWarpSlots && ex * ey * ez <= kNdtWarpSlots;
+  // ---- the block's box of base cells (+-1 for the face neighbours)
+  if (threadIdx.x < 6) s_box[threadIdx.x] = threadIdx.x < 3 ? 0x7fffffff : (int)0x80000000;
+  __syncthreads();
+  {
+    int lo0 = valid ? ci : 0x7fffffff, lo1 = valid ? cj : 0x7fffffff, lo2 = valid ? ck : 0x7fffffff;
+    int hi0 = valid ? ci : (int)0x80000000, hi1 = valid ? cj : (int)0x80000000, hi2 = valid ? ck : (int)0x80000000;
+    lo0 = __reduce_min_sync(0xffffffffu, lo0); lo1 = __reduce_min_sync(0xffffffffu, lo1); lo2 = __reduce_min_sync(0xffffffffu, lo2);
+    hi0 = __reduce_max_sync(0xffffffffu, hi0); hi1 = __reduce_max_sync(0xffffffffu, hi1); hi2 = __reduce_max_sync(0xffffffffu, hi2);
+    if (lane == 0 && lo0 <= hi0) {
+      atomicMin(&s_box[0], lo0); atomicMin(&s_box[1], lo1); atomicMin(&s_box[2], lo2);
+      atomicMax(&s_box[3], hi0); atomicMax(&s_box[4], hi1); atomicMax(&s_box[5], hi2);
+    }
+  }
+  __syncthreads();
+  const bool any = s_box[0] <= s_box[3];
+  const int bx0 = s_box[0] - 1, by0 = s_box[1] - 1, bz0 = s_box[2] - 1;
+  const long long ex = any ? (long long)s_box[3] - s_box[0] + 3 : 0, ey = any ? (long long)s_box[4] - s_box[1] + 3 : 0, ez = any ? (long long)s_box[5] - s_box[2] + 3 : 0;
+  const bool staged = any && ex <= kNdtSlots && ey <= kNdtSlots && ez <= kNdtSlots && ex * ey * ez <= kNdtSlots;
   const int dx = (int)ex, dxy = (int)(ex * ey);
   if (staged) {
     const int vol = dxy * (int)ez;
-    for (int slot = lane; slot < vol; slot += 32) {
+    for (int slot = threadIdx.x; slot < vol; slot += blockDim.x) {
       const int cz = slot / dxy, r = slot - cz * dxy, cy = r / dx, cx = r - cy * dx;
       const int pos = ndt_find(A.table, A.mask, V, bx0 + cx, by0 + cy, bz0 + cz);
       if (pos >= 0) {
         const uint4* g = reinterpret_cast<const uint4*>(A.cells + pos);
-        uint4* d = reinterpret_cast<uint4*>(&cell[slot]);
+        uint4* d = reinterpret_cast<uint4*>(&s_cell[slot]);
         d[0] = __ldg(g); d[1] = __ldg(g + 1); d[2] = __ldg(g + 2); d[3] = __ldg(g + 3);
       } else {
-        cell[slot].npts = -1;
+        s_cell[slot].npts = -1;
       }
     }
   }
-  __syncwarp();
+  __syncthreads();
   if (valid) {
     bool have_pd = false;
     float j13 = 0, j23 = 0, j04 = 0, j14 = 0, j24 = 0, j05 = 0, j15 = 0, j25 = 0;
@@ -433,7 +416,7 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
       const int cx = ci + c_off7[c][0], cy = cj + c_off7[c][1], cz = ck + c_off7[c][2];
       const NdtCell* L;
       if (staged) {
-        L = &cell[(cx - bx0) + (cy - by0) * dx + (cz - bz0) * dxy];
+        L = &s_cell[(cx - bx0) + (cy - by0) * dx + (cz - bz0) * dxy];
       } else {
         const int pos = ndt_find(A.table, A.mask, V, cx, cy, cz);
         if (pos < 0) continue;
@@ -516,74 +499,98 @@ __global__ void __launch_bounds__(kNdtThreads, 4) k_ndt_derivatives(const __grid
             u = fadd(u, pj);
             const double w = (double)fmul(exv, u);
             if (jj >= ii) { acc[hk] += w; hk++; }                     // upper triangle + diagonal: registers
-            else { slow[lk * kNdtWRow + lane] += w; lk++; }          // strict lower triangle: this lane's shared-memory column
+            else { s_low[lk][threadIdx.x] += w; lk++; }              // strict lower triangle: this thread's shared-memory column
           }
         }
 #undef B2R_CJ
       }
     }
   }
-  __syncwarp();  // the pair loop is over: the staging area becomes the reduction rows
-  // pair count (integer, exact): one atomic per sub-chunk
+  __syncthreads();  // the pair loop is over: s_cell becomes the reduction rows
+  // pair count (integer, exact) through a warp reduction + one atomic per warp
   npairs = __reduce_add_sync(0xffffffffu, npairs);
   if (lane == 0 && npairs) atomicAdd(A.pairs, (unsigned long long)npairs);
-  // ---- this sub-chunk's row of sums
-  double* my_row = A.partials + (size_t)sub * kNdtAcc;
+  // ---- this chunk's row of sums
+  double* tile = reinterpret_cast<double*>(s_cell);
+  double* my_row = A.partials + (size_t)chunk * kNdtAcc;
 #pragma unroll
-  for (int k = 0; k < 14; k++) tile[k * kNdtWRow + lane] = acc[k];
-  __syncwarp();
-  ndt_wrows_sum(tile, HESS ? 14 : 7, my_row, lane);
+  for (int k = 0; k < 14; k++) tile[k * kNdtRow + threadIdx.x] = acc[k];
+  __syncthreads();
+  ndt_rows_sum(tile, HESS ? 14 : 7, my_row);
   if (HESS) {
-    __syncwarp();
+    __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 14; k++) tile[k * kNdtWRow + lane] = acc[14 + k];
-    __syncwarp();
-    ndt_wrows_sum(tile, 14, my_row + 14, lane);
-    ndt_wrows_sum(slow, kNdtAccB, my_row + kNdtAccA, lane);
+    for (int k = 0; k < 14; k++) tile[k * kNdtRow + threadIdx.x] = acc[14 + k];
+    __syncthreads();
+    ndt_rows_sum(tile, 14, my_row + 14);
+    ndt_rows_sum(&s_low[0][0], kNdtAccB, my_row + kNdtAccA);
   }
-  // ---- fixed three-level tree: 32 sub-chunk rows -> group row, 32 group rows -> super row, super rows -> result
-  const int ngroups = (nsub + 31) >> 5, nsuper = (ngroups + 31) >> 5;
-  const int g = sub >> 5;
-  if (ndt_tree_arrive(A.gcount + g, min(32, nsub - (g << 5)), lane)) {
-    double a, b;
-    ndt_tree_node<NV>(A.partials + (size_t)(g << 5) * kNdtAcc, min(32, nsub - (g << 5)), lane, a, b);
-    double* grow = A.grows + (size_t)g * kNdtAcc;
-    if (lane < NV) grow[lane] = a;
-    if (lane + 32 < NV) grow[32 + lane] = b;
-    const int sg = g >> 5;
-    if (ndt_tree_arrive(A.gcount + ngroups + sg, min(32, ngroups - (sg << 5)), lane)) {
-      ndt_tree_node<NV>(A.grows + (size_t)(sg << 5) * kNdtAcc, min(32, ngroups - (sg << 5)), lane, a, b);
-      double* srow = A.grows + (size_t)(ngroups + sg) * kNdtAcc;
-      if (lane < NV) srow[lane] = a;
-      if (lane + 32 < NV) srow[32 + lane] = b;
-      if (ndt_tree_arrive(A.counter, nsuper, lane)) {  // the last super row is in: add them in ascending order and publish
-        double fa = 0.0, fb = 0.0;
-        for (int r0 = 0; r0 < nsuper; r0 += 32) {
-          ndt_tree_node<NV>(A.grows + (size_t)(ngroups + r0) * kNdtAcc, min(32, nsuper - r0), lane, a, b);
-          fa += a; fb += b;
+  __syncthreads();  // the row is written (by several threads); s_cell / s_low / s_box are free for the next chunk
+  // ---- fixed two-level tree over the chunk rows
+  const int g = chunk >> 5;
+  const int gsize = min(32, nchunks - (g << 5));
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(A.gcount + g, 1u);
+    const bool closes = t == (unsigned int)(gsize - 1);
+    if (closes) A.gcount[g] = 0;  // all increments of this group are in: ready for the next launch
+    s_role = closes ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_role) {  // block-uniform: this block completed group g and adds its rows in ascending chunk order
+    __threadfence();
+    if (threadIdx.x < NV) {
+      const double* col = A.partials + (size_t)(g << 5) * kNdtAcc + threadIdx.x;
+      double t[32];
+#pragma unroll
+      for (int u = 0; u < 32; u++) t[u] = (u < gsize) ? __ldcg(col + (size_t)u * kNdtAcc) : 0.0;  // 32 independent loads: one round trip
+      double sum = 0.0;
+#pragma unroll
+      for (int u = 0; u < 32; u++) sum += t[u];
+      A.grows[(size_t)g * kNdtAcc + threadIdx.x] = sum;
+    }
+    __syncthreads();
+    const unsigned int ngroups = (unsigned int)((nchunks + 31) >> 5);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int t2 = atomicAdd(A.counter, 1u);
+      const bool last = t2 == ngroups - 1;
+      if (last) *A.counter = 0;
+      s_role = last ? 2 : 0;
+    }
+    __syncthreads();
+    if (s_role == 2) {  // the last group is in: add the group rows in ascending order and publish
+      __threadfence();
+      if (threadIdx.x < kNdtAcc) {
+        double sum = 0.0;
+        if (threadIdx.x < NV) {
+          const double* col = A.grows + threadIdx.x;
+          unsigned int r = 0;
+          for (; r + 32 <= ngroups; r += 32) {
+            double t[32];
+#pragma unroll
+            for (int u = 0; u < 32; u++) t[u] = __ldcg(col + (size_t)(r + u) * kNdtAcc);
+#pragma unroll
+            for (int u = 0; u < 32; u++) sum += t[u];
+          }
+          for (; r < ngroups; r++) sum += __ldcg(col + (size_t)r * kNdtAcc);
         }
-        double* fin = tile + 14 * kNdtWRow;  // kNdtAcc values behind the reduction rows
-        A.out[lane] = fa; fin[lane] = fa;
-        if (lane + 32 < kNdtAcc) { A.out[32 + lane] = fb; fin[32 + lane] = fb; }
-        __syncwarp();
-        if (lane == 0) {
-          unsigned long long x = A.seq;
-          const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(A.pairs);
-          *A.pairs = 0;
-          reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc] = e;
-          x ^= msg_mix(e, kNdtAcc);
-          for (int i = 0; i < kNdtAcc; i++) x ^= msg_mix((unsigned long long)__double_as_longlong(fin[i]), i);
-          reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc + 1] = x;
-          *reinterpret_cast<volatile unsigned long long*>(A.flag) = A.seq;
-        }
+        A.out[threadIdx.x] = sum;
+        s_fin[threadIdx.x] = sum;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long x = A.seq;
+        const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(A.pairs);
+        *A.pairs = 0;
+        reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc] = e;
+        x ^= msg_mix(e, kNdtAcc);
+        for (int i = 0; i < kNdtAcc; i++) x ^= msg_mix((unsigned long long)__double_as_longlong(s_fin[i]), i);
+        reinterpret_cast<unsigned long long*>(A.out)[kNdtAcc + 1] = x;
+        *reinterpret_cast<volatile unsigned long long*>(A.flag) = A.seq;
       }
     }
   }
-  __syncwarp();  // staging area / columns are free for the next sub-chunk
-  // ---- next sub-chunk: tickets of this launch start at qbase (ndt_run_pass); every working warp draws until its first ticket past the end
-  int next = 0;
-  if (lane == 0) next = nwarps + (int)(atomicAdd(A.queue, 1ull) - A.qbase);
-  sub = __shfl_sync(0xffffffffu, next, 0);
   }
 }
 
@@ -962,13 +969,12 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   A.d1 = K.d1; A.d2 = K.d2;
   A.ncell_search = (cfg.ndt_search_method == 1) ? 1 : 7;
   A.compute_hessian = compute_hessian ? 1 : 0;
-  const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);  // 128-point blocks of the source
-  const unsigned nsub = (unsigned)((size_t)src.nsup * 1024 / kLeaf);      // 32-point sub-chunks (one row of sums each)
-  B2R_CUDA(W.partials.reserve((size_t)(nsub + 1) * kNdtAcc));  // derivative pass: [sub-chunks][kNdtAcc]; Hessian pass: [blocks][36]
-  const unsigned ngroups = (nsub + 31) / 32, nsuper = (ngroups + 31) / 32;
-  B2R_CUDA(W.grows.reserve((size_t)(ngroups + nsuper) * kNdtAcc));  // group rows, then super rows
-  if (ngroups + nsuper > W.gcount.cap) {
-    B2R_CUDA(W.gcount.reserve(ngroups + nsuper));  // arrival counters of the group rows, then of the super rows
+  const unsigned nb = (unsigned)((size_t)src.nsup * 1024 / kNdtThreads);  // 128-point chunks of the source
+  B2R_CUDA(W.partials.reserve((size_t)(nb + 1) * kNdtAcc));  // derivative pass: [chunks][kNdtAcc]; Hessian pass: [blocks][36]
+  const unsigned ngroups = (nb + 31) / 32;
+  B2R_CUDA(W.grows.reserve((size_t)ngroups * kNdtAcc));
+  if (ngroups > W.gcount.cap) {
+    B2R_CUDA(W.gcount.reserve(ngroups));
     B2R_CUDA(cudaMemsetAsync(W.gcount.p, 0, W.gcount.cap * sizeof(unsigned int), st));  // every launch leaves the counters at zero
   }
   A.partials = W.partials.p; A.grows = W.grows.p; A.gcount = W.gcount.p; A.queue = W.d_queue; A.qbase = 0;
@@ -988,7 +994,7 @@ inline int ndt_run_pass(const b2r_config& cfg, Cloud& src, Cloud& tgt, NdtWork& 
   { TEL_BEGIN(W.tel, st);  // W.d_pairs is zero here: allocated zeroed, and the last block of every pass resets it after reading it
     const unsigned ng = std::min(nb, ndt_resident_blocks(compute_hessian));
     A.qbase = W.qnext;
-    W.qnext += nsub;  // every working warp draws tickets until its first one past the end: nsub draws per launch whatever the grid
+    W.qnext += (unsigned long long)nb + ng;  // every block draws tickets until its first one past the last chunk: nb + ng draws per launch
     if (compute_hessian) k_ndt_derivatives<true><<<ng, kNdtThreads, 0, st>>>(A);
     else k_ndt_derivatives<false><<<ng, kNdtThreads, 0, st>>>(A);
     TEL_END(W.tel, KC_NDT_DERIV, 1, st);

@@ -359,7 +359,10 @@ __device__ __forceinline__ void red_emit(double v, double* tile, double* red, in
 
 // linearize (float64) at xe into the write set + compute_error of the previous set, per active pair.  Every block leaves its
 // 29 partial sums in the pair's `partials`; k_pair_lm (next launch) adds them in a fixed order and takes the LM step.
-__global__ void __launch_bounds__(kAccThreads, 3) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
+#ifndef B2R_ACC_MINBLOCKS
+#define B2R_ACC_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(kAccThreads, B2R_ACC_MINBLOCKS) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
   __shared__ double red[kAcc * 8];
   __shared__ double tiles[(kAccThreads / 32) * 8 * kRedRow];
   asm volatile("griddepcontrol.wait;" ::: "memory");
