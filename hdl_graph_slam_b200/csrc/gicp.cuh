@@ -15,6 +15,14 @@
 namespace b2r {
 
 constexpr int kKnnThreads = 128;
+// resident blocks per SM: the single-cloud kernel is bound by its slowest warp (4 blocks, 104 registers, no spills); the batched one by
+// throughput (5 blocks, 96 registers: +4 % on the k-NN share of the loop batch, profiles/r02_y; the same setting costs the odometry chain 2 %)
+#ifndef B2R_KNN_MINBLOCKS
+#define B2R_KNN_MINBLOCKS 4
+#endif
+#ifndef B2R_KNN_BATCH_MINBLOCKS
+#define B2R_KNN_BATCH_MINBLOCKS 5
+#endif
 constexpr int kLinThreads = 128;
 #ifndef B2R_ACC_THREADS
 #define B2R_ACC_THREADS 256
@@ -264,7 +272,7 @@ __device__ __forceinline__ void knn_cov_reg_body(const Bvh& b, const float* __re
 }
 
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg(Bvh b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
+__global__ void __launch_bounds__(kKnnThreads, B2R_KNN_MINBLOCKS) k_knn_cov_reg(Bvh b, const float* __restrict__ raw, int stride_f, double* __restrict__ cov,
                                                                 long long* prof) {
   __shared__ int nbr[K][kKnnThreads];  // neighbour indices, ascending (d2, idx), for the covariance pass
   knn_cov_reg_body<K>(b, raw, stride_f, cov, blockIdx.x, nbr, prof);
@@ -280,7 +288,7 @@ struct KnnBatchItem {
   int pad;
 };
 template <int K>
-__global__ void __launch_bounds__(kKnnThreads, 4) k_knn_cov_reg_batch(const KnnBatchItem* __restrict__ items) {
+__global__ void __launch_bounds__(kKnnThreads, B2R_KNN_BATCH_MINBLOCKS) k_knn_cov_reg_batch(const KnnBatchItem* __restrict__ items) {
   __shared__ int nbr[K][kKnnThreads];
   const KnnBatchItem it = items[blockIdx.y];
   knn_cov_reg_body<K>(it.b, it.raw, it.stride_f, it.cov, blockIdx.x, nbr, nullptr);

@@ -360,7 +360,7 @@ __device__ __forceinline__ void red_emit(double v, double* tile, double* red, in
 // linearize (float64) at xe into the write set + compute_error of the previous set, per active pair.  Every block leaves its
 // 29 partial sums in the pair's `partials`; k_pair_lm (next launch) adds them in a fixed order and takes the LM step.
 #ifndef B2R_ACC_MINBLOCKS
-#define B2R_ACC_MINBLOCKS 3
+#define B2R_ACC_MINBLOCKS 4  // 64 registers, 32 warps per SM: the pass is bound by gather latency (profiles/r02_x: 33.2 -> 28.0 ms per 5 passes of 256 pairs)
 #endif
 __global__ void __launch_bounds__(kAccThreads, B2R_ACC_MINBLOCKS) k_pair_accumulate(PairDev* pairs, const int* __restrict__ active, const __grid_constant__ LmCfg cfg) {
   __shared__ double red[kAcc * 8];
@@ -517,37 +517,64 @@ __global__ void __launch_bounds__(kLmThreads, 1) k_pair_lm(PairDev* pairs, const
   if (!active) asm volatile("griddepcontrol.launch_dependents;");  // single pair: the next round's search may queue up behind this block
   if (active && (int)blockIdx.x >= active[0]) return;
   PairDev* gp = pairs + (active ? active[1 + blockIdx.x] : blockIdx.x);
-  const int mode = gp->mode;
-  if (mode < PM_FIRST || mode > PM_FIT) return;
+  // Two dependent memory round trips instead of six: (1) the whole record (mode, partials pointer and block count included) comes in
+  // with one coalesced copy, (2) every load of the reduction is issued before the first one is consumed.
   {
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sp);
     for (int i = threadIdx.x; i < (int)(sizeof(PairDev) / 8); i += blockDim.x) dst[i] = src[i];
   }
-  const double* partials = gp->partials;
-  const unsigned int nrow = (unsigned int)gp->nblk_acc;
+  __syncthreads();
+  const int mode = sp.mode;
+  if (mode < PM_FIRST || mode > PM_FIT) return;  // block-uniform
+  const double* partials = sp.partials;
+  const unsigned int nrow = (unsigned int)sp.nblk_acc;
   {
     // the partials are stored transposed ([value][block], stride = blocks rounded up to 32): warp w sums the values w, w + 8, ...;
-    // one coalesced load covers 32 blocks of a value, all loads of a value are independent, lane l adds blocks l, l + 32, ... in
-    // ascending order and a fixed butterfly joins the lanes — a couple of memory round trips for the whole reduction
+    // one coalesced load covers 32 blocks of a value, lane l adds blocks l, l + 32, ... in ascending order and a fixed butterfly
+    // joins the lanes.  The loads of ALL the warp's values go out first (up to 4 values x 8 rows in flight per lane).
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int nw = kLmThreads / 32;
+    constexpr int kVals = (kAcc + nw - 1) / nw;  // values per warp
     const unsigned int stride = (nrow + 31u) & ~31u;
-    for (int i = warp; i < kAcc; i += nw) {
-      const double* col = partials + (size_t)i * stride;
-      double sacc = 0.0;
-      unsigned int row = lane;
-      for (; row + 7 * 32 < nrow; row += 8 * 32) {
-        double t[8];
+    if (nrow <= 8u * 32u) {
+      double t[kVals][8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = __ldcg(col + row + u * 32);
+      for (int q = 0; q < kVals; q++) {
+        const int i = warp + q * nw;
 #pragma unroll
-        for (int u = 0; u < 8; u++) sacc += t[u];
+        for (int u = 0; u < 8; u++) {
+          const unsigned int row = lane + 32u * u;
+          t[q][u] = (i < kAcc && row < nrow) ? __ldcg(partials + (size_t)i * stride + row) : 0.0;
+        }
       }
-      for (; row < nrow; row += 32) sacc += __ldcg(col + row);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
-      if (lane == 0) r[i] = sacc;
+      for (int q = 0; q < kVals; q++) {
+        const int i = warp + q * nw;
+        double sacc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (lane + 32u * u < nrow) sacc += t[q][u];  // same additions, same order as the general loop below
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0 && i < kAcc) r[i] = sacc;
+      }
+    } else {
+      for (int i = warp; i < kAcc; i += nw) {
+        const double* col = partials + (size_t)i * stride;
+        double sacc = 0.0;
+        unsigned int row = lane;
+        for (; row + 7 * 32 < nrow; row += 8 * 32) {
+          double t[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) t[u] = __ldcg(col + row + u * 32);
+#pragma unroll
+          for (int u = 0; u < 8; u++) sacc += t[u];
+        }
+        for (; row < nrow; row += 32) sacc += __ldcg(col + row);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) r[i] = sacc;
+      }
     }
     __syncthreads();
   }
