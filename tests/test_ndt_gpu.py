@@ -72,6 +72,33 @@ def test_derivatives(pair, oracle, search):
     r.close()
 
 
+def test_derivative_pass_is_bitwise_reproducible(synth):
+    """The pass hands its 128-point chunks out through a ticket counter (whichever block is free takes the next one); every chunk owns a row
+    of sums and the rows are added by a fixed tree, so the result must not depend on the scheduling: repeated passes, passes after a pass on
+    a cloud of another size (counters / ticket base carried over), and a second handle all give the same bits."""
+    tgt = synth.scan("vlp16_16k", frame=0, stride=8)
+    srcs = [synth.scan("vlp16_16k", frame=1, stride=8), synth.scan("vlp16", frame=1, stride=8), synth.scan("vlp16_16k", frame=2, stride=8)]
+    p = [0.9, 0.05, -0.02, 0.01, -0.015, 0.03]
+    r = make(1.0)
+    r.setInputTarget(tgt)
+    ref = {}
+    for rep in range(3):
+        for k, src in enumerate(srcs):
+            r.setInputSource(src)
+            for _ in range(2):
+                score, g, H, npairs = r.ndtDerivativesAt(p)
+                got = (np.float64(score).tobytes(), np.asarray(g).tobytes(), np.asarray(H).tobytes(), int(npairs))
+                if k in ref:
+                    assert got == ref[k], f"pass on cloud {k} differs from its first run (rep {rep})"
+                ref[k] = got
+    r2 = make(1.0)
+    r2.setInputTarget(tgt)
+    r2.setInputSource(srcs[1])
+    score, g, H, npairs = r2.ndtDerivativesAt(p)
+    assert (np.float64(score).tobytes(), np.asarray(g).tobytes(), np.asarray(H).tobytes(), int(npairs)) == ref[1]
+    r.close(); r2.close()
+
+
 @pytest.mark.parametrize("case", [0, 1, 2, 3])
 def test_align_matches_oracle(pair, oracle, case):
     src, tgt = pair
