@@ -44,7 +44,7 @@ def _frames(torch, dev, rank, count=N_FRAMES):
     return host, devbuf, int(n), int(stride_f)
 
 
-def _timed(torch, dist, dev, world, stream, K, body, sampler=None):
+def _timed(torch, dist, dev, world, stream, K, body, sampler=None, stats_fn=None):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -59,6 +59,7 @@ def _timed(torch, dist, dev, world, stream, K, body, sampler=None):
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = None
+    stats = stats_fn() if stats_fn else None  # counters of the timed region only (the hold steps below are not part of it)
     if sampler:  # untimed steps of the same workload until nvidia-smi has sampled the load (bench.ClockSampler)
         sampler.hold(lambda k: body(k % K), torch.cuda.synchronize)
         clocks = sampler.stop()
@@ -67,7 +68,7 @@ def _timed(torch, dist, dev, world, stream, K, body, sampler=None):
     if world > 1:
         dist.barrier()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item()), wall * 1e3, clocks
+    return float(t.item()), wall * 1e3, clocks, stats
 
 
 def _cpu_voxelgrid(host, leaf, budget_s=10.0):
@@ -108,8 +109,8 @@ def bench_voxelgrid(args, rank, world, local_rank, leaf=0.25):
         reg.setProfiling(arm == "profile")
         counts.clear()
         sampler = bench.ClockSampler(local_rank) if (rank == 0 and arm == "value") else None
-        ms, wall, clocks = _timed(torch, dist, dev, world, stream, K, body, sampler)
-        res[arm] = dict(ms=ms, wall=wall, clocks=clocks, stats=reg.getStats(), n_ds=float(np.mean(counts)))
+        ms, wall, clocks, stats = _timed(torch, dist, dev, world, stream, K, body, sampler, reg.getStats)
+        res[arm] = dict(ms=ms, wall=wall, clocks=clocks, stats=stats, n_ds=float(np.mean(counts)))
         reg.setProfiling(False)
     reg.close()
     if rank != 0:
@@ -212,8 +213,8 @@ def bench_kitti_pipeline(args, rank, world, local_rank):
             state[key].clear()
         state["conv"] = state["kf"] = 0
         sampler = bench.ClockSampler(local_rank) if (rank == 0 and arm == "value") else None
-        ms, wall, clocks = _timed(torch, dist, dev, world, stream, K, lambda k: step(k + W), sampler)
-        res[arm] = dict(ms=ms, wall=wall, clocks=clocks, stats=reg.getStats(), m=float(np.mean(state["m"])), iters=float(np.mean(state["iters"])),
+        ms, wall, clocks, stats = _timed(torch, dist, dev, world, stream, K, lambda k: step(k + W), sampler, reg.getStats)
+        res[arm] = dict(ms=ms, wall=wall, clocks=clocks, stats=stats, m=float(np.mean(state["m"])), iters=float(np.mean(state["iters"])),
                         conv=state["conv"], kf=state["kf"])
         reg.setProfiling(False)
         odo.close()
