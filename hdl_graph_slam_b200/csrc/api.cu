@@ -28,6 +28,10 @@
 #include "map_cloud.cuh"
 #include "ingest.cuh"
 
+#ifndef B2R_PREFETCH_KNN_BLOCKS_DEFAULT
+#define B2R_PREFETCH_KNN_BLOCKS_DEFAULT 0  // 0 = no cap on the prefetch stream's k-NN kernel
+#endif
+
 namespace b2r {
 thread_local std::string g_last_error;
 }
@@ -482,7 +486,21 @@ static int build_cov(b2r_handle* h, Cloud& c, BuildCtx& B, cudaStream_t st) {
 #endif
     TEL_BEGIN(&h->tel, st);
     if (k == kKnnRegK) {  // the reference's default reg_correspondence_randomness: lists live in registers
-      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, 0, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
+      // On the PREFETCH stream the kernel works for the NEXT frame while the align chain of the current one runs beside it.  All of its
+      // 512 blocks become resident at once (104 registers x 128 threads x 3.5 blocks per SM = 70 % of the register file) and stay for
+      // ~170 us — stream priorities only order PENDING blocks, so the chain's search kernels then run in the remaining third of each SM.
+      // Capping the prefetch kernel's residency with unused dynamic shared memory keeps most of every SM for the chain.
+      static const int cap = [] { const char* e = getenv("B2R_PREFETCH_KNN_BLOCKS"); return e ? atoi(e) : B2R_PREFETCH_KNN_BLOCKS_DEFAULT; }();
+      size_t pad_smem = 0;
+      if (cap > 0 && cap < B2R_KNN_MINBLOCKS && st == h->st2) {
+        pad_smem = ((size_t)227 * 1024 / (size_t)cap - (size_t)kKnnRegK * kKnnThreads * sizeof(int) - 2048) & ~(size_t)255;
+        static bool attr_set = false;
+        if (!attr_set) {
+          B2R_CUDA(cudaFuncSetAttribute(k_knn_cov_reg<kKnnRegK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024 - kKnnRegK * kKnnThreads * (int)sizeof(int) - 2048)));
+          attr_set = true;
+        }
+      }
+      k_knn_cov_reg<kKnnRegK><<<(unsigned)(padded / kKnnThreads), kKnnThreads, pad_smem, st>>>(c.bvh(), c.raw_view, c.stride_f, c.cov.p, prof);
     } else {
       if (smem > 48 * 1024 && !h->knn_smem_attr) {
         B2R_CUDA(cudaFuncSetAttribute(k_knn_cov, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kKnnThreads * 8));
