@@ -145,8 +145,11 @@ struct Nn1 {
 // the `pass` predicate is folded into the start key (key 0 beats everything) instead of being and-ed into every candidate's
 // decision.  No position is tracked: the caller maps the winning index through the target's pos_of table.  Same candidates, same
 // rule => the same answers as Nn1 (tests/warp_harness.cpp runs both on the emulated warp).
+#ifndef B2R_NN1K_TILE_LANES
+#define B2R_NN1K_TILE_LANES 8
+#endif
 struct Nn1K {
-  static constexpr int kTileLanes = 8;
+  static constexpr int kTileLanes = B2R_NN1K_TILE_LANES;
   static constexpr int kTileUnroll = 8;
   static constexpr bool kTwoPhase = false;
   static constexpr bool kKeyed = true;
