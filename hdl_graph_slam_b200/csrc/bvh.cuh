@@ -334,6 +334,8 @@ __device__ __forceinline__ bool bvh_visit_leaf(const Bvh& b, int l, float qx, fl
 #endif
 #endif
   if (__popc(mask) >= kTile) {
+    // (dynamic regrouping of sparse visits — the r-th interested query served by 2 or 4 adjacent lanes sweeping a half / a quarter of the
+    // leaf each — is exact but measured neutral out of line and 44 % slower inlined at every visit site: profiles/r02_ac, r02_ad)
     if constexpr (C > 1) {
       const int t0 = (lane / Q) * (kLeaf / C);
       if constexpr (keyed_visitor<Visitor>::value) {
@@ -435,14 +437,15 @@ __device__ __forceinline__ float aabb_aabb_bound2(float glx, float gly, float gl
 }
 
 // exact per-lane test + visit of one leaf
+// exact = false: every active lane takes the leaf without a bound test (the queries' own leaf in a self k-NN)
 template <int C = 1, class Visitor>
-__device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v) {
+__device__ __forceinline__ bool bvh_try_leaf(const Bvh& b, int l, float qx, float qy, float qz, bool active, Visitor& v, bool exact = true) {
 #ifdef B2R_KNN_PROFILE
   v.n_try++;
 #endif
   const float4 lo = __ldg(b.leaf_lo + l), hi = __ldg(b.leaf_hi + l);
   const float lb = aabb_bound2(qx, qy, qz, lo.x, lo.y, lo.z, hi.x, hi.y, hi.z);
-  const bool pass = active && !(lb > v.worst()) && (lb < v.limit());
+  const bool pass = active && (!exact || (!(lb > v.worst()) && (lb < v.limit())));
   return bvh_visit_leaf<C>(b, l, qx, qy, qz, pass, v);
 }
 
@@ -466,7 +469,6 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   if (__ballot_sync(FULL, active) == 0 || b.nleaf <= 0) return;
-  if (own_leaf >= 0) bvh_visit_leaf<C>(b, own_leaf, qx, qy, qz, active, v);
   // group AABB of the active queries
   float glx = active ? qx : INFINITY, gly = active ? qy : INFINITY, glz = active ? qz : INFINITY;
   float ghx = active ? qx : -INFINITY, ghy = active ? qy : -INFINITY, ghz = active ? qz : -INFINITY;
@@ -475,12 +477,13 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     glx = fminf(glx, __shfl_xor_sync(FULL, glx, o)); gly = fminf(gly, __shfl_xor_sync(FULL, gly, o)); glz = fminf(glz, __shfl_xor_sync(FULL, glz, o));
     ghx = fmaxf(ghx, __shfl_xor_sync(FULL, ghx, o)); ghy = fmaxf(ghy, __shfl_xor_sync(FULL, ghy, o)); ghz = fmaxf(ghz, __shfl_xor_sync(FULL, ghz, o));
   }
-  if (own_leaf < 0 && hint_leaf >= 0) {
-    bvh_try_leaf<C>(b, hint_leaf, qx, qy, qz, active, v);
-    own_leaf = hint_leaf;
-  }
-  // no hint: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
-  if (own_leaf < 0) {
+  // The first leaf — the queries' own one, the hinted one, or the one nearest to the group's centre — is visited at ONE call site, and
+  // so are the leaves of pass 1 and of pass 2: every site inlines the whole leaf visit (for the list visitors two copies of the
+  // 80-instruction insertion network), and six of them made the k-NN kernel 6 000 instructions long.
+  int first = own_leaf >= 0 ? own_leaf : hint_leaf;
+  const bool first_exact = own_leaf < 0;
+  // no own leaf, no hint: the leaf nearest to the group's centre inside the nearest super-node (ordering heuristic only)
+  if (first < 0) {
     const float gcx = 0.5f * (glx + ghx), gcy = 0.5f * (gly + ghy), gcz = 0.5f * (glz + ghz);
     float bd = INFINITY;
     int bs = 0;
@@ -508,8 +511,9 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
       const int ol = __shfl_xor_sync(FULL, ll, o);
       if (od < ld || (od == ld && ol < ll)) { ld = od; ll = ol; }
     }
-    if (ld < INFINITY) { bvh_try_leaf<C>(b, ll, qx, qy, qz, active, v); own_leaf = ll; }  // from here on `own_leaf` = already visited
+    if (ld < INFINITY) first = ll;
   }
+  if (first >= 0) { bvh_try_leaf<C>(b, first, qx, qy, qz, active, v, first_exact); own_leaf = first; }  // from here on `own_leaf` = already visited
   // pass 1: the window of 32 leaves CENTRED on the already-visited leaf, in order of index distance from it (Hilbert order:
   // index neighbours are space neighbours), so the bound is tight before anything else is looked at.  The window ignores
   // super-node borders: a leaf that straddles a jump of the curve at the end of its super-node has half of its true
@@ -525,10 +529,11 @@ __device__ __forceinline__ void bvh_group_search(const Bvh& b, float qx, float q
     unsigned lmask = __ballot_sync(FULL, !(lgb > gw) && lgb < INFINITY) & ~(1u << (own_leaf - win0));
     lmask = refine_node_mask(lmask, b.leaf_lo + win0, b.leaf_hi + win0, qx, qy, qz, active, v);
     const int c = own_leaf - win0;
-    for (int d = 1; d < kSuper && lmask; d++) {
-      const int ja = c - d, jb = c + d;
-      if (ja >= 0 && ((lmask >> ja) & 1u)) { lmask &= ~(1u << ja); bvh_try_leaf<C>(b, win0 + ja, qx, qy, qz, active, v); }
-      if (jb < kSuper && ((lmask >> jb) & 1u)) { lmask &= ~(1u << jb); bvh_try_leaf<C>(b, win0 + jb, qx, qy, qz, active, v); }
+#pragma unroll 1
+    for (int e = 2; e < 2 * kSuper && lmask; e++) {  // e = 2 d + side: c - 1, c + 1, c - 2, c + 2, ...
+      const int d = e >> 1;
+      const int j = (e & 1) ? c + d : c - d;
+      if (j >= 0 && j < kSuper && ((lmask >> j) & 1u)) { lmask &= ~(1u << j); bvh_try_leaf<C>(b, win0 + j, qx, qy, qz, active, v); }
     }
   }
   // pass 2: every super-node, 32 per step, then the leaves of each survivor, 32 per step — all against the group's box and
