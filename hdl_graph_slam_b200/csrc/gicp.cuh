@@ -402,60 +402,4 @@ __device__ __forceinline__ void finish_stored(double* partials, double* out, uns
   }
 }
 
-// finish_stored_t: the same last-block-done final reduction for partials stored TRANSPOSED — value i of block b at
-// partials[i * stride + b] (stride = gridDim.x rounded up to 32).  A warp then reads 32 consecutive blocks' values of one quantity in
-// ONE coalesced load, all loads of a quantity are independent, and the warp sum is a fixed butterfly: the whole reduction is a few
-// memory round trips instead of gridDim / (8 x warps) dependent batches (the NDT pass: 592 rows x 43 values cost ~30 k cycles of a
-// 100 k-cycle kernel in the row-major form, profiles/r02_s).  Lane l adds blocks l, l + 32, ... in ascending order, then the
-// butterfly joins the lanes: the order depends only on the launch geometry.
-template <int NV>
-__device__ __forceinline__ void finish_stored_t(double* partials, unsigned int stride, double* out, unsigned int* counter, unsigned long long* flag = nullptr,
-                                                unsigned long long seq = 0, unsigned long long* extra = nullptr) {
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
-    __threadfence();
-    unsigned int t = atomicAdd(counter, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    __shared__ double fin[NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const unsigned int nrow = gridDim.x;
-    for (int i = warp; i < NV; i += nw) {
-      const double* col = partials + (size_t)i * stride;
-      double s = 0.0;
-      unsigned int r = lane;
-      for (; r + 7 * 32 < nrow; r += 8 * 32) {
-        double t[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) t[u] = __ldcg(col + r + u * 32);
-#pragma unroll
-        for (int u = 0; u < 8; u++) s += t[u];
-      }
-      for (; r < nrow; r += 32) s += __ldcg(col + r);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) { out[i] = s; fin[i] = s; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      *counter = 0;
-      unsigned long long x = seq;
-      if (extra) {
-        const unsigned long long e = *reinterpret_cast<volatile unsigned long long*>(extra);
-        *extra = 0;
-        reinterpret_cast<unsigned long long*>(out)[NV] = e;
-        x ^= msg_mix(e, NV);
-      }
-      if (flag) {
-        for (int i = 0; i < NV; i++) x ^= msg_mix((unsigned long long)__double_as_longlong(fin[i]), i);
-        reinterpret_cast<unsigned long long*>(out)[NV + 1] = x;
-        *reinterpret_cast<volatile unsigned long long*>(flag) = seq;
-      }
-    }
-  }
-}
-
 }  // namespace b2r

@@ -77,3 +77,42 @@ def test_auxiliary_workloads_have_no_reference_arm_but_say_so():
         assert out.returncode == 0, out.stderr
         line = json.loads(out.stdout.strip().splitlines()[-1])
         assert line["impl"] == "reference" and "unavailable" in line
+
+
+def test_clock_sampler_window_and_hold(tmp_path, monkeypatch):
+    """ClockSampler keeps the samples whose timestamps lie inside [begin(), stop()] and holds untimed steps until the window is long
+    enough for nvidia-smi; without nvidia-smi it says so and never holds"""
+    import datetime
+    import time
+    b = _bench()
+    s = b.ClockSampler(0)
+    s.p = None  # nvidia-smi unavailable
+    assert not s.hold_needed()
+    calls = []
+    s.hold(lambda k: calls.append(k), lambda: None)
+    assert calls == [] and s.stop()["samples"] == 0 and "nvidia-smi unavailable" in s.stop()["reasons"]
+    # a fake nvidia-smi log: one sample before the window, two inside (one of them throttled), one malformed line
+    s = b.ClockSampler(0)
+    s.path = str(tmp_path / "clocks.csv")
+
+    class P:  # stands in for the nvidia-smi process
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+    s.p, s.f = P(), open(s.path, "w")
+    s.MIN_WINDOW_S = 0.05
+    s.begin()
+    fmt = "%Y/%m/%d %H:%M:%S.%f"
+    def line(t, mhz, power_cap):
+        return ", ".join([datetime.datetime.fromtimestamp(t).strftime(fmt)[:-3], str(mhz), "1965", "400.0", "0x0", "Not Active", "Not Active", "Not Active", power_cap]) + "\n"
+    s.f.write(line(s.t0 - 5.0, 345, "Not Active"))
+    s.f.write(line(s.t0 + 0.01, 1965, "Not Active"))
+    s.f.write(line(s.t0 + 0.02, 1950, "Active"))
+    s.f.write("garbage\n")
+    s.f.flush()
+    steps = []
+    s.hold(lambda k: (steps.append(k), time.sleep(0.01)), lambda: None)
+    assert len(steps) >= 3 and s.extra_steps == len(steps)
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1957.5 and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+    assert "untimed steps" in out["window"]
