@@ -4,4 +4,4 @@ include/b200reg.h); this package is the thin host-side mirror of the reference i
 """
 from ._capi import B2RError, B2R_METHOD_GICP, B2R_METHOD_NDT, Config, load as load_library  # noqa: F401
 from .registration import (Registration, select_registration_method, ScanMatchingOdometry, LoopDetector,  # noqa: F401
-                           default_config, RegistrationBatch, shard_range, loop_argmin, information_from_fitness)
+                           default_config, RegistrationBatch, shard_range, loop_argmin, information_from_fitness, LoopClosureGate)

@@ -52,6 +52,15 @@ class PointLayout(C.Structure):
                 ("intensity_datatype", C.c_uint32), ("is_bigendian", C.c_uint32)]
 
 
+class LoopParams(C.Structure):
+    _fields_ = [("distance_thresh", C.c_double), ("accum_distance_thresh", C.c_double), ("min_edge_interval", C.c_double),
+                ("fitness_score_max_range", C.c_double), ("fitness_score_thresh", C.c_double)]
+
+
+class KeyframeState(C.Structure):
+    _fields_ = [("accum_distance", C.c_double), ("estimate", C.c_double * 16)]
+
+
 class OdometryParams(C.Structure):
     _fields_ = [
         ("keyframe_delta_trans", C.c_double), ("keyframe_delta_angle", C.c_double), ("keyframe_delta_time", C.c_double),
@@ -138,6 +147,12 @@ SYMBOLS = [
     ("b2r_information_from_fitness", C.c_int, [C.POINTER(InformationParams), C.c_double, _F64P]),
     ("b2r_batch_last_rounds", C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("b2r_loop_argmin", C.c_int, [C.POINTER(Result), _SZ, C.c_double, _I32P]),
+    ("b2r_loop_params_default", C.c_int, [C.POINTER(LoopParams)]),
+    ("b2r_loop_find_candidates", C.c_int, [C.POINTER(LoopParams), C.POINTER(KeyframeState), _SZ, C.POINTER(KeyframeState), C.c_double, _I32P, _SZ, C.POINTER(_SZ)]),
+    ("b2r_loop_guess", C.c_int, [_F64P, _F64P, _F32P]),
+    ("b2r_loop_detect_plan", C.c_int, [C.POINTER(LoopParams), C.POINTER(KeyframeState), _SZ, C.POINTER(KeyframeState), _SZ, C.c_double, _I32P, _F32P, _SZ,
+                                       C.POINTER(C.c_int64), C.POINTER(_SZ)]),
+    ("b2r_loop_detect_replay", C.c_int, [C.POINTER(LoopParams), C.POINTER(KeyframeState), _SZ, C.POINTER(C.c_int64), _I32P, C.c_double, _F64P, _I32P]),
     ("b2r_nccl_unique_id", C.c_int, [_VP, _SZ]),
     ("b2r_batch_comm_init", C.c_int, [_VP, _VP, C.c_int, C.c_int]),
     ("b2r_shard_range", C.c_int, [_SZ, C.c_int, C.c_int, C.POINTER(_SZ), C.POINTER(_SZ)]),

@@ -420,6 +420,87 @@ def _result_dict(r):
     return dict(T=_from_colmajor(r.T), fitness=r.fitness, converged=bool(r.converged), iterations=r.iterations)
 
 
+def _keyframe_states(keyframes):
+    """keyframes: sequence of (accum_distance, 4x4 estimate) -> ctypes array of b2r_keyframe_state"""
+    arr = (_capi.KeyframeState * max(len(keyframes), 1))()
+    for i, (acc, est) in enumerate(keyframes):
+        arr[i].accum_distance = float(acc)
+        e = np.asarray(est, np.float64).T.reshape(-1)  # column-major
+        for k in range(16):
+            arr[i].estimate[k] = e[k]
+    return arr
+
+
+class LoopClosureGate:
+    """Host mirror of the gating half of hdl_graph_slam's LoopDetector (loop_detector.hpp:39-46,57-68,81-109,137-142): rosparams,
+    find_candidates, the initial guess, and detect() as plan -> batched matching -> sequential replay.  Nothing here computes on the
+    device; `detect` drives a RegistrationBatch for the matching."""
+
+    def __init__(self, **params):
+        self._lib = _capi.load()
+        self.params = _capi.LoopParams()
+        check(self._lib.b2r_loop_params_default(C.byref(self.params)))
+        for k, v in params.items():
+            setattr(self.params, k, v)
+        self.last_edge_accum_distance = 0.0  # loop_detector.hpp:48
+
+    def find_candidates(self, keyframes, new_keyframe):
+        ks, nk = _keyframe_states(keyframes), _keyframe_states([new_keyframe])
+        out = (C.c_int32 * max(len(keyframes), 1))()
+        n = C.c_size_t()
+        check(self._lib.b2r_loop_find_candidates(C.byref(self.params), ks, len(keyframes), nk, self.last_edge_accum_distance, out, len(keyframes), C.byref(n)))
+        return list(out[: n.value])
+
+    def guess(self, new_keyframe_estimate, candidate_estimate):
+        a = np.ascontiguousarray(np.asarray(new_keyframe_estimate, np.float64).T).reshape(-1)
+        b = np.ascontiguousarray(np.asarray(candidate_estimate, np.float64).T).reshape(-1)
+        g = np.empty(16, np.float32)
+        check(self._lib.b2r_loop_guess(a.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)), g.ctypes.data_as(C.POINTER(C.c_float))))
+        return g.reshape(4, 4).T.copy()
+
+    def plan(self, keyframes, new_keyframes):
+        """-> (candidate_index[n_pairs], guesses[n_pairs, 4, 4], group_first[n_new + 1]) under the gate as it stands now"""
+        ks, nks = _keyframe_states(keyframes), _keyframe_states(new_keyframes)
+        cap = max(len(keyframes) * len(new_keyframes), 1)
+        idx = (C.c_int32 * cap)()
+        g = np.empty((cap, 16), np.float32)
+        gf = (C.c_int64 * (len(new_keyframes) + 1))()
+        n = C.c_size_t()
+        check(self._lib.b2r_loop_detect_plan(C.byref(self.params), ks, len(keyframes), nks, len(new_keyframes), self.last_edge_accum_distance, idx,
+                                             g.ctypes.data_as(C.POINTER(C.c_float)), cap, gf, C.byref(n)))
+        guesses = g[: n.value].reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+        return list(idx[: n.value]), guesses, list(gf)
+
+    def replay(self, new_keyframes, group_first, best, planned_last_edge):
+        """the sequential walk of detect() over the batch's per-group answers -> accepted[g] (index inside the group or -1); updates
+        last_edge_accum_distance like loop_detector.hpp:166"""
+        nks = _keyframe_states(new_keyframes)
+        gf = (C.c_int64 * len(group_first))(*[int(x) for x in group_first])
+        b = (C.c_int32 * max(len(best), 1))(*[int(x) for x in best])
+        acc = (C.c_int32 * max(len(best), 1))()
+        last = C.c_double(self.last_edge_accum_distance)
+        check(self._lib.b2r_loop_detect_replay(C.byref(self.params), nks, len(new_keyframes), gf, b, float(planned_last_edge), C.byref(last), acc))
+        self.last_edge_accum_distance = last.value
+        return list(acc[: len(new_keyframes)])
+
+    def detect(self, batch, keyframes, keyframe_cloud_ids, new_keyframes, new_keyframe_cloud_ids):
+        """LoopDetector::detect for all new keyframes at once on a RegistrationBatch (its communicator shards the groups over the GPUs).
+        Returns [(new keyframe index, candidate keyframe index, relative pose 4x4)] of the registered loops, in the reference's order."""
+        planned_last = self.last_edge_accum_distance
+        cand, guesses, gf = self.plan(keyframes, new_keyframes)
+        pairs = []
+        for g in range(len(new_keyframes)):
+            for j in range(gf[g], gf[g + 1]):
+                pairs.append((keyframe_cloud_ids[cand[j]], new_keyframe_cloud_ids[g], guesses[j]))
+        best, results = batch.loopDetect(pairs, gf, self.params.fitness_score_max_range, self.params.fitness_score_thresh)
+        accepted = self.replay(new_keyframes, gf, best, planned_last)
+        loops = []
+        for g, a in enumerate(accepted):
+            if a >= 0:
+                loops.append((g, cand[gf[g] + a], results[gf[g] + a]["T"]))
+        return loops
+
+
 def shard_range(n_groups, world, rank):
     """contiguous block of groups owned by `rank` (b2r_shard_range)"""
     g0, g1 = C.c_size_t(), C.c_size_t()

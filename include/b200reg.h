@@ -356,6 +356,43 @@ int b2r_batch_last_rounds(const b2r_batch* b, uint64_t* rounds, uint64_t* pair_r
  * candidate (a later candidate with an EQUAL score wins) or -1 when nothing converged or the best score exceeds the threshold */
 int b2r_loop_argmin(const b2r_result* results, size_t n, double fitness_score_thresh, int32_t* best);
 
+/* ---- LoopDetector's gating around the batch (include/hdl_graph_slam/loop_detector.hpp:39-46,57-68,81-109,137-142): host logic only ----
+ * detect() walks the new keyframes one by one: find_candidates -> matching -> (loop found) last_edge_accum_distance = accum_distance.
+ * The only coupling between two new keyframes is that scalar, so the walk splits into  plan  (every new keyframe's candidates and
+ * guesses under the gate as it stands when the walk starts),  b2r_batch_loop_detect  (all pairs at once, sharded over the GPUs) and
+ * replay  (the sequential walk on the results: a keyframe gated out at ITS turn reports no loop, an accepted loop moves the distance).
+ * The outcome equals the reference's sequential detect(). */
+typedef struct b2r_loop_params {
+  double distance_thresh;          /* loop_detector.hpp:40  (5.0)  estimated xy distance between the two keyframes must not exceed it */
+  double accum_distance_thresh;    /* :41 (8.0)  travelled distance between the two keyframes must reach it */
+  double min_edge_interval;        /* :42 (5.0)  "distance_from_last_edge_thresh": travelled distance since the last registered loop edge */
+  double fitness_score_max_range;  /* :44 (DBL_MAX) */
+  double fitness_score_thresh;     /* :45 (0.5) */
+} b2r_loop_params;
+typedef struct b2r_keyframe_state {
+  double accum_distance;           /* KeyFrame::accum_distance */
+  double estimate[16];             /* KeyFrame::node->estimate().matrix(), column-major */
+} b2r_keyframe_state;
+int b2r_loop_params_default(b2r_loop_params* p);
+/* LoopDetector::find_candidates (:81-109): indices into `keyframes` in their order; none if the new keyframe is closer than
+ * min_edge_interval to the last registered loop edge.  *n_candidates = the number found (an error if it exceeds `capacity`). */
+int b2r_loop_find_candidates(const b2r_loop_params* p, const b2r_keyframe_state* keyframes, size_t n_keyframes, const b2r_keyframe_state* new_keyframe,
+                             double last_edge_accum_distance, int32_t* candidates, size_t capacity, size_t* n_candidates);
+/* the initial guess of LoopDetector::matching (:137-142): rotations re-normalised through a quaternion, new^-1 * candidate,
+ * cast to float, z translation zeroed; column-major in and out */
+int b2r_loop_guess(const double* new_keyframe_estimate, const double* candidate_estimate, float* guess);
+/* plan of one detect() walk: group g = new_keyframes[g]; pairs [group_first[g], group_first[g+1]) are its candidates
+ * (candidate_index = index into `keyframes`, guesses = 16 floats per pair); group_first has n_new + 1 entries.  The caller turns
+ * (candidate_index, g) into cloud ids of a b2r_batch and hands pairs + group_first to b2r_batch_loop_detect. */
+int b2r_loop_detect_plan(const b2r_loop_params* p, const b2r_keyframe_state* keyframes, size_t n_keyframes, const b2r_keyframe_state* new_keyframes,
+                         size_t n_new, double last_edge_accum_distance, int32_t* candidate_index, float* guesses, size_t capacity,
+                         int64_t* group_first, size_t* n_pairs);
+/* the sequential walk on the batch's answers: best[g] = b2r_batch_loop_detect's index inside group g or -1;
+ * planned_last_edge_accum_distance = the value the plan was made with; *last_edge_accum_distance is read and updated (:166);
+ * accepted[g] = index inside group g of the registered loop's start keyframe, or -1 */
+int b2r_loop_detect_replay(const b2r_loop_params* p, const b2r_keyframe_state* new_keyframes, size_t n_new, const int64_t* group_first, const int32_t* best,
+                           double planned_last_edge_accum_distance, double* last_edge_accum_distance, int32_t* accepted);
+
 /* multi-GPU: one process per GPU; rank 0 creates the id, every rank receives it through the launcher's own channel
  * (bench.py: torch.distributed broadcast) and joins.  The library links NCCL itself. */
 int b2r_nccl_unique_id(void* out128, size_t capacity);

@@ -180,3 +180,45 @@ def test_calc_fitness_score_batched_on_cached_keyframes(synth, oracle):
     lb.align([(ids[1], ids[0], edges[0][2])], True, 2.0)
     assert lb.calcFitnessScore([(ids[0], ids[1], edges[0][2])], 2.0)[0] == again[0]
     lb.close()
+
+
+def test_detect_plan_batch_replay_equals_the_sequential_walk(synth):
+    """LoopDetector::detect (loop_detector.hpp:57-68) as plan -> b2r_batch_loop_detect -> replay (LoopClosureGate.detect) against the reference's
+    sequential walk: find_candidates -> matching (b2r_loop_matching on one handle) -> last_edge_accum_distance update, new keyframe by new keyframe.
+    The second new keyframe lies 2 m after the first: it is planned speculatively and dropped by the replay once the first registers its loop."""
+    from test_loop_gate import ref_find_candidates
+    sensor = "vlp16_16k"
+    kf_frames = [0, 2, 10, 12, 20, 120]
+    new_frames = [251, 253, 261, 271]
+    kfs = [(float(f), synth.pose_matrix(f)) for f in kf_frames]
+    news = [(float(f), synth.pose_matrix(f) @ perturb(300 + f, 0.2, 1.0)) for f in new_frames]  # graph estimates drift a little
+    clouds = {f: synth.scan(sensor, frame=f, stride=8) for f in kf_frames + new_frames}
+    p = dict(distance_thresh=5.0, accum_distance_thresh=8.0, min_edge_interval=5.0)
+    gate = pkg.LoopClosureGate(fitness_score_max_range=2.5)
+    # (1) the reference's walk on the pcl::Registration-shaped handle
+    reg = pkg.select_registration_method({"registration_method": "FAST_GICP"})
+    det = pkg.LoopDetector(reg, fitness_score_max_range=2.5, fitness_score_thresh=0.5)
+    last, want = 0.0, []
+    for gi, nk in enumerate(news):
+        cands = ref_find_candidates(p, kfs, nk, last)
+        if not cands:
+            continue
+        guesses = [gate.guess(nk[1], kfs[c][1]) for c in cands]
+        best, results = det.matching([clouds[kf_frames[c]] for c in cands], clouds[new_frames[gi]], guesses)
+        if best >= 0:
+            want.append((gi, cands[best], results[best]["T"]))
+            last = nk[0]
+    reg.close()
+    assert len(want) >= 2 and all(g != 1 for g, _, _ in want), "the 2 m keyframe must be gated by the loop registered just before it"
+    # (2) plan -> batch -> replay
+    lb = pkg.RegistrationBatch(params={"registration_method": "FAST_GICP"})
+    kid = [lb.addCloud(clouds[f]) for f in kf_frames]
+    nid = [lb.addCloud(clouds[f]) for f in new_frames]
+    cand, _, gf = gate.plan(kfs, news)
+    assert gf[2] - gf[1] >= 1, "the gated keyframe has candidates in the plan (it is matched speculatively)"
+    got = gate.detect(lb, kfs, kid, news, nid)
+    lb.close()
+    assert [(g, c) for g, c, _ in got] == [(g, c) for g, c, _ in want]
+    for (_, _, Ta), (_, _, Tb) in zip(got, want):
+        assert np.array_equal(Ta, Tb)  # batch == single handle, bitwise
+    assert gate.last_edge_accum_distance == last
