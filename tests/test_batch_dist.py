@@ -105,3 +105,85 @@ def test_information_matrix_from_fitness_matches_reference_formula():
         assert np.allclose(pkg.information_from_fitness(f), ref(f), rtol=1e-15, atol=0)
     assert np.allclose(pkg.information_from_fitness(0.3, fitness_score_thresh=2.5, var_gain_a=10.0), ref(0.3, a=10.0, thr=2.5), rtol=1e-15)
     assert np.allclose(pkg.information_from_fitness(0.3, use_const_inf_matrix=1), [2.0, 2.0, 2.0, 10.0, 10.0, 10.0])
+
+
+# ---- LoopDetector::detect across two ranks: plan on every rank, each rank "matches" its shard, one gather, sequential replay
+def _detect_inputs():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_loop_gate import trajectory
+    rng = np.random.default_rng(21)
+    kfs = trajectory(rng, 60)
+    new = []
+    for k in (3, 4, 9, 17, 18, 30, 41, 42, 55):
+        T = kfs[k][1].copy()
+        T[:3, 3] += rng.normal(size=3) * 0.4
+        new.append((kfs[k][0] + 120.0, T))
+    return kfs, new
+
+
+def _fake_match(group_first, g0, g1, cand):
+    """a record per (new keyframe, candidate) that depends only on the pair: some groups find a loop, some do not"""
+    recs = []
+    for g in range(g0, g1):
+        for j in range(group_first[g], group_first[g + 1]):
+            r = np.zeros((), batch.RECORD_DTYPE)
+            r["T"] = np.arange(16, dtype=np.float32) + 10 * g + cand[j]
+            r["fitness"] = 0.9 if g % 4 == 1 else 0.05 + 0.01 * ((cand[j] * 31 + g) % 17)
+            r["converged"] = 1
+            r["iterations"] = 4
+            recs.append(r)
+    return np.array(recs, batch.RECORD_DTYPE) if recs else np.zeros(0, batch.RECORD_DTYPE)
+
+
+def _detect_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    kfs, new = _detect_inputs()
+    gate = pkg.LoopClosureGate()
+    gate.last_edge_accum_distance = 100.0
+    cand, _, gf = gate.plan(kfs, new)          # every rank computes the same plan from the same keyframe states
+    M, ranges = batch.layout(gf, world)
+    g0, g1 = batch.shard_range(len(new), world, rank)
+    local = _fake_match(gf, g0, g1, cand)       # stands in for the rank's share of b2r_batch_loop_detect
+    records = batch.unpack_gathered(batch.gather_records_torch(local, M, world, None), gf, world)
+    best = batch.argmin_per_group(records, gf, gate.params.fitness_score_thresh)
+    accepted = gate.replay(new, gf, best, 100.0)
+    q.put((rank, [(g, cand[gf[g] + a]) for g, a in enumerate(accepted) if a >= 0], gate.last_edge_accum_distance))
+    dist.destroy_process_group()
+
+
+def test_two_rank_detect_walk_equals_the_sequential_reference_walk():
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_loop_gate import ref_find_candidates
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_detect_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the reference's sequential walk (loop_detector.hpp:57-68) with the same fake matching
+    kfs, new = _detect_inputs()
+    p = dict(distance_thresh=5.0, accum_distance_thresh=8.0, min_edge_interval=5.0)
+    last, want = 100.0, []
+    for g, nk in enumerate(new):
+        cands = ref_find_candidates(p, kfs, nk, last)
+        if not cands:
+            continue
+        gf = [0, len(cands)]
+        rec = _fake_match([0] * g + gf, g, g + 1, cands)
+        b = batch.argmin_per_group(rec, gf, 0.5)[0]
+        if b >= 0:
+            want.append((g, cands[b]))
+            last = nk[0]
+    assert len(want) >= 3
+    for rank, loops, last_edge in outs:
+        assert loops == want and last_edge == last
