@@ -27,7 +27,7 @@
 #include "prefilter.cuh"
 #include "map_cloud.cuh"
 #include "ingest.cuh"
-#include "loop_detector.cuh"
+#include "loop_gate.cuh"
 
 #ifndef B2R_PREFETCH_KNN_BLOCKS_DEFAULT
 #define B2R_PREFETCH_KNN_BLOCKS_DEFAULT 0  // 0 = no cap on the prefetch stream's k-NN kernel

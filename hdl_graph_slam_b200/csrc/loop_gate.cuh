@@ -1,4 +1,4 @@
-// loop_detector.cuh — the host-side gating of hdl_graph_slam's LoopDetector around the batched registration (no device code).
+// loop_gate.cuh — the host-side gating of hdl_graph_slam's LoopDetector around the batched registration (no device code).
 //
 // Mirrors /root/reference/include/hdl_graph_slam/loop_detector.hpp:
 //   b2r_loop_params_default   <- constructor's rosparams                                     :39-46
